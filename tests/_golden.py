@@ -1,0 +1,83 @@
+"""Helpers shared by the golden-vector tests: rebuild the seeded inputs of a fixture and verify their checksums."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import taxo_oracle as orc
+from taxoexpan_b200 import synth
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+CASE_CFG = {
+    "pgat_wmr_lbm_small": dict(propagation_method="PGAT", readout_method="WMR", matching_method="LBM", in_dim=12,
+                               hidden_dim=8, out_dim=8, pos_dim=4, num_layers=1, heads=[4, 1]),
+    "pgat_wmr_lbm_3layer_small": dict(propagation_method="PGAT", readout_method="WMR", matching_method="BIM", in_dim=16,
+                                      hidden_dim=12, out_dim=20, pos_dim=4, num_layers=2, heads=[2, 3, 2]),
+    "gat_mr_mlp_small": dict(propagation_method="GAT", readout_method="MR", matching_method="MLP", in_dim=12,
+                             hidden_dim=8, out_dim=8, pos_dim=4, num_layers=1, heads=[4, 1]),
+    "pgcn_mr_bim_small": dict(propagation_method="PGCN", readout_method="MR", matching_method="BIM", in_dim=12,
+                              hidden_dim=8, out_dim=8, pos_dim=4, num_layers=1, heads=[4, 1]),
+    "gcn_cr_lbm_small": dict(propagation_method="GCN", readout_method="CR", matching_method="LBM", in_dim=12,
+                             hidden_dim=8, out_dim=8, pos_dim=4, num_layers=2, heads=[4, 1]),
+    "pgat_wmr_lbm_magcs": dict(propagation_method="PGAT", readout_method="WMR", matching_method="LBM", in_dim=250,
+                               hidden_dim=500, out_dim=500, pos_dim=50, num_layers=1, heads=[4, 1]),
+    "pgcn_mr_bim_wordnet": dict(propagation_method="PGCN", readout_method="MR", matching_method="BIM", in_dim=300,
+                                hidden_dim=600, out_dim=300, pos_dim=50, num_layers=1, heads=[4, 1]),
+}
+CASES = sorted(CASE_CFG)
+SUB_STEP = 97  # oracle/make_golden.py subsample()
+
+
+def checksum(t):
+    t = np.asarray(t, dtype=np.float64)
+    return np.array([t.sum(), np.abs(t).sum()])
+
+
+def sub(a):
+    return np.ascontiguousarray(np.asarray(a).reshape(-1)[::SUB_STEP])
+
+
+def load_case(name):
+    """Returns (cfg, OracleGraph, x, qf, params, fixture) with inputs regenerated from the recorded seeds."""
+    fx = np.load(os.path.join(GOLD, name + ".npz"))
+    cfg = orc.OracleConfig(**CASE_CFG[name])
+    og = orc.batch_star_egonets(fx["n_gp"], fx["n_sib"])
+    x = torch.from_numpy(synth.unit_rows(og.n, cfg.in_dim, seed=int(fx["feature_seed"][0])))
+    qf = torch.from_numpy(synth.unit_rows(og.num_graphs, cfg.in_dim, seed=int(fx["feature_seed"][1])))
+    params = orc.init_model_params(cfg, seed=int(fx["param_seed"][0]))
+    # the generators are deterministic for a given numpy/torch build; fail loudly if they ever drift
+    np.testing.assert_allclose(checksum(x), fx["x_checksum"], rtol=1e-12, err_msg="feature generator drifted")
+    np.testing.assert_allclose(checksum(qf), fx["qf_checksum"], rtol=1e-12, err_msg="query generator drifted")
+    pc = np.stack([checksum(v) for _, v in sorted(params.items())])
+    np.testing.assert_allclose(pc, fx["param_checksum"], rtol=1e-12, err_msg="parameter generator drifted")
+    return cfg, og, x, qf, params, fx
+
+
+def compare_to_fixture(fx, scores, hg, node_h, loss, grads, dh, tol, gtol):
+    """tol: max-abs tolerance on O(1) outputs; gtol: tolerance on gradients relative to the largest |grad| of a tensor."""
+    def close(a, b, t, what):
+        a = np.asarray(a, dtype=np.float64)
+        b = np.asarray(b, dtype=np.float64)
+        err = np.abs(a - b).max() if a.size else 0.0
+        assert err <= t, f"{what}: max-abs err {err:.3e} > {t:.3e}"
+
+    close(scores, fx["scores"], tol * max(1.0, float(np.abs(fx["scores"]).max())), "scores")
+    close(hg, fx["hg"], tol, "hg")
+    close(loss, fx["loss"], tol * max(1.0, float(abs(fx["loss"]))), "loss")
+    if "node_h" in fx:
+        close(node_h, fx["node_h"], tol, "node_h")
+        close(dh, fx["dh"], gtol * max(float(np.abs(fx["dh"]).max()), 1e-30), "dh")
+    else:
+        close(sub(node_h), fx["node_h_sub"], tol, "node_h")
+        close(sub(dh), fx["dh_sub"], gtol * max(float(np.abs(fx["dh_sub"]).max()), 1e-30), "dh")
+    gscale = max(float(np.abs(fx[k]).max()) for k in fx.files if k.startswith("grad.") or k.startswith("grad_sub."))
+    for k, g in grads.items():
+        if "grad." + k in fx:
+            ref = fx["grad." + k]
+            got = g
+        else:
+            ref = fx["grad_sub." + k]
+            got = sub(g)
+        scale = max(float(np.abs(ref).max()), 1e-3 * gscale)
+        close(got, ref, gtol * scale, "grad " + k)
