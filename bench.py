@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- egonets/s (fwd+bwd) of the PGAT+WMR(+LBM) hot path on MAG-CS-shaped synthetic batches.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = TaxoExpan.forward (propagate + readout + match) + InfoNCE loss + backward on one batch of
+256 queries x (1 positive + 31 negatives) = 8192 egonets per GPU (BASELINE.json configs[1]; configs[2] is the same
+per-GPU batch sharded by query group over N GPUs with one NCCL all-reduce of the flat gradient -> weak scaling).
+Prints ONE JSON line (rank 0). `value` times the step with inputs resident in HBM; `e2e` times it through the public
+API from pinned HOST buffers (H2D of features/queries/egonet counts + structure build + D2H of the loss inside the
+timed region).  `--impl reference` times the CPU port of the reference path (oracle/) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "egonets/s (fwd+bwd) PGAT d=250 on MAG-CS-shaped batches"
+UNIT = "egonets/s"
+MAGCS = dict(in_dim=250, hidden_dim=500, out_dim=500, pos_dim=50, num_layers=1, heads=[4, 1],
+             feat_drop=0.1, attn_drop=0.1, hidden_drop=0.1, out_drop=0.1)       # config_files/config.mag.json:11-20
+NEGATIVE_SIZE = 31                                                              # config.mag.json:30
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1400.0))), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithmic bytes, per GAT layer launch, W = H * D'
+# ------------------------------------------------------------------------------------------------
+def gaa_fwd_bytes(n, e, heads, width, training=True):
+    return 4 * (n * width + n * width + 2 * n * heads + (e * heads if training else 0)) + 4 * (n + 1 + e)
+
+
+def gaa_bwd_bytes(n, e, heads, width):
+    return 4 * (n * width + n * width + n * width + e * heads + 2 * n * heads) + 8 * (n + 1 + e)
+
+
+def gemm_flops_per_node(cfg):
+    k0 = cfg["in_dim"] + cfg["pos_dim"]
+    f0 = cfg["hidden_dim"] * cfg["heads"][0]
+    k1 = f0 + cfg["pos_dim"]
+    f1 = cfg["out_dim"] * cfg["heads"][1]
+    return 2 * (k0 * f0 + k1 * f1)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(n_queries, steps, warmup, seed=20200420):
+    from oracle import taxo_oracle as orc
+    from taxoexpan_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = orc.OracleConfig(propagation_method="PGAT", readout_method="WMR", matching_method="LBM",
+                           **{k: v for k, v in MAGCS.items()})
+    shapes = synth.sample_shapes(n_queries, NEGATIVE_SIZE, "mag-cs", seed=seed)
+    og = orc.batch_star_egonets(shapes.n_gp, shapes.n_sib)
+    x = torch.from_numpy(synth.unit_rows(og.n, cfg.in_dim, seed=1))
+    qf = torch.from_numpy(synth.unit_rows(og.num_graphs, cfg.in_dim, seed=2))
+    params = {k: v.clone().requires_grad_(True) for k, v in orc.init_model_params(cfg, seed=3).items()}
+
+    def step(i):
+        for p in params.values():
+            p.grad = None
+        masks = orc.random_keep_masks(cfg, og, seed=i)           # nn.Dropout's bernoulli is part of the reference step
+        scores, _, _ = orc.taxoexpan_forward(cfg, og, x, qf, params, masks=masks, training=True)
+        loss = orc.info_nce_step_loss(scores, n_queries)
+        loss.backward()
+        return float(loss.detach())
+
+    for i in range(warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(warmup + i)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    g = og.num_graphs
+    return {"value": g / dt, "ms_per_step": dt * 1e3, "cores": cores, "egonets": g, "nodes": og.n, "edges": int(og.src.numel())}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    nq = 32
+    r = cpu_reference_run(nq, args.steps, args.warmup)
+    sample = (f"{nq} queries x {1 + NEGATIVE_SIZE} = {r['egonets']} egonets ({r['nodes']} nodes) per step of the MAG-CS config, "
+              "fwd+InfoNCE+bwd, dropout 0.1 active, torch-CPU port of model_zoo.py PGAT/WMR/LBM (DGL 0.4.0 not installable offline)")
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: MAG-CS PGAT+WMR+LBM d=250 2-hop egonets (bounded CPU sample)", "egonets_per_step": r["egonets"],
+                       "nodes": r["nodes"], "edges": r["edges"]},
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import torch.distributed as dist
+    import torch.nn.functional as F
+
+    import taxoexpan_b200 as tx
+    from taxoexpan_b200 import _lib, synth
+    from taxoexpan_b200._lib import Stats
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    torch.backends.cuda.matmul.allow_tf32 = False          # parity bar is fp32 1e-5
+    _lib.load()
+    nq = args.queries
+    nb = args.batches
+
+    torch.manual_seed(0)
+    model = tx.TaxoExpan("PGAT", "WMR", "LBM", **MAGCS).to(dev)
+    if world > 1:   # identical replicas
+        for p in model.parameters():
+            dist.broadcast(p.data, 0)
+    model.train()
+    params = [p for p in model.parameters()]
+    flat = torch.zeros(sum(p.numel() for p in params), device=dev)
+    off = 0
+    for p in params:   # gradients live in one flat fp32 bucket -> ONE all-reduce per step
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+
+    # rotating seeded batches (different shapes/features per rank and per slot), host copies pinned
+    batches = []
+    for b in range(nb):
+        shapes = synth.sample_shapes(nq, NEGATIVE_SIZE, "mag-cs", seed=20200420 + 1000 * rank + b)
+        n = shapes.total_nodes
+        x = torch.from_numpy(synth.unit_rows(n, MAGCS["in_dim"], seed=11 + 1000 * rank + b)).pin_memory()
+        qf = torch.from_numpy(synth.unit_rows(shapes.num_graphs, MAGCS["in_dim"], seed=13 + 1000 * rank + b)).pin_memory()
+        g = tx.EgonetBatch.from_counts(shapes.n_gp, shapes.n_sib).pin_memory()
+        batches.append(dict(shapes=shapes, x_host=x, qf_host=qf, graph=g, x=x.to(dev), qf=qf.to(dev)))
+        g.structure(dev)
+    target = torch.zeros(nq, dtype=torch.long, device=dev)
+    torch.cuda.synchronize()
+
+    def fwd_bwd(g, x, qf):
+        flat.zero_()
+        scores = model(g, x, qf)                                              # trainer.py:51
+        loss = F.cross_entropy(scores.reshape(nq, -1), target, reduction="sum")   # trainer.py:52-56, loss.py:57
+        loss.backward()                                                       # trainer.py:60
+        if world > 1:
+            dist.all_reduce(flat)                                             # the only exchange of the path
+        return loss
+
+    def step_resident(i):
+        b = batches[i % nb]
+        g = b["graph"]
+        g.ndata["pos"] = tx.graph._LazyPos(g)        # PGAT.forward pops 'pos' (model_zoo.py:212)
+        return fwd_bwd(g, b["x"], b["qf"])
+
+    def step_e2e(i):
+        b = batches[i % nb]
+        sh = b["shapes"]
+        g = tx.EgonetBatch.from_counts(sh.n_gp, sh.n_sib)   # fresh batch object: structure is rebuilt from host counts
+        g._packed = b["graph"]._packed                       # reuse the pinned staging buffer
+        x = b["x_host"].to(dev, non_blocking=True)
+        qf = b["qf_host"].to(dev, non_blocking=True)
+        loss = fwd_bwd(g, x, qf)
+        return loss.item()                                   # D2H read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps, profile=False):
+        barrier()
+        Stats.reset()
+        Stats.profiling = profile
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step_fn(i)
+        e1.record()
+        barrier()
+        Stats.profiling = False
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), Stats.launches, Stats.timings_ms() if profile else {}
+
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    total_ms, launches, _ = timed(step_resident, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # per-kernel CUDA-event timings (separate pass so the headline loop carries no event overhead)
+    _, _, prof = timed(step_resident, args.steps, profile=True)
+    for i in range(3):
+        step_e2e(i)
+    e2e_ms, _, _ = timed(step_e2e, args.steps)
+
+    # totals over ranks
+    egonets = torch.tensor([sum(batches[i % nb]["shapes"].num_graphs for i in range(args.steps))], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(egonets)
+    total_egonets = float(egonets.item())
+    if rank != 0:
+        return
+
+    value = total_egonets / (total_ms * 1e-3)
+    e2e_value = total_egonets / (e2e_ms * 1e-3)
+    b0 = batches[0]
+    sh = b0["shapes"]
+    n_avg = float(np.mean([b["shapes"].total_nodes for b in batches]))
+    e_avg = float(np.mean([b["shapes"].total_edges for b in batches]))
+    hbm_peak, tf_peak, peak_src = load_peaks()
+    H0, H1 = MAGCS["heads"]
+    W0, W1 = MAGCS["hidden_dim"] * H0, MAGCS["out_dim"] * H1
+
+    def avg(name, tag):
+        v = prof.get((name, tag), [])
+        return float(np.mean(v)) if v else 0.0
+
+    kern = {}
+    for (name, tag), v in sorted(prof.items()):
+        kern[f"{name}[{tag}]"] = round(float(np.sum(v)) / args.steps, 4)
+    step_prof_ms = sum(kern.values())
+    rl = []
+    for tag, H, W in (("L0", H0, W0), ("L1", H1, W1)):
+        t_f = avg("tx_gat_aggregate_fwd", tag)
+        if t_f > 0:
+            by = gaa_fwd_bytes(n_avg, e_avg, H, W)
+            rl.append({"kernel": f"tx_gat_aggregate_fwd[{tag}]", "ms": t_f, "bytes": by, "achieved": by / t_f / 1e6})
+        t_b = avg("tx_gat_aggregate_bwd_dst", tag) + avg("tx_gat_aggregate_bwd_src", tag)
+        if t_b > 0:
+            by = gaa_bwd_bytes(n_avg, e_avg, H, W)
+            rl.append({"kernel": f"tx_gat_aggregate_bwd_dst+src[{tag}]", "ms": t_b, "bytes": by, "achieved": by / t_b / 1e6})
+    for r in rl:
+        r["frac"] = r["achieved"] / hbm_peak
+    dom = max(rl, key=lambda r: r["ms"]) if rl else None
+    roofline = None
+    if dom:
+        roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": round(dom["achieved"], 1), "peak": hbm_peak,
+                    "unit": "GB/s", "frac": round(dom["frac"], 4), "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": int(dom["bytes"]), "ms_per_launch": round(dom["ms"], 4)}
+    gemm_ms = sum(v for k, v in kern.items() if k.startswith("gemm"))
+    gemm_flops = 3 * gemm_flops_per_node(MAGCS) * n_avg - 2 * n_avg * MAGCS["in_dim"] * W0   # dz0 only for the 50 pos columns
+    x_bytes = int(b0["x_host"].numel() * 4 + b0["qf_host"].numel() * 4 + b0["graph"]._packed.numel() * 4)
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(32, 8, 1)
+        cpu = {"value": round(r["value"], 1), "unit": UNIT, "cores": r["cores"], "kind": "port",
+               "sample": f"32 queries x 32 = {r['egonets']} egonets ({r['nodes']} nodes) x 8 steps of the same MAG-CS config on the host "
+                         "cores: torch-CPU port of reference model_zoo.py PGAT/WMR/LBM + InfoNCE fwd+bwd, dropout 0.1 "
+                         "(real DGL 0.4.0 not installable offline)"}
+
+    line = {
+        "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: MAG-CS PGAT+WMR+LBM, d=250, 2-hop egonets, batch=256 queries x 32 = 8192 egonets per GPU"
+                               + (f" (configs[2] sharding: {world} x 256 queries, one NCCL all-reduce of {flat.numel()} fp32 grads)" if world > 1 else ""),
+                   "egonets_per_gpu_step": sh.num_graphs, "nodes_per_gpu_step": int(n_avg), "edges_per_gpu_step": int(e_avg),
+                   "dropout": 0.1, "parallelism": f"dp{world} (egonet shards by query group)",
+                   "l2": f"inputs larger than L2: per-step intermediates ~{(n_avg * (W0 * 3 + 2052 * 2 + W1 * 3) * 4) / 1e9:.2f} GB; {nb} rotating batches",
+                   "dense": "torch.mm (cuBLAS fp32, TF32 off)"},
+        "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": x_bytes, "d2h_bytes_per_step": 4,
+                "ms_per_step": round(e2e_ms / args.steps, 4)},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roofline,
+        "roofline_all": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()} for r in rl],
+        "gemm": {"ms_per_step": round(gemm_ms, 4), "tflops": round(gemm_flops / (gemm_ms * 1e-3) / 1e12, 2) if gemm_ms else None,
+                 "flops_per_step": int(gemm_flops)},
+        "kernel_ms_per_step": kern,
+        "kernel_ms_sum": round(step_prof_ms, 4),
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--queries", type=int, default=256, help="queries per GPU per step (x32 egonets)")
+    ap.add_argument("--batches", type=int, default=4, help="distinct rotating synthetic batches")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_b200(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,202 @@
+/*
+ * taxo_b200.h -- C ABI of libtaxo_sm100.so: TaxoExpan's position-enhanced graph propagation + readout
+ * hot path as hand-written CUDA for sm_100a (B200).
+ *
+ * The reference (mickeysjm/TaxoExpan) has no FFI: its boundary is Python duck typing
+ * (model/model.py:16-67,83-86).  The arithmetic of this path lives in DGL 0.4.0's message-passing kernels
+ * and torch ops called from model/model_zoo.py; every entry point below cites the reference call site
+ * (file:line under the reference root) it replaces.  taxoexpan_b200/model_zoo.py mirrors the reference's
+ * module surface on top of this ABI; INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; float = IEEE fp32; indices int32.
+ *   - caller owns every buffer (inputs, outputs, workspace); the library never allocates, frees or
+ *     synchronises; all work is enqueued on `stream` (a cudaStream_t passed as void*).
+ *   - returns 0 on success, a negative TX_ERR_* code otherwise; tx_last_error() gives the message of the
+ *     calling thread's last failure.
+ *   - row-major matrices with an explicit leading dimension `ld*` counted in floats.  Kernels use 128-bit
+ *     accesses when pointers are 16-byte aligned and ld % 4 == 0, scalar accesses otherwise.
+ *   - graphs are CSR by DESTINATION (in_ptr[N+1], in_src[E], in_eid[E]: in-edges of node i in edge-id
+ *     order) and CSR by SOURCE (out_ptr[N+1], out_dst[E], out_slot[E]: out_slot = position of that edge in
+ *     the destination-sorted order).  Per-edge arrays (alpha, elog, ...) are stored in destination-sorted
+ *     order ("slots").
+ *   - dropout: keep(seed, stream_id, index) is a counter-based Philox4x32-10 draw, reproducible in the
+ *     backward pass and by tx_dropout_keep_mask; drop(x) = keep ? x / (1 - p) : 0 (torch.nn.Dropout
+ *     semantics, reference model/model_zoo.py:57-64).  index = row * ld + col for feature matrices and
+ *     eid * H + head for attention coefficients.
+ */
+#ifndef TAXO_B200_H_
+#define TAXO_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TX_ABI_VERSION 1
+
+#define TX_OK 0
+#define TX_ERR_INVALID_ARGUMENT (-1)
+#define TX_ERR_CUDA (-2)
+#define TX_ERR_UNSUPPORTED (-3)
+
+/* activation applied by an aggregate epilogue: v > 0 ? v : slope * v.  slope = 1 means "no activation"
+ * (output layers, reference model_zoo.py:126,152,189,219); hidden layers use F.leaky_relu's default 0.01
+ * (model/model.py:25,30,35,40). */
+
+int tx_abi_version(void);
+const char* tx_last_error(void);
+/* Name of the device kernels are compiled for ("sm_100a"). */
+const char* tx_target_arch(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Graph structure (replaces DGL's graph index built by dgl.batch, data_loader/data_loaders.py:25, and the
+ * lazy CSR copies DGL makes on first kernel use).
+ * tx_build_csr: counting sort of E (src,dst) pairs by key (stable: ties keep edge-id order).
+ *   by_dst: key = dst  -> ptr = in_ptr, nbr = in_src, aux = in_eid
+ *   by_src: key = src  -> ptr = out_ptr, nbr = out_dst, aux = out_slot  (needs slot_of_eid from the by_dst pass)
+ * workspace: (N + 1) * 4 bytes, zero-filled by the call.
+ * ------------------------------------------------------------------------------------------------ */
+int tx_csr_workspace_bytes(int64_t n_nodes, int64_t n_edges, int64_t* bytes);
+int tx_build_csr_by_dst(const int32_t* src, const int32_t* dst, int64_t n_nodes, int64_t n_edges,
+                        int32_t* in_ptr, int32_t* in_src, int32_t* in_eid, int32_t* slot_of_eid,
+                        void* workspace, void* stream);
+int tx_build_csr_by_src(const int32_t* src, const int32_t* dst, const int32_t* slot_of_eid, int64_t n_nodes,
+                        int64_t n_edges, int32_t* out_ptr, int32_t* out_dst, int32_t* out_slot, void* workspace,
+                        void* stream);
+/* Closed-form structure of a batch of star egonets laid out as data_loader/dataset.py:404-437 does
+ * (nodes [gp.., anchor, sib..]; edges [gp->anchor.., anchor->sib.., self loops]) from per-egonet counts.
+ * node_off/edge_off are exclusive prefix sums [G+1] of n = n_gp+1+n_sib and e = 2n-1.  Writes pos, the
+ * edge list in edge-id order and both CSRs without any sort. Any output pointer may be NULL. */
+int tx_star_batch_structure(const int32_t* n_gp, const int32_t* n_sib, const int32_t* node_off,
+                            const int32_t* edge_off, int64_t n_graphs, int32_t* pos, int32_t* src, int32_t* dst,
+                            int32_t* in_ptr, int32_t* in_src, int32_t* in_eid, int32_t* out_ptr, int32_t* out_dst,
+                            int32_t* out_slot, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Position-embedding concat + feature dropout: z = drop([x || P[pos]])
+ * replaces nn.Embedding(3,pos_dim)(positions) + torch.cat((h,p),1) + feat_drop / GCN dropout
+ * (model/model_zoo.py:146,165-166,201,214-215,82,35-36).  pos_dim = 0 -> z = drop(x) (GAT / GCN stacks).
+ * z has ldz >= k_in + pos_dim columns; columns beyond k_in + pos_dim are zero-filled.
+ * ------------------------------------------------------------------------------------------------ */
+int tx_concat_pos_dropout_fwd(const float* x, int64_t ldx, const float* pos_table, const int32_t* pos,
+                              int64_t n_nodes, int64_t k_in, int64_t pos_dim, float* z, int64_t ldz, float p_drop,
+                              uint64_t seed, uint32_t stream_id, void* stream);
+
+/* Backward of an "activation -> [.|| P[pos]] -> dropout" epilogue, in place:
+ *   dz[i,c] *= keep(i,c)/(1-p) * (c < k_in ? act'(z[i,c]) : 1)          (act' = 1 where z > 0 else slope)
+ *   dpos_partial[b, r, :] = sum over rows i of block b with pos_i = r of dz[i, k_in : k_in+pos_dim]
+ * z is the saved forward output of the epilogue (its sign is the activation's sign); pass z = NULL or
+ * slope = 1 for "no activation" (the layer-0 concat).  dpos_partial has n_blocks = tx_row_blocks(n_nodes)
+ * blocks of 3*pos_dim floats, reduced by tx_reduce_partials. */
+int64_t tx_row_blocks(int64_t n_rows);
+int tx_epilogue_bwd(float* dz, int64_t ldz, const float* z, const int32_t* pos, int64_t n_nodes, int64_t k_in,
+                    int64_t pos_dim, int64_t vocab, float slope, float p_drop, uint64_t seed, uint32_t stream_id,
+                    float* dpos_partial, void* stream);
+/* out[m] = sum_b partial[b*m_len + m]  (fixed order: deterministic). */
+int tx_reduce_partials(const float* partial, int64_t n_blocks, int64_t m_len, float* out, void* stream);
+/* colsum_partial[b, c] = sum over rows of block b of x[i, c]  (GCN bias gradient, model_zoo.py:47). */
+int tx_colsum_partials(const float* x, int64_t ldx, int64_t n_rows, int64_t n_cols, float* partial, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GAT layer (model/model_zoo.py:80-114), everything after the dense projection ft = fc(h).
+ * ------------------------------------------------------------------------------------------------ */
+/* a1[i,h] = <ft[i,h,:], attn_l[h,:]>, a2[i,h] = <ft[i,h,:], attn_r[h,:]>           model_zoo.py:84-85 */
+int tx_gat_node_logits(const float* ft, int64_t ldf, const float* attn_l, const float* attn_r, int64_t n_nodes,
+                       int64_t heads, int64_t dim, float* a1, float* a2, void* stream);
+
+typedef struct tx_gat_epilogue {
+  /* mean_heads != 0: out[i, :dim] = mean_h agg[i,h,:]  (output layer, model_zoo.py:189,219); no activation.
+   * mean_heads == 0: out[i, h*dim + c] = drop(act(agg[i,h,c])) and, when pos_dim > 0,
+   *                  out[i, heads*dim + c] = drop(next_pos_table[pos_i, c])  -- i.e. the NEXT layer's
+   *                  input z = feat_drop(cat(leaky_relu(flatten(out)), p)) written in one pass
+   *                  (model_zoo.py:214-216 followed by :82 of the next layer). Columns up to ldo are zeroed. */
+  int32_t mean_heads;
+  float act_slope;
+  const float* next_pos_table; /* [vocab, pos_dim] or NULL */
+  const int32_t* pos;          /* [N] or NULL */
+  int64_t pos_dim;
+  float p_drop;                /* dropout on the written row (next layer's feat_drop); 0 = none */
+  uint64_t seed;
+  uint32_t stream_id;
+} tx_gat_epilogue;
+
+/* Fused edge attention + edge softmax + attention dropout + weighted aggregation (+ epilogue):
+ *   e = leaky_relu(a1[src] + a2[dst], neg_slope)                                    model_zoo.py:90,106-109
+ *   alpha = softmax over the in-edges of each destination, per head                 model_zoo.py:112
+ *   alpha_d = attn_drop(alpha)                                                      model_zoo.py:114
+ *   agg[i,h,:] = sum_e alpha_d[e,h] * ft[src_e,h,:]                                 model_zoo.py:95
+ * alpha / elog (post-leaky logits) are written per slot [E, heads] for the backward pass; alpha_d may alias
+ * alpha when p_attn == 0.  a1/a2 may be NULL: the kernel then derives the logits from the ft rows itself. */
+int tx_gat_aggregate_fwd(const float* ft, int64_t ldf, const float* attn_l, const float* attn_r, const float* a1,
+                         const float* a2, const int32_t* in_ptr, const int32_t* in_src, const int32_t* in_eid,
+                         int64_t n_nodes, int64_t n_edges, int64_t heads, int64_t dim, float neg_slope,
+                         float p_attn, uint64_t attn_seed, uint32_t attn_stream_id, float* alpha, float* alpha_d,
+                         float* elog, float* out, int64_t ldo, const tx_gat_epilogue* epi, void* stream);
+
+/* Backward, destination phase: for every destination i and head h, with g = d(agg) [N, heads*dim] (ldg):
+ *   dalpha_d[e] = <g[i,h,:], ft[src_e,h,:]>;  dalpha = dalpha_d * keep/(1-p)
+ *   de = alpha * (dalpha - sum_in(alpha * dalpha));  ds = de * (elog > 0 ? 1 : neg_slope)
+ *   writes ds[slot, h] and da2[i,h] = sum_in ds.
+ * g_scale multiplies g on load (1/heads for the output layer's mean over heads, model_zoo.py:219). */
+int tx_gat_aggregate_bwd_dst(const float* g, int64_t ldg, int64_t g_head_stride, float g_scale, const float* ft,
+                             int64_t ldf, const float* alpha, const float* elog, const int32_t* in_ptr,
+                             const int32_t* in_src, const int32_t* in_eid, int64_t n_nodes, int64_t heads,
+                             int64_t dim, float neg_slope, float p_attn, uint64_t attn_seed,
+                             uint32_t attn_stream_id, float* ds, float* da2, void* stream);
+/* Backward, source phase: dft[j,h,:] = sum_out alpha_d[slot,h] * g[dst,h,:] + da1[j,h]*attn_l[h,:] + da2[j,h]*attn_r[h,:]
+ * with da1[j,h] = sum_out ds[slot,h] (written to da1). */
+int tx_gat_aggregate_bwd_src(const float* g, int64_t ldg, int64_t g_head_stride, float g_scale,
+                             const float* alpha_d, const float* ds, const float* da2, const float* attn_l,
+                             const float* attn_r, const int32_t* out_ptr, const int32_t* out_dst,
+                             const int32_t* out_slot, int64_t n_nodes, int64_t heads, int64_t dim, float* da1,
+                             float* dft, int64_t ldd, void* stream);
+/* dattn_l[h,:] = sum_j da1[j,h] ft[j,h,:], dattn_r[h,:] = sum_j da2[j,h] ft[j,h,:] as per-block partials
+ * [n_blocks, 2, heads*dim] (n_blocks = tx_row_blocks(n_nodes)); reduce with tx_reduce_partials. */
+int tx_gat_attn_grad_partials(const float* ft, int64_t ldf, const float* da1, const float* da2, int64_t n_nodes,
+                              int64_t heads, int64_t dim, float* partial, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GCN layer (model/model_zoo.py:34-50) after y = dropout(h) @ W:
+ *   out[i,:] = act(norm_i * sum_in norm_src * y[src,:] + bias)      :39-49, copy_src/sum at :41
+ * with the same "next layer input" epilogue as the GAT kernel (heads = 1). norm = in_degree^-0.5 (inf -> 0),
+ * model_zoo.py:157-161, computed by tx_gcn_norm from in_ptr.
+ * ------------------------------------------------------------------------------------------------ */
+int tx_gcn_norm(const int32_t* in_ptr, int64_t n_nodes, float* norm, void* stream);
+int tx_gcn_aggregate_fwd(const float* y, int64_t ldy, const float* norm, const float* bias, const int32_t* in_ptr,
+                         const int32_t* in_src, int64_t n_nodes, int64_t dim, float* out, int64_t ldo,
+                         const tx_gat_epilogue* epi, void* stream);
+/* dy[j,:] = norm_j * sum_out norm_dst * g[dst,:] */
+int tx_gcn_aggregate_bwd(const float* g, int64_t ldg, const float* norm, const int32_t* out_ptr,
+                         const int32_t* out_dst, int64_t n_nodes, int64_t dim, float* dy, int64_t ldd, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Readout (model/model_zoo.py:227-258; dgl.mean_nodes / dgl.sum_nodes).
+ *   TX_READOUT_MEAN      hg[g,:] = mean_i h[i,:]                                       :231-232
+ *   TX_READOUT_WMEAN     a_i = softplus(w[pos_i]); hg = sum a_i h_i / sum a_i            :240-242
+ *   TX_READOUT_CONCAT    [sum_{pos=0} h / n_g || sum_{pos=1} h / #anchors || sum_{pos=2} h / n_g]   :248-258
+ * node_off[G+1] = exclusive prefix sum of batch_num_nodes.  hg is [G, dim] ([G, 3*dim] for CONCAT).
+ * ------------------------------------------------------------------------------------------------ */
+#define TX_READOUT_MEAN 0
+#define TX_READOUT_WMEAN 1
+#define TX_READOUT_CONCAT 2
+int tx_readout_fwd(int32_t kind, const float* h, int64_t ldh, const int32_t* pos, const float* pos_weight,
+                   const int32_t* node_off, int64_t n_graphs, int64_t dim, float* hg, int64_t ldhg, void* stream);
+/* dh[i,:] and, for WMEAN, dw_partial[g, 0..2] (reduce with tx_reduce_partials over n_graphs blocks of 3):
+ *   S = sum a; dh_i = a_i/S * dhg_g; da_i = <dhg_g, h_i - hg_g>/S; dw[pos_i] += da_i * sigmoid(w[pos_i]). */
+int tx_readout_bwd(int32_t kind, const float* dhg, int64_t lddhg, const float* h, int64_t ldh, const float* hg,
+                   int64_t ldhg, const int32_t* pos, const float* pos_weight, const int32_t* node_off,
+                   int64_t n_graphs, int64_t dim, float* dh, int64_t lddh, float* dw_partial, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Test / parity utility: materialise the keep-mask the kernels use (1 = keep) for n indices
+ * index = first_index .. first_index + n - 1, so the CPU oracle can be run with the same mask.
+ * ------------------------------------------------------------------------------------------------ */
+int tx_dropout_keep_mask(uint64_t seed, uint32_t stream_id, int64_t first_index, int64_t n, float p_drop,
+                         uint8_t* keep, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAXO_B200_H_ */

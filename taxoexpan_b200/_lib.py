@@ -1,0 +1,177 @@
+"""ctypes binding of libtaxo_sm100.so (include/taxo_b200.h).
+
+The product path has NO fallback: if the library is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_uint32, c_uint64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libtaxo_sm100.so")
+
+TX_READOUT_MEAN, TX_READOUT_WMEAN, TX_READOUT_CONCAT = 0, 1, 2
+
+
+class TaxoLibraryError(RuntimeError):
+    pass
+
+
+class GatEpilogue(Structure):
+    """struct tx_gat_epilogue"""
+    _fields_ = [
+        ("mean_heads", c_int32),
+        ("act_slope", c_float),
+        ("next_pos_table", c_void_p),
+        ("pos", c_void_p),
+        ("pos_dim", c_int64),
+        ("p_drop", c_float),
+        ("seed", c_uint64),
+        ("stream_id", c_uint32),
+    ]
+
+
+P = c_void_p
+I64 = c_int64
+F32 = c_float
+
+# name -> argtypes (all return int unless listed in _RESTYPES)
+_SIGNATURES = {
+    "tx_abi_version": [],
+    "tx_last_error": [],
+    "tx_target_arch": [],
+    "tx_row_blocks": [I64],
+    "tx_csr_workspace_bytes": [I64, I64, POINTER(c_int64)],
+    "tx_build_csr_by_dst": [P, P, I64, I64, P, P, P, P, P, P],
+    "tx_build_csr_by_src": [P, P, P, I64, I64, P, P, P, P, P],
+    "tx_star_batch_structure": [P, P, P, P, I64, P, P, P, P, P, P, P, P, P, P],
+    "tx_concat_pos_dropout_fwd": [P, I64, P, P, I64, I64, I64, P, I64, F32, c_uint64, c_uint32, P],
+    "tx_epilogue_bwd": [P, I64, P, P, I64, I64, I64, I64, F32, F32, c_uint64, c_uint32, P, P],
+    "tx_reduce_partials": [P, I64, I64, P, P],
+    "tx_colsum_partials": [P, I64, I64, I64, P, P],
+    "tx_gat_node_logits": [P, I64, P, P, I64, I64, I64, P, P, P],
+    "tx_gat_aggregate_fwd": [P, I64, P, P, P, P, P, P, P, I64, I64, I64, I64, F32, F32, c_uint64, c_uint32, P, P, P, P,
+                             I64, POINTER(GatEpilogue), P],
+    "tx_gat_aggregate_bwd_dst": [P, I64, I64, F32, P, I64, P, P, P, P, P, I64, I64, I64, F32, F32, c_uint64, c_uint32,
+                                 P, P, P],
+    "tx_gat_aggregate_bwd_src": [P, I64, I64, F32, P, P, P, P, P, P, P, P, I64, I64, I64, P, P, I64, P],
+    "tx_gat_attn_grad_partials": [P, I64, P, P, I64, I64, I64, P, P],
+    "tx_gcn_norm": [P, I64, P, P],
+    "tx_gcn_aggregate_fwd": [P, I64, P, P, P, P, I64, I64, P, I64, POINTER(GatEpilogue), P],
+    "tx_gcn_aggregate_bwd": [P, I64, P, P, P, I64, I64, P, I64, P],
+    "tx_readout_fwd": [c_int32, P, I64, P, P, P, I64, I64, P, I64, P],
+    "tx_readout_bwd": [c_int32, P, I64, P, I64, P, I64, P, P, P, I64, I64, P, I64, P, P],
+    "tx_dropout_keep_mask": [c_uint64, c_uint32, I64, I64, F32, P, P],
+}
+_RESTYPES = {"tx_last_error": c_char_p, "tx_target_arch": c_char_p, "tx_row_blocks": c_int64}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+_raw = None
+
+# names of ABI calls that do not enqueue GPU work
+_NO_LAUNCH = {"tx_abi_version", "tx_last_error", "tx_target_arch", "tx_row_blocks", "tx_csr_workspace_bytes"}
+
+
+class Stats:
+    """Launch accounting + optional CUDA-event timing of every ABI call (used by bench.py; off by default)."""
+    launches = 0          # ABI calls that enqueued kernels since the last reset
+    profiling = False
+    tag = ""
+    events = []           # (name, tag, start_event, end_event)
+
+    @classmethod
+    def reset(cls):
+        cls.launches = 0
+        cls.events = []
+
+    @classmethod
+    def timings_ms(cls):
+        """{(name, tag): [ms, ...]} after a torch.cuda.synchronize()."""
+        out = {}
+        for name, tag, e0, e1 in cls.events:
+            out.setdefault((name, tag), []).append(e0.elapsed_time(e1))
+        return out
+
+
+class timed_region:
+    """`with timed_region("mm", tag):` records CUDA events around non-ABI work (cuBLAS GEMMs) when profiling."""
+
+    def __init__(self, name, tag=None):
+        self.name, self.tag = name, tag
+
+    def __enter__(self):
+        if Stats.profiling:
+            import torch
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if Stats.profiling:
+            self.e1.record()
+            Stats.events.append((self.name, Stats.tag if self.tag is None else self.tag, self.e0, self.e1))
+        return False
+
+
+class _Namespace:
+    pass
+
+
+def _wrap(fn, name):
+    def call(*args):
+        Stats.launches += 1
+        if Stats.profiling:
+            with timed_region(name):
+                return fn(*args)
+        return fn(*args)
+    call.__name__ = name
+    return call
+
+
+def load():
+    """Loads the shared library (once). Raises TaxoLibraryError with build instructions when it is absent."""
+    global _lib, _raw
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TaxoLibraryError(
+            f"{LIB_PATH} not found: build it with `python -m taxoexpan_b200.build` (needs nvcc). "
+            "taxoexpan_b200 has no CPU or PyTorch fallback for the propagation/readout path.")
+    try:
+        lib = ctypes.CDLL(LIB_PATH)
+    except OSError as e:  # pragma: no cover
+        raise TaxoLibraryError(f"cannot load {LIB_PATH}: {e}") from e
+    ns = _Namespace()
+    for name, argtypes in _SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise TaxoLibraryError(f"{LIB_PATH} does not export {name}; rebuild with `python -m taxoexpan_b200.build --force`") from e
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, ctypes.c_int)
+        setattr(ns, name, fn if name in _NO_LAUNCH else _wrap(fn, name))
+    if lib.tx_abi_version() != 1:
+        raise TaxoLibraryError(f"ABI version mismatch: library {lib.tx_abi_version()}, binding 1")
+    _raw = lib
+    _lib = ns
+    return ns
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().tx_last_error().decode(errors="replace")
+        raise TaxoLibraryError(f"{what} failed (code {rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def current_stream():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)

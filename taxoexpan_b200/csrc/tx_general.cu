@@ -1,0 +1,890 @@
+// General-CSR kernels of the TaxoExpan propagation + readout path (sm_100a).
+//
+// One warp owns one destination (forward / destination phase of backward) or one source (source phase)
+// node, lanes stride over 128-bit column vectors of the feature row, neighbour reductions are short
+// serial loops (egonet in-degrees are 1, 2 or n_gp+1) and per-edge scalar reductions use warp shuffles.
+// These kernels are correct for ANY batched graph (the GAT/GCN classes accept arbitrary graphs,
+// reference model/model_zoo.py:116-137,169-190); the egonet-resident fast path lives in tx_egonet.cu.
+#include <math.h>
+#include <stdarg.h>
+
+#include "tx_common.cuh"
+
+namespace tx {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+struct Epilogue {  // device copy of tx_gat_epilogue
+  int mean_heads;
+  float act_slope;
+  const float* next_pos_table;
+  const int32_t* pos;
+  int pos_dim;
+  float inv_keep;   // 1/(1-p)
+  uint32_t thr;     // keep iff word >= thr
+  uint64_t seed;
+  uint32_t stream_id;
+};
+
+static int make_epilogue(const tx_gat_epilogue* e, Epilogue* d) {
+  d->mean_heads = e ? e->mean_heads : 0;
+  d->act_slope = e ? e->act_slope : 1.f;
+  d->next_pos_table = e ? e->next_pos_table : nullptr;
+  d->pos = e ? e->pos : nullptr;
+  d->pos_dim = e ? (int)e->pos_dim : 0;
+  float p = e ? e->p_drop : 0.f;
+  TX_REQUIRE(p >= 0.f && p < 1.f, "epilogue: p_drop must be in [0,1), got %f", p);
+  d->inv_keep = 1.f / (1.f - p);
+  d->thr = drop_threshold(p);
+  d->seed = e ? e->seed : 0;
+  d->stream_id = e ? e->stream_id : 0;
+  if (d->pos_dim > 0) TX_REQUIRE(d->next_pos_table && d->pos, "epilogue: pos_dim > 0 needs next_pos_table and pos");
+  return TX_OK;
+}
+
+// Writes VEC activated/dropped values of row i starting at column col of the output row.
+template <int VEC>
+__device__ __forceinline__ void epilogue_store(const Epilogue& ep, Vec<VEC> v, float* out_row, int64_t row_index_base,
+                                               int col, bool activate) {
+  if (activate) {
+#pragma unroll
+    for (int t = 0; t < VEC; ++t) v.v[t] = v.v[t] > 0.f ? v.v[t] : v.v[t] * ep.act_slope;
+  }
+  if (ep.thr) {
+    bool keep[VEC];
+    drop_keep_vec<VEC>(ep.seed, ep.stream_id, (uint64_t)(row_index_base + col), ep.thr, keep);
+#pragma unroll
+    for (int t = 0; t < VEC; ++t) v.v[t] = keep[t] ? v.v[t] * ep.inv_keep : 0.f;
+  }
+  v.store(out_row + col);
+}
+
+// Appends drop(P_next[pos_i]) after the feature columns and zero-fills up to ldo (one warp, all lanes).
+template <int VEC>
+__device__ __forceinline__ void epilogue_tail(const Epilogue& ep, float* out_row, int64_t row_index_base, int i,
+                                              int feat_cols, int ldo, int lane) {
+  const int pd = ep.pos_dim;
+  const float* prow = pd > 0 ? ep.next_pos_table + (int64_t)ep.pos[i] * pd : nullptr;
+  for (int c = feat_cols + lane; c < ldo; c += 32) {
+    float v = 0.f;
+    if (c < feat_cols + pd) {
+      v = __ldg(prow + (c - feat_cols));
+      if (ep.thr) v = drop_keep1(ep.seed, ep.stream_id, (uint64_t)(row_index_base + c), ep.thr) ? v * ep.inv_keep : 0.f;
+    }
+    out_row[c] = v;
+  }
+}
+
+// =============================================================================================
+// concat + dropout (layer-0 input):  z = drop([x || P[pos]])
+// =============================================================================================
+__global__ void concat_pos_dropout_fwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ ptab,
+                                              const int32_t* __restrict__ pos, int n, int k_in, int pd, float* __restrict__ z,
+                                              int ldz, float inv_keep, uint32_t thr, uint64_t seed, uint32_t stream_id) {
+  const int vec_per_row = ldz >> 2;
+  const int64_t total = (int64_t)n * vec_per_row;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t / vec_per_row);
+    const int c0 = (int)(t - (int64_t)i * vec_per_row) << 2;
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = c0 + u;
+      float val = 0.f;
+      if (c < k_in) val = __ldg(x + (int64_t)i * ldx + c);
+      else if (c < k_in + pd) val = __ldg(ptab + (int64_t)__ldg(pos + i) * pd + (c - k_in));
+      v[u] = val;
+    }
+    if (thr) {
+      const uint4 w = drop_words(seed, stream_id, (uint64_t)(((int64_t)i * ldz + c0) >> 2));
+      v[0] = w.x >= thr ? v[0] * inv_keep : 0.f;
+      v[1] = w.y >= thr ? v[1] * inv_keep : 0.f;
+      v[2] = w.z >= thr ? v[2] * inv_keep : 0.f;
+      v[3] = w.w >= thr ? v[3] * inv_keep : 0.f;
+    }
+    *reinterpret_cast<float4*>(z + (int64_t)i * ldz + c0) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// =============================================================================================
+// epilogue backward (in place) + position-table gradient partials
+// =============================================================================================
+__global__ void __launch_bounds__(256) epilogue_bwd_kernel(float* __restrict__ dz, int ldz, const float* __restrict__ z,
+                                                           const int32_t* __restrict__ pos, int n, int k_in, int pd,
+                                                           int vocab, float slope, float inv_keep, uint32_t thr,
+                                                           uint64_t seed, uint32_t stream_id,
+                                                           float* __restrict__ dpos_partial) {
+  const int r0 = blockIdx.x * kRowsPerBlock;
+  const int r1 = min(n, r0 + kRowsPerBlock);
+  const bool act = (z != nullptr) && (slope != 1.f);
+  // part 1: feature columns [0, k_in), vectors of 4 (ldz % 4 == 0; a vector may straddle k_in)
+  const int fvec = (k_in + 3) >> 2;
+  if (thr || act) {
+    for (int t = threadIdx.x; t < (r1 - r0) * fvec; t += blockDim.x) {
+      const int i = r0 + t / fvec;
+      const int c0 = (t % fvec) << 2;
+      float4 g = *reinterpret_cast<float4*>(dz + (int64_t)i * ldz + c0);
+      float gv[4] = {g.x, g.y, g.z, g.w};
+      float zv[4] = {1.f, 1.f, 1.f, 1.f};
+      if (act) {
+        const float4 zz = __ldg(reinterpret_cast<const float4*>(z + (int64_t)i * ldz + c0));
+        zv[0] = zz.x; zv[1] = zz.y; zv[2] = zz.z; zv[3] = zz.w;
+      }
+      uint4 w = make_uint4(~0u, ~0u, ~0u, ~0u);
+      if (thr) w = drop_words(seed, stream_id, (uint64_t)(((int64_t)i * ldz + c0) >> 2));
+      const uint32_t wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (c0 + u < k_in) {
+          float f = wv[u] >= thr ? inv_keep : 0.f;
+          if (act && !(zv[u] > 0.f)) f *= slope;
+          gv[u] *= f;
+        }
+      }
+      *reinterpret_cast<float4*>(dz + (int64_t)i * ldz + c0) = make_float4(gv[0], gv[1], gv[2], gv[3]);
+    }
+  }
+  // part 2: dP partials, one thread per position column
+  if (pd > 0 && dpos_partial) {
+    for (int c = threadIdx.x; c < pd; c += blockDim.x) {
+      float acc[kMaxVocab];
+#pragma unroll
+      for (int v = 0; v < kMaxVocab; ++v) acc[v] = 0.f;
+      for (int i = r0; i < r1; ++i) {
+        float g = dz[(int64_t)i * ldz + k_in + c];
+        if (thr) g = drop_keep1(seed, stream_id, (uint64_t)((int64_t)i * ldz + k_in + c), thr) ? g * inv_keep : 0.f;
+        const int r = __ldg(pos + i);
+#pragma unroll
+        for (int v = 0; v < kMaxVocab; ++v) acc[v] += (r == v) ? g : 0.f;
+      }
+      for (int v = 0; v < vocab; ++v) dpos_partial[((int64_t)blockIdx.x * vocab + v) * pd + c] = acc[v];
+    }
+  }
+}
+
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int64_t n_blocks, int64_t m_len,
+                                       float* __restrict__ out) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= m_len) return;
+  float acc = 0.f;
+  for (int64_t b = 0; b < n_blocks; ++b) acc += partial[b * m_len + m];
+  out[m] = acc;
+}
+
+__global__ void colsum_partials_kernel(const float* __restrict__ x, int64_t ldx, int n_rows, int n_cols,
+                                       float* __restrict__ partial) {
+  const int r0 = blockIdx.x * kRowsPerBlock;
+  const int r1 = min(n_rows, r0 + kRowsPerBlock);
+  for (int c = threadIdx.x; c < n_cols; c += blockDim.x) {
+    float acc = 0.f;
+    for (int i = r0; i < r1; ++i) acc += __ldg(x + (int64_t)i * ldx + c);
+    partial[(int64_t)blockIdx.x * n_cols + c] = acc;
+  }
+}
+
+// =============================================================================================
+// GAT
+// =============================================================================================
+template <int VEC>
+__global__ void __launch_bounds__(256) gat_node_logits_kernel(const float* __restrict__ ft, int64_t ldf,
+                                                              const float* __restrict__ attn_l,
+                                                              const float* __restrict__ attn_r, int n, int H, int D,
+                                                              float* __restrict__ a1, float* __restrict__ a2) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int nvec = D / VEC;
+  for (int64_t w = warp; w < (int64_t)n * H; w += nwarps) {
+    const int i = (int)(w / H), h = (int)(w % H);
+    const float* row = ft + (int64_t)i * ldf + (int64_t)h * D;
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < nvec; c += 32) {
+      const Vec<VEC> f = Vec<VEC>::load(row + c * VEC);
+      const Vec<VEC> l = Vec<VEC>::load(attn_l + (int64_t)h * D + c * VEC);
+      const Vec<VEC> r = Vec<VEC>::load(attn_r + (int64_t)h * D + c * VEC);
+#pragma unroll
+      for (int t = 0; t < VEC; ++t) {
+        s1 = fmaf(f.v[t], l.v[t], s1);
+        s2 = fmaf(f.v[t], r.v[t], s2);
+      }
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+      a1[w] = s1;
+      a2[w] = s2;
+    }
+  }
+}
+
+struct GatFwdParams {
+  const float* ft; int64_t ldf;
+  const float* a1; const float* a2;
+  const int32_t* in_ptr; const int32_t* in_src; const int32_t* in_eid;
+  int n; int H; int D;
+  float neg_slope; float attn_inv_keep; uint32_t attn_thr; uint64_t attn_seed; uint32_t attn_stream;
+  float* alpha; float* alpha_d; float* elog;
+  float* out; int64_t ldo;
+  Epilogue ep;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(256) gat_aggregate_fwd_kernel(const GatFwdParams p) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int H = p.H, D = p.D;
+  const int nvec = D / VEC;
+  const bool has_drop = p.attn_thr != 0;
+  for (int i = warp; i < p.n; i += nwarps) {
+    const int beg = __ldg(p.in_ptr + i), end = __ldg(p.in_ptr + i + 1);
+    // ---- stage 1: edge logits, edge softmax, attention dropout (lanes over in-edges) ----
+    for (int h = 0; h < H; ++h) {
+      const float a2i = __ldg(p.a2 + (int64_t)i * H + h);
+      float m = -INFINITY;
+      for (int k = beg + lane; k < end; k += 32) {
+        float s = __ldg(p.a1 + (int64_t)__ldg(p.in_src + k) * H + h) + a2i;
+        s = s > 0.f ? s : s * p.neg_slope;
+        p.elog[(int64_t)k * H + h] = s;
+        m = fmaxf(m, s);
+      }
+      m = warp_max(m);
+      float l = 0.f;
+      for (int k = beg + lane; k < end; k += 32) {
+        const float e = expf(p.elog[(int64_t)k * H + h] - m);
+        p.alpha[(int64_t)k * H + h] = e;
+        l += e;
+      }
+      l = warp_sum(l);
+      for (int k = beg + lane; k < end; k += 32) {
+        const float a = p.alpha[(int64_t)k * H + h] / l;
+        p.alpha[(int64_t)k * H + h] = a;
+        if (has_drop) {
+          const bool keep = drop_keep1(p.attn_seed, p.attn_stream, (uint64_t)((int64_t)__ldg(p.in_eid + k) * H + h), p.attn_thr);
+          p.alpha_d[(int64_t)k * H + h] = keep ? a * p.attn_inv_keep : 0.f;
+        }
+      }
+    }
+    __syncwarp();
+    // ---- stage 2: weighted aggregation (lanes over column vectors) + epilogue ----
+    const float* wts = has_drop ? p.alpha_d : p.alpha;
+    float* orow = p.out + (int64_t)i * p.ldo;
+    const int64_t idx_base = (int64_t)i * p.ldo;
+    if (!p.ep.mean_heads) {
+      for (int h = 0; h < H; ++h) {
+        for (int c = lane; c < nvec; c += 32) {
+          Vec<VEC> acc = vzero<VEC>();
+          const float* col = p.ft + (int64_t)h * D + c * VEC;
+          int k = beg;
+          for (; k + 4 <= end; k += 4) {
+            float w[4];
+            Vec<VEC> f[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              w[u] = wts[(int64_t)(k + u) * H + h];
+              f[u] = Vec<VEC>::load(col + (int64_t)__ldg(p.in_src + k + u) * p.ldf);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+              for (int t = 0; t < VEC; ++t) acc.v[t] = fmaf(w[u], f[u].v[t], acc.v[t]);
+          }
+          for (; k < end; ++k) {
+            const float w = wts[(int64_t)k * H + h];
+            const Vec<VEC> f = Vec<VEC>::load(col + (int64_t)__ldg(p.in_src + k) * p.ldf);
+#pragma unroll
+            for (int t = 0; t < VEC; ++t) acc.v[t] = fmaf(w, f.v[t], acc.v[t]);
+          }
+          epilogue_store<VEC>(p.ep, acc, orow, idx_base, h * D + c * VEC, p.ep.act_slope != 1.f);
+        }
+      }
+      epilogue_tail<VEC>(p.ep, orow, idx_base, i, H * D, (int)p.ldo, lane);
+    } else {
+      const float inv_h = 1.f / (float)H;
+      for (int c = lane; c < nvec; c += 32) {
+        Vec<VEC> tot = vzero<VEC>();
+        for (int h = 0; h < H; ++h) {
+          Vec<VEC> acc = vzero<VEC>();
+          const float* col = p.ft + (int64_t)h * D + c * VEC;
+          for (int k = beg; k < end; ++k) {
+            const float w = wts[(int64_t)k * H + h];
+            const Vec<VEC> f = Vec<VEC>::load(col + (int64_t)__ldg(p.in_src + k) * p.ldf);
+#pragma unroll
+            for (int t = 0; t < VEC; ++t) acc.v[t] = fmaf(w, f.v[t], acc.v[t]);
+          }
+#pragma unroll
+          for (int t = 0; t < VEC; ++t) tot.v[t] += acc.v[t];
+        }
+        if (H > 1) {
+#pragma unroll
+          for (int t = 0; t < VEC; ++t) tot.v[t] *= inv_h;
+        }
+        tot.store(orow + c * VEC);
+      }
+    }
+  }
+}
+
+struct GatBwdDstParams {
+  const float* g; int64_t ldg; int64_t g_head_stride; float g_scale;
+  const float* ft; int64_t ldf;
+  const float* alpha; const float* elog;
+  const int32_t* in_ptr; const int32_t* in_src; const int32_t* in_eid;
+  int n; int H; int D;
+  float neg_slope; float attn_inv_keep; uint32_t attn_thr; uint64_t attn_seed; uint32_t attn_stream;
+  float* ds; float* da2;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(256) gat_aggregate_bwd_dst_kernel(const GatBwdDstParams p) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int H = p.H, D = p.D;
+  const int nvec = D / VEC;
+  for (int i = warp; i < p.n; i += nwarps) {
+    const int beg = __ldg(p.in_ptr + i), end = __ldg(p.in_ptr + i + 1);
+    for (int h = 0; h < H; ++h) {
+      const float* grow = p.g + (int64_t)i * p.ldg + (int64_t)h * p.g_head_stride;
+      // d(alpha_d)[k] = <g_i, ft_src(k)>
+      for (int k = beg; k < end; ++k) {
+        const float* frow = p.ft + (int64_t)__ldg(p.in_src + k) * p.ldf + (int64_t)h * D;
+        float s = 0.f;
+        for (int c = lane; c < nvec; c += 32) {
+          const Vec<VEC> a = Vec<VEC>::load(grow + c * VEC);
+          const Vec<VEC> b = Vec<VEC>::load(frow + c * VEC);
+#pragma unroll
+          for (int t = 0; t < VEC; ++t) s = fmaf(a.v[t], b.v[t], s);
+        }
+        s = warp_sum(s);
+        if (lane == 0) p.ds[(int64_t)k * H + h] = s * p.g_scale;
+      }
+      __syncwarp();
+      // softmax backward over the in-edges, then leaky-relu backward
+      float tsum = 0.f;
+      for (int k = beg + lane; k < end; k += 32) {
+        float da = p.ds[(int64_t)k * H + h];
+        if (p.attn_thr) {
+          const bool keep = drop_keep1(p.attn_seed, p.attn_stream, (uint64_t)((int64_t)__ldg(p.in_eid + k) * H + h), p.attn_thr);
+          da = keep ? da * p.attn_inv_keep : 0.f;
+          p.ds[(int64_t)k * H + h] = da;
+        }
+        tsum = fmaf(__ldg(p.alpha + (int64_t)k * H + h), da, tsum);
+      }
+      tsum = warp_sum(tsum);
+      float a2sum = 0.f;
+      for (int k = beg + lane; k < end; k += 32) {
+        const float a = __ldg(p.alpha + (int64_t)k * H + h);
+        const float de = a * (p.ds[(int64_t)k * H + h] - tsum);
+        const float dsv = __ldg(p.elog + (int64_t)k * H + h) > 0.f ? de : de * p.neg_slope;
+        p.ds[(int64_t)k * H + h] = dsv;
+        a2sum += dsv;
+      }
+      a2sum = warp_sum(a2sum);
+      if (lane == 0) p.da2[(int64_t)i * H + h] = a2sum;
+      __syncwarp();
+    }
+  }
+}
+
+struct GatBwdSrcParams {
+  const float* g; int64_t ldg; int64_t g_head_stride; float g_scale;
+  const float* alpha_d; const float* ds; const float* da2;
+  const float* attn_l; const float* attn_r;
+  const int32_t* out_ptr; const int32_t* out_dst; const int32_t* out_slot;
+  int n; int H; int D;
+  float* da1; float* dft; int64_t ldd;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(256) gat_aggregate_bwd_src_kernel(const GatBwdSrcParams p) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int H = p.H, D = p.D;
+  const int nvec = D / VEC;
+  for (int j = warp; j < p.n; j += nwarps) {
+    const int beg = __ldg(p.out_ptr + j), end = __ldg(p.out_ptr + j + 1);
+    for (int h = 0; h < H; ++h) {
+      float d1 = 0.f;
+      for (int k = beg + lane; k < end; k += 32) d1 += __ldg(p.ds + (int64_t)__ldg(p.out_slot + k) * H + h);
+      d1 = warp_sum(d1);
+      if (lane == 0) p.da1[(int64_t)j * H + h] = d1;
+      const float d2 = __ldg(p.da2 + (int64_t)j * H + h);
+      for (int c = lane; c < nvec; c += 32) {
+        const Vec<VEC> l = Vec<VEC>::load(p.attn_l + (int64_t)h * D + c * VEC);
+        const Vec<VEC> r = Vec<VEC>::load(p.attn_r + (int64_t)h * D + c * VEC);
+        Vec<VEC> acc;
+#pragma unroll
+        for (int t = 0; t < VEC; ++t) acc.v[t] = fmaf(d1, l.v[t], d2 * r.v[t]);
+        const float* gcol = p.g + (int64_t)h * p.g_head_stride + c * VEC;
+        for (int k = beg; k < end; ++k) {
+          const float w = __ldg(p.alpha_d + (int64_t)__ldg(p.out_slot + k) * H + h) * p.g_scale;
+          const Vec<VEC> gv = Vec<VEC>::load(gcol + (int64_t)__ldg(p.out_dst + k) * p.ldg);
+#pragma unroll
+          for (int t = 0; t < VEC; ++t) acc.v[t] = fmaf(w, gv.v[t], acc.v[t]);
+        }
+        acc.store(p.dft + (int64_t)j * p.ldd + (int64_t)h * D + c * VEC);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) gat_attn_grad_partials_kernel(const float* __restrict__ ft, int64_t ldf,
+                                                                     const float* __restrict__ da1,
+                                                                     const float* __restrict__ da2, int n, int H, int D,
+                                                                     float* __restrict__ partial) {
+  const int r0 = blockIdx.x * kRowsPerBlock;
+  const int r1 = min(n, r0 + kRowsPerBlock);
+  const int F = H * D;
+  for (int c = threadIdx.x; c < F; c += blockDim.x) {
+    const int h = c / D;
+    float al = 0.f, ar = 0.f;
+    for (int j = r0; j < r1; ++j) {
+      const float f = __ldg(ft + (int64_t)j * ldf + c);
+      al = fmaf(__ldg(da1 + (int64_t)j * H + h), f, al);
+      ar = fmaf(__ldg(da2 + (int64_t)j * H + h), f, ar);
+    }
+    partial[((int64_t)blockIdx.x * 2 + 0) * F + c] = al;
+    partial[((int64_t)blockIdx.x * 2 + 1) * F + c] = ar;
+  }
+}
+
+// =============================================================================================
+// GCN
+// =============================================================================================
+__global__ void gcn_norm_kernel(const int32_t* __restrict__ in_ptr, int n, float* __restrict__ norm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int deg = in_ptr[i + 1] - in_ptr[i];
+  // torch.pow(degs, -0.5) with inf -> 0 (reference model_zoo.py:158-159)
+  norm[i] = deg > 0 ? 1.0f / sqrtf((float)deg) : 0.f;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) gcn_aggregate_fwd_kernel(const float* __restrict__ y, int64_t ldy,
+                                                                const float* __restrict__ norm,
+                                                                const float* __restrict__ bias,
+                                                                const int32_t* __restrict__ in_ptr,
+                                                                const int32_t* __restrict__ in_src, int n, int D,
+                                                                float* __restrict__ out, int64_t ldo, const Epilogue ep) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int nvec = D / VEC;
+  for (int i = warp; i < n; i += nwarps) {
+    const int beg = __ldg(in_ptr + i), end = __ldg(in_ptr + i + 1);
+    const float ni = __ldg(norm + i);
+    float* orow = out + (int64_t)i * ldo;
+    const int64_t idx_base = (int64_t)i * ldo;
+    for (int c = lane; c < nvec; c += 32) {
+      Vec<VEC> acc = vzero<VEC>();
+      for (int k = beg; k < end; ++k) {
+        const int j = __ldg(in_src + k);
+        const float nj = __ldg(norm + j);
+        const Vec<VEC> f = Vec<VEC>::load(y + (int64_t)j * ldy + c * VEC);
+        // (y_j * norm_j) summed, as the reference multiplies before update_all (model_zoo.py:39-41)
+#pragma unroll
+        for (int t = 0; t < VEC; ++t) acc.v[t] += f.v[t] * nj;
+      }
+      Vec<VEC> v;
+      if (bias) {
+        const Vec<VEC> b = Vec<VEC>::load(bias + c * VEC);
+#pragma unroll
+        for (int t = 0; t < VEC; ++t) v.v[t] = acc.v[t] * ni + b.v[t];
+      } else {
+#pragma unroll
+        for (int t = 0; t < VEC; ++t) v.v[t] = acc.v[t] * ni;
+      }
+      if (ep.mean_heads) v.store(orow + c * VEC);
+      else epilogue_store<VEC>(ep, v, orow, idx_base, c * VEC, ep.act_slope != 1.f);
+    }
+    if (!ep.mean_heads) epilogue_tail<VEC>(ep, orow, idx_base, i, D, (int)ldo, lane);
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) gcn_aggregate_bwd_kernel(const float* __restrict__ g, int64_t ldg,
+                                                                const float* __restrict__ norm,
+                                                                const int32_t* __restrict__ out_ptr,
+                                                                const int32_t* __restrict__ out_dst, int n, int D,
+                                                                float* __restrict__ dy, int64_t ldd) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int nvec = D / VEC;
+  for (int j = warp; j < n; j += nwarps) {
+    const int beg = __ldg(out_ptr + j), end = __ldg(out_ptr + j + 1);
+    const float nj = __ldg(norm + j);
+    for (int c = lane; c < nvec; c += 32) {
+      Vec<VEC> acc = vzero<VEC>();
+      for (int k = beg; k < end; ++k) {
+        const int i = __ldg(out_dst + k);
+        const float ni = __ldg(norm + i);
+        const Vec<VEC> gv = Vec<VEC>::load(g + (int64_t)i * ldg + c * VEC);
+#pragma unroll
+        for (int t = 0; t < VEC; ++t) acc.v[t] = fmaf(ni, gv.v[t], acc.v[t]);
+      }
+#pragma unroll
+      for (int t = 0; t < VEC; ++t) acc.v[t] *= nj;
+      acc.store(dy + (int64_t)j * ldd + c * VEC);
+    }
+  }
+}
+
+// =============================================================================================
+// Readout: one CTA per graph
+// =============================================================================================
+__device__ __forceinline__ float softplus_f(float x) {
+  // torch.nn.functional.softplus (beta=1, threshold=20): x if x > 20 else log1p(exp(x))
+  return x > 20.f ? x : log1pf(expf(x));
+}
+
+__device__ __forceinline__ float node_weight(int kind, const float* w, int r) {
+  return kind == TX_READOUT_WMEAN ? softplus_f(__ldg(w + r)) : 1.f;
+}
+
+__global__ void __launch_bounds__(128) readout_fwd_kernel(int kind, const float* __restrict__ h, int64_t ldh,
+                                                          const int32_t* __restrict__ pos,
+                                                          const float* __restrict__ pw,
+                                                          const int32_t* __restrict__ node_off, int D,
+                                                          float* __restrict__ hg, int64_t ldhg) {
+  const int g = blockIdx.x;
+  const int beg = __ldg(node_off + g), end = __ldg(node_off + g + 1);
+  float* orow = hg + (int64_t)g * ldhg;
+  if (kind == TX_READOUT_CONCAT) {
+    int n_anchor = 0;
+    for (int i = beg; i < end; ++i) n_anchor += (__ldg(pos + i) == 1);
+    const float inv_n = 1.f / (float)(end - beg);
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+      for (int i = beg; i < end; ++i) {
+        const float v = __ldg(h + (int64_t)i * ldh + c);
+        const int r = __ldg(pos + i);
+        s0 += r == 0 ? v : 0.f;
+        s1 += r == 1 ? v : 0.f;
+        s2 += r == 2 ? v : 0.f;
+      }
+      orow[c] = s0 * inv_n;  // sum_nodes / normalizer (model_zoo.py:252)
+      orow[D + c] = s1 / (float)n_anchor;  // mean_nodes with the 0/1 weight (model_zoo.py:254)
+      orow[2 * D + c] = s2 * inv_n;
+    }
+    return;
+  }
+  float S = 0.f;
+  for (int i = beg; i < end; ++i) S += node_weight(kind, pw, kind == TX_READOUT_WMEAN ? __ldg(pos + i) : 0);
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float acc = 0.f;
+    for (int i = beg; i < end; ++i) {
+      const float a = node_weight(kind, pw, kind == TX_READOUT_WMEAN ? __ldg(pos + i) : 0);
+      acc = fmaf(a, __ldg(h + (int64_t)i * ldh + c), acc);
+    }
+    orow[c] = acc / S;
+  }
+}
+
+__global__ void __launch_bounds__(128) readout_bwd_kernel(int kind, const float* __restrict__ dhg, int64_t lddhg,
+                                                          const float* __restrict__ h, int64_t ldh,
+                                                          const float* __restrict__ hg, int64_t ldhg,
+                                                          const int32_t* __restrict__ pos,
+                                                          const float* __restrict__ pw,
+                                                          const int32_t* __restrict__ node_off, int D,
+                                                          float* __restrict__ dh, int64_t lddh,
+                                                          float* __restrict__ dw_partial) {
+  const int g = blockIdx.x;
+  const int beg = __ldg(node_off + g), end = __ldg(node_off + g + 1);
+  const float* drow = dhg + (int64_t)g * lddhg;
+  if (kind == TX_READOUT_CONCAT) {
+    int n_anchor = 0;
+    for (int i = beg; i < end; ++i) n_anchor += (__ldg(pos + i) == 1);
+    const float inv_n = 1.f / (float)(end - beg);
+    for (int i = beg; i < end; ++i) {
+      const int r = __ldg(pos + i);
+      const float sc = r == 1 ? 1.f / (float)n_anchor : inv_n;
+      for (int c = threadIdx.x; c < D; c += blockDim.x)
+        dh[(int64_t)i * lddh + c] = (r >= 0 && r <= 2) ? __ldg(drow + r * D + c) * sc : 0.f;
+    }
+    return;
+  }
+  float S = 0.f;
+  for (int i = beg; i < end; ++i) S += node_weight(kind, pw, kind == TX_READOUT_WMEAN ? __ldg(pos + i) : 0);
+  const float inv_s = 1.f / S;
+  __shared__ float sdw[4][3];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float dw0 = 0.f, dw1 = 0.f, dw2 = 0.f;
+  // warp w owns rows beg+w, beg+w+4, ...
+  for (int i = beg + wid; i < end; i += 4) {
+    const int r = kind == TX_READOUT_WMEAN ? __ldg(pos + i) : 0;
+    const float a = node_weight(kind, pw, r);
+    const float sc = a * inv_s;
+    float dot = 0.f;
+    for (int c = lane; c < D; c += 32) {
+      const float d = __ldg(drow + c);
+      dh[(int64_t)i * lddh + c] = d * sc;
+      if (kind == TX_READOUT_WMEAN) dot = fmaf(d, __ldg(h + (int64_t)i * ldh + c) - __ldg(hg + (int64_t)g * ldhg + c), dot);
+    }
+    if (kind == TX_READOUT_WMEAN) {
+      dot = warp_sum(dot);
+      const float w = __ldg(pw + r);
+      const float sig = 1.f / (1.f + expf(-w));            // d softplus / dw
+      const float contrib = dot * inv_s * (w > 20.f ? 1.f : sig);
+      dw0 += r == 0 ? contrib : 0.f;
+      dw1 += r == 1 ? contrib : 0.f;
+      dw2 += r == 2 ? contrib : 0.f;
+    }
+  }
+  if (kind == TX_READOUT_WMEAN && dw_partial) {
+    if (lane == 0) { sdw[wid][0] = dw0; sdw[wid][1] = dw1; sdw[wid][2] = dw2; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      const int r = threadIdx.x;
+      dw_partial[(int64_t)g * 3 + r] = ((sdw[0][r] + sdw[1][r]) + sdw[2][r]) + sdw[3][r];
+    }
+  }
+}
+
+__global__ void dropout_keep_mask_kernel(uint64_t seed, uint32_t stream_id, int64_t first, int64_t n, uint32_t thr,
+                                         uint8_t* __restrict__ keep) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  keep[t] = drop_keep1(seed, stream_id, (uint64_t)(first + t), thr) ? 1 : 0;
+}
+
+}  // namespace tx
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+using namespace tx;
+
+extern "C" {
+
+int tx_abi_version(void) { return TX_ABI_VERSION; }
+const char* tx_last_error(void) { return tx::g_err; }
+const char* tx_target_arch(void) { return "sm_100a"; }
+int64_t tx_row_blocks(int64_t n_rows) { return row_blocks(n_rows); }
+
+int tx_concat_pos_dropout_fwd(const float* x, int64_t ldx, const float* pos_table, const int32_t* pos,
+                              int64_t n_nodes, int64_t k_in, int64_t pos_dim, float* z, int64_t ldz, float p_drop,
+                              uint64_t seed, uint32_t stream_id, void* stream) {
+  TX_REQUIRE(n_nodes >= 0 && k_in >= 0 && pos_dim >= 0, "concat: negative size");
+  TX_REQUIRE(ldz >= k_in + pos_dim && ldz % 4 == 0 && aligned16(z), "concat: z needs ld %% 4 == 0, ld >= k_in+pos_dim, 16B alignment");
+  TX_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "concat: p_drop must be in [0,1)");
+  TX_REQUIRE(pos_dim == 0 || (pos_table && pos), "concat: pos_dim > 0 needs pos_table and pos");
+  TX_REQUIRE(n_nodes * ldz < (int64_t)1 << 40, "concat: too large");
+  if (n_nodes == 0) return TX_OK;
+  const int64_t total = n_nodes * (ldz / 4);
+  const int grid = (int)((total + 255) / 256 < (int64_t)kNumSms * 16 ? (total + 255) / 256 : (int64_t)kNumSms * 16);
+  concat_pos_dropout_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, pos_table, pos, (int)n_nodes, (int)k_in,
+                                                                        (int)pos_dim, z, (int)ldz, 1.f / (1.f - p_drop),
+                                                                        drop_threshold(p_drop), seed, stream_id);
+  TX_LAUNCH_CHECK("tx_concat_pos_dropout_fwd");
+  return TX_OK;
+}
+
+int tx_epilogue_bwd(float* dz, int64_t ldz, const float* z, const int32_t* pos, int64_t n_nodes, int64_t k_in,
+                    int64_t pos_dim, int64_t vocab, float slope, float p_drop, uint64_t seed, uint32_t stream_id,
+                    float* dpos_partial, void* stream) {
+  TX_REQUIRE(ldz % 4 == 0 && aligned16(dz) && (!z || aligned16(z)), "epilogue_bwd: needs ld %% 4 == 0 and 16B alignment");
+  TX_REQUIRE(ldz >= k_in + pos_dim, "epilogue_bwd: ldz < k_in + pos_dim");
+  TX_REQUIRE(vocab <= kMaxVocab, "epilogue_bwd: position vocab %lld > %d", (long long)vocab, kMaxVocab);
+  TX_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "epilogue_bwd: p_drop must be in [0,1)");
+  TX_REQUIRE(pos_dim == 0 || !dpos_partial || pos, "epilogue_bwd: pos_dim > 0 needs pos");
+  if (n_nodes == 0) return TX_OK;
+  epilogue_bwd_kernel<<<(int)row_blocks(n_nodes), 256, 0, (cudaStream_t)stream>>>(
+      dz, (int)ldz, z, pos, (int)n_nodes, (int)k_in, (int)pos_dim, (int)vocab, slope, 1.f / (1.f - p_drop),
+      drop_threshold(p_drop), seed, stream_id, dpos_partial);
+  TX_LAUNCH_CHECK("tx_epilogue_bwd");
+  return TX_OK;
+}
+
+int tx_reduce_partials(const float* partial, int64_t n_blocks, int64_t m_len, float* out, void* stream) {
+  if (m_len <= 0) return TX_OK;
+  reduce_partials_kernel<<<(int)((m_len + 127) / 128), 128, 0, (cudaStream_t)stream>>>(partial, n_blocks, m_len, out);
+  TX_LAUNCH_CHECK("tx_reduce_partials");
+  return TX_OK;
+}
+
+int tx_colsum_partials(const float* x, int64_t ldx, int64_t n_rows, int64_t n_cols, float* partial, void* stream) {
+  if (n_rows == 0 || n_cols == 0) return TX_OK;
+  colsum_partials_kernel<<<(int)row_blocks(n_rows), 256, 0, (cudaStream_t)stream>>>(x, ldx, (int)n_rows, (int)n_cols, partial);
+  TX_LAUNCH_CHECK("tx_colsum_partials");
+  return TX_OK;
+}
+
+static bool vec4_ok(const void* p, int64_t ld, int64_t dim) { return aligned16(p) && ld % 4 == 0 && dim % 4 == 0; }
+
+int tx_gat_node_logits(const float* ft, int64_t ldf, const float* attn_l, const float* attn_r, int64_t n_nodes,
+                       int64_t heads, int64_t dim, float* a1, float* a2, void* stream) {
+  TX_REQUIRE(heads > 0 && dim > 0 && ldf >= heads * dim, "gat_node_logits: bad shape");
+  if (n_nodes == 0) return TX_OK;
+  const int grid = grid_for_warps(n_nodes * heads, 8, 8);
+  if (vec4_ok(ft, ldf, dim) && aligned16(attn_l) && aligned16(attn_r))
+    gat_node_logits_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(ft, ldf, attn_l, attn_r, (int)n_nodes, (int)heads, (int)dim, a1, a2);
+  else
+    gat_node_logits_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(ft, ldf, attn_l, attn_r, (int)n_nodes, (int)heads, (int)dim, a1, a2);
+  TX_LAUNCH_CHECK("tx_gat_node_logits");
+  return TX_OK;
+}
+
+int tx_gat_aggregate_fwd(const float* ft, int64_t ldf, const float* attn_l, const float* attn_r, const float* a1,
+                         const float* a2, const int32_t* in_ptr, const int32_t* in_src, const int32_t* in_eid,
+                         int64_t n_nodes, int64_t n_edges, int64_t heads, int64_t dim, float neg_slope,
+                         float p_attn, uint64_t attn_seed, uint32_t attn_stream_id, float* alpha, float* alpha_d,
+                         float* elog, float* out, int64_t ldo, const tx_gat_epilogue* epi, void* stream) {
+  (void)attn_l; (void)attn_r; (void)n_edges;
+  TX_REQUIRE(heads > 0 && dim > 0 && ldf >= heads * dim, "gat_aggregate_fwd: bad shape");
+  TX_REQUIRE(a1 && a2, "gat_aggregate_fwd: the general-CSR kernel needs a1/a2 (tx_gat_node_logits)");
+  TX_REQUIRE(p_attn >= 0.f && p_attn < 1.f, "gat_aggregate_fwd: p_attn must be in [0,1)");
+  TX_REQUIRE(alpha && elog && (p_attn == 0.f || (alpha_d && alpha_d != alpha)), "gat_aggregate_fwd: alpha/elog/alpha_d buffers");
+  GatFwdParams p;
+  if (make_epilogue(epi, &p.ep) != TX_OK) return TX_ERR_INVALID_ARGUMENT;
+  const int64_t need = p.ep.mean_heads ? dim : heads * dim + p.ep.pos_dim;
+  TX_REQUIRE(ldo >= need, "gat_aggregate_fwd: ldo %lld < %lld", (long long)ldo, (long long)need);
+  if (n_nodes == 0) return TX_OK;
+  p.ft = ft; p.ldf = ldf; p.a1 = a1; p.a2 = a2; p.in_ptr = in_ptr; p.in_src = in_src; p.in_eid = in_eid;
+  p.n = (int)n_nodes; p.H = (int)heads; p.D = (int)dim; p.neg_slope = neg_slope;
+  p.attn_inv_keep = 1.f / (1.f - p_attn); p.attn_thr = drop_threshold(p_attn); p.attn_seed = attn_seed; p.attn_stream = attn_stream_id;
+  p.alpha = alpha; p.alpha_d = alpha_d ? alpha_d : alpha; p.elog = elog; p.out = out; p.ldo = ldo;
+  const int grid = grid_for_warps(n_nodes, 8, 8);
+  if (vec4_ok(ft, ldf, dim) && vec4_ok(out, ldo, dim))
+    gat_aggregate_fwd_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  else
+    gat_aggregate_fwd_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  TX_LAUNCH_CHECK("tx_gat_aggregate_fwd");
+  return TX_OK;
+}
+
+int tx_gat_aggregate_bwd_dst(const float* g, int64_t ldg, int64_t g_head_stride, float g_scale, const float* ft,
+                             int64_t ldf, const float* alpha, const float* elog, const int32_t* in_ptr,
+                             const int32_t* in_src, const int32_t* in_eid, int64_t n_nodes, int64_t heads,
+                             int64_t dim, float neg_slope, float p_attn, uint64_t attn_seed,
+                             uint32_t attn_stream_id, float* ds, float* da2, void* stream) {
+  TX_REQUIRE(heads > 0 && dim > 0, "gat_aggregate_bwd_dst: bad shape");
+  TX_REQUIRE(p_attn >= 0.f && p_attn < 1.f, "gat_aggregate_bwd_dst: p_attn must be in [0,1)");
+  if (n_nodes == 0) return TX_OK;
+  GatBwdDstParams p;
+  p.g = g; p.ldg = ldg; p.g_head_stride = g_head_stride; p.g_scale = g_scale; p.ft = ft; p.ldf = ldf;
+  p.alpha = alpha; p.elog = elog; p.in_ptr = in_ptr; p.in_src = in_src; p.in_eid = in_eid;
+  p.n = (int)n_nodes; p.H = (int)heads; p.D = (int)dim; p.neg_slope = neg_slope;
+  p.attn_inv_keep = 1.f / (1.f - p_attn); p.attn_thr = drop_threshold(p_attn); p.attn_seed = attn_seed; p.attn_stream = attn_stream_id;
+  p.ds = ds; p.da2 = da2;
+  const int grid = grid_for_warps(n_nodes, 8, 8);
+  if (vec4_ok(g, ldg, dim) && vec4_ok(ft, ldf, dim) && g_head_stride % 4 == 0)
+    gat_aggregate_bwd_dst_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  else
+    gat_aggregate_bwd_dst_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  TX_LAUNCH_CHECK("tx_gat_aggregate_bwd_dst");
+  return TX_OK;
+}
+
+int tx_gat_aggregate_bwd_src(const float* g, int64_t ldg, int64_t g_head_stride, float g_scale,
+                             const float* alpha_d, const float* ds, const float* da2, const float* attn_l,
+                             const float* attn_r, const int32_t* out_ptr, const int32_t* out_dst,
+                             const int32_t* out_slot, int64_t n_nodes, int64_t heads, int64_t dim, float* da1,
+                             float* dft, int64_t ldd, void* stream) {
+  TX_REQUIRE(heads > 0 && dim > 0 && ldd >= heads * dim, "gat_aggregate_bwd_src: bad shape");
+  if (n_nodes == 0) return TX_OK;
+  GatBwdSrcParams p;
+  p.g = g; p.ldg = ldg; p.g_head_stride = g_head_stride; p.g_scale = g_scale; p.alpha_d = alpha_d; p.ds = ds; p.da2 = da2;
+  p.attn_l = attn_l; p.attn_r = attn_r; p.out_ptr = out_ptr; p.out_dst = out_dst; p.out_slot = out_slot;
+  p.n = (int)n_nodes; p.H = (int)heads; p.D = (int)dim; p.da1 = da1; p.dft = dft; p.ldd = ldd;
+  const int grid = grid_for_warps(n_nodes, 8, 8);
+  if (vec4_ok(g, ldg, dim) && vec4_ok(dft, ldd, dim) && g_head_stride % 4 == 0 && aligned16(attn_l) && aligned16(attn_r))
+    gat_aggregate_bwd_src_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  else
+    gat_aggregate_bwd_src_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  TX_LAUNCH_CHECK("tx_gat_aggregate_bwd_src");
+  return TX_OK;
+}
+
+int tx_gat_attn_grad_partials(const float* ft, int64_t ldf, const float* da1, const float* da2, int64_t n_nodes,
+                              int64_t heads, int64_t dim, float* partial, void* stream) {
+  TX_REQUIRE(heads > 0 && dim > 0, "gat_attn_grad_partials: bad shape");
+  if (n_nodes == 0) return TX_OK;
+  gat_attn_grad_partials_kernel<<<(int)row_blocks(n_nodes), 256, 0, (cudaStream_t)stream>>>(ft, ldf, da1, da2, (int)n_nodes,
+                                                                                            (int)heads, (int)dim, partial);
+  TX_LAUNCH_CHECK("tx_gat_attn_grad_partials");
+  return TX_OK;
+}
+
+int tx_gcn_norm(const int32_t* in_ptr, int64_t n_nodes, float* norm, void* stream) {
+  if (n_nodes == 0) return TX_OK;
+  gcn_norm_kernel<<<(int)((n_nodes + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in_ptr, (int)n_nodes, norm);
+  TX_LAUNCH_CHECK("tx_gcn_norm");
+  return TX_OK;
+}
+
+int tx_gcn_aggregate_fwd(const float* y, int64_t ldy, const float* norm, const float* bias, const int32_t* in_ptr,
+                         const int32_t* in_src, int64_t n_nodes, int64_t dim, float* out, int64_t ldo,
+                         const tx_gat_epilogue* epi, void* stream) {
+  TX_REQUIRE(dim > 0 && ldy >= dim, "gcn_aggregate_fwd: bad shape");
+  Epilogue ep;
+  if (make_epilogue(epi, &ep) != TX_OK) return TX_ERR_INVALID_ARGUMENT;
+  const int64_t need = ep.mean_heads ? dim : dim + ep.pos_dim;
+  TX_REQUIRE(ldo >= need, "gcn_aggregate_fwd: ldo %lld < %lld", (long long)ldo, (long long)need);
+  if (n_nodes == 0) return TX_OK;
+  const int grid = grid_for_warps(n_nodes, 8, 8);
+  if (vec4_ok(y, ldy, dim) && vec4_ok(out, ldo, dim) && (!bias || aligned16(bias)))
+    gcn_aggregate_fwd_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(y, ldy, norm, bias, in_ptr, in_src, (int)n_nodes, (int)dim, out, ldo, ep);
+  else
+    gcn_aggregate_fwd_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(y, ldy, norm, bias, in_ptr, in_src, (int)n_nodes, (int)dim, out, ldo, ep);
+  TX_LAUNCH_CHECK("tx_gcn_aggregate_fwd");
+  return TX_OK;
+}
+
+int tx_gcn_aggregate_bwd(const float* g, int64_t ldg, const float* norm, const int32_t* out_ptr,
+                         const int32_t* out_dst, int64_t n_nodes, int64_t dim, float* dy, int64_t ldd, void* stream) {
+  TX_REQUIRE(dim > 0 && ldg >= dim && ldd >= dim, "gcn_aggregate_bwd: bad shape");
+  if (n_nodes == 0) return TX_OK;
+  const int grid = grid_for_warps(n_nodes, 8, 8);
+  if (vec4_ok(g, ldg, dim) && vec4_ok(dy, ldd, dim))
+    gcn_aggregate_bwd_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(g, ldg, norm, out_ptr, out_dst, (int)n_nodes, (int)dim, dy, ldd);
+  else
+    gcn_aggregate_bwd_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(g, ldg, norm, out_ptr, out_dst, (int)n_nodes, (int)dim, dy, ldd);
+  TX_LAUNCH_CHECK("tx_gcn_aggregate_bwd");
+  return TX_OK;
+}
+
+int tx_readout_fwd(int32_t kind, const float* h, int64_t ldh, const int32_t* pos, const float* pos_weight,
+                   const int32_t* node_off, int64_t n_graphs, int64_t dim, float* hg, int64_t ldhg, void* stream) {
+  TX_REQUIRE(kind >= 0 && kind <= 2, "readout_fwd: unknown kind %d", kind);
+  TX_REQUIRE(kind == TX_READOUT_MEAN || pos, "readout_fwd: pos required");
+  TX_REQUIRE(kind != TX_READOUT_WMEAN || pos_weight, "readout_fwd: pos_weight required for WMEAN");
+  TX_REQUIRE(ldhg >= (kind == TX_READOUT_CONCAT ? 3 * dim : dim), "readout_fwd: ldhg too small");
+  if (n_graphs == 0) return TX_OK;
+  readout_fwd_kernel<<<(int)n_graphs, 128, 0, (cudaStream_t)stream>>>(kind, h, ldh, pos, pos_weight, node_off, (int)dim, hg, ldhg);
+  TX_LAUNCH_CHECK("tx_readout_fwd");
+  return TX_OK;
+}
+
+int tx_readout_bwd(int32_t kind, const float* dhg, int64_t lddhg, const float* h, int64_t ldh, const float* hg,
+                   int64_t ldhg, const int32_t* pos, const float* pos_weight, const int32_t* node_off,
+                   int64_t n_graphs, int64_t dim, float* dh, int64_t lddh, float* dw_partial, void* stream) {
+  TX_REQUIRE(kind >= 0 && kind <= 2, "readout_bwd: unknown kind %d", kind);
+  TX_REQUIRE(kind == TX_READOUT_MEAN || pos, "readout_bwd: pos required");
+  TX_REQUIRE(kind != TX_READOUT_WMEAN || (pos_weight && h && hg), "readout_bwd: WMEAN needs pos_weight, h, hg");
+  if (n_graphs == 0) return TX_OK;
+  readout_bwd_kernel<<<(int)n_graphs, 128, 0, (cudaStream_t)stream>>>(kind, dhg, lddhg, h, ldh, hg, ldhg, pos, pos_weight,
+                                                                     node_off, (int)dim, dh, lddh, dw_partial);
+  TX_LAUNCH_CHECK("tx_readout_bwd");
+  return TX_OK;
+}
+
+int tx_dropout_keep_mask(uint64_t seed, uint32_t stream_id, int64_t first_index, int64_t n, float p_drop,
+                         uint8_t* keep, void* stream) {
+  TX_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "dropout_keep_mask: p_drop must be in [0,1)");
+  if (n <= 0) return TX_OK;
+  dropout_keep_mask_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(seed, stream_id, first_index, n,
+                                                                                    drop_threshold(p_drop), keep);
+  TX_LAUNCH_CHECK("tx_dropout_keep_mask");
+  return TX_OK;
+}
+
+}  // extern "C"

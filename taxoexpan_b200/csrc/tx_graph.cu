@@ -1,0 +1,226 @@
+// Graph-structure kernels: CSR construction for arbitrary edge lists and the closed-form structure of a
+// batch of star egonets (reference data_loader/dataset.py:404-437 + dgl.batch, data_loaders.py:25).
+// Integer work only; results are bit-exact against oracle/taxo_oracle.py::csr_by_dst.
+#include "tx_common.cuh"
+
+namespace tx {
+
+__global__ void histogram_kernel(const int32_t* __restrict__ key, int64_t n_edges, int32_t* __restrict__ count_plus1) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd(count_plus1 + key[e] + 1, 1);
+}
+
+// Single-CTA exclusive scan of counts stored at ptr[1..n] (ptr[0] = 0) -> ptr becomes the CSR row pointer.
+// 1024 threads, each owning a contiguous chunk; not on the per-step path for egonet batches.
+__global__ void __launch_bounds__(1024) scan_kernel(int32_t* __restrict__ ptr, int64_t n) {
+  __shared__ int32_t sums[1024];
+  const int t = threadIdx.x;
+  const int64_t chunk = (n + 1023) / 1024;
+  const int64_t b = 1 + (int64_t)t * chunk, e = min(n + 1, b + chunk);
+  int32_t s = 0;
+  for (int64_t i = b; i < e; ++i) s += ptr[i];
+  sums[t] = s;
+  __syncthreads();
+  // inclusive scan of the 1024 chunk sums (Hillis-Steele)
+  for (int off = 1; off < 1024; off <<= 1) {
+    int32_t v = t >= off ? sums[t - off] : 0;
+    __syncthreads();
+    sums[t] += v;
+    __syncthreads();
+  }
+  int32_t run = t > 0 ? sums[t - 1] : 0;
+  for (int64_t i = b; i < e; ++i) {
+    run += ptr[i];
+    ptr[i] = run;
+  }
+  if (t == 0) ptr[0] = 0;
+}
+
+// Scatter edges into their rows with an atomic cursor (arbitrary order inside a row) ...
+__global__ void fill_kernel(const int32_t* __restrict__ key, int64_t n_edges, const int32_t* __restrict__ ptr,
+                            int32_t* __restrict__ cursor, int32_t* __restrict__ eid_out) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (int64_t)gridDim.x * blockDim.x) {
+    const int k = key[e];
+    const int slot = ptr[k] + atomicAdd(cursor + k, 1);
+    eid_out[slot] = (int32_t)e;
+  }
+}
+
+// ... then restore edge-id order inside every row (stable counting sort overall). One thread per row;
+// rows of egonet batches have <= expand_factor + 2 entries.
+__global__ void sort_rows_kernel(const int32_t* __restrict__ ptr, int64_t n_nodes, int32_t* __restrict__ eid) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_nodes) return;
+  const int b = ptr[i], e = ptr[i + 1];
+  for (int a = b + 1; a < e; ++a) {  // insertion sort
+    const int32_t v = eid[a];
+    int c = a - 1;
+    while (c >= b && eid[c] > v) {
+      eid[c + 1] = eid[c];
+      --c;
+    }
+    eid[c + 1] = v;
+  }
+}
+
+__global__ void gather_by_dst_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ in_eid, int64_t n_edges,
+                                     int32_t* __restrict__ in_src, int32_t* __restrict__ slot_of_eid) {
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_edges; s += (int64_t)gridDim.x * blockDim.x) {
+    const int e = in_eid[s];
+    in_src[s] = src[e];
+    if (slot_of_eid) slot_of_eid[e] = (int32_t)s;
+  }
+}
+
+__global__ void gather_by_src_kernel(const int32_t* __restrict__ dst, const int32_t* __restrict__ slot_of_eid,
+                                     const int32_t* __restrict__ out_eid, int64_t n_edges, int32_t* __restrict__ out_dst,
+                                     int32_t* __restrict__ out_slot) {
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_edges; s += (int64_t)gridDim.x * blockDim.x) {
+    const int e = out_eid[s];
+    out_dst[s] = dst[e];
+    out_slot[s] = slot_of_eid[e];
+  }
+}
+
+// One warp per egonet; lanes over its nodes. See the slot algebra in DESIGN.md ("closed-form egonet CSR").
+__global__ void __launch_bounds__(256) star_batch_structure_kernel(
+    const int32_t* __restrict__ n_gp, const int32_t* __restrict__ n_sib, const int32_t* __restrict__ node_off,
+    const int32_t* __restrict__ edge_off, int n_graphs, int32_t* __restrict__ pos, int32_t* __restrict__ src,
+    int32_t* __restrict__ dst, int32_t* __restrict__ in_ptr, int32_t* __restrict__ in_src, int32_t* __restrict__ in_eid,
+    int32_t* __restrict__ out_ptr, int32_t* __restrict__ out_dst, int32_t* __restrict__ out_slot) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int g = warp; g < n_graphs; g += nwarps) {
+    const int a = n_gp[g], s = n_sib[g], o = node_off[g], q = edge_off[g];
+    const int n = a + 1 + s;
+    const int self0 = q + a + s;  // edge id of the first self loop
+    for (int t = lane; t < n; t += 32) {
+      const int node = o + t;
+      if (t < a) {  // grand-parent t: in = {self}; out = {-> anchor, self}
+        if (pos) pos[node] = 0;
+        if (src) { src[q + t] = node; dst[q + t] = o + a; }
+        if (in_ptr) { in_ptr[node] = q + t; in_src[q + t] = node; in_eid[q + t] = self0 + t; }
+        if (out_ptr) {
+          out_ptr[node] = q + 2 * t;
+          out_dst[q + 2 * t] = o + a;      out_slot[q + 2 * t] = q + a + t;
+          out_dst[q + 2 * t + 1] = node;   out_slot[q + 2 * t + 1] = q + t;
+        }
+      } else if (t == a) {  // anchor: in = {gp_0..gp_{a-1}, self}; out = {-> sib_0.., self}
+        if (pos) pos[node] = 1;
+        if (in_ptr) {
+          in_ptr[node] = q + a;
+          for (int k = 0; k < a; ++k) { in_src[q + a + k] = o + k; in_eid[q + a + k] = q + k; }
+          in_src[q + 2 * a] = node; in_eid[q + 2 * a] = self0 + a;
+        }
+        if (out_ptr) {
+          out_ptr[node] = q + 2 * a;
+          out_dst[q + 2 * a + s] = node; out_slot[q + 2 * a + s] = q + 2 * a;
+        }
+      } else {  // sibling k: in = {anchor, self}; out = {self}
+        const int k = t - a - 1;
+        if (pos) pos[node] = 2;
+        if (src) { src[q + a + k] = o + a; dst[q + a + k] = node; }
+        const int slot = q + 2 * a + 1 + 2 * k;
+        if (in_ptr) {
+          in_ptr[node] = slot;
+          in_src[slot] = o + a;      in_eid[slot] = q + a + k;
+          in_src[slot + 1] = node;   in_eid[slot + 1] = self0 + t;
+        }
+        if (out_ptr) {
+          out_dst[q + 2 * a + k] = node; out_slot[q + 2 * a + k] = slot;          // anchor -> sib_k
+          out_ptr[node] = q + 2 * a + s + 1 + k;
+          out_dst[q + 2 * a + s + 1 + k] = node; out_slot[q + 2 * a + s + 1 + k] = slot + 1;
+        }
+      }
+      if (src) { src[self0 + t] = node; dst[self0 + t] = node; }
+    }
+    if (g == n_graphs - 1 && lane == 0) {
+      const int E = q + 2 * n - 1;
+      if (in_ptr) in_ptr[o + n] = E;
+      if (out_ptr) out_ptr[o + n] = E;
+    }
+  }
+}
+
+}  // namespace tx
+
+using namespace tx;
+
+extern "C" {
+
+int tx_csr_workspace_bytes(int64_t n_nodes, int64_t n_edges, int64_t* bytes) {
+  TX_REQUIRE(bytes, "csr_workspace_bytes: null output");
+  *bytes = (n_nodes + 1) * 4 + n_edges * 4;  // row cursor + edge-id scratch for the by-src pass
+  return TX_OK;
+}
+
+static int build_rows(const int32_t* key, int64_t n_nodes, int64_t n_edges, int32_t* ptr, int32_t* eid_sorted,
+                      int32_t* cursor, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(ptr, 0, (n_nodes + 1) * sizeof(int32_t), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(cursor, 0, (n_nodes + 1) * sizeof(int32_t), st);
+  if (e != cudaSuccess) {
+    set_error("build_csr: memset failed: %s", cudaGetErrorString(e));
+    return TX_ERR_CUDA;
+  }
+  if (n_edges > 0) {
+    const int grid = (int)((n_edges + 255) / 256 < (int64_t)kNumSms * 8 ? (n_edges + 255) / 256 : (int64_t)kNumSms * 8);
+    histogram_kernel<<<grid, 256, 0, st>>>(key, n_edges, ptr);
+    scan_kernel<<<1, 1024, 0, st>>>(ptr, n_nodes);
+    fill_kernel<<<grid, 256, 0, st>>>(key, n_edges, ptr, cursor, eid_sorted);
+    sort_rows_kernel<<<(int)((n_nodes + 127) / 128), 128, 0, st>>>(ptr, n_nodes, eid_sorted);
+  }
+  TX_LAUNCH_CHECK("tx_build_csr");
+  return TX_OK;
+}
+
+int tx_build_csr_by_dst(const int32_t* src, const int32_t* dst, int64_t n_nodes, int64_t n_edges, int32_t* in_ptr,
+                        int32_t* in_src, int32_t* in_eid, int32_t* slot_of_eid, void* workspace, void* stream) {
+  TX_REQUIRE(n_nodes >= 0 && n_edges >= 0 && n_nodes < INT32_MAX && n_edges < INT32_MAX, "build_csr: sizes must fit int32");
+  TX_REQUIRE(workspace && in_ptr, "build_csr: null buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = build_rows(dst, n_nodes, n_edges, in_ptr, in_eid, (int32_t*)workspace, st);
+  if (rc != TX_OK) return rc;
+  if (n_edges > 0) {
+    const int grid = (int)((n_edges + 255) / 256 < (int64_t)kNumSms * 8 ? (n_edges + 255) / 256 : (int64_t)kNumSms * 8);
+    gather_by_dst_kernel<<<grid, 256, 0, st>>>(src, in_eid, n_edges, in_src, slot_of_eid);
+    TX_LAUNCH_CHECK("tx_build_csr_by_dst");
+  }
+  return TX_OK;
+}
+
+int tx_build_csr_by_src(const int32_t* src, const int32_t* dst, const int32_t* slot_of_eid, int64_t n_nodes,
+                        int64_t n_edges, int32_t* out_ptr, int32_t* out_dst, int32_t* out_slot, void* workspace,
+                        void* stream) {
+  TX_REQUIRE(n_nodes >= 0 && n_edges >= 0 && n_nodes < INT32_MAX && n_edges < INT32_MAX, "build_csr: sizes must fit int32");
+  TX_REQUIRE(workspace && out_ptr && slot_of_eid, "build_csr: null buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  int32_t* cursor = (int32_t*)workspace;
+  int32_t* out_eid = cursor + (n_nodes + 1);
+  int rc = build_rows(src, n_nodes, n_edges, out_ptr, out_eid, cursor, st);
+  if (rc != TX_OK) return rc;
+  if (n_edges > 0) {
+    const int grid = (int)((n_edges + 255) / 256 < (int64_t)kNumSms * 8 ? (n_edges + 255) / 256 : (int64_t)kNumSms * 8);
+    gather_by_src_kernel<<<grid, 256, 0, st>>>(dst, slot_of_eid, out_eid, n_edges, out_dst, out_slot);
+    TX_LAUNCH_CHECK("tx_build_csr_by_src");
+  }
+  return TX_OK;
+}
+
+int tx_star_batch_structure(const int32_t* n_gp, const int32_t* n_sib, const int32_t* node_off,
+                            const int32_t* edge_off, int64_t n_graphs, int32_t* pos, int32_t* src, int32_t* dst,
+                            int32_t* in_ptr, int32_t* in_src, int32_t* in_eid, int32_t* out_ptr, int32_t* out_dst,
+                            int32_t* out_slot, void* stream) {
+  TX_REQUIRE(n_graphs >= 0 && n_graphs < INT32_MAX, "star_batch_structure: bad graph count");
+  TX_REQUIRE((src == nullptr) == (dst == nullptr), "star_batch_structure: src and dst go together");
+  TX_REQUIRE(!in_ptr || (in_src && in_eid), "star_batch_structure: in_ptr needs in_src and in_eid");
+  TX_REQUIRE(!out_ptr || (out_dst && out_slot), "star_batch_structure: out_ptr needs out_dst and out_slot");
+  if (n_graphs == 0) return TX_OK;
+  const int grid = grid_for_warps(n_graphs, 8, 8);
+  star_batch_structure_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n_gp, n_sib, node_off, edge_off, (int)n_graphs, pos, src,
+                                                                     dst, in_ptr, in_src, in_eid, out_ptr, out_dst, out_slot);
+  TX_LAUNCH_CHECK("tx_star_batch_structure");
+  return TX_OK;
+}
+
+}  // extern "C"

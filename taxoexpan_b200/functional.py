@@ -1,0 +1,387 @@
+"""torch.autograd Functions over the C ABI (include/taxo_b200.h): the only way compute reaches the GPU here.
+
+Every Function below allocates its outputs/workspace with torch (device memory + stream plumbing) and calls the
+hand-written CUDA kernels through ctypes; dense projections are torch.mm (cuBLAS fp32, TF32 off) unless the
+tcgen05 GEMM of tx_gemm.cu is enabled.  There is no eager/CPU fallback: a CPU tensor raises.
+
+Feature matrices travel between layers as PADDED row-major buffers [N, ld] with ld % 4 == 0 (16-byte aligned rows
+for 128-bit accesses / TMA); the logical width K <= ld is tracked by the caller, padding columns are zero.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from ._lib import GatEpilogue, Stats, check, current_stream, ptr, timed_region
+from .graph import GraphStructure
+
+_NEG_SLOPE_NONE = 1.0
+
+
+def round4(k: int) -> int:
+    return (int(k) + 3) // 4 * 4
+
+
+def _check_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise _lib.TaxoLibraryError(f"{name} must be a CUDA tensor: taxoexpan_b200 has no CPU path (got device {t.device})")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32 (the reference path is fp32 end to end), got {t.dtype}")
+
+
+def _rowmajor(t: torch.Tensor) -> torch.Tensor:
+    """2-D view with unit column stride (copy only if needed)."""
+    if t.dim() != 2:
+        raise ValueError("expected a 2-D tensor")
+    if t.stride(1) != 1 or (t.shape[0] > 1 and t.stride(0) < t.shape[1]):
+        t = t.contiguous()
+    return t
+
+
+def new_seed() -> int:
+    """A fresh 62-bit dropout seed from torch's CPU generator (so torch.manual_seed makes runs repeatable)."""
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
+def _reduce_partials(lib, partial: torch.Tensor, n_blocks: int, m_len: int) -> torch.Tensor:
+    out = torch.empty(m_len, dtype=torch.float32, device=partial.device)
+    check(lib.tx_reduce_partials(ptr(partial), n_blocks, m_len, ptr(out), current_stream()), "tx_reduce_partials")
+    return out
+
+
+def dropout_keep_mask(seed: int, stream_id: int, first_index: int, n: int, p: float, device) -> torch.Tensor:
+    """The exact keep-mask (uint8, 1 = keep) the kernels use; lets the CPU oracle replay a dropout run."""
+    lib = _lib.load()
+    keep = torch.empty(n, dtype=torch.uint8, device=device)
+    with torch.cuda.device(keep.device):
+        check(lib.tx_dropout_keep_mask(seed, stream_id, first_index, n, p, ptr(keep), current_stream()), "tx_dropout_keep_mask")
+    return keep
+
+
+# --------------------------------------------------------------------------------------------------
+# z = drop([x || P[pos]])
+# --------------------------------------------------------------------------------------------------
+class ConcatPosDropout(Function):
+    @staticmethod
+    def forward(ctx, x, pos_table, pos32, p, seed, stream_id):
+        lib = _lib.load()
+        _check_cuda(x, "features")
+        x = _rowmajor(x)
+        n, k_in = x.shape
+        pd = 0 if pos_table is None else int(pos_table.shape[1])
+        vocab = 0 if pos_table is None else int(pos_table.shape[0])
+        ldz = round4(k_in + pd)
+        z = torch.empty((n, ldz), dtype=torch.float32, device=x.device)
+        tab = None if pos_table is None else pos_table.contiguous()
+        with torch.cuda.device(x.device):
+            check(lib.tx_concat_pos_dropout_fwd(ptr(x), x.stride(0) if n > 1 else k_in, ptr(tab), ptr(pos32), n, k_in, pd,
+                                                ptr(z), ldz, p, seed, stream_id, current_stream()),
+                  "tx_concat_pos_dropout_fwd")
+        ctx.save_for_backward(pos32 if pos32 is not None else torch.empty(0))
+        ctx.meta = (n, k_in, pd, vocab, ldz, float(p), int(seed), int(stream_id))
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        lib = _lib.load()
+        (pos32,) = ctx.saved_tensors
+        n, k_in, pd, vocab, ldz, p, seed, stream_id = ctx.meta
+        need_x, need_tab = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and pd > 0
+        dx = dtab = None
+        if not (need_x or need_tab):
+            return None, None, None, None, None, None
+        dz = _rowmajor(dz)
+        if p > 0.0:
+            dz = dz.clone()      # the kernel rescales the kept entries in place; never touch the caller's grad
+        with torch.cuda.device(dz.device):
+            nb = int(lib.tx_row_blocks(n))
+            partial = torch.empty(nb * vocab * pd, dtype=torch.float32, device=dz.device) if need_tab else None
+            # with p == 0 and no activation the kernel's feature pass is a no-op (dz is only read)
+            check(lib.tx_epilogue_bwd(ptr(dz), dz.stride(0) if n > 1 else ldz, None, ptr(pos32) if pd > 0 else None, n, k_in,
+                                      pd if need_tab else 0, vocab, 1.0, p, seed, stream_id, ptr(partial), current_stream()),
+                  "tx_epilogue_bwd")
+            if need_tab:
+                dtab = _reduce_partials(lib, partial, nb, vocab * pd).view(vocab, pd)
+        if need_x:
+            dx = dz[:, :k_in].contiguous()
+        return dx, dtab, None, None, None, None
+
+
+# --------------------------------------------------------------------------------------------------
+# GAT layer: ft = z W^T ; fused attention/softmax/aggregate ; epilogue = next layer's input or head mean
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class GatLayerCfg:
+    k: int                      # logical input width (z[:, :k])
+    heads: int
+    dim: int                    # per-head width D'
+    neg_slope: float = 0.2      # leaky-relu slope inside attention (model_zoo.py:70)
+    p_attn: float = 0.0
+    attn_seed: int = 0
+    attn_stream: int = 1
+    hidden: bool = True         # True: emit next layer's input; False: output layer (mean over heads)
+    act_slope: float = 1.0      # activation after a hidden layer (0.01 = F.leaky_relu default); 1 = none
+    p_next: float = 0.0         # next layer's feat_drop, applied by this layer's epilogue
+    next_seed: int = 0
+    next_stream: int = 0
+    dz_from: int = 0            # columns [0, dz_from) of d(z) are not needed by the caller (layer 0, x without grad)
+    tag: str = ""               # label for bench.py's per-kernel CUDA-event timings
+
+
+class GatLayer(Function):
+    @staticmethod
+    def forward(ctx, z, weight, attn_l, attn_r, next_pos_table, st: GraphStructure, pos32, cfg: GatLayerCfg):
+        lib = _lib.load()
+        _check_cuda(z, "z")
+        n, ldz = z.shape
+        H, D, K = cfg.heads, cfg.dim, cfg.k
+        F_ = H * D
+        dev = z.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            stream = current_stream()
+            Stats.tag = cfg.tag
+            zk = z[:, :K]
+            with timed_region("gemm_fwd"):
+                ft = torch.mm(zk, weight.t())                              # model_zoo.py:83 (cuBLAS fp32)
+            al = attn_l.reshape(-1).contiguous()
+            ar = attn_r.reshape(-1).contiguous()
+            a1 = torch.empty(n * H, **f32)
+            a2 = torch.empty(n * H, **f32)
+            check(lib.tx_gat_node_logits(ptr(ft), F_, ptr(al), ptr(ar), n, H, D, ptr(a1), ptr(a2), stream), "tx_gat_node_logits")
+            alpha = torch.empty(st.e * H, **f32)
+            elog = torch.empty(st.e * H, **f32)
+            alpha_d = torch.empty(st.e * H, **f32) if cfg.p_attn > 0.0 else alpha
+            pd = 0 if next_pos_table is None else int(next_pos_table.shape[1])
+            tab = None if next_pos_table is None else next_pos_table.contiguous()
+            if cfg.hidden:
+                ldo = round4(F_ + pd)
+                out = torch.empty((n, ldo), **f32)
+            else:
+                ldo = D
+                out = torch.empty((n, D), **f32)
+            epi = GatEpilogue(mean_heads=0 if cfg.hidden else 1, act_slope=cfg.act_slope, next_pos_table=ptr(tab),
+                              pos=ptr(pos32) if pd > 0 else None, pos_dim=pd, p_drop=cfg.p_next if cfg.hidden else 0.0,
+                              seed=cfg.next_seed, stream_id=cfg.next_stream)
+            check(lib.tx_gat_aggregate_fwd(ptr(ft), F_, ptr(al), ptr(ar), ptr(a1), ptr(a2), ptr(st.in_ptr), ptr(st.in_src),
+                                           ptr(st.in_eid), n, st.e, H, D, cfg.neg_slope, cfg.p_attn, cfg.attn_seed,
+                                           cfg.attn_stream, ptr(alpha), ptr(alpha_d), ptr(elog), ptr(out), ldo, epi, stream),
+                  "tx_gat_aggregate_fwd")
+        ctx.st, ctx.cfg, ctx.pd = st, cfg, pd
+        ctx.vocab = 0 if next_pos_table is None else int(next_pos_table.shape[0])
+        ctx.save_for_backward(z, weight, al, ar, ft, alpha, alpha_d, elog, out if cfg.hidden else None, pos32)
+        ctx.attn_shape = attn_l.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        z, weight, al, ar, ft, alpha, alpha_d, elog, out, pos32 = ctx.saved_tensors
+        st, cfg, pd = ctx.st, ctx.cfg, ctx.pd
+        n, ldz = z.shape
+        H, D, K = cfg.heads, cfg.dim, cfg.k
+        F_ = H * D
+        dev = z.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        dtab = None
+        with torch.cuda.device(dev):
+            stream = current_stream()
+            Stats.tag = cfg.tag
+            dout = _rowmajor(dout)
+            if cfg.hidden:
+                ldg = dout.stride(0) if n > 1 else dout.shape[1]
+                need_tab = ctx.needs_input_grad[4] and pd > 0
+                if cfg.p_next > 0.0 or cfg.act_slope != 1.0 or need_tab:
+                    if cfg.p_next > 0.0 or cfg.act_slope != 1.0:
+                        dout = dout.clone()
+                        ldg = dout.stride(0) if n > 1 else dout.shape[1]
+                    nb = int(lib.tx_row_blocks(n))
+                    partial = torch.empty(nb * ctx.vocab * pd, **f32) if need_tab else None
+                    check(lib.tx_epilogue_bwd(ptr(dout), ldg, ptr(out), ptr(pos32) if pd > 0 else None, n, F_,
+                                              pd if need_tab else 0, ctx.vocab, cfg.act_slope, cfg.p_next, cfg.next_seed,
+                                              cfg.next_stream, ptr(partial), stream), "tx_epilogue_bwd")
+                    if need_tab:
+                        dtab = _reduce_partials(lib, partial, nb, ctx.vocab * pd).view(ctx.vocab, pd)
+                g, g_head_stride, g_scale = dout, D, 1.0
+            else:
+                g, ldg, g_head_stride, g_scale = dout, (dout.stride(0) if n > 1 else D), 0, 1.0 / H
+            ds = torch.empty(st.e * H, **f32)
+            da2 = torch.empty(n * H, **f32)
+            check(lib.tx_gat_aggregate_bwd_dst(ptr(g), ldg, g_head_stride, g_scale, ptr(ft), F_, ptr(alpha), ptr(elog),
+                                               ptr(st.in_ptr), ptr(st.in_src), ptr(st.in_eid), n, H, D, cfg.neg_slope,
+                                               cfg.p_attn, cfg.attn_seed, cfg.attn_stream, ptr(ds), ptr(da2), stream),
+                  "tx_gat_aggregate_bwd_dst")
+            da1 = torch.empty(n * H, **f32)
+            dft = torch.empty((n, F_), **f32)
+            check(lib.tx_gat_aggregate_bwd_src(ptr(g), ldg, g_head_stride, g_scale, ptr(alpha_d), ptr(ds), ptr(da2), ptr(al),
+                                               ptr(ar), ptr(st.out_ptr), ptr(st.out_dst), ptr(st.out_slot), n, H, D, ptr(da1),
+                                               ptr(dft), F_, stream), "tx_gat_aggregate_bwd_src")
+            dal = dar = None
+            if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+                nb = int(lib.tx_row_blocks(n))
+                partial = torch.empty(nb * 2 * F_, **f32)
+                check(lib.tx_gat_attn_grad_partials(ptr(ft), F_, ptr(da1), ptr(da2), n, H, D, ptr(partial), stream),
+                      "tx_gat_attn_grad_partials")
+                both = _reduce_partials(lib, partial, nb, 2 * F_)
+                dal, dar = both[:F_].view(ctx.attn_shape), both[F_:].view(ctx.attn_shape)
+            with timed_region("gemm_dw"):
+                dw = torch.mm(dft.t(), z[:, :K]) if ctx.needs_input_grad[1] else None
+            dz = None
+            if ctx.needs_input_grad[0]:
+                c0 = min(cfg.dz_from, K)
+                with timed_region("gemm_dz"):
+                    if ldz == K and c0 == 0:
+                        dz = torch.mm(dft, weight)
+                    else:
+                        dz = torch.empty((n, ldz), **f32)
+                        if K > c0:
+                            torch.mm(dft, weight[:, c0:K], out=dz[:, c0:K])
+                        if ldz > K:
+                            dz[:, K:].zero_()
+        return dz, dw, dal, dar, dtab, None, None, None
+
+
+# --------------------------------------------------------------------------------------------------
+# GCN layer: y = z W ; out = act(norm * sum_in(norm * y) + b) ; same epilogue
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class GcnLayerCfg:
+    k: int
+    dim: int
+    hidden: bool = True
+    act_slope: float = 1.0
+    p_next: float = 0.0
+    next_seed: int = 0
+    next_stream: int = 0
+    dz_from: int = 0
+    tag: str = ""
+
+
+class GcnLayer(Function):
+    @staticmethod
+    def forward(ctx, z, weight, bias, next_pos_table, st: GraphStructure, pos32, cfg: GcnLayerCfg):
+        lib = _lib.load()
+        _check_cuda(z, "z")
+        n, ldz = z.shape
+        D, K = cfg.dim, cfg.k
+        dev = z.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            stream = current_stream()
+            Stats.tag = cfg.tag
+            with timed_region("gemm_fwd"):
+                y = torch.mm(z[:, :K], weight)                             # model_zoo.py:37
+            norm = st.gcn_norm()
+            pd = 0 if next_pos_table is None else int(next_pos_table.shape[1])
+            tab = None if next_pos_table is None else next_pos_table.contiguous()
+            ldo = round4(D + pd) if cfg.hidden else D
+            out = torch.empty((n, ldo), **f32)
+            epi = GatEpilogue(mean_heads=0 if cfg.hidden else 1, act_slope=cfg.act_slope, next_pos_table=ptr(tab),
+                              pos=ptr(pos32) if pd > 0 else None, pos_dim=pd, p_drop=cfg.p_next if cfg.hidden else 0.0,
+                              seed=cfg.next_seed, stream_id=cfg.next_stream)
+            b = None if bias is None else bias.contiguous()
+            check(lib.tx_gcn_aggregate_fwd(ptr(y), D, ptr(norm), ptr(b), ptr(st.in_ptr), ptr(st.in_src), n, D, ptr(out), ldo,
+                                           epi, stream), "tx_gcn_aggregate_fwd")
+        ctx.st, ctx.cfg, ctx.pd = st, cfg, pd
+        ctx.vocab = 0 if next_pos_table is None else int(next_pos_table.shape[0])
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(z, weight, out if cfg.hidden else None, pos32, norm)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        z, weight, out, pos32, norm = ctx.saved_tensors
+        st, cfg, pd = ctx.st, ctx.cfg, ctx.pd
+        n, ldz = z.shape
+        D, K = cfg.dim, cfg.k
+        dev = z.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        dtab = db = None
+        with torch.cuda.device(dev):
+            stream = current_stream()
+            dout = _rowmajor(dout)
+            ldg = dout.stride(0) if n > 1 else dout.shape[1]
+            if cfg.hidden:
+                need_tab = ctx.needs_input_grad[3] and pd > 0
+                if cfg.p_next > 0.0 or cfg.act_slope != 1.0 or need_tab:
+                    if cfg.p_next > 0.0 or cfg.act_slope != 1.0:
+                        dout = dout.clone()
+                        ldg = dout.stride(0) if n > 1 else dout.shape[1]
+                    nb = int(lib.tx_row_blocks(n))
+                    partial = torch.empty(nb * ctx.vocab * pd, **f32) if need_tab else None
+                    check(lib.tx_epilogue_bwd(ptr(dout), ldg, ptr(out), ptr(pos32) if pd > 0 else None, n, D,
+                                              pd if need_tab else 0, ctx.vocab, cfg.act_slope, cfg.p_next, cfg.next_seed,
+                                              cfg.next_stream, ptr(partial), stream), "tx_epilogue_bwd")
+                    if need_tab:
+                        dtab = _reduce_partials(lib, partial, nb, ctx.vocab * pd).view(ctx.vocab, pd)
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                nb = int(lib.tx_row_blocks(n))
+                partial = torch.empty(nb * D, **f32)
+                check(lib.tx_colsum_partials(ptr(dout), ldg, n, D, ptr(partial), stream), "tx_colsum_partials")
+                db = _reduce_partials(lib, partial, nb, D)
+            dy = torch.empty((n, D), **f32)
+            check(lib.tx_gcn_aggregate_bwd(ptr(dout), ldg, ptr(norm), ptr(st.out_ptr), ptr(st.out_dst), n, D, ptr(dy), D, stream),
+                  "tx_gcn_aggregate_bwd")
+            with timed_region("gemm_dw"):
+                dw = torch.mm(z[:, :K].t(), dy) if ctx.needs_input_grad[1] else None
+            dz = None
+            if ctx.needs_input_grad[0]:
+                c0 = min(cfg.dz_from, K)
+                with timed_region("gemm_dz"):
+                    if ldz == K and c0 == 0:
+                        dz = torch.mm(dy, weight.t())
+                    else:
+                        dz = torch.empty((n, ldz), **f32)
+                        if K > c0:
+                            torch.mm(dy, weight[c0:K, :].t(), out=dz[:, c0:K])
+                        if ldz > K:
+                            dz[:, K:].zero_()
+        return dz, dw, db, dtab, None, None, None
+
+
+# --------------------------------------------------------------------------------------------------
+# Readout
+# --------------------------------------------------------------------------------------------------
+class Readout(Function):
+    @staticmethod
+    def forward(ctx, h, pos_weight, st: GraphStructure, pos32, kind):
+        lib = _lib.load()
+        _check_cuda(h, "node states")
+        h = _rowmajor(h)
+        n, D = h.shape
+        if n != st.n:
+            raise ValueError(f"readout: {n} node rows for a graph with {st.n} nodes")
+        width = 3 * D if kind == _lib.TX_READOUT_CONCAT else D
+        hg = torch.empty((st.g, width), dtype=torch.float32, device=h.device)
+        w = None if pos_weight is None else pos_weight.reshape(-1).contiguous()
+        with torch.cuda.device(h.device):
+            check(lib.tx_readout_fwd(kind, ptr(h), h.stride(0) if n > 1 else D, ptr(pos32), ptr(w), ptr(st.node_off), st.g, D,
+                                     ptr(hg), width, current_stream()), "tx_readout_fwd")
+        ctx.st, ctx.kind = st, kind
+        ctx.wshape = None if pos_weight is None else pos_weight.shape
+        ctx.save_for_backward(h, hg, w, pos32)
+        return hg
+
+    @staticmethod
+    def backward(ctx, dhg):
+        lib = _lib.load()
+        h, hg, w, pos32 = ctx.saved_tensors
+        st, kind = ctx.st, ctx.kind
+        n, D = h.shape
+        dhg = _rowmajor(dhg)
+        dh = torch.empty((n, D), dtype=torch.float32, device=h.device)
+        dw = None
+        with torch.cuda.device(h.device):
+            need_w = kind == _lib.TX_READOUT_WMEAN and ctx.needs_input_grad[1]
+            partial = torch.empty(st.g * 3, dtype=torch.float32, device=h.device) if need_w else None
+            check(lib.tx_readout_bwd(kind, ptr(dhg), dhg.stride(0) if st.g > 1 else dhg.shape[1], ptr(h),
+                                     h.stride(0) if n > 1 else D, ptr(hg), hg.shape[1], ptr(pos32), ptr(w), ptr(st.node_off),
+                                     st.g, D, ptr(dh), D, ptr(partial), current_stream()), "tx_readout_bwd")
+            if need_w:
+                dw = _reduce_partials(lib, partial, st.g, 3).view(ctx.wshape)
+        return dh, dw, None, None, None

@@ -1,0 +1,111 @@
+"""CPU: the C-ABI library loads and exports every symbol include/taxo_b200.h declares; host-side logic."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import taxoexpan_b200 as tx
+from taxoexpan_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    text = open(os.path.join(ROOT, "include", "taxo_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(tx_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from taxoexpan_b200 import build
+    build.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    declared = _header_functions()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/taxo_b200.h but not exported"
+    assert sorted(_lib.EXPORTED_SYMBOLS) == declared, "ctypes binding and header disagree"
+    l = _lib.load()
+    assert l.tx_abi_version() == 1
+    assert l.tx_target_arch() == b"sm_100a"
+    assert l.tx_row_blocks(65) == 2
+
+
+def test_argument_validation_without_gpu():
+    l = _lib.load()
+    # invalid dropout rate is rejected before any CUDA call
+    rc = l.tx_dropout_keep_mask(1, 0, 0, 16, 1.5, None, None)
+    assert rc == -1 and b"p_drop" in l.tx_last_error()
+    rc = l.tx_readout_fwd(7, None, 4, None, None, None, 1, 4, None, 4, None)
+    assert rc == -1 and b"unknown kind" in l.tx_last_error()
+
+
+def test_product_path_refuses_cpu_tensors():
+    m = tx.TaxoExpan("PGAT", "WMR", "LBM", in_dim=8, hidden_dim=4, out_dim=4, pos_dim=4, num_layers=1, heads=[2, 1],
+                     feat_drop=0.0, attn_drop=0.0, hidden_drop=0.0, out_drop=0.0)
+    g = tx.EgonetBatch.from_counts([1, 0], [2, 0])
+    with pytest.raises(tx.TaxoLibraryError):
+        m(g, torch.randn(5, 8), torch.randn(2, 8))
+
+
+def test_unknown_method_names_raise():
+    with pytest.raises(ValueError):
+        tx.TaxoExpan("XGAT", "WMR", "LBM", in_dim=8, hidden_dim=4, out_dim=4, pos_dim=4, num_layers=1, heads=[2, 1],
+                     feat_drop=0.0, attn_drop=0.0, hidden_drop=0.0, out_drop=0.0)
+
+
+def test_state_dict_keys_match_reference_layout():
+    m = tx.TaxoExpan("PGAT", "WMR", "LBM", in_dim=250, hidden_dim=500, out_dim=500, pos_dim=50, num_layers=1, heads=[4, 1],
+                     feat_drop=0.1, attn_drop=0.1, hidden_drop=0.1, out_drop=0.1)
+    sd = m.state_dict()
+    assert {k: tuple(v.shape) for k, v in sd.items()} == {
+        "graph_propagate.gat_layers.0.attn_l": (1, 4, 500), "graph_propagate.gat_layers.0.attn_r": (1, 4, 500),
+        "graph_propagate.gat_layers.0.fc.weight": (2000, 300),
+        "graph_propagate.gat_layers.1.attn_l": (1, 1, 500), "graph_propagate.gat_layers.1.attn_r": (1, 1, 500),
+        "graph_propagate.gat_layers.1.fc.weight": (500, 2050),
+        "graph_propagate.prop_position_embeddings.0.weight": (3, 50),
+        "graph_propagate.prop_position_embeddings.1.weight": (3, 50),
+        "readout.position_weights.weight": (3, 1), "match.W.weight": (1, 500, 250)}
+    assert sum(v.numel() for v in sd.values()) == 1755303
+    m2 = tx.TaxoExpan("PGCN", "MR", "BIM", in_dim=300, hidden_dim=600, out_dim=300, pos_dim=50, num_layers=1, heads=[4, 1],
+                      feat_drop=0.1, attn_drop=0.1, hidden_drop=0.1, out_drop=0.1)
+    assert {k: tuple(v.shape) for k, v in m2.state_dict().items()} == {
+        "graph_propagate.layers.0.weight": (350, 600), "graph_propagate.layers.0.bias": (600,),
+        "graph_propagate.layers.1.weight": (650, 300), "graph_propagate.layers.1.bias": (300,),
+        "graph_propagate.prop_position_embeddings.0.weight": (3, 50),
+        "graph_propagate.prop_position_embeddings.1.weight": (3, 50), "match.W.weight": (1, 300, 300)}
+
+
+def test_graph_host_api_follows_dgl_calls_of_dataset_py():
+    """dataset.py:429-435 + data_loaders.py:25 through the DGL-free graph class."""
+    from oracle import taxo_oracle as orc
+    gs = []
+    for n_gp, n_sib in [(2, 3), (0, 0), (1, 4)]:
+        n = n_gp + 1 + n_sib
+        g = tx.DGLGraph()
+        g.add_nodes(n, {"x": torch.randn(n, 4), "_id": torch.arange(n), "pos": torch.tensor([0] * n_gp + [1] + [2] * n_sib)})
+        g.add_edges(list(range(n_gp)), n_gp)
+        g.add_edges(n_gp, list(range(n_gp + 1, n)))
+        g.add_edges(g.nodes(), g.nodes())
+        gs.append(g)
+    bg = tx.batch(gs)
+    og = orc.batch_star_egonets([2, 0, 1], [3, 0, 4])
+    assert torch.equal(bg.edges()[0], og.src) and torch.equal(bg.edges()[1], og.dst)
+    assert bg.batch_num_nodes == og.batch_num_nodes and torch.equal(bg.ndata["pos"], og.pos)
+    assert torch.equal(bg.in_degrees(), og.in_degrees())
+    eb = tx.EgonetBatch.from_counts([2, 0, 1], [3, 0, 4])
+    assert torch.equal(eb.edges()[0], og.src) and torch.equal(eb.edges()[1], og.dst)
+    assert torch.equal(eb.in_degrees(), og.in_degrees()) and torch.equal(eb.ndata["pos"].cpu(), og.pos)
+    assert eb.batch_num_nodes == og.batch_num_nodes and eb.number_of_edges() == og.src.numel()
+    assert bg.ndata.pop("pos") is not None and "pos" not in bg.ndata
+
+
+def test_synthetic_shapes_statistics():
+    s = tx.synth.sample_shapes(256, 31, "mag-cs")
+    assert s.num_graphs == 8192
+    assert s.total_edges == 2 * s.total_nodes - s.num_graphs
+    assert 3.5 < s.total_nodes / s.num_graphs < 6.0 and int(s.num_nodes.max()) <= 1 + 50 + 8
+    assert (s.n_sib <= 50).all() and (s.n_gp >= 1).all()

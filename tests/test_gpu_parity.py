@@ -1,0 +1,324 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden vectors frozen from
+the unmodified reference.  Tolerance: 1e-5 max-abs on O(1) fp32 outputs (BASELINE.json north_star); gradients
+2e-5 relative to the largest entry of each gradient tensor; integer/index work bit-exact."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import taxoexpan_b200 as tx
+from oracle import taxo_oracle as orc
+from taxoexpan_b200 import _lib
+from taxoexpan_b200 import functional as txf
+from tests._golden import CASES, compare_to_fixture, load_case
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5       # BASELINE.json: "within 1e-5 fp32"
+GTOL = 2e-5
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def build_model(cfg, params, p_feat=0.0, p_attn=0.0, p_hidden=0.0, p_out=0.0):
+    m = tx.TaxoExpan(cfg.propagation_method, cfg.readout_method, cfg.matching_method, in_dim=cfg.in_dim,
+                     hidden_dim=cfg.hidden_dim, out_dim=cfg.out_dim, pos_dim=cfg.pos_dim, num_layers=cfg.num_layers,
+                     heads=list(cfg.heads), feat_drop=p_feat, attn_drop=p_attn, hidden_drop=p_hidden, out_drop=p_out)
+    m.load_state_dict(params, strict=True)
+    return m.to(dev())
+
+
+def run_cuda(model, graph, x, qf, n_q):
+    h = x.to(dev()).requires_grad_(True)
+    scores = model(graph, h, qf.to(dev()))
+    node_h = graph.ndata["h"]
+    pos = torch.as_tensor(np.asarray(graph.host_pos() if hasattr(graph, "host_pos") else graph._pos_backup))
+    hg = model.readout(graph, pos)
+    loss = F.cross_entropy(scores.reshape(n_q, -1), torch.zeros(n_q, dtype=torch.long, device=dev()), reduction="sum")
+    loss.backward()
+    torch.cuda.synchronize()
+    grads = {k: p.grad.detach().cpu().numpy() for k, p in model.named_parameters()}
+    return (scores.detach().cpu().numpy(), hg.detach().cpu().numpy(), node_h.detach().cpu().numpy(),
+            loss.detach().cpu().numpy(), grads, h.grad.cpu().numpy())
+
+
+def run_oracle(cfg, og, x, qf, params, n_q, masks=None, training=False, dtype=torch.float32):
+    p = {k: v.to(dtype).clone().requires_grad_(True) for k, v in params.items()}
+    h = x.to(dtype).clone().requires_grad_(True)
+    scores, hg, node_h = orc.taxoexpan_forward(cfg, og, h, qf.to(dtype), p, masks=masks, training=training)
+    loss = orc.info_nce_step_loss(scores, n_q)
+    loss.backward()
+    grads = {k: v.grad.numpy() for k, v in p.items()}
+    return scores.detach().numpy(), hg.detach().numpy(), node_h.detach().numpy(), loss.detach().numpy(), grads, h.grad.numpy()
+
+
+def assert_close(got, ref, tol, gtol, what=""):
+    names = ["scores", "hg", "node_h", "loss"]
+    for name, a, b in zip(names, got[:4], ref[:4]):
+        scale = max(1.0, float(np.abs(b).max())) if name in ("scores", "loss") else 1.0
+        err = float(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max())
+        assert err <= tol * scale, f"{what}{name}: max-abs err {err:.3e} > {tol * scale:.3e}"
+    gscale = max(float(np.abs(v).max()) for v in ref[4].values())
+    for k, v in ref[4].items():
+        err = float(np.abs(got[4][k].astype(np.float64) - v.astype(np.float64)).max())
+        bound = gtol * max(float(np.abs(v).max()), 1e-3 * gscale)
+        assert err <= bound, f"{what}grad {k}: max-abs err {err:.3e} > {bound:.3e}"
+    err = float(np.abs(got[5].astype(np.float64) - ref[5].astype(np.float64)).max())
+    bound = gtol * max(float(np.abs(ref[5]).max()), 1e-30)
+    assert err <= bound, f"{what}d(features): max-abs err {err:.3e} > {bound:.3e}"
+
+
+# ------------------------------------------------------------------------------------------------
+# integer / index work: bit-exact
+# ------------------------------------------------------------------------------------------------
+def _check_structure(st, og):
+    n = og.n
+    src, dst = og.src.numpy(), og.dst.numpy()
+    indptr, in_src, in_eid = orc.csr_by_dst(n, src, dst)
+    assert np.array_equal(st.in_ptr.cpu().numpy(), indptr)
+    assert np.array_equal(st.in_src.cpu().numpy(), in_src)
+    assert np.array_equal(st.in_eid.cpu().numpy(), in_eid)
+    slot_of_eid = np.empty_like(in_eid)
+    slot_of_eid[in_eid] = np.arange(len(in_eid))
+    outptr, out_dst, out_eid = orc.csr_by_dst(n, dst, src)      # same routine keyed by src
+    assert np.array_equal(st.out_ptr.cpu().numpy(), outptr)
+    assert np.array_equal(st.out_dst.cpu().numpy(), out_dst)
+    assert np.array_equal(st.out_slot.cpu().numpy(), slot_of_eid[out_eid])
+    assert np.array_equal(st.node_off.cpu().numpy(), np.concatenate([[0], np.cumsum(og.batch_num_nodes)]))
+
+
+def test_star_structure_closed_form_is_bit_exact():
+    shapes = tx.synth.sample_shapes(64, 31, "mag-cs", seed=5)
+    n_gp = np.concatenate([shapes.n_gp, [0, 0, 3, 1]])
+    n_sib = np.concatenate([shapes.n_sib, [0, 50, 0, 1]])
+    og = orc.batch_star_egonets(n_gp, n_sib)
+    eb = tx.EgonetBatch.from_counts(n_gp, n_sib)
+    st = eb.structure(dev())
+    _check_structure(st, og)
+    assert np.array_equal(st.pos.cpu().numpy(), og.pos.numpy())
+
+
+def test_general_csr_build_is_bit_exact():
+    rng = np.random.default_rng(0)
+    n, e = 1000, 7000
+    src = rng.integers(0, n, e)
+    dst = rng.integers(0, n // 2, e)          # half of the nodes have no in-edge; duplicates present
+    g = tx.DGLGraph()
+    g.add_nodes(n)
+    g.add_edges(torch.from_numpy(src), torch.from_numpy(dst))
+    og = orc.OracleGraph(n, torch.from_numpy(src), torch.from_numpy(dst), torch.zeros(n, dtype=torch.int64), [n], [e])
+    _check_structure(g.structure(dev()), og)
+    # and a batched star graph built edge by edge must agree with the closed form
+    og2 = orc.batch_star_egonets([1, 0, 2], [3, 0, 5])
+    g2 = tx.DGLGraph()
+    g2.add_nodes(og2.n)
+    g2.add_edges(og2.src, og2.dst)
+    g2.batch_num_nodes = og2.batch_num_nodes
+    _check_structure(g2.structure(dev()), og2)
+
+
+def test_dropout_mask_is_reproducible_and_calibrated():
+    m1 = txf.dropout_keep_mask(123, 4, 0, 1 << 20, 0.1, dev())
+    m2 = txf.dropout_keep_mask(123, 4, 0, 1 << 20, 0.1, dev())
+    m3 = txf.dropout_keep_mask(123, 5, 0, 1 << 20, 0.1, dev())
+    m4 = txf.dropout_keep_mask(123, 4, 4096, 1024, 0.1, dev())
+    assert torch.equal(m1, m2) and not torch.equal(m1, m3)
+    assert torch.equal(m1[4096:4096 + 1024], m4)
+    rate = 1.0 - m1.float().mean().item()
+    assert abs(rate - 0.1) < 2e-3
+    assert txf.dropout_keep_mask(1, 0, 0, 4096, 0.0, dev()).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# golden vectors from the unmodified reference
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("graph_kind", ["egonet_batch", "dgl_batch"])
+def test_cuda_path_matches_reference_golden(name, graph_kind):
+    cfg, og, x, qf, params, fx = load_case(name)
+    model = build_model(cfg, params)
+    model.train()     # dropout rates 0: exercises the training graph exactly like the golden run
+    if graph_kind == "egonet_batch":
+        g = tx.EgonetBatch.from_counts(fx["n_gp"], fx["n_sib"])
+    else:
+        g = tx.DGLGraph()
+        g.add_nodes(og.n, {"pos": og.pos.clone()})
+        g.add_edges(og.src, og.dst)
+        g.batch_num_nodes = list(og.batch_num_nodes)
+        g._pos_backup = og.pos.numpy()
+    got = run_cuda(model, g, x, qf, int(fx["n_queries"][0]))
+    compare_to_fixture(fx, *got, tol=TOL, gtol=GTOL)
+
+
+# ------------------------------------------------------------------------------------------------
+# oracle parity on seeded synthetic batches (sizes the oracle finishes in seconds)
+# ------------------------------------------------------------------------------------------------
+MAGCS = dict(propagation_method="PGAT", readout_method="WMR", matching_method="LBM", in_dim=250, hidden_dim=500,
+             out_dim=500, pos_dim=50, num_layers=1, heads=[4, 1])
+WORDNET = dict(propagation_method="PGCN", readout_method="MR", matching_method="BIM", in_dim=300, hidden_dim=600,
+               out_dim=300, pos_dim=50, num_layers=1, heads=[4, 1])
+
+
+@pytest.mark.parametrize("cfg_kw,model_name,n_q", [(MAGCS, "mag-cs", 16), (WORDNET, "wordnet", 16),
+                                                    (dict(MAGCS, readout_method="CR"), "mag-cs", 4),
+                                                    (dict(MAGCS, propagation_method="GAT", readout_method="MR"), "mag-cs", 4),
+                                                    (dict(WORDNET, propagation_method="GCN", num_layers=2), "wordnet", 4)])
+def test_cuda_path_matches_oracle_on_synthetic_batches(cfg_kw, model_name, n_q):
+    cfg = orc.OracleConfig(**cfg_kw)
+    shapes = tx.synth.sample_shapes(n_q, 31, model_name, seed=99)
+    og = orc.batch_star_egonets(shapes.n_gp, shapes.n_sib)
+    x = torch.from_numpy(tx.synth.unit_rows(og.n, cfg.in_dim, seed=1))
+    qf = torch.from_numpy(tx.synth.unit_rows(og.num_graphs, cfg.in_dim, seed=2))
+    params = orc.init_model_params(cfg, seed=3)
+    ref = run_oracle(cfg, og, x, qf, params, n_q)
+    model = build_model(cfg, params).train()
+    got = run_cuda(model, tx.EgonetBatch.from_counts(shapes.n_gp, shapes.n_sib), x, qf, n_q)
+    assert_close(got, ref, TOL, GTOL)
+
+
+def test_eval_mode_ignores_dropout_rates():
+    cfg = orc.OracleConfig(**MAGCS)
+    shapes = tx.synth.sample_shapes(2, 31, "mag-cs", seed=4)
+    og = orc.batch_star_egonets(shapes.n_gp, shapes.n_sib)
+    x = torch.from_numpy(tx.synth.unit_rows(og.n, cfg.in_dim, seed=1))
+    qf = torch.from_numpy(tx.synth.unit_rows(og.num_graphs, cfg.in_dim, seed=2))
+    params = orc.init_model_params(cfg, seed=3)
+    model = build_model(cfg, params, p_feat=0.1, p_attn=0.1).eval()
+    with torch.no_grad():
+        s = model(tx.EgonetBatch.from_counts(shapes.n_gp, shapes.n_sib), x.to(dev()), qf.to(dev()))
+    s_ref, _, _ = orc.taxoexpan_forward(cfg, og, x, qf, params)
+    assert float((s.cpu() - s_ref).abs().max()) <= TOL * max(1.0, float(s_ref.abs().max()))
+
+
+def _replay_masks(cfg, og, seed, p_feat, p_attn):
+    """Keep-masks of one training forward, rebuilt from the kernels' counter-based generator (feature index =
+    row * ld + col, attention index = eid * H + h; stream ids 2l / 2l+1 as in model_zoo._gat_stack_forward)."""
+    masks = {}
+    pd = cfg.pos_dim if cfg.propagation_method in ("PGAT", "PGCN") else 0
+    k = cfg.in_dim + pd
+    heads = list(cfg.heads)
+    gat = cfg.propagation_method in ("PGAT", "GAT")
+    for l in range(cfg.num_layers + 1):
+        ld = txf.round4(k)
+        if p_feat[l] > 0:
+            m = txf.dropout_keep_mask(seed, 2 * l, 0, og.n * ld, p_feat[l], dev()).view(og.n, ld)[:, :k]
+            masks[f"feat.{l}"] = m.bool().cpu()
+        if gat and p_attn > 0:
+            e = og.src.numel()
+            m = txf.dropout_keep_mask(seed, 2 * l + 1, 0, e * heads[l], p_attn, dev()).view(e, heads[l], 1)
+            masks[f"attn.{l}"] = m.bool().cpu()
+        k = (cfg.hidden_dim * heads[l] if gat else cfg.hidden_dim) + pd
+    return masks
+
+
+@pytest.mark.parametrize("cfg_kw,model_name", [(MAGCS, "mag-cs"), (WORDNET, "wordnet")])
+def test_training_mode_dropout_matches_oracle_with_replayed_masks(cfg_kw, model_name, monkeypatch):
+    """Dropout active (reference rates 0.1): replay the kernels' exact keep-masks into the oracle -> same 1e-5 bar."""
+    cfg = orc.OracleConfig(**dict(cfg_kw, feat_drop=0.1, attn_drop=0.1, hidden_drop=0.1, out_drop=0.1))
+    n_q = 8
+    shapes = tx.synth.sample_shapes(n_q, 31, model_name, seed=17)
+    og = orc.batch_star_egonets(shapes.n_gp, shapes.n_sib)
+    x = torch.from_numpy(tx.synth.unit_rows(og.n, cfg.in_dim, seed=1))
+    qf = torch.from_numpy(tx.synth.unit_rows(og.num_graphs, cfg.in_dim, seed=2))
+    params = orc.init_model_params(cfg, seed=3)
+    seed = 0x1234_5678_9ABC
+    monkeypatch.setattr(txf, "new_seed", lambda: seed)
+    model = build_model(cfg, params, 0.1, 0.1, 0.1, 0.1).train()
+    got = run_cuda(model, tx.EgonetBatch.from_counts(shapes.n_gp, shapes.n_sib), x, qf, n_q)
+    n_layers = cfg.num_layers + 1
+    masks = _replay_masks(cfg, og, seed, [0.1] * n_layers, 0.1)
+    ref = run_oracle(cfg, og, x, qf, params, n_q, masks=masks, training=True)
+    assert_close(got, ref, TOL, GTOL, what="dropout: ")
+
+
+def test_general_graph_gat_and_gcn_layers_match_oracle():
+    """Arbitrary multigraph (duplicate edges, nodes without in-edges, no self loops) through GAT / GCN stacks."""
+    rng = np.random.default_rng(1)
+    n, e, d = 300, 1500, 24
+    src = torch.from_numpy(rng.integers(0, n, e))
+    dst = torch.from_numpy(rng.integers(0, 200, e))
+    og = orc.OracleGraph(n, src, dst, torch.zeros(n, dtype=torch.int64), [100, 200], [0, 0])
+    x = torch.from_numpy(tx.synth.unit_rows(n, d, seed=5))
+    for pm in ("GAT", "GCN"):
+        cfg = orc.OracleConfig(propagation_method=pm, readout_method="MR", matching_method="BIM", in_dim=d, hidden_dim=16,
+                               out_dim=12, pos_dim=4, num_layers=2, heads=[3, 2, 2])
+        params = orc.init_model_params(cfg, seed=8)
+        p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+        h = x.clone().requires_grad_(True)
+        ref = orc.propagate(cfg, og, h, p)
+        w = torch.from_numpy(tx.synth.unit_rows(n, ref.shape[1], seed=6))
+        (ref * w).sum().backward()
+        model = build_model(cfg, params).train()
+        g = tx.DGLGraph()
+        g.add_nodes(n)
+        g.add_edges(src, dst)
+        g.batch_num_nodes = [100, 200]
+        hc = x.to(dev()).requires_grad_(True)
+        out = model.graph_propagate(g, hc)
+        (out * w.to(dev())).sum().backward()
+        assert float((out.detach().cpu() - ref.detach()).abs().max()) <= TOL, pm
+        assert float((hc.grad.cpu() - h.grad).abs().max()) <= GTOL * float(h.grad.abs().max()), pm
+        gscale = max(float(v.grad.abs().max()) for k, v in p.items() if k.startswith("graph_propagate") and v.grad is not None)
+        for k, v in model.named_parameters():
+            if not k.startswith("graph_propagate"):
+                continue
+            r = p[k].grad
+            bound = GTOL * max(float(r.abs().max()), 1e-3 * gscale)
+            assert float((v.grad.cpu() - r).abs().max()) <= bound, (pm, k)
+
+
+def test_standalone_layers_follow_reference_signatures():
+    """GATLayer.forward(g, feature) -> [N, H, D'] and GCNLayer.forward(g, h) -> [N, out] (model_zoo.py:34,80)."""
+    og = orc.batch_star_egonets([1, 0, 2], [3, 0, 5])
+    g = tx.EgonetBatch.from_counts([1, 0, 2], [3, 0, 5])
+    x = torch.from_numpy(tx.synth.unit_rows(og.n, 16, seed=5))
+    layer = tx.GATLayer(16, 8, num_heads=3, feat_drop=0.0, attn_drop=0.0).to(dev())
+    out = layer(g, x.to(dev()))
+    ref = orc.gat_layer(og, x, layer.fc.weight.detach().cpu(), layer.attn_l.detach().cpu(), layer.attn_r.detach().cpu(), 3)
+    assert out.shape == (og.n, 3, 8) and float((out.detach().cpu() - ref).abs().max()) <= TOL
+    gl = tx.GCNLayer(16, 8, F.leaky_relu, 0.0).to(dev())
+    out = gl(g, x.to(dev()))
+    ref = orc.gcn_layer(og, x, gl.weight.detach().cpu(), gl.bias.detach().cpu(), orc.gcn_norm(og, torch.float32), F.leaky_relu)
+    assert out.shape == (og.n, 8) and float((out.detach().cpu() - ref).abs().max()) <= TOL
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE config 2 at full size: size-independent properties
+# ------------------------------------------------------------------------------------------------
+def test_full_size_properties_magcs_batch256():
+    cfg = orc.OracleConfig(**MAGCS)
+    shapes = tx.synth.sample_shapes(256, 31, "mag-cs")            # G = 8192
+    params = orc.init_model_params(cfg, seed=3)
+    model = build_model(cfg, params).train()
+    n = shapes.total_nodes
+    x = torch.from_numpy(tx.synth.unit_rows(n, cfg.in_dim, seed=1)).to(dev())
+    qf = torch.from_numpy(tx.synth.unit_rows(shapes.num_graphs, cfg.in_dim, seed=2)).to(dev())
+
+    def step():
+        model.zero_grad()
+        g = tx.EgonetBatch.from_counts(shapes.n_gp, shapes.n_sib)
+        s = model(g, x, qf)
+        loss = F.cross_entropy(s.reshape(256, -1), torch.zeros(256, dtype=torch.long, device=dev()), reduction="sum")
+        loss.backward()
+        return s.detach().clone(), g.ndata["h"].detach().clone(), {k: p.grad.clone() for k, p in model.named_parameters()}, g
+
+    s1, h1, g1, graph = step()
+    s2, h2, g2, _ = step()
+    # (1) determinism: no atomics on floats anywhere -> bitwise identical across runs
+    assert torch.equal(s1, s2) and torch.equal(h1, h2)
+    for k in g1:
+        assert torch.equal(g1[k], g2[k]), k
+    assert torch.isfinite(s1).all() and all(torch.isfinite(v).all() for v in g1.values())
+    # (2) a prefix of the batch is independent of the rest (egonets are disjoint components): compare the first
+    #     512 egonets against the CPU oracle run on that prefix only
+    k = 512
+    og = orc.batch_star_egonets(shapes.n_gp[:k], shapes.n_sib[:k])
+    s_ref, hg_ref, nh_ref = orc.taxoexpan_forward(cfg, og, x[:og.n].cpu(), qf[:k].cpu(), params)
+    assert float((h1[:og.n].cpu() - nh_ref).abs().max()) <= TOL
+    assert float((s1[:k].cpu() - s_ref).abs().max()) <= TOL * max(1.0, float(s_ref.abs().max()))
+    # (3) readout of a constant field is that constant (weights normalise to 1), any egonet size
+    graph.ndata["h"] = torch.ones(n, 8, device=dev()) * 3.0
+    pos = graph.host_pos()
+    hg = model.readout(graph, pos)
+    assert float((hg - 3.0).abs().max()) < 1e-6
