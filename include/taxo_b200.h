@@ -56,7 +56,7 @@ const char* tx_target_arch(void);
  * tx_build_csr: counting sort of E (src,dst) pairs by key (stable: ties keep edge-id order).
  *   by_dst: key = dst  -> ptr = in_ptr, nbr = in_src, aux = in_eid
  *   by_src: key = src  -> ptr = out_ptr, nbr = out_dst, aux = out_slot  (needs slot_of_eid from the by_dst pass)
- * workspace: (N + 1) * 4 bytes, zero-filled by the call.
+ * workspace: tx_csr_workspace_bytes(N, E) bytes ((N + 1 + E) int32), initialised by the call.
  * ------------------------------------------------------------------------------------------------ */
 int tx_csr_workspace_bytes(int64_t n_nodes, int64_t n_edges, int64_t* bytes);
 int tx_build_csr_by_dst(const int32_t* src, const int32_t* dst, int64_t n_nodes, int64_t n_edges,
@@ -158,6 +158,43 @@ int tx_gat_attn_grad_partials(const float* ft, int64_t ldf, const float* da1, co
                               int64_t heads, int64_t dim, float* partial, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Fused fast path for batched graphs (the egonet batches of data_loader/dataset.py:404-437): same arithmetic as
+ * tx_gat_node_logits + tx_gat_aggregate_fwd, and tx_epilogue_bwd + tx_gat_aggregate_bwd_dst/_src +
+ * tx_gat_attn_grad_partials, in ONE forward and ONE backward kernel with algorithmic DRAM traffic (read ft once, write out
+ * once; read g, ft once, write dft once).  Needs dim % 4 == 0, dim <= 512 and, for the output layer
+ * (epi->mean_heads), heads == 1 -- tx_gat_fused_supported() says whether a shape qualifies; otherwise use the general
+ * kernels above.  The backward kernel needs every edge to stay inside one graph of node_off (true for any dgl.batch).
+ *   maskbits: tx_gat_fused_mask_words(N, heads, dim) uint32 words written by the forward epilogue (sign of the
+ *             pre-activation and dropout keep bits) and consumed by the backward kernel, which reads g straight from
+ *             d(z_next) (ldg = ld of z_next, g_head_stride = dim) and applies keep/(1-p_next) * leaky' on load.
+ *             NULL = no activation/dropout to undo (g is used as is).
+ *   dattn_partial: [tx_gat_fused_bwd_blocks(N, heads), 2, heads, dim] -> reduce with tx_reduce_partials to
+ *             [d attn_l (heads*dim) | d attn_r (heads*dim)].
+ *   ds [E*heads], da2 [N*heads]: scratch.
+ * ------------------------------------------------------------------------------------------------ */
+int tx_gat_fused_supported(int64_t heads, int64_t dim, int32_t mean_heads);
+int64_t tx_gat_fused_mask_words(int64_t n_nodes, int64_t heads, int64_t dim);
+int64_t tx_gat_fused_bwd_blocks(int64_t n_nodes, int64_t heads);
+int tx_gat_fused_fwd(const float* ft, int64_t ldf, const float* attn_l, const float* attn_r, const int32_t* in_ptr,
+                     const int32_t* in_src, const int32_t* in_eid, int64_t n_nodes, int64_t heads, int64_t dim,
+                     float neg_slope, float p_attn, uint64_t attn_seed, uint32_t attn_stream_id, float* alpha,
+                     float* alpha_d, float* elog, float* out, int64_t ldo, const tx_gat_epilogue* epi, uint32_t* maskbits,
+                     void* stream);
+int tx_gat_fused_bwd(const float* g, int64_t ldg, int64_t g_head_stride, float g_scale, const uint32_t* maskbits,
+                     int32_t has_keep_plane, float act_slope, float p_next, const float* ft, int64_t ldf,
+                     const float* alpha, const float* alpha_d, const float* elog, const float* attn_l,
+                     const float* attn_r, const int32_t* in_ptr, const int32_t* in_src, const int32_t* in_eid,
+                     const int32_t* out_ptr, const int32_t* out_dst, const int32_t* out_slot, const int32_t* node_off,
+                     int64_t n_graphs, int64_t n_nodes, int64_t heads, int64_t dim, float neg_slope, float p_attn,
+                     uint64_t attn_seed, uint32_t attn_stream_id, float* ds, float* da2, float* dft, int64_t ldd,
+                     float* dattn_partial, void* stream);
+/* dpos_partial[b, r, :] = sum over rows i of block b (tx_row_blocks) with pos_i = r of dz[i, col0 : col0+pos_dim] * keep/(1-p)
+ * (gradient of the appended position-embedding block, reference model_zoo.py:214-215). */
+int tx_pos_grad_partials(const float* dz, int64_t ldz, int64_t col0, const int32_t* pos, int64_t n_nodes,
+                         int64_t pos_dim, int64_t vocab, float p_drop, uint64_t seed, uint32_t stream_id,
+                         float* partial, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * GCN layer (model/model_zoo.py:34-50) after y = dropout(h) @ W:
  *   out[i,:] = act(norm_i * sum_in norm_src * y[src,:] + bias)      :39-49, copy_src/sum at :41
  * with the same "next layer input" epilogue as the GAT kernel (heads = 1). norm = in_degree^-0.5 (inf -> 0),
@@ -183,8 +220,9 @@ int tx_gcn_aggregate_bwd(const float* g, int64_t ldg, const float* norm, const i
 #define TX_READOUT_CONCAT 2
 int tx_readout_fwd(int32_t kind, const float* h, int64_t ldh, const int32_t* pos, const float* pos_weight,
                    const int32_t* node_off, int64_t n_graphs, int64_t dim, float* hg, int64_t ldhg, void* stream);
-/* dh[i,:] and, for WMEAN, dw_partial[g, 0..2] (reduce with tx_reduce_partials over n_graphs blocks of 3):
+/* dh[i,:] and, for WMEAN, dw_partial[b, 0..2] for b < tx_readout_bwd_blocks(n_graphs) (reduce with tx_reduce_partials):
  *   S = sum a; dh_i = a_i/S * dhg_g; da_i = <dhg_g, h_i - hg_g>/S; dw[pos_i] += da_i * sigmoid(w[pos_i]). */
+int64_t tx_readout_bwd_blocks(int64_t n_graphs);
 int tx_readout_bwd(int32_t kind, const float* dhg, int64_t lddhg, const float* h, int64_t ldh, const float* hg,
                    int64_t ldhg, const int32_t* pos, const float* pos_weight, const int32_t* node_off,
                    int64_t n_graphs, int64_t dim, float* dh, int64_t lddh, float* dw_partial, void* stream);

@@ -168,13 +168,29 @@ __global__ void __launch_bounds__(256) epilogue_bwd_kernel(float* __restrict__ d
   }
 }
 
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, int64_t n_blocks, int64_t m_len,
-                                       float* __restrict__ out) {
-  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= m_len) return;
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int64_t n_blocks, int64_t m_len,
+                                                              float* __restrict__ out) {
+  __shared__ float sm[8][33];
+  const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+  const int64_t m = (int64_t)blockIdx.x * 32 + x;
   float acc = 0.f;
-  for (int64_t b = 0; b < n_blocks; ++b) acc += partial[b * m_len + m];
-  out[m] = acc;
+  if (m < m_len) {
+    int64_t b = y;
+    for (; b + 24 < n_blocks; b += 32) {   // 4 independent loads in flight per thread
+      const float v0 = partial[b * m_len + m], v1 = partial[(b + 8) * m_len + m];
+      const float v2 = partial[(b + 16) * m_len + m], v3 = partial[(b + 24) * m_len + m];
+      acc += v0; acc += v1; acc += v2; acc += v3;
+    }
+    for (; b < n_blocks; b += 8) acc += partial[b * m_len + m];
+  }
+  sm[y][x] = acc;
+  __syncthreads();
+  if (y == 0 && m < m_len) {
+    float t = sm[0][x];
+#pragma unroll
+    for (int r = 1; r < 8; ++r) t += sm[r][x];
+    out[m] = t;
+  }
 }
 
 __global__ void colsum_partials_kernel(const float* __restrict__ x, int64_t ldx, int n_rows, int n_cols,
@@ -546,105 +562,158 @@ __device__ __forceinline__ float softplus_f(float x) {
   return x > 20.f ? x : log1pf(expf(x));
 }
 
-__device__ __forceinline__ float node_weight(int kind, const float* w, int r) {
-  return kind == TX_READOUT_WMEAN ? softplus_f(__ldg(w + r)) : 1.f;
-}
-
-__global__ void __launch_bounds__(128) readout_fwd_kernel(int kind, const float* __restrict__ h, int64_t ldh,
-                                                          const int32_t* __restrict__ pos,
-                                                          const float* __restrict__ pw,
-                                                          const int32_t* __restrict__ node_off, int D,
+template <int VEC>
+__global__ void __launch_bounds__(256) readout_fwd_kernel(int kind, const float* __restrict__ h, int64_t ldh,
+                                                          const int32_t* __restrict__ pos, const float* __restrict__ pw,
+                                                          const int32_t* __restrict__ node_off, int n_graphs, int D,
                                                           float* __restrict__ hg, int64_t ldhg) {
-  const int g = blockIdx.x;
-  const int beg = __ldg(node_off + g), end = __ldg(node_off + g + 1);
-  float* orow = hg + (int64_t)g * ldhg;
-  if (kind == TX_READOUT_CONCAT) {
-    int n_anchor = 0;
-    for (int i = beg; i < end; ++i) n_anchor += (__ldg(pos + i) == 1);
-    const float inv_n = 1.f / (float)(end - beg);
-    for (int c = threadIdx.x; c < D; c += blockDim.x) {
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-      for (int i = beg; i < end; ++i) {
-        const float v = __ldg(h + (int64_t)i * ldh + c);
-        const int r = __ldg(pos + i);
-        s0 += r == 0 ? v : 0.f;
-        s1 += r == 1 ? v : 0.f;
-        s2 += r == 2 ? v : 0.f;
-      }
-      orow[c] = s0 * inv_n;  // sum_nodes / normalizer (model_zoo.py:252)
-      orow[D + c] = s1 / (float)n_anchor;  // mean_nodes with the 0/1 weight (model_zoo.py:254)
-      orow[2 * D + c] = s2 * inv_n;
-    }
-    return;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int nvec = D / VEC;
+  float sw[3] = {1.f, 1.f, 1.f};
+  if (kind == TX_READOUT_WMEAN) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) sw[r] = softplus_f(__ldg(pw + r));   // a_i = softplus(w[pos_i]), model_zoo.py:241
   }
-  float S = 0.f;
-  for (int i = beg; i < end; ++i) S += node_weight(kind, pw, kind == TX_READOUT_WMEAN ? __ldg(pos + i) : 0);
-  for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    float acc = 0.f;
-    for (int i = beg; i < end; ++i) {
-      const float a = node_weight(kind, pw, kind == TX_READOUT_WMEAN ? __ldg(pos + i) : 0);
-      acc = fmaf(a, __ldg(h + (int64_t)i * ldh + c), acc);
+  for (int g = warp; g < n_graphs; g += nwarps) {
+    const int beg = __ldg(node_off + g), end = __ldg(node_off + g + 1);
+    float* orow = hg + (int64_t)g * ldhg;
+    if (kind == TX_READOUT_CONCAT) {
+      float na = 0.f;
+      for (int i = beg + lane; i < end; i += 32) na += (__ldg(pos + i) == 1) ? 1.f : 0.f;
+      na = warp_sum(na);
+      const float inv_n = 1.f / (float)(end - beg);
+      for (int c = lane; c < nvec; c += 32) {
+        Vec<VEC> s0 = vzero<VEC>(), s1 = vzero<VEC>(), s2 = vzero<VEC>();
+        for (int i = beg; i < end; ++i) {
+          const Vec<VEC> v = Vec<VEC>::load(h + (int64_t)i * ldh + c * VEC);
+          const int r = __ldg(pos + i);
+#pragma unroll
+          for (int t = 0; t < VEC; ++t) {
+            s0.v[t] += r == 0 ? v.v[t] : 0.f;
+            s1.v[t] += r == 1 ? v.v[t] : 0.f;
+            s2.v[t] += r == 2 ? v.v[t] : 0.f;
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < VEC; ++t) {
+          s0.v[t] *= inv_n;          // sum_nodes / normalizer (model_zoo.py:252)
+          s1.v[t] /= na;             // mean_nodes with the 0/1 weight (model_zoo.py:254)
+          s2.v[t] *= inv_n;
+        }
+        s0.store(orow + c * VEC);
+        s1.store(orow + D + c * VEC);
+        s2.store(orow + 2 * D + c * VEC);
+      }
+      continue;
     }
-    orow[c] = acc / S;
+    float S = 0.f;
+    for (int i = beg + lane; i < end; i += 32) {
+      const int r = kind == TX_READOUT_WMEAN ? __ldg(pos + i) : 0;
+      S += r == 0 ? sw[0] : (r == 1 ? sw[1] : sw[2]);
+    }
+    S = warp_sum(S);
+    for (int c = lane; c < nvec; c += 32) {
+      Vec<VEC> acc = vzero<VEC>();
+      for (int i = beg; i < end; ++i) {
+        const int r = kind == TX_READOUT_WMEAN ? __ldg(pos + i) : 0;
+        const float a = r == 0 ? sw[0] : (r == 1 ? sw[1] : sw[2]);
+        const Vec<VEC> v = Vec<VEC>::load(h + (int64_t)i * ldh + c * VEC);
+#pragma unroll
+        for (int t = 0; t < VEC; ++t) acc.v[t] = fmaf(a, v.v[t], acc.v[t]);
+      }
+#pragma unroll
+      for (int t = 0; t < VEC; ++t) acc.v[t] /= S;
+      acc.store(orow + c * VEC);
+    }
   }
 }
 
-__global__ void __launch_bounds__(128) readout_bwd_kernel(int kind, const float* __restrict__ dhg, int64_t lddhg,
+template <int VEC>
+__global__ void __launch_bounds__(256) readout_bwd_kernel(int kind, const float* __restrict__ dhg, int64_t lddhg,
                                                           const float* __restrict__ h, int64_t ldh,
                                                           const float* __restrict__ hg, int64_t ldhg,
-                                                          const int32_t* __restrict__ pos,
-                                                          const float* __restrict__ pw,
-                                                          const int32_t* __restrict__ node_off, int D,
-                                                          float* __restrict__ dh, int64_t lddh,
-                                                          float* __restrict__ dw_partial) {
-  const int g = blockIdx.x;
-  const int beg = __ldg(node_off + g), end = __ldg(node_off + g + 1);
-  const float* drow = dhg + (int64_t)g * lddhg;
-  if (kind == TX_READOUT_CONCAT) {
-    int n_anchor = 0;
-    for (int i = beg; i < end; ++i) n_anchor += (__ldg(pos + i) == 1);
-    const float inv_n = 1.f / (float)(end - beg);
-    for (int i = beg; i < end; ++i) {
-      const int r = __ldg(pos + i);
-      const float sc = r == 1 ? 1.f / (float)n_anchor : inv_n;
-      for (int c = threadIdx.x; c < D; c += blockDim.x)
-        dh[(int64_t)i * lddh + c] = (r >= 0 && r <= 2) ? __ldg(drow + r * D + c) * sc : 0.f;
-    }
-    return;
-  }
-  float S = 0.f;
-  for (int i = beg; i < end; ++i) S += node_weight(kind, pw, kind == TX_READOUT_WMEAN ? __ldg(pos + i) : 0);
-  const float inv_s = 1.f / S;
-  __shared__ float sdw[4][3];
+                                                          const int32_t* __restrict__ pos, const float* __restrict__ pw,
+                                                          const int32_t* __restrict__ node_off, int n_graphs, int D,
+                                                          float* __restrict__ dh, int64_t lddh, float* __restrict__ dw_partial) {
+  __shared__ float sdw[8][3];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  float dw0 = 0.f, dw1 = 0.f, dw2 = 0.f;
-  // warp w owns rows beg+w, beg+w+4, ...
-  for (int i = beg + wid; i < end; i += 4) {
-    const int r = kind == TX_READOUT_WMEAN ? __ldg(pos + i) : 0;
-    const float a = node_weight(kind, pw, r);
-    const float sc = a * inv_s;
-    float dot = 0.f;
-    for (int c = lane; c < D; c += 32) {
-      const float d = __ldg(drow + c);
-      dh[(int64_t)i * lddh + c] = d * sc;
-      if (kind == TX_READOUT_WMEAN) dot = fmaf(d, __ldg(h + (int64_t)i * ldh + c) - __ldg(hg + (int64_t)g * ldhg + c), dot);
-    }
-    if (kind == TX_READOUT_WMEAN) {
-      dot = warp_sum(dot);
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int nvec = D / VEC;
+  float sw[3] = {1.f, 1.f, 1.f}, sg[3] = {0.f, 0.f, 0.f};
+  if (kind == TX_READOUT_WMEAN) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
       const float w = __ldg(pw + r);
-      const float sig = 1.f / (1.f + expf(-w));            // d softplus / dw
-      const float contrib = dot * inv_s * (w > 20.f ? 1.f : sig);
-      dw0 += r == 0 ? contrib : 0.f;
-      dw1 += r == 1 ? contrib : 0.f;
-      dw2 += r == 2 ? contrib : 0.f;
+      sw[r] = softplus_f(w);
+      sg[r] = w > 20.f ? 1.f : 1.f / (1.f + expf(-w));   // d softplus / dw
+    }
+  }
+  float dw[3] = {0.f, 0.f, 0.f};
+  for (int g = warp; g < n_graphs; g += nwarps) {
+    const int beg = __ldg(node_off + g), end = __ldg(node_off + g + 1);
+    const float* drow = dhg + (int64_t)g * lddhg;
+    if (kind == TX_READOUT_CONCAT) {
+      float na = 0.f;
+      for (int i = beg + lane; i < end; i += 32) na += (__ldg(pos + i) == 1) ? 1.f : 0.f;
+      na = warp_sum(na);
+      const float inv_n = 1.f / (float)(end - beg);
+      for (int i = beg; i < end; ++i) {
+        const int r = __ldg(pos + i);
+        const bool ok = r >= 0 && r <= 2;
+        const float sc = r == 1 ? 1.f / na : inv_n;
+        for (int c = lane; c < nvec; c += 32) {
+          Vec<VEC> v = ok ? Vec<VEC>::load(drow + (int64_t)r * D + c * VEC) : vzero<VEC>();
+#pragma unroll
+          for (int t = 0; t < VEC; ++t) v.v[t] *= sc;
+          v.store(dh + (int64_t)i * lddh + c * VEC);
+        }
+      }
+      continue;
+    }
+    float S = 0.f;
+    for (int i = beg + lane; i < end; i += 32) {
+      const int r = kind == TX_READOUT_WMEAN ? __ldg(pos + i) : 0;
+      S += r == 0 ? sw[0] : (r == 1 ? sw[1] : sw[2]);
+    }
+    S = warp_sum(S);
+    const float inv_s = 1.f / S;
+    for (int i = beg; i < end; ++i) {
+      const int r = kind == TX_READOUT_WMEAN ? __ldg(pos + i) : 0;
+      const float a = r == 0 ? sw[0] : (r == 1 ? sw[1] : sw[2]);
+      const float sc = a * inv_s;
+      float dot = 0.f;
+      for (int c = lane; c < nvec; c += 32) {
+        const Vec<VEC> d = Vec<VEC>::load(drow + c * VEC);
+        Vec<VEC> o;
+#pragma unroll
+        for (int t = 0; t < VEC; ++t) o.v[t] = d.v[t] * sc;
+        o.store(dh + (int64_t)i * lddh + c * VEC);
+        if (kind == TX_READOUT_WMEAN) {
+          const Vec<VEC> hv = Vec<VEC>::load(h + (int64_t)i * ldh + c * VEC);
+          const Vec<VEC> gv = Vec<VEC>::load(hg + (int64_t)g * ldhg + c * VEC);
+#pragma unroll
+          for (int t = 0; t < VEC; ++t) dot = fmaf(d.v[t], hv.v[t] - gv.v[t], dot);
+        }
+      }
+      if (kind == TX_READOUT_WMEAN) {
+        dot = warp_sum(dot) * inv_s;
+        dw[0] += r == 0 ? dot * sg[0] : 0.f;
+        dw[1] += r == 1 ? dot * sg[1] : 0.f;
+        dw[2] += r == 2 ? dot * sg[2] : 0.f;
+      }
     }
   }
   if (kind == TX_READOUT_WMEAN && dw_partial) {
-    if (lane == 0) { sdw[wid][0] = dw0; sdw[wid][1] = dw1; sdw[wid][2] = dw2; }
+    if (lane == 0) { sdw[wid][0] = dw[0]; sdw[wid][1] = dw[1]; sdw[wid][2] = dw[2]; }
     __syncthreads();
     if (threadIdx.x < 3) {
-      const int r = threadIdx.x;
-      dw_partial[(int64_t)g * 3 + r] = ((sdw[0][r] + sdw[1][r]) + sdw[2][r]) + sdw[3][r];
+      float t = sdw[0][threadIdx.x];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) t += sdw[w][threadIdx.x];
+      dw_partial[(int64_t)blockIdx.x * 3 + threadIdx.x] = t;
     }
   }
 }
@@ -706,7 +775,7 @@ int tx_epilogue_bwd(float* dz, int64_t ldz, const float* z, const int32_t* pos, 
 
 int tx_reduce_partials(const float* partial, int64_t n_blocks, int64_t m_len, float* out, void* stream) {
   if (m_len <= 0) return TX_OK;
-  reduce_partials_kernel<<<(int)((m_len + 127) / 128), 128, 0, (cudaStream_t)stream>>>(partial, n_blocks, m_len, out);
+  reduce_partials_kernel<<<(int)((m_len + 31) / 32), 256, 0, (cudaStream_t)stream>>>(partial, n_blocks, m_len, out);
   TX_LAUNCH_CHECK("tx_reduce_partials");
   return TX_OK;
 }
@@ -852,6 +921,9 @@ int tx_gcn_aggregate_bwd(const float* g, int64_t ldg, const float* norm, const i
   return TX_OK;
 }
 
+static int readout_grid(int64_t n_graphs) { return grid_for_warps(n_graphs, 8, 8); }
+int64_t tx_readout_bwd_blocks(int64_t n_graphs) { return readout_grid(n_graphs); }
+
 int tx_readout_fwd(int32_t kind, const float* h, int64_t ldh, const int32_t* pos, const float* pos_weight,
                    const int32_t* node_off, int64_t n_graphs, int64_t dim, float* hg, int64_t ldhg, void* stream) {
   TX_REQUIRE(kind >= 0 && kind <= 2, "readout_fwd: unknown kind %d", kind);
@@ -859,7 +931,11 @@ int tx_readout_fwd(int32_t kind, const float* h, int64_t ldh, const int32_t* pos
   TX_REQUIRE(kind != TX_READOUT_WMEAN || pos_weight, "readout_fwd: pos_weight required for WMEAN");
   TX_REQUIRE(ldhg >= (kind == TX_READOUT_CONCAT ? 3 * dim : dim), "readout_fwd: ldhg too small");
   if (n_graphs == 0) return TX_OK;
-  readout_fwd_kernel<<<(int)n_graphs, 128, 0, (cudaStream_t)stream>>>(kind, h, ldh, pos, pos_weight, node_off, (int)dim, hg, ldhg);
+  const int grid = readout_grid(n_graphs);
+  if (vec4_ok(h, ldh, dim) && vec4_ok(hg, ldhg, dim))
+    readout_fwd_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(kind, h, ldh, pos, pos_weight, node_off, (int)n_graphs, (int)dim, hg, ldhg);
+  else
+    readout_fwd_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(kind, h, ldh, pos, pos_weight, node_off, (int)n_graphs, (int)dim, hg, ldhg);
   TX_LAUNCH_CHECK("tx_readout_fwd");
   return TX_OK;
 }
@@ -871,8 +947,14 @@ int tx_readout_bwd(int32_t kind, const float* dhg, int64_t lddhg, const float* h
   TX_REQUIRE(kind == TX_READOUT_MEAN || pos, "readout_bwd: pos required");
   TX_REQUIRE(kind != TX_READOUT_WMEAN || (pos_weight && h && hg), "readout_bwd: WMEAN needs pos_weight, h, hg");
   if (n_graphs == 0) return TX_OK;
-  readout_bwd_kernel<<<(int)n_graphs, 128, 0, (cudaStream_t)stream>>>(kind, dhg, lddhg, h, ldh, hg, ldhg, pos, pos_weight,
-                                                                     node_off, (int)dim, dh, lddh, dw_partial);
+  const int grid = readout_grid(n_graphs);
+  const bool v4 = vec4_ok(dhg, lddhg, dim) && vec4_ok(dh, lddh, dim) && (kind != TX_READOUT_WMEAN || (vec4_ok(h, ldh, dim) && vec4_ok(hg, ldhg, dim)));
+  if (v4)
+    readout_bwd_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(kind, dhg, lddhg, h, ldh, hg, ldhg, pos, pos_weight, node_off,
+                                                                  (int)n_graphs, (int)dim, dh, lddh, dw_partial);
+  else
+    readout_bwd_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(kind, dhg, lddhg, h, ldh, hg, ldhg, pos, pos_weight, node_off,
+                                                                  (int)n_graphs, (int)dim, dh, lddh, dw_partial);
   TX_LAUNCH_CHECK("tx_readout_bwd");
   return TX_OK;
 }

@@ -9,6 +9,7 @@ for 128-bit accesses / TMA); the logical width K <= ld is tracked by the caller,
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -40,6 +41,15 @@ def _rowmajor(t: torch.Tensor) -> torch.Tensor:
     if t.stride(1) != 1 or (t.shape[0] > 1 and t.stride(0) < t.shape[1]):
         t = t.contiguous()
     return t
+
+
+FUSED_ENABLED = os.environ.get("TAXO_DISABLE_FUSED", "") == ""
+
+
+def use_fused(lib, heads: int, dim: int, mean_heads: int) -> bool:
+    """Fused single-kernel GAT forward/backward when the shape qualifies (dim % 4 == 0, dim <= 512, heads == 1 for the
+    head-mean output layer); otherwise the general-CSR kernels. TAXO_DISABLE_FUSED=1 forces the general path (tests)."""
+    return FUSED_ENABLED and bool(lib.tx_gat_fused_supported(heads, dim, mean_heads))
 
 
 def new_seed() -> int:
@@ -150,9 +160,6 @@ class GatLayer(Function):
                 ft = torch.mm(zk, weight.t())                              # model_zoo.py:83 (cuBLAS fp32)
             al = attn_l.reshape(-1).contiguous()
             ar = attn_r.reshape(-1).contiguous()
-            a1 = torch.empty(n * H, **f32)
-            a2 = torch.empty(n * H, **f32)
-            check(lib.tx_gat_node_logits(ptr(ft), F_, ptr(al), ptr(ar), n, H, D, ptr(a1), ptr(a2), stream), "tx_gat_node_logits")
             alpha = torch.empty(st.e * H, **f32)
             elog = torch.empty(st.e * H, **f32)
             alpha_d = torch.empty(st.e * H, **f32) if cfg.p_attn > 0.0 else alpha
@@ -167,10 +174,24 @@ class GatLayer(Function):
             epi = GatEpilogue(mean_heads=0 if cfg.hidden else 1, act_slope=cfg.act_slope, next_pos_table=ptr(tab),
                               pos=ptr(pos32) if pd > 0 else None, pos_dim=pd, p_drop=cfg.p_next if cfg.hidden else 0.0,
                               seed=cfg.next_seed, stream_id=cfg.next_stream)
-            check(lib.tx_gat_aggregate_fwd(ptr(ft), F_, ptr(al), ptr(ar), ptr(a1), ptr(a2), ptr(st.in_ptr), ptr(st.in_src),
-                                           ptr(st.in_eid), n, st.e, H, D, cfg.neg_slope, cfg.p_attn, cfg.attn_seed,
-                                           cfg.attn_stream, ptr(alpha), ptr(alpha_d), ptr(elog), ptr(out), ldo, epi, stream),
-                  "tx_gat_aggregate_fwd")
+            fused = use_fused(lib, H, D, 0 if cfg.hidden else 1)
+            maskbits = None
+            if fused:
+                # ONE kernel: logits from the gathered rows, edge softmax, dropout, aggregation, next-layer epilogue
+                if cfg.hidden and (cfg.act_slope != 1.0 or cfg.p_next > 0.0):
+                    maskbits = torch.empty(int(lib.tx_gat_fused_mask_words(n, H, D)), dtype=torch.int32, device=dev)
+                check(lib.tx_gat_fused_fwd(ptr(ft), F_, ptr(al), ptr(ar), ptr(st.in_ptr), ptr(st.in_src), ptr(st.in_eid), n, H, D,
+                                           cfg.neg_slope, cfg.p_attn, cfg.attn_seed, cfg.attn_stream, ptr(alpha), ptr(alpha_d),
+                                           ptr(elog), ptr(out), ldo, epi, ptr(maskbits), stream), "tx_gat_fused_fwd")
+            else:
+                a1 = torch.empty(n * H, **f32)
+                a2 = torch.empty(n * H, **f32)
+                check(lib.tx_gat_node_logits(ptr(ft), F_, ptr(al), ptr(ar), n, H, D, ptr(a1), ptr(a2), stream), "tx_gat_node_logits")
+                check(lib.tx_gat_aggregate_fwd(ptr(ft), F_, ptr(al), ptr(ar), ptr(a1), ptr(a2), ptr(st.in_ptr), ptr(st.in_src),
+                                               ptr(st.in_eid), n, st.e, H, D, cfg.neg_slope, cfg.p_attn, cfg.attn_seed,
+                                               cfg.attn_stream, ptr(alpha), ptr(alpha_d), ptr(elog), ptr(out), ldo, epi, stream),
+                      "tx_gat_aggregate_fwd")
+        ctx.fused, ctx.maskbits = fused, maskbits
         ctx.st, ctx.cfg, ctx.pd = st, cfg, pd
         ctx.vocab = 0 if next_pos_table is None else int(next_pos_table.shape[0])
         ctx.save_for_backward(z, weight, al, ar, ft, alpha, alpha_d, elog, out if cfg.hidden else None, pos32)
@@ -192,42 +213,60 @@ class GatLayer(Function):
             stream = current_stream()
             Stats.tag = cfg.tag
             dout = _rowmajor(dout)
-            if cfg.hidden:
-                ldg = dout.stride(0) if n > 1 else dout.shape[1]
-                need_tab = ctx.needs_input_grad[4] and pd > 0
-                if cfg.p_next > 0.0 or cfg.act_slope != 1.0 or need_tab:
-                    if cfg.p_next > 0.0 or cfg.act_slope != 1.0:
-                        dout = dout.clone()
-                        ldg = dout.stride(0) if n > 1 else dout.shape[1]
-                    nb = int(lib.tx_row_blocks(n))
-                    partial = torch.empty(nb * ctx.vocab * pd, **f32) if need_tab else None
-                    check(lib.tx_epilogue_bwd(ptr(dout), ldg, ptr(out), ptr(pos32) if pd > 0 else None, n, F_,
-                                              pd if need_tab else 0, ctx.vocab, cfg.act_slope, cfg.p_next, cfg.next_seed,
-                                              cfg.next_stream, ptr(partial), stream), "tx_epilogue_bwd")
-                    if need_tab:
-                        dtab = _reduce_partials(lib, partial, nb, ctx.vocab * pd).view(ctx.vocab, pd)
-                g, g_head_stride, g_scale = dout, D, 1.0
-            else:
-                g, ldg, g_head_stride, g_scale = dout, (dout.stride(0) if n > 1 else D), 0, 1.0 / H
+            ldg = dout.stride(0) if n > 1 else dout.shape[1]
+            need_tab = cfg.hidden and ctx.needs_input_grad[4] and pd > 0
+            nb = int(lib.tx_row_blocks(n))
+            dft = torch.empty((n, F_), **f32)
             ds = torch.empty(st.e * H, **f32)
             da2 = torch.empty(n * H, **f32)
-            check(lib.tx_gat_aggregate_bwd_dst(ptr(g), ldg, g_head_stride, g_scale, ptr(ft), F_, ptr(alpha), ptr(elog),
-                                               ptr(st.in_ptr), ptr(st.in_src), ptr(st.in_eid), n, H, D, cfg.neg_slope,
-                                               cfg.p_attn, cfg.attn_seed, cfg.attn_stream, ptr(ds), ptr(da2), stream),
-                  "tx_gat_aggregate_bwd_dst")
-            da1 = torch.empty(n * H, **f32)
-            dft = torch.empty((n, F_), **f32)
-            check(lib.tx_gat_aggregate_bwd_src(ptr(g), ldg, g_head_stride, g_scale, ptr(alpha_d), ptr(ds), ptr(da2), ptr(al),
-                                               ptr(ar), ptr(st.out_ptr), ptr(st.out_dst), ptr(st.out_slot), n, H, D, ptr(da1),
-                                               ptr(dft), F_, stream), "tx_gat_aggregate_bwd_src")
-            dal = dar = None
-            if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
-                nb = int(lib.tx_row_blocks(n))
-                partial = torch.empty(nb * 2 * F_, **f32)
-                check(lib.tx_gat_attn_grad_partials(ptr(ft), F_, ptr(da1), ptr(da2), n, H, D, ptr(partial), stream),
-                      "tx_gat_attn_grad_partials")
-                both = _reduce_partials(lib, partial, nb, 2 * F_)
+            if ctx.fused:
+                # g is read straight from d(z_next); dropout / leaky-relu derivative rebuilt from the forward's bit-planes
+                if need_tab:
+                    partial = torch.empty(nb * ctx.vocab * pd, **f32)
+                    check(lib.tx_pos_grad_partials(ptr(dout), ldg, F_, ptr(pos32), n, pd, ctx.vocab, cfg.p_next, cfg.next_seed,
+                                                   cfg.next_stream, ptr(partial), stream), "tx_pos_grad_partials")
+                    dtab = _reduce_partials(lib, partial, nb, ctx.vocab * pd).view(ctx.vocab, pd)
+                nbf = int(lib.tx_gat_fused_bwd_blocks(n, H))
+                partial = torch.empty(nbf * 2 * F_, **f32)
+                g_head_stride, g_scale = (D, 1.0) if cfg.hidden else (0, 1.0 / H)
+                check(lib.tx_gat_fused_bwd(ptr(dout), ldg, g_head_stride, g_scale, ptr(ctx.maskbits), 1 if cfg.p_next > 0.0 else 0,
+                                           cfg.act_slope, cfg.p_next if cfg.hidden else 0.0, ptr(ft), F_, ptr(alpha), ptr(alpha_d),
+                                           ptr(elog), ptr(al), ptr(ar), ptr(st.in_ptr), ptr(st.in_src), ptr(st.in_eid),
+                                           ptr(st.out_ptr), ptr(st.out_dst), ptr(st.out_slot), ptr(st.node_off), st.g, n, H, D,
+                                           cfg.neg_slope, cfg.p_attn, cfg.attn_seed, cfg.attn_stream, ptr(ds), ptr(da2), ptr(dft),
+                                           F_, ptr(partial), stream), "tx_gat_fused_bwd")
+                both = _reduce_partials(lib, partial, nbf, 2 * F_)
                 dal, dar = both[:F_].view(ctx.attn_shape), both[F_:].view(ctx.attn_shape)
+            else:
+                if cfg.hidden:
+                    if cfg.p_next > 0.0 or cfg.act_slope != 1.0 or need_tab:
+                        if cfg.p_next > 0.0 or cfg.act_slope != 1.0:
+                            dout = dout.clone()
+                            ldg = dout.stride(0) if n > 1 else dout.shape[1]
+                        partial = torch.empty(nb * ctx.vocab * pd, **f32) if need_tab else None
+                        check(lib.tx_epilogue_bwd(ptr(dout), ldg, ptr(out), ptr(pos32) if pd > 0 else None, n, F_,
+                                                  pd if need_tab else 0, ctx.vocab, cfg.act_slope, cfg.p_next, cfg.next_seed,
+                                                  cfg.next_stream, ptr(partial), stream), "tx_epilogue_bwd")
+                        if need_tab:
+                            dtab = _reduce_partials(lib, partial, nb, ctx.vocab * pd).view(ctx.vocab, pd)
+                    g, g_head_stride, g_scale = dout, D, 1.0
+                else:
+                    g, g_head_stride, g_scale = dout, 0, 1.0 / H
+                check(lib.tx_gat_aggregate_bwd_dst(ptr(g), ldg, g_head_stride, g_scale, ptr(ft), F_, ptr(alpha), ptr(elog),
+                                                   ptr(st.in_ptr), ptr(st.in_src), ptr(st.in_eid), n, H, D, cfg.neg_slope,
+                                                   cfg.p_attn, cfg.attn_seed, cfg.attn_stream, ptr(ds), ptr(da2), stream),
+                      "tx_gat_aggregate_bwd_dst")
+                da1 = torch.empty(n * H, **f32)
+                check(lib.tx_gat_aggregate_bwd_src(ptr(g), ldg, g_head_stride, g_scale, ptr(alpha_d), ptr(ds), ptr(da2), ptr(al),
+                                                   ptr(ar), ptr(st.out_ptr), ptr(st.out_dst), ptr(st.out_slot), n, H, D, ptr(da1),
+                                                   ptr(dft), F_, stream), "tx_gat_aggregate_bwd_src")
+                dal = dar = None
+                if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+                    partial = torch.empty(nb * 2 * F_, **f32)
+                    check(lib.tx_gat_attn_grad_partials(ptr(ft), F_, ptr(da1), ptr(da2), n, H, D, ptr(partial), stream),
+                          "tx_gat_attn_grad_partials")
+                    both = _reduce_partials(lib, partial, nb, 2 * F_)
+                    dal, dar = both[:F_].view(ctx.attn_shape), both[F_:].view(ctx.attn_shape)
             with timed_region("gemm_dw"):
                 dw = torch.mm(dft.t(), z[:, :K]) if ctx.needs_input_grad[1] else None
             dz = None
@@ -378,10 +417,11 @@ class Readout(Function):
         dw = None
         with torch.cuda.device(h.device):
             need_w = kind == _lib.TX_READOUT_WMEAN and ctx.needs_input_grad[1]
-            partial = torch.empty(st.g * 3, dtype=torch.float32, device=h.device) if need_w else None
+            nbr = int(lib.tx_readout_bwd_blocks(st.g))
+            partial = torch.empty(nbr * 3, dtype=torch.float32, device=h.device) if need_w else None
             check(lib.tx_readout_bwd(kind, ptr(dhg), dhg.stride(0) if st.g > 1 else dhg.shape[1], ptr(h),
                                      h.stride(0) if n > 1 else D, ptr(hg), hg.shape[1], ptr(pos32), ptr(w), ptr(st.node_off),
                                      st.g, D, ptr(dh), D, ptr(partial), current_stream()), "tx_readout_bwd")
             if need_w:
-                dw = _reduce_partials(lib, partial, st.g, 3).view(ctx.wshape)
+                dw = _reduce_partials(lib, partial, nbr, 3).view(ctx.wshape)
         return dh, dw, None, None, None

