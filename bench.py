@@ -298,14 +298,19 @@ def run_b200(args, rank, world, local_rank):
     step_prof_ms = sum(kern.values())
     rl = []
     for tag, H, W in (("L0", H0, W0), ("L1", H1, W1)):
-        t_f = avg("tx_gat_aggregate_fwd", tag)
-        if t_f > 0:
-            by = gaa_fwd_bytes(n_avg, e_avg, H, W)
-            rl.append({"kernel": f"tx_gat_aggregate_fwd[{tag}]", "ms": t_f, "bytes": by, "achieved": by / t_f / 1e6})
-        t_b = avg("tx_gat_aggregate_bwd_dst", tag) + avg("tx_gat_aggregate_bwd_src", tag)
-        if t_b > 0:
+        for fwd_names, label in ((("tx_gat_fused_fwd",), "tx_gat_fused_fwd"), (("tx_gat_node_logits", "tx_gat_aggregate_fwd"), "tx_gat_node_logits+aggregate_fwd")):
+            t_f = sum(avg(nm, tag) for nm in fwd_names)
+            if t_f > 0:
+                by = gaa_fwd_bytes(n_avg, e_avg, H, W)
+                rl.append({"kernel": f"{label}[{tag}]", "ms": t_f, "bytes": by, "achieved": by / t_f / 1e6})
+        for bwd_names, label in ((("tx_gat_fused_bwd",), "tx_gat_fused_bwd"),
+                                 (("tx_epilogue_bwd", "tx_gat_aggregate_bwd_dst", "tx_gat_aggregate_bwd_src", "tx_gat_attn_grad_partials"),
+                                  "tx_epilogue_bwd+aggregate_bwd_dst+src+attn_grad")):
+            if not avg(bwd_names[-1] if len(bwd_names) == 1 else "tx_gat_aggregate_bwd_dst", tag):
+                continue
+            t_b = sum(avg(nm, tag) for nm in bwd_names)
             by = gaa_bwd_bytes(n_avg, e_avg, H, W)
-            rl.append({"kernel": f"tx_gat_aggregate_bwd_dst+src[{tag}]", "ms": t_b, "bytes": by, "achieved": by / t_b / 1e6})
+            rl.append({"kernel": f"{label}[{tag}]", "ms": t_b, "bytes": by, "achieved": by / t_b / 1e6})
     for r in rl:
         r["frac"] = r["achieved"] / hbm_peak
     dom = max(rl, key=lambda r: r["ms"]) if rl else None

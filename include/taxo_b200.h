@@ -20,8 +20,9 @@
  *     order) and CSR by SOURCE (out_ptr[N+1], out_dst[E], out_slot[E]: out_slot = position of that edge in
  *     the destination-sorted order).  Per-edge arrays (alpha, elog, ...) are stored in destination-sorted
  *     order ("slots").
- *   - dropout: keep(seed, stream_id, index) is a counter-based Philox4x32-10 draw, reproducible in the
- *     backward pass and by tx_dropout_keep_mask; drop(x) = keep ? x / (1 - p) : 0 (torch.nn.Dropout
+ *   - dropout: keep(seed, stream_id, index) is a counter-based hash draw (16-bit uniform >= round(p * 65536);
+ *     tx_common.cuh), a pure function of its arguments: reproducible in the backward pass and by
+ *     tx_dropout_keep_mask; drop(x) = keep ? x / (1 - p) : 0 (torch.nn.Dropout
  *     semantics, reference model/model_zoo.py:57-64).  index = row * ld + col for feature matrices and
  *     eid * H + head for attention coefficients.
  */
@@ -226,6 +227,18 @@ int64_t tx_readout_bwd_blocks(int64_t n_graphs);
 int tx_readout_bwd(int32_t kind, const float* dhg, int64_t lddhg, const float* h, int64_t ldh, const float* hg,
                    int64_t ldhg, const int32_t* pos, const float* pos_weight, const int32_t* node_off,
                    int64_t n_graphs, int64_t dim, float* dh, int64_t lddh, float* dw_partial, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense projection on tcgen05 tensor cores with fp32-faithful accuracy (3xTF32 split, fp32 accumulation in TMEM):
+ *   C[m, n] = sum_k A[m, k] * B[n, k]          (A: [M, K] row-major, B: [N, K] row-major, C: [M, ldc])
+ * replaces self.fc(h) / torch.mm(h, W) and their autograd GEMMs (reference model/model_zoo.py:83,37), which the
+ * reference runs as cuBLAS/MKL fp32.  Operands are passed PRE-SPLIT: x = hi + lo with hi = rn_tf32(x) and
+ * lo = rn_tf32(x - hi) (tx_split_tf32), row pitch a multiple of 4 floats, 16-byte aligned.  Columns
+ * [N, round4(N)) of C are written as zeros when ldc allows (padded activations buffers).
+ * ------------------------------------------------------------------------------------------------ */
+int tx_split_tf32(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* hi, float* lo, int64_t ldo, void* stream);
+int tx_gemm_nt_tf32x3(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi, const float* b_lo, int64_t ldb,
+                      float* c, int64_t ldc, int64_t m, int64_t n, int64_t k, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Test / parity utility: materialise the keep-mask the kernels use (1 = keep) for n indices

@@ -72,6 +72,8 @@ _SIGNATURES = {
     "tx_gat_fused_bwd": [P, I64, I64, F32, P, c_int32, F32, F32, P, I64, P, P, P, P, P, P, P, P, P, P, P, P, I64, I64, I64, I64,
                          F32, F32, c_uint64, c_uint32, P, P, P, I64, P, P],
     "tx_pos_grad_partials": [P, I64, I64, P, I64, I64, I64, F32, c_uint64, c_uint32, P, P],
+    "tx_split_tf32": [P, I64, I64, I64, P, P, I64, P],
+    "tx_gemm_nt_tf32x3": [P, P, I64, P, P, I64, P, I64, I64, I64, I64, P],
 }
 _RESTYPES = {"tx_last_error": c_char_p, "tx_target_arch": c_char_p, "tx_row_blocks": c_int64, "tx_readout_bwd_blocks": c_int64,
              "tx_gat_fused_mask_words": c_int64, "tx_gat_fused_bwd_blocks": c_int64}

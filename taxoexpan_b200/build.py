@@ -58,7 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {src}")
-    link = [nvcc_path(), "-shared", "-o", LIB] + objs + ["-lcuda"]
+    link = [nvcc_path(), "-shared", "-o", LIB] + objs
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     if r.returncode:
         sys.stderr.write(r.stdout.decode())

@@ -32,38 +32,43 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 // ---------------------------------------------------------------------------------------------
-// Counter-based dropout (Philox4x32-10). One call yields the keep decision of 4 consecutive indices.
+// Counter-based dropout.  keep(seed, stream, index) is a pure function of its arguments (reproducible in the
+// backward pass, by tx_dropout_keep_mask and across kernels): one 32-bit mix of (index / 4, seed, stream) followed
+// by two independent avalanche finalisers yields four 16-bit uniforms, one per element of an aligned group of 4.
+// keep iff u16 >= round(p * 65536).  (~20 integer instructions per 4 elements: a Philox4x32-10 draw cost ~100 and
+// made the fused aggregate kernel issue-bound - profiles/r2.)
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
-  double t = (double)p * 4294967296.0;
-  if (t <= 0.0) return 0u;
-  if (t >= 4294967295.0) return 4294967295u;
+  double t = (double)p * 65536.0 + 0.5;
+  if (t <= 0.5) return 0u;
+  if (t >= 65535.0) return 65535u;
   return (uint32_t)t;
 }
 
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
-    const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
-    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-    k.x += W0;
-    k.y += W1;
-  }
-  return c;
+// returns {w.x: u16 of elements 0 (low half) and 1 (high half), w.y: elements 2 and 3} of group idx4
+__device__ __forceinline__ uint2 drop_words(uint64_t seed, uint32_t stream_id, uint64_t idx4) {
+  uint32_t h = ((uint32_t)idx4 * 0x9E3779B1u) ^ (uint32_t)seed;                  // bijective in the low index word
+  h ^= ((uint32_t)(idx4 >> 32) + stream_id * 0x85EBCA77u + (uint32_t)(seed >> 32)) * 0xC2B2AE3Du;
+  uint32_t a = h;
+  a ^= a >> 16; a *= 0x7FEB352Du; a ^= a >> 15; a *= 0x846CA68Bu; a ^= a >> 16;
+  uint32_t b = h + 0x9E3779B9u;
+  b ^= b >> 16; b *= 0x21F0AAADu; b ^= b >> 15; b *= 0x735A2D97u; b ^= b >> 15;
+  return make_uint2(a, b);
 }
 
-// random words of indices 4*idx4 .. 4*idx4+3
-__device__ __forceinline__ uint4 drop_words(uint64_t seed, uint32_t stream_id, uint64_t idx4) {
-  return philox4x32_10(make_uint4((uint32_t)idx4, (uint32_t)(idx4 >> 32), stream_id, 0u),
-                       make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+__device__ __forceinline__ void drop_keep4(uint64_t seed, uint32_t stream_id, uint64_t idx4, uint32_t thr, bool (&keep)[4]) {
+  const uint2 w = drop_words(seed, stream_id, idx4);
+  keep[0] = (w.x & 0xFFFFu) >= thr;
+  keep[1] = (w.x >> 16) >= thr;
+  keep[2] = (w.y & 0xFFFFu) >= thr;
+  keep[3] = (w.y >> 16) >= thr;
 }
 
 __device__ __forceinline__ bool drop_keep1(uint64_t seed, uint32_t stream_id, uint64_t idx, uint32_t thr) {
-  const uint4 w = drop_words(seed, stream_id, idx >> 2);
+  const uint2 w = drop_words(seed, stream_id, idx >> 2);
   const uint32_t sel = (uint32_t)(idx & 3);
-  const uint32_t r = sel == 0 ? w.x : (sel == 1 ? w.y : (sel == 2 ? w.z : w.w));
+  const uint32_t word = sel < 2 ? w.x : w.y;
+  const uint32_t r = (sel & 1) ? (word >> 16) : (word & 0xFFFFu);
   return r >= thr;
 }
 
@@ -121,11 +126,7 @@ template <int VEC>
 __device__ __forceinline__ void drop_keep_vec(uint64_t seed, uint32_t stream_id, uint64_t idx, uint32_t thr,
                                               bool (&keep)[VEC]) {
   if constexpr (VEC == 4) {
-    const uint4 w = drop_words(seed, stream_id, idx >> 2);
-    keep[0] = w.x >= thr;
-    keep[1] = w.y >= thr;
-    keep[2] = w.z >= thr;
-    keep[3] = w.w >= thr;
+    drop_keep4(seed, stream_id, idx >> 2, thr, keep);
   } else {
     keep[0] = drop_keep1(seed, stream_id, idx, thr);
   }

@@ -17,12 +17,13 @@
 //   d(z_next): the dropout / leaky-relu derivative factor is rebuilt from the bit-planes on load.
 //   No float atomics anywhere: d(attn) partials are reduced per CTA in a fixed order.
 #include <math.h>
+#include <stdlib.h>
 
 #include "tx_common.cuh"
 
 namespace tx {
 
-constexpr int kTileRows = 16;   // backward tile window (rows); tiles are graph-aligned
+constexpr int kTileRows = 16;   // default backward tile window (rows); tiles are graph-aligned (TAXO_BWD_TILE_ROWS overrides)
 constexpr int kMaxNV = 4;       // up to 4 float4 per lane per head row -> D' <= 512
 
 template <int NV>
@@ -32,6 +33,12 @@ __device__ __forceinline__ void load_row(const float* __restrict__ p, int lane, 
     const int c = (lane + 32 * t) * 4;
     v[t] = c < D ? __ldg(reinterpret_cast<const float4*>(p + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
+}
+
+// Bulk L2 prefetch of `bytes` (multiple of 16) starting at a 16-byte aligned global address (cp.async.bulk.prefetch, sm_90+):
+// pulls the rows a warp / CTA will touch NEXT into L2 so the demand loads later pay L2, not HBM, latency.
+__device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
 template <int NV>
@@ -72,14 +79,20 @@ struct FusedFwdParams {
   float neg_slope; float attn_inv_keep; uint32_t attn_thr; uint64_t attn_seed; uint32_t attn_stream;
   float* alpha; float* alpha_d; float* elog;
   float* out; int64_t ldo;
-  uint32_t* maskbits;      // [n, H, NV, 8] words: 4 sign planes (one per float4 component) + 4 keep planes; may be null
+  uint32_t* maskbits;      // [n, H, NV, 32] bytes (8 words per (row, head, t)): per lane 4 sign bits | 4 keep bits << 4; may be null
   // epilogue
   int hidden; float act_slope; const float* next_pos_table; const int32_t* pos; int pos_dim;
   float next_inv_keep; uint32_t next_thr; uint64_t next_seed; uint32_t next_stream;
 };
 
 template <int NV>
-__global__ void __launch_bounds__(256) gat_fused_fwd_kernel(const FusedFwdParams p) {
+__device__ __forceinline__ void scale_row(float sc, float4 (&y)[NV]) {
+#pragma unroll
+  for (int t = 0; t < NV; ++t) { y[t].x *= sc; y[t].y *= sc; y[t].z *= sc; y[t].w *= sc; }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256, 3) gat_fused_fwd_kernel(const FusedFwdParams p) {
   __shared__ float4 s_l[NV * 32];
   __shared__ float4 s_r[NV * 32];
   const int h = blockIdx.y;
@@ -94,69 +107,62 @@ __global__ void __launch_bounds__(256) gat_fused_fwd_kernel(const FusedFwdParams
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const bool attn_drop = p.attn_thr != 0;
+  const float* base = p.ft + (int64_t)h * D;
   for (int i = warp; i < p.n; i += nwarps) {
     const int beg = __ldg(p.in_ptr + i), end = __ldg(p.in_ptr + i + 1);
-    const float* base = p.ft + (int64_t)h * D;
-    float4 own[NV];
-    load_row<NV>(base + (int64_t)i * p.ldf, lane, D, own);
-    const float a2i = warp_sum(dot_row<NV>(own, s_r, lane));
-    // ---- pass 1: logits of the in-edges (a1 from the gathered rows), kept lane-distributed ----
-    for (int k = beg; k < end; ++k) {
-      const int j = __ldg(p.in_src + k);
-      float d;
-      if (j == i) {
-        d = dot_row<NV>(own, s_l, lane);
-      } else {
-        float4 fj[NV];
-        load_row<NV>(base + (int64_t)j * p.ldf, lane, D, fj);
-        d = dot_row<NV>(fj, s_l, lane);
-      }
-      float s = warp_sum(d) + a2i;
-      s = s > 0.f ? s : s * p.neg_slope;
-      if (lane == 0) p.elog[(int64_t)k * H + h] = s;
-    }
-    __syncwarp();
-    // ---- edge softmax, lane-parallel over the in-edges ----
-    float m = -INFINITY;
-    for (int c = beg; c < end; c += 32) {
-      const int k = c + lane;
-      if (k < end) m = fmaxf(m, p.elog[(int64_t)k * H + h]);
-    }
-    m = warp_max(m);
-    float l = 0.f;
-    for (int c = beg; c < end; c += 32) {
-      const int k = c + lane;
-      if (k < end) l += expf(p.elog[(int64_t)k * H + h] - m);
-    }
-    l = warp_sum(l);
-    // ---- pass 2: attention dropout + weighted aggregation ----
+    const int deg = end - beg;
+    if (lane == 0 && i + nwarps < p.n) prefetch_l2(base + (int64_t)(i + nwarps) * p.ldf, (uint32_t)D * 4u);
+    float4 cur[NV], nxt[NV];
+    int jn = deg > 0 ? __ldg(p.in_src + beg) : i;
+    load_row<NV>(base + (int64_t)i * p.ldf, lane, D, cur);          // own row: a2 = <ft_i, attn_r>
+    load_row<NV>(base + (int64_t)jn * p.ldf, lane, D, nxt);         // first neighbour row in flight
+    const float a2i = warp_sum(dot_row<NV>(cur, s_r, lane));
+    // ---- single pass over the in-edges: logits from the gathered rows + ONLINE edge softmax + aggregation ----
+    float m = -INFINITY, l = 0.f, s_mine = 0.f, kw_mine = 1.f;
     float4 acc[NV];
 #pragma unroll
     for (int t = 0; t < NV; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int c = beg; c < end; c += 32) {
-      const int k = c + lane;
-      float ad = 0.f;
-      if (k < end) {
-        const float a = expf(p.elog[(int64_t)k * H + h] - m) / l;
-        p.alpha[(int64_t)k * H + h] = a;
-        ad = a;
-        if (attn_drop) {
-          const bool keep = drop_keep1(p.attn_seed, p.attn_stream, (uint64_t)((int64_t)__ldg(p.in_eid + k) * H + h), p.attn_thr);
-          ad = keep ? a * p.attn_inv_keep : 0.f;
-          p.alpha_d[(int64_t)k * H + h] = ad;
-        }
+    for (int k = beg; k < end; ++k) {
+#pragma unroll
+      for (int t = 0; t < NV; ++t) cur[t] = nxt[t];
+      if (k + 1 < end) {
+        jn = __ldg(p.in_src + k + 1);
+        load_row<NV>(base + (int64_t)jn * p.ldf, lane, D, nxt);     // prefetch the next neighbour row
       }
-      const int cnt = min(32, end - c);
-      for (int q = 0; q < cnt; ++q) {
-        const float w = __shfl_sync(0xffffffffu, ad, q);
-        const int j = __ldg(p.in_src + c + q);
-        if (j == i) {
-          axpy_row<NV>(w, own, acc);
-        } else {
-          float4 fj[NV];
-          load_row<NV>(base + (int64_t)j * p.ldf, lane, D, fj);   // second touch: L1/L2 hit
-          axpy_row<NV>(w, fj, acc);
-        }
+      float s = warp_sum(dot_row<NV>(cur, s_l, lane)) + a2i;        // a1[src] + a2[dst]     (model_zoo.py:108)
+      s = s > 0.f ? s : s * p.neg_slope;
+      float kw = 1.f;
+      if (attn_drop)
+        kw = drop_keep1(p.attn_seed, p.attn_stream, (uint64_t)((int64_t)__ldg(p.in_eid + k) * H + h), p.attn_thr) ? p.attn_inv_keep : 0.f;
+      if (lane == ((k - beg) & 31)) { s_mine = s; kw_mine = kw; }
+      if (deg > 32 && lane == 0) p.elog[(int64_t)k * H + h] = s;     // rare: spill logits for the fix-up pass
+      const float m_new = fmaxf(m, s);
+      const float sc = expf(m - m_new);                              // 0 on the first edge (m = -inf)
+      const float e = expf(s - m_new);
+      l = fmaf(l, sc, e);
+      if (sc != 1.f) scale_row<NV>(sc, acc);                          // warp-uniform
+      axpy_row<NV>(e * kw, cur, acc);
+      m = m_new;
+    }
+    const float inv_l = deg > 0 ? 1.f / l : 0.f;
+    scale_row<NV>(inv_l, acc);
+    // ---- per-edge outputs for the backward pass (slot order) ----
+    if (deg <= 32) {
+      if (lane < deg) {
+        const int64_t o = (int64_t)(beg + lane) * H + h;
+        const float a = expf(s_mine - m) * inv_l;
+        p.elog[o] = s_mine;
+        p.alpha[o] = a;
+        if (attn_drop) p.alpha_d[o] = a * kw_mine;
+      }
+    } else {
+      __syncwarp();
+      for (int k = beg + lane; k < end; k += 32) {
+        const int64_t o = (int64_t)k * H + h;
+        const float a = expf(p.elog[o] - m) * inv_l;
+        p.alpha[o] = a;
+        if (attn_drop)
+          p.alpha_d[o] = drop_keep1(p.attn_seed, p.attn_stream, (uint64_t)((int64_t)__ldg(p.in_eid + k) * H + h), p.attn_thr) ? a * p.attn_inv_keep : 0.f;
       }
     }
     // ---- epilogue ----
@@ -177,26 +183,17 @@ __global__ void __launch_bounds__(256) gat_fused_fwd_kernel(const FusedFwdParams
           for (int u = 0; u < 4; ++u) v[u] = posv[u] ? v[u] : v[u] * p.act_slope;
         }
         if (p.next_thr && valid) {
-          const uint4 w = drop_words(p.next_seed, p.next_stream, (uint64_t)(idx_base + c) >> 2);
-          keep[0] = w.x >= p.next_thr; keep[1] = w.y >= p.next_thr; keep[2] = w.z >= p.next_thr; keep[3] = w.w >= p.next_thr;
+          drop_keep4(p.next_seed, p.next_stream, (uint64_t)(idx_base + c) >> 2, p.next_thr, keep);
 #pragma unroll
           for (int u = 0; u < 4; ++u) v[u] = keep[u] ? v[u] * p.next_inv_keep : 0.f;
         }
       }
       if (valid) *reinterpret_cast<float4*>(orow + c) = make_float4(v[0], v[1], v[2], v[3]);
-      if (p.maskbits) {
-        uint32_t words[8];
+      if (p.maskbits) {   // one byte per lane: sign bits (low nibble) + keep bits (high nibble) of its 4 elements
+        uint32_t code = 0;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          words[u] = __ballot_sync(0xffffffffu, valid && posv[u]);
-          words[4 + u] = __ballot_sync(0xffffffffu, valid && keep[u]);
-        }
-        if (lane < 8) {
-          uint32_t mine = words[0];
-#pragma unroll
-          for (int u = 1; u < 8; ++u) mine = lane == u ? words[u] : mine;
-          p.maskbits[(((int64_t)i * H + h) * NV + t) * 8 + lane] = mine;
-        }
+        for (int u = 0; u < 4; ++u) code |= ((posv[u] ? 1u : 0u) | (keep[u] ? 16u : 0u)) << u;
+        reinterpret_cast<uint8_t*>(p.maskbits)[(((int64_t)i * H + h) * NV + t) * 32 + lane] = (uint8_t)(valid ? code : 0u);
       }
     }
     // position-embedding append + zero padding (once per row: the warp of the last head)
@@ -227,7 +224,7 @@ struct FusedBwdParams {
   const int32_t* in_ptr; const int32_t* in_src; const int32_t* in_eid;
   const int32_t* out_ptr; const int32_t* out_dst; const int32_t* out_slot;
   const int32_t* node_off; int n_graphs;
-  int n; int H; int D;
+  int n; int H; int D; int tile_rows;
   float neg_slope; float attn_inv_keep; uint32_t attn_thr; uint64_t attn_seed; uint32_t attn_stream;
   float* ds; float* da2;
   float* dft; int64_t ldd;
@@ -243,15 +240,13 @@ __device__ __forceinline__ void load_g_row(const FusedBwdParams& p, int i, int h
     const int c = (lane + 32 * t) * 4;
     float4 x = c < p.D ? __ldg(reinterpret_cast<const float4*>(row + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.maskbits) {
-      const uint32_t* w = p.maskbits + (((int64_t)i * p.H + h) * NV + t) * 8;
-      const uint4 sp = __ldg(reinterpret_cast<const uint4*>(w));
-      uint4 kp = make_uint4(~0u, ~0u, ~0u, ~0u);
-      if (p.has_keep_plane) kp = __ldg(reinterpret_cast<const uint4*>(w + 4));
+      uint32_t code = __ldg(reinterpret_cast<const uint8_t*>(p.maskbits) + (((int64_t)i * p.H + h) * NV + t) * 32 + lane);
+      if (!p.has_keep_plane) code |= 0xF0u;
       const float on = p.next_inv_keep, neg = p.act_slope * p.next_inv_keep;
-      x.x *= ((kp.x >> lane) & 1u) ? (((sp.x >> lane) & 1u) ? on : neg) : 0.f;
-      x.y *= ((kp.y >> lane) & 1u) ? (((sp.y >> lane) & 1u) ? on : neg) : 0.f;
-      x.z *= ((kp.z >> lane) & 1u) ? (((sp.z >> lane) & 1u) ? on : neg) : 0.f;
-      x.w *= ((kp.w >> lane) & 1u) ? (((sp.w >> lane) & 1u) ? on : neg) : 0.f;
+      x.x *= (code & 16u) ? ((code & 1u) ? on : neg) : 0.f;
+      x.y *= (code & 32u) ? ((code & 2u) ? on : neg) : 0.f;
+      x.z *= (code & 64u) ? ((code & 4u) ? on : neg) : 0.f;
+      x.w *= (code & 128u) ? ((code & 8u) ? on : neg) : 0.f;
     }
     v[t] = x;
   }
@@ -266,11 +261,16 @@ __device__ __forceinline__ int lower_bound_i32(const int32_t* __restrict__ a, in
   return lo;
 }
 
+constexpr int kHeavyOut = 12;   // sources with more out-edges than this are processed by the whole CTA
+
+// dynamic smem: s_l, s_r [NV*32] float4 | s_acc [8][2][NV*32] float4 (per-warp d(attn) accumulators) | s_part [8][NV*32]
 template <int NV>
-__global__ void __launch_bounds__(256, 2) gat_fused_bwd_kernel(const FusedBwdParams p) {
-  __shared__ float4 s_red[8][2][NV * 32];   // also holds attn_l / attn_r in slots [0][0], [0][1] during the main loop
-  __shared__ float4 s_l[NV * 32];
-  __shared__ float4 s_r[NV * 32];
+__global__ void __launch_bounds__(256, 3) gat_fused_bwd_kernel(const FusedBwdParams p) {
+  extern __shared__ float4 smem_f4[];
+  float4* s_l = smem_f4;
+  float4* s_r = s_l + NV * 32;
+  float4* s_acc = s_r + NV * 32;            // [(w*2 + lr) * NV*32 + q]
+  float4* s_part = s_acc + 16 * NV * 32;    // [w * NV*32 + q]
   const int h = blockIdx.y;
   const int H = p.H, D = p.D;
   for (int t = threadIdx.x; t < NV * 32; t += blockDim.x) {
@@ -278,46 +278,85 @@ __global__ void __launch_bounds__(256, 2) gat_fused_bwd_kernel(const FusedBwdPar
     s_l[t] = c < D ? __ldg(reinterpret_cast<const float4*>(p.attn_l + (int64_t)h * D + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
     s_r[t] = c < D ? __ldg(reinterpret_cast<const float4*>(p.attn_r + (int64_t)h * D + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  for (int t = threadIdx.x; t < 16 * NV * 32; t += blockDim.x) s_acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const bool attn_drop = p.attn_thr != 0;
-  float4 accl[NV], accr[NV];
-#pragma unroll
-  for (int t = 0; t < NV; ++t) accl[t] = accr[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int n_tiles = (p.n + kTileRows - 1) / kTileRows;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int gb = lower_bound_i32(p.node_off, p.n_graphs + 1, tile * kTileRows);
-    const int ge = lower_bound_i32(p.node_off, p.n_graphs + 1, (tile + 1) * kTileRows);
-    const int r0 = gb <= p.n_graphs ? __ldg(p.node_off + min(gb, p.n_graphs)) : p.n;
-    const int r1 = __ldg(p.node_off + min(ge, p.n_graphs));
-    // ---------------- phase A: per destination ----------------
+  float4* my_accl = s_acc + (wid * 2 + 0) * NV * 32;
+  float4* my_accr = s_acc + (wid * 2 + 1) * NV * 32;
+  const float* fbase = p.ft + (int64_t)h * D;
+  const int n_tiles = (p.n + p.tile_rows - 1) / p.tile_rows;
+  __shared__ int s_bounds[2][2];
+  auto tile_bounds = [&](int tile, int slot) {   // graphs whose first row lies in [tile*R, (tile+1)*R)
+    if (tile < n_tiles) {
+      const int gb = lower_bound_i32(p.node_off, p.n_graphs + 1, tile * p.tile_rows);
+      const int ge = lower_bound_i32(p.node_off, p.n_graphs + 1, (tile + 1) * p.tile_rows);
+      s_bounds[slot][0] = __ldg(p.node_off + min(gb, p.n_graphs));
+      s_bounds[slot][1] = __ldg(p.node_off + min(ge, p.n_graphs));
+    } else {
+      s_bounds[slot][0] = s_bounds[slot][1] = 0;
+    }
+  };
+  if (threadIdx.x == 0) tile_bounds(blockIdx.x, 0);
+  __syncthreads();
+  int slot = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, slot ^= 1) {
+    const int r0 = s_bounds[slot][0], r1 = s_bounds[slot][1];
+    if (wid == 7) {   // bounds of this CTA's next tile + L2 prefetch of its g / ft rows while this tile is processed
+      if (lane == 0) tile_bounds(tile + gridDim.x, slot ^ 1);
+      __syncwarp();
+      const int q0 = s_bounds[slot ^ 1][0], q1 = s_bounds[slot ^ 1][1];
+      for (int r = q0 + lane; r < q1; r += 32) {
+        prefetch_l2(p.g + (int64_t)r * p.ldg + (int64_t)h * p.g_head_stride, (uint32_t)D * 4u);
+        prefetch_l2(fbase + (int64_t)r * p.ldf, (uint32_t)D * 4u);
+      }
+    }
+    // ---------------- phase A: per destination: d(alpha~) = <g_i, ft_j>, softmax / leaky-relu backward ----------------
     for (int i = r0 + wid; i < r1; i += 8) {
       const int beg = __ldg(p.in_ptr + i), end = __ldg(p.in_ptr + i + 1);
-      float4 gi[NV];
+      const int deg = end - beg;
+      float4 gi[NV], cur[NV], nxt[NV];
+      if (deg > 0) load_row<NV>(fbase + (int64_t)__ldg(p.in_src + beg) * p.ldf, lane, D, nxt);
       load_g_row<NV>(p, i, h, lane, gi);
-      const float* fbase = p.ft + (int64_t)h * D;
+      float d_mine = 0.f;
       for (int k = beg; k < end; ++k) {
-        float4 fj[NV];
-        load_row<NV>(fbase + (int64_t)__ldg(p.in_src + k) * p.ldf, lane, D, fj);
-        const float d = warp_sum(dot_rows<NV>(gi, fj)) * p.g_scale;
-        if (lane == 0) p.ds[(int64_t)k * H + h] = d;
+#pragma unroll
+        for (int t = 0; t < NV; ++t) cur[t] = nxt[t];
+        if (k + 1 < end) load_row<NV>(fbase + (int64_t)__ldg(p.in_src + k + 1) * p.ldf, lane, D, nxt);
+        const float d = warp_sum(dot_rows<NV>(gi, cur)) * p.g_scale;
+        if (lane == ((k - beg) & 31)) d_mine = d;
+        if (deg > 32 && lane == 0) p.ds[(int64_t)k * H + h] = d;
       }
-      __syncwarp();
-      float tsum = 0.f;
-      for (int c = beg; c < end; c += 32) {
-        const int k = c + lane;
-        if (k < end) {
+      if (deg <= 32) {
+        float da = 0.f, a = 0.f;
+        const int64_t o = (int64_t)(beg + lane) * H + h;
+        if (lane < deg) {
+          da = d_mine;
+          if (attn_drop)
+            da = drop_keep1(p.attn_seed, p.attn_stream, (uint64_t)((int64_t)__ldg(p.in_eid + beg + lane) * H + h), p.attn_thr) ? da * p.attn_inv_keep : 0.f;
+          a = __ldg(p.alpha + o);
+        }
+        const float tsum = warp_sum(a * da);
+        float dsv = 0.f;
+        if (lane < deg) {
+          const float de = a * (da - tsum);
+          dsv = __ldg(p.elog + o) > 0.f ? de : de * p.neg_slope;
+          p.ds[o] = dsv;
+        }
+        const float a2 = warp_sum(dsv);
+        if (lane == 0) p.da2[(int64_t)i * H + h] = a2;
+      } else {
+        __syncwarp();
+        float tsum = 0.f;
+        for (int k = beg + lane; k < end; k += 32) {
           float da = p.ds[(int64_t)k * H + h];
           if (attn_drop)
             da = drop_keep1(p.attn_seed, p.attn_stream, (uint64_t)((int64_t)__ldg(p.in_eid + k) * H + h), p.attn_thr) ? da * p.attn_inv_keep : 0.f;
           tsum = fmaf(__ldg(p.alpha + (int64_t)k * H + h), da, tsum);
         }
-      }
-      tsum = warp_sum(tsum);
-      float a2 = 0.f;
-      for (int c = beg; c < end; c += 32) {
-        const int k = c + lane;
-        if (k < end) {
+        tsum = warp_sum(tsum);
+        float a2 = 0.f;
+        for (int k = beg + lane; k < end; k += 32) {
           float da = p.ds[(int64_t)k * H + h];
           if (attn_drop)
             da = drop_keep1(p.attn_seed, p.attn_stream, (uint64_t)((int64_t)__ldg(p.in_eid + k) * H + h), p.attn_thr) ? da * p.attn_inv_keep : 0.f;
@@ -326,44 +365,42 @@ __global__ void __launch_bounds__(256, 2) gat_fused_bwd_kernel(const FusedBwdPar
           p.ds[(int64_t)k * H + h] = dsv;
           a2 += dsv;
         }
-      }
-      a2 = warp_sum(a2);
-      if (lane == 0) p.da2[(int64_t)i * H + h] = a2;
-      __syncwarp();
-      // d(attn_l) += ds_k * ft[src_k] ; d(attn_r) += da2_i * ft[i]
-      for (int k = beg; k < end; ++k) {
-        float4 fj[NV];
-        load_row<NV>(fbase + (int64_t)__ldg(p.in_src + k) * p.ldf, lane, D, fj);   // L1 hit
-        axpy_row<NV>(p.ds[(int64_t)k * H + h], fj, accl);
-      }
-      {
-        float4 fi[NV];
-        load_row<NV>(fbase + (int64_t)i * p.ldf, lane, D, fi);
-        axpy_row<NV>(a2, fi, accr);
+        a2 = warp_sum(a2);
+        if (lane == 0) p.da2[(int64_t)i * H + h] = a2;
       }
     }
     __syncthreads();   // ds / da2 of the whole tile are visible to the CTA
-    // ---------------- phase B: per source ----------------
+    // ---------------- phase B: per source (light rows: one warp each) ----------------
     for (int j = r0 + wid; j < r1; j += 8) {
       const int beg = __ldg(p.out_ptr + j), end = __ldg(p.out_ptr + j + 1);
+      if (end - beg > kHeavyOut) continue;
+      float4 cur[NV], nxt[NV];
+      if (beg < end) load_g_row<NV>(p, __ldg(p.out_dst + beg), h, lane, nxt);
       float d1 = 0.f;
-      for (int c = beg; c < end; c += 32) {
-        const int k = c + lane;
-        if (k < end) d1 += p.ds[(int64_t)__ldg(p.out_slot + k) * H + h];
-      }
+      if (beg + lane < end) d1 = p.ds[(int64_t)__ldg(p.out_slot + beg + lane) * H + h];
       d1 = warp_sum(d1);
       const float d2 = p.da2[(int64_t)j * H + h];
       float4 acc[NV];
+      {
+        float4 fj[NV];
+        load_row<NV>(fbase + (int64_t)j * p.ldf, lane, D, fj);   // L1/L2 hit: read by this CTA in phase A
 #pragma unroll
-      for (int t = 0; t < NV; ++t) {
-        const float4 l = s_l[lane + 32 * t], r = s_r[lane + 32 * t];
-        acc[t] = make_float4(fmaf(d1, l.x, d2 * r.x), fmaf(d1, l.y, d2 * r.y), fmaf(d1, l.z, d2 * r.z), fmaf(d1, l.w, d2 * r.w));
+        for (int t = 0; t < NV; ++t) {
+          const int q = lane + 32 * t;
+          float4 xl = my_accl[q], xr = my_accr[q];
+          xl.x = fmaf(d1, fj[t].x, xl.x); xl.y = fmaf(d1, fj[t].y, xl.y); xl.z = fmaf(d1, fj[t].z, xl.z); xl.w = fmaf(d1, fj[t].w, xl.w);
+          xr.x = fmaf(d2, fj[t].x, xr.x); xr.y = fmaf(d2, fj[t].y, xr.y); xr.z = fmaf(d2, fj[t].z, xr.z); xr.w = fmaf(d2, fj[t].w, xr.w);
+          my_accl[q] = xl; my_accr[q] = xr;
+          const float4 l = s_l[q], r = s_r[q];
+          acc[t] = make_float4(fmaf(d1, l.x, d2 * r.x), fmaf(d1, l.y, d2 * r.y), fmaf(d1, l.z, d2 * r.z), fmaf(d1, l.w, d2 * r.w));
+        }
       }
       for (int k = beg; k < end; ++k) {
+#pragma unroll
+        for (int t = 0; t < NV; ++t) cur[t] = nxt[t];
+        if (k + 1 < end) load_g_row<NV>(p, __ldg(p.out_dst + k + 1), h, lane, nxt);
         const float w = __ldg(p.alpha_d + (int64_t)__ldg(p.out_slot + k) * H + h) * p.g_scale;
-        float4 gv[NV];
-        load_g_row<NV>(p, __ldg(p.out_dst + k), h, lane, gv);
-        axpy_row<NV>(w, gv, acc);
+        axpy_row<NV>(w, cur, acc);
       }
       float* orow = p.dft + (int64_t)j * p.ldd + (int64_t)h * D;
 #pragma unroll
@@ -372,21 +409,68 @@ __global__ void __launch_bounds__(256, 2) gat_fused_bwd_kernel(const FusedBwdPar
         if (c < D) *reinterpret_cast<float4*>(orow + c) = acc[t];
       }
     }
-    __syncthreads();   // the next tile's phase A overwrites nothing this tile still reads, but keep tiles in lock-step
-  }
-  // ---- d(attn) partials: fixed-order reduction over the 8 warps of the CTA ----
+    // ---------------- phase B, heavy sources (e.g. the anchor of a large egonet): the whole CTA per row ----------------
+    for (int jb = r0; jb < r1; jb += 32) {
+     const int jl = jb + lane;
+     unsigned heavy = __ballot_sync(0xffffffffu, jl < r1 && (__ldg(p.out_ptr + min(jl, r1 - 1) + 1) - __ldg(p.out_ptr + min(jl, r1 - 1))) > kHeavyOut);
+     while (heavy) {            // identical in every warp of the CTA -> uniform control flow around the barriers below
+      const int j = jb + __ffs(heavy) - 1;
+      heavy &= heavy - 1;
+      const int beg = __ldg(p.out_ptr + j), end = __ldg(p.out_ptr + j + 1);
+      float4 acc[NV], cur[NV], nxt[NV];
 #pragma unroll
-  for (int t = 0; t < NV; ++t) {
-    s_red[wid][0][lane + 32 * t] = accl[t];
-    s_red[wid][1][lane + 32 * t] = accr[t];
+      for (int t = 0; t < NV; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      int k = beg + wid;
+      if (k < end) load_g_row<NV>(p, __ldg(p.out_dst + k), h, lane, nxt);
+      for (; k < end; k += 8) {
+#pragma unroll
+        for (int t = 0; t < NV; ++t) cur[t] = nxt[t];
+        if (k + 8 < end) load_g_row<NV>(p, __ldg(p.out_dst + k + 8), h, lane, nxt);
+        const float w = __ldg(p.alpha_d + (int64_t)__ldg(p.out_slot + k) * H + h) * p.g_scale;
+        axpy_row<NV>(w, cur, acc);
+      }
+#pragma unroll
+      for (int t = 0; t < NV; ++t) s_part[wid * NV * 32 + lane + 32 * t] = acc[t];
+      __syncthreads();
+      if (wid == 0) {
+        float d1 = 0.f;
+        for (int kk = beg + lane; kk < end; kk += 32) d1 += p.ds[(int64_t)__ldg(p.out_slot + kk) * H + h];
+        d1 = warp_sum(d1);
+        const float d2 = p.da2[(int64_t)j * H + h];
+        float4 fj[NV];
+        load_row<NV>(fbase + (int64_t)j * p.ldf, lane, D, fj);
+        float* orow = p.dft + (int64_t)j * p.ldd + (int64_t)h * D;
+#pragma unroll
+        for (int t = 0; t < NV; ++t) {
+          const int q = lane + 32 * t;
+          float4 xl = my_accl[q], xr = my_accr[q];
+          xl.x = fmaf(d1, fj[t].x, xl.x); xl.y = fmaf(d1, fj[t].y, xl.y); xl.z = fmaf(d1, fj[t].z, xl.z); xl.w = fmaf(d1, fj[t].w, xl.w);
+          xr.x = fmaf(d2, fj[t].x, xr.x); xr.y = fmaf(d2, fj[t].y, xr.y); xr.z = fmaf(d2, fj[t].z, xr.z); xr.w = fmaf(d2, fj[t].w, xr.w);
+          my_accl[q] = xl; my_accr[q] = xr;
+          const float4 l = s_l[q], r = s_r[q];
+          float4 o = make_float4(fmaf(d1, l.x, d2 * r.x), fmaf(d1, l.y, d2 * r.y), fmaf(d1, l.z, d2 * r.z), fmaf(d1, l.w, d2 * r.w));
+#pragma unroll
+          for (int w = 0; w < 8; ++w) {   // fixed order: deterministic
+            const float4 x = s_part[w * NV * 32 + q];
+            o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
+          }
+          const int c = q * 4;
+          if (c < D) *reinterpret_cast<float4*>(orow + c) = o;
+        }
+      }
+      __syncthreads();
+     }
+    }
+    __syncthreads();   // next tile: its bounds (written by warp 7) are visible, s_part is free
   }
+  // ---- d(attn) partials: fixed-order reduction over the 8 per-warp accumulators ----
   __syncthreads();
   for (int t = threadIdx.x; t < 2 * NV * 32; t += blockDim.x) {
     const int lr = t / (NV * 32), q = t % (NV * 32);
-    float4 s = s_red[0][lr][q];
+    float4 s = s_acc[(0 * 2 + lr) * NV * 32 + q];
 #pragma unroll
     for (int w = 1; w < 8; ++w) {
-      const float4 x = s_red[w][lr][q];
+      const float4 x = s_acc[(w * 2 + lr) * NV * 32 + q];
       s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
     }
     const int c = q * 4;
@@ -436,9 +520,19 @@ int64_t tx_gat_fused_mask_words(int64_t n_nodes, int64_t heads, int64_t dim) {
   return n_nodes * heads * nv * 8;
 }
 
+static int bwd_tile_rows() {
+  static int cached = 0;
+  if (!cached) {
+    const char* e = getenv("TAXO_BWD_TILE_ROWS");
+    int v = e ? atoi(e) : kTileRows;
+    cached = v >= 1 && v <= 4096 ? v : kTileRows;
+  }
+  return cached;
+}
+
 int64_t tx_gat_fused_bwd_blocks(int64_t n_nodes, int64_t heads) {
-  const int64_t tiles = (n_nodes + kTileRows - 1) / kTileRows;
-  int64_t gx = (2 * (int64_t)kNumSms + heads - 1) / heads;
+  const int64_t tiles = (n_nodes + bwd_tile_rows() - 1) / bwd_tile_rows();
+  int64_t gx = (3 * (int64_t)kNumSms + heads - 1) / heads;
   if (gx > tiles) gx = tiles;
   return gx < 1 ? 1 : gx;
 }
@@ -468,7 +562,7 @@ int tx_gat_fused_fwd(const float* ft, int64_t ldf, const float* attn_l, const fl
   p.pos_dim = (int)epi->pos_dim; p.next_inv_keep = 1.f / (1.f - epi->p_drop); p.next_thr = drop_threshold(epi->p_drop);
   p.next_seed = epi->seed; p.next_stream = epi->stream_id;
   const int nv = (int)((dim + 127) / 128);
-  int gx = grid_for_warps(n_nodes, 8, 8);
+  int gx = grid_for_warps(n_nodes, 8, 6);
   gx = (gx + (int)heads - 1) / (int)heads;
   if (gx < 1) gx = 1;
   dim3 grid(gx, (unsigned)heads);
@@ -507,14 +601,31 @@ int tx_gat_fused_bwd(const float* g, int64_t ldg, int64_t g_head_stride, float g
   p.node_off = node_off; p.n_graphs = (int)n_graphs; p.n = (int)n_nodes; p.H = (int)heads; p.D = (int)dim;
   p.neg_slope = neg_slope; p.attn_inv_keep = 1.f / (1.f - p_attn); p.attn_thr = drop_threshold(p_attn); p.attn_seed = attn_seed;
   p.attn_stream = attn_stream_id; p.ds = ds; p.da2 = da2; p.dft = dft; p.ldd = ldd; p.dattn_partial = dattn_partial;
+  p.tile_rows = bwd_tile_rows();
   const int nv = (int)((dim + 127) / 128);
   dim3 grid((unsigned)tx_gat_fused_bwd_blocks(n_nodes, heads), (unsigned)heads);
   cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (size_t)(2 + 16 + 8) * nv * 32 * sizeof(float4);
+  static bool attr_set[kMaxNV + 1] = {false, false, false, false, false};
+  if (!attr_set[nv]) {
+    cudaError_t e = cudaSuccess;
+    switch (nv) {
+      case 1: e = cudaFuncSetAttribute(gat_fused_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); break;
+      case 2: e = cudaFuncSetAttribute(gat_fused_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); break;
+      case 3: e = cudaFuncSetAttribute(gat_fused_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); break;
+      default: e = cudaFuncSetAttribute(gat_fused_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); break;
+    }
+    if (e != cudaSuccess) {
+      set_error("gat_fused_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return TX_ERR_CUDA;
+    }
+    attr_set[nv] = true;
+  }
   switch (nv) {
-    case 1: gat_fused_bwd_kernel<1><<<grid, 256, 0, st>>>(p); break;
-    case 2: gat_fused_bwd_kernel<2><<<grid, 256, 0, st>>>(p); break;
-    case 3: gat_fused_bwd_kernel<3><<<grid, 256, 0, st>>>(p); break;
-    default: gat_fused_bwd_kernel<4><<<grid, 256, 0, st>>>(p); break;
+    case 1: gat_fused_bwd_kernel<1><<<grid, 256, smem, st>>>(p); break;
+    case 2: gat_fused_bwd_kernel<2><<<grid, 256, smem, st>>>(p); break;
+    case 3: gat_fused_bwd_kernel<3><<<grid, 256, smem, st>>>(p); break;
+    default: gat_fused_bwd_kernel<4><<<grid, 256, smem, st>>>(p); break;
   }
   TX_LAUNCH_CHECK("tx_gat_fused_bwd");
   return TX_OK;

@@ -102,11 +102,10 @@ __global__ void concat_pos_dropout_fwd_kernel(const float* __restrict__ x, int64
       v[u] = val;
     }
     if (thr) {
-      const uint4 w = drop_words(seed, stream_id, (uint64_t)(((int64_t)i * ldz + c0) >> 2));
-      v[0] = w.x >= thr ? v[0] * inv_keep : 0.f;
-      v[1] = w.y >= thr ? v[1] * inv_keep : 0.f;
-      v[2] = w.z >= thr ? v[2] * inv_keep : 0.f;
-      v[3] = w.w >= thr ? v[3] * inv_keep : 0.f;
+      bool keep[4];
+      drop_keep4(seed, stream_id, (uint64_t)(((int64_t)i * ldz + c0) >> 2), thr, keep);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = keep[u] ? v[u] * inv_keep : 0.f;
     }
     *reinterpret_cast<float4*>(z + (int64_t)i * ldz + c0) = make_float4(v[0], v[1], v[2], v[3]);
   }
@@ -136,13 +135,12 @@ __global__ void __launch_bounds__(256) epilogue_bwd_kernel(float* __restrict__ d
         const float4 zz = __ldg(reinterpret_cast<const float4*>(z + (int64_t)i * ldz + c0));
         zv[0] = zz.x; zv[1] = zz.y; zv[2] = zz.z; zv[3] = zz.w;
       }
-      uint4 w = make_uint4(~0u, ~0u, ~0u, ~0u);
-      if (thr) w = drop_words(seed, stream_id, (uint64_t)(((int64_t)i * ldz + c0) >> 2));
-      const uint32_t wv[4] = {w.x, w.y, w.z, w.w};
+      bool keep[4] = {true, true, true, true};
+      if (thr) drop_keep4(seed, stream_id, (uint64_t)(((int64_t)i * ldz + c0) >> 2), thr, keep);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         if (c0 + u < k_in) {
-          float f = wv[u] >= thr ? inv_keep : 0.f;
+          float f = keep[u] ? inv_keep : 0.f;
           if (act && !(zv[u] > 0.f)) f *= slope;
           gv[u] *= f;
         }

@@ -46,10 +46,68 @@ def _rowmajor(t: torch.Tensor) -> torch.Tensor:
 FUSED_ENABLED = os.environ.get("TAXO_DISABLE_FUSED", "") == ""
 
 
-def use_fused(lib, heads: int, dim: int, mean_heads: int) -> bool:
+FUSED_MAX_GRAPH_NODES = 2048
+
+
+def use_fused(lib, heads: int, dim: int, mean_heads: int, st=None) -> bool:
     """Fused single-kernel GAT forward/backward when the shape qualifies (dim % 4 == 0, dim <= 512, heads == 1 for the
-    head-mean output layer); otherwise the general-CSR kernels. TAXO_DISABLE_FUSED=1 forces the general path (tests)."""
+    head-mean output layer) and no graph of the batch is huge (the backward kernel gives one CTA per tile of whole
+    graphs); otherwise the general-CSR kernels. TAXO_DISABLE_FUSED=1 forces the general path (tests)."""
+    if st is not None and getattr(st, "max_nodes", 0) > FUSED_MAX_GRAPH_NODES:
+        return False
     return FUSED_ENABLED and bool(lib.tx_gat_fused_supported(heads, dim, mean_heads))
+
+
+GEMM_BACKEND = os.environ.get("TAXO_GEMM", "cublas")    # "cublas" (torch.mm fp32) | "tf32x3" (tcgen05 kernel of tx_gemm.cu)
+
+
+def split_tf32(x: torch.Tensor, cols: int = None):
+    """x [rows, >=cols] -> (hi, lo) padded [rows, round4(cols)] TF32-representable parts with x = hi + lo (+ 2^-22 rel.)."""
+    lib = _lib.load()
+    x = _rowmajor(x)
+    rows = x.shape[0]
+    cols = x.shape[1] if cols is None else cols
+    ldo = round4(cols)
+    hi = torch.empty((rows, ldo), dtype=torch.float32, device=x.device)
+    lo = torch.empty((rows, ldo), dtype=torch.float32, device=x.device)
+    check(lib.tx_split_tf32(ptr(x), x.stride(0) if rows > 1 else x.shape[1], rows, cols, ptr(hi), ptr(lo), ldo, current_stream()),
+          "tx_split_tf32")
+    return hi, lo
+
+
+def gemm_nt(a: torch.Tensor, k: int, b: torch.Tensor, out: torch.Tensor = None, n_out: int = None) -> torch.Tensor:
+    """C = a[:, :k] @ b[:, :k]^T in fp32-faithful precision.  a: [M, >=k], b: [N, >=k] row-major.
+    cublas backend: torch.mm (fp32 SIMT).  tf32x3 backend: split + tcgen05 3xTF32 kernel.
+    `out` (optional) is a [M, ldc] buffer whose first N columns receive the result."""
+    m, n = a.shape[0], b.shape[0]
+    if GEMM_BACKEND != "tf32x3" or m == 0:
+        if out is None:
+            return torch.mm(a[:, :k], b[:, :k].t())
+        torch.mm(a[:, :k], b[:, :k].t(), out=out[:, :n])
+        return out
+    lib = _lib.load()
+    a_hi, a_lo = split_tf32(a, k)
+    b_hi, b_lo = split_tf32(b, k)
+    if out is None:
+        out = torch.empty((m, round4(n)), dtype=torch.float32, device=a.device)
+    ldc = out.stride(0) if m > 1 else out.shape[1]
+    check(lib.tx_gemm_nt_tf32x3(ptr(a_hi), ptr(a_lo), a_hi.shape[1], ptr(b_hi), ptr(b_lo), b_hi.shape[1], ptr(out), ldc, m, n, k,
+                                current_stream()), "tx_gemm_nt_tf32x3")
+    return out if out.shape[1] == n else out[:, :n]
+
+
+def _gemm_dz(dy: torch.Tensor, f: int, w_kf: torch.Tensor, c0: int, k: int, ldz: int) -> torch.Tensor:
+    """d(z)[:, c0a:k] = dy[:, :f] @ w_kf[c0a:k, :f]^T into a fresh padded [n, ldz] buffer (c0a = c0 rounded down to a
+    multiple of 4 so the output pointer stays 16-byte aligned; columns < c0a are not needed by the caller and stay
+    uninitialised; padding columns >= k are zero)."""
+    n = dy.shape[0]
+    c0a = (min(c0, k) // 4) * 4
+    dz = torch.empty((n, ldz), dtype=torch.float32, device=dy.device)
+    if k > c0a:
+        gemm_nt(dy, f, w_kf[c0a:k], out=dz[:, c0a:])
+    if GEMM_BACKEND != "tf32x3" and ldz > k:
+        dz[:, k:].zero_()
+    return dz
 
 
 def new_seed() -> int:
@@ -155,9 +213,8 @@ class GatLayer(Function):
         with torch.cuda.device(dev):
             stream = current_stream()
             Stats.tag = cfg.tag
-            zk = z[:, :K]
             with timed_region("gemm_fwd"):
-                ft = torch.mm(zk, weight.t())                              # model_zoo.py:83 (cuBLAS fp32)
+                ft = gemm_nt(z, K, weight)                                 # ft = fc(h), model_zoo.py:83
             al = attn_l.reshape(-1).contiguous()
             ar = attn_r.reshape(-1).contiguous()
             alpha = torch.empty(st.e * H, **f32)
@@ -174,7 +231,7 @@ class GatLayer(Function):
             epi = GatEpilogue(mean_heads=0 if cfg.hidden else 1, act_slope=cfg.act_slope, next_pos_table=ptr(tab),
                               pos=ptr(pos32) if pd > 0 else None, pos_dim=pd, p_drop=cfg.p_next if cfg.hidden else 0.0,
                               seed=cfg.next_seed, stream_id=cfg.next_stream)
-            fused = use_fused(lib, H, D, 0 if cfg.hidden else 1)
+            fused = use_fused(lib, H, D, 0 if cfg.hidden else 1, st)
             maskbits = None
             if fused:
                 # ONE kernel: logits from the gathered rows, edge softmax, dropout, aggregation, next-layer epilogue
@@ -273,14 +330,7 @@ class GatLayer(Function):
             if ctx.needs_input_grad[0]:
                 c0 = min(cfg.dz_from, K)
                 with timed_region("gemm_dz"):
-                    if ldz == K and c0 == 0:
-                        dz = torch.mm(dft, weight)
-                    else:
-                        dz = torch.empty((n, ldz), **f32)
-                        if K > c0:
-                            torch.mm(dft, weight[:, c0:K], out=dz[:, c0:K])
-                        if ldz > K:
-                            dz[:, K:].zero_()
+                    dz = _gemm_dz(dft, F_, weight.t(), c0, K, ldz)
         return dz, dw, dal, dar, dtab, None, None, None
 
 
@@ -313,7 +363,7 @@ class GcnLayer(Function):
             stream = current_stream()
             Stats.tag = cfg.tag
             with timed_region("gemm_fwd"):
-                y = torch.mm(z[:, :K], weight)                             # model_zoo.py:37
+                y = gemm_nt(z, K, weight.t())                              # torch.mm(h, W), model_zoo.py:37
             norm = st.gcn_norm()
             pd = 0 if next_pos_table is None else int(next_pos_table.shape[1])
             tab = None if next_pos_table is None else next_pos_table.contiguous()
@@ -372,14 +422,7 @@ class GcnLayer(Function):
             if ctx.needs_input_grad[0]:
                 c0 = min(cfg.dz_from, K)
                 with timed_region("gemm_dz"):
-                    if ldz == K and c0 == 0:
-                        dz = torch.mm(dy, weight.t())
-                    else:
-                        dz = torch.empty((n, ldz), **f32)
-                        if K > c0:
-                            torch.mm(dy, weight[c0:K, :].t(), out=dz[:, c0:K])
-                        if ldz > K:
-                            dz[:, K:].zero_()
+                    dz = _gemm_dz(dy, D, weight, c0, K, ldz)
         return dz, dw, db, dtab, None, None, None
 
 

@@ -1,0 +1,60 @@
+"""GPU: the tcgen05 3xTF32 GEMM (tx_gemm_nt_tf32x3) against an fp64 product; it must be as accurate as fp32 SIMT."""
+import numpy as np
+import pytest
+import torch
+
+from taxoexpan_b200 import functional as txf
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(m, n, k, seed, scale_rows=True):
+    g = torch.Generator().manual_seed(seed)
+    a = torch.randn(m, k, generator=g)
+    b = torch.randn(n, k, generator=g) / np.sqrt(k)
+    if scale_rows:
+        a = torch.nn.functional.normalize(a, dim=1)
+    return a, b
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 64, 32), (128, 256, 64), (300, 500, 2050), (1000, 2000, 300), (257, 50, 2000),
+                                   (4099, 2052, 500), (64, 8, 40), (129, 129, 33)])
+def test_tf32x3_gemm_matches_fp64(m, n, k, monkeypatch):
+    monkeypatch.setattr(txf, "GEMM_BACKEND", "tf32x3")
+    dev = torch.device("cuda", 0)
+    a, b = _case(m, n, k, seed=m + n + k)
+    ref = a.double() @ b.double().t()
+    ld = txf.round4(k)
+    a_dev = torch.zeros(m, ld, device=dev)
+    a_dev[:, :k] = a.to(dev)
+    got = txf.gemm_nt(a_dev, k, b.to(dev)).cpu().double()
+    assert got.shape == (m, n)
+    cublas = (a.to(dev) @ b.to(dev).t()).cpu().double()
+    err = float((got - ref).abs().max())
+    err_cublas = float((cublas - ref).abs().max())
+    scale = float(ref.abs().max())
+    print(f"[{m}x{n}x{k}] max|err| tf32x3 {err:.3e}  cublas-fp32 {err_cublas:.3e}  max|ref| {scale:.3f}")
+    assert err <= max(4.0 * err_cublas, 2e-6 * max(scale, 1.0)), (err, err_cublas)
+
+
+def test_tf32x3_gemm_writes_padded_output_and_tails(monkeypatch):
+    monkeypatch.setattr(txf, "GEMM_BACKEND", "tf32x3")
+    dev = torch.device("cuda", 0)
+    m, n, k = 333, 2050, 500
+    a, b = _case(m, n, k, seed=7)
+    out = torch.full((m, 2052), 7.0, device=dev)
+    res = txf.gemm_nt(a.to(dev), k, b.to(dev), out=out)
+    ref = a.double() @ b.double().t()
+    assert float((out[:, :n].cpu().double() - ref).abs().max()) < 5e-6
+    assert float(out[:, n:].abs().max()) == 0.0            # padding columns are written as zeros
+    assert res.data_ptr() == out.data_ptr()
+
+
+def test_split_is_exact_to_22_bits():
+    dev = torch.device("cuda", 0)
+    x = torch.randn(257, 301, device=dev) * 3
+    hi, lo = txf.split_tf32(x)
+    assert hi.shape == (257, 304) and float(hi[:, 301:].abs().max()) == 0.0
+    rel = ((hi[:, :301] + lo[:, :301] - x).abs() / x.abs().clamp_min(1e-30)).max()
+    assert float(rel) < 2.0 ** -21
+    assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0 and int((lo.view(torch.int32) & 0x1FFF).abs().max()) == 0

@@ -243,7 +243,7 @@ def test_general_graph_gat_and_gcn_layers_match_oracle():
     n, e, d = 300, 1500, 24
     src = torch.from_numpy(rng.integers(0, n, e))
     dst = torch.from_numpy(rng.integers(0, 200, e))
-    og = orc.OracleGraph(n, src, dst, torch.zeros(n, dtype=torch.int64), [100, 200], [0, 0])
+    og = orc.OracleGraph(n, src, dst, torch.zeros(n, dtype=torch.int64), [n], [e])    # ONE graph: edges may go anywhere
     x = torch.from_numpy(tx.synth.unit_rows(n, d, seed=5))
     for pm in ("GAT", "GCN"):
         cfg = orc.OracleConfig(propagation_method=pm, readout_method="MR", matching_method="BIM", in_dim=d, hidden_dim=16,
@@ -258,7 +258,6 @@ def test_general_graph_gat_and_gcn_layers_match_oracle():
         g = tx.DGLGraph()
         g.add_nodes(n)
         g.add_edges(src, dst)
-        g.batch_num_nodes = [100, 200]
         hc = x.to(dev()).requires_grad_(True)
         out = model.graph_propagate(g, hc)
         (out * w.to(dev())).sum().backward()
@@ -326,4 +325,4 @@ def test_full_size_properties_magcs_batch256():
     graph.ndata["h"] = torch.ones(n, 8, device=dev()) * 3.0
     pos = graph.host_pos()
     hg = model.readout(graph, pos)
-    assert float((hg - 3.0).abs().max()) < 1e-6
+    assert float((hg.detach() - 3.0).abs().max()) < 1e-5
