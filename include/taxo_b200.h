@@ -237,6 +237,14 @@ int tx_readout_bwd(int32_t kind, const float* dhg, int64_t lddhg, const float* h
  * [N, round4(N)) of C are written as zeros when ldc allows (padded activations buffers).
  * ------------------------------------------------------------------------------------------------ */
 int tx_split_tf32(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* hi, float* lo, int64_t ldo, void* stream);
+/* Weight gradient form: C[m, n] = sum_r A[r, m] * B[r, n]  (A: [R, M], B: [R, N] row-major, reduction over the R rows =
+ * nodes; dW = dft^T . z, the autograd GEMM of model_zoo.py:83,37).  The reduction is split over `splits`
+ * (tx_gemm_tn_splits) CTAs per output tile; split s writes its partial [M, ldc] at c_partial + s * split_stride; sum them
+ * with tx_reduce_partials (fixed order, deterministic). */
+int64_t tx_gemm_tn_splits(int64_t m, int64_t n, int64_t r);
+int tx_gemm_tn_tf32x3(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi, const float* b_lo, int64_t ldb,
+                      float* c_partial, int64_t ldc, int64_t split_stride, int64_t m, int64_t n, int64_t r, int64_t splits,
+                      void* stream);
 int tx_gemm_nt_tf32x3(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi, const float* b_lo, int64_t ldb,
                       float* c, int64_t ldc, int64_t m, int64_t n, int64_t k, void* stream);
 

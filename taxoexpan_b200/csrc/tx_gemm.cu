@@ -73,20 +73,65 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       : "memory");
 }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1)
-gemm_nt_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-                      const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                      float* __restrict__ C, int64_t ldc, int M, int n_store, int num_k_blocks) {
+// MN-major operands (reduction index slow in memory).  For 32-bit (tf32) MN-major operands the tensor core accepts ONE
+// shared-memory layout: SWIZZLE_128B_BASE32B (CUTLASS sm100_smem_selector: "for mn-major tf32 operands, SW128_32B is the
+// only available smem layout"; UMMA::LayoutType 1, Swizzle<2,5,2>): 128-byte rows of 32 consecutive MN elements, atoms
+// of 4 k-rows (512 B) whose 32-byte chunks are XOR-permuted by the row index - exactly what a {32 cols, kBK rows} TMA box
+// with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B writes.  Canonical form ((4,8,m),(4,k)) : ((1,4,LBO),(32,SBO)) in floats:
+//   LBO = bytes between consecutive 32-float MN blocks (one TMA box = kBK * 128 B), SBO = bytes between 4-row k groups (512).
+__host__ __device__ __forceinline__ uint64_t umma_desc_mn_bits(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  return ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
+}
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr, uint64_t bits) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | bits;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+constexpr int kChunk = 2;        // k-blocks accumulated inside the tensor core before promotion to fp32 registers
+constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 per TMEM lane quadrant)
+
+// C[M, N] (+ split offset) = sum_k A . B with 3xTF32 products and CHUNKED PROMOTION:
+//   the tensor core adds each MMA into its fp32 TMEM accumulator with truncation (measured: ~0.5 ulp lost per MMA, a
+//   relative bias of ~2e-8 x #MMAs, 1.5e-5 at K = 2050), so the accumulator is drained every kChunk k-blocks
+//   (24 MMAs) into fp32 REGISTERS of the epilogue warps (round-to-nearest adds) while the MMA warp fills the other
+//   TMEM buffer.  2 x BN columns of TMEM, double buffered.
+// TN = false: A [M, K], B [N, K] row-major (K-major operands): y = z W^T, dz = dy W.
+// TN = true : A [R, M], B [R, N] row-major (MN-major operands, reduction over rows): dW = dy^T z; grid.z = split index.
+template <int BN, int STAGES, bool TN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                   const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                   float* __restrict__ C, int64_t ldc, int64_t split_stride, int M, int n_store, int k_blocks_total,
+                   int k_blocks_per_split, uint64_t mn_desc_bits) {
   constexpr int B_BYTES = BN * kBK * 4;
   constexpr int STAGE_BYTES = 2 * kABytes + 2 * B_BYTES;
+  constexpr int BOX_BYTES = kBK * 128;       // TN: one {32 cols, kBK rows} box
+  constexpr int HALF = BN / 2;               // columns owned by one epilogue warp
+  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);   // full[STAGES], empty[STAGES], acc_full
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);   // full[S], empty[S], tfull[2], tempty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), accfull = smem_u32(bars + 2 * STAGES);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
+  const uint32_t tfull0 = smem_u32(bars + 2 * STAGES), tempty0 = smem_u32(bars + 2 * STAGES + 2);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
@@ -97,86 +142,123 @@ gemm_nt_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
     }
-    mbar_init(accfull, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull0 + 8 * b, 1);
+      mbar_init(tempty0 + 8 * b, 8);           // one arrive per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {   // one warp allocates the accumulator columns (power of two >= 32)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
+  if (warp == 1) {   // one warp allocates both accumulator buffers (power of two >= 32 columns)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem_acc = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * BN;
+  const int kb0 = blockIdx.z * k_blocks_per_split;
+  const int nkb = max(0, min(k_blocks_per_split, k_blocks_total - kb0));
+  const int n_chunks = (nkb + kChunk - 1) / kChunk;
 
   if (warp == 0) {
     if (lane == 0) {   // ===== TMA producer =====
-      for (int kb = 0; kb < num_k_blocks; ++kb) {
+      for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(empty0 + 8 * s, ph ^ 1);                     // slot released by the MMA warp
         const uint32_t full = full0 + 8 * s;
         mbar_expect_tx(full, STAGE_BYTES);
         const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
-        tma_load_2d(base, &map_a_hi, full, kb * kBK, m0);
-        tma_load_2d(base + kABytes, &map_a_lo, full, kb * kBK, m0);
-        tma_load_2d(base + 2 * kABytes, &map_b_hi, full, kb * kBK, n0);
-        tma_load_2d(base + 2 * kABytes + B_BYTES, &map_b_lo, full, kb * kBK, n0);
+        const int kk = (kb0 + kb) * kBK;
+        if constexpr (!TN) {
+          tma_load_2d(base, &map_a_hi, full, kk, m0);
+          tma_load_2d(base + kABytes, &map_a_lo, full, kk, m0);
+          tma_load_2d(base + 2 * kABytes, &map_b_hi, full, kk, n0);
+          tma_load_2d(base + 2 * kABytes + B_BYTES, &map_b_lo, full, kk, n0);
+        } else {
+#pragma unroll
+          for (int b = 0; b < kBM / 32; ++b) {
+            tma_load_2d(base + b * BOX_BYTES, &map_a_hi, full, m0 + 32 * b, kk);
+            tma_load_2d(base + kABytes + b * BOX_BYTES, &map_a_lo, full, m0 + 32 * b, kk);
+          }
+#pragma unroll
+          for (int b = 0; b < BN / 32; ++b) {
+            tma_load_2d(base + 2 * kABytes + b * BOX_BYTES, &map_b_hi, full, n0 + 32 * b, kk);
+            tma_load_2d(base + 2 * kABytes + B_BYTES + b * BOX_BYTES, &map_b_lo, full, n0 + 32 * b, kk);
+          }
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {   // ===== MMA issuer =====
       // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6) = 1, a/b_format TF32 [7,10),[10,13) = 2,
-      // a/b major K (0), n_dim [17,23) = N >> 3, m_dim [24,29) = M >> 4
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
-      for (int kb = 0; kb < num_k_blocks; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(full0 + 8 * s, ph);                          // TMA bytes have landed
+      // a_major [15], b_major [16] (0 = K-major, 1 = MN-major), n_dim [17,23) = N >> 3, m_dim [24,29) = M >> 4
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (TN ? ((1u << 15) | (1u << 16)) : 0u) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        const int buf = ch & 1;
+        mbar_wait(tempty0 + 8 * buf, ((ch >> 1) & 1) ^ 1);     // epilogue has drained this accumulator buffer
         tcgen05_fence_after();
-        const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
-        const uint64_t a_hi = umma_desc_k_sw128(base), a_lo = umma_desc_k_sw128(base + kABytes);
-        const uint64_t b_hi = umma_desc_k_sw128(base + 2 * kABytes), b_lo = umma_desc_k_sw128(base + 2 * kABytes + B_BYTES);
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
+        const int kb_end = min(nkb, (ch + 1) * kChunk);
+        for (int kb = ch * kChunk; kb < kb_end; ++kb) {
+          const int s = kb % STAGES;
+          const uint32_t ph = (kb / STAGES) & 1;
+          mbar_wait(full0 + 8 * s, ph);                        // TMA bytes have landed
+          tcgen05_fence_after();
+          const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+          uint64_t a_hi, a_lo, b_hi, b_lo;
+          if constexpr (!TN) {
+            a_hi = umma_desc_k_sw128(base); a_lo = umma_desc_k_sw128(base + kABytes);
+            b_hi = umma_desc_k_sw128(base + 2 * kABytes); b_lo = umma_desc_k_sw128(base + 2 * kABytes + B_BYTES);
+          } else {
+            a_hi = umma_desc_mn(base, mn_desc_bits); a_lo = umma_desc_mn(base + kABytes, mn_desc_bits);
+            b_hi = umma_desc_mn(base + 2 * kABytes, mn_desc_bits); b_lo = umma_desc_mn(base + 2 * kABytes + B_BYTES, mn_desc_bits);
+          }
 #pragma unroll
-        for (int k = 0; k < kBK / 8; ++k) {                    // UMMA_K = 8 tf32 = 32 bytes: advance the start address by 2 (x16 B)
-          const uint64_t adv = (uint64_t)(2 * k);
-          umma_tf32(tmem_acc, a_lo + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
-          umma_tf32(tmem_acc, a_hi + adv, b_lo + adv, idesc, 1u);
-          umma_tf32(tmem_acc, a_hi + adv, b_hi + adv, idesc, 1u);
+          for (int k = 0; k < kBK / 8; ++k) {
+            // UMMA_K = 8 tf32.  K-major: +32 bytes inside the 128-byte swizzle row; MN-major: next 8 reduction rows (+1024 bytes)
+            const uint64_t adv = TN ? (uint64_t)((k * 1024) >> 4) : (uint64_t)(2 * k);
+            const uint32_t first = (kb == ch * kChunk && k == 0) ? 0u : 1u;
+            umma_tf32(tacc, a_lo + adv, b_hi + adv, idesc, first);
+            umma_tf32(tacc, a_hi + adv, b_lo + adv, idesc, 1u);
+            umma_tf32(tacc, a_hi + adv, b_hi + adv, idesc, 1u);
+          }
+          tcgen05_commit(empty0 + 8 * s);                      // frees the smem stage once these MMAs retire
         }
-        tcgen05_commit(empty0 + 8 * s);                        // frees the smem stage once these MMAs retire
+        tcgen05_commit(tfull0 + 8 * buf);                      // chunk accumulator complete
       }
-      tcgen05_commit(accfull);                                 // accumulator complete
     }
-  } else {             // ===== epilogue warps: TMEM -> registers -> global =====
-    mbar_wait(accfull, 0);
-    tcgen05_fence_after();
+  } else {             // ===== epilogue warps: drain chunk accumulators into fp32 registers, then store =====
     const int q = warp & 3;                                    // a warp may only touch TMEM lanes [32 q, 32 q + 32)
-    const int row = m0 + q * 32 + lane;
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-            "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-            "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-          : "r"(taddr)
-          : "memory");
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (row < M) {
-        float* crow = C + (int64_t)row * ldc + n0 + c * 32;
+    const int hsel = (warp - 2) >> 2;                          // which half of the BN columns
+    float acc[HALF];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (n0 + c * 32 + j * 4 < n_store)
-            *reinterpret_cast<float4*>(crow + j * 4) = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                                                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-        }
+    for (int c = 0; c < HALF; ++c) acc[c] = 0.f;
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      const int buf = ch & 1;
+      mbar_wait(tfull0 + 8 * buf, (ch >> 1) & 1);
+      tcgen05_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(buf * BN + hsel * HALF) + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+      for (int c = 0; c < HALF / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tacc + (uint32_t)(c * 32), r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(r[j]);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+    }
+    const int row = m0 + q * 32 + lane;
+    if (row < M) {
+      float* crow = C + (int64_t)blockIdx.z * split_stride + (int64_t)row * ldc + n0 + hsel * HALF;
+#pragma unroll
+      for (int j = 0; j < HALF / 4; ++j) {
+        if (n0 + hsel * HALF + j * 4 < n_store)
+          *reinterpret_cast<float4*>(crow + j * 4) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
       }
     }
   }
@@ -184,7 +266,7 @@ gemm_nt_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -232,7 +314,12 @@ static EncodeTiledFn encode_fn() {
 }
 
 // 2-D fp32 tensor [rows, cols] with row pitch ld (floats); box = [box_rows, 32 cols], 128-byte swizzle, zero OOB fill
-static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+  if (rows <= 0 || cols <= 0) {
+    set_error("gemm: empty operand");
+    return TX_ERR_INVALID_ARGUMENT;
+  }
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("gemm: cuTensorMapEncodeTiled driver entry point unavailable");
@@ -243,7 +330,7 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
   const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("gemm: cuTensorMapEncodeTiled failed with CUresult %d (rows %lld cols %lld ld %lld)", (int)r, (long long)rows,
@@ -253,31 +340,48 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
   return TX_OK;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool TN>
 static int launch_gemm(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi, const float* b_lo, int64_t ldb,
-                       float* c, int64_t ldc, int64_t M, int64_t N, int64_t K, cudaStream_t st) {
+                       float* c, int64_t ldc, int64_t split_stride, int64_t M, int64_t N, int64_t K, int splits, cudaStream_t st) {
   alignas(64) CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
-  if ((rc = make_map(&ma_hi, a_hi, M, K, lda, kBM)) != TX_OK) return rc;
-  if ((rc = make_map(&ma_lo, a_lo, M, K, lda, kBM)) != TX_OK) return rc;
-  if ((rc = make_map(&mb_hi, b_hi, N, K, ldb, BN)) != TX_OK) return rc;
-  if ((rc = make_map(&mb_lo, b_lo, N, K, ldb, BN)) != TX_OK) return rc;
+  if (!TN) {   // A [M, K], B [N, K]: box = {32 k-cols, tile rows}
+    if ((rc = make_map(&ma_hi, a_hi, M, K, lda, kBM)) != TX_OK) return rc;
+    if ((rc = make_map(&ma_lo, a_lo, M, K, lda, kBM)) != TX_OK) return rc;
+    if ((rc = make_map(&mb_hi, b_hi, N, K, ldb, BN)) != TX_OK) return rc;
+    if ((rc = make_map(&mb_lo, b_lo, N, K, ldb, BN)) != TX_OK) return rc;
+  } else {     // A [K, M], B [K, N]: box = {32 m/n-cols, kBK reduction rows}
+    // (debug knobs TAXO_TN_SWIZZLE / _LAYOUT / _LBO / _SBO override the layout constants below)
+    const char* e_sw = getenv("TAXO_TN_SWIZZLE");
+    const CUtensorMapSwizzle sw = e_sw ? (CUtensorMapSwizzle)atoi(e_sw) : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    if ((rc = make_map(&ma_hi, a_hi, K, M, lda, kBK, sw)) != TX_OK) return rc;
+    if ((rc = make_map(&ma_lo, a_lo, K, M, lda, kBK, sw)) != TX_OK) return rc;
+    if ((rc = make_map(&mb_hi, b_hi, K, N, ldb, kBK, sw)) != TX_OK) return rc;
+    if ((rc = make_map(&mb_lo, b_lo, K, N, ldb, kBK, sw)) != TX_OK) return rc;
+  }
   constexpr int STAGE_BYTES = 2 * kABytes + 2 * BN * kBK * 4;
   constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers + tmem slot */;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_nt_tf32x3_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, STAGES, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
     if (e != cudaSuccess) {
       set_error("gemm: cudaFuncSetAttribute(%zu B smem) failed: %s", SMEM, cudaGetErrorString(e));
       return TX_ERR_CUDA;
     }
     attr_done = true;
   }
-  const int64_t n_store = ((N + 3) / 4) * 4 <= ldc ? ((N + 3) / 4) * 4 : N;
-  dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + kBM - 1) / kBM));
-  gemm_nt_tf32x3_kernel<BN, STAGES><<<grid, 192, SMEM, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, c, ldc, (int)M, (int)n_store,
-                                                           (int)((K + kBK - 1) / kBK));
-  TX_LAUNCH_CHECK("tx_gemm_nt_tf32x3");
+  const int kbt = (int)((K + kBK - 1) / kBK);
+  const int kbs = (kbt + splits - 1) / splits;
+  const int64_t n_store = ((N + 3) / 4) * 4;
+  dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + kBM - 1) / kBM), (unsigned)splits);
+  const char* e_l = getenv("TAXO_TN_LAYOUT");
+  const char* e_lbo = getenv("TAXO_TN_LBO");
+  const char* e_sbo = getenv("TAXO_TN_SBO");
+  const uint64_t mn_bits = umma_desc_mn_bits(e_lbo ? (uint32_t)atoi(e_lbo) : (uint32_t)(kBK * 128), e_sbo ? (uint32_t)atoi(e_sbo) : 512u,
+                                             e_l ? (uint32_t)atoi(e_l) : 1u);
+  gemm_tf32x3_kernel<BN, STAGES, TN><<<grid, kGemmThreads, SMEM, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, c, ldc, split_stride, (int)M,
+                                                                     (int)n_store, kbt, kbs, mn_bits);
+  TX_LAUNCH_CHECK(TN ? "tx_gemm_tn_tf32x3" : "tx_gemm_nt_tf32x3");
   return TX_OK;
 }
 
@@ -286,6 +390,30 @@ static int launch_gemm(const float* a_hi, const float* a_lo, int64_t lda, const 
 using namespace tx;
 
 extern "C" {
+
+int64_t tx_gemm_tn_splits(int64_t m, int64_t n, int64_t r) {
+  const int64_t bn = n > 128 ? 256 : (n > 64 ? 128 : 64);
+  const int64_t tiles = ((m + kBM - 1) / kBM) * ((n + bn - 1) / bn);
+  int64_t s = kNumSms / (tiles > 0 ? tiles : 1);
+  const int64_t kbt = (r + kBK - 1) / kBK;
+  if (s > kbt / 8) s = kbt / 8;          // keep at least 8 k-blocks per split
+  if (s > 32) s = 32;
+  return s < 1 ? 1 : s;
+}
+
+int tx_gemm_tn_tf32x3(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi, const float* b_lo, int64_t ldb,
+                      float* c_partial, int64_t ldc, int64_t split_stride, int64_t m, int64_t n, int64_t r, int64_t splits,
+                      void* stream) {
+  TX_REQUIRE(m > 0 && n > 0 && r > 0 && m < INT32_MAX && n < INT32_MAX && r < INT32_MAX, "gemm_tn: bad shape");
+  TX_REQUIRE(lda % 4 == 0 && ldb % 4 == 0 && lda >= m && ldb >= n, "gemm_tn: operand row pitch must be a multiple of 4 floats and >= M / N");
+  TX_REQUIRE(aligned16(a_hi) && aligned16(a_lo) && aligned16(b_hi) && aligned16(b_lo) && aligned16(c_partial), "gemm_tn: 16-byte aligned pointers required");
+  TX_REQUIRE(ldc % 4 == 0 && ldc >= ((n + 3) / 4) * 4 && split_stride % 4 == 0 && split_stride >= m * ldc, "gemm_tn: bad ldc / split_stride");
+  TX_REQUIRE(splits >= 1 && splits <= 65535, "gemm_tn: bad split count");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n > 128) return launch_gemm<256, 2, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c_partial, ldc, split_stride, m, n, r, (int)splits, st);
+  if (n > 64) return launch_gemm<128, 3, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c_partial, ldc, split_stride, m, n, r, (int)splits, st);
+  return launch_gemm<64, 4, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c_partial, ldc, split_stride, m, n, r, (int)splits, st);
+}
 
 int tx_split_tf32(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* hi, float* lo, int64_t ldo, void* stream) {
   TX_REQUIRE(ldo % 4 == 0 && ldo >= cols && aligned16(hi) && aligned16(lo), "split_tf32: outputs need ld %% 4 == 0, ld >= cols, 16B alignment");
@@ -305,9 +433,10 @@ int tx_gemm_nt_tf32x3(const float* a_hi, const float* a_lo, int64_t lda, const f
   TX_REQUIRE(aligned16(a_hi) && aligned16(a_lo) && aligned16(b_hi) && aligned16(b_lo) && aligned16(c), "gemm: 16-byte aligned pointers required");
   TX_REQUIRE(ldc % 4 == 0 && ldc >= n, "gemm: ldc must be a multiple of 4 and >= N");
   cudaStream_t st = (cudaStream_t)stream;
-  if (n > 128) return launch_gemm<256, 2>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, m, n, k, st);
-  if (n > 64) return launch_gemm<128, 3>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, m, n, k, st);
-  return launch_gemm<64, 4>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, m, n, k, st);
+  TX_REQUIRE(ldc >= ((n + 3) / 4) * 4, "gemm: ldc must hold round4(N) columns");
+  if (n > 128) return launch_gemm<256, 2, false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st);
+  if (n > 64) return launch_gemm<128, 3, false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st);
+  return launch_gemm<64, 4, false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st);
 }
 
 }  // extern "C"

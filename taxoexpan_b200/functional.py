@@ -75,7 +75,35 @@ def split_tf32(x: torch.Tensor, cols: int = None):
     return hi, lo
 
 
-def gemm_nt(a: torch.Tensor, k: int, b: torch.Tensor, out: torch.Tensor = None, n_out: int = None) -> torch.Tensor:
+def gemm_nt_ps(a_hi, a_lo, k: int, b_hi, b_lo, n: int, out: torch.Tensor = None) -> torch.Tensor:
+    """C[:, :n] = A[:, :k] @ B[:n, :k]^T from pre-split operands on the tcgen05 3xTF32 kernel."""
+    lib = _lib.load()
+    m = a_hi.shape[0]
+    if out is None:
+        out = torch.empty((m, round4(n)), dtype=torch.float32, device=a_hi.device)
+    ldc = out.stride(0) if m > 1 else out.shape[1]
+    if m > 0:
+        check(lib.tx_gemm_nt_tf32x3(ptr(a_hi), ptr(a_lo), a_hi.stride(0), ptr(b_hi), ptr(b_lo), b_hi.stride(0), ptr(out), ldc, m, n, k,
+                                    current_stream()), "tx_gemm_nt_tf32x3")
+    return out if out.shape[1] == n else out[:, :n]
+
+
+def gemm_tn_ps(a_hi, a_lo, m: int, b_hi, b_lo, n: int) -> torch.Tensor:
+    """C[m, n] = sum_r A[r, :m]^T B[r, :n] (weight-gradient form) from pre-split operands; split-K + fixed-order reduce."""
+    lib = _lib.load()
+    r = a_hi.shape[0]
+    ldc = round4(n)
+    if r == 0:
+        return torch.zeros((m, n), dtype=torch.float32, device=a_hi.device)
+    splits = int(lib.tx_gemm_tn_splits(m, n, r))
+    partial = torch.empty((splits, m, ldc), dtype=torch.float32, device=a_hi.device)
+    check(lib.tx_gemm_tn_tf32x3(ptr(a_hi), ptr(a_lo), a_hi.stride(0), ptr(b_hi), ptr(b_lo), b_hi.stride(0), ptr(partial), ldc, m * ldc,
+                                m, n, r, splits, current_stream()), "tx_gemm_tn_tf32x3")
+    out = partial[0] if splits == 1 else _reduce_partials(lib, partial, splits, m * ldc).view(m, ldc)
+    return out[:, :n]
+
+
+def gemm_nt(a: torch.Tensor, k: int, b: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
     """C = a[:, :k] @ b[:, :k]^T in fp32-faithful precision.  a: [M, >=k], b: [N, >=k] row-major.
     cublas backend: torch.mm (fp32 SIMT).  tf32x3 backend: split + tcgen05 3xTF32 kernel.
     `out` (optional) is a [M, ldc] buffer whose first N columns receive the result."""
@@ -85,29 +113,53 @@ def gemm_nt(a: torch.Tensor, k: int, b: torch.Tensor, out: torch.Tensor = None, 
             return torch.mm(a[:, :k], b[:, :k].t())
         torch.mm(a[:, :k], b[:, :k].t(), out=out[:, :n])
         return out
-    lib = _lib.load()
     a_hi, a_lo = split_tf32(a, k)
     b_hi, b_lo = split_tf32(b, k)
-    if out is None:
-        out = torch.empty((m, round4(n)), dtype=torch.float32, device=a.device)
-    ldc = out.stride(0) if m > 1 else out.shape[1]
-    check(lib.tx_gemm_nt_tf32x3(ptr(a_hi), ptr(a_lo), a_hi.shape[1], ptr(b_hi), ptr(b_lo), b_hi.shape[1], ptr(out), ldc, m, n, k,
-                                current_stream()), "tx_gemm_nt_tf32x3")
-    return out if out.shape[1] == n else out[:, :n]
+    return gemm_nt_ps(a_hi, a_lo, k, b_hi, b_lo, n, out)
 
 
-def _gemm_dz(dy: torch.Tensor, f: int, w_kf: torch.Tensor, c0: int, k: int, ldz: int) -> torch.Tensor:
-    """d(z)[:, c0a:k] = dy[:, :f] @ w_kf[c0a:k, :f]^T into a fresh padded [n, ldz] buffer (c0a = c0 rounded down to a
-    multiple of 4 so the output pointer stays 16-byte aligned; columns < c0a are not needed by the caller and stay
-    uninitialised; padding columns >= k are zero)."""
+def _layer_gemms_fwd(z, k, w_nk):
+    """y = z[:, :k] @ w_nk[:, :k]^T.  Returns (y, saved) where `saved` is what backward needs of z: z itself (cublas) or its
+    TF32 split (tf32x3: the split is computed once and reused by the weight-gradient GEMM)."""
+    if GEMM_BACKEND != "tf32x3" or z.shape[0] == 0:
+        return torch.mm(z[:, :k], w_nk[:, :k].t()), (z, None)
+    z_hi, z_lo = split_tf32(z, k)
+    w_hi, w_lo = split_tf32(w_nk, k)
+    return gemm_nt_ps(z_hi, z_lo, k, w_hi, w_lo, w_nk.shape[0]), (z_hi, z_lo)
+
+
+def _layer_gemms_bwd(dy, f, saved, w_kf, k, ldz, c0, need_w, need_z):
+    """dW_fk = dy[:, :f]^T @ z[:, :k]  and  dz[:, c0a:k] = dy[:, :f] @ w_kf[c0a:k, :f]^T (see _gemm_dz)."""
     n = dy.shape[0]
-    c0a = (min(c0, k) // 4) * 4
-    dz = torch.empty((n, ldz), dtype=torch.float32, device=dy.device)
-    if k > c0a:
-        gemm_nt(dy, f, w_kf[c0a:k], out=dz[:, c0a:])
-    if GEMM_BACKEND != "tf32x3" and ldz > k:
-        dz[:, k:].zero_()
-    return dz
+    dw = dz = None
+    if GEMM_BACKEND != "tf32x3" or n == 0:
+        z = saved[0]
+        if need_w:
+            with timed_region("gemm_dw"):
+                dw = torch.mm(dy[:, :f].t(), z[:, :k])
+        if need_z:
+            with timed_region("gemm_dz"):
+                c0a = (min(c0, k) // 4) * 4
+                dz = torch.empty((n, ldz), dtype=torch.float32, device=dy.device)
+                if k > c0a:
+                    torch.mm(dy[:, :f], w_kf[c0a:k, :f].t(), out=dz[:, c0a:k])
+                if ldz > k:
+                    dz[:, k:].zero_()
+        return dw, dz
+    z_hi, z_lo = saved
+    with timed_region("split_dy"):
+        d_hi, d_lo = split_tf32(dy, f)
+    if need_w:
+        with timed_region("gemm_dw"):
+            dw = gemm_tn_ps(d_hi, d_lo, f, z_hi, z_lo, k)
+    if need_z:
+        with timed_region("gemm_dz"):
+            c0a = (min(c0, k) // 4) * 4
+            dz = torch.empty((n, ldz), dtype=torch.float32, device=dy.device)
+            if k > c0a:
+                w_hi, w_lo = split_tf32(w_kf[c0a:k], f)
+                gemm_nt_ps(d_hi, d_lo, f, w_hi, w_lo, k - c0a, out=dz[:, c0a:])
+    return dw, dz
 
 
 def new_seed() -> int:
@@ -214,7 +266,7 @@ class GatLayer(Function):
             stream = current_stream()
             Stats.tag = cfg.tag
             with timed_region("gemm_fwd"):
-                ft = gemm_nt(z, K, weight)                                 # ft = fc(h), model_zoo.py:83
+                ft, zsaved = _layer_gemms_fwd(z, K, weight)                # ft = fc(h), model_zoo.py:83
             al = attn_l.reshape(-1).contiguous()
             ar = attn_r.reshape(-1).contiguous()
             alpha = torch.empty(st.e * H, **f32)
@@ -251,19 +303,21 @@ class GatLayer(Function):
         ctx.fused, ctx.maskbits = fused, maskbits
         ctx.st, ctx.cfg, ctx.pd = st, cfg, pd
         ctx.vocab = 0 if next_pos_table is None else int(next_pos_table.shape[0])
-        ctx.save_for_backward(z, weight, al, ar, ft, alpha, alpha_d, elog, out if cfg.hidden else None, pos32)
+        ctx.save_for_backward(zsaved[0], zsaved[1], weight, al, ar, ft, alpha, alpha_d, elog,
+                              out if (cfg.hidden and not fused) else None, pos32)
         ctx.attn_shape = attn_l.shape
+        ctx.zshape = tuple(z.shape)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         lib = _lib.load()
-        z, weight, al, ar, ft, alpha, alpha_d, elog, out, pos32 = ctx.saved_tensors
+        z0, z1, weight, al, ar, ft, alpha, alpha_d, elog, out, pos32 = ctx.saved_tensors
         st, cfg, pd = ctx.st, ctx.cfg, ctx.pd
-        n, ldz = z.shape
+        n, ldz = ctx.zshape
         H, D, K = cfg.heads, cfg.dim, cfg.k
         F_ = H * D
-        dev = z.device
+        dev = ft.device
         f32 = dict(dtype=torch.float32, device=dev)
         dtab = None
         with torch.cuda.device(dev):
@@ -324,13 +378,8 @@ class GatLayer(Function):
                           "tx_gat_attn_grad_partials")
                     both = _reduce_partials(lib, partial, nb, 2 * F_)
                     dal, dar = both[:F_].view(ctx.attn_shape), both[F_:].view(ctx.attn_shape)
-            with timed_region("gemm_dw"):
-                dw = torch.mm(dft.t(), z[:, :K]) if ctx.needs_input_grad[1] else None
-            dz = None
-            if ctx.needs_input_grad[0]:
-                c0 = min(cfg.dz_from, K)
-                with timed_region("gemm_dz"):
-                    dz = _gemm_dz(dft, F_, weight.t(), c0, K, ldz)
+            dw, dz = _layer_gemms_bwd(dft, F_, (z0, z1), weight.t(), K, ldz, cfg.dz_from, ctx.needs_input_grad[1],
+                                      ctx.needs_input_grad[0])
         return dz, dw, dal, dar, dtab, None, None, None
 
 
@@ -363,7 +412,7 @@ class GcnLayer(Function):
             stream = current_stream()
             Stats.tag = cfg.tag
             with timed_region("gemm_fwd"):
-                y = gemm_nt(z, K, weight.t())                              # torch.mm(h, W), model_zoo.py:37
+                y, zsaved = _layer_gemms_fwd(z, K, weight.t())             # torch.mm(h, W), model_zoo.py:37
             norm = st.gcn_norm()
             pd = 0 if next_pos_table is None else int(next_pos_table.shape[1])
             tab = None if next_pos_table is None else next_pos_table.contiguous()
@@ -378,17 +427,18 @@ class GcnLayer(Function):
         ctx.st, ctx.cfg, ctx.pd = st, cfg, pd
         ctx.vocab = 0 if next_pos_table is None else int(next_pos_table.shape[0])
         ctx.has_bias = bias is not None
-        ctx.save_for_backward(z, weight, out if cfg.hidden else None, pos32, norm)
+        ctx.save_for_backward(zsaved[0], zsaved[1], weight, out if cfg.hidden else None, pos32, norm)
+        ctx.zshape = tuple(z.shape)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         lib = _lib.load()
-        z, weight, out, pos32, norm = ctx.saved_tensors
+        z0, z1, weight, out, pos32, norm = ctx.saved_tensors
         st, cfg, pd = ctx.st, ctx.cfg, ctx.pd
-        n, ldz = z.shape
+        n, ldz = ctx.zshape
         D, K = cfg.dim, cfg.k
-        dev = z.device
+        dev = norm.device
         f32 = dict(dtype=torch.float32, device=dev)
         dtab = db = None
         with torch.cuda.device(dev):
@@ -416,13 +466,9 @@ class GcnLayer(Function):
             dy = torch.empty((n, D), **f32)
             check(lib.tx_gcn_aggregate_bwd(ptr(dout), ldg, ptr(norm), ptr(st.out_ptr), ptr(st.out_dst), n, D, ptr(dy), D, stream),
                   "tx_gcn_aggregate_bwd")
-            with timed_region("gemm_dw"):
-                dw = torch.mm(z[:, :K].t(), dy) if ctx.needs_input_grad[1] else None
-            dz = None
-            if ctx.needs_input_grad[0]:
-                c0 = min(cfg.dz_from, K)
-                with timed_region("gemm_dz"):
-                    dz = _gemm_dz(dy, D, weight, c0, K, ldz)
+            dwt, dz = _layer_gemms_bwd(dy, D, (z0, z1), weight, K, ldz, cfg.dz_from, ctx.needs_input_grad[1],
+                                       ctx.needs_input_grad[0])
+            dw = None if dwt is None else dwt.t()                         # weight is [K, D]
         return dz, dw, db, dtab, None, None, None
 
 

@@ -34,7 +34,7 @@ def test_tf32x3_gemm_matches_fp64(m, n, k, monkeypatch):
     err_cublas = float((cublas - ref).abs().max())
     scale = float(ref.abs().max())
     print(f"[{m}x{n}x{k}] max|err| tf32x3 {err:.3e}  cublas-fp32 {err_cublas:.3e}  max|ref| {scale:.3f}")
-    assert err <= max(4.0 * err_cublas, 2e-6 * max(scale, 1.0)), (err, err_cublas)
+    assert err <= max(3.0 * err_cublas, 1e-6 * max(scale, 1.0)), (err, err_cublas)
 
 
 def test_tf32x3_gemm_writes_padded_output_and_tails(monkeypatch):
@@ -48,6 +48,27 @@ def test_tf32x3_gemm_writes_padded_output_and_tails(monkeypatch):
     assert float((out[:, :n].cpu().double() - ref).abs().max()) < 5e-6
     assert float(out[:, n:].abs().max()) == 0.0            # padding columns are written as zeros
     assert res.data_ptr() == out.data_ptr()
+
+
+@pytest.mark.parametrize("r,m,n", [(256, 128, 64), (1000, 500, 2050), (4099, 2000, 300), (37039, 500, 2050), (37039, 2000, 300),
+                                   (77, 40, 12), (8192, 600, 350)])
+def test_tf32x3_weight_gradient_gemm_matches_fp64(r, m, n):
+    """C = A^T B with the reduction over the rows (nodes): MN-major operands, split-K, fixed-order reduce."""
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(r + m + n)
+    a = torch.randn(r, m, generator=g) / np.sqrt(r)
+    b = torch.nn.functional.normalize(torch.randn(r, n, generator=g), dim=1)
+    ref = a.double().t() @ b.double()
+    a_hi, a_lo = txf.split_tf32(a.to(dev))
+    b_hi, b_lo = txf.split_tf32(b.to(dev))
+    got = txf.gemm_tn_ps(a_hi, a_lo, m, b_hi, b_lo, n).cpu().double()
+    assert got.shape == (m, n)
+    cublas = (a.to(dev).t() @ b.to(dev)).cpu().double()
+    err, err_cublas, scale = float((got - ref).abs().max()), float((cublas - ref).abs().max()), float(ref.abs().max())
+    print(f"[TN {r}: {m}x{n}] max|err| tf32x3 {err:.3e}  cublas-fp32 {err_cublas:.3e}  max|ref| {scale:.3f}")
+    assert err <= max(3.0 * err_cublas, 1e-6 * max(scale, 1.0)), (err, err_cublas)
+    got2 = txf.gemm_tn_ps(a_hi, a_lo, m, b_hi, b_lo, n).cpu().double()
+    assert torch.equal(got, got2)          # split-K partials are reduced in a fixed order
 
 
 def test_split_is_exact_to_22_bits():
