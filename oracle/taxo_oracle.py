@@ -220,11 +220,32 @@ def init_pgcn_params(in_dim, hidden_dim, out_dim, pos_dim, num_layers, seed=0, p
 # --------------------------------------------------------------------------------------
 # Propagation stacks
 # --------------------------------------------------------------------------------------
+def _activate(h, activation, branch, l, tol=2e-6):
+    """Hidden-layer activation.  `branch` (optional {"act.<l>": bool [N, F]}) pins the leaky-relu branch (True = positive
+    side) taken by the implementation under test: the derivative is discontinuous at 0, so two fp32-accurate
+    implementations may legitimately pick different branches for pre-activations within rounding noise of 0 and their
+    GRADIENTS then differ by O(1e-3).  A pinned branch may only disagree with the oracle's own sign where
+    |pre-activation| <= tol (asserted) or where the element is dropped afterwards ("keep.<l>" mask)."""
+    key = f"act.{l}"
+    if branch is None or key not in branch:
+        return activation(h)
+    assert activation is F.leaky_relu, "branch replay is implemented for leaky_relu(0.01)"
+    pos = branch[key]
+    disagree = (h.detach() > 0) != pos
+    keep = branch.get(f"keep.{l}")
+    if keep is not None:
+        disagree = disagree & keep
+    worst = float(h.detach().abs()[disagree].max()) if bool(disagree.any()) else 0.0
+    assert worst <= tol, f"activation branch of layer {l} differs at |pre-activation| = {worst:.3e} > {tol:.1e}"
+    return torch.where(pos, h, 0.01 * h)
+
+
 def pgat_forward(g: OracleGraph, features, params, num_layers, heads, activation=F.leaky_relu,
                  negative_slope=0.2, p_feat=0.0, p_attn=0.0, masks: Optional[dict] = None, positional=True):
     """PGAT.forward (model_zoo.py:210-220); positional=False gives GAT.forward (:183-190).
 
-    masks: optional {"feat.<l>": bool [N, K_l], "attn.<l>": bool [E, H_l, 1]} keep-masks (edge-id order).
+    masks: optional {"feat.<l>": bool [N, K_l], "attn.<l>": bool [E, H_l, 1]} keep-masks (edge-id order), and
+           optional {"act.<l>": bool [N, F_l]} leaky-relu branch pins (see _activate).
     """
     masks = masks or {}
     h = features
@@ -239,7 +260,7 @@ def pgat_forward(g: OracleGraph, features, params, num_layers, heads, activation
                         params[f"gat_layers.{l}.attn_r"], heads[l], negative_slope,
                         masks.get(f"feat.{l}"), p_feat, masks.get(f"attn.{l}"), p_attn)
         if l < num_layers:
-            h = activation(out.flatten(1))                                         # :215-216
+            h = _activate(out.flatten(1), activation, masks, l)                    # :215-216
         else:
             h = out.mean(1)                                                        # :219
     return h
@@ -258,7 +279,7 @@ def pgcn_forward(g: OracleGraph, features, params, num_layers, activation=F.leak
         else:
             z = h
         p = p_in if l == 0 else (p_out if l == n_total - 1 else p_hidden)          # :145-152
-        act = activation if l < n_total - 1 else None
+        act = (lambda v, _l=l: _activate(v, activation, masks, _l)) if l < n_total - 1 else None
         h = gcn_layer(g, z, params[f"layers.{l}.weight"], params[f"layers.{l}.bias"], norm, act,
                       masks.get(f"feat.{l}"), p)
     return h

@@ -1,8 +1,8 @@
 """torch.autograd Functions over the C ABI (include/taxo_b200.h): the only way compute reaches the GPU here.
 
 Every Function below allocates its outputs/workspace with torch (device memory + stream plumbing) and calls the
-hand-written CUDA kernels through ctypes; dense projections are torch.mm (cuBLAS fp32, TF32 off) unless the
-tcgen05 GEMM of tx_gemm.cu is enabled.  There is no eager/CPU fallback: a CPU tensor raises.
+hand-written CUDA kernels through ctypes; dense projections run on the tcgen05 3xTF32 kernels of tx_gemm.cu
+(TAXO_GEMM=cublas switches them to torch.mm as a cross-check).  There is no eager/CPU fallback: a CPU tensor raises.
 
 Feature matrices travel between layers as PADDED row-major buffers [N, ld] with ld % 4 == 0 (16-byte aligned rows
 for 128-bit accesses / TMA); the logical width K <= ld is tracked by the caller, padding columns are zero.
@@ -58,7 +58,9 @@ def use_fused(lib, heads: int, dim: int, mean_heads: int, st=None) -> bool:
     return FUSED_ENABLED and bool(lib.tx_gat_fused_supported(heads, dim, mean_heads))
 
 
-GEMM_BACKEND = os.environ.get("TAXO_GEMM", "cublas")    # "cublas" (torch.mm fp32) | "tf32x3" (tcgen05 kernel of tx_gemm.cu)
+# dense projections: "tf32x3" = hand-written tcgen05 3xTF32 kernels of tx_gemm.cu (default; fp32-faithful),
+# "cublas" = torch.mm (cuBLAS fp32 SIMT, TF32 off) kept as the yardstick / cross-check
+GEMM_BACKEND = os.environ.get("TAXO_GEMM", "tf32x3")
 
 
 def split_tf32(x: torch.Tensor, cols: int = None):
@@ -159,6 +161,18 @@ def _layer_gemms_bwd(dy, f, saved, w_kf, k, ldz, c0, need_w, need_z):
             if k > c0a:
                 w_hi, w_lo = split_tf32(w_kf[c0a:k], f)
                 gemm_nt_ps(d_hi, d_lo, f, w_hi, w_lo, k - c0a, out=dz[:, c0a:])
+    if os.environ.get("TAXO_DEBUG_GEMM"):
+        torch.cuda.synchronize()
+        z = (z_hi + z_lo)
+        print(f"[debug gemm] f={f} k={k} n={n} dy finite {bool(torch.isfinite(dy).all())} split err {float((d_hi + d_lo - dy[:, :f]).abs().max()):.2e}")
+        if dw is not None:
+            ref = torch.mm(dy[:, :f].t(), z[:, :k])
+            d = (dw - ref).abs()
+            print(f"   dw diff {float(d.max()):.3e} at {divmod(int(d.argmax()), k)} ref {float(ref.abs().max()):.3e}")
+        if dz is not None:
+            ref = torch.mm(dy[:, :f], w_kf[:k, :f].t())
+            d = (dz[:, :k] - ref).abs()
+            print(f"   dz diff {float(d.max()):.3e} at {divmod(int(d.argmax()), k)} ref {float(ref.abs().max()):.3e}")
     return dw, dz
 
 

@@ -51,7 +51,8 @@ def test_tf32x3_gemm_writes_padded_output_and_tails(monkeypatch):
 
 
 @pytest.mark.parametrize("r,m,n", [(256, 128, 64), (1000, 500, 2050), (4099, 2000, 300), (37039, 500, 2050), (37039, 2000, 300),
-                                   (77, 40, 12), (8192, 600, 350)])
+                                   (77, 40, 12), (8192, 600, 350), (1099, 2000, 300), (1099, 500, 2050), (1120, 2000, 300), (1100, 128, 64),
+                                   (2297, 2000, 300)])
 def test_tf32x3_weight_gradient_gemm_matches_fp64(r, m, n):
     """C = A^T B with the reduction over the rows (nodes): MN-major operands, split-K, fixed-order reduce."""
     dev = torch.device("cuda", 0)

@@ -53,6 +53,33 @@ def run_oracle(cfg, og, x, qf, params, n_q, masks=None, training=False, dtype=to
     return scores.detach().numpy(), hg.detach().numpy(), node_h.detach().numpy(), loss.detach().numpy(), grads, h.grad.numpy()
 
 
+def capture_hidden_outputs(monkeypatch):
+    """Records the output of every GAT / GCN layer Function call (the next layer's input z for hidden layers)."""
+    captured = []
+    for fn in (txf.GatLayer, txf.GcnLayer):
+        orig = fn.apply
+
+        def wrapped(*a, _orig=orig):
+            out = _orig(*a)
+            captured.append(out.detach())
+            return out
+        monkeypatch.setattr(fn, "apply", wrapped)
+    return captured
+
+
+def branch_pins(cfg, captured, masks=None):
+    """leaky-relu branches taken by the CUDA run: sign of the hidden layers' outputs (dropped entries are 0 -> irrelevant)."""
+    pins = dict(masks or {})
+    gat = cfg.propagation_method in ("PGAT", "GAT")
+    heads = list(cfg.heads)
+    for l in range(cfg.num_layers):
+        f = cfg.hidden_dim * heads[l] if gat else cfg.hidden_dim
+        pins[f"act.{l}"] = (captured[l][:, :f] > 0).cpu()
+        if masks and f"feat.{l + 1}" in masks:
+            pins[f"keep.{l}"] = masks[f"feat.{l + 1}"][:, :f]
+    return pins
+
+
 def assert_close(got, ref, tol, gtol, what=""):
     names = ["scores", "hg", "node_h", "loss"]
     for name, a, b in zip(names, got[:4], ref[:4]):
@@ -168,16 +195,18 @@ WORDNET = dict(propagation_method="PGCN", readout_method="MR", matching_method="
                                                     (dict(MAGCS, readout_method="CR"), "mag-cs", 4),
                                                     (dict(MAGCS, propagation_method="GAT", readout_method="MR"), "mag-cs", 4),
                                                     (dict(WORDNET, propagation_method="GCN", num_layers=2), "wordnet", 4)])
-def test_cuda_path_matches_oracle_on_synthetic_batches(cfg_kw, model_name, n_q):
+def test_cuda_path_matches_oracle_on_synthetic_batches(cfg_kw, model_name, n_q, monkeypatch):
     cfg = orc.OracleConfig(**cfg_kw)
     shapes = tx.synth.sample_shapes(n_q, 31, model_name, seed=99)
     og = orc.batch_star_egonets(shapes.n_gp, shapes.n_sib)
     x = torch.from_numpy(tx.synth.unit_rows(og.n, cfg.in_dim, seed=1))
     qf = torch.from_numpy(tx.synth.unit_rows(og.num_graphs, cfg.in_dim, seed=2))
     params = orc.init_model_params(cfg, seed=3)
-    ref = run_oracle(cfg, og, x, qf, params, n_q)
+    captured = capture_hidden_outputs(monkeypatch)
     model = build_model(cfg, params).train()
     got = run_cuda(model, tx.EgonetBatch.from_counts(shapes.n_gp, shapes.n_sib), x, qf, n_q)
+    # the oracle takes the same leaky-relu branch as the CUDA run wherever the pre-activation is within 2e-6 of the kink
+    ref = run_oracle(cfg, og, x, qf, params, n_q, masks=branch_pins(cfg, captured))
     assert_close(got, ref, TOL, GTOL)
 
 
@@ -229,10 +258,11 @@ def test_training_mode_dropout_matches_oracle_with_replayed_masks(cfg_kw, model_
     params = orc.init_model_params(cfg, seed=3)
     seed = 0x1234_5678_9ABC
     monkeypatch.setattr(txf, "new_seed", lambda: seed)
+    captured = capture_hidden_outputs(monkeypatch)
     model = build_model(cfg, params, 0.1, 0.1, 0.1, 0.1).train()
     got = run_cuda(model, tx.EgonetBatch.from_counts(shapes.n_gp, shapes.n_sib), x, qf, n_q)
     n_layers = cfg.num_layers + 1
-    masks = _replay_masks(cfg, og, seed, [0.1] * n_layers, 0.1)
+    masks = branch_pins(cfg, captured, _replay_masks(cfg, og, seed, [0.1] * n_layers, 0.1))
     ref = run_oracle(cfg, og, x, qf, params, n_q, masks=masks, training=True)
     assert_close(got, ref, TOL, GTOL, what="dropout: ")
 
