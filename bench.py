@@ -191,12 +191,9 @@ def run_b200(args, rank, world, local_rank):
         for p in model.parameters():
             dist.broadcast(p.data, 0)
     model.train()
-    params = [p for p in model.parameters()]
-    flat = torch.zeros(sum(p.numel() for p in params), device=dev)
-    off = 0
-    for p in params:   # gradients live in one flat fp32 bucket -> ONE all-reduce per step
-        p.grad = flat[off:off + p.numel()].view_as(p)
-        off += p.numel()
+    from taxoexpan_b200.dist import FlatGradBucket
+    bucket = FlatGradBucket(model.parameters())     # gradients live in one flat fp32 bucket -> ONE all-reduce per step
+    flat = bucket.flat
 
     # rotating seeded batches (different shapes/features per rank and per slot), host copies pinned
     batches = []
@@ -216,8 +213,7 @@ def run_b200(args, rank, world, local_rank):
         scores = model(g, x, qf)                                              # trainer.py:51
         loss = F.cross_entropy(scores.reshape(nq, -1), target, reduction="sum")   # trainer.py:52-56, loss.py:57
         loss.backward()                                                       # trainer.py:60
-        if world > 1:
-            dist.all_reduce(flat)                                             # the only exchange of the path
+        bucket.all_reduce()                                                   # the only exchange of the path (no-op at N = 1)
         return loss
 
     def step_resident(i):
