@@ -247,6 +247,18 @@ int tx_gemm_tn_tf32x3(const float* a_hi, const float* a_lo, int64_t lda, const f
                       void* stream);
 int tx_gemm_nt_tf32x3(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi, const float* b_lo, int64_t ldb,
                       float* c, int64_t ldc, int64_t m, int64_t n, int64_t k, void* stream);
+/* Same with a fused output transform: for columns c < heads*dim, C[row, c] *= keep ? (positive ? 1 : act_slope) / (1 - p_drop) : 0,
+ * decoded from the sign/keep bytes written by tx_gat_fused_fwd (maskbits viewed as bytes; mask_stride = bytes per (row, head)
+ * = 32 * ceil(dim / 128)).  Used for d(z_next) = d(ft_next) . W_next: the backward of "leaky_relu -> feat_drop"
+ * (reference autograd of model_zoo.py:215-216,82) is applied where the gradient is produced, so tx_gat_fused_bwd reads it as is. */
+typedef struct tx_gemm_epilogue {
+  const uint8_t* act_mask;
+  int64_t heads, dim, mask_stride, col0;
+  float act_slope, p_drop;
+  int32_t has_keep_plane;
+} tx_gemm_epilogue;
+int tx_gemm_nt_tf32x3_ex(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi, const float* b_lo, int64_t ldb,
+                         float* c, int64_t ldc, int64_t m, int64_t n, int64_t k, const tx_gemm_epilogue* epilogue, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Test / parity utility: materialise the keep-mask the kernels use (1 = keep) for n indices

@@ -36,6 +36,13 @@ P = c_void_p
 I64 = c_int64
 F32 = c_float
 
+
+class GemmEpilogue(Structure):
+    """struct tx_gemm_epilogue"""
+    _fields_ = [("act_mask", c_void_p), ("heads", c_int64), ("dim", c_int64), ("mask_stride", c_int64), ("col0", c_int64),
+                ("act_slope", c_float), ("p_drop", c_float), ("has_keep_plane", c_int32)]
+
+
 # name -> argtypes (all return int unless listed in _RESTYPES)
 _SIGNATURES = {
     "tx_abi_version": [],
@@ -74,6 +81,7 @@ _SIGNATURES = {
     "tx_pos_grad_partials": [P, I64, I64, P, I64, I64, I64, F32, c_uint64, c_uint32, P, P],
     "tx_split_tf32": [P, I64, I64, I64, P, P, I64, P],
     "tx_gemm_nt_tf32x3": [P, P, I64, P, P, I64, P, I64, I64, I64, I64, P],
+    "tx_gemm_nt_tf32x3_ex": [P, P, I64, P, P, I64, P, I64, I64, I64, I64, POINTER(GemmEpilogue), P],
     "tx_gemm_tn_splits": [I64, I64, I64],
     "tx_gemm_tn_tf32x3": [P, P, I64, P, P, I64, P, I64, I64, I64, I64, I64, I64, P],
 }

@@ -47,6 +47,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
               "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
     if verbose:
         common += ["-Xptxas", "-v"]
+    common += os.environ.get("TAXO_NVCC_FLAGS", "").split()      # e.g. -DTX_BWD_MIN_BLOCKS=2 (tuning experiments)
     procs = []
     for src in sources():
         obj = os.path.join(HERE, "build", os.path.basename(src) + ".o")

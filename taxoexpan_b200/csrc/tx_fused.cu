@@ -112,24 +112,17 @@ __global__ void __launch_bounds__(256, 3) gat_fused_fwd_kernel(const FusedFwdPar
     const int beg = __ldg(p.in_ptr + i), end = __ldg(p.in_ptr + i + 1);
     const int deg = end - beg;
     if (lane == 0 && i + nwarps < p.n) prefetch_l2(base + (int64_t)(i + nwarps) * p.ldf, (uint32_t)D * 4u);
-    float4 cur[NV], nxt[NV];
-    int jn = deg > 0 ? __ldg(p.in_src + beg) : i;
-    load_row<NV>(base + (int64_t)i * p.ldf, lane, D, cur);          // own row: a2 = <ft_i, attn_r>
-    load_row<NV>(base + (int64_t)jn * p.ldf, lane, D, nxt);         // first neighbour row in flight
-    const float a2i = warp_sum(dot_row<NV>(cur, s_r, lane));
+    float4 ra[NV], rb[NV];
+    load_row<NV>(base + (int64_t)i * p.ldf, lane, D, ra);            // own row: a2 = <ft_i, attn_r>
+    if (deg > 0) load_row<NV>(base + (int64_t)__ldg(p.in_src + beg) * p.ldf, lane, D, rb);   // first neighbour row in flight
+    const float a2i = warp_sum(dot_row<NV>(ra, s_r, lane));
     // ---- single pass over the in-edges: logits from the gathered rows + ONLINE edge softmax + aggregation ----
     float m = -INFINITY, l = 0.f, s_mine = 0.f, kw_mine = 1.f;
     float4 acc[NV];
 #pragma unroll
     for (int t = 0; t < NV; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k = beg; k < end; ++k) {
-#pragma unroll
-      for (int t = 0; t < NV; ++t) cur[t] = nxt[t];
-      if (k + 1 < end) {
-        jn = __ldg(p.in_src + k + 1);
-        load_row<NV>(base + (int64_t)jn * p.ldf, lane, D, nxt);     // prefetch the next neighbour row
-      }
-      float s = warp_sum(dot_row<NV>(cur, s_l, lane)) + a2i;        // a1[src] + a2[dst]     (model_zoo.py:108)
+    auto edge = [&](const float4 (&row)[NV], int k) {
+      float s = warp_sum(dot_row<NV>(row, s_l, lane)) + a2i;          // a1[src] + a2[dst]     (model_zoo.py:108)
       s = s > 0.f ? s : s * p.neg_slope;
       float kw = 1.f;
       if (attn_drop)
@@ -141,8 +134,16 @@ __global__ void __launch_bounds__(256, 3) gat_fused_fwd_kernel(const FusedFwdPar
       const float e = expf(s - m_new);
       l = fmaf(l, sc, e);
       if (sc != 1.f) scale_row<NV>(sc, acc);                          // warp-uniform
-      axpy_row<NV>(e * kw, cur, acc);
+      axpy_row<NV>(e * kw, row, acc);
       m = m_new;
+    };
+    for (int k = beg; k < end;) {                                     // ping-pong register buffers: next row in flight
+      if (k + 1 < end) load_row<NV>(base + (int64_t)__ldg(p.in_src + k + 1) * p.ldf, lane, D, ra);
+      edge(rb, k);
+      if (++k >= end) break;
+      if (k + 1 < end) load_row<NV>(base + (int64_t)__ldg(p.in_src + k + 1) * p.ldf, lane, D, rb);
+      edge(ra, k);
+      ++k;
     }
     const float inv_l = deg > 0 ? 1.f / l : 0.f;
     scale_row<NV>(inv_l, acc);
@@ -264,8 +265,11 @@ __device__ __forceinline__ int lower_bound_i32(const int32_t* __restrict__ a, in
 constexpr int kHeavyOut = 12;   // sources with more out-edges than this are processed by the whole CTA
 
 // dynamic smem: s_l, s_r [NV*32] float4 | s_acc [8][2][NV*32] float4 (per-warp d(attn) accumulators) | s_part [8][NV*32]
+#ifndef TX_BWD_MIN_BLOCKS
+#define TX_BWD_MIN_BLOCKS 2   /* 128 registers, no spills: measured 0.71 ms vs 0.85 ms at 3 CTAs/SM with spills (r11) */
+#endif
 template <int NV>
-__global__ void __launch_bounds__(256, 3) gat_fused_bwd_kernel(const FusedBwdParams p) {
+__global__ void __launch_bounds__(256, TX_BWD_MIN_BLOCKS) gat_fused_bwd_kernel(const FusedBwdParams p) {
   extern __shared__ float4 smem_f4[];
   float4* s_l = smem_f4;
   float4* s_r = s_l + NV * 32;
@@ -315,17 +319,22 @@ __global__ void __launch_bounds__(256, 3) gat_fused_bwd_kernel(const FusedBwdPar
     for (int i = r0 + wid; i < r1; i += 8) {
       const int beg = __ldg(p.in_ptr + i), end = __ldg(p.in_ptr + i + 1);
       const int deg = end - beg;
-      float4 gi[NV], cur[NV], nxt[NV];
-      if (deg > 0) load_row<NV>(fbase + (int64_t)__ldg(p.in_src + beg) * p.ldf, lane, D, nxt);
+      float4 gi[NV], ra[NV], rb[NV];
+      if (deg > 0) load_row<NV>(fbase + (int64_t)__ldg(p.in_src + beg) * p.ldf, lane, D, ra);
       load_g_row<NV>(p, i, h, lane, gi);
       float d_mine = 0.f;
-      for (int k = beg; k < end; ++k) {
-#pragma unroll
-        for (int t = 0; t < NV; ++t) cur[t] = nxt[t];
-        if (k + 1 < end) load_row<NV>(fbase + (int64_t)__ldg(p.in_src + k + 1) * p.ldf, lane, D, nxt);
-        const float d = warp_sum(dot_rows<NV>(gi, cur)) * p.g_scale;
+      auto edge = [&](const float4 (&row)[NV], int k) {
+        const float d = warp_sum(dot_rows<NV>(gi, row)) * p.g_scale;
         if (lane == ((k - beg) & 31)) d_mine = d;
         if (deg > 32 && lane == 0) p.ds[(int64_t)k * H + h] = d;
+      };
+      for (int k = beg; k < end;) {
+        if (k + 1 < end) load_row<NV>(fbase + (int64_t)__ldg(p.in_src + k + 1) * p.ldf, lane, D, rb);
+        edge(ra, k);
+        if (++k >= end) break;
+        if (k + 1 < end) load_row<NV>(fbase + (int64_t)__ldg(p.in_src + k + 1) * p.ldf, lane, D, ra);
+        edge(rb, k);
+        ++k;
       }
       if (deg <= 32) {
         float da = 0.f, a = 0.f;
@@ -374,8 +383,8 @@ __global__ void __launch_bounds__(256, 3) gat_fused_bwd_kernel(const FusedBwdPar
     for (int j = r0 + wid; j < r1; j += 8) {
       const int beg = __ldg(p.out_ptr + j), end = __ldg(p.out_ptr + j + 1);
       if (end - beg > kHeavyOut) continue;
-      float4 cur[NV], nxt[NV];
-      if (beg < end) load_g_row<NV>(p, __ldg(p.out_dst + beg), h, lane, nxt);
+      float4 ra[NV], rb[NV];
+      if (beg < end) load_g_row<NV>(p, __ldg(p.out_dst + beg), h, lane, ra);
       float d1 = 0.f;
       if (beg + lane < end) d1 = p.ds[(int64_t)__ldg(p.out_slot + beg + lane) * H + h];
       d1 = warp_sum(d1);
@@ -395,12 +404,13 @@ __global__ void __launch_bounds__(256, 3) gat_fused_bwd_kernel(const FusedBwdPar
           acc[t] = make_float4(fmaf(d1, l.x, d2 * r.x), fmaf(d1, l.y, d2 * r.y), fmaf(d1, l.z, d2 * r.z), fmaf(d1, l.w, d2 * r.w));
         }
       }
-      for (int k = beg; k < end; ++k) {
-#pragma unroll
-        for (int t = 0; t < NV; ++t) cur[t] = nxt[t];
-        if (k + 1 < end) load_g_row<NV>(p, __ldg(p.out_dst + k + 1), h, lane, nxt);
-        const float w = __ldg(p.alpha_d + (int64_t)__ldg(p.out_slot + k) * H + h) * p.g_scale;
-        axpy_row<NV>(w, cur, acc);
+      for (int k = beg; k < end;) {
+        if (k + 1 < end) load_g_row<NV>(p, __ldg(p.out_dst + k + 1), h, lane, rb);
+        axpy_row<NV>(__ldg(p.alpha_d + (int64_t)__ldg(p.out_slot + k) * H + h) * p.g_scale, ra, acc);
+        if (++k >= end) break;
+        if (k + 1 < end) load_g_row<NV>(p, __ldg(p.out_dst + k + 1), h, lane, ra);
+        axpy_row<NV>(__ldg(p.alpha_d + (int64_t)__ldg(p.out_slot + k) * H + h) * p.g_scale, rb, acc);
+        ++k;
       }
       float* orow = p.dft + (int64_t)j * p.ldd + (int64_t)h * D;
 #pragma unroll
@@ -417,17 +427,19 @@ __global__ void __launch_bounds__(256, 3) gat_fused_bwd_kernel(const FusedBwdPar
       const int j = jb + __ffs(heavy) - 1;
       heavy &= heavy - 1;
       const int beg = __ldg(p.out_ptr + j), end = __ldg(p.out_ptr + j + 1);
-      float4 acc[NV], cur[NV], nxt[NV];
+      float4 acc[NV], ra[NV], rb[NV];
 #pragma unroll
       for (int t = 0; t < NV; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
       int k = beg + wid;
-      if (k < end) load_g_row<NV>(p, __ldg(p.out_dst + k), h, lane, nxt);
-      for (; k < end; k += 8) {
-#pragma unroll
-        for (int t = 0; t < NV; ++t) cur[t] = nxt[t];
-        if (k + 8 < end) load_g_row<NV>(p, __ldg(p.out_dst + k + 8), h, lane, nxt);
-        const float w = __ldg(p.alpha_d + (int64_t)__ldg(p.out_slot + k) * H + h) * p.g_scale;
-        axpy_row<NV>(w, cur, acc);
+      if (k < end) load_g_row<NV>(p, __ldg(p.out_dst + k), h, lane, ra);
+      while (k < end) {
+        if (k + 8 < end) load_g_row<NV>(p, __ldg(p.out_dst + k + 8), h, lane, rb);
+        axpy_row<NV>(__ldg(p.alpha_d + (int64_t)__ldg(p.out_slot + k) * H + h) * p.g_scale, ra, acc);
+        k += 8;
+        if (k >= end) break;
+        if (k + 8 < end) load_g_row<NV>(p, __ldg(p.out_dst + k + 8), h, lane, ra);
+        axpy_row<NV>(__ldg(p.alpha_d + (int64_t)__ldg(p.out_slot + k) * H + h) * p.g_scale, rb, acc);
+        k += 8;
       }
 #pragma unroll
       for (int t = 0; t < NV; ++t) s_part[wid * NV * 32 + lane + 32 * t] = acc[t];
@@ -530,9 +542,12 @@ static int bwd_tile_rows() {
   return cached;
 }
 
+#ifndef TX_BWD_MIN_BLOCKS
+#define TX_BWD_MIN_BLOCKS 2   /* 128 registers, no spills: measured 0.71 ms vs 0.85 ms at 3 CTAs/SM with spills (r11) */
+#endif
 int64_t tx_gat_fused_bwd_blocks(int64_t n_nodes, int64_t heads) {
   const int64_t tiles = (n_nodes + bwd_tile_rows() - 1) / bwd_tile_rows();
-  int64_t gx = (3 * (int64_t)kNumSms + heads - 1) / heads;
+  int64_t gx = (TX_BWD_MIN_BLOCKS * (int64_t)kNumSms + heads - 1) / heads;
   if (gx > tiles) gx = tiles;
   return gx < 1 ? 1 : gx;
 }

@@ -104,6 +104,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Optional fused output transform of the NT kernel: C[row, c] *= keep ? (positive ? on : neg) : 0 for c < feat_cols, decoded
+// from the sign/keep bytes the fused GAT forward wrote (1 byte per aligned group of 4 columns of a head, groups contiguous
+// per (row, head): byte index = (row * heads + head) * stride + (c - head*dim) / 4).  This is the backward of
+// "leaky-relu -> dropout" applied right where d(z) is produced (reference: autograd of model_zoo.py:215-216 and :82).
+struct GemmEpilogue {
+  const uint8_t* mask;
+  int heads, dim, stride, feat_cols, has_keep;
+  float on, neg;
+};
+
 constexpr int kChunk = 2;        // k-blocks accumulated inside the tensor core before promotion to fp32 registers
 constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 per TMEM lane quadrant)
 
@@ -119,7 +129,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                    float* __restrict__ C, int64_t ldc, int64_t split_stride, int M, int n_store, int k_blocks_total,
-                   int k_blocks_per_split, uint64_t mn_desc_bits) {
+                   int k_blocks_per_split, uint64_t mn_desc_bits, const GemmEpilogue epi) {
   constexpr int B_BYTES = BN * kBK * 4;
   constexpr int STAGE_BYTES = 2 * kABytes + 2 * B_BYTES;
   constexpr int BOX_BYTES = kBK * 128;       // TN: one {32 cols, kBK rows} box
@@ -257,8 +267,20 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
       float* crow = C + (int64_t)blockIdx.z * split_stride + (int64_t)row * ldc + n0 + hsel * HALF;
 #pragma unroll
       for (int j = 0; j < HALF / 4; ++j) {
-        if (n0 + hsel * HALF + j * 4 < n_store)
-          *reinterpret_cast<float4*>(crow + j * 4) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+        const int col = n0 + hsel * HALF + j * 4;
+        if (col < n_store) {
+          float4 v = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+          if (!TN && epi.mask != nullptr && col < epi.feat_cols) {
+            const int hd = col / epi.dim;
+            uint32_t code = __ldg(epi.mask + ((int64_t)row * epi.heads + hd) * epi.stride + ((col - hd * epi.dim) >> 2));
+            if (!epi.has_keep) code |= 0xF0u;
+            v.x *= (code & 16u) ? ((code & 1u) ? epi.on : epi.neg) : 0.f;
+            v.y *= (code & 32u) ? ((code & 2u) ? epi.on : epi.neg) : 0.f;
+            v.z *= (code & 64u) ? ((code & 4u) ? epi.on : epi.neg) : 0.f;
+            v.w *= (code & 128u) ? ((code & 8u) ? epi.on : epi.neg) : 0.f;
+          }
+          *reinterpret_cast<float4*>(crow + j * 4) = v;
+        }
       }
     }
   }
@@ -342,7 +364,8 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
 
 template <int BN, int STAGES, bool TN>
 static int launch_gemm(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi, const float* b_lo, int64_t ldb,
-                       float* c, int64_t ldc, int64_t split_stride, int64_t M, int64_t N, int64_t K, int splits, cudaStream_t st) {
+                       float* c, int64_t ldc, int64_t split_stride, int64_t M, int64_t N, int64_t K, int splits, cudaStream_t st,
+                       const GemmEpilogue& epi = GemmEpilogue{nullptr, 0, 1, 0, 0, 0, 1.f, 1.f}) {
   alignas(64) CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
   if (!TN) {   // A [M, K], B [N, K]: box = {32 k-cols, tile rows}
@@ -380,7 +403,7 @@ static int launch_gemm(const float* a_hi, const float* a_lo, int64_t lda, const 
   const uint64_t mn_bits = umma_desc_mn_bits(e_lbo ? (uint32_t)atoi(e_lbo) : (uint32_t)(kBK * 128), e_sbo ? (uint32_t)atoi(e_sbo) : 512u,
                                              e_l ? (uint32_t)atoi(e_l) : 1u);
   gemm_tf32x3_kernel<BN, STAGES, TN><<<grid, kGemmThreads, SMEM, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, c, ldc, split_stride, (int)M,
-                                                                     (int)n_store, kbt, kbs, mn_bits);
+                                                                     (int)n_store, kbt, kbs, mn_bits, epi);
   TX_LAUNCH_CHECK(TN ? "tx_gemm_tn_tf32x3" : "tx_gemm_nt_tf32x3");
   return TX_OK;
 }
@@ -428,15 +451,30 @@ int tx_split_tf32(const float* x, int64_t ldx, int64_t rows, int64_t cols, float
 
 int tx_gemm_nt_tf32x3(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi, const float* b_lo, int64_t ldb,
                       float* c, int64_t ldc, int64_t m, int64_t n, int64_t k, void* stream) {
+  return tx_gemm_nt_tf32x3_ex(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, m, n, k, nullptr, stream);
+}
+
+int tx_gemm_nt_tf32x3_ex(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi, const float* b_lo, int64_t ldb,
+                         float* c, int64_t ldc, int64_t m, int64_t n, int64_t k, const tx_gemm_epilogue* e, void* stream) {
   TX_REQUIRE(m > 0 && n > 0 && k > 0 && m < INT32_MAX && n < INT32_MAX && k < INT32_MAX, "gemm: bad shape %lld x %lld x %lld", (long long)m, (long long)n, (long long)k);
   TX_REQUIRE(lda % 4 == 0 && ldb % 4 == 0 && lda >= k && ldb >= k, "gemm: operand row pitch must be a multiple of 4 floats (16 B) and >= K");
   TX_REQUIRE(aligned16(a_hi) && aligned16(a_lo) && aligned16(b_hi) && aligned16(b_lo) && aligned16(c), "gemm: 16-byte aligned pointers required");
   TX_REQUIRE(ldc % 4 == 0 && ldc >= n, "gemm: ldc must be a multiple of 4 and >= N");
   cudaStream_t st = (cudaStream_t)stream;
   TX_REQUIRE(ldc >= ((n + 3) / 4) * 4, "gemm: ldc must hold round4(N) columns");
-  if (n > 128) return launch_gemm<256, 2, false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st);
-  if (n > 64) return launch_gemm<128, 3, false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st);
-  return launch_gemm<64, 4, false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st);
+  GemmEpilogue epi{nullptr, 0, 1, 0, 0, 0, 1.f, 1.f};
+  if (e && e->act_mask) {
+    TX_REQUIRE(e->heads > 0 && e->dim > 0 && e->dim % 4 == 0 && e->mask_stride >= (e->dim + 3) / 4, "gemm epilogue: bad mask geometry");
+    TX_REQUIRE(e->col0 % 4 == 0 && e->col0 >= 0, "gemm epilogue: col0 must be a non-negative multiple of 4");
+    TX_REQUIRE(e->col0 == 0, "gemm epilogue: a column offset is not supported with a fused mask");
+    TX_REQUIRE(e->p_drop >= 0.f && e->p_drop < 1.f, "gemm epilogue: p_drop must be in [0,1)");
+    epi.mask = e->act_mask; epi.heads = (int)e->heads; epi.dim = (int)e->dim; epi.stride = (int)e->mask_stride;
+    epi.feat_cols = (int)(e->heads * e->dim); epi.has_keep = e->has_keep_plane;
+    epi.on = 1.f / (1.f - e->p_drop); epi.neg = e->act_slope * epi.on;
+  }
+  if (n > 128) return launch_gemm<256, 2, false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
+  if (n > 64) return launch_gemm<128, 3, false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
+  return launch_gemm<64, 4, false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
 }
 
 }  // extern "C"

@@ -47,6 +47,9 @@ FUSED_ENABLED = os.environ.get("TAXO_DISABLE_FUSED", "") == ""
 
 
 FUSED_MAX_GRAPH_NODES = 2048
+# apply the leaky-relu/dropout derivative of the previous layer's epilogue inside the d(z) GEMM epilogue (parity-tested; off by
+# default: measured +0.12 ms on the GEMM vs -0.03 ms on the fused backward kernel with byte-granular mask loads, r11)
+FUSE_DZ_EPILOGUE = os.environ.get("TAXO_FUSE_DZ_EPILOGUE", "") != ""
 
 
 def use_fused(lib, heads: int, dim: int, mean_heads: int, st=None) -> bool:
@@ -77,16 +80,17 @@ def split_tf32(x: torch.Tensor, cols: int = None):
     return hi, lo
 
 
-def gemm_nt_ps(a_hi, a_lo, k: int, b_hi, b_lo, n: int, out: torch.Tensor = None) -> torch.Tensor:
-    """C[:, :n] = A[:, :k] @ B[:n, :k]^T from pre-split operands on the tcgen05 3xTF32 kernel."""
+def gemm_nt_ps(a_hi, a_lo, k: int, b_hi, b_lo, n: int, out: torch.Tensor = None, epi=None) -> torch.Tensor:
+    """C[:, :n] = A[:, :k] @ B[:n, :k]^T from pre-split operands on the tcgen05 3xTF32 kernel (optional fused output
+    transform `epi`, a _lib.GemmEpilogue)."""
     lib = _lib.load()
     m = a_hi.shape[0]
     if out is None:
         out = torch.empty((m, round4(n)), dtype=torch.float32, device=a_hi.device)
     ldc = out.stride(0) if m > 1 else out.shape[1]
     if m > 0:
-        check(lib.tx_gemm_nt_tf32x3(ptr(a_hi), ptr(a_lo), a_hi.stride(0), ptr(b_hi), ptr(b_lo), b_hi.stride(0), ptr(out), ldc, m, n, k,
-                                    current_stream()), "tx_gemm_nt_tf32x3")
+        check(lib.tx_gemm_nt_tf32x3_ex(ptr(a_hi), ptr(a_lo), a_hi.stride(0), ptr(b_hi), ptr(b_lo), b_hi.stride(0), ptr(out), ldc,
+                                       m, n, k, epi, current_stream()), "tx_gemm_nt_tf32x3")
     return out if out.shape[1] == n else out[:, :n]
 
 
@@ -130,7 +134,7 @@ def _layer_gemms_fwd(z, k, w_nk):
     return gemm_nt_ps(z_hi, z_lo, k, w_hi, w_lo, w_nk.shape[0]), (z_hi, z_lo)
 
 
-def _layer_gemms_bwd(dy, f, saved, w_kf, k, ldz, c0, need_w, need_z):
+def _layer_gemms_bwd(dy, f, saved, w_kf, k, ldz, c0, need_w, need_z, in_link=None):
     """dW_fk = dy[:, :f]^T @ z[:, :k]  and  dz[:, c0a:k] = dy[:, :f] @ w_kf[c0a:k, :f]^T (see _gemm_dz)."""
     n = dy.shape[0]
     dw = dz = None
@@ -160,8 +164,16 @@ def _layer_gemms_bwd(dy, f, saved, w_kf, k, ldz, c0, need_w, need_z):
             dz = torch.empty((n, ldz), dtype=torch.float32, device=dy.device)
             if k > c0a:
                 w_hi, w_lo = split_tf32(w_kf[c0a:k], f)
-                gemm_nt_ps(d_hi, d_lo, f, w_hi, w_lo, k - c0a, out=dz[:, c0a:])
-    if os.environ.get("TAXO_DEBUG_GEMM"):
+                epi = None
+                if FUSE_DZ_EPILOGUE and in_link is not None and in_link.mask is not None and c0a == 0:
+                    nv = (in_link.dim + 127) // 128
+                    epi = _lib.GemmEpilogue(act_mask=ptr(in_link.mask), heads=in_link.heads, dim=in_link.dim, mask_stride=32 * nv,
+                                            col0=0, act_slope=in_link.act_slope, p_drop=in_link.p_drop,
+                                            has_keep_plane=1 if in_link.p_drop > 0.0 else 0)
+                gemm_nt_ps(d_hi, d_lo, f, w_hi, w_lo, k - c0a, out=dz[:, c0a:], epi=epi)
+                if epi is not None:
+                    in_link.applied = True
+    if os.environ.get("TAXO_DEBUG_GEMM") and in_link is None:
         torch.cuda.synchronize()
         z = (z_hi + z_lo)
         print(f"[debug gemm] f={f} k={k} n={n} dy finite {bool(torch.isfinite(dy).all())} split err {float((d_hi + d_lo - dy[:, :f]).abs().max()):.2e}")
@@ -248,6 +260,17 @@ class ConcatPosDropout(Function):
 # --------------------------------------------------------------------------------------------------
 # GAT layer: ft = z W^T ; fused attention/softmax/aggregate ; epilogue = next layer's input or head mean
 # --------------------------------------------------------------------------------------------------
+class MaskLink:
+    """Hand-shake between consecutive fused GAT layers: layer l-1's forward publishes the sign/keep bytes of its epilogue,
+    layer l's backward applies their derivative inside its d(z) GEMM epilogue and flags it, so layer l-1's backward kernel
+    reads d(z) as is (no per-load decode)."""
+    __slots__ = ("mask", "heads", "dim", "act_slope", "p_drop", "applied")
+
+    def __init__(self):
+        self.mask = None
+        self.applied = False
+
+
 @dataclass
 class GatLayerCfg:
     k: int                      # logical input width (z[:, :k])
@@ -264,6 +287,8 @@ class GatLayerCfg:
     next_stream: int = 0
     dz_from: int = 0            # columns [0, dz_from) of d(z) are not needed by the caller (layer 0, x without grad)
     tag: str = ""               # label for bench.py's per-kernel CUDA-event timings
+    in_link: Optional[MaskLink] = None    # published by the previous layer (its epilogue produced this layer's z)
+    out_link: Optional[MaskLink] = None   # published to the next layer
 
 
 class GatLayer(Function):
@@ -306,6 +331,9 @@ class GatLayer(Function):
                 check(lib.tx_gat_fused_fwd(ptr(ft), F_, ptr(al), ptr(ar), ptr(st.in_ptr), ptr(st.in_src), ptr(st.in_eid), n, H, D,
                                            cfg.neg_slope, cfg.p_attn, cfg.attn_seed, cfg.attn_stream, ptr(alpha), ptr(alpha_d),
                                            ptr(elog), ptr(out), ldo, epi, ptr(maskbits), stream), "tx_gat_fused_fwd")
+                if cfg.out_link is not None and maskbits is not None:
+                    lk = cfg.out_link
+                    lk.mask, lk.heads, lk.dim, lk.act_slope, lk.p_drop, lk.applied = maskbits, H, D, cfg.act_slope, cfg.p_next, False
             else:
                 a1 = torch.empty(n * H, **f32)
                 a2 = torch.empty(n * H, **f32)
@@ -354,8 +382,10 @@ class GatLayer(Function):
                 nbf = int(lib.tx_gat_fused_bwd_blocks(n, H))
                 partial = torch.empty(nbf * 2 * F_, **f32)
                 g_head_stride, g_scale = (D, 1.0) if cfg.hidden else (0, 1.0 / H)
-                check(lib.tx_gat_fused_bwd(ptr(dout), ldg, g_head_stride, g_scale, ptr(ctx.maskbits), 1 if cfg.p_next > 0.0 else 0,
-                                           cfg.act_slope, cfg.p_next if cfg.hidden else 0.0, ptr(ft), F_, ptr(alpha), ptr(alpha_d),
+                pre = cfg.out_link is not None and cfg.out_link.applied     # d(z_next) already carries the epilogue derivative
+                check(lib.tx_gat_fused_bwd(ptr(dout), ldg, g_head_stride, g_scale, None if pre else ptr(ctx.maskbits),
+                                           1 if cfg.p_next > 0.0 else 0, cfg.act_slope, cfg.p_next if cfg.hidden else 0.0,
+                                           ptr(ft), F_, ptr(alpha), ptr(alpha_d),
                                            ptr(elog), ptr(al), ptr(ar), ptr(st.in_ptr), ptr(st.in_src), ptr(st.in_eid),
                                            ptr(st.out_ptr), ptr(st.out_dst), ptr(st.out_slot), ptr(st.node_off), st.g, n, H, D,
                                            cfg.neg_slope, cfg.p_attn, cfg.attn_seed, cfg.attn_stream, ptr(ds), ptr(da2), ptr(dft),
@@ -393,7 +423,7 @@ class GatLayer(Function):
                     both = _reduce_partials(lib, partial, nb, 2 * F_)
                     dal, dar = both[:F_].view(ctx.attn_shape), both[F_:].view(ctx.attn_shape)
             dw, dz = _layer_gemms_bwd(dft, F_, (z0, z1), weight.t(), K, ldz, cfg.dz_from, ctx.needs_input_grad[1],
-                                      ctx.needs_input_grad[0])
+                                      ctx.needs_input_grad[0], cfg.in_link)
         return dz, dw, dal, dar, dtab, None, None, None
 
 

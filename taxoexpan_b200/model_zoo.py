@@ -118,9 +118,11 @@ def _gat_stack_forward(mod, g, features, positions, pos_tables):
     p0 = layers[0].feat_drop if tr else 0.0
     z = txf.ConcatPosDropout.apply(features, tab(0), pos32, p0, seed, 0)
     k = features.shape[1] + pd
+    links = [txf.MaskLink() for _ in range(n_total - 1)]     # layer l's epilogue mask -> layer l+1's d(z) GEMM epilogue
     for l, layer in enumerate(layers):
         hidden = l < n_total - 1
         cfg = txf.GatLayerCfg(
+            in_link=links[l - 1] if l > 0 else None, out_link=links[l] if hidden else None,
             k=k, heads=layer.num_heads, dim=layer.out_dim, neg_slope=layer.negative_slope,
             p_attn=layer.attn_drop if tr else 0.0, attn_seed=seed, attn_stream=2 * l + 1, hidden=hidden,
             act_slope=slope if hidden else 1.0,
