@@ -175,6 +175,7 @@ int tx_gat_attn_grad_partials(const float* ft, int64_t ldf, const float* da1, co
  * ------------------------------------------------------------------------------------------------ */
 int tx_gat_fused_supported(int64_t heads, int64_t dim, int32_t mean_heads);
 int64_t tx_gat_fused_mask_words(int64_t n_nodes, int64_t heads, int64_t dim);
+int64_t tx_gat_fused_mask_ld(int64_t heads, int64_t dim); /* bytes per row of maskbits: heads*dim/4 rounded up to 16 */
 int64_t tx_gat_fused_bwd_blocks(int64_t n_nodes, int64_t heads);
 int tx_gat_fused_fwd(const float* ft, int64_t ldf, const float* attn_l, const float* attn_r, const int32_t* in_ptr,
                      const int32_t* in_src, const int32_t* in_eid, int64_t n_nodes, int64_t heads, int64_t dim,
@@ -248,8 +249,8 @@ int tx_gemm_tn_tf32x3(const float* a_hi, const float* a_lo, int64_t lda, const f
 int tx_gemm_nt_tf32x3(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi, const float* b_lo, int64_t ldb,
                       float* c, int64_t ldc, int64_t m, int64_t n, int64_t k, void* stream);
 /* Same with a fused output transform: for columns c < heads*dim, C[row, c] *= keep ? (positive ? 1 : act_slope) / (1 - p_drop) : 0,
- * decoded from the sign/keep bytes written by tx_gat_fused_fwd (maskbits viewed as bytes; mask_stride = bytes per (row, head)
- * = 32 * ceil(dim / 128)).  Used for d(z_next) = d(ft_next) . W_next: the backward of "leaky_relu -> feat_drop"
+ * decoded from the sign/keep bytes written by tx_gat_fused_fwd (maskbits viewed as bytes; mask_stride =
+ * tx_gat_fused_mask_ld(heads, dim) bytes per row).  Used for d(z_next) = d(ft_next) . W_next: the backward of "leaky_relu -> feat_drop"
  * (reference autograd of model_zoo.py:215-216,82) is applied where the gradient is produced, so tx_gat_fused_bwd reads it as is. */
 typedef struct tx_gemm_epilogue {
   const uint8_t* act_mask;

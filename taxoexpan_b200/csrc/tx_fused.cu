@@ -23,7 +23,7 @@
 
 namespace tx {
 
-constexpr int kTileRows = 16;   // default backward tile window (rows); tiles are graph-aligned (TAXO_BWD_TILE_ROWS overrides)
+constexpr int kTileRows = 32;   // default backward tile window (rows); tiles are graph-aligned (TAXO_BWD_TILE_ROWS overrides; 16/32 measured, r13-r14)
 constexpr int kMaxNV = 4;       // up to 4 float4 per lane per head row -> D' <= 512
 
 template <int NV>
@@ -79,7 +79,8 @@ struct FusedFwdParams {
   float neg_slope; float attn_inv_keep; uint32_t attn_thr; uint64_t attn_seed; uint32_t attn_stream;
   float* alpha; float* alpha_d; float* elog;
   float* out; int64_t ldo;
-  uint32_t* maskbits;      // [n, H, NV, 32] bytes (8 words per (row, head, t)): per lane 4 sign bits | 4 keep bits << 4; may be null
+  uint32_t* maskbits;      // bytes [n, mask_ld]: byte (h*D + c)/4 of a row = 4 sign bits | 4 keep bits << 4 of columns c..c+3; may be null
+  int mask_ld;             // = tx_gat_fused_mask_ld(H, D): H*D/4 rounded up to 16
   // epilogue
   int hidden; float act_slope; const float* next_pos_table; const int32_t* pos; int pos_dim;
   float next_inv_keep; uint32_t next_thr; uint64_t next_seed; uint32_t next_stream;
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(256, 3) gat_fused_fwd_kernel(const FusedFwdPar
         uint32_t code = 0;
 #pragma unroll
         for (int u = 0; u < 4; ++u) code |= ((posv[u] ? 1u : 0u) | (keep[u] ? 16u : 0u)) << u;
-        reinterpret_cast<uint8_t*>(p.maskbits)[(((int64_t)i * H + h) * NV + t) * 32 + lane] = (uint8_t)(valid ? code : 0u);
+        if (valid) reinterpret_cast<uint8_t*>(p.maskbits)[(int64_t)i * p.mask_ld + ((h * D + c) >> 2)] = (uint8_t)code;
       }
     }
     // position-embedding append + zero padding (once per row: the warp of the last head)
@@ -218,14 +219,14 @@ __global__ void __launch_bounds__(256, 3) gat_fused_fwd_kernel(const FusedFwdPar
 // ---------------------------------------------------------------------------------------------------------
 struct FusedBwdParams {
   const float* g; int64_t ldg; int64_t g_head_stride; float g_scale;
-  const uint32_t* maskbits; int has_keep_plane; float act_slope; float next_inv_keep;
+  const uint32_t* maskbits; int mask_ld; int has_keep_plane; float act_slope; float next_inv_keep;
   const float* ft; int64_t ldf;
   const float* alpha; const float* alpha_d; const float* elog;
   const float* attn_l; const float* attn_r;
   const int32_t* in_ptr; const int32_t* in_src; const int32_t* in_eid;
   const int32_t* out_ptr; const int32_t* out_dst; const int32_t* out_slot;
   const int32_t* node_off; int n_graphs;
-  int n; int H; int D; int tile_rows;
+  int n; int H; int D; int tile_rows; int stage_meta;
   float neg_slope; float attn_inv_keep; uint32_t attn_thr; uint64_t attn_seed; uint32_t attn_stream;
   float* ds; float* da2;
   float* dft; int64_t ldd;
@@ -241,7 +242,7 @@ __device__ __forceinline__ void load_g_row(const FusedBwdParams& p, int i, int h
     const int c = (lane + 32 * t) * 4;
     float4 x = c < p.D ? __ldg(reinterpret_cast<const float4*>(row + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.maskbits) {
-      uint32_t code = __ldg(reinterpret_cast<const uint8_t*>(p.maskbits) + (((int64_t)i * p.H + h) * NV + t) * 32 + lane);
+      uint32_t code = c < p.D ? __ldg(reinterpret_cast<const uint8_t*>(p.maskbits) + (int64_t)i * p.mask_ld + ((h * p.D + c) >> 2)) : 0u;
       if (!p.has_keep_plane) code |= 0xF0u;
       const float on = p.next_inv_keep, neg = p.act_slope * p.next_inv_keep;
       x.x *= (code & 16u) ? ((code & 1u) ? on : neg) : 0.f;
@@ -263,11 +264,13 @@ __device__ __forceinline__ int lower_bound_i32(const int32_t* __restrict__ a, in
 }
 
 constexpr int kHeavyOut = 12;   // sources with more out-edges than this are processed by the whole CTA
+constexpr int kStRows = 96;     // tile metadata staged in shared memory when the tile has <= kStRows rows ...
+constexpr int kStEdges = 192;   // ... and <= kStEdges edges (else the same code reads the global arrays)
 
-// dynamic smem: s_l, s_r [NV*32] float4 | s_acc [8][2][NV*32] float4 (per-warp d(attn) accumulators) | s_part [8][NV*32]
 #ifndef TX_BWD_MIN_BLOCKS
 #define TX_BWD_MIN_BLOCKS 2   /* 128 registers, no spills: measured 0.71 ms vs 0.85 ms at 3 CTAs/SM with spills (r11) */
 #endif
+// dynamic smem: s_l, s_r [NV*32] float4 | s_acc [8][2][NV*32] float4 (per-warp d(attn) accumulators) | s_part [8][NV*32]
 template <int NV>
 __global__ void __launch_bounds__(256, TX_BWD_MIN_BLOCKS) gat_fused_bwd_kernel(const FusedBwdParams p) {
   extern __shared__ float4 smem_f4[];
@@ -275,6 +278,10 @@ __global__ void __launch_bounds__(256, TX_BWD_MIN_BLOCKS) gat_fused_bwd_kernel(c
   float4* s_r = s_l + NV * 32;
   float4* s_acc = s_r + NV * 32;            // [(w*2 + lr) * NV*32 + q]
   float4* s_part = s_acc + 16 * NV * 32;    // [w * NV*32 + q]
+  // tile metadata (CSR slices, attention coefficients of this head) and the ds / da2 exchange between the two phases
+  __shared__ int s_inptr[kStRows + 1], s_outptr[kStRows + 1], s_insrc[kStEdges], s_outdst[kStEdges], s_outslot[kStEdges];
+  __shared__ float s_alpha[kStEdges], s_alphad[kStEdges], s_elog[kStEdges], s_keepw[kStEdges], s_ds[kStEdges], s_da2[kStRows];
+  __shared__ int s_bounds[2][2];
   const int h = blockIdx.y;
   const int H = p.H, D = p.D;
   for (int t = threadIdx.x; t < NV * 32; t += blockDim.x) {
@@ -283,14 +290,12 @@ __global__ void __launch_bounds__(256, TX_BWD_MIN_BLOCKS) gat_fused_bwd_kernel(c
     s_r[t] = c < D ? __ldg(reinterpret_cast<const float4*>(p.attn_r + (int64_t)h * D + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (int t = threadIdx.x; t < 16 * NV * 32; t += blockDim.x) s_acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-  __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const bool attn_drop = p.attn_thr != 0;
   float4* my_accl = s_acc + (wid * 2 + 0) * NV * 32;
   float4* my_accr = s_acc + (wid * 2 + 1) * NV * 32;
   const float* fbase = p.ft + (int64_t)h * D;
   const int n_tiles = (p.n + p.tile_rows - 1) / p.tile_rows;
-  __shared__ int s_bounds[2][2];
   auto tile_bounds = [&](int tile, int slot) {   // graphs whose first row lies in [tile*R, (tile+1)*R)
     if (tile < n_tiles) {
       const int gb = lower_bound_i32(p.node_off, p.n_graphs + 1, tile * p.tile_rows);
@@ -306,6 +311,10 @@ __global__ void __launch_bounds__(256, TX_BWD_MIN_BLOCKS) gat_fused_bwd_kernel(c
   int slot = 0;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, slot ^= 1) {
     const int r0 = s_bounds[slot][0], r1 = s_bounds[slot][1];
+    const int nrows = r1 - r0;
+    const int s0 = nrows > 0 ? __ldg(p.in_ptr + r0) : 0, s1 = nrows > 0 ? __ldg(p.in_ptr + r1) : 0;
+    const int o0 = nrows > 0 ? __ldg(p.out_ptr + r0) : 0, o1 = nrows > 0 ? __ldg(p.out_ptr + r1) : 0;
+    const bool staged = p.stage_meta && nrows <= kStRows && (s1 - s0) <= kStEdges && (o1 - o0) <= kStEdges;
     if (wid == 7) {   // bounds of this CTA's next tile + L2 prefetch of its g / ft rows while this tile is processed
       if (lane == 0) tile_bounds(tile + gridDim.x, slot ^ 1);
       __syncwarp();
@@ -315,80 +324,106 @@ __global__ void __launch_bounds__(256, TX_BWD_MIN_BLOCKS) gat_fused_bwd_kernel(c
         prefetch_l2(fbase + (int64_t)r * p.ldf, (uint32_t)D * 4u);
       }
     }
+    if (staged) {     // one coalesced sweep instead of 3-4 dependent L2 round trips per row in each phase
+      for (int t = threadIdx.x; t <= nrows; t += blockDim.x) {
+        s_inptr[t] = __ldg(p.in_ptr + r0 + t);
+        s_outptr[t] = __ldg(p.out_ptr + r0 + t);
+      }
+      for (int t = threadIdx.x; t < s1 - s0; t += blockDim.x) {
+        const int64_t o = (int64_t)(s0 + t) * H + h;
+        s_insrc[t] = __ldg(p.in_src + s0 + t);
+        s_alpha[t] = __ldg(p.alpha + o);
+        s_alphad[t] = __ldg(p.alpha_d + o);
+        s_elog[t] = __ldg(p.elog + o);
+        s_keepw[t] = !attn_drop ? 1.f
+                   : (drop_keep1(p.attn_seed, p.attn_stream, (uint64_t)((int64_t)__ldg(p.in_eid + s0 + t) * H + h), p.attn_thr) ? p.attn_inv_keep : 0.f);
+      }
+      for (int t = threadIdx.x; t < o1 - o0; t += blockDim.x) {
+        s_outdst[t] = __ldg(p.out_dst + o0 + t);
+        s_outslot[t] = __ldg(p.out_slot + o0 + t);
+      }
+      __syncthreads();
+    }
+    auto IN_PTR = [&](int i) { return staged ? s_inptr[i - r0] : __ldg(p.in_ptr + i); };
+    auto IN_SRC = [&](int k) { return staged ? s_insrc[k - s0] : __ldg(p.in_src + k); };
+    auto OUT_PTR = [&](int j) { return staged ? s_outptr[j - r0] : __ldg(p.out_ptr + j); };
+    auto OUT_DST = [&](int k) { return staged ? s_outdst[k - o0] : __ldg(p.out_dst + k); };
+    auto OUT_SLOT = [&](int k) { return staged ? s_outslot[k - o0] : __ldg(p.out_slot + k); };
+    auto ALPHA = [&](int k) { return staged ? s_alpha[k - s0] : __ldg(p.alpha + (int64_t)k * H + h); };
+    auto ALPHAD = [&](int k) { return staged ? s_alphad[k - s0] : __ldg(p.alpha_d + (int64_t)k * H + h); };
+    auto ELOG = [&](int k) { return staged ? s_elog[k - s0] : __ldg(p.elog + (int64_t)k * H + h); };
+    auto KEEPW = [&](int k) {
+      if (!attn_drop) return 1.f;
+      if (staged) return s_keepw[k - s0];
+      return drop_keep1(p.attn_seed, p.attn_stream, (uint64_t)((int64_t)__ldg(p.in_eid + k) * H + h), p.attn_thr) ? p.attn_inv_keep : 0.f;
+    };
+    auto DS_W = [&](int k, float v) { if (staged) s_ds[k - s0] = v; else p.ds[(int64_t)k * H + h] = v; };
+    auto DS_R = [&](int k) { return staged ? s_ds[k - s0] : p.ds[(int64_t)k * H + h]; };
     // ---------------- phase A: per destination: d(alpha~) = <g_i, ft_j>, softmax / leaky-relu backward ----------------
     for (int i = r0 + wid; i < r1; i += 8) {
-      const int beg = __ldg(p.in_ptr + i), end = __ldg(p.in_ptr + i + 1);
+      const int beg = IN_PTR(i), end = IN_PTR(i + 1);
       const int deg = end - beg;
       float4 gi[NV], ra[NV], rb[NV];
-      if (deg > 0) load_row<NV>(fbase + (int64_t)__ldg(p.in_src + beg) * p.ldf, lane, D, ra);
+      if (deg > 0) load_row<NV>(fbase + (int64_t)IN_SRC(beg) * p.ldf, lane, D, ra);
       load_g_row<NV>(p, i, h, lane, gi);
       float d_mine = 0.f;
       auto edge = [&](const float4 (&row)[NV], int k) {
         const float d = warp_sum(dot_rows<NV>(gi, row)) * p.g_scale;
         if (lane == ((k - beg) & 31)) d_mine = d;
-        if (deg > 32 && lane == 0) p.ds[(int64_t)k * H + h] = d;
+        if (deg > 32 && lane == 0) DS_W(k, d);
       };
       for (int k = beg; k < end;) {
-        if (k + 1 < end) load_row<NV>(fbase + (int64_t)__ldg(p.in_src + k + 1) * p.ldf, lane, D, rb);
+        if (k + 1 < end) load_row<NV>(fbase + (int64_t)IN_SRC(k + 1) * p.ldf, lane, D, rb);
         edge(ra, k);
         if (++k >= end) break;
-        if (k + 1 < end) load_row<NV>(fbase + (int64_t)__ldg(p.in_src + k + 1) * p.ldf, lane, D, ra);
+        if (k + 1 < end) load_row<NV>(fbase + (int64_t)IN_SRC(k + 1) * p.ldf, lane, D, ra);
         edge(rb, k);
         ++k;
       }
+      float a2;
       if (deg <= 32) {
         float da = 0.f, a = 0.f;
-        const int64_t o = (int64_t)(beg + lane) * H + h;
         if (lane < deg) {
-          da = d_mine;
-          if (attn_drop)
-            da = drop_keep1(p.attn_seed, p.attn_stream, (uint64_t)((int64_t)__ldg(p.in_eid + beg + lane) * H + h), p.attn_thr) ? da * p.attn_inv_keep : 0.f;
-          a = __ldg(p.alpha + o);
+          da = d_mine * KEEPW(beg + lane);
+          a = ALPHA(beg + lane);
         }
         const float tsum = warp_sum(a * da);
         float dsv = 0.f;
         if (lane < deg) {
           const float de = a * (da - tsum);
-          dsv = __ldg(p.elog + o) > 0.f ? de : de * p.neg_slope;
-          p.ds[o] = dsv;
+          dsv = ELOG(beg + lane) > 0.f ? de : de * p.neg_slope;
+          DS_W(beg + lane, dsv);
         }
-        const float a2 = warp_sum(dsv);
-        if (lane == 0) p.da2[(int64_t)i * H + h] = a2;
+        a2 = warp_sum(dsv);
       } else {
         __syncwarp();
         float tsum = 0.f;
-        for (int k = beg + lane; k < end; k += 32) {
-          float da = p.ds[(int64_t)k * H + h];
-          if (attn_drop)
-            da = drop_keep1(p.attn_seed, p.attn_stream, (uint64_t)((int64_t)__ldg(p.in_eid + k) * H + h), p.attn_thr) ? da * p.attn_inv_keep : 0.f;
-          tsum = fmaf(__ldg(p.alpha + (int64_t)k * H + h), da, tsum);
-        }
+        for (int k = beg + lane; k < end; k += 32) tsum = fmaf(ALPHA(k), DS_R(k) * KEEPW(k), tsum);
         tsum = warp_sum(tsum);
-        float a2 = 0.f;
+        a2 = 0.f;
         for (int k = beg + lane; k < end; k += 32) {
-          float da = p.ds[(int64_t)k * H + h];
-          if (attn_drop)
-            da = drop_keep1(p.attn_seed, p.attn_stream, (uint64_t)((int64_t)__ldg(p.in_eid + k) * H + h), p.attn_thr) ? da * p.attn_inv_keep : 0.f;
-          const float de = __ldg(p.alpha + (int64_t)k * H + h) * (da - tsum);
-          const float dsv = __ldg(p.elog + (int64_t)k * H + h) > 0.f ? de : de * p.neg_slope;
-          p.ds[(int64_t)k * H + h] = dsv;
+          const float de = ALPHA(k) * (DS_R(k) * KEEPW(k) - tsum);
+          const float dsv = ELOG(k) > 0.f ? de : de * p.neg_slope;
+          DS_W(k, dsv);
           a2 += dsv;
         }
         a2 = warp_sum(a2);
-        if (lane == 0) p.da2[(int64_t)i * H + h] = a2;
+      }
+      if (lane == 0) {
+        if (staged) s_da2[i - r0] = a2; else p.da2[(int64_t)i * H + h] = a2;
       }
     }
     __syncthreads();   // ds / da2 of the whole tile are visible to the CTA
     // ---------------- phase B: per source (light rows: one warp each) ----------------
     for (int j = r0 + wid; j < r1; j += 8) {
-      const int beg = __ldg(p.out_ptr + j), end = __ldg(p.out_ptr + j + 1);
+      const int beg = OUT_PTR(j), end = OUT_PTR(j + 1);
       if (end - beg > kHeavyOut) continue;
       float4 ra[NV], rb[NV];
-      if (beg < end) load_g_row<NV>(p, __ldg(p.out_dst + beg), h, lane, ra);
+      if (beg < end) load_g_row<NV>(p, OUT_DST(beg), h, lane, ra);
       float d1 = 0.f;
-      if (beg + lane < end) d1 = p.ds[(int64_t)__ldg(p.out_slot + beg + lane) * H + h];
+      if (beg + lane < end) d1 = DS_R(OUT_SLOT(beg + lane));
       d1 = warp_sum(d1);
-      const float d2 = p.da2[(int64_t)j * H + h];
+      const float d2 = staged ? s_da2[j - r0] : p.da2[(int64_t)j * H + h];
       float4 acc[NV];
       {
         float4 fj[NV];
@@ -405,11 +440,11 @@ __global__ void __launch_bounds__(256, TX_BWD_MIN_BLOCKS) gat_fused_bwd_kernel(c
         }
       }
       for (int k = beg; k < end;) {
-        if (k + 1 < end) load_g_row<NV>(p, __ldg(p.out_dst + k + 1), h, lane, rb);
-        axpy_row<NV>(__ldg(p.alpha_d + (int64_t)__ldg(p.out_slot + k) * H + h) * p.g_scale, ra, acc);
+        if (k + 1 < end) load_g_row<NV>(p, OUT_DST(k + 1), h, lane, rb);
+        axpy_row<NV>(ALPHAD(OUT_SLOT(k)) * p.g_scale, ra, acc);
         if (++k >= end) break;
-        if (k + 1 < end) load_g_row<NV>(p, __ldg(p.out_dst + k + 1), h, lane, ra);
-        axpy_row<NV>(__ldg(p.alpha_d + (int64_t)__ldg(p.out_slot + k) * H + h) * p.g_scale, rb, acc);
+        if (k + 1 < end) load_g_row<NV>(p, OUT_DST(k + 1), h, lane, ra);
+        axpy_row<NV>(ALPHAD(OUT_SLOT(k)) * p.g_scale, rb, acc);
         ++k;
       }
       float* orow = p.dft + (int64_t)j * p.ldd + (int64_t)h * D;
@@ -421,24 +456,24 @@ __global__ void __launch_bounds__(256, TX_BWD_MIN_BLOCKS) gat_fused_bwd_kernel(c
     }
     // ---------------- phase B, heavy sources (e.g. the anchor of a large egonet): the whole CTA per row ----------------
     for (int jb = r0; jb < r1; jb += 32) {
-     const int jl = jb + lane;
-     unsigned heavy = __ballot_sync(0xffffffffu, jl < r1 && (__ldg(p.out_ptr + min(jl, r1 - 1) + 1) - __ldg(p.out_ptr + min(jl, r1 - 1))) > kHeavyOut);
+     const int jl = min(jb + lane, r1 - 1);
+     unsigned heavy = __ballot_sync(0xffffffffu, jb + lane < r1 && (OUT_PTR(jl + 1) - OUT_PTR(jl)) > kHeavyOut);
      while (heavy) {            // identical in every warp of the CTA -> uniform control flow around the barriers below
       const int j = jb + __ffs(heavy) - 1;
       heavy &= heavy - 1;
-      const int beg = __ldg(p.out_ptr + j), end = __ldg(p.out_ptr + j + 1);
+      const int beg = OUT_PTR(j), end = OUT_PTR(j + 1);
       float4 acc[NV], ra[NV], rb[NV];
 #pragma unroll
       for (int t = 0; t < NV; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
       int k = beg + wid;
-      if (k < end) load_g_row<NV>(p, __ldg(p.out_dst + k), h, lane, ra);
+      if (k < end) load_g_row<NV>(p, OUT_DST(k), h, lane, ra);
       while (k < end) {
-        if (k + 8 < end) load_g_row<NV>(p, __ldg(p.out_dst + k + 8), h, lane, rb);
-        axpy_row<NV>(__ldg(p.alpha_d + (int64_t)__ldg(p.out_slot + k) * H + h) * p.g_scale, ra, acc);
+        if (k + 8 < end) load_g_row<NV>(p, OUT_DST(k + 8), h, lane, rb);
+        axpy_row<NV>(ALPHAD(OUT_SLOT(k)) * p.g_scale, ra, acc);
         k += 8;
         if (k >= end) break;
-        if (k + 8 < end) load_g_row<NV>(p, __ldg(p.out_dst + k + 8), h, lane, ra);
-        axpy_row<NV>(__ldg(p.alpha_d + (int64_t)__ldg(p.out_slot + k) * H + h) * p.g_scale, rb, acc);
+        if (k + 8 < end) load_g_row<NV>(p, OUT_DST(k + 8), h, lane, ra);
+        axpy_row<NV>(ALPHAD(OUT_SLOT(k)) * p.g_scale, rb, acc);
         k += 8;
       }
 #pragma unroll
@@ -446,9 +481,9 @@ __global__ void __launch_bounds__(256, TX_BWD_MIN_BLOCKS) gat_fused_bwd_kernel(c
       __syncthreads();
       if (wid == 0) {
         float d1 = 0.f;
-        for (int kk = beg + lane; kk < end; kk += 32) d1 += p.ds[(int64_t)__ldg(p.out_slot + kk) * H + h];
+        for (int kk = beg + lane; kk < end; kk += 32) d1 += DS_R(OUT_SLOT(kk));
         d1 = warp_sum(d1);
-        const float d2 = p.da2[(int64_t)j * H + h];
+        const float d2 = staged ? s_da2[j - r0] : p.da2[(int64_t)j * H + h];
         float4 fj[NV];
         load_row<NV>(fbase + (int64_t)j * p.ldf, lane, D, fj);
         float* orow = p.dft + (int64_t)j * p.ldd + (int64_t)h * D;
@@ -473,7 +508,7 @@ __global__ void __launch_bounds__(256, TX_BWD_MIN_BLOCKS) gat_fused_bwd_kernel(c
       __syncthreads();
      }
     }
-    __syncthreads();   // next tile: its bounds (written by warp 7) are visible, s_part is free
+    __syncthreads();   // next tile: its bounds (written by warp 7) are visible, staging buffers and s_part are free
   }
   // ---- d(attn) partials: fixed-order reduction over the 8 per-warp accumulators ----
   __syncthreads();
@@ -527,9 +562,10 @@ int tx_gat_fused_supported(int64_t heads, int64_t dim, int32_t mean_heads) {
   return 1;
 }
 
+int64_t tx_gat_fused_mask_ld(int64_t heads, int64_t dim) { return ((heads * dim / 4 + 15) / 16) * 16; }
+
 int64_t tx_gat_fused_mask_words(int64_t n_nodes, int64_t heads, int64_t dim) {
-  const int64_t nv = (dim + 127) / 128;
-  return n_nodes * heads * nv * 8;
+  return n_nodes * tx_gat_fused_mask_ld(heads, dim) / 4;
 }
 
 static int bwd_tile_rows() {
@@ -573,6 +609,7 @@ int tx_gat_fused_fwd(const float* ft, int64_t ldf, const float* attn_l, const fl
   p.n = (int)n_nodes; p.H = (int)heads; p.D = (int)dim; p.neg_slope = neg_slope;
   p.attn_inv_keep = 1.f / (1.f - p_attn); p.attn_thr = drop_threshold(p_attn); p.attn_seed = attn_seed; p.attn_stream = attn_stream_id;
   p.alpha = alpha; p.alpha_d = alpha_d ? alpha_d : alpha; p.elog = elog; p.out = out; p.ldo = ldo; p.maskbits = maskbits;
+  p.mask_ld = (int)tx_gat_fused_mask_ld(heads, dim);
   p.hidden = epi->mean_heads ? 0 : 1; p.act_slope = epi->act_slope; p.next_pos_table = epi->next_pos_table; p.pos = epi->pos;
   p.pos_dim = (int)epi->pos_dim; p.next_inv_keep = 1.f / (1.f - epi->p_drop); p.next_thr = drop_threshold(epi->p_drop);
   p.next_seed = epi->seed; p.next_stream = epi->stream_id;
@@ -610,6 +647,7 @@ int tx_gat_fused_bwd(const float* g, int64_t ldg, int64_t g_head_stride, float g
   if (n_nodes == 0) return TX_OK;
   FusedBwdParams p;
   p.g = g; p.ldg = ldg; p.g_head_stride = g_head_stride; p.g_scale = g_scale; p.maskbits = maskbits; p.has_keep_plane = has_keep_plane;
+  p.mask_ld = (int)tx_gat_fused_mask_ld(heads, dim);
   p.act_slope = act_slope; p.next_inv_keep = 1.f / (1.f - p_next); p.ft = ft; p.ldf = ldf; p.alpha = alpha;
   p.alpha_d = alpha_d ? alpha_d : alpha; p.elog = elog; p.attn_l = attn_l; p.attn_r = attn_r;
   p.in_ptr = in_ptr; p.in_src = in_src; p.in_eid = in_eid; p.out_ptr = out_ptr; p.out_dst = out_dst; p.out_slot = out_slot;
@@ -617,6 +655,7 @@ int tx_gat_fused_bwd(const float* g, int64_t ldg, int64_t g_head_stride, float g
   p.neg_slope = neg_slope; p.attn_inv_keep = 1.f / (1.f - p_attn); p.attn_thr = drop_threshold(p_attn); p.attn_seed = attn_seed;
   p.attn_stream = attn_stream_id; p.ds = ds; p.da2 = da2; p.dft = dft; p.ldd = ldd; p.dattn_partial = dattn_partial;
   p.tile_rows = bwd_tile_rows();
+  { const char* e = getenv("TAXO_BWD_STAGE"); p.stage_meta = e ? atoi(e) : 1; }
   const int nv = (int)((dim + 127) / 128);
   dim3 grid((unsigned)tx_gat_fused_bwd_blocks(n_nodes, heads), (unsigned)heads);
   cudaStream_t st = (cudaStream_t)stream;

@@ -105,8 +105,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 // Optional fused output transform of the NT kernel: C[row, c] *= keep ? (positive ? on : neg) : 0 for c < feat_cols, decoded
-// from the sign/keep bytes the fused GAT forward wrote (1 byte per aligned group of 4 columns of a head, groups contiguous
-// per (row, head): byte index = (row * heads + head) * stride + (c - head*dim) / 4).  This is the backward of
+// from the sign/keep bytes the fused GAT forward wrote (1 byte per aligned group of 4 columns: byte index = row * stride + c / 4,
+// stride = tx_gat_fused_mask_ld, a multiple of 16, so a thread's 32-column chunks are aligned 8-byte runs).  This is the backward of
 // "leaky-relu -> dropout" applied right where d(z) is produced (reference: autograd of model_zoo.py:215-216 and :82).
 struct GemmEpilogue {
   const uint8_t* mask;
@@ -133,8 +133,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   constexpr int B_BYTES = BN * kBK * 4;
   constexpr int STAGE_BYTES = 2 * kABytes + 2 * B_BYTES;
   constexpr int BOX_BYTES = kBK * 128;       // TN: one {32 cols, kBK rows} box
-  constexpr int HALF = BN / 2;               // columns owned by one epilogue warp
-  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  constexpr int HALF = ((BN / 32 + 1) / 2) * 32;   // columns owned by an epilogue warp of group 0 (group 1: BN - HALF), chunks of 32
+  constexpr uint32_t TMEM_COLS = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  static_assert(BN % 32 == 0 && BN >= 64 && BN <= 256, "BN must be a multiple of 32 in [64, 256]");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);   // full[S], empty[S], tfull[2], tempty[2]
@@ -242,7 +243,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     }
   } else {             // ===== epilogue warps: drain chunk accumulators into fp32 registers, then store =====
     const int q = warp & 3;                                    // a warp may only touch TMEM lanes [32 q, 32 q + 32)
-    const int hsel = (warp - 2) >> 2;                          // which half of the BN columns
+    const int hsel = (warp - 2) >> 2;                          // which part of the BN columns: [0, HALF) or [HALF, BN)
+    const int n_chunks32 = hsel == 0 ? HALF / 32 : (BN - HALF) / 32;
     float acc[HALF];
 #pragma unroll
     for (int c = 0; c < HALF; ++c) acc[c] = 0.f;
@@ -253,10 +255,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
       const uint32_t tacc = tmem_base + (uint32_t)(buf * BN + hsel * HALF) + ((uint32_t)(q * 32) << 16);
 #pragma unroll
       for (int c = 0; c < HALF / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tacc + (uint32_t)(c * 32), r);
+        if (c < n_chunks32) {                                  // warp-uniform
+          uint32_t r[32];
+          tmem_ld32(tacc + (uint32_t)(c * 32), r);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(r[j]);
+          for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(r[j]);
+        }
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -265,14 +269,23 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     const int row = m0 + q * 32 + lane;
     if (row < M) {
       float* crow = C + (int64_t)blockIdx.z * split_stride + (int64_t)row * ldc + n0 + hsel * HALF;
+      uint32_t mw[HALF / 16];                                  // 4 mask bytes (16 columns) per word
+      const bool masked = !TN && epi.mask != nullptr;
+      if (masked) {
+#pragma unroll
+        for (int w = 0; w < HALF / 16; ++w) {
+          const int col = n0 + hsel * HALF + w * 16;
+          mw[w] = (w < n_chunks32 * 2 && col < epi.feat_cols)
+                      ? __ldg(reinterpret_cast<const uint32_t*>(epi.mask + (int64_t)row * epi.stride + (col >> 2))) : 0xFFFFFFFFu;
+        }
+      }
 #pragma unroll
       for (int j = 0; j < HALF / 4; ++j) {
         const int col = n0 + hsel * HALF + j * 4;
-        if (col < n_store) {
+        if (j < n_chunks32 * 8 && col < n_store) {
           float4 v = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-          if (!TN && epi.mask != nullptr && col < epi.feat_cols) {
-            const int hd = col / epi.dim;
-            uint32_t code = __ldg(epi.mask + ((int64_t)row * epi.heads + hd) * epi.stride + ((col - hd * epi.dim) >> 2));
+          if (masked && col < epi.feat_cols) {
+            uint32_t code = (mw[j >> 2] >> (8 * (j & 3))) & 0xFFu;
             if (!epi.has_keep) code |= 0xF0u;
             v.x *= (code & 16u) ? ((code & 1u) ? epi.on : epi.neg) : 0.f;
             v.y *= (code & 32u) ? ((code & 2u) ? epi.on : epi.neg) : 0.f;
@@ -414,8 +427,16 @@ using namespace tx;
 
 extern "C" {
 
+// tile width: 64 / 128 for narrow outputs, else 256 unless 160-wide tiles waste fewer MMA columns (e.g. N = 300: 2 x 160 vs 2 x 256)
+static int pick_bn(int64_t n) {
+  if (n <= 64) return 64;
+  if (n <= 128) return 128;
+  const int64_t w256 = ((n + 255) / 256) * 256, w160 = ((n + 159) / 160) * 160;
+  return w160 * 10 < w256 * 8 ? 160 : 256;      // switch only for a > 20 % saving
+}
+
 int64_t tx_gemm_tn_splits(int64_t m, int64_t n, int64_t r) {
-  const int64_t bn = n > 128 ? 256 : (n > 64 ? 128 : 64);
+  const int64_t bn = pick_bn(n);
   const int64_t tiles = ((m + kBM - 1) / kBM) * ((n + bn - 1) / bn);
   int64_t s = kNumSms / (tiles > 0 ? tiles : 1);
   const int64_t kbt = (r + kBK - 1) / kBK;
@@ -433,6 +454,7 @@ int tx_gemm_tn_tf32x3(const float* a_hi, const float* a_lo, int64_t lda, const f
   TX_REQUIRE(ldc % 4 == 0 && ldc >= ((n + 3) / 4) * 4 && split_stride % 4 == 0 && split_stride >= m * ldc, "gemm_tn: bad ldc / split_stride");
   TX_REQUIRE(splits >= 1 && splits <= 65535, "gemm_tn: bad split count");
   cudaStream_t st = (cudaStream_t)stream;
+  if (n > 128 && pick_bn(n) == 160) return launch_gemm<160, 3, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c_partial, ldc, split_stride, m, n, r, (int)splits, st);
   if (n > 128) return launch_gemm<256, 2, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c_partial, ldc, split_stride, m, n, r, (int)splits, st);
   if (n > 64) return launch_gemm<128, 3, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c_partial, ldc, split_stride, m, n, r, (int)splits, st);
   return launch_gemm<64, 4, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c_partial, ldc, split_stride, m, n, r, (int)splits, st);
@@ -464,7 +486,8 @@ int tx_gemm_nt_tf32x3_ex(const float* a_hi, const float* a_lo, int64_t lda, cons
   TX_REQUIRE(ldc >= ((n + 3) / 4) * 4, "gemm: ldc must hold round4(N) columns");
   GemmEpilogue epi{nullptr, 0, 1, 0, 0, 0, 1.f, 1.f};
   if (e && e->act_mask) {
-    TX_REQUIRE(e->heads > 0 && e->dim > 0 && e->dim % 4 == 0 && e->mask_stride >= (e->dim + 3) / 4, "gemm epilogue: bad mask geometry");
+    TX_REQUIRE(e->heads > 0 && e->dim > 0 && e->dim % 4 == 0 && e->mask_stride % 16 == 0 && e->mask_stride >= e->heads * e->dim / 4 &&
+               aligned16(e->act_mask), "gemm epilogue: bad mask geometry");
     TX_REQUIRE(e->col0 % 4 == 0 && e->col0 >= 0, "gemm epilogue: col0 must be a non-negative multiple of 4");
     TX_REQUIRE(e->col0 == 0, "gemm epilogue: a column offset is not supported with a fused mask");
     TX_REQUIRE(e->p_drop >= 0.f && e->p_drop < 1.f, "gemm epilogue: p_drop must be in [0,1)");
@@ -472,6 +495,7 @@ int tx_gemm_nt_tf32x3_ex(const float* a_hi, const float* a_lo, int64_t lda, cons
     epi.feat_cols = (int)(e->heads * e->dim); epi.has_keep = e->has_keep_plane;
     epi.on = 1.f / (1.f - e->p_drop); epi.neg = e->act_slope * epi.on;
   }
+  if (n > 128 && pick_bn(n) == 160) return launch_gemm<160, 3, false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
   if (n > 128) return launch_gemm<256, 2, false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
   if (n > 64) return launch_gemm<128, 3, false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
   return launch_gemm<64, 4, false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);

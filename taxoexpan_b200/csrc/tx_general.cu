@@ -716,6 +716,147 @@ __global__ void __launch_bounds__(256) readout_bwd_kernel(int kind, const float*
   }
 }
 
+// ---- fast readout path (MEAN / WMEAN, 16-byte aligned rows, D <= 512): whole row of a graph per warp iteration, 4 rows
+// in flight per warp (the generic kernels above keep one row in flight and were latency-bound: 105 / 165 us for 75 MB) ----
+template <int NV>
+__device__ __forceinline__ void ro_load(const float* __restrict__ p, int lane, int D, float4 (&v)[NV]) {
+#pragma unroll
+  for (int t = 0; t < NV; ++t) {
+    const int c = (lane + 32 * t) * 4;
+    v[t] = c < D ? __ldg(reinterpret_cast<const float4*>(p + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256) readout_fwd_fast_kernel(int kind, const float* __restrict__ h, int64_t ldh,
+                                                               const int32_t* __restrict__ pos, const float* __restrict__ pw,
+                                                               const int32_t* __restrict__ node_off, int n_graphs, int D,
+                                                               float* __restrict__ hg, int64_t ldhg) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  float sw[3] = {1.f, 1.f, 1.f};
+  if (kind == TX_READOUT_WMEAN) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) sw[r] = softplus_f(__ldg(pw + r));
+  }
+  for (int g = warp; g < n_graphs; g += nwarps) {
+    const int beg = __ldg(node_off + g), end = __ldg(node_off + g + 1);
+    float S = 0.f;
+    float4 acc[NV];
+#pragma unroll
+    for (int t = 0; t < NV; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = beg; i < end; i += 4) {
+      float4 r[4][NV];
+      float a[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool ok = i + u < end;
+        const int row = ok ? i + u : beg;
+        const int pr = kind == TX_READOUT_WMEAN ? __ldg(pos + row) : 0;
+        a[u] = ok ? (pr == 0 ? sw[0] : (pr == 1 ? sw[1] : sw[2])) : 0.f;
+        ro_load<NV>(h + (int64_t)row * ldh, lane, D, r[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        S += a[u];
+#pragma unroll
+        for (int t = 0; t < NV; ++t) {
+          acc[t].x = fmaf(a[u], r[u][t].x, acc[t].x); acc[t].y = fmaf(a[u], r[u][t].y, acc[t].y);
+          acc[t].z = fmaf(a[u], r[u][t].z, acc[t].z); acc[t].w = fmaf(a[u], r[u][t].w, acc[t].w);
+        }
+      }
+    }
+    float* orow = hg + (int64_t)g * ldhg;
+#pragma unroll
+    for (int t = 0; t < NV; ++t) {
+      const int c = (lane + 32 * t) * 4;
+      if (c < D) *reinterpret_cast<float4*>(orow + c) = make_float4(acc[t].x / S, acc[t].y / S, acc[t].z / S, acc[t].w / S);
+    }
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256) readout_bwd_fast_kernel(int kind, const float* __restrict__ dhg, int64_t lddhg,
+                                                               const float* __restrict__ h, int64_t ldh,
+                                                               const float* __restrict__ hg, int64_t ldhg,
+                                                               const int32_t* __restrict__ pos, const float* __restrict__ pw,
+                                                               const int32_t* __restrict__ node_off, int n_graphs, int D,
+                                                               float* __restrict__ dh, int64_t lddh, float* __restrict__ dw_partial) {
+  __shared__ float sdw[8][3];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const bool wm = kind == TX_READOUT_WMEAN;
+  float sw[3] = {1.f, 1.f, 1.f}, sg[3] = {0.f, 0.f, 0.f};
+  if (wm) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const float w = __ldg(pw + r);
+      sw[r] = softplus_f(w);
+      sg[r] = w > 20.f ? 1.f : 1.f / (1.f + expf(-w));
+    }
+  }
+  float dw[3] = {0.f, 0.f, 0.f};
+  for (int g = warp; g < n_graphs; g += nwarps) {
+    const int beg = __ldg(node_off + g), end = __ldg(node_off + g + 1);
+    float4 d[NV], m[NV];
+    ro_load<NV>(dhg + (int64_t)g * lddhg, lane, D, d);
+    if (wm) ro_load<NV>(hg + (int64_t)g * ldhg, lane, D, m);
+    float S = 0.f;
+    for (int i = beg + lane; i < end; i += 32) {
+      const int pr = wm ? __ldg(pos + i) : 0;
+      S += pr == 0 ? sw[0] : (pr == 1 ? sw[1] : sw[2]);
+    }
+    S = warp_sum(S);
+    const float inv_s = 1.f / S;
+    for (int i = beg; i < end; i += 4) {
+      float4 r[4][NV];
+      int pr[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int row = i + u < end ? i + u : beg;
+        pr[u] = wm ? __ldg(pos + row) : 0;
+        if (wm) ro_load<NV>(h + (int64_t)row * ldh, lane, D, r[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (i + u < end) {                       // warp-uniform
+          const float a = pr[u] == 0 ? sw[0] : (pr[u] == 1 ? sw[1] : sw[2]);
+          const float sc = a * inv_s;
+          float dot = 0.f;
+          float* orow = dh + (int64_t)(i + u) * lddh;
+#pragma unroll
+          for (int t = 0; t < NV; ++t) {
+            const int c = (lane + 32 * t) * 4;
+            if (c < D) *reinterpret_cast<float4*>(orow + c) = make_float4(d[t].x * sc, d[t].y * sc, d[t].z * sc, d[t].w * sc);
+            if (wm) {
+              dot = fmaf(d[t].x, r[u][t].x - m[t].x, dot); dot = fmaf(d[t].y, r[u][t].y - m[t].y, dot);
+              dot = fmaf(d[t].z, r[u][t].z - m[t].z, dot); dot = fmaf(d[t].w, r[u][t].w - m[t].w, dot);
+            }
+          }
+          if (wm) {
+            dot = warp_sum(dot) * inv_s;
+            dw[0] += pr[u] == 0 ? dot * sg[0] : 0.f;
+            dw[1] += pr[u] == 1 ? dot * sg[1] : 0.f;
+            dw[2] += pr[u] == 2 ? dot * sg[2] : 0.f;
+          }
+        }
+      }
+    }
+  }
+  if (wm && dw_partial) {
+    if (lane == 0) { sdw[wid][0] = dw[0]; sdw[wid][1] = dw[1]; sdw[wid][2] = dw[2]; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      float t = sdw[0][threadIdx.x];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) t += sdw[w][threadIdx.x];
+      dw_partial[(int64_t)blockIdx.x * 3 + threadIdx.x] = t;
+    }
+  }
+}
+
 __global__ void dropout_keep_mask_kernel(uint64_t seed, uint32_t stream_id, int64_t first, int64_t n, uint32_t thr,
                                          uint8_t* __restrict__ keep) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -930,6 +1071,16 @@ int tx_readout_fwd(int32_t kind, const float* h, int64_t ldh, const int32_t* pos
   TX_REQUIRE(ldhg >= (kind == TX_READOUT_CONCAT ? 3 * dim : dim), "readout_fwd: ldhg too small");
   if (n_graphs == 0) return TX_OK;
   const int grid = readout_grid(n_graphs);
+  if (kind != TX_READOUT_CONCAT && dim <= 512 && vec4_ok(h, ldh, dim) && vec4_ok(hg, ldhg, dim)) {
+    switch ((int)((dim + 127) / 128)) {
+      case 1: readout_fwd_fast_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(kind, h, ldh, pos, pos_weight, node_off, (int)n_graphs, (int)dim, hg, ldhg); break;
+      case 2: readout_fwd_fast_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(kind, h, ldh, pos, pos_weight, node_off, (int)n_graphs, (int)dim, hg, ldhg); break;
+      case 3: readout_fwd_fast_kernel<3><<<grid, 256, 0, (cudaStream_t)stream>>>(kind, h, ldh, pos, pos_weight, node_off, (int)n_graphs, (int)dim, hg, ldhg); break;
+      default: readout_fwd_fast_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(kind, h, ldh, pos, pos_weight, node_off, (int)n_graphs, (int)dim, hg, ldhg); break;
+    }
+    TX_LAUNCH_CHECK("tx_readout_fwd");
+    return TX_OK;
+  }
   if (vec4_ok(h, ldh, dim) && vec4_ok(hg, ldhg, dim))
     readout_fwd_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(kind, h, ldh, pos, pos_weight, node_off, (int)n_graphs, (int)dim, hg, ldhg);
   else
@@ -947,6 +1098,17 @@ int tx_readout_bwd(int32_t kind, const float* dhg, int64_t lddhg, const float* h
   if (n_graphs == 0) return TX_OK;
   const int grid = readout_grid(n_graphs);
   const bool v4 = vec4_ok(dhg, lddhg, dim) && vec4_ok(dh, lddh, dim) && (kind != TX_READOUT_WMEAN || (vec4_ok(h, ldh, dim) && vec4_ok(hg, ldhg, dim)));
+  if (v4 && kind != TX_READOUT_CONCAT && dim <= 512) {
+    cudaStream_t st = (cudaStream_t)stream;
+    switch ((int)((dim + 127) / 128)) {
+      case 1: readout_bwd_fast_kernel<1><<<grid, 256, 0, st>>>(kind, dhg, lddhg, h, ldh, hg, ldhg, pos, pos_weight, node_off, (int)n_graphs, (int)dim, dh, lddh, dw_partial); break;
+      case 2: readout_bwd_fast_kernel<2><<<grid, 256, 0, st>>>(kind, dhg, lddhg, h, ldh, hg, ldhg, pos, pos_weight, node_off, (int)n_graphs, (int)dim, dh, lddh, dw_partial); break;
+      case 3: readout_bwd_fast_kernel<3><<<grid, 256, 0, st>>>(kind, dhg, lddhg, h, ldh, hg, ldhg, pos, pos_weight, node_off, (int)n_graphs, (int)dim, dh, lddh, dw_partial); break;
+      default: readout_bwd_fast_kernel<4><<<grid, 256, 0, st>>>(kind, dhg, lddhg, h, ldh, hg, ldhg, pos, pos_weight, node_off, (int)n_graphs, (int)dim, dh, lddh, dw_partial); break;
+    }
+    TX_LAUNCH_CHECK("tx_readout_bwd");
+    return TX_OK;
+  }
   if (v4)
     readout_bwd_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(kind, dhg, lddhg, h, ldh, hg, ldhg, pos, pos_weight, node_off,
                                                                   (int)n_graphs, (int)dim, dh, lddh, dw_partial);

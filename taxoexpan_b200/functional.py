@@ -47,9 +47,9 @@ FUSED_ENABLED = os.environ.get("TAXO_DISABLE_FUSED", "") == ""
 
 
 FUSED_MAX_GRAPH_NODES = 2048
-# apply the leaky-relu/dropout derivative of the previous layer's epilogue inside the d(z) GEMM epilogue (parity-tested; off by
-# default: measured +0.12 ms on the GEMM vs -0.03 ms on the fused backward kernel with byte-granular mask loads, r11)
-FUSE_DZ_EPILOGUE = os.environ.get("TAXO_FUSE_DZ_EPILOGUE", "") != ""
+# apply the leaky-relu/dropout derivative of the previous layer's epilogue inside the d(z) GEMM epilogue, so the fused backward
+# kernel reads d(z) as is (decoding the mask on each of its ~2.8 row loads cost 0.3 ms on L0; r11 / r13)
+FUSE_DZ_EPILOGUE = os.environ.get("TAXO_FUSE_DZ_EPILOGUE", "1") not in ("", "0")
 
 
 def use_fused(lib, heads: int, dim: int, mean_heads: int, st=None) -> bool:
@@ -166,8 +166,8 @@ def _layer_gemms_bwd(dy, f, saved, w_kf, k, ldz, c0, need_w, need_z, in_link=Non
                 w_hi, w_lo = split_tf32(w_kf[c0a:k], f)
                 epi = None
                 if FUSE_DZ_EPILOGUE and in_link is not None and in_link.mask is not None and c0a == 0:
-                    nv = (in_link.dim + 127) // 128
-                    epi = _lib.GemmEpilogue(act_mask=ptr(in_link.mask), heads=in_link.heads, dim=in_link.dim, mask_stride=32 * nv,
+                    epi = _lib.GemmEpilogue(act_mask=ptr(in_link.mask), heads=in_link.heads, dim=in_link.dim,
+                                            mask_stride=int(_lib.load().tx_gat_fused_mask_ld(in_link.heads, in_link.dim)),
                                             col0=0, act_slope=in_link.act_slope, p_drop=in_link.p_drop,
                                             has_keep_plane=1 if in_link.p_drop > 0.0 else 0)
                 gemm_nt_ps(d_hi, d_lo, f, w_hi, w_lo, k - c0a, out=dz[:, c0a:], epi=epi)

@@ -224,6 +224,13 @@ class EgonetBatch(DGLGraph):
             self._packed = self._packed.pin_memory()
         return self
 
+    def stage(self, device):
+        """Enqueue the host->device copy of the 4 count vectors on the CURRENT stream (e.g. a copy stream of a prefetching
+        loader); structure() then only launches the closed-form structure kernel."""
+        device = _require_cuda(device)
+        self._staged = self._packed.to(device, non_blocking=True)
+        return self
+
     def _build_edges(self):
         if not self._edges_built:
             from .synth import EgonetShapes, star_batch_arrays
@@ -275,7 +282,9 @@ class EgonetBatch(DGLGraph):
         st.is_star = True
         g = self._g
         with torch.cuda.device(device):
-            packed = self._packed.to(device, non_blocking=True)
+            packed = getattr(self, "_staged", None)
+            if packed is None or packed.device != device:
+                packed = self._packed.to(device, non_blocking=True)
             n_gp, n_sib = packed[:g], packed[g:2 * g]
             node_off, edge_off = packed[2 * g:3 * g + 1], packed[3 * g + 1:4 * g + 2]
             i32 = dict(dtype=torch.int32, device=device)
