@@ -271,12 +271,14 @@ def run_b200(args, rank, world, local_rank):
         Stats.reset()
         Stats.profiling = profile
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_host = time.perf_counter()
         e0.record()
         for i in range(steps):
             step_fn(i)
         if flush is not None:
             flush()
         e1.record()
+        timed.host_enqueue_ms = (time.perf_counter() - t_host) * 1e3 / max(steps, 1)
         barrier()
         Stats.profiling = False
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -290,6 +292,7 @@ def run_b200(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     total_ms, launches, _ = timed(step_resident, args.steps)
+    host_enqueue_ms = timed.host_enqueue_ms
     clocks = sampler.stop() if rank == 0 else None
 
     # per-kernel CUDA-event timings (separate pass so the headline loop carries no event overhead)
@@ -374,6 +377,7 @@ def run_b200(args, rank, world, local_rank):
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": x_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": round(e2e_ms / args.steps, 4)},
         "gpu_launches": launches,
+        "host_enqueue_ms_per_step": round(host_enqueue_ms, 4),
         "clocks": clocks,
         "roofline": roofline,
         "roofline_all": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()} for r in rl],

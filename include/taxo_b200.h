@@ -172,6 +172,9 @@ int tx_gat_attn_grad_partials(const float* ft, int64_t ldf, const float* da1, co
  *   dattn_partial: [tx_gat_fused_bwd_blocks(N, heads), 2, heads, dim] -> reduce with tx_reduce_partials to
  *             [d attn_l (heads*dim) | d attn_r (heads*dim)].
  *   ds [E*heads], da2 [N*heads]: scratch.
+ *   out_lo / dft_lo (optional, same shape and pitch as out / dft): when given, out / dft receive the TF32 "hi" part and
+ *             out_lo / dft_lo the "lo" part of every value (the split of tx_split_tf32 done in the producer's registers), so the
+ *             3xTF32 GEMMs consume them without a separate split pass.
  * ------------------------------------------------------------------------------------------------ */
 int tx_gat_fused_supported(int64_t heads, int64_t dim, int32_t mean_heads);
 int64_t tx_gat_fused_mask_words(int64_t n_nodes, int64_t heads, int64_t dim);
@@ -181,7 +184,7 @@ int tx_gat_fused_fwd(const float* ft, int64_t ldf, const float* attn_l, const fl
                      const int32_t* in_src, const int32_t* in_eid, int64_t n_nodes, int64_t heads, int64_t dim,
                      float neg_slope, float p_attn, uint64_t attn_seed, uint32_t attn_stream_id, float* alpha,
                      float* alpha_d, float* elog, float* out, int64_t ldo, const tx_gat_epilogue* epi, uint32_t* maskbits,
-                     void* stream);
+                     float* out_lo, void* stream);
 int tx_gat_fused_bwd(const float* g, int64_t ldg, int64_t g_head_stride, float g_scale, const uint32_t* maskbits,
                      int32_t has_keep_plane, float act_slope, float p_next, const float* ft, int64_t ldf,
                      const float* alpha, const float* alpha_d, const float* elog, const float* attn_l,
@@ -189,7 +192,7 @@ int tx_gat_fused_bwd(const float* g, int64_t ldg, int64_t g_head_stride, float g
                      const int32_t* out_ptr, const int32_t* out_dst, const int32_t* out_slot, const int32_t* node_off,
                      int64_t n_graphs, int64_t n_nodes, int64_t heads, int64_t dim, float neg_slope, float p_attn,
                      uint64_t attn_seed, uint32_t attn_stream_id, float* ds, float* da2, float* dft, int64_t ldd,
-                     float* dattn_partial, void* stream);
+                     float* dft_lo, float* dattn_partial, void* stream);
 /* dpos_partial[b, r, :] = sum over rows i of block b (tx_row_blocks) with pos_i = r of dz[i, col0 : col0+pos_dim] * keep/(1-p)
  * (gradient of the appended position-embedding block, reference model_zoo.py:214-215). */
 int tx_pos_grad_partials(const float* dz, int64_t ldz, int64_t col0, const int32_t* pos, int64_t n_nodes,

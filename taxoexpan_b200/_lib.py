@@ -76,9 +76,9 @@ _SIGNATURES = {
     "tx_gat_fused_mask_ld": [I64, I64],
     "tx_gat_fused_bwd_blocks": [I64, I64],
     "tx_gat_fused_fwd": [P, I64, P, P, P, P, P, I64, I64, I64, F32, F32, c_uint64, c_uint32, P, P, P, P, I64,
-                         POINTER(GatEpilogue), P, P],
+                         POINTER(GatEpilogue), P, P, P],
     "tx_gat_fused_bwd": [P, I64, I64, F32, P, c_int32, F32, F32, P, I64, P, P, P, P, P, P, P, P, P, P, P, P, I64, I64, I64, I64,
-                         F32, F32, c_uint64, c_uint32, P, P, P, I64, P, P],
+                         F32, F32, c_uint64, c_uint32, P, P, P, I64, P, P, P],
     "tx_pos_grad_partials": [P, I64, I64, P, I64, I64, I64, F32, c_uint64, c_uint32, P, P],
     "tx_split_tf32": [P, I64, I64, I64, P, P, I64, P],
     "tx_gemm_nt_tf32x3": [P, P, I64, P, P, I64, P, I64, I64, I64, I64, P],

@@ -71,6 +71,14 @@ __device__ __forceinline__ void axpy_row(float w, const float4 (&x)[NV], float4 
   }
 }
 
+// TF32 split of an fp32 value (same rounding as tx_split_tf32): v = hi + lo up to 2^-22 relative
+__device__ __forceinline__ float rn_tf32_f(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
+__device__ __forceinline__ void store_split4(float* hi_ptr, float* lo_ptr, float4 v) {
+  const float4 h = make_float4(rn_tf32_f(v.x), rn_tf32_f(v.y), rn_tf32_f(v.z), rn_tf32_f(v.w));
+  *reinterpret_cast<float4*>(hi_ptr) = h;
+  *reinterpret_cast<float4*>(lo_ptr) = make_float4(rn_tf32_f(v.x - h.x), rn_tf32_f(v.y - h.y), rn_tf32_f(v.z - h.z), rn_tf32_f(v.w - h.w));
+}
+
 struct FusedFwdParams {
   const float* ft; int64_t ldf;
   const float* attn_l; const float* attn_r;
@@ -79,6 +87,7 @@ struct FusedFwdParams {
   float neg_slope; float attn_inv_keep; uint32_t attn_thr; uint64_t attn_seed; uint32_t attn_stream;
   float* alpha; float* alpha_d; float* elog;
   float* out; int64_t ldo;
+  float* out_lo;           // optional: when set, `out` receives the TF32 hi part and out_lo the lo part of every written value
   uint32_t* maskbits;      // bytes [n, mask_ld]: byte (h*D + c)/4 of a row = 4 sign bits | 4 keep bits << 4 of columns c..c+3; may be null
   int mask_ld;             // = tx_gat_fused_mask_ld(H, D): H*D/4 rounded up to 16
   // epilogue
@@ -190,7 +199,10 @@ __global__ void __launch_bounds__(256, 3) gat_fused_fwd_kernel(const FusedFwdPar
           for (int u = 0; u < 4; ++u) v[u] = keep[u] ? v[u] * p.next_inv_keep : 0.f;
         }
       }
-      if (valid) *reinterpret_cast<float4*>(orow + c) = make_float4(v[0], v[1], v[2], v[3]);
+      if (valid) {
+        if (p.out_lo) store_split4(orow + c, p.out_lo + (orow - p.out) + c, make_float4(v[0], v[1], v[2], v[3]));
+        else *reinterpret_cast<float4*>(orow + c) = make_float4(v[0], v[1], v[2], v[3]);
+      }
       if (p.maskbits) {   // one byte per lane: sign bits (low nibble) + keep bits (high nibble) of its 4 elements
         uint32_t code = 0;
 #pragma unroll
@@ -210,7 +222,13 @@ __global__ void __launch_bounds__(256, 3) gat_fused_fwd_kernel(const FusedFwdPar
           v = __ldg(prow + (c - feat));
           if (p.next_thr) v = drop_keep1(p.next_seed, p.next_stream, (uint64_t)((int64_t)i * p.ldo + c), p.next_thr) ? v * p.next_inv_keep : 0.f;
         }
-        row[c] = v;
+        if (p.out_lo) {
+          const float vh = rn_tf32_f(v);
+          row[c] = vh;
+          p.out_lo[(int64_t)i * p.ldo + c] = rn_tf32_f(v - vh);
+        } else {
+          row[c] = v;
+        }
       }
     }
   }
@@ -230,6 +248,7 @@ struct FusedBwdParams {
   float neg_slope; float attn_inv_keep; uint32_t attn_thr; uint64_t attn_seed; uint32_t attn_stream;
   float* ds; float* da2;
   float* dft; int64_t ldd;
+  float* dft_lo;          // optional: when set, dft receives the TF32 hi part and dft_lo the lo part (feeds the 3xTF32 GEMMs directly)
   float* dattn_partial;   // [gridDim.x, 2, H, D]
 };
 
@@ -451,7 +470,10 @@ __global__ void __launch_bounds__(256, TX_BWD_MIN_BLOCKS) gat_fused_bwd_kernel(c
 #pragma unroll
       for (int t = 0; t < NV; ++t) {
         const int c = (lane + 32 * t) * 4;
-        if (c < D) *reinterpret_cast<float4*>(orow + c) = acc[t];
+        if (c < D) {
+          if (p.dft_lo) store_split4(orow + c, p.dft_lo + (orow - p.dft) + c, acc[t]);
+          else *reinterpret_cast<float4*>(orow + c) = acc[t];
+        }
       }
     }
     // ---------------- phase B, heavy sources (e.g. the anchor of a large egonet): the whole CTA per row ----------------
@@ -502,7 +524,10 @@ __global__ void __launch_bounds__(256, TX_BWD_MIN_BLOCKS) gat_fused_bwd_kernel(c
             o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
           }
           const int c = q * 4;
-          if (c < D) *reinterpret_cast<float4*>(orow + c) = o;
+          if (c < D) {
+            if (p.dft_lo) store_split4(orow + c, p.dft_lo + (orow - p.dft) + c, o);
+            else *reinterpret_cast<float4*>(orow + c) = o;
+          }
         }
       }
       __syncthreads();
@@ -592,8 +617,9 @@ int tx_gat_fused_fwd(const float* ft, int64_t ldf, const float* attn_l, const fl
                      const int32_t* in_src, const int32_t* in_eid, int64_t n_nodes, int64_t heads, int64_t dim,
                      float neg_slope, float p_attn, uint64_t attn_seed, uint32_t attn_stream_id, float* alpha,
                      float* alpha_d, float* elog, float* out, int64_t ldo, const tx_gat_epilogue* epi, uint32_t* maskbits,
-                     void* stream) {
+                     float* out_lo, void* stream) {
   TX_REQUIRE(epi, "gat_fused_fwd: epilogue required");
+  TX_REQUIRE(!out_lo || aligned16(out_lo), "gat_fused_fwd: out_lo must be 16-byte aligned");
   TX_REQUIRE(tx_gat_fused_supported(heads, dim, epi->mean_heads), "gat_fused_fwd: unsupported shape (heads %lld dim %lld); use the general path",
              (long long)heads, (long long)dim);
   TX_REQUIRE(aligned16(ft) && ldf % 4 == 0 && aligned16(out) && ldo % 4 == 0 && aligned16(attn_l) && aligned16(attn_r),
@@ -610,6 +636,7 @@ int tx_gat_fused_fwd(const float* ft, int64_t ldf, const float* attn_l, const fl
   p.attn_inv_keep = 1.f / (1.f - p_attn); p.attn_thr = drop_threshold(p_attn); p.attn_seed = attn_seed; p.attn_stream = attn_stream_id;
   p.alpha = alpha; p.alpha_d = alpha_d ? alpha_d : alpha; p.elog = elog; p.out = out; p.ldo = ldo; p.maskbits = maskbits;
   p.mask_ld = (int)tx_gat_fused_mask_ld(heads, dim);
+  p.out_lo = out_lo;
   p.hidden = epi->mean_heads ? 0 : 1; p.act_slope = epi->act_slope; p.next_pos_table = epi->next_pos_table; p.pos = epi->pos;
   p.pos_dim = (int)epi->pos_dim; p.next_inv_keep = 1.f / (1.f - epi->p_drop); p.next_thr = drop_threshold(epi->p_drop);
   p.next_seed = epi->seed; p.next_stream = epi->stream_id;
@@ -636,7 +663,7 @@ int tx_gat_fused_bwd(const float* g, int64_t ldg, int64_t g_head_stride, float g
                      const int32_t* out_ptr, const int32_t* out_dst, const int32_t* out_slot, const int32_t* node_off,
                      int64_t n_graphs, int64_t n_nodes, int64_t heads, int64_t dim, float neg_slope, float p_attn,
                      uint64_t attn_seed, uint32_t attn_stream_id, float* ds, float* da2, float* dft, int64_t ldd,
-                     float* dattn_partial, void* stream) {
+                     float* dft_lo, float* dattn_partial, void* stream) {
   TX_REQUIRE(g_head_stride != 0 || heads == 1, "gat_fused_bwd: a shared g row (head mean) needs heads == 1");
   TX_REQUIRE(dim % 4 == 0 && dim <= 128 * kMaxNV, "gat_fused_bwd: dim must be a multiple of 4 and <= %d", 128 * kMaxNV);
   TX_REQUIRE(aligned16(g) && ldg % 4 == 0 && g_head_stride % 4 == 0 && aligned16(ft) && ldf % 4 == 0 && aligned16(dft) && ldd % 4 == 0 &&
@@ -654,6 +681,7 @@ int tx_gat_fused_bwd(const float* g, int64_t ldg, int64_t g_head_stride, float g
   p.node_off = node_off; p.n_graphs = (int)n_graphs; p.n = (int)n_nodes; p.H = (int)heads; p.D = (int)dim;
   p.neg_slope = neg_slope; p.attn_inv_keep = 1.f / (1.f - p_attn); p.attn_thr = drop_threshold(p_attn); p.attn_seed = attn_seed;
   p.attn_stream = attn_stream_id; p.ds = ds; p.da2 = da2; p.dft = dft; p.ldd = ldd; p.dattn_partial = dattn_partial;
+  p.dft_lo = dft_lo;
   p.tile_rows = bwd_tile_rows();
   { const char* e = getenv("TAXO_BWD_STAGE"); p.stage_meta = e ? atoi(e) : 1; }
   const int nv = (int)((dim + 127) / 128);

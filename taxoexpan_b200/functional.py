@@ -50,6 +50,8 @@ FUSED_MAX_GRAPH_NODES = 2048
 # apply the leaky-relu/dropout derivative of the previous layer's epilogue inside the d(z) GEMM epilogue, so the fused backward
 # kernel reads d(z) as is (decoding the mask on each of its ~2.8 row loads cost 0.3 ms on L0; r11 / r13)
 FUSE_DZ_EPILOGUE = os.environ.get("TAXO_FUSE_DZ_EPILOGUE", "1") not in ("", "0")
+# the fused GAT kernels write their outputs already TF32-split (hi/lo) for the 3xTF32 GEMMs instead of a separate split pass
+FUSE_SPLIT = os.environ.get("TAXO_FUSE_SPLIT", "1") not in ("", "0")
 
 
 def use_fused(lib, heads: int, dim: int, mean_heads: int, st=None) -> bool:
@@ -124,17 +126,20 @@ def gemm_nt(a: torch.Tensor, k: int, b: torch.Tensor, out: torch.Tensor = None) 
     return gemm_nt_ps(a_hi, a_lo, k, b_hi, b_lo, n, out)
 
 
-def _layer_gemms_fwd(z, k, w_nk):
+def _layer_gemms_fwd(z, k, w_nk, z_lo=None):
     """y = z[:, :k] @ w_nk[:, :k]^T.  Returns (y, saved) where `saved` is what backward needs of z: z itself (cublas) or its
     TF32 split (tf32x3: the split is computed once and reused by the weight-gradient GEMM)."""
     if GEMM_BACKEND != "tf32x3" or z.shape[0] == 0:
         return torch.mm(z[:, :k], w_nk[:, :k].t()), (z, None)
-    z_hi, z_lo = split_tf32(z, k)
+    if z_lo is None:
+        z_hi, z_lo = split_tf32(z, k)
+    else:
+        z_hi = z                                      # produced pre-split by the previous layer's epilogue
     w_hi, w_lo = split_tf32(w_nk, k)
     return gemm_nt_ps(z_hi, z_lo, k, w_hi, w_lo, w_nk.shape[0]), (z_hi, z_lo)
 
 
-def _layer_gemms_bwd(dy, f, saved, w_kf, k, ldz, c0, need_w, need_z, in_link=None):
+def _layer_gemms_bwd(dy, f, saved, w_kf, k, ldz, c0, need_w, need_z, in_link=None, dy_lo=None):
     """dW_fk = dy[:, :f]^T @ z[:, :k]  and  dz[:, c0a:k] = dy[:, :f] @ w_kf[c0a:k, :f]^T (see _gemm_dz)."""
     n = dy.shape[0]
     dw = dz = None
@@ -153,8 +158,11 @@ def _layer_gemms_bwd(dy, f, saved, w_kf, k, ldz, c0, need_w, need_z, in_link=Non
                     dz[:, k:].zero_()
         return dw, dz
     z_hi, z_lo = saved
-    with timed_region("split_dy"):
-        d_hi, d_lo = split_tf32(dy, f)
+    if dy_lo is not None:
+        d_hi, d_lo = dy, dy_lo                        # written pre-split by the fused backward kernel
+    else:
+        with timed_region("split_dy"):
+            d_hi, d_lo = split_tf32(dy, f)
     if need_w:
         with timed_region("gemm_dw"):
             dw = gemm_tn_ps(d_hi, d_lo, f, z_hi, z_lo, k)
@@ -264,11 +272,12 @@ class MaskLink:
     """Hand-shake between consecutive fused GAT layers: layer l-1's forward publishes the sign/keep bytes of its epilogue,
     layer l's backward applies their derivative inside its d(z) GEMM epilogue and flags it, so layer l-1's backward kernel
     reads d(z) as is (no per-load decode)."""
-    __slots__ = ("mask", "heads", "dim", "act_slope", "p_drop", "applied")
+    __slots__ = ("mask", "heads", "dim", "act_slope", "p_drop", "applied", "z_lo")
 
     def __init__(self):
         self.mask = None
         self.applied = False
+        self.z_lo = None      # TF32 "lo" part of the published z when the producer wrote z pre-split (z itself is then the "hi" part)
 
 
 @dataclass
@@ -305,7 +314,8 @@ class GatLayer(Function):
             stream = current_stream()
             Stats.tag = cfg.tag
             with timed_region("gemm_fwd"):
-                ft, zsaved = _layer_gemms_fwd(z, K, weight)                # ft = fc(h), model_zoo.py:83
+                ft, zsaved = _layer_gemms_fwd(z, K, weight,               # ft = fc(h), model_zoo.py:83
+                                              cfg.in_link.z_lo if (cfg.in_link is not None and GEMM_BACKEND == "tf32x3") else None)
             al = attn_l.reshape(-1).contiguous()
             ar = attn_r.reshape(-1).contiguous()
             alpha = torch.empty(st.e * H, **f32)
@@ -324,16 +334,21 @@ class GatLayer(Function):
                               seed=cfg.next_seed, stream_id=cfg.next_stream)
             fused = use_fused(lib, H, D, 0 if cfg.hidden else 1, st)
             maskbits = None
+            out_lo = None
+            if FUSE_SPLIT and fused and cfg.hidden and cfg.out_link is not None and GEMM_BACKEND == "tf32x3":
+                out_lo = torch.empty_like(out)        # the epilogue writes the next layer's input already TF32-split
             if fused:
                 # ONE kernel: logits from the gathered rows, edge softmax, dropout, aggregation, next-layer epilogue
                 if cfg.hidden and (cfg.act_slope != 1.0 or cfg.p_next > 0.0):
                     maskbits = torch.empty(int(lib.tx_gat_fused_mask_words(n, H, D)), dtype=torch.int32, device=dev)
                 check(lib.tx_gat_fused_fwd(ptr(ft), F_, ptr(al), ptr(ar), ptr(st.in_ptr), ptr(st.in_src), ptr(st.in_eid), n, H, D,
                                            cfg.neg_slope, cfg.p_attn, cfg.attn_seed, cfg.attn_stream, ptr(alpha), ptr(alpha_d),
-                                           ptr(elog), ptr(out), ldo, epi, ptr(maskbits), stream), "tx_gat_fused_fwd")
-                if cfg.out_link is not None and maskbits is not None:
+                                           ptr(elog), ptr(out), ldo, epi, ptr(maskbits), ptr(out_lo), stream), "tx_gat_fused_fwd")
+                if cfg.out_link is not None:
                     lk = cfg.out_link
-                    lk.mask, lk.heads, lk.dim, lk.act_slope, lk.p_drop, lk.applied = maskbits, H, D, cfg.act_slope, cfg.p_next, False
+                    lk.z_lo = out_lo
+                    if maskbits is not None:
+                        lk.mask, lk.heads, lk.dim, lk.act_slope, lk.p_drop, lk.applied = maskbits, H, D, cfg.act_slope, cfg.p_next, False
             else:
                 a1 = torch.empty(n * H, **f32)
                 a2 = torch.empty(n * H, **f32)
@@ -381,6 +396,7 @@ class GatLayer(Function):
                     dtab = _reduce_partials(lib, partial, nb, ctx.vocab * pd).view(ctx.vocab, pd)
                 nbf = int(lib.tx_gat_fused_bwd_blocks(n, H))
                 partial = torch.empty(nbf * 2 * F_, **f32)
+                dft_lo = torch.empty_like(dft) if (FUSE_SPLIT and GEMM_BACKEND == "tf32x3") else None
                 g_head_stride, g_scale = (D, 1.0) if cfg.hidden else (0, 1.0 / H)
                 pre = cfg.out_link is not None and cfg.out_link.applied     # d(z_next) already carries the epilogue derivative
                 check(lib.tx_gat_fused_bwd(ptr(dout), ldg, g_head_stride, g_scale, None if pre else ptr(ctx.maskbits),
@@ -389,10 +405,11 @@ class GatLayer(Function):
                                            ptr(elog), ptr(al), ptr(ar), ptr(st.in_ptr), ptr(st.in_src), ptr(st.in_eid),
                                            ptr(st.out_ptr), ptr(st.out_dst), ptr(st.out_slot), ptr(st.node_off), st.g, n, H, D,
                                            cfg.neg_slope, cfg.p_attn, cfg.attn_seed, cfg.attn_stream, ptr(ds), ptr(da2), ptr(dft),
-                                           F_, ptr(partial), stream), "tx_gat_fused_bwd")
+                                           F_, ptr(dft_lo), ptr(partial), stream), "tx_gat_fused_bwd")
                 both = _reduce_partials(lib, partial, nbf, 2 * F_)
                 dal, dar = both[:F_].view(ctx.attn_shape), both[F_:].view(ctx.attn_shape)
             else:
+                dft_lo = None
                 if cfg.hidden:
                     if cfg.p_next > 0.0 or cfg.act_slope != 1.0 or need_tab:
                         if cfg.p_next > 0.0 or cfg.act_slope != 1.0:
@@ -423,7 +440,7 @@ class GatLayer(Function):
                     both = _reduce_partials(lib, partial, nb, 2 * F_)
                     dal, dar = both[:F_].view(ctx.attn_shape), both[F_:].view(ctx.attn_shape)
             dw, dz = _layer_gemms_bwd(dft, F_, (z0, z1), weight.t(), K, ldz, cfg.dz_from, ctx.needs_input_grad[1],
-                                      ctx.needs_input_grad[0], cfg.in_link)
+                                      ctx.needs_input_grad[0], cfg.in_link, dft_lo)
         return dz, dw, dal, dar, dtab, None, None, None
 
 
