@@ -244,7 +244,7 @@ struct FusedBwdParams {
   const int32_t* in_ptr; const int32_t* in_src; const int32_t* in_eid;
   const int32_t* out_ptr; const int32_t* out_dst; const int32_t* out_slot;
   const int32_t* node_off; int n_graphs;
-  int n; int H; int D; int tile_rows; int stage_meta;
+  int n; int H; int D; int tile_rows; int stage_meta; int prefetch;
   float neg_slope; float attn_inv_keep; uint32_t attn_thr; uint64_t attn_seed; uint32_t attn_stream;
   float* ds; float* da2;
   float* dft; int64_t ldd;
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(256, TX_BWD_MIN_BLOCKS) gat_fused_bwd_kernel(c
     if (wid == 7) {   // bounds of this CTA's next tile + L2 prefetch of its g / ft rows while this tile is processed
       if (lane == 0) tile_bounds(tile + gridDim.x, slot ^ 1);
       __syncwarp();
-      const int q0 = s_bounds[slot ^ 1][0], q1 = s_bounds[slot ^ 1][1];
+      const int q0 = s_bounds[slot ^ 1][0], q1 = p.prefetch ? s_bounds[slot ^ 1][1] : s_bounds[slot ^ 1][0];
       for (int r = q0 + lane; r < q1; r += 32) {
         prefetch_l2(p.g + (int64_t)r * p.ldg + (int64_t)h * p.g_head_stride, (uint32_t)D * 4u);
         prefetch_l2(fbase + (int64_t)r * p.ldf, (uint32_t)D * 4u);
@@ -608,7 +608,9 @@ static int bwd_tile_rows() {
 #endif
 int64_t tx_gat_fused_bwd_blocks(int64_t n_nodes, int64_t heads) {
   const int64_t tiles = (n_nodes + bwd_tile_rows() - 1) / bwd_tile_rows();
-  int64_t gx = (TX_BWD_MIN_BLOCKS * (int64_t)kNumSms + heads - 1) / heads;
+  const char* e_c = getenv("TAXO_BWD_CTAS_PER_SM");
+  const int64_t per_sm = e_c && atoi(e_c) > 0 ? atoi(e_c) : TX_BWD_MIN_BLOCKS;
+  int64_t gx = (per_sm * (int64_t)kNumSms + heads - 1) / heads;
   if (gx > tiles) gx = tiles;
   return gx < 1 ? 1 : gx;
 }
@@ -684,6 +686,7 @@ int tx_gat_fused_bwd(const float* g, int64_t ldg, int64_t g_head_stride, float g
   p.dft_lo = dft_lo;
   p.tile_rows = bwd_tile_rows();
   { const char* e = getenv("TAXO_BWD_STAGE"); p.stage_meta = e ? atoi(e) : 1; }
+  { const char* e = getenv("TAXO_BWD_PREFETCH"); p.prefetch = e ? atoi(e) : 1; }
   const int nv = (int)((dim + 127) / 128);
   dim3 grid((unsigned)tx_gat_fused_bwd_blocks(n_nodes, heads), (unsigned)heads);
   cudaStream_t st = (cudaStream_t)stream;

@@ -49,6 +49,27 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
                ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
                : "memory");
 }
+// multicast variants for a 2-CTA cluster: the TMA box lands in BOTH CTAs' shared memory (same offsets) and completes bytes on
+// both CTAs' mbarriers; the commit arrives on the barrier at the same offset in every CTA of the mask
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -61,6 +82,14 @@ __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fe
 //   [61,64) layout type = 2 (SWIZZLE_128B)
 __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// same with 64-byte rows (16 fp32 per k-block): SWIZZLE_64B (layout type 4), 8 rows x 64 B = 512 B between 8-row groups
+__device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
+}
+template <int BK>
+__device__ __forceinline__ uint64_t umma_desc_k(uint32_t smem_addr) {
+  return BK == 32 ? umma_desc_k_sw128(smem_addr) : umma_desc_k_sw64(smem_addr);
 }
 
 // D[tmem] (+)= A[smem] . B[smem]^T, kind::tf32, cta_group::1
@@ -114,7 +143,7 @@ struct GemmEpilogue {
   float on, neg;
 };
 
-constexpr int kChunk = 2;        // k-blocks accumulated inside the tensor core before promotion to fp32 registers
+constexpr int kChunkK = 64;      // K extent accumulated inside the tensor core before promotion to fp32 registers (24 MMAs)
 constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 per TMEM lane quadrant)
 
 // C[M, N] (+ split offset) = sum_k A . B with 3xTF32 products and CHUNKED PROMOTION:
@@ -124,12 +153,18 @@ constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogu
 //   TMEM buffer.  2 x BN columns of TMEM, double buffered.
 // TN = false: A [M, K], B [N, K] row-major (K-major operands): y = z W^T, dz = dy W.
 // TN = true : A [R, M], B [R, N] row-major (MN-major operands, reduction over rows): dW = dy^T z; grid.z = split index.
-template <int BN, int STAGES, bool TN>
+// CL = 2: clusters of two CTAs along M share every B tile - each CTA fetches half of it and TMA-multicasts it to both, which cuts
+// the L2 -> SM operand traffic per CTA from (A + B) to (A + B/2) (the 3xTF32 kernel is L2-bandwidth bound: 96 KB per k-block).
+template <int BN, int STAGES, bool TN, int BK, int CL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                    float* __restrict__ C, int64_t ldc, int64_t split_stride, int M, int n_store, int k_blocks_total,
                    int k_blocks_per_split, uint64_t mn_desc_bits, const GemmEpilogue epi) {
+  static_assert(BK == 32 || (BK == 16 && !TN), "BK = 16 (64-byte rows, SWIZZLE_64B) is implemented for the K-major form only");
+  constexpr int kBK = BK;
+  constexpr int kABytes = kBM * BK * 4;
+  constexpr int kChunk = kChunkK / BK;
   constexpr int B_BYTES = BN * kBK * 4;
   constexpr int STAGE_BYTES = 2 * kABytes + 2 * B_BYTES;
   constexpr int BOX_BYTES = kBK * 128;       // TN: one {32 cols, kBK rows} box
@@ -151,7 +186,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo) : "memory");
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full0 + 8 * s, 1);
-      mbar_init(empty0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, CL);           // the stage is reusable once the MMAs of every CTA writing into it retired
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull0 + 8 * b, 1);
@@ -159,12 +194,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
   if (warp == 1) {   // one warp allocates both accumulator buffers (power of two >= 32 columns)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();              // the peer's barriers are initialised before anything is multicast into it
   tcgen05_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * BN;
@@ -185,18 +222,30 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         if constexpr (!TN) {
           tma_load_2d(base, &map_a_hi, full, kk, m0);
           tma_load_2d(base + kABytes, &map_a_lo, full, kk, m0);
-          tma_load_2d(base + 2 * kABytes, &map_b_hi, full, kk, n0);
-          tma_load_2d(base + 2 * kABytes + B_BYTES, &map_b_lo, full, kk, n0);
+          if constexpr (CL == 1) {
+            tma_load_2d(base + 2 * kABytes, &map_b_hi, full, kk, n0);
+            tma_load_2d(base + 2 * kABytes + B_BYTES, &map_b_lo, full, kk, n0);
+          } else {   // my half of the B rows (the B maps have box rows = BN / 2), delivered to both CTAs
+            const uint32_t off = crank * (uint32_t)(B_BYTES / 2);
+            tma_load_2d_mc(base + 2 * kABytes + off, &map_b_hi, full, kk, n0 + (int)crank * (BN / 2), (uint16_t)3);
+            tma_load_2d_mc(base + 2 * kABytes + B_BYTES + off, &map_b_lo, full, kk, n0 + (int)crank * (BN / 2), (uint16_t)3);
+          }
         } else {
 #pragma unroll
           for (int b = 0; b < kBM / 32; ++b) {
             tma_load_2d(base + b * BOX_BYTES, &map_a_hi, full, m0 + 32 * b, kk);
             tma_load_2d(base + kABytes + b * BOX_BYTES, &map_a_lo, full, m0 + 32 * b, kk);
           }
+          constexpr int NB = BN / 32, NB0 = (NB + 1) / 2;          // CL = 2: rank 0 fetches boxes [0, NB0), rank 1 the rest
 #pragma unroll
-          for (int b = 0; b < BN / 32; ++b) {
-            tma_load_2d(base + 2 * kABytes + b * BOX_BYTES, &map_b_hi, full, n0 + 32 * b, kk);
-            tma_load_2d(base + 2 * kABytes + B_BYTES + b * BOX_BYTES, &map_b_lo, full, n0 + 32 * b, kk);
+          for (int b = 0; b < NB; ++b) {
+            if (CL == 1) {
+              tma_load_2d(base + 2 * kABytes + b * BOX_BYTES, &map_b_hi, full, n0 + 32 * b, kk);
+              tma_load_2d(base + 2 * kABytes + B_BYTES + b * BOX_BYTES, &map_b_lo, full, n0 + 32 * b, kk);
+            } else if ((b < NB0) == (crank == 0)) {
+              tma_load_2d_mc(base + 2 * kABytes + b * BOX_BYTES, &map_b_hi, full, n0 + 32 * b, kk, (uint16_t)3);
+              tma_load_2d_mc(base + 2 * kABytes + B_BYTES + b * BOX_BYTES, &map_b_lo, full, n0 + 32 * b, kk, (uint16_t)3);
+            }
           }
         }
       }
@@ -221,8 +270,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
           const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
           uint64_t a_hi, a_lo, b_hi, b_lo;
           if constexpr (!TN) {
-            a_hi = umma_desc_k_sw128(base); a_lo = umma_desc_k_sw128(base + kABytes);
-            b_hi = umma_desc_k_sw128(base + 2 * kABytes); b_lo = umma_desc_k_sw128(base + 2 * kABytes + B_BYTES);
+            a_hi = umma_desc_k<BK>(base); a_lo = umma_desc_k<BK>(base + kABytes);
+            b_hi = umma_desc_k<BK>(base + 2 * kABytes); b_lo = umma_desc_k<BK>(base + 2 * kABytes + B_BYTES);
           } else {
             a_hi = umma_desc_mn(base, mn_desc_bits); a_lo = umma_desc_mn(base + kABytes, mn_desc_bits);
             b_hi = umma_desc_mn(base + 2 * kABytes, mn_desc_bits); b_lo = umma_desc_mn(base + 2 * kABytes + B_BYTES, mn_desc_bits);
@@ -236,7 +285,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             umma_tf32(tacc, a_hi + adv, b_lo + adv, idesc, 1u);
             umma_tf32(tacc, a_hi + adv, b_hi + adv, idesc, 1u);
           }
-          tcgen05_commit(empty0 + 8 * s);                      // frees the smem stage once these MMAs retire
+          if (CL == 1) tcgen05_commit(empty0 + 8 * s);         // frees the smem stage once these MMAs retire
+          else tcgen05_commit_mc(empty0 + 8 * s, (uint16_t)3);  // ... in both CTAs (each writes half of B into the other)
         }
         tcgen05_commit(tfull0 + 8 * buf);                      // chunk accumulator complete
       }
@@ -299,6 +349,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();              // nobody exits while its peer may still multicast into it / arrive on its barriers
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -350,7 +401,7 @@ static EncodeTiledFn encode_fn() {
 
 // 2-D fp32 tensor [rows, cols] with row pitch ld (floats); box = [box_rows, 32 cols], 128-byte swizzle, zero OOB fill
 static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
-                    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+                    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B, int box_cols = 32) {
   if (rows <= 0 || cols <= 0) {
     set_error("gemm: empty operand");
     return TX_ERR_INVALID_ARGUMENT;
@@ -362,7 +413,7 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
   }
   const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
-  const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -375,17 +426,20 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
   return TX_OK;
 }
 
-template <int BN, int STAGES, bool TN>
+template <int BN, int STAGES, bool TN, int BK = 32, int CL = 1>
 static int launch_gemm(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi, const float* b_lo, int64_t ldb,
                        float* c, int64_t ldc, int64_t split_stride, int64_t M, int64_t N, int64_t K, int splits, cudaStream_t st,
                        const GemmEpilogue& epi = GemmEpilogue{nullptr, 0, 1, 0, 0, 0, 1.f, 1.f}) {
   alignas(64) CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
-  if (!TN) {   // A [M, K], B [N, K]: box = {32 k-cols, tile rows}
-    if ((rc = make_map(&ma_hi, a_hi, M, K, lda, kBM)) != TX_OK) return rc;
-    if ((rc = make_map(&ma_lo, a_lo, M, K, lda, kBM)) != TX_OK) return rc;
-    if ((rc = make_map(&mb_hi, b_hi, N, K, ldb, BN)) != TX_OK) return rc;
-    if ((rc = make_map(&mb_lo, b_lo, N, K, ldb, BN)) != TX_OK) return rc;
+  constexpr int kBK = BK;
+  constexpr int kABytes = kBM * BK * 4;
+  if (!TN) {   // A [M, K], B [N, K]: box = {BK k-cols, tile rows}; 128-byte (BK = 32) or 64-byte (BK = 16) swizzle
+    const CUtensorMapSwizzle swk = BK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    if ((rc = make_map(&ma_hi, a_hi, M, K, lda, kBM, swk, BK)) != TX_OK) return rc;
+    if ((rc = make_map(&ma_lo, a_lo, M, K, lda, kBM, swk, BK)) != TX_OK) return rc;
+    if ((rc = make_map(&mb_hi, b_hi, N, K, ldb, BN / CL, swk, BK)) != TX_OK) return rc;   // CL = 2: each CTA fetches half of the rows
+    if ((rc = make_map(&mb_lo, b_lo, N, K, ldb, BN / CL, swk, BK)) != TX_OK) return rc;
   } else {     // A [K, M], B [K, N]: box = {32 m/n-cols, kBK reduction rows}
     // (debug knobs TAXO_TN_SWIZZLE / _LAYOUT / _LBO / _SBO override the layout constants below)
     const char* e_sw = getenv("TAXO_TN_SWIZZLE");
@@ -399,7 +453,7 @@ static int launch_gemm(const float* a_hi, const float* a_lo, int64_t lda, const 
   constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers + tmem slot */;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, STAGES, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, STAGES, TN, BK, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
     if (e != cudaSuccess) {
       set_error("gemm: cudaFuncSetAttribute(%zu B smem) failed: %s", SMEM, cudaGetErrorString(e));
       return TX_ERR_CUDA;
@@ -409,14 +463,36 @@ static int launch_gemm(const float* a_hi, const float* a_lo, int64_t lda, const 
   const int kbt = (int)((K + kBK - 1) / kBK);
   const int kbs = (kbt + splits - 1) / splits;
   const int64_t n_store = ((N + 3) / 4) * 4;
-  dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + kBM - 1) / kBM), (unsigned)splits);
+  const unsigned m_tiles = (unsigned)((M + kBM - 1) / kBM);
+  dim3 grid((unsigned)((N + BN - 1) / BN), (m_tiles + CL - 1) / CL * CL, (unsigned)splits);   // padded M tiles are fully masked
   const char* e_l = getenv("TAXO_TN_LAYOUT");
   const char* e_lbo = getenv("TAXO_TN_LBO");
   const char* e_sbo = getenv("TAXO_TN_SBO");
   const uint64_t mn_bits = umma_desc_mn_bits(e_lbo ? (uint32_t)atoi(e_lbo) : (uint32_t)(kBK * 128), e_sbo ? (uint32_t)atoi(e_sbo) : 512u,
                                              e_l ? (uint32_t)atoi(e_l) : 1u);
-  gemm_tf32x3_kernel<BN, STAGES, TN><<<grid, kGemmThreads, SMEM, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, c, ldc, split_stride, (int)M,
-                                                                     (int)n_store, kbt, kbs, mn_bits, epi);
+  if (CL == 1) {
+    gemm_tf32x3_kernel<BN, STAGES, TN, BK, CL><<<grid, kGemmThreads, SMEM, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, c, ldc, split_stride, (int)M,
+                                                                             (int)n_store, kbt, kbs, mn_bits, epi);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = CL;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<BN, STAGES, TN, BK, CL>, ma_hi, ma_lo, mb_hi, mb_lo, c, ldc, split_stride,
+                                       (int)M, (int)n_store, kbt, kbs, mn_bits, epi);
+    if (e != cudaSuccess) {
+      set_error("gemm: cluster launch failed: %s", cudaGetErrorString(e));
+      return TX_ERR_CUDA;
+    }
+  }
   TX_LAUNCH_CHECK(TN ? "tx_gemm_tn_tf32x3" : "tx_gemm_nt_tf32x3");
   return TX_OK;
 }
@@ -426,6 +502,12 @@ static int launch_gemm(const float* a_hi, const float* a_lo, int64_t lda, const 
 using namespace tx;
 
 extern "C" {
+
+static bool use_cluster() {   // TAXO_GEMM_CLUSTER=1 -> no 2-CTA multicast clusters
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TAXO_GEMM_CLUSTER"); v = (e && atoi(e) == 1) ? 0 : 1; }
+  return v != 0;
+}
 
 // tile width: 64 / 128 for narrow outputs, else 256 unless 160-wide tiles waste fewer MMA columns (e.g. N = 300: 2 x 160 vs 2 x 256)
 static int pick_bn(int64_t n) {
@@ -454,6 +536,10 @@ int tx_gemm_tn_tf32x3(const float* a_hi, const float* a_lo, int64_t lda, const f
   TX_REQUIRE(ldc % 4 == 0 && ldc >= ((n + 3) / 4) * 4 && split_stride % 4 == 0 && split_stride >= m * ldc, "gemm_tn: bad ldc / split_stride");
   TX_REQUIRE(splits >= 1 && splits <= 65535, "gemm_tn: bad split count");
   cudaStream_t st = (cudaStream_t)stream;
+  if (use_cluster() && m > kBM) {
+    if (n > 128 && pick_bn(n) == 160) return launch_gemm<160, 3, true, 32, 2>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c_partial, ldc, split_stride, m, n, r, (int)splits, st);
+    if (n > 128) return launch_gemm<256, 2, true, 32, 2>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c_partial, ldc, split_stride, m, n, r, (int)splits, st);
+  }
   if (n > 128 && pick_bn(n) == 160) return launch_gemm<160, 3, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c_partial, ldc, split_stride, m, n, r, (int)splits, st);
   if (n > 128) return launch_gemm<256, 2, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c_partial, ldc, split_stride, m, n, r, (int)splits, st);
   if (n > 64) return launch_gemm<128, 3, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c_partial, ldc, split_stride, m, n, r, (int)splits, st);
@@ -495,7 +581,17 @@ int tx_gemm_nt_tf32x3_ex(const float* a_hi, const float* a_lo, int64_t lda, cons
     epi.feat_cols = (int)(e->heads * e->dim); epi.has_keep = e->has_keep_plane;
     epi.on = 1.f / (1.f - e->p_drop); epi.neg = e->act_slope * epi.on;
   }
+  if (use_cluster() && m > kBM && n > 128) {
+    if (pick_bn(n) == 160) return launch_gemm<160, 3, false, 32, 2>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
+    return launch_gemm<256, 2, false, 32, 2>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
+  }
   if (n > 128 && pick_bn(n) == 160) return launch_gemm<160, 3, false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
+  {
+    // 256-wide tiles: 64-byte k-blocks (BK = 16) give a 4-deep TMA ring in the same 192 KB instead of 2 stages of BK = 32
+    static int bk16 = -1;
+    if (bk16 < 0) { const char* e_bk = getenv("TAXO_NT_BK"); bk16 = (e_bk && atoi(e_bk) == 16) ? 1 : 0; }   // measured slower (r20): off by default
+    if (n > 128 && bk16) return launch_gemm<256, 4, false, 16>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
+  }
   if (n > 128) return launch_gemm<256, 2, false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
   if (n > 64) return launch_gemm<128, 3, false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
   return launch_gemm<64, 4, false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
