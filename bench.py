@@ -290,10 +290,9 @@ def run_b200(args, rank, world, local_rank):
         step_resident(i)
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()          # sampled across the value, per-kernel and e2e loops (a 30-step loop alone is ~0.1 s)
     total_ms, launches, _ = timed(step_resident, args.steps)
     host_enqueue_ms = timed.host_enqueue_ms
-    clocks = sampler.stop() if rank == 0 else None
 
     # per-kernel CUDA-event timings (separate pass so the headline loop carries no event overhead)
     _, _, prof = timed(step_resident, args.steps, profile=True)
@@ -301,6 +300,7 @@ def run_b200(args, rank, world, local_rank):
         step_e2e(i)
     e2e_flush()
     e2e_ms, _, _ = timed(step_e2e, args.steps, flush=e2e_flush)
+    clocks = sampler.stop() if rank == 0 else None
 
     # totals over ranks
     egonets = torch.tensor([sum(batches[i % nb]["shapes"].num_graphs for i in range(args.steps))], device=dev, dtype=torch.float64)
@@ -346,11 +346,18 @@ def run_b200(args, rank, world, local_rank):
             rl.append({"kernel": f"{label}[{tag}]", "ms": t_b, "bytes": by, "achieved": by / t_b / 1e6})
     for r in rl:
         r["frac"] = r["achieved"] / hbm_peak
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")      # dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu --set full)
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("per_launch_bytes", {})
+    for r in rl:
+        r["traffic"] = traffic.get(r["kernel"])
     dom = max(rl, key=lambda r: r["ms"]) if rl else None
     roofline = None
     if dom:
         roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": round(dom["achieved"], 1), "peak": hbm_peak,
-                    "unit": "GB/s", "frac": round(dom["frac"], 4), "traffic": None, "peak_source": peak_src,
+                    "unit": "GB/s", "frac": round(dom["frac"], 4), "traffic": dom.get("traffic"), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": int(dom["bytes"]), "ms_per_launch": round(dom["ms"], 4)}
     gemm_ms = sum(v for k, v in kern.items() if k.startswith("gemm") or k.startswith("split_dy"))
     gemm_flops = 3 * gemm_flops_per_node(MAGCS) * n_avg - 2 * n_avg * MAGCS["in_dim"] * W0   # dz0 only for the 50 pos columns
