@@ -356,6 +356,231 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   }
 }
 
+// =====================================================================================================================
+// cta_group::2 variant: a PAIR of CTAs (cluster {1,2,1}) computes a 256 x BN tile with one tcgen05.mma.cta_group::2 stream
+// issued by the leader CTA.  Each CTA stages its own 128 rows of A and HALF of the B tile (BN/2 rows or BN/64 boxes); the
+// tensor cores of both SMs read both halves, so per SM and k-block the operand traffic is 64 KB instead of 96 KB from L2
+// AND the shared-memory read traffic of the MMAs drops from A + B to A + B/2 (the single-CTA kernel is shared-memory /
+// L2 bandwidth bound at ~55 % tensor-pipe utilisation).  Accumulator rows [0,128) live in the leader's TMEM, [128,256) in the
+// peer's; each CTA's epilogue warps drain their own TMEM (chunked promotion as above).
+//   barriers:  full[s]  (leader)  <- TMA bytes of BOTH CTAs (peer's loads signal the leader's barrier: peer bit cleared)
+//              empty[s] (both)    <- leader's tcgen05.commit.cta_group::2 multicast
+//              tfull[b] (both)    <- leader's commit multicast after a chunk
+//              tempty[b](leader)  <- 8 + 8 epilogue warps (the peer's arrive remotely through mapa)
+// =====================================================================================================================
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+// TMA load whose completion bytes are credited to the LEADER CTA's mbarrier (same offset, peer bit cleared)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta0(uint32_t bar) {   // arrive on the barrier at this offset in CTA rank 0 of the cluster
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(bar));
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
+template <int BN, int STAGES, bool TN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                        const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                        float* __restrict__ C, int64_t ldc, int64_t split_stride, int M, int n_store, int k_blocks_total,
+                        int k_blocks_per_split, uint64_t mn_desc_bits, const GemmEpilogue epi) {
+  constexpr int BK = 32;
+  constexpr int kABytes = kBM * BK * 4;
+  constexpr int kChunk = kChunkK / BK;
+  constexpr int BH = BN / 2;                              // B rows (NT) / columns (TN) staged by one CTA
+  static_assert(BN % 64 == 0, "the pair kernel splits B into two halves of whole 32-wide blocks");
+  constexpr int BH_BYTES = BH * BK * 4;
+  constexpr int STAGE_BYTES = 2 * kABytes + 2 * BH_BYTES;
+  constexpr int BOX_BYTES = BK * 128;
+  constexpr int HALF = ((BN / 32 + 1) / 2) * 32;
+  constexpr uint32_t TMEM_COLS = 2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512));
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
+  const uint32_t tfull0 = smem_u32(bars + 2 * STAGES), tempty0 = smem_u32(bars + 2 * STAGES + 2);
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull0 + 8 * b, 1);
+      mbar_init(tempty0 + 8 * b, 16);          // 8 epilogue warps of each CTA of the pair
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // both CTAs, same warp id: paired TMEM allocation
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  // grid.x = 2 * n_tiles (the two CTAs of a pair are neighbours in x: cluster {2,1,1}), grid.y = pairs of M tiles
+  const int m0 = (int)(blockIdx.y * 2 + (blockIdx.x & 1)) * kBM, n0 = (int)(blockIdx.x >> 1) * BN;
+  const int kb0 = blockIdx.z * k_blocks_per_split;
+  const int nkb = max(0, min(k_blocks_per_split, k_blocks_total - kb0));
+  const int n_chunks = (nkb + kChunk - 1) / kChunk;
+
+  if (warp == 0) {
+    if (lane == 0) {   // ===== TMA producer (both CTAs) =====
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        const uint32_t full = full0 + 8 * s;
+        if (leader) mbar_expect_tx(full, 2 * STAGE_BYTES);       // bytes of both CTAs land on the leader's barrier
+        const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+        const int kk = (kb0 + kb) * BK;
+        if constexpr (!TN) {
+          tma_load_2d_pair(base, &map_a_hi, full, kk, m0);
+          tma_load_2d_pair(base + kABytes, &map_a_lo, full, kk, m0);
+          tma_load_2d_pair(base + 2 * kABytes, &map_b_hi, full, kk, n0 + (int)crank * BH);
+          tma_load_2d_pair(base + 2 * kABytes + BH_BYTES, &map_b_lo, full, kk, n0 + (int)crank * BH);
+        } else {
+#pragma unroll
+          for (int b = 0; b < kBM / 32; ++b) {
+            tma_load_2d_pair(base + b * BOX_BYTES, &map_a_hi, full, m0 + 32 * b, kk);
+            tma_load_2d_pair(base + kABytes + b * BOX_BYTES, &map_a_lo, full, m0 + 32 * b, kk);
+          }
+#pragma unroll
+          for (int b = 0; b < BH / 32; ++b) {
+            tma_load_2d_pair(base + 2 * kABytes + b * BOX_BYTES, &map_b_hi, full, n0 + (int)crank * BH + 32 * b, kk);
+            tma_load_2d_pair(base + 2 * kABytes + BH_BYTES + b * BOX_BYTES, &map_b_lo, full, n0 + (int)crank * BH + 32 * b, kk);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {   // ===== MMA issuer (leader CTA only) =====
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (TN ? ((1u << 15) | (1u << 16)) : 0u) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * kBM) >> 4) << 24);       // M = 256 across the pair
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        const int buf = ch & 1;
+        mbar_wait(tempty0 + 8 * buf, ((ch >> 1) & 1) ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
+        const int kb_end = min(nkb, (ch + 1) * kChunk);
+        for (int kb = ch * kChunk; kb < kb_end; ++kb) {
+          const int s = kb % STAGES;
+          const uint32_t ph = (kb / STAGES) & 1;
+          mbar_wait(full0 + 8 * s, ph);
+          tcgen05_fence_after();
+          const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+          uint64_t a_hi, a_lo, b_hi, b_lo;
+          if constexpr (!TN) {
+            a_hi = umma_desc_k_sw128(base); a_lo = umma_desc_k_sw128(base + kABytes);
+            b_hi = umma_desc_k_sw128(base + 2 * kABytes); b_lo = umma_desc_k_sw128(base + 2 * kABytes + BH_BYTES);
+          } else {
+            a_hi = umma_desc_mn(base, mn_desc_bits); a_lo = umma_desc_mn(base + kABytes, mn_desc_bits);
+            b_hi = umma_desc_mn(base + 2 * kABytes, mn_desc_bits); b_lo = umma_desc_mn(base + 2 * kABytes + BH_BYTES, mn_desc_bits);
+          }
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint64_t adv = TN ? (uint64_t)((k * 1024) >> 4) : (uint64_t)(2 * k);
+            const uint32_t first = (kb == ch * kChunk && k == 0) ? 0u : 1u;
+            umma_tf32_pair(tacc, a_lo + adv, b_hi + adv, idesc, first);
+            umma_tf32_pair(tacc, a_hi + adv, b_lo + adv, idesc, 1u);
+            umma_tf32_pair(tacc, a_hi + adv, b_hi + adv, idesc, 1u);
+          }
+          tcgen05_commit_pair(empty0 + 8 * s);                   // stage free in both CTAs
+        }
+        tcgen05_commit_pair(tfull0 + 8 * buf);                   // chunk accumulator complete in both CTAs
+      }
+    }
+  } else {             // ===== epilogue warps (both CTAs): own TMEM lanes = own 128 rows =====
+    const int q = warp & 3;
+    const int hsel = (warp - 2) >> 2;
+    const int n_chunks32 = hsel == 0 ? HALF / 32 : (BN - HALF) / 32;
+    float acc[HALF];
+#pragma unroll
+    for (int c = 0; c < HALF; ++c) acc[c] = 0.f;
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      const int buf = ch & 1;
+      mbar_wait(tfull0 + 8 * buf, (ch >> 1) & 1);
+      tcgen05_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(buf * BN + hsel * HALF) + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+      for (int c = 0; c < HALF / 32; ++c) {
+        if (c < n_chunks32) {
+          uint32_t r[32];
+          tmem_ld32(tacc + (uint32_t)(c * 32), r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(r[j]);
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(tempty0 + 8 * buf); else mbar_arrive_cta0(tempty0 + 8 * buf);
+      }
+    }
+    const int row = m0 + q * 32 + lane;
+    if (row < M) {
+      float* crow = C + (int64_t)blockIdx.z * split_stride + (int64_t)row * ldc + n0 + hsel * HALF;
+      uint32_t mw[HALF / 16];
+      const bool masked = !TN && epi.mask != nullptr;
+      if (masked) {
+#pragma unroll
+        for (int w = 0; w < HALF / 16; ++w) {
+          const int col = n0 + hsel * HALF + w * 16;
+          mw[w] = (w < n_chunks32 * 2 && col < epi.feat_cols)
+                      ? __ldg(reinterpret_cast<const uint32_t*>(epi.mask + (int64_t)row * epi.stride + (col >> 2))) : 0xFFFFFFFFu;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < HALF / 4; ++j) {
+        const int col = n0 + hsel * HALF + j * 4;
+        if (j < n_chunks32 * 8 && col < n_store) {
+          float4 v = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+          if (masked && col < epi.feat_cols) {
+            uint32_t code = (mw[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+            if (!epi.has_keep) code |= 0xF0u;
+            v.x *= (code & 16u) ? ((code & 1u) ? epi.on : epi.neg) : 0.f;
+            v.y *= (code & 32u) ? ((code & 2u) ? epi.on : epi.neg) : 0.f;
+            v.z *= (code & 64u) ? ((code & 4u) ? epi.on : epi.neg) : 0.f;
+            v.w *= (code & 128u) ? ((code & 8u) ? epi.on : epi.neg) : 0.f;
+          }
+          *reinterpret_cast<float4*>(crow + j * 4) = v;
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // hi = rn_tf32(x), lo = rn_tf32(x - hi) (x - hi is exact in fp32); round-to-nearest keeps the split error signed and
 // unbiased (truncation left a systematic 1e-6 drift over K = 2050).  Outputs padded to ldo with zeros.
 __device__ __forceinline__ float rn_tf32(float v) {
@@ -497,11 +722,74 @@ static int launch_gemm(const float* a_hi, const float* a_lo, int64_t lda, const 
   return TX_OK;
 }
 
+template <int BN, int STAGES, bool TN>
+static int launch_gemm_pair(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi, const float* b_lo, int64_t ldb,
+                            float* c, int64_t ldc, int64_t split_stride, int64_t M, int64_t N, int64_t K, int splits, cudaStream_t st,
+                            const GemmEpilogue& epi = GemmEpilogue{nullptr, 0, 1, 0, 0, 0, 1.f, 1.f}) {
+  alignas(64) CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  int rc;
+  constexpr int BK = 32;
+  if (!TN) {
+    if ((rc = make_map(&ma_hi, a_hi, M, K, lda, kBM)) != TX_OK) return rc;
+    if ((rc = make_map(&ma_lo, a_lo, M, K, lda, kBM)) != TX_OK) return rc;
+    if ((rc = make_map(&mb_hi, b_hi, N, K, ldb, BN / 2)) != TX_OK) return rc;
+    if ((rc = make_map(&mb_lo, b_lo, N, K, ldb, BN / 2)) != TX_OK) return rc;
+  } else {
+    const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    if ((rc = make_map(&ma_hi, a_hi, K, M, lda, BK, sw)) != TX_OK) return rc;
+    if ((rc = make_map(&ma_lo, a_lo, K, M, lda, BK, sw)) != TX_OK) return rc;
+    if ((rc = make_map(&mb_hi, b_hi, K, N, ldb, BK, sw)) != TX_OK) return rc;
+    if ((rc = make_map(&mb_lo, b_lo, K, N, ldb, BK, sw)) != TX_OK) return rc;
+  }
+  constexpr int STAGE_BYTES = 2 * kBM * BK * 4 + 2 * (BN / 2) * BK * 4;
+  constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_pair_kernel<BN, STAGES, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+    if (e != cudaSuccess) {
+      set_error("gemm(pair): cudaFuncSetAttribute(%zu B smem) failed: %s", SMEM, cudaGetErrorString(e));
+      return TX_ERR_CUDA;
+    }
+    attr_done = true;
+  }
+  const int kbt = (int)((K + BK - 1) / BK);
+  const int kbs = (kbt + splits - 1) / splits;
+  const int64_t n_store = ((N + 3) / 4) * 4;
+  const unsigned m_tiles = (unsigned)((M + kBM - 1) / kBM);
+  dim3 grid(2u * (unsigned)((N + BN - 1) / BN), (m_tiles + 1) / 2, (unsigned)splits);   // a padded odd M tile is fully masked
+  const uint64_t mn_bits = umma_desc_mn_bits((uint32_t)(BK * 128), 512u, 1u);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tf32x3_pair_kernel<BN, STAGES, TN>, ma_hi, ma_lo, mb_hi, mb_lo, c, ldc, split_stride,
+                                     (int)M, (int)n_store, kbt, kbs, mn_bits, epi);
+  if (e != cudaSuccess) {
+    set_error("gemm(pair): cluster launch failed: %s", cudaGetErrorString(e));
+    return TX_ERR_CUDA;
+  }
+  return TX_OK;
+}
+
 }  // namespace tx
 
 using namespace tx;
 
 extern "C" {
+
+static bool use_pair() {      // cta_group::2 pair kernel for 256-wide tiles (default); TAXO_GEMM_PAIR=0 -> single-CTA MMAs
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TAXO_GEMM_PAIR"); v = (e && atoi(e) == 0) ? 0 : 1; }
+  return v != 0;
+}
 
 static bool use_cluster() {   // TAXO_GEMM_CLUSTER=1 -> no 2-CTA multicast clusters
   static int v = -1;
@@ -536,6 +824,8 @@ int tx_gemm_tn_tf32x3(const float* a_hi, const float* a_lo, int64_t lda, const f
   TX_REQUIRE(ldc % 4 == 0 && ldc >= ((n + 3) / 4) * 4 && split_stride % 4 == 0 && split_stride >= m * ldc, "gemm_tn: bad ldc / split_stride");
   TX_REQUIRE(splits >= 1 && splits <= 65535, "gemm_tn: bad split count");
   cudaStream_t st = (cudaStream_t)stream;
+  if (use_pair() && m > kBM && n > 128 && pick_bn(n) == 256)
+    return launch_gemm_pair<256, 3, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c_partial, ldc, split_stride, m, n, r, (int)splits, st);
   if (use_cluster() && m > kBM) {
     if (n > 128 && pick_bn(n) == 160) return launch_gemm<160, 3, true, 32, 2>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c_partial, ldc, split_stride, m, n, r, (int)splits, st);
     if (n > 128) return launch_gemm<256, 2, true, 32, 2>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c_partial, ldc, split_stride, m, n, r, (int)splits, st);
@@ -581,6 +871,8 @@ int tx_gemm_nt_tf32x3_ex(const float* a_hi, const float* a_lo, int64_t lda, cons
     epi.feat_cols = (int)(e->heads * e->dim); epi.has_keep = e->has_keep_plane;
     epi.on = 1.f / (1.f - e->p_drop); epi.neg = e->act_slope * epi.on;
   }
+  if (use_pair() && m > kBM && n > 128 && pick_bn(n) == 256)
+    return launch_gemm_pair<256, 3, false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
   if (use_cluster() && m > kBM && n > 128) {
     if (pick_bn(n) == 160) return launch_gemm<160, 3, false, 32, 2>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
     return launch_gemm<256, 2, false, 32, 2>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
