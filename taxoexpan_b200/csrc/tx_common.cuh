@@ -33,10 +33,9 @@ void set_error(const char* fmt, ...);
 
 // ---------------------------------------------------------------------------------------------
 // Counter-based dropout.  keep(seed, stream, index) is a pure function of its arguments (reproducible in the
-// backward pass, by tx_dropout_keep_mask and across kernels): one 32-bit mix of (index / 4, seed, stream) followed
-// by two independent avalanche finalisers yields four 16-bit uniforms, one per element of an aligned group of 4.
-// keep iff u16 >= round(p * 65536).  (~20 integer instructions per 4 elements: a Philox4x32-10 draw cost ~100 and
-// made the fused aggregate kernel issue-bound - profiles/r2.)
+// backward pass, by tx_dropout_keep_mask and across kernels): a 4-round Philox-2x32-style network on (index / 4) keyed by
+// (seed, stream) yields four 16-bit uniforms, one per element of an aligned group of 4; keep iff u16 >= round(p * 65536).
+// (A Philox4x32-10 draw cost ~100 integer instructions per group and made the fused aggregate kernel issue-bound.)
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
   double t = (double)p * 65536.0 + 0.5;
@@ -45,15 +44,18 @@ __host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
   return (uint32_t)t;
 }
 
-// returns {w.x: u16 of elements 0 (low half) and 1 (high half), w.y: elements 2 and 3} of group idx4
+// returns {w.x: u16 of elements 0 (low half) and 1 (high half), w.y: elements 2 and 3} of group idx4.
+// Four rounds of the Philox-2x32 multiply/xor network on the 64-bit counter idx4 keyed by (seed, stream): each round is one
+// 32x32->64 multiply (IMAD.WIDE) and one 3-input xor (LOP3) - ~10 integer instructions per group of 4 elements.
 __device__ __forceinline__ uint2 drop_words(uint64_t seed, uint32_t stream_id, uint64_t idx4) {
-  uint32_t h = ((uint32_t)idx4 * 0x9E3779B1u) ^ (uint32_t)seed;                  // bijective in the low index word
-  h ^= ((uint32_t)(idx4 >> 32) + stream_id * 0x85EBCA77u + (uint32_t)(seed >> 32)) * 0xC2B2AE3Du;
-  uint32_t a = h;
-  a ^= a >> 16; a *= 0x7FEB352Du; a ^= a >> 15; a *= 0x846CA68Bu; a ^= a >> 16;
-  uint32_t b = h + 0x9E3779B9u;
-  b ^= b >> 16; b *= 0x21F0AAADu; b ^= b >> 15; b *= 0x735A2D97u; b ^= b >> 15;
-  return make_uint2(a, b);
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32) ^ (stream_id * 0x9E3779B1u);
+  uint32_t x = (uint32_t)idx4, y = (uint32_t)(idx4 >> 32) ^ 0x85EBCA77u;
+  uint64_t p;
+  p = (uint64_t)x * 0xD2511F53u; x = (uint32_t)(p >> 32) ^ y ^ k0; y = (uint32_t)p;
+  p = (uint64_t)x * 0xCD9E8D57u; x = (uint32_t)(p >> 32) ^ y ^ k1; y = (uint32_t)p;
+  p = (uint64_t)x * 0xD2511F53u; x = (uint32_t)(p >> 32) ^ y ^ (k0 + 0x9E3779B9u); y = (uint32_t)p;
+  p = (uint64_t)x * 0xCD9E8D57u; x = (uint32_t)(p >> 32) ^ y ^ (k1 + 0xBB67AE85u); y = (uint32_t)p;
+  return make_uint2(x, y);
 }
 
 __device__ __forceinline__ void drop_keep4(uint64_t seed, uint32_t stream_id, uint64_t idx4, uint32_t thr, bool (&keep)[4]) {

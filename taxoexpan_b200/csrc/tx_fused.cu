@@ -176,38 +176,38 @@ __global__ void __launch_bounds__(256, 3) gat_fused_fwd_kernel(const FusedFwdPar
           p.alpha_d[o] = drop_keep1(p.attn_seed, p.attn_stream, (uint64_t)((int64_t)__ldg(p.in_eid + k) * H + h), p.attn_thr) ? a * p.attn_inv_keep : 0.f;
       }
     }
-    // ---- epilogue ----
-    float* orow = p.out + (int64_t)i * p.ldo + (p.hidden ? (int64_t)h * D : 0);
-    const int64_t idx_base = (int64_t)i * p.ldo + (int64_t)h * D;
+    // ---- epilogue (per-row bases hoisted: the per-vector work is address-free) ----
+    const int64_t row_off = (int64_t)i * p.ldo + (p.hidden ? (int64_t)h * D : 0) + lane * 4;
+    float* orow = p.out + row_off;
+    float* olo = p.out_lo ? p.out_lo + row_off : nullptr;
+    uint8_t* mrow = p.maskbits ? reinterpret_cast<uint8_t*>(p.maskbits) + (int64_t)i * p.mask_ld + ((h * D) >> 2) + lane : nullptr;
+    const uint64_t idx4_base = (uint64_t)(((int64_t)i * p.ldo + (int64_t)h * D) >> 2) + (uint64_t)lane;   // ldo % 4 == 0, D % 4 == 0
+    const bool act = p.hidden && p.act_slope != 1.f;
+    const bool drop = p.hidden && p.next_thr != 0;
 #pragma unroll
     for (int t = 0; t < NV; ++t) {
-      const int c = (lane + 32 * t) * 4;
-      const bool valid = c < D;
-      float v[4] = {acc[t].x, acc[t].y, acc[t].z, acc[t].w};
-      bool keep[4] = {true, true, true, true};
-      bool posv[4];
+      if ((lane + 32 * t) * 4 < D) {
+        float v[4] = {acc[t].x, acc[t].y, acc[t].z, acc[t].w};
+        uint32_t code = 0xF0u;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) posv[u] = v[u] > 0.f;
-      if (p.hidden) {
-        if (p.act_slope != 1.f) {
+        for (int u = 0; u < 4; ++u) code |= v[u] > 0.f ? (1u << u) : 0u;
+        if (act) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) v[u] = posv[u] ? v[u] : v[u] * p.act_slope;
+          for (int u = 0; u < 4; ++u) v[u] = (code >> u) & 1u ? v[u] : v[u] * p.act_slope;
         }
-        if (p.next_thr && valid) {
-          drop_keep4(p.next_seed, p.next_stream, (uint64_t)(idx_base + c) >> 2, p.next_thr, keep);
+        if (drop) {
+          const uint2 w = drop_words(p.next_seed, p.next_stream, idx4_base + 32u * t);
+          const uint32_t r[4] = {w.x & 0xFFFFu, w.x >> 16, w.y & 0xFFFFu, w.y >> 16};
 #pragma unroll
-          for (int u = 0; u < 4; ++u) v[u] = keep[u] ? v[u] * p.next_inv_keep : 0.f;
+          for (int u = 0; u < 4; ++u) {
+            const bool keep = r[u] >= p.next_thr;
+            v[u] = keep ? v[u] * p.next_inv_keep : 0.f;
+            code &= keep ? 0xFFu : ~(16u << u);
+          }
         }
-      }
-      if (valid) {
-        if (p.out_lo) store_split4(orow + c, p.out_lo + (orow - p.out) + c, make_float4(v[0], v[1], v[2], v[3]));
-        else *reinterpret_cast<float4*>(orow + c) = make_float4(v[0], v[1], v[2], v[3]);
-      }
-      if (p.maskbits) {   // one byte per lane: sign bits (low nibble) + keep bits (high nibble) of its 4 elements
-        uint32_t code = 0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) code |= ((posv[u] ? 1u : 0u) | (keep[u] ? 16u : 0u)) << u;
-        if (valid) reinterpret_cast<uint8_t*>(p.maskbits)[(int64_t)i * p.mask_ld + ((h * D + c) >> 2)] = (uint8_t)code;
+        if (olo) store_split4(orow + 128 * t, olo + 128 * t, make_float4(v[0], v[1], v[2], v[3]));
+        else *reinterpret_cast<float4*>(orow + 128 * t) = make_float4(v[0], v[1], v[2], v[3]);
+        if (mrow) mrow[32 * t] = (uint8_t)code;     // 4 sign bits | 4 keep bits << 4 of this lane's 4 columns
       }
     }
     // position-embedding append + zero padding (once per row: the warp of the last head)
