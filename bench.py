@@ -336,7 +336,7 @@ def run_b200(args, rank, world, local_rank):
             if t_f > 0:
                 by = gaa_fwd_bytes(n_avg, e_avg, H, W)
                 rl.append({"kernel": f"{label}[{tag}]", "ms": t_f, "bytes": by, "achieved": by / t_f / 1e6})
-        for bwd_names, label in ((("tx_gat_fused_bwd",), "tx_gat_fused_bwd"),
+        for bwd_names, label in ((("tx_gat_fused_bwd_staged",), "tx_gat_fused_bwd_staged"), (("tx_gat_fused_bwd",), "tx_gat_fused_bwd"),
                                  (("tx_epilogue_bwd", "tx_gat_aggregate_bwd_dst", "tx_gat_aggregate_bwd_src", "tx_gat_attn_grad_partials"),
                                   "tx_epilogue_bwd+aggregate_bwd_dst+src+attn_grad")):
             if not avg(bwd_names[-1] if len(bwd_names) == 1 else "tx_gat_aggregate_bwd_dst", tag):

@@ -193,6 +193,26 @@ int tx_gat_fused_bwd(const float* g, int64_t ldg, int64_t g_head_stride, float g
                      int64_t n_graphs, int64_t n_nodes, int64_t heads, int64_t dim, float neg_slope, float p_attn,
                      uint64_t attn_seed, uint32_t attn_stream_id, float* ds, float* da2, float* dft, int64_t ldd,
                      float* dft_lo, float* dattn_partial, void* stream);
+/* TMA-staged variant of tx_gat_fused_bwd (same arithmetic, same outputs; replaces the same reference autograd of
+ * model_zoo.py:83-96,106-114) for g that already carries the epilogue derivative (no maskbits): a producer warp bulk-copies
+ * the g / ft rows of the next tile of whole graphs into shared memory (cp.async.bulk + mbarrier) while 16 compute warps run
+ * the two phases on the current tile out of shared memory.
+ *   tiles: int32 [(tx_gat_bwd_num_tiles(N, dim) + 1) * 4] written by tx_gat_bwd_tiles (per tile: first row, first in-edge,
+ *          first out-edge, 0; tile t = graphs whose first row lies in [t R, (t+1) R), R = tx_gat_bwd_tile_rows(dim)); depends on
+ *          the batch structure and dim only - build once per batch.
+ *   dattn_partial: [tx_gat_fused_bwd_staged_blocks(N, heads, dim), 2, heads, dim]. */
+int64_t tx_gat_bwd_tile_rows(int64_t dim);
+int64_t tx_gat_bwd_num_tiles(int64_t n_nodes, int64_t dim);
+int tx_gat_bwd_tiles(const int32_t* node_off, int64_t n_graphs, int64_t n_nodes, const int32_t* in_ptr, const int32_t* out_ptr,
+                     int64_t dim, int32_t* tiles, void* stream);
+int64_t tx_gat_fused_bwd_staged_blocks(int64_t n_nodes, int64_t heads, int64_t dim);
+int tx_gat_fused_bwd_staged(const float* g, int64_t ldg, int64_t g_head_stride, float g_scale, const float* ft, int64_t ldf,
+                            const float* alpha, const float* alpha_d, const float* elog, const float* attn_l,
+                            const float* attn_r, const int32_t* in_ptr, const int32_t* in_src, const int32_t* in_eid,
+                            const int32_t* out_ptr, const int32_t* out_dst, const int32_t* out_slot, const int32_t* tiles,
+                            int64_t n_nodes, int64_t heads, int64_t dim, float neg_slope, float p_attn, uint64_t attn_seed,
+                            uint32_t attn_stream_id, float* ds, float* da2, float* dft, int64_t ldd, float* dft_lo,
+                            float* dattn_partial, void* stream);
 /* dpos_partial[b, r, :] = sum over rows i of block b (tx_row_blocks) with pos_i = r of dz[i, col0 : col0+pos_dim] * keep/(1-p)
  * (gradient of the appended position-embedding block, reference model_zoo.py:214-215). */
 int tx_pos_grad_partials(const float* dz, int64_t ldz, int64_t col0, const int32_t* pos, int64_t n_nodes,

@@ -52,6 +52,8 @@ FUSED_MAX_GRAPH_NODES = 2048
 FUSE_DZ_EPILOGUE = os.environ.get("TAXO_FUSE_DZ_EPILOGUE", "1") not in ("", "0")
 # the fused GAT kernels write their outputs already TF32-split (hi/lo) for the 3xTF32 GEMMs instead of a separate split pass
 FUSE_SPLIT = os.environ.get("TAXO_FUSE_SPLIT", "1") not in ("", "0")
+# TMA-staged fused GAT backward (tx_fused_bwd.cu) whenever d(z_next) needs no per-load mask decode; TAXO_STAGED_BWD=0 -> first kernel
+STAGED_BWD = os.environ.get("TAXO_STAGED_BWD", "1") not in ("", "0")
 
 
 def use_fused(lib, heads: int, dim: int, mean_heads: int, st=None) -> bool:
@@ -394,18 +396,29 @@ class GatLayer(Function):
                     check(lib.tx_pos_grad_partials(ptr(dout), ldg, F_, ptr(pos32), n, pd, ctx.vocab, cfg.p_next, cfg.next_seed,
                                                    cfg.next_stream, ptr(partial), stream), "tx_pos_grad_partials")
                     dtab = _reduce_partials(lib, partial, nb, ctx.vocab * pd).view(ctx.vocab, pd)
-                nbf = int(lib.tx_gat_fused_bwd_blocks(n, H))
-                partial = torch.empty(nbf * 2 * F_, **f32)
                 dft_lo = torch.empty_like(dft) if (FUSE_SPLIT and GEMM_BACKEND == "tf32x3") else None
                 g_head_stride, g_scale = (D, 1.0) if cfg.hidden else (0, 1.0 / H)
                 pre = cfg.out_link is not None and cfg.out_link.applied     # d(z_next) already carries the epilogue derivative
-                check(lib.tx_gat_fused_bwd(ptr(dout), ldg, g_head_stride, g_scale, None if pre else ptr(ctx.maskbits),
-                                           1 if cfg.p_next > 0.0 else 0, cfg.act_slope, cfg.p_next if cfg.hidden else 0.0,
-                                           ptr(ft), F_, ptr(alpha), ptr(alpha_d),
-                                           ptr(elog), ptr(al), ptr(ar), ptr(st.in_ptr), ptr(st.in_src), ptr(st.in_eid),
-                                           ptr(st.out_ptr), ptr(st.out_dst), ptr(st.out_slot), ptr(st.node_off), st.g, n, H, D,
-                                           cfg.neg_slope, cfg.p_attn, cfg.attn_seed, cfg.attn_stream, ptr(ds), ptr(da2), ptr(dft),
-                                           F_, ptr(dft_lo), ptr(partial), stream), "tx_gat_fused_bwd")
+                if STAGED_BWD and (pre or ctx.maskbits is None):
+                    # TMA-staged kernel: rows of a tile of whole graphs are bulk-copied to shared memory one tile ahead
+                    tiles = st.bwd_tiles(D)
+                    nbf = int(lib.tx_gat_fused_bwd_staged_blocks(n, H, D))
+                    partial = torch.empty(nbf * 2 * F_, **f32)
+                    check(lib.tx_gat_fused_bwd_staged(ptr(dout), ldg, g_head_stride, g_scale, ptr(ft), F_, ptr(alpha), ptr(alpha_d),
+                                                      ptr(elog), ptr(al), ptr(ar), ptr(st.in_ptr), ptr(st.in_src), ptr(st.in_eid),
+                                                      ptr(st.out_ptr), ptr(st.out_dst), ptr(st.out_slot), ptr(tiles), n, H, D,
+                                                      cfg.neg_slope, cfg.p_attn, cfg.attn_seed, cfg.attn_stream, ptr(ds), ptr(da2),
+                                                      ptr(dft), F_, ptr(dft_lo), ptr(partial), stream), "tx_gat_fused_bwd_staged")
+                else:
+                    nbf = int(lib.tx_gat_fused_bwd_blocks(n, H))
+                    partial = torch.empty(nbf * 2 * F_, **f32)
+                    check(lib.tx_gat_fused_bwd(ptr(dout), ldg, g_head_stride, g_scale, None if pre else ptr(ctx.maskbits),
+                                               1 if cfg.p_next > 0.0 else 0, cfg.act_slope, cfg.p_next if cfg.hidden else 0.0,
+                                               ptr(ft), F_, ptr(alpha), ptr(alpha_d),
+                                               ptr(elog), ptr(al), ptr(ar), ptr(st.in_ptr), ptr(st.in_src), ptr(st.in_eid),
+                                               ptr(st.out_ptr), ptr(st.out_dst), ptr(st.out_slot), ptr(st.node_off), st.g, n, H, D,
+                                               cfg.neg_slope, cfg.p_attn, cfg.attn_seed, cfg.attn_stream, ptr(ds), ptr(da2), ptr(dft),
+                                               F_, ptr(dft_lo), ptr(partial), stream), "tx_gat_fused_bwd")
                 both = _reduce_partials(lib, partial, nbf, 2 * F_)
                 dal, dar = both[:F_].view(ctx.attn_shape), both[F_:].view(ctx.attn_shape)
             else:

@@ -26,14 +26,28 @@ class GraphStructure:
     """Device-resident structure of one batched graph (all int32)."""
 
     __slots__ = ("device", "n", "e", "g", "in_ptr", "in_src", "in_eid", "out_ptr", "out_dst", "out_slot", "node_off",
-                 "pos", "src", "dst", "max_nodes", "_norm", "is_star")
+                 "pos", "src", "dst", "max_nodes", "_norm", "is_star", "_bwd_tiles")
 
     def __init__(self, device):
         self.device = device
         self._norm = None
+        self._bwd_tiles = {}
         self.pos = None
         self.src = self.dst = None
         self.is_star = False
+
+    def bwd_tiles(self, dim: int) -> torch.Tensor:
+        """Tile table of the TMA-staged fused GAT backward (tx_gat_bwd_tiles) for per-head width `dim`; built once per batch."""
+        lib = _lib.load()
+        rows = int(lib.tx_gat_bwd_tile_rows(dim))
+        t = self._bwd_tiles.get(rows)
+        if t is None:
+            nt = int(lib.tx_gat_bwd_num_tiles(self.n, dim))
+            t = torch.empty((nt + 1) * 4, dtype=torch.int32, device=self.device)
+            _lib.check(lib.tx_gat_bwd_tiles(_lib.ptr(self.node_off), self.g, self.n, _lib.ptr(self.in_ptr), _lib.ptr(self.out_ptr), dim,
+                                            _lib.ptr(t), _lib.current_stream()), "tx_gat_bwd_tiles")
+            self._bwd_tiles[rows] = t
+        return t
 
     def gcn_norm(self) -> torch.Tensor:
         """in_degree ** -0.5 with inf -> 0 (model_zoo.py:157-161), fp32 [N]."""
