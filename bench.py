@@ -327,8 +327,10 @@ def run_b200(args, rank, world, local_rank):
     kern = {}
     for (name, tag), v in sorted(prof.items()):
         kern[f"{name}[{tag}]"] = round(float(np.sum(v)) / args.steps, 4)
-    nested = ("tx_gemm_nt_tf32x3", "tx_gemm_tn_tf32x3", "tx_split_tf32")      # recorded inside the gemm_* / split_dy regions
-    step_prof_ms = sum(v for k, v in kern.items() if not k.startswith(nested) or txf.GEMM_BACKEND != "tf32x3")
+    # ABI calls recorded INSIDE the gemm_* / split_dy regions (not added twice to the per-step sum)
+    nested = ("tx_gemm_nt_tf32x3", "tx_gemm_tn_tf32x3", "tx_split_tf32", "tx_gemm_nt_f16x3", "tx_gemm_tn_f16x3", "tx_split_f16", "tx_absmax")
+    in_region = {"tx_reduce_partials"} if txf.GEMM_BACKEND in ("tf32x3", "f16x3") else set()
+    step_prof_ms = sum(v for k, v in kern.items() if not k.startswith(nested) or txf.GEMM_BACKEND == "cublas")
     rl = []
     for tag, H, W in (("L0", H0, W0), ("L1", H1, W1)):
         for fwd_names, label in ((("tx_gat_fused_fwd",), "tx_gat_fused_fwd"), (("tx_gat_node_logits", "tx_gat_aggregate_fwd"), "tx_gat_node_logits+aggregate_fwd")):
@@ -380,7 +382,8 @@ def run_b200(args, rank, world, local_rank):
                    "egonets_per_gpu_step": sh.num_graphs, "nodes_per_gpu_step": int(n_avg), "edges_per_gpu_step": int(e_avg),
                    "dropout": 0.1, "parallelism": f"dp{world} (egonet shards by query group)",
                    "l2": f"inputs larger than L2: per-step intermediates ~{(n_avg * (W0 * 3 + 2052 * 2 + W1 * 3) * 4) / 1e9:.2f} GB; {nb} rotating batches",
-                   "dense": ("tcgen05 3xTF32 (tx_gemm.cu), fp32-faithful" if txf.GEMM_BACKEND == "tf32x3" else "torch.mm (cuBLAS fp32, TF32 off)")},
+                   "dense": {"f16x3": "tcgen05 kind::f16 on fp16 hi/lo operand pairs, 3 MMAs per product (tx_gemm.cu), fp32-faithful",
+                             "tf32x3": "tcgen05 3xTF32 (tx_gemm.cu), fp32-faithful"}.get(txf.GEMM_BACKEND, "torch.mm (cuBLAS fp32, TF32 off)")},
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": x_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": round(e2e_ms / args.steps, 4)},
         "gpu_launches": launches,

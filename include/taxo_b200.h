@@ -212,7 +212,19 @@ int tx_gat_fused_bwd_staged(const float* g, int64_t ldg, int64_t g_head_stride, 
                             const int32_t* out_ptr, const int32_t* out_dst, const int32_t* out_slot, const int32_t* tiles,
                             int64_t n_nodes, int64_t heads, int64_t dim, float neg_slope, float p_attn, uint64_t attn_seed,
                             uint32_t attn_stream_id, float* ds, float* da2, float* dft, int64_t ldd, float* dft_lo,
+                            void* dft16_hi, void* dft16_lo, int64_t ld16, const float* bound, float* scale_out,
                             float* dattn_partial, void* stream);
+/* fp16-split outputs of the fused kernels (operands of tx_gemm_*_f16x3; x * scale = hi + lo, hi / lo fp16 [N, ld16], ld16 % 8 == 0,
+ * scale derived on the device from *bound, an upper bound of the written magnitudes, and stored to *scale_out):
+ *   tx_gat_fused_bwd_staged: dft16_hi != NULL replaces dft / dft_lo;  bound from tx_bound_dft.
+ *   tx_gat_fused_fwd_f16   : a hidden layer's epilogue (the next layer's input) replaces `out`; bound = max(max|ft| / ((1 - p_attn)
+ *                            (1 - p_drop)), max|next_pos_table| / (1 - p_drop)) (attention weights are convex).  `ldo` stays the
+ *                            LOGICAL fp32 pitch round4(heads*dim + pos_dim): it indexes the dropout counters. */
+int tx_gat_fused_fwd_f16(const float* ft, int64_t ldf, const float* attn_l, const float* attn_r, const int32_t* in_ptr,
+                         const int32_t* in_src, const int32_t* in_eid, int64_t n_nodes, int64_t heads, int64_t dim,
+                         float neg_slope, float p_attn, uint64_t attn_seed, uint32_t attn_stream_id, float* alpha,
+                         float* alpha_d, float* elog, int64_t ldo, const tx_gat_epilogue* epi, uint32_t* maskbits, void* out16_hi,
+                         void* out16_lo, int64_t ld16, const float* bound, float* scale_out, void* stream);
 /* dpos_partial[b, r, :] = sum over rows i of block b (tx_row_blocks) with pos_i = r of dz[i, col0 : col0+pos_dim] * keep/(1-p)
  * (gradient of the appended position-embedding block, reference model_zoo.py:214-215). */
 int tx_pos_grad_partials(const float* dz, int64_t ldz, int64_t col0, const int32_t* pos, int64_t n_nodes,
@@ -290,6 +302,36 @@ int tx_gemm_nt_tf32x3_ex(const float* a_hi, const float* a_lo, int64_t lda, cons
  * ------------------------------------------------------------------------------------------------ */
 int tx_dropout_keep_mask(uint64_t seed, uint32_t stream_id, int64_t first_index, int64_t n, float p_drop,
                          uint8_t* keep, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * fp16-split variant of the dense projections (same reference call sites: model/model_zoo.py:83,37 and their autograd GEMMs):
+ * every fp32 operand x is passed as TWO fp16 arrays with x * scale = hi + lo (hi = rn_f16(x scale), lo = rn_f16(x scale - hi)) and a
+ * per-tensor power-of-two `scale` held in a DEVICE float; the product is accumulated as A_lo.B_hi + A_hi.B_lo + A_hi.B_hi by
+ * tcgen05.mma.kind::f16 (fp32 accumulation in tensor memory, chunked promotion as for the TF32 form) and the epilogue multiplies by
+ * 1 / (scale_a scale_b).  22 significant bits per operand like the 3xTF32 form, at twice the tensor rate and half the operand
+ * bytes.  The scale comes from an UPPER BOUND of max|x| (device float, tx_absmax or an analytic bound combined on the device by
+ * tx_bound_max2 / tx_bound_dft): |x| scale <= 2^13; accuracy is full while the bound is within 2^16 of the true maximum.
+ * Nothing here synchronises with the host.  Row pitches of the fp16 arrays are multiples of 8 elements (16 bytes).
+ * ------------------------------------------------------------------------------------------------ */
+int tx_absmax(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* out, void* stream);  /* *out = max |x[i, c]| */
+int tx_bound_max2(const float* a, float ca, const float* b, float cb, float* out, void* stream);  /* *out = max(*a ca, *b cb); b may be NULL */
+/* *out = *g_amax (c_direct + c_attn *ft_amax max(*attn_l_amax, *attn_r_amax)): bound of |dft| written by the fused GAT backward
+ * (dft_j = sum_i alpha~_ij g_i + da1_j attn_l + da2_j attn_r with |d alpha~| <= dim max|g| max|ft|). */
+int tx_bound_dft(const float* g_amax, const float* ft_amax, const float* attn_l_amax, const float* attn_r_amax, float c_direct,
+                 float c_attn, float* out, void* stream);
+/* hi, lo: fp16 [rows, ldo] (columns >= cols zero); *scale_out (optional) = the scale derived from *bound. */
+int tx_split_f16(const float* x, int64_t ldx, int64_t rows, int64_t cols, const float* bound, void* hi, void* lo, int64_t ldo,
+                 float* scale_out, void* stream);
+/* C[m, n] = sum_k A[m, k] B[n, k] / (scale_a scale_b); optional fused mask epilogue (as tx_gemm_nt_tf32x3_ex) and optional
+ * *amax_out = max |C| (device float, atomically maximised; zeroed by the call). */
+int tx_gemm_nt_f16x3(const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi, const void* b_lo, int64_t ldb,
+                     const float* scale_a, const float* scale_b, float* c, int64_t ldc, int64_t m, int64_t n, int64_t k,
+                     const tx_gemm_epilogue* epilogue, float* amax_out, void* stream);
+/* Weight-gradient form C[m, n] = sum_r A[r, m] B[r, n] / (scale_a scale_b), split-K partials as tx_gemm_tn_tf32x3. */
+int64_t tx_gemm_tn_f16_splits(int64_t m, int64_t n, int64_t r);
+int tx_gemm_tn_f16x3(const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi, const void* b_lo, int64_t ldb,
+                     const float* scale_a, const float* scale_b, float* c_partial, int64_t ldc, int64_t split_stride, int64_t m,
+                     int64_t n, int64_t r, int64_t splits, void* stream);
 
 #ifdef __cplusplus
 }

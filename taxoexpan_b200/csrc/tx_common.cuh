@@ -1,5 +1,6 @@
 // Shared device helpers for libtaxo_sm100 (sm_100a only).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -143,6 +144,32 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp16 hi/lo split of fp32 data for the tcgen05 kind::f16 GEMMs (tx_gemm.cu): x * scale = hi + lo with a per-tensor power-of-two
+// scale derived from an UPPER BOUND of |x| so that |x| * scale <= 2^13 (fp16 max is 65504).  hi carries 11 significant bits,
+// lo the next 11 (exactly when |x * scale| >= 2^-3, else down to the fp16 subnormal spacing 2^-24): the absolute error is at most
+// max(2^-22 |x|, 2^-25 / scale), i.e. <= 2^-22 of the tensor's largest entry whenever the bound is within 2^16 of the true maximum.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float f16_split_scale(float bound) {
+  if (!(bound > 0.f) || !(bound < 3.0e38f)) return 1.f;
+  int e;
+  frexpf(bound, &e);                 // bound = m 2^e with m in [0.5, 1)  =>  bound <= 2^e
+  int sh = 13 - e;
+  sh = sh < -120 ? -120 : (sh > 120 ? 120 : sh);
+  return ldexpf(1.f, sh);
+}
+// returns {hi.x | hi.y << 16, ...}: packs the fp16 hi (or lo) halves of 4 scaled values into two 32-bit words
+__device__ __forceinline__ void f16_split4(float4 v, float scale, uint2& hi, uint2& lo) {
+  const float c = 65504.f;
+  const float x0 = fminf(fmaxf(v.x * scale, -c), c), x1 = fminf(fmaxf(v.y * scale, -c), c);
+  const float x2 = fminf(fmaxf(v.z * scale, -c), c), x3 = fminf(fmaxf(v.w * scale, -c), c);
+  const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+  const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+  const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y), l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
+  hi = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+  lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
 }
 
 __host__ __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

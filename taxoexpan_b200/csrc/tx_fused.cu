@@ -88,6 +88,8 @@ struct FusedFwdParams {
   float* alpha; float* alpha_d; float* elog;
   float* out; int64_t ldo;
   float* out_lo;           // optional: when set, `out` receives the TF32 hi part and out_lo the lo part of every written value
+  // optional fp16-split output (next layer's GEMM operand): x * scale = hi + lo, scale derived from the device bound; replaces `out`
+  __half* out16_hi; __half* out16_lo; int64_t ld16; const float* bound; float* scale_out;
   uint32_t* maskbits;      // bytes [n, mask_ld]: byte (h*D + c)/4 of a row = 4 sign bits | 4 keep bits << 4 of columns c..c+3; may be null
   int mask_ld;             // = tx_gat_fused_mask_ld(H, D): H*D/4 rounded up to 16
   // epilogue
@@ -118,6 +120,8 @@ __global__ void __launch_bounds__(256, 3) gat_fused_fwd_kernel(const FusedFwdPar
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const bool attn_drop = p.attn_thr != 0;
   const float* base = p.ft + (int64_t)h * D;
+  const float scale16 = p.out16_hi ? f16_split_scale(__ldg(p.bound)) : 1.f;
+  if (p.out16_hi && p.scale_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *p.scale_out = scale16;
   for (int i = warp; i < p.n; i += nwarps) {
     const int beg = __ldg(p.in_ptr + i), end = __ldg(p.in_ptr + i + 1);
     const int deg = end - beg;
@@ -205,7 +209,13 @@ __global__ void __launch_bounds__(256, 3) gat_fused_fwd_kernel(const FusedFwdPar
             code &= keep ? 0xFFu : ~(16u << u);
           }
         }
-        if (olo) store_split4(orow + 128 * t, olo + 128 * t, make_float4(v[0], v[1], v[2], v[3]));
+        if (p.out16_hi) {
+          uint2 h16, l16;
+          f16_split4(make_float4(v[0], v[1], v[2], v[3]), scale16, h16, l16);
+          const int64_t o16 = (int64_t)i * p.ld16 + (int64_t)h * D + (lane + 32 * t) * 4;
+          *reinterpret_cast<uint2*>(p.out16_hi + o16) = h16;
+          *reinterpret_cast<uint2*>(p.out16_lo + o16) = l16;
+        } else if (olo) store_split4(orow + 128 * t, olo + 128 * t, make_float4(v[0], v[1], v[2], v[3]));
         else *reinterpret_cast<float4*>(orow + 128 * t) = make_float4(v[0], v[1], v[2], v[3]);
         if (mrow) mrow[32 * t] = (uint8_t)code;     // 4 sign bits | 4 keep bits << 4 of this lane's 4 columns
       }
@@ -216,13 +226,19 @@ __global__ void __launch_bounds__(256, 3) gat_fused_fwd_kernel(const FusedFwdPar
       const int pd = p.pos_dim;
       float* row = p.out + (int64_t)i * p.ldo;
       const float* prow = pd > 0 ? p.next_pos_table + (int64_t)__ldg(p.pos + i) * pd : nullptr;
-      for (int c = feat + lane; c < (int)p.ldo; c += 32) {
+      const int c_end = p.out16_hi ? (int)p.ld16 : (int)p.ldo;
+      for (int c = feat + lane; c < c_end; c += 32) {
         float v = 0.f;
         if (c < feat + pd) {
           v = __ldg(prow + (c - feat));
           if (p.next_thr) v = drop_keep1(p.next_seed, p.next_stream, (uint64_t)((int64_t)i * p.ldo + c), p.next_thr) ? v * p.next_inv_keep : 0.f;
         }
-        if (p.out_lo) {
+        if (p.out16_hi) {
+          const float x = fminf(fmaxf(v * scale16, -65504.f), 65504.f);
+          const __half hh = __float2half_rn(x);
+          p.out16_hi[(int64_t)i * p.ld16 + c] = hh;
+          p.out16_lo[(int64_t)i * p.ld16 + c] = __float2half_rn(x - __half2float(hh));
+        } else if (p.out_lo) {
           const float vh = rn_tf32_f(v);
           row[c] = vh;
           p.out_lo[(int64_t)i * p.ldo + c] = rn_tf32_f(v - vh);
@@ -615,16 +631,47 @@ int64_t tx_gat_fused_bwd_blocks(int64_t n_nodes, int64_t heads) {
   return gx < 1 ? 1 : gx;
 }
 
+static int gat_fused_fwd_impl(const float* ft, int64_t ldf, const float* attn_l, const float* attn_r, const int32_t* in_ptr,
+                              const int32_t* in_src, const int32_t* in_eid, int64_t n_nodes, int64_t heads, int64_t dim,
+                              float neg_slope, float p_attn, uint64_t attn_seed, uint32_t attn_stream_id, float* alpha,
+                              float* alpha_d, float* elog, float* out, int64_t ldo, const tx_gat_epilogue* epi, uint32_t* maskbits,
+                              float* out_lo, void* out16_hi, void* out16_lo, int64_t ld16, const float* bound, float* scale_out,
+                              void* stream);
+
 int tx_gat_fused_fwd(const float* ft, int64_t ldf, const float* attn_l, const float* attn_r, const int32_t* in_ptr,
                      const int32_t* in_src, const int32_t* in_eid, int64_t n_nodes, int64_t heads, int64_t dim,
                      float neg_slope, float p_attn, uint64_t attn_seed, uint32_t attn_stream_id, float* alpha,
                      float* alpha_d, float* elog, float* out, int64_t ldo, const tx_gat_epilogue* epi, uint32_t* maskbits,
                      float* out_lo, void* stream) {
+  return gat_fused_fwd_impl(ft, ldf, attn_l, attn_r, in_ptr, in_src, in_eid, n_nodes, heads, dim, neg_slope, p_attn, attn_seed,
+                            attn_stream_id, alpha, alpha_d, elog, out, ldo, epi, maskbits, out_lo, nullptr, nullptr, 0, nullptr, nullptr,
+                            stream);
+}
+
+int tx_gat_fused_fwd_f16(const float* ft, int64_t ldf, const float* attn_l, const float* attn_r, const int32_t* in_ptr,
+                         const int32_t* in_src, const int32_t* in_eid, int64_t n_nodes, int64_t heads, int64_t dim,
+                         float neg_slope, float p_attn, uint64_t attn_seed, uint32_t attn_stream_id, float* alpha,
+                         float* alpha_d, float* elog, int64_t ldo, const tx_gat_epilogue* epi, uint32_t* maskbits, void* out16_hi,
+                         void* out16_lo, int64_t ld16, const float* bound, float* scale_out, void* stream) {
+  TX_REQUIRE(epi && !epi->mean_heads, "gat_fused_fwd_f16: only a hidden layer's epilogue (the next layer's input) can be written fp16-split");
+  TX_REQUIRE(out16_hi && out16_lo && bound && aligned16(out16_hi) && aligned16(out16_lo) && ld16 % 8 == 0 &&
+             ld16 >= heads * dim + epi->pos_dim, "gat_fused_fwd_f16: bad fp16 output buffers");
+  return gat_fused_fwd_impl(ft, ldf, attn_l, attn_r, in_ptr, in_src, in_eid, n_nodes, heads, dim, neg_slope, p_attn, attn_seed,
+                            attn_stream_id, alpha, alpha_d, elog, nullptr, ldo, epi, maskbits, nullptr, out16_hi, out16_lo, ld16, bound,
+                            scale_out, stream);
+}
+
+static int gat_fused_fwd_impl(const float* ft, int64_t ldf, const float* attn_l, const float* attn_r, const int32_t* in_ptr,
+                              const int32_t* in_src, const int32_t* in_eid, int64_t n_nodes, int64_t heads, int64_t dim,
+                              float neg_slope, float p_attn, uint64_t attn_seed, uint32_t attn_stream_id, float* alpha,
+                              float* alpha_d, float* elog, float* out, int64_t ldo, const tx_gat_epilogue* epi, uint32_t* maskbits,
+                              float* out_lo, void* out16_hi, void* out16_lo, int64_t ld16, const float* bound, float* scale_out,
+                              void* stream) {
   TX_REQUIRE(epi, "gat_fused_fwd: epilogue required");
   TX_REQUIRE(!out_lo || aligned16(out_lo), "gat_fused_fwd: out_lo must be 16-byte aligned");
   TX_REQUIRE(tx_gat_fused_supported(heads, dim, epi->mean_heads), "gat_fused_fwd: unsupported shape (heads %lld dim %lld); use the general path",
              (long long)heads, (long long)dim);
-  TX_REQUIRE(aligned16(ft) && ldf % 4 == 0 && aligned16(out) && ldo % 4 == 0 && aligned16(attn_l) && aligned16(attn_r),
+  TX_REQUIRE(aligned16(ft) && ldf % 4 == 0 && (out16_hi || (out && aligned16(out))) && ldo % 4 == 0 && aligned16(attn_l) && aligned16(attn_r),
              "gat_fused_fwd: 16-byte aligned rows required");
   TX_REQUIRE(p_attn >= 0.f && p_attn < 1.f && epi->p_drop >= 0.f && epi->p_drop < 1.f, "gat_fused_fwd: dropout rates must be in [0,1)");
   TX_REQUIRE(alpha && elog && (p_attn == 0.f || (alpha_d && alpha_d != alpha)), "gat_fused_fwd: alpha/elog/alpha_d buffers");
@@ -639,6 +686,7 @@ int tx_gat_fused_fwd(const float* ft, int64_t ldf, const float* attn_l, const fl
   p.alpha = alpha; p.alpha_d = alpha_d ? alpha_d : alpha; p.elog = elog; p.out = out; p.ldo = ldo; p.maskbits = maskbits;
   p.mask_ld = (int)tx_gat_fused_mask_ld(heads, dim);
   p.out_lo = out_lo;
+  p.out16_hi = (__half*)out16_hi; p.out16_lo = (__half*)out16_lo; p.ld16 = ld16; p.bound = bound; p.scale_out = scale_out;
   p.hidden = epi->mean_heads ? 0 : 1; p.act_slope = epi->act_slope; p.next_pos_table = epi->next_pos_table; p.pos = epi->pos;
   p.pos_dim = (int)epi->pos_dim; p.next_inv_keep = 1.f / (1.f - epi->p_drop); p.next_thr = drop_threshold(epi->p_drop);
   p.next_seed = epi->seed; p.next_stream = epi->stream_id;

@@ -60,6 +60,8 @@ struct StagedBwdParams {
   float neg_slope; float attn_inv_keep; uint32_t attn_thr; uint64_t attn_seed; uint32_t attn_stream;
   float* ds; float* da2;
   float* dft; int64_t ldd; float* dft_lo;
+  // optional fp16-split output (operand of the weight / input gradient GEMMs): dft * scale = hi + lo; replaces dft / dft_lo
+  __half* dft16_hi; __half* dft16_lo; int64_t ld16; const float* bound; float* scale_out;
   float* dattn_partial;   // [gridDim.x, 2, H, D]
 };
 
@@ -106,6 +108,20 @@ __device__ __forceinline__ void store_dft4(float* hi_ptr, float* lo_ptr, float4 
     *reinterpret_cast<float4*>(lo_ptr) = make_float4(rn_tf32_b(v.x - h.x), rn_tf32_b(v.y - h.y), rn_tf32_b(v.z - h.z), rn_tf32_b(v.w - h.w));
   } else {
     *reinterpret_cast<float4*>(hi_ptr) = v;
+  }
+}
+
+// one float4 of dft at (row, column c of head h): fp32, TF32 hi/lo or fp16 hi/lo
+__device__ __forceinline__ void store_dft(const StagedBwdParams& p, float scale16, int64_t row, int h, int c, float4 v) {
+  if (p.dft16_hi) {
+    uint2 h16, l16;
+    f16_split4(v, scale16, h16, l16);
+    const int64_t o = row * p.ld16 + (int64_t)h * p.D + c;
+    *reinterpret_cast<uint2*>(p.dft16_hi + o) = h16;
+    *reinterpret_cast<uint2*>(p.dft16_lo + o) = l16;
+  } else {
+    const int64_t off = row * p.ldd + (int64_t)h * p.D + c;
+    store_dft4(p.dft + off, p.dft_lo ? p.dft_lo + off : nullptr, v);
   }
 }
 
@@ -311,6 +327,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gat_bwd_staged_kernel(const St
   const int hgrp = ctid / W, hcol = ctid - hgrp * W;
   const bool col_thread = hgrp < groups;
   const bool has2 = hcol + W < D4;
+  const float scale16 = p.dft16_hi ? f16_split_scale(__ldg(p.bound)) : 1.f;
+  if (p.dft16_hi && p.scale_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *p.scale_out = scale16;
   const int c1 = has2 ? hcol + W : hcol;       // clamped: reads stay in range, the duplicate is never stored
 
 #ifdef TX_BWD_PROFILE
@@ -403,11 +421,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gat_bwd_staged_kernel(const St
           float d1 = 0.f;
           float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
           const int ob = m.out_ptr[t], oe = m.out_ptr[t + 1];
-#ifdef TX_EXP_NOEDGE
-          for (int k = ob; k < min(oe, ob + 1); ++k) {
-#else
           for (int k = ob; k < oe; ++k) {
-#endif
             const int sl = m.out_slot[k];
             const int di = m.out_dst[k];
             d1 += m.ds[sl];                                     // da1_t = sum over out-edges of ds
@@ -424,14 +438,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gat_bwd_staged_kernel(const St
           }
           fma4(d1, cl0, acc0); fma4(d2, cr0, acc0);
           fma4(d1, cl1, acc1); fma4(d2, cr1, acc1);
-          const int64_t off = (int64_t)(r0 + t) * p.ldd + (int64_t)h * D;
-#ifdef TX_EXP_NOSTORE
-          if (acc0.x == 1234.5f && acc1.y == 77.f)
-#endif
-          {
-          store_dft4(p.dft + off + hcol * 4, p.dft_lo ? p.dft_lo + off + hcol * 4 : nullptr, acc0);
-          if (has2) store_dft4(p.dft + off + c1 * 4, p.dft_lo ? p.dft_lo + off + c1 * 4 : nullptr, acc1);
-          }
+          store_dft(p, scale16, r0 + t, h, hcol * 4, acc0);
+          if (has2) store_dft(p, scale16, r0 + t, h, c1 * 4, acc1);
         }
       }
     } else if (nrows > 0) {
@@ -484,9 +492,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gat_bwd_staged_kernel(const St
           fma4(d1, frow[c1], hvl[1]); fma4(d2, frow[c1], hvr[1]);
           fma4(d1, cl0, acc0); fma4(d2, cr0, acc0);
           fma4(d1, cl1, acc1); fma4(d2, cr1, acc1);
-          const int64_t off = (int64_t)j * p.ldd + (int64_t)h * D;
-          store_dft4(p.dft + off + hcol * 4, p.dft_lo ? p.dft_lo + off + hcol * 4 : nullptr, acc0);
-          if (has2) store_dft4(p.dft + off + c1 * 4, p.dft_lo ? p.dft_lo + off + c1 * 4 : nullptr, acc1);
+          store_dft(p, scale16, j, h, hcol * 4, acc0);
+          if (has2) store_dft(p, scale16, j, h, c1 * 4, acc1);
         }
       }
     }
@@ -609,10 +616,14 @@ int tx_gat_fused_bwd_staged(const float* g, int64_t ldg, int64_t g_head_stride, 
                             const int32_t* out_ptr, const int32_t* out_dst, const int32_t* out_slot, const int32_t* tiles,
                             int64_t n_nodes, int64_t heads, int64_t dim, float neg_slope, float p_attn, uint64_t attn_seed,
                             uint32_t attn_stream_id, float* ds, float* da2, float* dft, int64_t ldd, float* dft_lo,
+                            void* dft16_hi, void* dft16_lo, int64_t ld16, const float* bound, float* scale_out,
                             float* dattn_partial, void* stream) {
   TX_REQUIRE(g_head_stride != 0 || heads == 1, "gat_fused_bwd_staged: a shared g row (head mean) needs heads == 1");
+  TX_REQUIRE(!dft16_hi || (dft16_lo && bound && aligned16(dft16_hi) && aligned16(dft16_lo) && ld16 % 8 == 0 && ld16 >= heads * dim),
+             "gat_fused_bwd_staged: bad fp16 output buffers");
+  TX_REQUIRE(dft16_hi || dft, "gat_fused_bwd_staged: an output buffer is required");
   TX_REQUIRE(dim > 0 && dim % 4 == 0 && dim <= 512, "gat_fused_bwd_staged: dim must be a multiple of 4 and <= 512");
-  TX_REQUIRE(aligned16(g) && ldg % 4 == 0 && g_head_stride % 4 == 0 && aligned16(ft) && ldf % 4 == 0 && aligned16(dft) && ldd % 4 == 0 &&
+  TX_REQUIRE(aligned16(g) && ldg % 4 == 0 && g_head_stride % 4 == 0 && aligned16(ft) && ldf % 4 == 0 && (!dft || aligned16(dft)) && ldd % 4 == 0 &&
              aligned16(attn_l) && aligned16(attn_r) && aligned16(dattn_partial) && (!dft_lo || aligned16(dft_lo)) && aligned16(tiles),
              "gat_fused_bwd_staged: 16-byte aligned rows required");
   TX_REQUIRE(p_attn >= 0.f && p_attn < 1.f, "gat_fused_bwd_staged: dropout rate must be in [0,1)");
@@ -627,6 +638,7 @@ int tx_gat_fused_bwd_staged(const float* g, int64_t ldg, int64_t g_head_stride, 
   p.n = (int)n_nodes; p.H = (int)heads; p.D = (int)dim;
   p.neg_slope = neg_slope; p.attn_inv_keep = 1.f / (1.f - p_attn); p.attn_thr = drop_threshold(p_attn); p.attn_seed = attn_seed;
   p.attn_stream = attn_stream_id; p.ds = ds; p.da2 = da2; p.dft = dft; p.ldd = ldd; p.dft_lo = dft_lo; p.dattn_partial = dattn_partial;
+  p.dft16_hi = (__half*)dft16_hi; p.dft16_lo = (__half*)dft16_lo; p.ld16 = ld16; p.bound = bound; p.scale_out = scale_out;
   const int nv = (int)((dim + 127) / 128);
   size_t ring_bytes = (size_t)p.ring_rows * 2 * dim * 4;
   const size_t scratch_bytes = (size_t)kCT * 4 * 16;   // [groups][2][D4] float4, groups * D4 <= 2 kCT

@@ -92,14 +92,24 @@ __device__ __forceinline__ uint64_t umma_desc_k(uint32_t smem_addr) {
   return BK == 32 ? umma_desc_k_sw128(smem_addr) : umma_desc_k_sw64(smem_addr);
 }
 
-// D[tmem] (+)= A[smem] . B[smem]^T, kind::tf32, cta_group::1
+// D[tmem] (+)= A[smem] . B[smem]^T, kind::tf32 (F16 = false) or kind::f16 (F16 = true), cta_group::1
+template <bool F16>
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if constexpr (F16) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
 
 // MN-major operands (reduction index slow in memory).  For 32-bit (tf32) MN-major operands the tensor core accepts ONE
@@ -141,6 +151,10 @@ struct GemmEpilogue {
   const uint8_t* mask;
   int heads, dim, stride, feat_cols, has_keep;
   float on, neg;
+  // fp16-split operands carry per-tensor power-of-two scales: C = acc / (scale_a * scale_b) (device scalars; null = 1)
+  const float* scale_a;
+  const float* scale_b;
+  float* amax_out;      // optional: atomicMax of |C| over everything stored (device scalar, zeroed by the launcher)
 };
 
 constexpr int kChunkK = 64;      // K extent accumulated inside the tensor core before promotion to fp32 registers (24 MMAs)
@@ -155,19 +169,25 @@ constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogu
 // TN = true : A [R, M], B [R, N] row-major (MN-major operands, reduction over rows): dW = dy^T z; grid.z = split index.
 // CL = 2: clusters of two CTAs along M share every B tile - each CTA fetches half of it and TMA-multicasts it to both, which cuts
 // the L2 -> SM operand traffic per CTA from (A + B) to (A + B/2) (the 3xTF32 kernel is L2-bandwidth bound: 96 KB per k-block).
-template <int BN, int STAGES, bool TN, int BK, int CL>
+// F16 = true: the operands are fp16 hi / lo pairs (x * scale = hi + lo, per-tensor power-of-two scale): same 128-byte smem rows
+// (64 fp16 instead of 32 tf32 per k-block row), tcgen05.mma.kind::f16 (UMMA_K = 16, i.e. the same 32 bytes per step) at twice
+// the tensor rate and half the operand bytes per flop; MN-major operands use the plain SWIZZLE_128B layout (64 elements per row).
+template <int BN, int STAGES, bool TN, int BK, int CL, bool F16>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                    float* __restrict__ C, int64_t ldc, int64_t split_stride, int M, int n_store, int k_blocks_total,
                    int k_blocks_per_split, uint64_t mn_desc_bits, const GemmEpilogue epi) {
   static_assert(BK == 32 || (BK == 16 && !TN), "BK = 16 (64-byte rows, SWIZZLE_64B) is implemented for the K-major form only");
-  constexpr int kBK = BK;
+  constexpr int kBK = BK;                     // 4-byte units per k-block row of a K-major tile (32 = 128 bytes)
+  constexpr int BKE = F16 ? 2 * BK : BK;      // reduction ELEMENTS per k-block
+  constexpr int BOXC = F16 ? 64 : 32;         // TN: MN elements per box row (128 bytes)
   constexpr int kABytes = kBM * BK * 4;
   constexpr int kChunk = kChunkK / BK;
   constexpr int B_BYTES = BN * kBK * 4;
   constexpr int STAGE_BYTES = 2 * kABytes + 2 * B_BYTES;
-  constexpr int BOX_BYTES = kBK * 128;       // TN: one {32 cols, kBK rows} box
+  constexpr int BOX_BYTES = BKE * 128;       // TN: one {BOXC cols, BKE rows} box
+  static_assert(!(TN && F16) || BN % 64 == 0, "fp16 MN-major tiles are made of 64-column boxes");
   constexpr int HALF = ((BN / 32 + 1) / 2) * 32;   // columns owned by an epilogue warp of group 0 (group 1: BN - HALF), chunks of 32
   constexpr uint32_t TMEM_COLS = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   static_assert(BN % 32 == 0 && BN >= 64 && BN <= 256, "BN must be a multiple of 32 in [64, 256]");
@@ -218,7 +238,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         const uint32_t full = full0 + 8 * s;
         mbar_expect_tx(full, STAGE_BYTES);
         const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
-        const int kk = (kb0 + kb) * kBK;
+        const int kk = (kb0 + kb) * BKE;
         if constexpr (!TN) {
           tma_load_2d(base, &map_a_hi, full, kk, m0);
           tma_load_2d(base + kABytes, &map_a_lo, full, kk, m0);
@@ -232,19 +252,19 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
           }
         } else {
 #pragma unroll
-          for (int b = 0; b < kBM / 32; ++b) {
-            tma_load_2d(base + b * BOX_BYTES, &map_a_hi, full, m0 + 32 * b, kk);
-            tma_load_2d(base + kABytes + b * BOX_BYTES, &map_a_lo, full, m0 + 32 * b, kk);
+          for (int b = 0; b < kBM / BOXC; ++b) {
+            tma_load_2d(base + b * BOX_BYTES, &map_a_hi, full, m0 + BOXC * b, kk);
+            tma_load_2d(base + kABytes + b * BOX_BYTES, &map_a_lo, full, m0 + BOXC * b, kk);
           }
-          constexpr int NB = BN / 32, NB0 = (NB + 1) / 2;          // CL = 2: rank 0 fetches boxes [0, NB0), rank 1 the rest
+          constexpr int NB = BN / BOXC, NB0 = (NB + 1) / 2;        // CL = 2: rank 0 fetches boxes [0, NB0), rank 1 the rest
 #pragma unroll
           for (int b = 0; b < NB; ++b) {
             if (CL == 1) {
-              tma_load_2d(base + 2 * kABytes + b * BOX_BYTES, &map_b_hi, full, n0 + 32 * b, kk);
-              tma_load_2d(base + 2 * kABytes + B_BYTES + b * BOX_BYTES, &map_b_lo, full, n0 + 32 * b, kk);
+              tma_load_2d(base + 2 * kABytes + b * BOX_BYTES, &map_b_hi, full, n0 + BOXC * b, kk);
+              tma_load_2d(base + 2 * kABytes + B_BYTES + b * BOX_BYTES, &map_b_lo, full, n0 + BOXC * b, kk);
             } else if ((b < NB0) == (crank == 0)) {
-              tma_load_2d_mc(base + 2 * kABytes + b * BOX_BYTES, &map_b_hi, full, n0 + 32 * b, kk, (uint16_t)3);
-              tma_load_2d_mc(base + 2 * kABytes + B_BYTES + b * BOX_BYTES, &map_b_lo, full, n0 + 32 * b, kk, (uint16_t)3);
+              tma_load_2d_mc(base + 2 * kABytes + b * BOX_BYTES, &map_b_hi, full, n0 + BOXC * b, kk, (uint16_t)3);
+              tma_load_2d_mc(base + 2 * kABytes + B_BYTES + b * BOX_BYTES, &map_b_lo, full, n0 + BOXC * b, kk, (uint16_t)3);
             }
           }
         }
@@ -254,8 +274,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     if (lane == 0) {   // ===== MMA issuer =====
       // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6) = 1, a/b_format TF32 [7,10),[10,13) = 2,
       // a_major [15], b_major [16] (0 = K-major, 1 = MN-major), n_dim [17,23) = N >> 3, m_dim [24,29) = M >> 4
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (TN ? ((1u << 15) | (1u << 16)) : 0u) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (F16 ? 0u : ((2u << 7) | (2u << 10))) | (TN ? ((1u << 15) | (1u << 16)) : 0u) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);   // a/b_format: 0 = F16, 2 = TF32
       for (int ch = 0; ch < n_chunks; ++ch) {
         const int buf = ch & 1;
         mbar_wait(tempty0 + 8 * buf, ((ch >> 1) & 1) ^ 1);     // epilogue has drained this accumulator buffer
@@ -278,12 +298,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
           }
 #pragma unroll
           for (int k = 0; k < kBK / 8; ++k) {
-            // UMMA_K = 8 tf32.  K-major: +32 bytes inside the 128-byte swizzle row; MN-major: next 8 reduction rows (+1024 bytes)
-            const uint64_t adv = TN ? (uint64_t)((k * 1024) >> 4) : (uint64_t)(2 * k);
+            // UMMA_K = 8 tf32 / 16 fp16.  K-major: +32 bytes inside the 128-byte swizzle row; MN-major: the next 8 / 16 reduction
+            // rows (+1024 / +2048 bytes)
+            const uint64_t adv = TN ? (uint64_t)((k * (F16 ? 2048 : 1024)) >> 4) : (uint64_t)(2 * k);
             const uint32_t first = (kb == ch * kChunk && k == 0) ? 0u : 1u;
-            umma_tf32(tacc, a_lo + adv, b_hi + adv, idesc, first);
-            umma_tf32(tacc, a_hi + adv, b_lo + adv, idesc, 1u);
-            umma_tf32(tacc, a_hi + adv, b_hi + adv, idesc, 1u);
+            umma_tf32<F16>(tacc, a_lo + adv, b_hi + adv, idesc, first);
+            umma_tf32<F16>(tacc, a_hi + adv, b_lo + adv, idesc, 1u);
+            umma_tf32<F16>(tacc, a_hi + adv, b_hi + adv, idesc, 1u);
           }
           if (CL == 1) tcgen05_commit(empty0 + 8 * s);         // frees the smem stage once these MMAs retire
           else tcgen05_commit_mc(empty0 + 8 * s, (uint16_t)3);  // ... in both CTAs (each writes half of B into the other)
@@ -317,6 +338,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
       if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
     }
     const int row = m0 + q * 32 + lane;
+    const float inv_scale = (epi.scale_a ? 1.f / __ldg(epi.scale_a) : 1.f) * (epi.scale_b ? 1.f / __ldg(epi.scale_b) : 1.f);   // powers of two: exact
+    float vmax = 0.f;
     if (row < M) {
       float* crow = C + (int64_t)blockIdx.z * split_stride + (int64_t)row * ldc + n0 + hsel * HALF;
       uint32_t mw[HALF / 16];                                  // 4 mask bytes (16 columns) per word
@@ -333,7 +356,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
       for (int j = 0; j < HALF / 4; ++j) {
         const int col = n0 + hsel * HALF + j * 4;
         if (j < n_chunks32 * 8 && col < n_store) {
-          float4 v = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+          float4 v = make_float4(acc[4 * j] * inv_scale, acc[4 * j + 1] * inv_scale, acc[4 * j + 2] * inv_scale, acc[4 * j + 3] * inv_scale);
           if (masked && col < epi.feat_cols) {
             uint32_t code = (mw[j >> 2] >> (8 * (j & 3))) & 0xFFu;
             if (!epi.has_keep) code |= 0xF0u;
@@ -343,8 +366,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             v.w *= (code & 128u) ? ((code & 8u) ? epi.on : epi.neg) : 0.f;
           }
           *reinterpret_cast<float4*>(crow + j * 4) = v;
+          vmax = fmaxf(vmax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
         }
       }
+    }
+    if (epi.amax_out) {      // warp-uniform branch
+      vmax = warp_max(vmax);
+      if (lane == 0 && vmax > 0.f) atomicMax(reinterpret_cast<unsigned int*>(epi.amax_out), __float_as_uint(vmax));   // non-negative floats order like uints
     }
   }
   tcgen05_fence_before();
@@ -368,13 +396,23 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 //              tfull[b] (both)    <- leader's commit multicast after a chunk
 //              tempty[b](leader)  <- 8 + 8 epilogue warps (the peer's arrive remotely through mapa)
 // =====================================================================================================================
+template <bool F16>
 __device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if constexpr (F16) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
 __device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
@@ -392,20 +430,24 @@ __device__ __forceinline__ void mbar_arrive_cta0(uint32_t bar) {   // arrive on 
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
-template <int BN, int STAGES, bool TN>
+template <int BN, int STAGES, bool TN, bool F16>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                         const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                         float* __restrict__ C, int64_t ldc, int64_t split_stride, int M, int n_store, int k_blocks_total,
-                        int k_blocks_per_split, uint64_t mn_desc_bits, const GemmEpilogue epi) {
+                        int k_blocks_per_split, uint64_t mn_desc_bits, const GemmEpilogue epi, int n_tiles_n, int n_m_pairs,
+                        int n_work) {
   constexpr int BK = 32;
+  constexpr int BKE = F16 ? 2 * BK : BK;                  // reduction elements per k-block
+  constexpr int BOXC = F16 ? 64 : 32;                     // TN: MN elements per box row
   constexpr int kABytes = kBM * BK * 4;
   constexpr int kChunk = kChunkK / BK;
   constexpr int BH = BN / 2;                              // B rows (NT) / columns (TN) staged by one CTA
   static_assert(BN % 64 == 0, "the pair kernel splits B into two halves of whole 32-wide blocks");
+  static_assert(!(TN && F16) || BH % 64 == 0, "fp16 MN-major halves are made of 64-column boxes");
   constexpr int BH_BYTES = BH * BK * 4;
   constexpr int STAGE_BYTES = 2 * kABytes + 2 * BH_BYTES;
-  constexpr int BOX_BYTES = BK * 128;
+  constexpr int BOX_BYTES = BKE * 128;
   constexpr int HALF = ((BN / 32 + 1) / 2) * 32;
   constexpr uint32_t TMEM_COLS = 2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512));
   extern __shared__ uint8_t smem_raw[];
@@ -442,22 +484,34 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
   cluster_sync_all();
   tcgen05_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
-  // grid.x = 2 * n_tiles (the two CTAs of a pair are neighbours in x: cluster {2,1,1}), grid.y = pairs of M tiles
-  const int m0 = (int)(blockIdx.y * 2 + (blockIdx.x & 1)) * kBM, n0 = (int)(blockIdx.x >> 1) * BN;
-  const int kb0 = blockIdx.z * k_blocks_per_split;
-  const int nkb = max(0, min(k_blocks_per_split, k_blocks_total - kb0));
-  const int n_chunks = (nkb + kChunk - 1) / kChunk;
+  // PERSISTENT: a 1-D grid of 2 x n_clusters CTAs (cluster {2,1,1}); cluster c walks the work items c, c + n_clusters, ... of the
+  // linear list (n tile fastest, then M-tile pair, then k split), so that the epilogue of one tile (accumulator drain + global
+  // stores) overlaps the TMA / MMA stream of the next: the smem ring and the two TMEM buffers simply keep rotating across tiles.
+  const int n_clusters = (int)(gridDim.x >> 1), cluster_id = (int)(blockIdx.x >> 1);
+  auto work_coords = [&](int w, int& m0, int& n0, int& kb0, int& nkb, int& z) {
+    const int n_idx = w % n_tiles_n, rest = w / n_tiles_n;
+    const int mp = rest % n_m_pairs;
+    z = rest / n_m_pairs;
+    m0 = (mp * 2 + (int)crank) * kBM;
+    n0 = n_idx * BN;
+    kb0 = z * k_blocks_per_split;
+    nkb = max(0, min(k_blocks_per_split, k_blocks_total - kb0));
+  };
 
   if (warp == 0) {
     if (lane == 0) {   // ===== TMA producer (both CTAs) =====
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
+      int gkb = 0;       // k-blocks issued so far by this CTA (ring position)
+      for (int w = cluster_id; w < n_work; w += n_clusters) {
+      int m0, n0, kb0, nkb, z;
+      work_coords(w, m0, n0, kb0, nkb, z);
+      for (int kb = 0; kb < nkb; ++kb, ++gkb) {
+        const int s = gkb % STAGES;
+        const uint32_t ph = (gkb / STAGES) & 1;
         mbar_wait(empty0 + 8 * s, ph ^ 1);
         const uint32_t full = full0 + 8 * s;
         if (leader) mbar_expect_tx(full, 2 * STAGE_BYTES);       // bytes of both CTAs land on the leader's barrier
         const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
-        const int kk = (kb0 + kb) * BK;
+        const int kk = (kb0 + kb) * BKE;
         if constexpr (!TN) {
           tma_load_2d_pair(base, &map_a_hi, full, kk, m0);
           tma_load_2d_pair(base + kABytes, &map_a_lo, full, kk, m0);
@@ -465,31 +519,37 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
           tma_load_2d_pair(base + 2 * kABytes + BH_BYTES, &map_b_lo, full, kk, n0 + (int)crank * BH);
         } else {
 #pragma unroll
-          for (int b = 0; b < kBM / 32; ++b) {
-            tma_load_2d_pair(base + b * BOX_BYTES, &map_a_hi, full, m0 + 32 * b, kk);
-            tma_load_2d_pair(base + kABytes + b * BOX_BYTES, &map_a_lo, full, m0 + 32 * b, kk);
+          for (int b = 0; b < kBM / BOXC; ++b) {
+            tma_load_2d_pair(base + b * BOX_BYTES, &map_a_hi, full, m0 + BOXC * b, kk);
+            tma_load_2d_pair(base + kABytes + b * BOX_BYTES, &map_a_lo, full, m0 + BOXC * b, kk);
           }
 #pragma unroll
-          for (int b = 0; b < BH / 32; ++b) {
-            tma_load_2d_pair(base + 2 * kABytes + b * BOX_BYTES, &map_b_hi, full, n0 + (int)crank * BH + 32 * b, kk);
-            tma_load_2d_pair(base + 2 * kABytes + BH_BYTES + b * BOX_BYTES, &map_b_lo, full, n0 + (int)crank * BH + 32 * b, kk);
+          for (int b = 0; b < BH / BOXC; ++b) {
+            tma_load_2d_pair(base + 2 * kABytes + b * BOX_BYTES, &map_b_hi, full, n0 + (int)crank * BH + BOXC * b, kk);
+            tma_load_2d_pair(base + 2 * kABytes + BH_BYTES + b * BOX_BYTES, &map_b_lo, full, n0 + (int)crank * BH + BOXC * b, kk);
           }
         }
+      }
       }
     }
   } else if (warp == 1) {
     if (leader && lane == 0) {   // ===== MMA issuer (leader CTA only) =====
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (TN ? ((1u << 15) | (1u << 16)) : 0u) |
+      const uint32_t idesc = (1u << 4) | (F16 ? 0u : ((2u << 7) | (2u << 10))) | (TN ? ((1u << 15) | (1u << 16)) : 0u) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * kBM) >> 4) << 24);       // M = 256 across the pair
-      for (int ch = 0; ch < n_chunks; ++ch) {
-        const int buf = ch & 1;
-        mbar_wait(tempty0 + 8 * buf, ((ch >> 1) & 1) ^ 1);
+      int gkb = 0, gch = 0;     // k-blocks / chunks consumed so far (ring and TMEM buffer positions)
+      for (int w = cluster_id; w < n_work; w += n_clusters) {
+      int m0, n0, kb0, nkb, z;
+      work_coords(w, m0, n0, kb0, nkb, z);
+      const int n_chunks = (nkb + kChunk - 1) / kChunk;
+      for (int ch = 0; ch < n_chunks; ++ch, ++gch) {
+        const int buf = gch & 1;
+        mbar_wait(tempty0 + 8 * buf, ((gch >> 1) & 1) ^ 1);
         tcgen05_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
         const int kb_end = min(nkb, (ch + 1) * kChunk);
-        for (int kb = ch * kChunk; kb < kb_end; ++kb) {
-          const int s = kb % STAGES;
-          const uint32_t ph = (kb / STAGES) & 1;
+        for (int kb = ch * kChunk; kb < kb_end; ++kb, ++gkb) {
+          const int s = gkb % STAGES;
+          const uint32_t ph = (gkb / STAGES) & 1;
           mbar_wait(full0 + 8 * s, ph);
           tcgen05_fence_after();
           const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
@@ -503,27 +563,35 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
           }
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {
-            const uint64_t adv = TN ? (uint64_t)((k * 1024) >> 4) : (uint64_t)(2 * k);
+            const uint64_t adv = TN ? (uint64_t)((k * (F16 ? 2048 : 1024)) >> 4) : (uint64_t)(2 * k);
             const uint32_t first = (kb == ch * kChunk && k == 0) ? 0u : 1u;
-            umma_tf32_pair(tacc, a_lo + adv, b_hi + adv, idesc, first);
-            umma_tf32_pair(tacc, a_hi + adv, b_lo + adv, idesc, 1u);
-            umma_tf32_pair(tacc, a_hi + adv, b_hi + adv, idesc, 1u);
+            umma_tf32_pair<F16>(tacc, a_lo + adv, b_hi + adv, idesc, first);
+            umma_tf32_pair<F16>(tacc, a_hi + adv, b_lo + adv, idesc, 1u);
+            umma_tf32_pair<F16>(tacc, a_hi + adv, b_hi + adv, idesc, 1u);
           }
           tcgen05_commit_pair(empty0 + 8 * s);                   // stage free in both CTAs
         }
         tcgen05_commit_pair(tfull0 + 8 * buf);                   // chunk accumulator complete in both CTAs
+      }
       }
     }
   } else {             // ===== epilogue warps (both CTAs): own TMEM lanes = own 128 rows =====
     const int q = warp & 3;
     const int hsel = (warp - 2) >> 2;
     const int n_chunks32 = hsel == 0 ? HALF / 32 : (BN - HALF) / 32;
+    const float inv_scale = (epi.scale_a ? 1.f / __ldg(epi.scale_a) : 1.f) * (epi.scale_b ? 1.f / __ldg(epi.scale_b) : 1.f);   // powers of two: exact
+    float vmax = 0.f;
+    int gch = 0;
+    for (int w = cluster_id; w < n_work; w += n_clusters) {
+    int m0, n0, kb0, nkb, z;
+    work_coords(w, m0, n0, kb0, nkb, z);
+    const int n_chunks = (nkb + kChunk - 1) / kChunk;
     float acc[HALF];
 #pragma unroll
     for (int c = 0; c < HALF; ++c) acc[c] = 0.f;
-    for (int ch = 0; ch < n_chunks; ++ch) {
-      const int buf = ch & 1;
-      mbar_wait(tfull0 + 8 * buf, (ch >> 1) & 1);
+    for (int ch = 0; ch < n_chunks; ++ch, ++gch) {
+      const int buf = gch & 1;
+      mbar_wait(tfull0 + 8 * buf, (gch >> 1) & 1);
       tcgen05_fence_after();
       const uint32_t tacc = tmem_base + (uint32_t)(buf * BN + hsel * HALF) + ((uint32_t)(q * 32) << 16);
 #pragma unroll
@@ -543,7 +611,7 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
     }
     const int row = m0 + q * 32 + lane;
     if (row < M) {
-      float* crow = C + (int64_t)blockIdx.z * split_stride + (int64_t)row * ldc + n0 + hsel * HALF;
+      float* crow = C + (int64_t)z * split_stride + (int64_t)row * ldc + n0 + hsel * HALF;
       uint32_t mw[HALF / 16];
       const bool masked = !TN && epi.mask != nullptr;
       if (masked) {
@@ -558,7 +626,7 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
       for (int j = 0; j < HALF / 4; ++j) {
         const int col = n0 + hsel * HALF + j * 4;
         if (j < n_chunks32 * 8 && col < n_store) {
-          float4 v = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+          float4 v = make_float4(acc[4 * j] * inv_scale, acc[4 * j + 1] * inv_scale, acc[4 * j + 2] * inv_scale, acc[4 * j + 3] * inv_scale);
           if (masked && col < epi.feat_cols) {
             uint32_t code = (mw[j >> 2] >> (8 * (j & 3))) & 0xFFu;
             if (!epi.has_keep) code |= 0xF0u;
@@ -568,8 +636,14 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
             v.w *= (code & 128u) ? ((code & 8u) ? epi.on : epi.neg) : 0.f;
           }
           *reinterpret_cast<float4*>(crow + j * 4) = v;
+          vmax = fmaxf(vmax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
         }
       }
+    }
+    }   // next work item
+    if (epi.amax_out) {      // warp-uniform branch
+      vmax = warp_max(vmax);
+      if (lane == 0 && vmax > 0.f) atomicMax(reinterpret_cast<unsigned int*>(epi.amax_out), __float_as_uint(vmax));   // non-negative floats order like uints
     }
   }
   tcgen05_fence_before();
@@ -608,6 +682,54 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, int64_t ldx, int 
   }
 }
 
+// ---- fp16 split path: per-tensor bounds and scales live in DEVICE scalars, so nothing here synchronises with the host ----
+__global__ void absmax_kernel(const float* __restrict__ x, int64_t ldx, int rows, int cols, float* __restrict__ out) {
+  float m = 0.f;
+  const int64_t total = (int64_t)rows * cols;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t / cols);
+    const int c = (int)(t - (int64_t)i * cols);
+    m = fmaxf(m, fabsf(__ldg(x + (int64_t)i * ldx + c)));
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(m));
+}
+
+// out = max(a ca, b cb)  (b may be null)
+__global__ void bound_max2_kernel(const float* a, float ca, const float* b, float cb, float* out) {
+  *out = fmaxf(*a * ca, b ? *b * cb : 0.f);
+}
+// bound of |dft| (see tx_bound_dft): g (c_direct + c_attn ft max(al, ar))
+__global__ void bound_dft_kernel(const float* g, const float* ft, const float* al, const float* ar, float c_direct, float c_attn, float* out) {
+  *out = *g * (c_direct + c_attn * *ft * fmaxf(*al, *ar));
+}
+
+__global__ void split_f16_kernel(const float* __restrict__ x, int64_t ldx, int rows, int cols, const float* __restrict__ bound,
+                                 __half* __restrict__ hi, __half* __restrict__ lo, int ldo, float* __restrict__ scale_out) {
+  const float scale = f16_split_scale(__ldg(bound));
+  if (scale_out && blockIdx.x == 0 && threadIdx.x == 0) *scale_out = scale;
+  const int vec_per_row = ldo >> 2;
+  const int64_t total = (int64_t)rows * vec_per_row;
+  const bool vec_in = (ldx & 3) == 0 && aligned16(x);
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t / vec_per_row);
+    const int c0 = (int)(t - (int64_t)i * vec_per_row) << 2;
+    float4 v;
+    if (vec_in && c0 + 3 < cols) {
+      v = __ldg(reinterpret_cast<const float4*>(x + (int64_t)i * ldx + c0));
+    } else {
+      v.x = c0 < cols ? __ldg(x + (int64_t)i * ldx + c0) : 0.f;
+      v.y = c0 + 1 < cols ? __ldg(x + (int64_t)i * ldx + c0 + 1) : 0.f;
+      v.z = c0 + 2 < cols ? __ldg(x + (int64_t)i * ldx + c0 + 2) : 0.f;
+      v.w = c0 + 3 < cols ? __ldg(x + (int64_t)i * ldx + c0 + 3) : 0.f;
+    }
+    uint2 h, l;
+    f16_split4(v, scale, h, l);
+    *reinterpret_cast<uint2*>(hi + (int64_t)i * ldo + c0) = h;
+    *reinterpret_cast<uint2*>(lo + (int64_t)i * ldo + c0) = l;
+  }
+}
+
 // ---- host: tensor maps through the driver entry point (no link-time dependency on libcuda) ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -625,8 +747,8 @@ static EncodeTiledFn encode_fn() {
 }
 
 // 2-D fp32 tensor [rows, cols] with row pitch ld (floats); box = [box_rows, 32 cols], 128-byte swizzle, zero OOB fill
-static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
-                    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B, int box_cols = 32) {
+static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B, int box_cols = 32, bool f16 = false) {
   if (rows <= 0 || cols <= 0) {
     set_error("gemm: empty operand");
     return TX_ERR_INVALID_ARGUMENT;
@@ -637,10 +759,10 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
     return TX_ERR_CUDA;
   }
   const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  const cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+  const cuuint64_t gstr[1] = {(cuuint64_t)ld * (f16 ? 2 : 4)};
   const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+  CUresult r = fn(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -651,41 +773,45 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
   return TX_OK;
 }
 
-template <int BN, int STAGES, bool TN, int BK = 32, int CL = 1>
-static int launch_gemm(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi, const float* b_lo, int64_t ldb,
+template <int BN, int STAGES, bool TN, int BK = 32, int CL = 1, bool F16 = false>
+static int launch_gemm(const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi, const void* b_lo, int64_t ldb,
                        float* c, int64_t ldc, int64_t split_stride, int64_t M, int64_t N, int64_t K, int splits, cudaStream_t st,
-                       const GemmEpilogue& epi = GemmEpilogue{nullptr, 0, 1, 0, 0, 0, 1.f, 1.f}) {
+                       const GemmEpilogue& epi = GemmEpilogue{nullptr, 0, 1, 0, 0, 0, 1.f, 1.f, nullptr, nullptr, nullptr}) {
   alignas(64) CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
   constexpr int kBK = BK;
   constexpr int kABytes = kBM * BK * 4;
   if (!TN) {   // A [M, K], B [N, K]: box = {BK k-cols, tile rows}; 128-byte (BK = 32) or 64-byte (BK = 16) swizzle
     const CUtensorMapSwizzle swk = BK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-    if ((rc = make_map(&ma_hi, a_hi, M, K, lda, kBM, swk, BK)) != TX_OK) return rc;
-    if ((rc = make_map(&ma_lo, a_lo, M, K, lda, kBM, swk, BK)) != TX_OK) return rc;
-    if ((rc = make_map(&mb_hi, b_hi, N, K, ldb, BN / CL, swk, BK)) != TX_OK) return rc;   // CL = 2: each CTA fetches half of the rows
-    if ((rc = make_map(&mb_lo, b_lo, N, K, ldb, BN / CL, swk, BK)) != TX_OK) return rc;
+    constexpr int BKE = F16 ? 2 * BK : BK;
+    if ((rc = make_map(&ma_hi, a_hi, M, K, lda, kBM, swk, BKE, F16)) != TX_OK) return rc;
+    if ((rc = make_map(&ma_lo, a_lo, M, K, lda, kBM, swk, BKE, F16)) != TX_OK) return rc;
+    if ((rc = make_map(&mb_hi, b_hi, N, K, ldb, BN / CL, swk, BKE, F16)) != TX_OK) return rc;   // CL = 2: each CTA fetches half of the rows
+    if ((rc = make_map(&mb_lo, b_lo, N, K, ldb, BN / CL, swk, BKE, F16)) != TX_OK) return rc;
   } else {     // A [K, M], B [K, N]: box = {32 m/n-cols, kBK reduction rows}
     // (debug knobs TAXO_TN_SWIZZLE / _LAYOUT / _LBO / _SBO override the layout constants below)
     const char* e_sw = getenv("TAXO_TN_SWIZZLE");
-    const CUtensorMapSwizzle sw = e_sw ? (CUtensorMapSwizzle)atoi(e_sw) : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-    if ((rc = make_map(&ma_hi, a_hi, K, M, lda, kBK, sw)) != TX_OK) return rc;
-    if ((rc = make_map(&ma_lo, a_lo, K, M, lda, kBK, sw)) != TX_OK) return rc;
-    if ((rc = make_map(&mb_hi, b_hi, K, N, ldb, kBK, sw)) != TX_OK) return rc;
-    if ((rc = make_map(&mb_lo, b_lo, K, N, ldb, kBK, sw)) != TX_OK) return rc;
+    // fp16: plain SWIZZLE_128B boxes of {64 cols, 64 reduction rows}; tf32: SWIZZLE_128B_ATOM_32B boxes of {32 cols, 32 rows}
+    const CUtensorMapSwizzle sw = F16 ? CU_TENSOR_MAP_SWIZZLE_128B : (e_sw ? (CUtensorMapSwizzle)atoi(e_sw) : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    constexpr int KROWS = F16 ? 2 * BK : BK, BOXC = F16 ? 64 : 32;
+    if ((rc = make_map(&ma_hi, a_hi, K, M, lda, KROWS, sw, BOXC, F16)) != TX_OK) return rc;
+    if ((rc = make_map(&ma_lo, a_lo, K, M, lda, KROWS, sw, BOXC, F16)) != TX_OK) return rc;
+    if ((rc = make_map(&mb_hi, b_hi, K, N, ldb, KROWS, sw, BOXC, F16)) != TX_OK) return rc;
+    if ((rc = make_map(&mb_lo, b_lo, K, N, ldb, KROWS, sw, BOXC, F16)) != TX_OK) return rc;
   }
   constexpr int STAGE_BYTES = 2 * kABytes + 2 * BN * kBK * 4;
   constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers + tmem slot */;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, STAGES, TN, BK, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, STAGES, TN, BK, CL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
     if (e != cudaSuccess) {
       set_error("gemm: cudaFuncSetAttribute(%zu B smem) failed: %s", SMEM, cudaGetErrorString(e));
       return TX_ERR_CUDA;
     }
     attr_done = true;
   }
-  const int kbt = (int)((K + kBK - 1) / kBK);
+  constexpr int kBKE = F16 ? 2 * BK : BK;      // reduction elements per k-block
+  const int kbt = (int)((K + kBKE - 1) / kBKE);
   const int kbs = (kbt + splits - 1) / splits;
   const int64_t n_store = ((N + 3) / 4) * 4;
   const unsigned m_tiles = (unsigned)((M + kBM - 1) / kBM);
@@ -693,11 +819,14 @@ static int launch_gemm(const float* a_hi, const float* a_lo, int64_t lda, const 
   const char* e_l = getenv("TAXO_TN_LAYOUT");
   const char* e_lbo = getenv("TAXO_TN_LBO");
   const char* e_sbo = getenv("TAXO_TN_SBO");
-  const uint64_t mn_bits = umma_desc_mn_bits(e_lbo ? (uint32_t)atoi(e_lbo) : (uint32_t)(kBK * 128), e_sbo ? (uint32_t)atoi(e_sbo) : 512u,
-                                             e_l ? (uint32_t)atoi(e_l) : 1u);
+  // MN-major descriptors: LBO = bytes between consecutive boxes (one box = k-rows x 128 B), SBO = bytes between k-row groups of the
+  // swizzle atom (tf32 / SWIZZLE_128B_BASE32B: 4 rows = 512 B; fp16 / SWIZZLE_128B: 8 rows = 1024 B)
+  const uint64_t mn_bits = F16 ? umma_desc_mn_bits((uint32_t)(kBKE * 128), 1024u, 2u)
+                               : umma_desc_mn_bits(e_lbo ? (uint32_t)atoi(e_lbo) : (uint32_t)(kBK * 128), e_sbo ? (uint32_t)atoi(e_sbo) : 512u,
+                                                   e_l ? (uint32_t)atoi(e_l) : 1u);
   if (CL == 1) {
-    gemm_tf32x3_kernel<BN, STAGES, TN, BK, CL><<<grid, kGemmThreads, SMEM, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, c, ldc, split_stride, (int)M,
-                                                                             (int)n_store, kbt, kbs, mn_bits, epi);
+    gemm_tf32x3_kernel<BN, STAGES, TN, BK, CL, F16><<<grid, kGemmThreads, SMEM, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, c, ldc, split_stride, (int)M,
+                                                                                  (int)n_store, kbt, kbs, mn_bits, epi);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
@@ -711,7 +840,7 @@ static int launch_gemm(const float* a_hi, const float* a_lo, int64_t lda, const 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<BN, STAGES, TN, BK, CL>, ma_hi, ma_lo, mb_hi, mb_lo, c, ldc, split_stride,
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<BN, STAGES, TN, BK, CL, F16>, ma_hi, ma_lo, mb_hi, mb_lo, c, ldc, split_stride,
                                        (int)M, (int)n_store, kbt, kbs, mn_bits, epi);
     if (e != cudaSuccess) {
       set_error("gemm: cluster launch failed: %s", cudaGetErrorString(e));
@@ -722,42 +851,55 @@ static int launch_gemm(const float* a_hi, const float* a_lo, int64_t lda, const 
   return TX_OK;
 }
 
-template <int BN, int STAGES, bool TN>
-static int launch_gemm_pair(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi, const float* b_lo, int64_t ldb,
+template <int BN, int STAGES, bool TN, bool F16 = false>
+static int launch_gemm_pair(const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi, const void* b_lo, int64_t ldb,
                             float* c, int64_t ldc, int64_t split_stride, int64_t M, int64_t N, int64_t K, int splits, cudaStream_t st,
-                            const GemmEpilogue& epi = GemmEpilogue{nullptr, 0, 1, 0, 0, 0, 1.f, 1.f}) {
+                            const GemmEpilogue& epi = GemmEpilogue{nullptr, 0, 1, 0, 0, 0, 1.f, 1.f, nullptr, nullptr, nullptr}) {
   alignas(64) CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
   constexpr int BK = 32;
+  constexpr int BKE = F16 ? 2 * BK : BK;
   if (!TN) {
-    if ((rc = make_map(&ma_hi, a_hi, M, K, lda, kBM)) != TX_OK) return rc;
-    if ((rc = make_map(&ma_lo, a_lo, M, K, lda, kBM)) != TX_OK) return rc;
-    if ((rc = make_map(&mb_hi, b_hi, N, K, ldb, BN / 2)) != TX_OK) return rc;
-    if ((rc = make_map(&mb_lo, b_lo, N, K, ldb, BN / 2)) != TX_OK) return rc;
+    const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
+    if ((rc = make_map(&ma_hi, a_hi, M, K, lda, kBM, sw, BKE, F16)) != TX_OK) return rc;
+    if ((rc = make_map(&ma_lo, a_lo, M, K, lda, kBM, sw, BKE, F16)) != TX_OK) return rc;
+    if ((rc = make_map(&mb_hi, b_hi, N, K, ldb, BN / 2, sw, BKE, F16)) != TX_OK) return rc;
+    if ((rc = make_map(&mb_lo, b_lo, N, K, ldb, BN / 2, sw, BKE, F16)) != TX_OK) return rc;
   } else {
-    const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-    if ((rc = make_map(&ma_hi, a_hi, K, M, lda, BK, sw)) != TX_OK) return rc;
-    if ((rc = make_map(&ma_lo, a_lo, K, M, lda, BK, sw)) != TX_OK) return rc;
-    if ((rc = make_map(&mb_hi, b_hi, K, N, ldb, BK, sw)) != TX_OK) return rc;
-    if ((rc = make_map(&mb_lo, b_lo, K, N, ldb, BK, sw)) != TX_OK) return rc;
+    const CUtensorMapSwizzle sw = F16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    constexpr int BOXC = F16 ? 64 : 32;
+    if ((rc = make_map(&ma_hi, a_hi, K, M, lda, BKE, sw, BOXC, F16)) != TX_OK) return rc;
+    if ((rc = make_map(&ma_lo, a_lo, K, M, lda, BKE, sw, BOXC, F16)) != TX_OK) return rc;
+    if ((rc = make_map(&mb_hi, b_hi, K, N, ldb, BKE, sw, BOXC, F16)) != TX_OK) return rc;
+    if ((rc = make_map(&mb_lo, b_lo, K, N, ldb, BKE, sw, BOXC, F16)) != TX_OK) return rc;
   }
   constexpr int STAGE_BYTES = 2 * kBM * BK * 4 + 2 * (BN / 2) * BK * 4;
   constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_pair_kernel<BN, STAGES, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_pair_kernel<BN, STAGES, TN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
     if (e != cudaSuccess) {
       set_error("gemm(pair): cudaFuncSetAttribute(%zu B smem) failed: %s", SMEM, cudaGetErrorString(e));
       return TX_ERR_CUDA;
     }
     attr_done = true;
   }
-  const int kbt = (int)((K + BK - 1) / BK);
+  const int kbt = (int)((K + BKE - 1) / BKE);
   const int kbs = (kbt + splits - 1) / splits;
   const int64_t n_store = ((N + 3) / 4) * 4;
   const unsigned m_tiles = (unsigned)((M + kBM - 1) / kBM);
-  dim3 grid(2u * (unsigned)((N + BN - 1) / BN), (m_tiles + 1) / 2, (unsigned)splits);   // a padded odd M tile is fully masked
-  const uint64_t mn_bits = umma_desc_mn_bits((uint32_t)(BK * 128), 512u, 1u);
+  const int n_tiles_n = (int)((N + BN - 1) / BN), n_m_pairs = (int)((m_tiles + 1) / 2);   // a padded odd M tile is fully masked
+  const int64_t n_work64 = (int64_t)n_tiles_n * n_m_pairs * splits;
+  if (n_work64 >= INT32_MAX) {
+    set_error("gemm(pair): too many tiles");
+    return TX_ERR_INVALID_ARGUMENT;
+  }
+  const int n_work = (int)n_work64;
+  static int persist = -1;     // TAXO_GEMM_PERSIST=0 -> one cluster per tile (the pre-persistent behaviour)
+  if (persist < 0) { const char* e_p = getenv("TAXO_GEMM_PERSIST"); persist = (e_p && atoi(e_p) == 0) ? 0 : 1; }
+  const int n_clusters = persist ? (n_work < kNumSms / 2 ? n_work : kNumSms / 2) : n_work;
+  dim3 grid(2u * (unsigned)n_clusters, 1, 1);
+  const uint64_t mn_bits = F16 ? umma_desc_mn_bits((uint32_t)(BKE * 128), 1024u, 2u) : umma_desc_mn_bits((uint32_t)(BK * 128), 512u, 1u);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(kGemmThreads);
@@ -770,8 +912,8 @@ static int launch_gemm_pair(const float* a_hi, const float* a_lo, int64_t lda, c
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tf32x3_pair_kernel<BN, STAGES, TN>, ma_hi, ma_lo, mb_hi, mb_lo, c, ldc, split_stride,
-                                     (int)M, (int)n_store, kbt, kbs, mn_bits, epi);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tf32x3_pair_kernel<BN, STAGES, TN, F16>, ma_hi, ma_lo, mb_hi, mb_lo, c, ldc, split_stride,
+                                     (int)M, (int)n_store, kbt, kbs, mn_bits, epi, n_tiles_n, n_m_pairs, n_work);
   if (e != cudaSuccess) {
     set_error("gemm(pair): cluster launch failed: %s", cudaGetErrorString(e));
     return TX_ERR_CUDA;
@@ -860,7 +1002,7 @@ int tx_gemm_nt_tf32x3_ex(const float* a_hi, const float* a_lo, int64_t lda, cons
   TX_REQUIRE(ldc % 4 == 0 && ldc >= n, "gemm: ldc must be a multiple of 4 and >= N");
   cudaStream_t st = (cudaStream_t)stream;
   TX_REQUIRE(ldc >= ((n + 3) / 4) * 4, "gemm: ldc must hold round4(N) columns");
-  GemmEpilogue epi{nullptr, 0, 1, 0, 0, 0, 1.f, 1.f};
+  GemmEpilogue epi{nullptr, 0, 1, 0, 0, 0, 1.f, 1.f, nullptr, nullptr, nullptr};
   if (e && e->act_mask) {
     TX_REQUIRE(e->heads > 0 && e->dim > 0 && e->dim % 4 == 0 && e->mask_stride % 16 == 0 && e->mask_stride >= e->heads * e->dim / 4 &&
                aligned16(e->act_mask), "gemm epilogue: bad mask geometry");
@@ -887,6 +1029,116 @@ int tx_gemm_nt_tf32x3_ex(const float* a_hi, const float* a_lo, int64_t lda, cons
   if (n > 128) return launch_gemm<256, 2, false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
   if (n > 64) return launch_gemm<128, 3, false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
   return launch_gemm<64, 4, false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// fp16-split (3 x kind::f16) GEMMs
+// ------------------------------------------------------------------------------------------------
+int tx_absmax(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* out, void* stream) {
+  TX_REQUIRE(out && rows >= 0 && cols >= 0 && rows < INT32_MAX && cols < INT32_MAX && (rows == 0 || cols == 0 || x), "absmax: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(out, 0, sizeof(float), st) != cudaSuccess) { set_error("absmax: memset failed"); return TX_ERR_CUDA; }
+  if (rows == 0 || cols == 0) return TX_OK;
+  const int64_t total = rows * cols;
+  const int grid = (int)((total + 1023) / 1024 < (int64_t)kNumSms * 8 ? (total + 1023) / 1024 : (int64_t)kNumSms * 8);
+  absmax_kernel<<<grid, 256, 0, st>>>(x, ldx, (int)rows, (int)cols, out);
+  TX_LAUNCH_CHECK("tx_absmax");
+  return TX_OK;
+}
+
+int tx_bound_max2(const float* a, float ca, const float* b, float cb, float* out, void* stream) {
+  TX_REQUIRE(a && out, "bound_max2: bad arguments");
+  bound_max2_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(a, ca, b, cb, out);
+  TX_LAUNCH_CHECK("tx_bound_max2");
+  return TX_OK;
+}
+
+int tx_bound_dft(const float* g_amax, const float* ft_amax, const float* attn_l_amax, const float* attn_r_amax, float c_direct,
+                 float c_attn, float* out, void* stream) {
+  TX_REQUIRE(g_amax && ft_amax && attn_l_amax && attn_r_amax && out, "bound_dft: bad arguments");
+  bound_dft_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(g_amax, ft_amax, attn_l_amax, attn_r_amax, c_direct, c_attn, out);
+  TX_LAUNCH_CHECK("tx_bound_dft");
+  return TX_OK;
+}
+
+int tx_split_f16(const float* x, int64_t ldx, int64_t rows, int64_t cols, const float* bound, void* hi, void* lo, int64_t ldo,
+                 float* scale_out, void* stream) {
+  TX_REQUIRE(ldo % 8 == 0 && ldo >= cols && aligned16(hi) && aligned16(lo), "split_f16: outputs need ld %% 8 == 0, ld >= cols, 16B alignment");
+  TX_REQUIRE(rows >= 0 && cols >= 0 && rows < INT32_MAX && ldo < INT32_MAX && bound, "split_f16: bad arguments");
+  if (rows == 0 || cols == 0) return TX_OK;
+  const int64_t total = rows * (ldo / 4);
+  const int grid = (int)((total + 255) / 256 < (int64_t)kNumSms * 16 ? (total + 255) / 256 : (int64_t)kNumSms * 16);
+  split_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, (int)rows, (int)cols, bound, (__half*)hi, (__half*)lo, (int)ldo, scale_out);
+  TX_LAUNCH_CHECK("tx_split_f16");
+  return TX_OK;
+}
+
+static int pick_bn_tn16(int64_t n) {     // MN-major fp16 tiles are made of 64-column boxes
+  if (n <= 64) return 64;
+  if (n <= 128) return 128;
+  const int64_t w256 = ((n + 255) / 256) * 256, w192 = ((n + 191) / 192) * 192;
+  return w192 * 10 < w256 * 8 ? 192 : 256;
+}
+
+int64_t tx_gemm_tn_f16_splits(int64_t m, int64_t n, int64_t r) {
+  const int64_t bn = pick_bn_tn16(n);
+  const int64_t tiles = ((m + kBM - 1) / kBM) * ((n + bn - 1) / bn);
+  int64_t s = kNumSms / (tiles > 0 ? tiles : 1);
+  const int64_t kbt = (r + 63) / 64;
+  if (s > kbt / 8) s = kbt / 8;          // keep at least 8 k-blocks per split
+  if (s > 32) s = 32;
+  return s < 1 ? 1 : s;
+}
+
+int tx_gemm_tn_f16x3(const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi, const void* b_lo, int64_t ldb,
+                     const float* scale_a, const float* scale_b, float* c_partial, int64_t ldc, int64_t split_stride, int64_t m,
+                     int64_t n, int64_t r, int64_t splits, void* stream) {
+  TX_REQUIRE(m > 0 && n > 0 && r > 0 && m < INT32_MAX && n < INT32_MAX && r < INT32_MAX, "gemm_tn_f16: bad shape");
+  TX_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && lda >= m && ldb >= n, "gemm_tn_f16: operand row pitch must be a multiple of 8 halves and >= M / N");
+  TX_REQUIRE(aligned16(a_hi) && aligned16(a_lo) && aligned16(b_hi) && aligned16(b_lo) && aligned16(c_partial), "gemm_tn_f16: 16-byte aligned pointers required");
+  TX_REQUIRE(ldc % 4 == 0 && ldc >= ((n + 3) / 4) * 4 && split_stride % 4 == 0 && split_stride >= m * ldc, "gemm_tn_f16: bad ldc / split_stride");
+  TX_REQUIRE(splits >= 1 && splits <= 65535, "gemm_tn_f16: bad split count");
+  cudaStream_t st = (cudaStream_t)stream;
+  GemmEpilogue epi{nullptr, 0, 1, 0, 0, 0, 1.f, 1.f, scale_a, scale_b, nullptr};
+  const int bn = pick_bn_tn16(n);
+  if (use_pair() && m > kBM && bn == 256)
+    return launch_gemm_pair<256, 3, true, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c_partial, ldc, split_stride, m, n, r, (int)splits, st, epi);
+  if (bn == 256) return launch_gemm<256, 2, true, 32, 1, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c_partial, ldc, split_stride, m, n, r, (int)splits, st, epi);
+  if (bn == 192) return launch_gemm<192, 2, true, 32, 1, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c_partial, ldc, split_stride, m, n, r, (int)splits, st, epi);
+  if (bn == 128) return launch_gemm<128, 3, true, 32, 1, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c_partial, ldc, split_stride, m, n, r, (int)splits, st, epi);
+  return launch_gemm<64, 4, true, 32, 1, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c_partial, ldc, split_stride, m, n, r, (int)splits, st, epi);
+}
+
+int tx_gemm_nt_f16x3(const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi, const void* b_lo, int64_t ldb,
+                     const float* scale_a, const float* scale_b, float* c, int64_t ldc, int64_t m, int64_t n, int64_t k,
+                     const tx_gemm_epilogue* e, float* amax_out, void* stream) {
+  TX_REQUIRE(m > 0 && n > 0 && k > 0 && m < INT32_MAX && n < INT32_MAX && k < INT32_MAX, "gemm_f16: bad shape %lld x %lld x %lld", (long long)m, (long long)n, (long long)k);
+  TX_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && lda >= k && ldb >= k, "gemm_f16: operand row pitch must be a multiple of 8 halves (16 B) and >= K");
+  TX_REQUIRE(aligned16(a_hi) && aligned16(a_lo) && aligned16(b_hi) && aligned16(b_lo) && aligned16(c), "gemm_f16: 16-byte aligned pointers required");
+  TX_REQUIRE(ldc % 4 == 0 && ldc >= ((n + 3) / 4) * 4, "gemm_f16: ldc must be a multiple of 4 and hold round4(N) columns");
+  cudaStream_t st = (cudaStream_t)stream;
+  GemmEpilogue epi{nullptr, 0, 1, 0, 0, 0, 1.f, 1.f, scale_a, scale_b, amax_out};
+  if (e && e->act_mask) {
+    TX_REQUIRE(e->heads > 0 && e->dim > 0 && e->dim % 4 == 0 && e->mask_stride % 16 == 0 && e->mask_stride >= e->heads * e->dim / 4 &&
+               aligned16(e->act_mask), "gemm_f16 epilogue: bad mask geometry");
+    TX_REQUIRE(e->col0 == 0, "gemm_f16 epilogue: a column offset is not supported with a fused mask");
+    TX_REQUIRE(e->p_drop >= 0.f && e->p_drop < 1.f, "gemm_f16 epilogue: p_drop must be in [0,1)");
+    epi.mask = e->act_mask; epi.heads = (int)e->heads; epi.dim = (int)e->dim; epi.stride = (int)e->mask_stride;
+    epi.feat_cols = (int)(e->heads * e->dim); epi.has_keep = e->has_keep_plane;
+    epi.on = 1.f / (1.f - e->p_drop); epi.neg = e->act_slope * epi.on;
+  }
+  if (amax_out && cudaMemsetAsync(amax_out, 0, sizeof(float), st) != cudaSuccess) { set_error("gemm_f16: memset failed"); return TX_ERR_CUDA; }
+  if (use_pair() && m > kBM && n > 128 && pick_bn(n) == 256)
+    return launch_gemm_pair<256, 3, false, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
+  if (use_cluster() && m > kBM && n > 128) {
+    if (pick_bn(n) == 160) return launch_gemm<160, 3, false, 32, 2, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
+    return launch_gemm<256, 2, false, 32, 2, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
+  }
+  if (n > 128 && pick_bn(n) == 160) return launch_gemm<160, 3, false, 32, 1, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
+  if (n > 128) return launch_gemm<256, 2, false, 32, 1, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
+  if (n > 64) return launch_gemm<128, 3, false, 32, 1, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
+  return launch_gemm<64, 4, false, 32, 1, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
 }
 
 }  // extern "C"

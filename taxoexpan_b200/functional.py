@@ -65,9 +65,14 @@ def use_fused(lib, heads: int, dim: int, mean_heads: int, st=None) -> bool:
     return FUSED_ENABLED and bool(lib.tx_gat_fused_supported(heads, dim, mean_heads))
 
 
-# dense projections: "tf32x3" = hand-written tcgen05 3xTF32 kernels of tx_gemm.cu (default; fp32-faithful),
-# "cublas" = torch.mm (cuBLAS fp32 SIMT, TF32 off) kept as the yardstick / cross-check
-GEMM_BACKEND = os.environ.get("TAXO_GEMM", "tf32x3")
+# dense projections: "f16x3" = hand-written tcgen05 kernels of tx_gemm.cu on fp16 hi/lo operand pairs with per-tensor power-of-two
+# scales (default: 22 significant bits per operand like 3xTF32, twice the tensor rate, half the operand bytes),
+# "tf32x3" = the same kernels on TF32 hi/lo pairs, "cublas" = torch.mm (cuBLAS fp32 SIMT, TF32 off) kept as the yardstick
+GEMM_BACKEND = os.environ.get("TAXO_GEMM", "f16x3")
+
+
+def _tc_backend() -> bool:
+    return GEMM_BACKEND in ("tf32x3", "f16x3")
 
 
 def split_tf32(x: torch.Tensor, cols: int = None):
@@ -113,11 +118,85 @@ def gemm_tn_ps(a_hi, a_lo, m: int, b_hi, b_lo, n: int) -> torch.Tensor:
     return out[:, :n]
 
 
+def round8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+class F16Pair:
+    """x * scale = hi + lo: the fp16 hi / lo parts [rows, round8(cols)] of an fp32 operand and its per-tensor power-of-two scale (a
+    1-element DEVICE tensor - never read on the host).  `amax` (optional) is a device bound of max|x|."""
+    __slots__ = ("hi", "lo", "scale", "cols")
+
+    def __init__(self, hi, lo, scale, cols):
+        self.hi, self.lo, self.scale, self.cols = hi, lo, scale, cols
+
+
+def absmax(x: torch.Tensor, cols: int = None) -> torch.Tensor:
+    """max |x[:, :cols]| as a 1-element device tensor (tx_absmax)."""
+    lib = _lib.load()
+    x = _rowmajor(x)
+    rows = x.shape[0]
+    cols = x.shape[1] if cols is None else cols
+    out = torch.empty(1, dtype=torch.float32, device=x.device)
+    check(lib.tx_absmax(ptr(x), x.stride(0) if rows > 1 else x.shape[1], rows, cols, ptr(out), current_stream()), "tx_absmax")
+    return out
+
+
+def split_f16(x: torch.Tensor, cols: int = None, bound: torch.Tensor = None) -> F16Pair:
+    """fp16 hi/lo split of x[:, :cols] (tx_split_f16).  `bound`: device upper bound of max|x| (default: measured with tx_absmax)."""
+    lib = _lib.load()
+    x = _rowmajor(x)
+    rows = x.shape[0]
+    cols = x.shape[1] if cols is None else cols
+    if bound is None:
+        bound = absmax(x, cols)
+    ldo = round8(cols)
+    hi = torch.empty((rows, ldo), dtype=torch.float16, device=x.device)
+    lo = torch.empty((rows, ldo), dtype=torch.float16, device=x.device)
+    scale = torch.empty(1, dtype=torch.float32, device=x.device)
+    check(lib.tx_split_f16(ptr(x), x.stride(0) if rows > 1 else x.shape[1], rows, cols, ptr(bound), ptr(hi), ptr(lo), ldo, ptr(scale),
+                           current_stream()), "tx_split_f16")
+    return F16Pair(hi, lo, scale, cols)
+
+
+def gemm_nt_f16(a: F16Pair, k: int, b: F16Pair, n: int, out: torch.Tensor = None, epi=None, want_amax: bool = False):
+    """C[:, :n] = A[:, :k] @ B[:n, :k]^T from fp16-split operands (tx_gemm_nt_f16x3).  Returns C, or (C, amax) with a device
+    scalar max|C| when want_amax."""
+    lib = _lib.load()
+    m = a.hi.shape[0]
+    if out is None:
+        out = torch.empty((m, round4(n)), dtype=torch.float32, device=a.hi.device)
+    ldc = out.stride(0) if m > 1 else out.shape[1]
+    amax = torch.zeros(1, dtype=torch.float32, device=a.hi.device) if want_amax else None
+    if m > 0:
+        check(lib.tx_gemm_nt_f16x3(ptr(a.hi), ptr(a.lo), a.hi.stride(0), ptr(b.hi), ptr(b.lo), b.hi.stride(0), ptr(a.scale), ptr(b.scale),
+                                   ptr(out), ldc, m, n, k, epi, ptr(amax), current_stream()), "tx_gemm_nt_f16x3")
+    res = out if out.shape[1] == n else out[:, :n]
+    return (res, amax) if want_amax else res
+
+
+def gemm_tn_f16(a: F16Pair, m: int, b: F16Pair, n: int) -> torch.Tensor:
+    """C[m, n] = sum_r A[r, :m]^T B[r, :n] from fp16-split operands; split-K + fixed-order reduce (tx_gemm_tn_f16x3)."""
+    lib = _lib.load()
+    r = a.hi.shape[0]
+    ldc = round4(n)
+    if r == 0:
+        return torch.zeros((m, n), dtype=torch.float32, device=a.hi.device)
+    splits = int(lib.tx_gemm_tn_f16_splits(m, n, r))
+    partial = torch.empty((splits, m, ldc), dtype=torch.float32, device=a.hi.device)
+    check(lib.tx_gemm_tn_f16x3(ptr(a.hi), ptr(a.lo), a.hi.stride(0), ptr(b.hi), ptr(b.lo), b.hi.stride(0), ptr(a.scale), ptr(b.scale),
+                               ptr(partial), ldc, m * ldc, m, n, r, splits, current_stream()), "tx_gemm_tn_f16x3")
+    out = partial[0] if splits == 1 else _reduce_partials(lib, partial, splits, m * ldc).view(m, ldc)
+    return out[:, :n]
+
+
 def gemm_nt(a: torch.Tensor, k: int, b: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
     """C = a[:, :k] @ b[:, :k]^T in fp32-faithful precision.  a: [M, >=k], b: [N, >=k] row-major.
     cublas backend: torch.mm (fp32 SIMT).  tf32x3 backend: split + tcgen05 3xTF32 kernel.
     `out` (optional) is a [M, ldc] buffer whose first N columns receive the result."""
     m, n = a.shape[0], b.shape[0]
+    if GEMM_BACKEND == "f16x3" and m > 0:
+        return gemm_nt_f16(split_f16(a, k), k, split_f16(b, k), n, out=out)
     if GEMM_BACKEND != "tf32x3" or m == 0:
         if out is None:
             return torch.mm(a[:, :k], b[:, :k].t())
@@ -128,21 +207,66 @@ def gemm_nt(a: torch.Tensor, k: int, b: torch.Tensor, out: torch.Tensor = None) 
     return gemm_nt_ps(a_hi, a_lo, k, b_hi, b_lo, n, out)
 
 
-def _layer_gemms_fwd(z, k, w_nk, z_lo=None):
-    """y = z[:, :k] @ w_nk[:, :k]^T.  Returns (y, saved) where `saved` is what backward needs of z: z itself (cublas) or its
-    TF32 split (tf32x3: the split is computed once and reused by the weight-gradient GEMM)."""
+def _layer_gemms_fwd(z, k, w_nk, z_lo=None, z16=None):
+    """y = z[:, :k] @ w_nk[:, :k]^T.  Returns (y, saved, y_amax) where `saved` is what backward needs of z: z itself (cublas), its
+    TF32 split (tf32x3) or its fp16 split (f16x3: (hi, lo, scale)) - the split is computed once and reused by the weight-gradient
+    GEMM - and y_amax is a device scalar max|y| (f16x3 only: it bounds the next tensors' fp16 scales)."""
+    if GEMM_BACKEND == "f16x3" and z.shape[0] > 0:
+        zp = z16 if z16 is not None else split_f16(z, k)      # z16: produced pre-split by the previous layer's epilogue
+        wp = split_f16(w_nk, k)
+        y, y_amax = gemm_nt_f16(zp, k, wp, w_nk.shape[0], want_amax=True)
+        return y, (zp.hi, zp.lo, zp.scale), y_amax
     if GEMM_BACKEND != "tf32x3" or z.shape[0] == 0:
-        return torch.mm(z[:, :k], w_nk[:, :k].t()), (z, None)
+        return torch.mm(z[:, :k], w_nk[:, :k].t()), (z, None, None), None
     if z_lo is None:
         z_hi, z_lo = split_tf32(z, k)
     else:
         z_hi = z                                      # produced pre-split by the previous layer's epilogue
     w_hi, w_lo = split_tf32(w_nk, k)
-    return gemm_nt_ps(z_hi, z_lo, k, w_hi, w_lo, w_nk.shape[0]), (z_hi, z_lo)
+    return gemm_nt_ps(z_hi, z_lo, k, w_hi, w_lo, w_nk.shape[0]), (z_hi, z_lo, None), None
 
 
-def _layer_gemms_bwd(dy, f, saved, w_kf, k, ldz, c0, need_w, need_z, in_link=None, dy_lo=None):
+def _dz_epilogue(in_link, c0a):
+    if FUSE_DZ_EPILOGUE and in_link is not None and in_link.mask is not None and c0a == 0:
+        return _lib.GemmEpilogue(act_mask=ptr(in_link.mask), heads=in_link.heads, dim=in_link.dim,
+                                 mask_stride=int(_lib.load().tx_gat_fused_mask_ld(in_link.heads, in_link.dim)),
+                                 col0=0, act_slope=in_link.act_slope, p_drop=in_link.p_drop,
+                                 has_keep_plane=1 if in_link.p_drop > 0.0 else 0)
+    return None
+
+
+def _layer_gemms_bwd_f16(dy, f, saved, w_kf, k, ldz, c0, need_w, need_z, in_link=None, dy16=None):
+    """f16x3 form of _layer_gemms_bwd: dy comes fp16-split from the fused backward kernel (dy16) or is split here."""
+    n = saved[0].shape[0]
+    dw = dz = None
+    zp = F16Pair(saved[0], saved[1], saved[2], k)
+    if dy16 is None:
+        with timed_region("split_dy"):
+            dy16 = split_f16(dy, f)
+    if need_w:
+        with timed_region("gemm_dw"):
+            dw = gemm_tn_f16(dy16, f, zp, k)
+    if need_z:
+        with timed_region("gemm_dz"):
+            c0a = (min(c0, k) // 8) * 8                   # fp16 rows: 16-byte aligned slices start at multiples of 8 columns
+            dz = torch.empty((n, ldz), dtype=torch.float32, device=zp.hi.device)
+            if k > c0a:
+                wp = split_f16(w_kf[c0a:k], f)
+                epi = _dz_epilogue(in_link, c0a)
+                _, dz_amax = gemm_nt_f16(dy16, f, wp, k - c0a, out=dz[:, c0a:], epi=epi, want_amax=True)
+                if in_link is not None:
+                    in_link.dz_amax = dz_amax             # bounds |g| of the layer below (its fused backward writes fp16-split dft)
+                    if epi is not None:
+                        in_link.applied = True
+            if ldz > k and round4(k) < ldz:
+                dz[:, round4(k):].zero_()
+    return dw, dz
+
+
+def _layer_gemms_bwd(dy, f, saved, w_kf, k, ldz, c0, need_w, need_z, in_link=None, dy_lo=None, dy16=None):
     """dW_fk = dy[:, :f]^T @ z[:, :k]  and  dz[:, c0a:k] = dy[:, :f] @ w_kf[c0a:k, :f]^T (see _gemm_dz)."""
+    if GEMM_BACKEND == "f16x3" and saved[0].shape[0] > 0:
+        return _layer_gemms_bwd_f16(dy, f, saved, w_kf, k, ldz, c0, need_w, need_z, in_link, dy16)
     n = dy.shape[0]
     dw = dz = None
     if GEMM_BACKEND != "tf32x3" or n == 0:
@@ -159,7 +283,7 @@ def _layer_gemms_bwd(dy, f, saved, w_kf, k, ldz, c0, need_w, need_z, in_link=Non
                 if ldz > k:
                     dz[:, k:].zero_()
         return dw, dz
-    z_hi, z_lo = saved
+    z_hi, z_lo = saved[0], saved[1]
     if dy_lo is not None:
         d_hi, d_lo = dy, dy_lo                        # written pre-split by the fused backward kernel
     else:
@@ -174,12 +298,7 @@ def _layer_gemms_bwd(dy, f, saved, w_kf, k, ldz, c0, need_w, need_z, in_link=Non
             dz = torch.empty((n, ldz), dtype=torch.float32, device=dy.device)
             if k > c0a:
                 w_hi, w_lo = split_tf32(w_kf[c0a:k], f)
-                epi = None
-                if FUSE_DZ_EPILOGUE and in_link is not None and in_link.mask is not None and c0a == 0:
-                    epi = _lib.GemmEpilogue(act_mask=ptr(in_link.mask), heads=in_link.heads, dim=in_link.dim,
-                                            mask_stride=int(_lib.load().tx_gat_fused_mask_ld(in_link.heads, in_link.dim)),
-                                            col0=0, act_slope=in_link.act_slope, p_drop=in_link.p_drop,
-                                            has_keep_plane=1 if in_link.p_drop > 0.0 else 0)
+                epi = _dz_epilogue(in_link, c0a)
                 gemm_nt_ps(d_hi, d_lo, f, w_hi, w_lo, k - c0a, out=dz[:, c0a:], epi=epi)
                 if epi is not None:
                     in_link.applied = True
@@ -274,12 +393,14 @@ class MaskLink:
     """Hand-shake between consecutive fused GAT layers: layer l-1's forward publishes the sign/keep bytes of its epilogue,
     layer l's backward applies their derivative inside its d(z) GEMM epilogue and flags it, so layer l-1's backward kernel
     reads d(z) as is (no per-load decode)."""
-    __slots__ = ("mask", "heads", "dim", "act_slope", "p_drop", "applied", "z_lo")
+    __slots__ = ("mask", "heads", "dim", "act_slope", "p_drop", "applied", "z_lo", "z16", "dz_amax")
 
     def __init__(self):
         self.mask = None
         self.applied = False
         self.z_lo = None      # TF32 "lo" part of the published z when the producer wrote z pre-split (z itself is then the "hi" part)
+        self.z16 = None       # F16Pair of the published z when the producer wrote it fp16-split (z itself is then never written)
+        self.dz_amax = None   # device scalar max|d(z)| published by the consumer layer's backward GEMM epilogue
 
 
 @dataclass
@@ -315,9 +436,11 @@ class GatLayer(Function):
         with torch.cuda.device(dev):
             stream = current_stream()
             Stats.tag = cfg.tag
+            f16 = GEMM_BACKEND == "f16x3"
             with timed_region("gemm_fwd"):
-                ft, zsaved = _layer_gemms_fwd(z, K, weight,               # ft = fc(h), model_zoo.py:83
-                                              cfg.in_link.z_lo if (cfg.in_link is not None and GEMM_BACKEND == "tf32x3") else None)
+                ft, zsaved, ft_amax = _layer_gemms_fwd(z, K, weight,      # ft = fc(h), model_zoo.py:83
+                                                       cfg.in_link.z_lo if (cfg.in_link is not None and GEMM_BACKEND == "tf32x3") else None,
+                                                       cfg.in_link.z16 if (cfg.in_link is not None and f16) else None)
             al = attn_l.reshape(-1).contiguous()
             ar = attn_r.reshape(-1).contiguous()
             alpha = torch.empty(st.e * H, **f32)
@@ -337,18 +460,37 @@ class GatLayer(Function):
             fused = use_fused(lib, H, D, 0 if cfg.hidden else 1, st)
             maskbits = None
             out_lo = None
+            out16 = None
             if FUSE_SPLIT and fused and cfg.hidden and cfg.out_link is not None and GEMM_BACKEND == "tf32x3":
                 out_lo = torch.empty_like(out)        # the epilogue writes the next layer's input already TF32-split
             if fused:
                 # ONE kernel: logits from the gathered rows, edge softmax, dropout, aggregation, next-layer epilogue
                 if cfg.hidden and (cfg.act_slope != 1.0 or cfg.p_next > 0.0):
                     maskbits = torch.empty(int(lib.tx_gat_fused_mask_words(n, H, D)), dtype=torch.int32, device=dev)
-                check(lib.tx_gat_fused_fwd(ptr(ft), F_, ptr(al), ptr(ar), ptr(st.in_ptr), ptr(st.in_src), ptr(st.in_eid), n, H, D,
-                                           cfg.neg_slope, cfg.p_attn, cfg.attn_seed, cfg.attn_stream, ptr(alpha), ptr(alpha_d),
-                                           ptr(elog), ptr(out), ldo, epi, ptr(maskbits), ptr(out_lo), stream), "tx_gat_fused_fwd")
+                if FUSE_SPLIT and f16 and cfg.hidden and cfg.out_link is not None and ft_amax is not None and n > 0:
+                    # the epilogue writes the next layer's input fp16-split (x * scale = hi + lo); `out` itself is never written.
+                    # |z_next| <= max|ft| / ((1 - p_attn)(1 - p_next)) (attention weights are convex), appended rows <= max|P| / (1 - p_next)
+                    ld16 = round8(F_ + pd)
+                    o_hi = torch.empty((n, ld16), dtype=torch.float16, device=dev)
+                    o_lo = torch.empty((n, ld16), dtype=torch.float16, device=dev)
+                    o_scale = torch.empty(1, **f32)
+                    bound = torch.empty(1, **f32)
+                    tab_amax = absmax(tab) if pd > 0 else None
+                    check(lib.tx_bound_max2(ptr(ft_amax), 1.0 / ((1.0 - cfg.p_attn) * (1.0 - cfg.p_next)), ptr(tab_amax),
+                                            1.0 / (1.0 - cfg.p_next), ptr(bound), stream), "tx_bound_max2")
+                    check(lib.tx_gat_fused_fwd_f16(ptr(ft), F_, ptr(al), ptr(ar), ptr(st.in_ptr), ptr(st.in_src), ptr(st.in_eid), n, H, D,
+                                                   cfg.neg_slope, cfg.p_attn, cfg.attn_seed, cfg.attn_stream, ptr(alpha), ptr(alpha_d),
+                                                   ptr(elog), ldo, epi, ptr(maskbits), ptr(o_hi), ptr(o_lo), ld16, ptr(bound),
+                                                   ptr(o_scale), stream), "tx_gat_fused_fwd")
+                    out16 = F16Pair(o_hi, o_lo, o_scale, F_ + pd)
+                else:
+                    check(lib.tx_gat_fused_fwd(ptr(ft), F_, ptr(al), ptr(ar), ptr(st.in_ptr), ptr(st.in_src), ptr(st.in_eid), n, H, D,
+                                               cfg.neg_slope, cfg.p_attn, cfg.attn_seed, cfg.attn_stream, ptr(alpha), ptr(alpha_d),
+                                               ptr(elog), ptr(out), ldo, epi, ptr(maskbits), ptr(out_lo), stream), "tx_gat_fused_fwd")
                 if cfg.out_link is not None:
                     lk = cfg.out_link
                     lk.z_lo = out_lo
+                    lk.z16 = out16
                     if maskbits is not None:
                         lk.mask, lk.heads, lk.dim, lk.act_slope, lk.p_drop, lk.applied = maskbits, H, D, cfg.act_slope, cfg.p_next, False
             else:
@@ -363,7 +505,7 @@ class GatLayer(Function):
         ctx.st, ctx.cfg, ctx.pd = st, cfg, pd
         ctx.vocab = 0 if next_pos_table is None else int(next_pos_table.shape[0])
         ctx.save_for_backward(zsaved[0], zsaved[1], weight, al, ar, ft, alpha, alpha_d, elog,
-                              out if (cfg.hidden and not fused) else None, pos32)
+                              out if (cfg.hidden and not fused) else None, pos32, zsaved[2], ft_amax)
         ctx.attn_shape = attn_l.shape
         ctx.zshape = tuple(z.shape)
         return out
@@ -371,7 +513,7 @@ class GatLayer(Function):
     @staticmethod
     def backward(ctx, dout):
         lib = _lib.load()
-        z0, z1, weight, al, ar, ft, alpha, alpha_d, elog, out, pos32 = ctx.saved_tensors
+        z0, z1, weight, al, ar, ft, alpha, alpha_d, elog, out, pos32, z_scale, ft_amax = ctx.saved_tensors
         st, cfg, pd = ctx.st, ctx.cfg, ctx.pd
         n, ldz = ctx.zshape
         H, D, K = cfg.heads, cfg.dim, cfg.k
@@ -387,6 +529,7 @@ class GatLayer(Function):
             need_tab = cfg.hidden and ctx.needs_input_grad[4] and pd > 0
             nb = int(lib.tx_row_blocks(n))
             dft = torch.empty((n, F_), **f32)
+            dft16 = None
             ds = torch.empty(st.e * H, **f32)
             da2 = torch.empty(n * H, **f32)
             if ctx.fused:
@@ -404,11 +547,33 @@ class GatLayer(Function):
                     tiles = st.bwd_tiles(D)
                     nbf = int(lib.tx_gat_fused_bwd_staged_blocks(n, H, D))
                     partial = torch.empty(nbf * 2 * F_, **f32)
+                    d_hi = d_lo = d_scale = bound = None
+                    ld16 = round8(F_)
+                    if FUSE_SPLIT and GEMM_BACKEND == "f16x3" and ft_amax is not None and n > 0:
+                        # dft goes out fp16-split.  Its scale needs an upper bound of |dft| BEFORE the kernel runs:
+                        #   |sum_i alpha~_ij g_i| <= outdeg max|g| / (1 - p_attn),  |d alpha~| = |<g_i, ft_j>| <= D max|g| max|ft|,
+                        #   |ds| <= 2 |d alpha~| / (1 - p_attn),  |da1_j| <= outdeg |ds|,  |da2_i| <= |ds|
+                        g_amax = cfg.out_link.dz_amax if (cfg.out_link is not None and cfg.out_link.dz_amax is not None and pre) \
+                            else absmax(dout, F_ if cfg.hidden else D)
+                        al_amax, ar_amax = absmax(al.view(1, -1)), absmax(ar.view(1, -1))
+                        deg = max(int(st.max_out_deg), 1)
+                        slope = max(1.0, abs(cfg.neg_slope))
+                        bound = torch.empty(1, **f32)
+                        check(lib.tx_bound_dft(ptr(g_amax), ptr(ft_amax), ptr(al_amax), ptr(ar_amax), g_scale * deg / (1.0 - cfg.p_attn),
+                                               g_scale * 2.0 * (deg + 1) * D * slope / (1.0 - cfg.p_attn), ptr(bound), stream), "tx_bound_dft")
+                        d_hi = torch.empty((n, ld16), dtype=torch.float16, device=dev)
+                        d_lo = torch.empty((n, ld16), dtype=torch.float16, device=dev)
+                        if ld16 > F_:
+                            d_hi[:, F_:].zero_()
+                            d_lo[:, F_:].zero_()
+                        d_scale = torch.empty(1, **f32)
+                        dft16 = F16Pair(d_hi, d_lo, d_scale, F_)
                     check(lib.tx_gat_fused_bwd_staged(ptr(dout), ldg, g_head_stride, g_scale, ptr(ft), F_, ptr(alpha), ptr(alpha_d),
                                                       ptr(elog), ptr(al), ptr(ar), ptr(st.in_ptr), ptr(st.in_src), ptr(st.in_eid),
                                                       ptr(st.out_ptr), ptr(st.out_dst), ptr(st.out_slot), ptr(tiles), n, H, D,
                                                       cfg.neg_slope, cfg.p_attn, cfg.attn_seed, cfg.attn_stream, ptr(ds), ptr(da2),
-                                                      ptr(dft), F_, ptr(dft_lo), ptr(partial), stream), "tx_gat_fused_bwd_staged")
+                                                      ptr(dft), F_, ptr(dft_lo), ptr(d_hi), ptr(d_lo), ld16, ptr(bound), ptr(d_scale),
+                                                      ptr(partial), stream), "tx_gat_fused_bwd_staged")
                 else:
                     nbf = int(lib.tx_gat_fused_bwd_blocks(n, H))
                     partial = torch.empty(nbf * 2 * F_, **f32)
@@ -452,8 +617,8 @@ class GatLayer(Function):
                           "tx_gat_attn_grad_partials")
                     both = _reduce_partials(lib, partial, nb, 2 * F_)
                     dal, dar = both[:F_].view(ctx.attn_shape), both[F_:].view(ctx.attn_shape)
-            dw, dz = _layer_gemms_bwd(dft, F_, (z0, z1), weight.t(), K, ldz, cfg.dz_from, ctx.needs_input_grad[1],
-                                      ctx.needs_input_grad[0], cfg.in_link, dft_lo)
+            dw, dz = _layer_gemms_bwd(dft, F_, (z0, z1, z_scale), weight.t(), K, ldz, cfg.dz_from, ctx.needs_input_grad[1],
+                                      ctx.needs_input_grad[0], cfg.in_link, dft_lo, dft16)
         return dz, dw, dal, dar, dtab, None, None, None
 
 
@@ -486,7 +651,7 @@ class GcnLayer(Function):
             stream = current_stream()
             Stats.tag = cfg.tag
             with timed_region("gemm_fwd"):
-                y, zsaved = _layer_gemms_fwd(z, K, weight.t())             # torch.mm(h, W), model_zoo.py:37
+                y, zsaved, _ = _layer_gemms_fwd(z, K, weight.t())          # torch.mm(h, W), model_zoo.py:37
             norm = st.gcn_norm()
             pd = 0 if next_pos_table is None else int(next_pos_table.shape[1])
             tab = None if next_pos_table is None else next_pos_table.contiguous()
@@ -501,14 +666,14 @@ class GcnLayer(Function):
         ctx.st, ctx.cfg, ctx.pd = st, cfg, pd
         ctx.vocab = 0 if next_pos_table is None else int(next_pos_table.shape[0])
         ctx.has_bias = bias is not None
-        ctx.save_for_backward(zsaved[0], zsaved[1], weight, out if cfg.hidden else None, pos32, norm)
+        ctx.save_for_backward(zsaved[0], zsaved[1], weight, out if cfg.hidden else None, pos32, norm, zsaved[2])
         ctx.zshape = tuple(z.shape)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         lib = _lib.load()
-        z0, z1, weight, out, pos32, norm = ctx.saved_tensors
+        z0, z1, weight, out, pos32, norm, z_scale = ctx.saved_tensors
         st, cfg, pd = ctx.st, ctx.cfg, ctx.pd
         n, ldz = ctx.zshape
         D, K = cfg.dim, cfg.k
@@ -540,7 +705,7 @@ class GcnLayer(Function):
             dy = torch.empty((n, D), **f32)
             check(lib.tx_gcn_aggregate_bwd(ptr(dout), ldg, ptr(norm), ptr(st.out_ptr), ptr(st.out_dst), n, D, ptr(dy), D, stream),
                   "tx_gcn_aggregate_bwd")
-            dwt, dz = _layer_gemms_bwd(dy, D, (z0, z1), weight, K, ldz, cfg.dz_from, ctx.needs_input_grad[1],
+            dwt, dz = _layer_gemms_bwd(dy, D, (z0, z1, z_scale), weight, K, ldz, cfg.dz_from, ctx.needs_input_grad[1],
                                        ctx.needs_input_grad[0])
             dw = None if dwt is None else dwt.t()                         # weight is [K, D]
         return dz, dw, db, dtab, None, None, None

@@ -26,12 +26,13 @@ class GraphStructure:
     """Device-resident structure of one batched graph (all int32)."""
 
     __slots__ = ("device", "n", "e", "g", "in_ptr", "in_src", "in_eid", "out_ptr", "out_dst", "out_slot", "node_off",
-                 "pos", "src", "dst", "max_nodes", "_norm", "is_star", "_bwd_tiles")
+                 "pos", "src", "dst", "max_nodes", "max_out_deg", "_norm", "is_star", "_bwd_tiles")
 
     def __init__(self, device):
         self.device = device
         self._norm = None
         self._bwd_tiles = {}
+        self.max_out_deg = 0       # host-side upper bound of the largest out-degree (bounds |dft| for the fp16-split GEMM operands)
         self.pos = None
         self.src = self.dst = None
         self.is_star = False
@@ -170,6 +171,7 @@ class DGLGraph:
         if st is None:
             st = _build_structure_from_edges(self._src, self._dst, self._n, self.node_offsets(), device)
             st.max_nodes = max(self.batch_num_nodes) if self.batch_num_nodes else 0
+            st.max_out_deg = int(torch.bincount(self._src.reshape(-1).to(torch.int64)).max()) if self._src.numel() else 0
             self._structure[device] = st
         return st
 
@@ -293,6 +295,7 @@ class EgonetBatch(DGLGraph):
         st = GraphStructure(device)
         st.n, st.e, st.g = self._n, self._e, self._g
         st.max_nodes = self._max_nodes
+        st.max_out_deg = self._max_nodes          # the anchor: every sibling + its self-loop (<= graph size)
         st.is_star = True
         g = self._g
         with torch.cuda.device(device):

@@ -80,3 +80,57 @@ def test_split_is_exact_to_22_bits():
     rel = ((hi[:, :301] + lo[:, :301] - x).abs() / x.abs().clamp_min(1e-30)).max()
     assert float(rel) < 2.0 ** -21
     assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0 and int((lo.view(torch.int32) & 0x1FFF).abs().max()) == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# fp16-split (3 x kind::f16) GEMMs
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m,n,k", [(128, 64, 32), (128, 256, 64), (300, 500, 2050), (1000, 2000, 300), (257, 50, 2000),
+                                   (4099, 2052, 500), (64, 8, 40), (129, 129, 33), (37039, 500, 2050)])
+def test_f16x3_gemm_matches_fp64(m, n, k):
+    dev = torch.device("cuda", 0)
+    a, b = _case(m, n, k, seed=m + n + k)
+    a = a * 37.0                       # not in fp16's comfortable range on purpose: the per-tensor scale takes care of it
+    b = b * 1e-3
+    ref = a.double() @ b.double().t()
+    pa, pb = txf.split_f16(a.to(dev)), txf.split_f16(b.to(dev))
+    got, amax = txf.gemm_nt_f16(pa, k, pb, n, want_amax=True)
+    got = got.cpu().double()
+    assert got.shape == (m, n)
+    cublas = (a.to(dev) @ b.to(dev).t()).cpu().double()
+    err, err_cublas, scale = float((got - ref).abs().max()), float((cublas - ref).abs().max()), float(ref.abs().max())
+    print(f"[f16 {m}x{n}x{k}] max|err| f16x3 {err:.3e}  cublas-fp32 {err_cublas:.3e}  max|ref| {scale:.3e}")
+    assert err <= max(3.0 * err_cublas, 1e-6 * scale), (err, err_cublas)
+    assert abs(float(amax.cpu()) - float(got.abs().max())) <= 1e-6 * scale      # fused max|C|
+
+
+@pytest.mark.parametrize("r,m,n", [(256, 128, 64), (1000, 500, 2050), (4099, 2000, 300), (37039, 500, 2050), (37039, 2000, 300),
+                                   (77, 40, 12), (8192, 600, 350), (1099, 2000, 300), (1099, 500, 2050), (1100, 128, 64), (2297, 200, 130)])
+def test_f16x3_weight_gradient_gemm_matches_fp64(r, m, n):
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(r + m + n)
+    a = torch.randn(r, m, generator=g) / np.sqrt(r) * 1e-4        # gradient-like magnitudes
+    b = torch.nn.functional.normalize(torch.randn(r, n, generator=g), dim=1)
+    ref = a.double().t() @ b.double()
+    pa, pb = txf.split_f16(a.to(dev)), txf.split_f16(b.to(dev))
+    got = txf.gemm_tn_f16(pa, m, pb, n).cpu().double()
+    assert got.shape == (m, n)
+    cublas = (a.to(dev).t() @ b.to(dev)).cpu().double()
+    err, err_cublas, scale = float((got - ref).abs().max()), float((cublas - ref).abs().max()), float(ref.abs().max())
+    print(f"[f16 TN {r}: {m}x{n}] max|err| f16x3 {err:.3e}  cublas-fp32 {err_cublas:.3e}  max|ref| {scale:.3e}")
+    assert err <= max(3.0 * err_cublas, 1e-6 * scale), (err, err_cublas)
+    got2 = txf.gemm_tn_f16(pa, m, pb, n).cpu().double()
+    assert torch.equal(got, got2)
+
+
+def test_f16_split_is_exact_to_22_bits_of_the_maximum():
+    dev = torch.device("cuda", 0)
+    x = torch.randn(257, 301, device=dev) * 1e-5
+    x[3, 7] = 2.5e-3                       # an outlier sets the scale
+    p = txf.split_f16(x)
+    assert p.hi.shape == (257, 304) and float(p.hi[:, 301:].float().abs().max()) == 0.0
+    s = float(p.scale.cpu())
+    assert 2.0 ** 12 < 2.5e-3 * s <= 2.0 ** 13 and np.log2(s) == round(np.log2(s))
+    back = (p.hi[:, :301].double() + p.lo[:, :301].double()) / s
+    err = float((back - x.double()).abs().max())
+    assert err <= 2.0 ** -22 * 2.5e-3
