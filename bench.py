@@ -243,7 +243,10 @@ def run_b200(args, rank, world, local_rank):
 
     e2e_state = {"next": None, "loss": None}
 
+    host_t = {"prefetch": 0.0, "fwd_bwd": 0.0, "item": 0.0, "n": 0}
+
     def step_e2e(i):
+        t0 = time.perf_counter()
         if e2e_state["next"] is None:
             e2e_state["next"] = prefetch(i)
         g, x, qf, ev = e2e_state["next"]
@@ -251,10 +254,14 @@ def run_b200(args, rank, world, local_rank):
         main_stream.wait_event(ev)
         for t in (x, qf, g._staged):
             t.record_stream(main_stream)
+        t1 = time.perf_counter()
         prev = e2e_state["loss"]
         e2e_state["loss"] = fwd_bwd(g, x, qf)
+        t2 = time.perf_counter()
         if prev is not None:
             prev.item()                                          # D2H read of the previous step's result (keeps the CPU one step ahead)
+        t3 = time.perf_counter()
+        host_t["prefetch"] += t1 - t0; host_t["fwd_bwd"] += t2 - t1; host_t["item"] += t3 - t2; host_t["n"] += 1
 
     def e2e_flush():
         if e2e_state["loss"] is not None:
@@ -299,7 +306,9 @@ def run_b200(args, rank, world, local_rank):
     for i in range(3):
         step_e2e(i)
     e2e_flush()
+    host_t.update(prefetch=0.0, fwd_bwd=0.0, item=0.0, n=0)
     e2e_ms, _, _ = timed(step_e2e, args.steps, flush=e2e_flush)
+    e2e_host = {k: round(v / max(host_t["n"], 1) * 1e3, 4) for k, v in host_t.items() if k != "n"}   # host ms per step by phase
     clocks = sampler.stop() if rank == 0 else None
 
     # totals over ranks
@@ -385,7 +394,7 @@ def run_b200(args, rank, world, local_rank):
                    "dense": {"f16x3": "tcgen05 kind::f16 on fp16 hi/lo operand pairs, 3 MMAs per product (tx_gemm.cu), fp32-faithful",
                              "tf32x3": "tcgen05 3xTF32 (tx_gemm.cu), fp32-faithful"}.get(txf.GEMM_BACKEND, "torch.mm (cuBLAS fp32, TF32 off)")},
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": x_bytes, "d2h_bytes_per_step": 4,
-                "ms_per_step": round(e2e_ms / args.steps, 4)},
+                "ms_per_step": round(e2e_ms / args.steps, 4), "host_ms_per_step": e2e_host},
         "gpu_launches": launches,
         "host_enqueue_ms_per_step": round(host_enqueue_ms, 4),
         "clocks": clocks,

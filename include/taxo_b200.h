@@ -314,14 +314,20 @@ int tx_dropout_keep_mask(uint64_t seed, uint32_t stream_id, int64_t first_index,
  * Nothing here synchronises with the host.  Row pitches of the fp16 arrays are multiples of 8 elements (16 bytes).
  * ------------------------------------------------------------------------------------------------ */
 int tx_absmax(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* out, void* stream);  /* *out = max |x[i, c]| */
-int tx_bound_max2(const float* a, float ca, const float* b, float cb, float* out, void* stream);  /* *out = max(*a ca, *b cb); b may be NULL */
-/* *out = *g_amax (c_direct + c_attn *ft_amax max(*attn_l_amax, *attn_r_amax)): bound of |dft| written by the fused GAT backward
- * (dft_j = sum_i alpha~_ij g_i + da1_j attn_l + da2_j attn_r with |d alpha~| <= dim max|g| max|ft|). */
-int tx_bound_dft(const float* g_amax, const float* ft_amax, const float* attn_l_amax, const float* attn_r_amax, float c_direct,
+/* *out = max(*a ca, max|b[0..b_len)| cb); b (a small parameter table, reduced by the same launch) may be NULL */
+int tx_bound_max2(const float* a, float ca, const float* b, int64_t b_len, float cb, float* out, void* stream);
+/* *out = *g_amax (c_direct + c_attn *ft_amax max(max|attn_l|, max|attn_r|)) over attn_l/attn_r[0..attn_len): bound of |dft| written
+ * by the fused GAT backward (dft_j = sum_i alpha~_ij g_i + da1_j attn_l + da2_j attn_r with |d alpha~| <= dim max|g| max|ft|). */
+int tx_bound_dft(const float* g_amax, const float* ft_amax, const float* attn_l, const float* attn_r, int64_t attn_len, float c_direct,
                  float c_attn, float* out, void* stream);
 /* hi, lo: fp16 [rows, ldo] (columns >= cols zero); *scale_out (optional) = the scale derived from *bound. */
 int tx_split_f16(const float* x, int64_t ldx, int64_t rows, int64_t cols, const float* bound, void* hi, void* lo, int64_t ldo,
                  float* scale_out, void* stream);
+/* One launch for a weight matrix w [rows, cols]: max|w|, then the split both row-major (hi, lo: [rows, ld]) and transposed
+ * (hi_t, lo_t: [cols, ld_t]) with the same scale -- the forward projection and the input-gradient GEMM read the same weights in the
+ * two orientations (model_zoo.py:83 and its autograd).  scratch2: 2 device floats of workspace. */
+int tx_split_f16_weight(const float* w, int64_t ldw, int64_t rows, int64_t cols, void* hi, void* lo, int64_t ld, void* hi_t, void* lo_t,
+                        int64_t ld_t, float* scratch2, float* scale_out, void* stream);
 /* C[m, n] = sum_k A[m, k] B[n, k] / (scale_a scale_b); optional fused mask epilogue (as tx_gemm_nt_tf32x3_ex) and optional
  * *amax_out = max |C| (device float, atomically maximised; zeroed by the call). */
 int tx_gemm_nt_f16x3(const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi, const void* b_lo, int64_t ldb,

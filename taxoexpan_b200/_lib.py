@@ -94,9 +94,10 @@ _SIGNATURES = {
     "tx_gemm_tn_splits": [I64, I64, I64],
     "tx_gemm_tn_tf32x3": [P, P, I64, P, P, I64, P, I64, I64, I64, I64, I64, I64, P],
     "tx_absmax": [P, I64, I64, I64, P, P],
-    "tx_bound_max2": [P, F32, P, F32, P, P],
-    "tx_bound_dft": [P, P, P, P, F32, F32, P, P],
+    "tx_bound_max2": [P, F32, P, I64, F32, P, P],
+    "tx_bound_dft": [P, P, P, P, I64, F32, F32, P, P],
     "tx_split_f16": [P, I64, I64, I64, P, P, P, I64, P, P],
+    "tx_split_f16_weight": [P, I64, I64, I64, P, P, I64, P, P, I64, P, P, P],
     "tx_gemm_nt_f16x3": [P, P, I64, P, P, I64, P, P, P, I64, I64, I64, I64, POINTER(GemmEpilogue), P, P],
     "tx_gemm_tn_f16_splits": [I64, I64, I64],
     "tx_gemm_tn_f16x3": [P, P, I64, P, P, I64, P, P, P, I64, I64, I64, I64, I64, I64, P],
@@ -214,6 +215,16 @@ def ptr(t):
     return None if t is None else c_void_p(t.data_ptr())
 
 
+_raw_stream = None
+
+
 def current_stream():
+    """cudaStream_t of torch's current stream on the current device (the raw-handle query: ~0.3 us instead of ~15 us for
+    torch.cuda.current_stream().cuda_stream, which was a quarter of the host time of a training step)."""
+    global _raw_stream
     import torch
+    if _raw_stream is None:
+        _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", False)
+    if _raw_stream:
+        return c_void_p(_raw_stream(torch.cuda.current_device()))
     return c_void_p(torch.cuda.current_stream().cuda_stream)

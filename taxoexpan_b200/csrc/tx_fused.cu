@@ -570,24 +570,39 @@ __global__ void __launch_bounds__(256, TX_BWD_MIN_BLOCKS) gat_fused_bwd_kernel(c
 }
 
 // d(P_next) partials only: dpos_partial[b, r, :] = sum_{i in block b, pos_i = r} dz[i, col0 : col0+pd] * keep/(1-p)
-__global__ void __launch_bounds__(128) pos_grad_partials_kernel(const float* __restrict__ dz, int64_t ldz, int col0,
+// 256 threads = 4 row groups x 64 columns; the row groups are summed in a fixed order (deterministic)
+__global__ void __launch_bounds__(256) pos_grad_partials_kernel(const float* __restrict__ dz, int64_t ldz, int col0,
                                                                 const int32_t* __restrict__ pos, int n, int pd, int vocab,
                                                                 float inv_keep, uint32_t thr, uint64_t seed, uint32_t stream_id,
                                                                 float* __restrict__ partial) {
+  __shared__ float s_acc[3][kMaxVocab][64];
   const int r0 = blockIdx.x * kRowsPerBlock;
   const int r1 = min(n, r0 + kRowsPerBlock);
-  for (int c = threadIdx.x; c < pd; c += blockDim.x) {
+  const int cl = threadIdx.x & 63, rg = threadIdx.x >> 6;
+  for (int cb = 0; cb < pd; cb += 64) {
+    const int c = cb + cl;
     float acc[kMaxVocab];
 #pragma unroll
     for (int v = 0; v < kMaxVocab; ++v) acc[v] = 0.f;
-    for (int i = r0; i < r1; ++i) {
-      float g = __ldg(dz + (int64_t)i * ldz + col0 + c);
-      if (thr) g = drop_keep1(seed, stream_id, (uint64_t)((int64_t)i * ldz + col0 + c), thr) ? g * inv_keep : 0.f;
-      const int r = __ldg(pos + i);
+    if (c < pd) {
+      for (int i = r0 + rg; i < r1; i += 4) {
+        float g = __ldg(dz + (int64_t)i * ldz + col0 + c);
+        if (thr) g = drop_keep1(seed, stream_id, (uint64_t)((int64_t)i * ldz + col0 + c), thr) ? g * inv_keep : 0.f;
+        const int r = __ldg(pos + i);
 #pragma unroll
-      for (int v = 0; v < kMaxVocab; ++v) acc[v] += (r == v) ? g : 0.f;
+        for (int v = 0; v < kMaxVocab; ++v) acc[v] += (r == v) ? g : 0.f;
+      }
     }
-    for (int v = 0; v < vocab; ++v) partial[((int64_t)blockIdx.x * vocab + v) * pd + c] = acc[v];
+    if (rg > 0) {
+#pragma unroll
+      for (int v = 0; v < kMaxVocab; ++v) s_acc[rg - 1][v][cl] = acc[v];
+    }
+    __syncthreads();
+    if (rg == 0 && c < pd) {
+      for (int v = 0; v < vocab; ++v)
+        partial[((int64_t)blockIdx.x * vocab + v) * pd + c] = ((acc[v] + s_acc[0][v][cl]) + s_acc[1][v][cl]) + s_acc[2][v][cl];
+    }
+    __syncthreads();
   }
 }
 
@@ -771,7 +786,7 @@ int tx_pos_grad_partials(const float* dz, int64_t ldz, int64_t col0, const int32
   TX_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "pos_grad_partials: p_drop must be in [0,1)");
   TX_REQUIRE(pos && partial && ldz >= col0 + pos_dim, "pos_grad_partials: bad arguments");
   if (n_nodes == 0 || pos_dim == 0) return TX_OK;
-  pos_grad_partials_kernel<<<(int)row_blocks(n_nodes), 128, 0, (cudaStream_t)stream>>>(dz, ldz, (int)col0, pos, (int)n_nodes, (int)pos_dim,
+  pos_grad_partials_kernel<<<(int)row_blocks(n_nodes), 256, 0, (cudaStream_t)stream>>>(dz, ldz, (int)col0, pos, (int)n_nodes, (int)pos_dim,
                                                                                       (int)vocab, 1.f / (1.f - p_drop), drop_threshold(p_drop),
                                                                                       seed, stream_id, partial);
   TX_LAUNCH_CHECK("tx_pos_grad_partials");

@@ -143,6 +143,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // Optional fused output transform of the NT kernel: C[row, c] *= keep ? (positive ? on : neg) : 0 for c < feat_cols, decoded
 // from the sign/keep bytes the fused GAT forward wrote (1 byte per aligned group of 4 columns: byte index = row * stride + c / 4,
 // stride = tx_gat_fused_mask_ld, a multiple of 16, so a thread's 32-column chunks are aligned 8-byte runs).  This is the backward of
@@ -159,6 +170,8 @@ struct GemmEpilogue {
 
 constexpr int kChunkK = 64;      // K extent accumulated inside the tensor core before promotion to fp32 registers (24 MMAs)
 constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 per TMEM lane quadrant)
+constexpr int kPairThreads = 576;  // cta_group::2 kernel: warp 0 TMA, warp 1 MMA, warps 2..17 epilogue (4 per TMEM lane quadrant, 64 columns
+                                   // each: the accumulator drain + global stores of a 128 x 256 tile were the bound of the short-K GEMMs)
 
 // C[M, N] (+ split offset) = sum_k A . B with 3xTF32 products and CHUNKED PROMOTION:
 //   the tensor core adds each MMA into its fp32 TMEM accumulator with truncation (measured: ~0.5 ulp lost per MMA, a
@@ -431,24 +444,24 @@ __device__ __forceinline__ void mbar_arrive_cta0(uint32_t bar) {   // arrive on 
 }
 
 template <int BN, int STAGES, bool TN, bool F16>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kPairThreads, 1)
 gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                         const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                         float* __restrict__ C, int64_t ldc, int64_t split_stride, int M, int n_store, int k_blocks_total,
                         int k_blocks_per_split, uint64_t mn_desc_bits, const GemmEpilogue epi, int n_tiles_n, int n_m_pairs,
-                        int n_work) {
+                        int n_work, int kChunk) {
   constexpr int BK = 32;
   constexpr int BKE = F16 ? 2 * BK : BK;                  // reduction elements per k-block
   constexpr int BOXC = F16 ? 64 : 32;                     // TN: MN elements per box row
   constexpr int kABytes = kBM * BK * 4;
-  constexpr int kChunk = kChunkK / BK;
   constexpr int BH = BN / 2;                              // B rows (NT) / columns (TN) staged by one CTA
   static_assert(BN % 64 == 0, "the pair kernel splits B into two halves of whole 32-wide blocks");
   static_assert(!(TN && F16) || BH % 64 == 0, "fp16 MN-major halves are made of 64-column boxes");
   constexpr int BH_BYTES = BH * BK * 4;
   constexpr int STAGE_BYTES = 2 * kABytes + 2 * BH_BYTES;
   constexpr int BOX_BYTES = BKE * 128;
-  constexpr int HALF = ((BN / 32 + 1) / 2) * 32;
+  constexpr int SL = BN / 4;                              // columns drained / stored by one epilogue warp (4 warps per TMEM lane quadrant)
+  static_assert(BN % 128 == 0, "the pair kernel's 16 epilogue warps take BN / 4 columns each, in chunks of 32");
   constexpr uint32_t TMEM_COLS = 2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512));
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -471,7 +484,7 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull0 + 8 * b, 1);
-      mbar_init(tempty0 + 8 * b, 16);          // 8 epilogue warps of each CTA of the pair
+      mbar_init(tempty0 + 8 * b, 32);          // 16 epilogue warps of each CTA of the pair
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -577,8 +590,7 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
     }
   } else {             // ===== epilogue warps (both CTAs): own TMEM lanes = own 128 rows =====
     const int q = warp & 3;
-    const int hsel = (warp - 2) >> 2;
-    const int n_chunks32 = hsel == 0 ? HALF / 32 : (BN - HALF) / 32;
+    const int hsel = (warp - 2) >> 2;                          // column slice [hsel SL, (hsel + 1) SL)
     const float inv_scale = (epi.scale_a ? 1.f / __ldg(epi.scale_a) : 1.f) * (epi.scale_b ? 1.f / __ldg(epi.scale_b) : 1.f);   // powers of two: exact
     float vmax = 0.f;
     int gch = 0;
@@ -586,22 +598,20 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
     int m0, n0, kb0, nkb, z;
     work_coords(w, m0, n0, kb0, nkb, z);
     const int n_chunks = (nkb + kChunk - 1) / kChunk;
-    float acc[HALF];
+    float acc[SL];
 #pragma unroll
-    for (int c = 0; c < HALF; ++c) acc[c] = 0.f;
+    for (int c = 0; c < SL; ++c) acc[c] = 0.f;
     for (int ch = 0; ch < n_chunks; ++ch, ++gch) {
       const int buf = gch & 1;
       mbar_wait(tfull0 + 8 * buf, (gch >> 1) & 1);
       tcgen05_fence_after();
-      const uint32_t tacc = tmem_base + (uint32_t)(buf * BN + hsel * HALF) + ((uint32_t)(q * 32) << 16);
+      const uint32_t tacc = tmem_base + (uint32_t)(buf * BN + hsel * SL) + ((uint32_t)(q * 32) << 16);
 #pragma unroll
-      for (int c = 0; c < HALF / 32; ++c) {
-        if (c < n_chunks32) {
-          uint32_t r[32];
-          tmem_ld32(tacc + (uint32_t)(c * 32), r);
+      for (int c = 0; c < SL / 16; ++c) {
+        uint32_t r[16];
+        tmem_ld16(tacc + (uint32_t)(c * 16), r);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(r[j]);
-        }
+        for (int j = 0; j < 16; ++j) acc[c * 16 + j] += __uint_as_float(r[j]);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -610,22 +620,24 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
       }
     }
     const int row = m0 + q * 32 + lane;
+    uint32_t mw[SL / 16];
+    const bool masked = !TN && epi.mask != nullptr;
     if (row < M) {
-      float* crow = C + (int64_t)z * split_stride + (int64_t)row * ldc + n0 + hsel * HALF;
-      uint32_t mw[HALF / 16];
-      const bool masked = !TN && epi.mask != nullptr;
       if (masked) {
 #pragma unroll
-        for (int w = 0; w < HALF / 16; ++w) {
-          const int col = n0 + hsel * HALF + w * 16;
-          mw[w] = (w < n_chunks32 * 2 && col < epi.feat_cols)
+        for (int w = 0; w < SL / 16; ++w) {
+          const int col = n0 + hsel * SL + w * 16;
+          mw[w] = (col < epi.feat_cols)
                       ? __ldg(reinterpret_cast<const uint32_t*>(epi.mask + (int64_t)row * epi.stride + (col >> 2))) : 0xFFFFFFFFu;
         }
       }
+    }
+    if (row < M) {
+      float* crow = C + (int64_t)z * split_stride + (int64_t)row * ldc + n0 + hsel * SL;
 #pragma unroll
-      for (int j = 0; j < HALF / 4; ++j) {
-        const int col = n0 + hsel * HALF + j * 4;
-        if (j < n_chunks32 * 8 && col < n_store) {
+      for (int j = 0; j < SL / 4; ++j) {
+        const int col = n0 + hsel * SL + j * 4;
+        if (col < n_store) {
           float4 v = make_float4(acc[4 * j] * inv_scale, acc[4 * j + 1] * inv_scale, acc[4 * j + 2] * inv_scale, acc[4 * j + 3] * inv_scale);
           if (masked && col < epi.feat_cols) {
             uint32_t code = (mw[j >> 2] >> (8 * (j & 3))) & 0xFFu;
@@ -685,23 +697,51 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, int64_t ldx, int 
 // ---- fp16 split path: per-tensor bounds and scales live in DEVICE scalars, so nothing here synchronises with the host ----
 __global__ void absmax_kernel(const float* __restrict__ x, int64_t ldx, int rows, int cols, float* __restrict__ out) {
   float m = 0.f;
-  const int64_t total = (int64_t)rows * cols;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int i = (int)(t / cols);
-    const int c = (int)(t - (int64_t)i * cols);
-    m = fmaxf(m, fabsf(__ldg(x + (int64_t)i * ldx + c)));
+  if ((ldx & 3) == 0 && (cols & 3) == 0 && aligned16(x)) {      // 128-bit loads, one division per 4 elements
+    const int vpr = cols >> 2;
+    const int64_t total = (int64_t)rows * vpr;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+      const int i = (int)(t / vpr);
+      const int c = (int)(t - (int64_t)i * vpr) << 2;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + (int64_t)i * ldx + c));
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+  } else {
+    const int64_t total = (int64_t)rows * cols;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+      const int i = (int)(t / cols);
+      const int c = (int)(t - (int64_t)i * cols);
+      m = fmaxf(m, fabsf(__ldg(x + (int64_t)i * ldx + c)));
+    }
   }
   m = warp_max(m);
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(m));
 }
 
-// out = max(a ca, b cb)  (b may be null)
-__global__ void bound_max2_kernel(const float* a, float ca, const float* b, float cb, float* out) {
-  *out = fmaxf(*a * ca, b ? *b * cb : 0.f);
+// max |v[0 .. len)| over one 256-thread block (small parameter vectors / tables), returned to every thread
+__device__ __forceinline__ float block_absmax(const float* __restrict__ v, int64_t len, float* s_red) {
+  float m = 0.f;
+  if (v) for (int64_t t = threadIdx.x; t < len; t += blockDim.x) m = fmaxf(m, fabsf(__ldg(v + t)));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  float r = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) r = fmaxf(r, s_red[w]);
+  __syncthreads();
+  return r;
 }
-// bound of |dft| (see tx_bound_dft): g (c_direct + c_attn ft max(al, ar))
-__global__ void bound_dft_kernel(const float* g, const float* ft, const float* al, const float* ar, float c_direct, float c_attn, float* out) {
-  *out = *g * (c_direct + c_attn * *ft * fmaxf(*al, *ar));
+// out = max(a ca, max|b[0..b_len)| cb)  (b may be null)
+__global__ void bound_max2_kernel(const float* a, float ca, const float* b, int64_t b_len, float cb, float* out) {
+  __shared__ float s_red[8];
+  const float mb = block_absmax(b, b_len, s_red);
+  if (threadIdx.x == 0) *out = fmaxf(*a * ca, mb * cb);
+}
+// bound of |dft| (see tx_bound_dft): g (c_direct + c_attn ft max(max|attn_l|, max|attn_r|))
+__global__ void bound_dft_kernel(const float* g, const float* ft, const float* al, const float* ar, int64_t len, float c_direct, float c_attn,
+                                 float* out) {
+  __shared__ float s_red[8];
+  const float ml = block_absmax(al, len, s_red), mr = block_absmax(ar, len, s_red);
+  if (threadIdx.x == 0) *out = *g * (c_direct + c_attn * *ft * fmaxf(ml, mr));
 }
 
 __global__ void split_f16_kernel(const float* __restrict__ x, int64_t ldx, int rows, int cols, const float* __restrict__ bound,
@@ -727,6 +767,60 @@ __global__ void split_f16_kernel(const float* __restrict__ x, int64_t ldx, int r
     f16_split4(v, scale, h, l);
     *reinterpret_cast<uint2*>(hi + (int64_t)i * ldo + c0) = h;
     *reinterpret_cast<uint2*>(lo + (int64_t)i * ldo + c0) = l;
+  }
+}
+
+// One launch for a WEIGHT matrix w [rows, cols]: max|w| (grid-wide, through a device counter: the grid is at most one CTA per SM,
+// so every CTA is resident and the spin below cannot deadlock), then the fp16 hi/lo split both row-major [rows, ld] (forward
+// projection operand) and transposed [cols, ldt] (input-gradient operand) with the same scale.
+__global__ void __launch_bounds__(256) split_f16_weight_kernel(const float* __restrict__ w, int64_t ldw, int rows, int cols,
+                                                               __half* __restrict__ hi, __half* __restrict__ lo, int ld,
+                                                               __half* __restrict__ hit, __half* __restrict__ lot, int ldt,
+                                                               float* __restrict__ amax, unsigned int* __restrict__ counter,
+                                                               float* __restrict__ scale_out) {
+  const int64_t total = (int64_t)rows * cols;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  float m = 0.f;
+  for (int64_t t = tid; t < total; t += nth) {
+    const int i = (int)(t / cols), c = (int)(t - (int64_t)i * cols);
+    m = fmaxf(m, fabsf(__ldg(w + (int64_t)i * ldw + c)));
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned int*>(amax), __float_as_uint(m));
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(counter, 1u);
+    while (atomicAdd(counter, 0u) < gridDim.x) __nanosleep(64);
+  }
+  __syncthreads();
+  const float scale = f16_split_scale(__ldcg(amax));
+  if (scale_out && tid == 0) *scale_out = scale;
+  const float c65 = 65504.f;
+  // 32 x 32 tiles: coalesced reads, row-major outputs written directly, transposed outputs through a shared-memory tile.
+  // The tile grid covers the padded extents (ld columns, ldt transposed columns): padding is written as zeros.
+  __shared__ __half s_hi[32][34], s_lo[32][34];
+  const int tr = (max(rows, ldt) + 31) / 32, tc = (max(cols, ld) + 31) / 32;
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;      // 8 warps x 4 rows each
+  for (int tile = blockIdx.x; tile < tr * tc; tile += gridDim.x) {
+    const int i0 = (tile / tc) * 32, c0 = (tile % tc) * 32;
+    const int c = c0 + lane;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int il = wy * 4 + r, i = i0 + il;
+      const float x = (i < rows && c < cols) ? fminf(fmaxf(__ldg(w + (int64_t)i * ldw + c) * scale, -c65), c65) : 0.f;
+      const __half h = __float2half_rn(x);
+      const __half l = __float2half_rn(x - __half2float(h));
+      if (i < rows && c < ld) { hi[(int64_t)i * ld + c] = h; lo[(int64_t)i * ld + c] = l; }
+      s_hi[il][lane] = h; s_lo[il][lane] = l;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int cl = wy * 4 + r, cc = c0 + cl, i = i0 + lane;      // transposed row cc, transposed column i
+      if (cc < cols && i < ldt) { hit[(int64_t)cc * ldt + i] = s_hi[lane][cl]; lot[(int64_t)cc * ldt + i] = s_lo[lane][cl]; }
+    }
+    __syncthreads();
   }
 }
 
@@ -898,11 +992,16 @@ static int launch_gemm_pair(const void* a_hi, const void* a_lo, int64_t lda, con
   static int persist = -1;     // TAXO_GEMM_PERSIST=0 -> one cluster per tile (the pre-persistent behaviour)
   if (persist < 0) { const char* e_p = getenv("TAXO_GEMM_PERSIST"); persist = (e_p && atoi(e_p) == 0) ? 0 : 1; }
   const int n_clusters = persist ? (n_work < kNumSms / 2 ? n_work : kNumSms / 2) : n_work;
+  // k-blocks accumulated inside the tensor core between promotions to fp32 registers (see gemm_tf32x3_kernel): 2 by default (24 MMAs);
+  // TAXO_GEMM_CHUNK overrides (longer chunks = fewer TMEM drains, more accumulated truncation bias)
+  static int chunk_env = -1;
+  if (chunk_env < 0) { const char* e_c = getenv("TAXO_GEMM_CHUNK"); chunk_env = e_c ? atoi(e_c) : 0; }
+  const int chunk_kb = chunk_env > 0 ? chunk_env : kChunkK / BK;
   dim3 grid(2u * (unsigned)n_clusters, 1, 1);
   const uint64_t mn_bits = F16 ? umma_desc_mn_bits((uint32_t)(BKE * 128), 1024u, 2u) : umma_desc_mn_bits((uint32_t)(BK * 128), 512u, 1u);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(kGemmThreads);
+  cfg.blockDim = dim3(kPairThreads);
   cfg.dynamicSmemBytes = SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -913,7 +1012,7 @@ static int launch_gemm_pair(const void* a_hi, const void* a_lo, int64_t lda, con
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tf32x3_pair_kernel<BN, STAGES, TN, F16>, ma_hi, ma_lo, mb_hi, mb_lo, c, ldc, split_stride,
-                                     (int)M, (int)n_store, kbt, kbs, mn_bits, epi, n_tiles_n, n_m_pairs, n_work);
+                                     (int)M, (int)n_store, kbt, kbs, mn_bits, epi, n_tiles_n, n_m_pairs, n_work, chunk_kb);
   if (e != cudaSuccess) {
     set_error("gemm(pair): cluster launch failed: %s", cudaGetErrorString(e));
     return TX_ERR_CUDA;
@@ -1047,17 +1146,17 @@ int tx_absmax(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* ou
   return TX_OK;
 }
 
-int tx_bound_max2(const float* a, float ca, const float* b, float cb, float* out, void* stream) {
-  TX_REQUIRE(a && out, "bound_max2: bad arguments");
-  bound_max2_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(a, ca, b, cb, out);
+int tx_bound_max2(const float* a, float ca, const float* b, int64_t b_len, float cb, float* out, void* stream) {
+  TX_REQUIRE(a && out && b_len >= 0, "bound_max2: bad arguments");
+  bound_max2_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(a, ca, b, b_len, cb, out);
   TX_LAUNCH_CHECK("tx_bound_max2");
   return TX_OK;
 }
 
-int tx_bound_dft(const float* g_amax, const float* ft_amax, const float* attn_l_amax, const float* attn_r_amax, float c_direct,
+int tx_bound_dft(const float* g_amax, const float* ft_amax, const float* attn_l, const float* attn_r, int64_t attn_len, float c_direct,
                  float c_attn, float* out, void* stream) {
-  TX_REQUIRE(g_amax && ft_amax && attn_l_amax && attn_r_amax && out, "bound_dft: bad arguments");
-  bound_dft_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(g_amax, ft_amax, attn_l_amax, attn_r_amax, c_direct, c_attn, out);
+  TX_REQUIRE(g_amax && ft_amax && attn_l && attn_r && attn_len >= 0 && out, "bound_dft: bad arguments");
+  bound_dft_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(g_amax, ft_amax, attn_l, attn_r, attn_len, c_direct, c_attn, out);
   TX_LAUNCH_CHECK("tx_bound_dft");
   return TX_OK;
 }
@@ -1071,6 +1170,23 @@ int tx_split_f16(const float* x, int64_t ldx, int64_t rows, int64_t cols, const 
   const int grid = (int)((total + 255) / 256 < (int64_t)kNumSms * 16 ? (total + 255) / 256 : (int64_t)kNumSms * 16);
   split_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, (int)rows, (int)cols, bound, (__half*)hi, (__half*)lo, (int)ldo, scale_out);
   TX_LAUNCH_CHECK("tx_split_f16");
+  return TX_OK;
+}
+
+int tx_split_f16_weight(const float* w, int64_t ldw, int64_t rows, int64_t cols, void* hi, void* lo, int64_t ld, void* hi_t, void* lo_t,
+                        int64_t ld_t, float* scratch2, float* scale_out, void* stream) {
+  TX_REQUIRE(w && hi && lo && hi_t && lo_t && scratch2 && rows > 0 && cols > 0 && rows < INT32_MAX && cols < INT32_MAX, "split_f16_weight: bad arguments");
+  TX_REQUIRE(ld % 8 == 0 && ld >= cols && ld_t % 8 == 0 && ld_t >= rows && aligned16(hi) && aligned16(lo) && aligned16(hi_t) && aligned16(lo_t),
+             "split_f16_weight: outputs need ld %% 8 == 0 and 16-byte alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(scratch2, 0, 2 * sizeof(float), st) != cudaSuccess) { set_error("split_f16_weight: memset failed"); return TX_ERR_CUDA; }
+  const int64_t total = rows * (ld > ld_t ? ld : ld_t);
+  int64_t grid = (total + 2047) / 2048;
+  if (grid > kNumSms) grid = kNumSms;     // <= one CTA per SM: the grid-wide rendezvous needs every CTA resident
+  if (grid < 1) grid = 1;
+  split_f16_weight_kernel<<<(int)grid, 256, 0, st>>>(w, ldw, (int)rows, (int)cols, (__half*)hi, (__half*)lo, (int)ld, (__half*)hi_t, (__half*)lo_t,
+                                                     (int)ld_t, scratch2, reinterpret_cast<unsigned int*>(scratch2 + 1), scale_out);
+  TX_LAUNCH_CHECK("tx_split_f16_weight");
   return TX_OK;
 }
 

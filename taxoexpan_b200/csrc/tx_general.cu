@@ -166,6 +166,19 @@ __global__ void __launch_bounds__(256) epilogue_bwd_kernel(float* __restrict__ d
   }
 }
 
+// few partial blocks of many elements (split-K GEMM partials): one float4 column per thread, blocks summed in index order
+__global__ void __launch_bounds__(256) reduce_partials_wide_kernel(const float* __restrict__ partial, int n_blocks, int64_t m4,
+                                                                   float* __restrict__ out) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < m4; t += (int64_t)gridDim.x * blockDim.x) {
+    float4 s = __ldg(reinterpret_cast<const float4*>(partial) + t);
+    for (int b = 1; b < n_blocks; ++b) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(partial) + (int64_t)b * m4 + t);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    reinterpret_cast<float4*>(out)[t] = s;
+  }
+}
+
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int64_t n_blocks, int64_t m_len,
                                                               float* __restrict__ out) {
   __shared__ float sm[8][33];
@@ -914,6 +927,13 @@ int tx_epilogue_bwd(float* dz, int64_t ldz, const float* z, const int32_t* pos, 
 
 int tx_reduce_partials(const float* partial, int64_t n_blocks, int64_t m_len, float* out, void* stream) {
   if (m_len <= 0) return TX_OK;
+  if (n_blocks <= 64 && m_len >= 4096 && m_len % 4 == 0 && aligned16(partial) && aligned16(out)) {   // split-K partials: few, long
+    const int64_t m4 = m_len / 4;
+    const int grid = (int)((m4 + 255) / 256 < (int64_t)kNumSms * 16 ? (m4 + 255) / 256 : (int64_t)kNumSms * 16);
+    reduce_partials_wide_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(partial, (int)n_blocks, m4, out);
+    TX_LAUNCH_CHECK("tx_reduce_partials");
+    return TX_OK;
+  }
   reduce_partials_kernel<<<(int)((m_len + 31) / 32), 256, 0, (cudaStream_t)stream>>>(partial, n_blocks, m_len, out);
   TX_LAUNCH_CHECK("tx_reduce_partials");
   return TX_OK;

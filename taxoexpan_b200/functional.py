@@ -159,6 +159,25 @@ def split_f16(x: torch.Tensor, cols: int = None, bound: torch.Tensor = None) -> 
     return F16Pair(hi, lo, scale, cols)
 
 
+def split_f16_weight(w: torch.Tensor):
+    """One launch: max|w|, then the fp16 split of the weight matrix w [rows, cols] (row-major) in both orientations with the same
+    scale.  Returns (F16Pair [rows, cols], F16Pair [cols, rows])."""
+    lib = _lib.load()
+    w = _rowmajor(w)
+    rows, cols = w.shape
+    ld, ldt = round8(cols), round8(rows)
+    dev = w.device
+    buf = torch.empty((rows * ld + cols * ldt) * 2, dtype=torch.float16, device=dev)      # hi | lo | hi_t | lo_t in one allocation
+    hi, lo = buf[:rows * ld].view(rows, ld), buf[rows * ld:2 * rows * ld].view(rows, ld)
+    o = 2 * rows * ld
+    hit, lot = buf[o:o + cols * ldt].view(cols, ldt), buf[o + cols * ldt:].view(cols, ldt)
+    scal = torch.empty(3, dtype=torch.float32, device=dev)                                # [amax, counter] workspace + scale
+    scale = scal[2:3]
+    check(lib.tx_split_f16_weight(ptr(w), w.stride(0) if rows > 1 else cols, rows, cols, ptr(hi), ptr(lo), ld, ptr(hit), ptr(lot), ldt,
+                                  ptr(scal), ptr(scale), current_stream()), "tx_split_f16_weight")
+    return F16Pair(hi, lo, scale, cols), F16Pair(hit, lot, scale, rows)
+
+
 def gemm_nt_f16(a: F16Pair, k: int, b: F16Pair, n: int, out: torch.Tensor = None, epi=None, want_amax: bool = False):
     """C[:, :n] = A[:, :k] @ B[:n, :k]^T from fp16-split operands (tx_gemm_nt_f16x3).  Returns C, or (C, amax) with a device
     scalar max|C| when want_amax."""
@@ -207,23 +226,28 @@ def gemm_nt(a: torch.Tensor, k: int, b: torch.Tensor, out: torch.Tensor = None) 
     return gemm_nt_ps(a_hi, a_lo, k, b_hi, b_lo, n, out)
 
 
-def _layer_gemms_fwd(z, k, w_nk, z_lo=None, z16=None):
+def _layer_gemms_fwd(z, k, w_nk, z_lo=None, z16=None, w_rowmajor=None, w_is_nk=True):
     """y = z[:, :k] @ w_nk[:, :k]^T.  Returns (y, saved, y_amax) where `saved` is what backward needs of z: z itself (cublas), its
     TF32 split (tf32x3) or its fp16 split (f16x3: (hi, lo, scale)) - the split is computed once and reused by the weight-gradient
     GEMM - and y_amax is a device scalar max|y| (f16x3 only: it bounds the next tensors' fp16 scales)."""
     if GEMM_BACKEND == "f16x3" and z.shape[0] > 0:
         zp = z16 if z16 is not None else split_f16(z, k)      # z16: produced pre-split by the previous layer's epilogue
-        wp = split_f16(w_nk, k)
+        # the weights are split ONCE per step, in both orientations: [N, K] for this GEMM, [K, N] for the input-gradient GEMM
+        if w_rowmajor is not None:
+            p_a, p_b = split_f16_weight(w_rowmajor)
+            wp, wt = (p_a, p_b) if w_is_nk else (p_b, p_a)
+        else:
+            wp, wt = split_f16(w_nk, k), None
         y, y_amax = gemm_nt_f16(zp, k, wp, w_nk.shape[0], want_amax=True)
-        return y, (zp.hi, zp.lo, zp.scale), y_amax
+        return y, (zp.hi, zp.lo, zp.scale, None if wt is None else wt.hi, None if wt is None else wt.lo, None if wt is None else wt.scale), y_amax
     if GEMM_BACKEND != "tf32x3" or z.shape[0] == 0:
-        return torch.mm(z[:, :k], w_nk[:, :k].t()), (z, None, None), None
+        return torch.mm(z[:, :k], w_nk[:, :k].t()), (z, None, None, None, None, None), None
     if z_lo is None:
         z_hi, z_lo = split_tf32(z, k)
     else:
         z_hi = z                                      # produced pre-split by the previous layer's epilogue
     w_hi, w_lo = split_tf32(w_nk, k)
-    return gemm_nt_ps(z_hi, z_lo, k, w_hi, w_lo, w_nk.shape[0]), (z_hi, z_lo, None), None
+    return gemm_nt_ps(z_hi, z_lo, k, w_hi, w_lo, w_nk.shape[0]), (z_hi, z_lo, None, None, None, None), None
 
 
 def _dz_epilogue(in_link, c0a):
@@ -251,7 +275,10 @@ def _layer_gemms_bwd_f16(dy, f, saved, w_kf, k, ldz, c0, need_w, need_z, in_link
             c0a = (min(c0, k) // 8) * 8                   # fp16 rows: 16-byte aligned slices start at multiples of 8 columns
             dz = torch.empty((n, ldz), dtype=torch.float32, device=zp.hi.device)
             if k > c0a:
-                wp = split_f16(w_kf[c0a:k], f)
+                if len(saved) > 3 and saved[3] is not None:       # [K, F] orientation split in the forward pass
+                    wp = F16Pair(saved[3][c0a:k], saved[4][c0a:k], saved[5], f)
+                else:
+                    wp = split_f16(w_kf[c0a:k], f)
                 epi = _dz_epilogue(in_link, c0a)
                 _, dz_amax = gemm_nt_f16(dy16, f, wp, k - c0a, out=dz[:, c0a:], epi=epi, want_amax=True)
                 if in_link is not None:
@@ -370,6 +397,16 @@ class ConcatPosDropout(Function):
         if not (need_x or need_tab):
             return None, None, None, None, None, None
         dz = _rowmajor(dz)
+        if not need_x:
+            # x carries no gradient (the usual case, trainer.py:48): only d(position table) = sum over rows of the kept,
+            # rescaled position columns is needed - one read of [N, pos_dim] instead of a rescale of the whole d(z)
+            with torch.cuda.device(dz.device):
+                nb = int(lib.tx_row_blocks(n))
+                partial = torch.empty(nb * vocab * pd, dtype=torch.float32, device=dz.device)
+                check(lib.tx_pos_grad_partials(ptr(dz), dz.stride(0) if n > 1 else ldz, k_in, ptr(pos32), n, pd, vocab, p, seed, stream_id,
+                                               ptr(partial), current_stream()), "tx_pos_grad_partials")
+                dtab = _reduce_partials(lib, partial, nb, vocab * pd).view(vocab, pd)
+            return None, dtab, None, None, None, None
         if p > 0.0:
             dz = dz.clone()      # the kernel rescales the kept entries in place; never touch the caller's grad
         with torch.cuda.device(dz.device):
@@ -440,7 +477,8 @@ class GatLayer(Function):
             with timed_region("gemm_fwd"):
                 ft, zsaved, ft_amax = _layer_gemms_fwd(z, K, weight,      # ft = fc(h), model_zoo.py:83
                                                        cfg.in_link.z_lo if (cfg.in_link is not None and GEMM_BACKEND == "tf32x3") else None,
-                                                       cfg.in_link.z16 if (cfg.in_link is not None and f16) else None)
+                                                       cfg.in_link.z16 if (cfg.in_link is not None and f16) else None,
+                                                       w_rowmajor=weight if (f16 and weight.shape[1] == K) else None)
             al = attn_l.reshape(-1).contiguous()
             ar = attn_r.reshape(-1).contiguous()
             alpha = torch.empty(st.e * H, **f32)
@@ -475,9 +513,8 @@ class GatLayer(Function):
                     o_lo = torch.empty((n, ld16), dtype=torch.float16, device=dev)
                     o_scale = torch.empty(1, **f32)
                     bound = torch.empty(1, **f32)
-                    tab_amax = absmax(tab) if pd > 0 else None
-                    check(lib.tx_bound_max2(ptr(ft_amax), 1.0 / ((1.0 - cfg.p_attn) * (1.0 - cfg.p_next)), ptr(tab_amax),
-                                            1.0 / (1.0 - cfg.p_next), ptr(bound), stream), "tx_bound_max2")
+                    check(lib.tx_bound_max2(ptr(ft_amax), 1.0 / ((1.0 - cfg.p_attn) * (1.0 - cfg.p_next)), ptr(tab) if pd > 0 else None,
+                                            tab.numel() if pd > 0 else 0, 1.0 / (1.0 - cfg.p_next), ptr(bound), stream), "tx_bound_max2")
                     check(lib.tx_gat_fused_fwd_f16(ptr(ft), F_, ptr(al), ptr(ar), ptr(st.in_ptr), ptr(st.in_src), ptr(st.in_eid), n, H, D,
                                                    cfg.neg_slope, cfg.p_attn, cfg.attn_seed, cfg.attn_stream, ptr(alpha), ptr(alpha_d),
                                                    ptr(elog), ldo, epi, ptr(maskbits), ptr(o_hi), ptr(o_lo), ld16, ptr(bound),
@@ -505,7 +542,7 @@ class GatLayer(Function):
         ctx.st, ctx.cfg, ctx.pd = st, cfg, pd
         ctx.vocab = 0 if next_pos_table is None else int(next_pos_table.shape[0])
         ctx.save_for_backward(zsaved[0], zsaved[1], weight, al, ar, ft, alpha, alpha_d, elog,
-                              out if (cfg.hidden and not fused) else None, pos32, zsaved[2], ft_amax)
+                              out if (cfg.hidden and not fused) else None, pos32, zsaved[2], ft_amax, zsaved[3], zsaved[4], zsaved[5])
         ctx.attn_shape = attn_l.shape
         ctx.zshape = tuple(z.shape)
         return out
@@ -513,7 +550,7 @@ class GatLayer(Function):
     @staticmethod
     def backward(ctx, dout):
         lib = _lib.load()
-        z0, z1, weight, al, ar, ft, alpha, alpha_d, elog, out, pos32, z_scale, ft_amax = ctx.saved_tensors
+        z0, z1, weight, al, ar, ft, alpha, alpha_d, elog, out, pos32, z_scale, ft_amax, wt_hi, wt_lo, wt_scale = ctx.saved_tensors
         st, cfg, pd = ctx.st, ctx.cfg, ctx.pd
         n, ldz = ctx.zshape
         H, D, K = cfg.heads, cfg.dim, cfg.k
@@ -555,11 +592,10 @@ class GatLayer(Function):
                         #   |ds| <= 2 |d alpha~| / (1 - p_attn),  |da1_j| <= outdeg |ds|,  |da2_i| <= |ds|
                         g_amax = cfg.out_link.dz_amax if (cfg.out_link is not None and cfg.out_link.dz_amax is not None and pre) \
                             else absmax(dout, F_ if cfg.hidden else D)
-                        al_amax, ar_amax = absmax(al.view(1, -1)), absmax(ar.view(1, -1))
                         deg = max(int(st.max_out_deg), 1)
                         slope = max(1.0, abs(cfg.neg_slope))
                         bound = torch.empty(1, **f32)
-                        check(lib.tx_bound_dft(ptr(g_amax), ptr(ft_amax), ptr(al_amax), ptr(ar_amax), g_scale * deg / (1.0 - cfg.p_attn),
+                        check(lib.tx_bound_dft(ptr(g_amax), ptr(ft_amax), ptr(al), ptr(ar), al.numel(), g_scale * deg / (1.0 - cfg.p_attn),
                                                g_scale * 2.0 * (deg + 1) * D * slope / (1.0 - cfg.p_attn), ptr(bound), stream), "tx_bound_dft")
                         d_hi = torch.empty((n, ld16), dtype=torch.float16, device=dev)
                         d_lo = torch.empty((n, ld16), dtype=torch.float16, device=dev)
@@ -617,7 +653,7 @@ class GatLayer(Function):
                           "tx_gat_attn_grad_partials")
                     both = _reduce_partials(lib, partial, nb, 2 * F_)
                     dal, dar = both[:F_].view(ctx.attn_shape), both[F_:].view(ctx.attn_shape)
-            dw, dz = _layer_gemms_bwd(dft, F_, (z0, z1, z_scale), weight.t(), K, ldz, cfg.dz_from, ctx.needs_input_grad[1],
+            dw, dz = _layer_gemms_bwd(dft, F_, (z0, z1, z_scale, wt_hi, wt_lo, wt_scale), weight.t(), K, ldz, cfg.dz_from, ctx.needs_input_grad[1],
                                       ctx.needs_input_grad[0], cfg.in_link, dft_lo, dft16)
         return dz, dw, dal, dar, dtab, None, None, None
 
@@ -651,7 +687,8 @@ class GcnLayer(Function):
             stream = current_stream()
             Stats.tag = cfg.tag
             with timed_region("gemm_fwd"):
-                y, zsaved, _ = _layer_gemms_fwd(z, K, weight.t())          # torch.mm(h, W), model_zoo.py:37
+                y, zsaved, _ = _layer_gemms_fwd(z, K, weight.t(),         # torch.mm(h, W), model_zoo.py:37
+                                                w_rowmajor=weight if (GEMM_BACKEND == "f16x3" and weight.shape[0] == K) else None, w_is_nk=False)
             norm = st.gcn_norm()
             pd = 0 if next_pos_table is None else int(next_pos_table.shape[1])
             tab = None if next_pos_table is None else next_pos_table.contiguous()
@@ -666,14 +703,14 @@ class GcnLayer(Function):
         ctx.st, ctx.cfg, ctx.pd = st, cfg, pd
         ctx.vocab = 0 if next_pos_table is None else int(next_pos_table.shape[0])
         ctx.has_bias = bias is not None
-        ctx.save_for_backward(zsaved[0], zsaved[1], weight, out if cfg.hidden else None, pos32, norm, zsaved[2])
+        ctx.save_for_backward(zsaved[0], zsaved[1], weight, out if cfg.hidden else None, pos32, norm, zsaved[2], zsaved[3], zsaved[4], zsaved[5])
         ctx.zshape = tuple(z.shape)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         lib = _lib.load()
-        z0, z1, weight, out, pos32, norm, z_scale = ctx.saved_tensors
+        z0, z1, weight, out, pos32, norm, z_scale, wt_hi, wt_lo, wt_scale = ctx.saved_tensors
         st, cfg, pd = ctx.st, ctx.cfg, ctx.pd
         n, ldz = ctx.zshape
         D, K = cfg.dim, cfg.k
@@ -705,7 +742,7 @@ class GcnLayer(Function):
             dy = torch.empty((n, D), **f32)
             check(lib.tx_gcn_aggregate_bwd(ptr(dout), ldg, ptr(norm), ptr(st.out_ptr), ptr(st.out_dst), n, D, ptr(dy), D, stream),
                   "tx_gcn_aggregate_bwd")
-            dwt, dz = _layer_gemms_bwd(dy, D, (z0, z1, z_scale), weight, K, ldz, cfg.dz_from, ctx.needs_input_grad[1],
+            dwt, dz = _layer_gemms_bwd(dy, D, (z0, z1, z_scale, wt_hi, wt_lo, wt_scale), weight, K, ldz, cfg.dz_from, ctx.needs_input_grad[1],
                                        ctx.needs_input_grad[0])
             dw = None if dwt is None else dwt.t()                         # weight is [K, D]
         return dz, dw, db, dtab, None, None, None

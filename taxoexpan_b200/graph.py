@@ -217,8 +217,8 @@ class EgonetBatch(DGLGraph):
             raise ValueError("batch too large for int32 indices")
         self._n = int(self._node_off[-1])
         self._e = int(self._edge_off[-1])
-        self.batch_num_nodes = n.tolist()
-        self.batch_num_edges = (2 * n - 1).tolist()
+        self._n_per_graph = n                 # batch_num_nodes / batch_num_edges lists are materialised on first use only
+        self._bnn = self._bne = None          # (two 8192-element tolist() calls were 0.2 ms of every freshly built batch)
         self._edges_built = False
         self._max_nodes = int(n.max()) if n.size else 0
         # one pinned staging buffer: [n_gp | n_sib | node_off | edge_off] as int32
@@ -230,6 +230,26 @@ class EgonetBatch(DGLGraph):
             self.ndata.update(ndata)
         if "pos" not in self.ndata:
             self.ndata["pos"] = _LazyPos(self)
+
+    @property
+    def batch_num_nodes(self):
+        if self._bnn is None:
+            self._bnn = self._n_per_graph.tolist() if hasattr(self, "_n_per_graph") else [0]
+        return self._bnn
+
+    @batch_num_nodes.setter
+    def batch_num_nodes(self, v):
+        self._bnn = v
+
+    @property
+    def batch_num_edges(self):
+        if self._bne is None:
+            self._bne = (2 * self._n_per_graph - 1).tolist() if hasattr(self, "_n_per_graph") else [0]
+        return self._bne
+
+    @batch_num_edges.setter
+    def batch_num_edges(self, v):
+        self._bne = v
 
     @classmethod
     def from_counts(cls, n_gp, n_sib, ndata=None) -> "EgonetBatch":
@@ -263,14 +283,14 @@ class EgonetBatch(DGLGraph):
 
     def in_degrees(self):
         # gp: 1 (self loop), anchor: n_gp + 1, sibling: 2
-        n = np.asarray(self.batch_num_nodes, dtype=np.int64)
+        n = self._n_per_graph
         gid = np.repeat(np.arange(self._g), n)
         local = np.arange(self._n) - self._node_off[gid]
         a = self.n_gp.astype(np.int64)[gid]
         return torch.from_numpy(np.where(local < a, 1, np.where(local == a, a + 1, 2)))
 
     def host_pos(self) -> torch.Tensor:
-        n = np.asarray(self.batch_num_nodes, dtype=np.int64)
+        n = self._n_per_graph
         gid = np.repeat(np.arange(self._g), n)
         local = np.arange(self._n) - self._node_off[gid]
         a = self.n_gp.astype(np.int64)[gid]
