@@ -749,6 +749,47 @@ class GcnLayer(Function):
 
 
 # --------------------------------------------------------------------------------------------------
+# y = a @ w  (the bilinear matching modules' projection, model_zoo.py:301-328), fp32-faithful on the tcgen05 GEMMs
+# --------------------------------------------------------------------------------------------------
+class DenseRight(Function):
+    """y[m, r] = sum_l a[m, l] w[l, r] with its autograd GEMMs (da = dy w^T, dw = a^T dy) on the f16x3 kernels; the weight is
+    split once per step in both orientations (tx_split_f16_weight)."""
+
+    @staticmethod
+    def forward(ctx, a, w):
+        _check_cuda(a, "a")
+        with torch.cuda.device(a.device):
+            m, l = a.shape
+            r = w.shape[1]
+            ap = split_f16(a, l)
+            wp, wt = split_f16_weight(w)                 # wp: [l, r] (input-gradient operand), wt: [r, l] (forward operand)
+            y = gemm_nt_f16(ap, l, wt, r)
+        ctx.save_for_backward(ap.hi, ap.lo, ap.scale, wp.hi, wp.lo, wp.scale)
+        ctx.dims = (m, l, r)
+        return y.contiguous() if y.shape[1] != r else y
+
+    @staticmethod
+    def backward(ctx, dy):
+        a_hi, a_lo, a_sc, w_hi, w_lo, w_sc = ctx.saved_tensors
+        m, l, r = ctx.dims
+        da = dw = None
+        with torch.cuda.device(dy.device):
+            dp = split_f16(_rowmajor(dy), r)
+            if ctx.needs_input_grad[0]:
+                da = gemm_nt_f16(dp, r, F16Pair(w_hi, w_lo, w_sc, r), l)
+            if ctx.needs_input_grad[1]:
+                dw = gemm_tn_f16(F16Pair(a_hi, a_lo, a_sc, l), l, dp, r)
+        return da, dw
+
+
+def dense_right(a: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """a @ w through the library's fp32-faithful tensor-core GEMMs when they are the dense backend (else torch.mm)."""
+    if GEMM_BACKEND == "f16x3" and a.is_cuda and a.shape[0] > 0 and a.dtype == torch.float32:
+        return DenseRight.apply(a, w)
+    return torch.mm(a, w)
+
+
+# --------------------------------------------------------------------------------------------------
 # Readout
 # --------------------------------------------------------------------------------------------------
 class Readout(Function):

@@ -273,7 +273,8 @@ class ConcatReadout(nn.Module):
 
 
 # =====================================================================================================
-# Graph matching modules (dense, tiny; plain PyTorch -- SURVEY.md section 8 row f1 "next")
+# Graph matching modules (SURVEY.md section 8 row f1 "next"): plain PyTorch, except that the bilinear forms' projection e1 W and its
+# autograd GEMMs run on the library's fp32-faithful tensor-core kernels (they were 180 us of cuBLAS SIMT sgemm per step)
 # =====================================================================================================
 class MLP(nn.Module):
     """reference model_zoo.py:281-298"""
@@ -294,7 +295,7 @@ class BIM(nn.Module):
         self.W = nn.Bilinear(l_dim, r_dim, 1, bias=False)
 
     def forward(self, e1, e2):
-        return (torch.mm(e1, self.W.weight[0]) * e2).sum(dim=1, keepdim=True)
+        return (txf.dense_right(e1, self.W.weight[0]) * e2).sum(dim=1, keepdim=True)
 
 
 class LBM(BIM):
