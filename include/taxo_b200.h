@@ -225,6 +225,16 @@ int tx_gat_fused_fwd_f16(const float* ft, int64_t ldf, const float* attn_l, cons
                          float neg_slope, float p_attn, uint64_t attn_seed, uint32_t attn_stream_id, float* alpha,
                          float* alpha_d, float* elog, int64_t ldo, const tx_gat_epilogue* epi, uint32_t* maskbits, void* out16_hi,
                          void* out16_lo, int64_t ld16, const float* bound, float* scale_out, void* stream);
+/* TMA-staged variant of tx_gat_fused_fwd / tx_gat_fused_fwd_f16 (same arithmetic and outputs, reference model_zoo.py:83-96,106-114):
+ * the ft rows of a tile of whole graphs (tiles of tx_gat_bwd_tiles) are bulk-copied into shared memory one tile ahead; a1 / a2 are
+ * computed once per node, the edge softmax by one thread per destination row, aggregation + epilogue by one thread per (row
+ * group, pair of float4 columns).  Exactly one of {out (+ optional TF32 out_lo), out16_hi/out16_lo (+ bound, scale_out)} is written. */
+int tx_gat_fused_fwd_staged(const float* ft, int64_t ldf, const float* attn_l, const float* attn_r, const int32_t* in_ptr,
+                            const int32_t* in_src, const int32_t* in_eid, const int32_t* tiles, int64_t n_nodes, int64_t heads,
+                            int64_t dim, float neg_slope, float p_attn, uint64_t attn_seed, uint32_t attn_stream_id, float* alpha,
+                            float* alpha_d, float* elog, float* out, int64_t ldo, const tx_gat_epilogue* epi, uint32_t* maskbits,
+                            float* out_lo, void* out16_hi, void* out16_lo, int64_t ld16, const float* bound, float* scale_out,
+                            void* stream);
 /* dpos_partial[b, r, :] = sum over rows i of block b (tx_row_blocks) with pos_i = r of dz[i, col0 : col0+pos_dim] * keep/(1-p)
  * (gradient of the appended position-embedding block, reference model_zoo.py:214-215). */
 int tx_pos_grad_partials(const float* dz, int64_t ldz, int64_t col0, const int32_t* pos, int64_t n_nodes,

@@ -1,0 +1,98 @@
+"""Turn the raw outputs of scripts/gpu_profile.sh (gpurun_out/) into the tracked evidence under profiles/:
+   r1_bench_n1.json, r1_bench_reference.json, r1_launches.csv (+ _summary), r1_ncu_full_summary.csv, traffic.json, r1_env.txt"""
+import collections, csv, json, os, re, shutil, subprocess, sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "gpurun_out")
+DST = os.path.join(ROOT, "profiles")
+os.makedirs(DST, exist_ok=True)
+
+
+def last_json_line(path):
+    with open(path) as f:
+        lines = [ln for ln in f.read().strip().splitlines() if ln.startswith("{")]
+    return json.loads(lines[-1])
+
+
+for name, out in (("bench_n1.json", "r1_bench_n1.json"), ("bench_reference.json", "r1_bench_reference.json")):
+    d = last_json_line(os.path.join(SRC, name))
+    with open(os.path.join(DST, out), "w") as f:
+        f.write(json.dumps(d) + "\n")
+shutil.copy(os.path.join(SRC, "smi.txt"), os.path.join(DST, "r1_env.txt"))
+with open(os.path.join(DST, "r1_env.txt"), "a") as f:
+    f.write(open(os.path.join(SRC, "pytest_gpu.log")).read())
+
+# ---- launch list (ncu --metrics gpu__time_duration.sum --clock-control none on `bench.py --steps 2 --warmup 3`) ----
+rows = list(csv.reader(open(os.path.join(SRC, "launches.csv"))))
+hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+hdr, data = rows[hi], rows[hi + 1:]
+kn, mv = hdr.index("Kernel Name"), hdr.index("Metric Value")
+with open(os.path.join(DST, "r1_launches.csv"), "w", newline="") as f:
+    w = csv.writer(f)
+    w.writerow(["launch", "kernel", "grid", "block", "gpu__time_duration_us"])
+    gi, bi = hdr.index("Grid Size"), hdr.index("Block Size")
+    for n, r in enumerate(data):
+        if len(r) > mv:
+            w.writerow([n, r[kn][:160], r[gi], r[bi], round(float(r[mv].replace(",", "")) / 1000.0, 3)])
+agg = collections.defaultdict(lambda: [0, 0.0])
+for r in data:
+    if len(r) <= mv:
+        continue
+    name = re.sub(r"\(.*", "", r[kn])[:100]
+    agg[name][0] += 1
+    agg[name][1] += float(r[mv].replace(",", "")) / 1000.0
+tot = sum(v[1] for v in agg.values())
+with open(os.path.join(DST, "r1_launches_summary.csv"), "w", newline="") as f:
+    w = csv.writer(f)
+    w.writerow(["kernel", "launches", "total_us", "avg_us", "share_of_captured"])
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        w.writerow([k, v[0], round(v[1], 2), round(v[1] / v[0], 2), round(v[1] / tot, 4)])
+
+# ---- ncu --set full of the fused GAT kernels and the GEMMs ----
+rep = os.path.join(SRC, "kernels_full.ncu-rep")
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr, units = rows[0], rows[1]
+want = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__registers_per_thread", "gpu__time_duration.sum",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio"]
+cols = [c for c in want if c in hdr]
+
+
+def to_bytes(val, unit):
+    v = float(val.replace(",", ""))
+    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+
+
+per_kernel = collections.defaultdict(list)
+with open(os.path.join(DST, "r1_ncu_full_summary.csv"), "w", newline="") as f:
+    w = csv.writer(f)
+    w.writerow([f"{c} [{units[hdr.index(c)]}]" if units[hdr.index(c)] else c for c in cols])
+    for r in rows[2:]:
+        if len(r) != len(hdr):
+            continue
+        w.writerow([r[hdr.index(c)][:140] for c in cols])
+        name = r[hdr.index("Kernel Name")]
+        dr = to_bytes(r[hdr.index("dram__bytes_read.sum")], units[hdr.index("dram__bytes_read.sum")])
+        dw = to_bytes(r[hdr.index("dram__bytes_write.sum")], units[hdr.index("dram__bytes_write.sum")])
+        per_kernel[name.split("(")[0]].append((float(r[hdr.index("gpu__time_duration.sum")].replace(",", "")), dr + dw))
+traffic = {}
+for key, label in (("gat_bwd_staged_kernel", "tx_gat_fused_bwd_staged"), ("gat_fused_fwd_kernel", "tx_gat_fused_fwd")):
+    ls = [v for k, v in per_kernel.items() if key in k]
+    ls = sorted(ls[0], key=lambda t: -t[1]) if ls else []
+    if ls and ls[0][1] > 2.5 * ls[-1][1]:                          # L0 launches move ~4x the bytes of L1 launches
+        cut = (ls[0][1] * ls[-1][1]) ** 0.5
+        big = [b for _, b in ls if b > cut]
+        small = [b for _, b in ls if b <= cut]
+        traffic[f"{label}[L0]"] = int(sum(big) / len(big))
+        traffic[f"{label}[L1]"] = int(sum(small) / len(small))
+with open(os.path.join(DST, "traffic.json"), "w") as f:
+    json.dump({"source": "profiles/r1_ncu_full_summary.csv: dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu --set full)",
+               "per_launch_bytes": traffic}, f, indent=1)
+print("profiles written:", sorted(os.listdir(DST)))
+print(traffic)

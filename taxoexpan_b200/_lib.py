@@ -85,6 +85,8 @@ _SIGNATURES = {
     "tx_gat_fused_bwd_staged_blocks": [I64, I64, I64],
     "tx_gat_fused_bwd_staged": [P, I64, I64, F32, P, I64, P, P, P, P, P, P, P, P, P, P, P, P, I64, I64, I64, F32, F32, c_uint64, c_uint32,
                                 P, P, P, I64, P, P, P, I64, P, P, P, P],
+    "tx_gat_fused_fwd_staged": [P, I64, P, P, P, P, P, P, I64, I64, I64, F32, F32, c_uint64, c_uint32, P, P, P, P, I64,
+                                POINTER(GatEpilogue), P, P, P, P, I64, P, P, P],
     "tx_gat_fused_fwd_f16": [P, I64, P, P, P, P, P, I64, I64, I64, F32, F32, c_uint64, c_uint32, P, P, P, I64,
                              POINTER(GatEpilogue), P, P, P, I64, P, P, P],
     "tx_pos_grad_partials": [P, I64, I64, P, I64, I64, I64, F32, c_uint64, c_uint32, P, P],

@@ -54,6 +54,10 @@ FUSE_DZ_EPILOGUE = os.environ.get("TAXO_FUSE_DZ_EPILOGUE", "1") not in ("", "0")
 FUSE_SPLIT = os.environ.get("TAXO_FUSE_SPLIT", "1") not in ("", "0")
 # TMA-staged fused GAT backward (tx_fused_bwd.cu) whenever d(z_next) needs no per-load mask decode; TAXO_STAGED_BWD=0 -> first kernel
 STAGED_BWD = os.environ.get("TAXO_STAGED_BWD", "1") not in ("", "0")
+# TMA-staged fused GAT forward (tx_fused_fwd.cu): parity-green but measured SLOWER than the warp-per-(row, head) kernel on the
+# MAG-CS shapes (L0: 0.35 ms vs 0.23 ms - its one-thread-per-row softmax step and the two extra CTA barriers per tile cost more than
+# the gather they save), so it is opt-in: TAXO_STAGED_FWD=1
+STAGED_FWD = os.environ.get("TAXO_STAGED_FWD", "0") not in ("", "0")
 
 
 def use_fused(lib, heads: int, dim: int, mean_heads: int, st=None) -> bool:
@@ -515,11 +519,24 @@ class GatLayer(Function):
                     bound = torch.empty(1, **f32)
                     check(lib.tx_bound_max2(ptr(ft_amax), 1.0 / ((1.0 - cfg.p_attn) * (1.0 - cfg.p_next)), ptr(tab) if pd > 0 else None,
                                             tab.numel() if pd > 0 else 0, 1.0 / (1.0 - cfg.p_next), ptr(bound), stream), "tx_bound_max2")
-                    check(lib.tx_gat_fused_fwd_f16(ptr(ft), F_, ptr(al), ptr(ar), ptr(st.in_ptr), ptr(st.in_src), ptr(st.in_eid), n, H, D,
-                                                   cfg.neg_slope, cfg.p_attn, cfg.attn_seed, cfg.attn_stream, ptr(alpha), ptr(alpha_d),
-                                                   ptr(elog), ldo, epi, ptr(maskbits), ptr(o_hi), ptr(o_lo), ld16, ptr(bound),
-                                                   ptr(o_scale), stream), "tx_gat_fused_fwd")
+                    if STAGED_FWD:
+                        check(lib.tx_gat_fused_fwd_staged(ptr(ft), F_, ptr(al), ptr(ar), ptr(st.in_ptr), ptr(st.in_src), ptr(st.in_eid),
+                                                          ptr(st.bwd_tiles(D)), n, H, D, cfg.neg_slope, cfg.p_attn, cfg.attn_seed,
+                                                          cfg.attn_stream, ptr(alpha), ptr(alpha_d), ptr(elog), None, ldo, epi,
+                                                          ptr(maskbits), None, ptr(o_hi), ptr(o_lo), ld16, ptr(bound), ptr(o_scale),
+                                                          stream), "tx_gat_fused_fwd_staged")
+                    else:
+                        check(lib.tx_gat_fused_fwd_f16(ptr(ft), F_, ptr(al), ptr(ar), ptr(st.in_ptr), ptr(st.in_src), ptr(st.in_eid), n, H, D,
+                                                       cfg.neg_slope, cfg.p_attn, cfg.attn_seed, cfg.attn_stream, ptr(alpha), ptr(alpha_d),
+                                                       ptr(elog), ldo, epi, ptr(maskbits), ptr(o_hi), ptr(o_lo), ld16, ptr(bound),
+                                                       ptr(o_scale), stream), "tx_gat_fused_fwd")
                     out16 = F16Pair(o_hi, o_lo, o_scale, F_ + pd)
+                elif STAGED_FWD and n > 0:
+                    check(lib.tx_gat_fused_fwd_staged(ptr(ft), F_, ptr(al), ptr(ar), ptr(st.in_ptr), ptr(st.in_src), ptr(st.in_eid),
+                                                      ptr(st.bwd_tiles(D)), n, H, D, cfg.neg_slope, cfg.p_attn, cfg.attn_seed,
+                                                      cfg.attn_stream, ptr(alpha), ptr(alpha_d), ptr(elog), ptr(out), ldo, epi,
+                                                      ptr(maskbits), ptr(out_lo), None, None, 0, None, None, stream),
+                          "tx_gat_fused_fwd_staged")
                 else:
                     check(lib.tx_gat_fused_fwd(ptr(ft), F_, ptr(al), ptr(ar), ptr(st.in_ptr), ptr(st.in_src), ptr(st.in_eid), n, H, D,
                                                cfg.neg_slope, cfg.p_attn, cfg.attn_seed, cfg.attn_stream, ptr(alpha), ptr(alpha_d),

@@ -166,15 +166,23 @@ def test_dropout_mask_is_reproducible_and_calibrated():
 # golden vectors from the unmodified reference
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", CASES)
-@pytest.mark.parametrize("graph_kind", ["egonet_batch", "dgl_batch", "general_kernels"])
+@pytest.mark.parametrize("graph_kind", ["egonet_batch", "dgl_batch", "general_kernels", "first_gen_fused", "staged_fwd", "tf32x3", "cublas"])
 def test_cuda_path_matches_reference_golden(name, graph_kind, monkeypatch):
-    """egonet_batch: closed-form structure + fused kernels; dgl_batch: per-edge construction + GPU CSR build + fused
-    kernels; general_kernels: the general-CSR kernels (fused path disabled)."""
+    """egonet_batch: closed-form structure + default kernels (TMA-staged fused backward, fp16-split GEMMs); dgl_batch: per-edge
+    construction + GPU CSR build; general_kernels: the general-CSR kernels (fused path disabled); first_gen_fused: the
+    warp-per-row fused backward instead of the staged one; staged_fwd: the opt-in TMA-staged forward; tf32x3 / cublas: the other
+    dense backends."""
     cfg, og, x, qf, params, fx = load_case(name)
     model = build_model(cfg, params)
     model.train()     # dropout rates 0: exercises the training graph exactly like the golden run
     if graph_kind == "general_kernels":
         monkeypatch.setattr(txf, "FUSED_ENABLED", False)
+    elif graph_kind == "first_gen_fused":
+        monkeypatch.setattr(txf, "STAGED_BWD", False)
+    elif graph_kind == "staged_fwd":
+        monkeypatch.setattr(txf, "STAGED_FWD", True)
+    elif graph_kind in ("tf32x3", "cublas"):
+        monkeypatch.setattr(txf, "GEMM_BACKEND", graph_kind)
     if graph_kind != "dgl_batch":
         g = tx.EgonetBatch.from_counts(fx["n_gp"], fx["n_sib"])
     else:
