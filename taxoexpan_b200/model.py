@@ -66,6 +66,8 @@ class TaxoExpan(BaseModel):
 
     def forward(self, g, h, qf):
         """model/model.py:70-87: scores[G,1] of each egonet in batched graph g against its query feature."""
+        if h.shape[0] == 0:          # empty batch (the reference cannot build one: dgl.batch([]) fails): nothing to score
+            return h.new_zeros((0, 1))
         pos = g.ndata['pos'].to(h.device)
         g.ndata['h'] = self.graph_propagate(g, h)
         hg = self.readout(g, pos)

@@ -315,6 +315,82 @@ def test_general_graph_gat_and_gcn_layers_match_oracle():
             assert float((v.grad.cpu() - r).abs().max()) <= bound, (pm, k)
 
 
+def _random_batched_graph(sizes, rng, edge_factor=2.0):
+    """Disjoint union of random multigraphs (self loops, duplicate edges, nodes without in-edges) with the given sizes."""
+    srcs, dsts, off = [], [], 0
+    n_e = []
+    for nn in sizes:
+        e = max(1, int(edge_factor * nn))
+        srcs.append(torch.from_numpy(rng.integers(0, nn, e)) + off)
+        dsts.append(torch.from_numpy(rng.integers(0, nn, e)) + off)
+        n_e.append(e)
+        off += nn
+    n = off
+    pos = torch.from_numpy(rng.integers(0, 3, n))
+    return n, torch.cat(srcs), torch.cat(dsts), pos, n_e
+
+
+@pytest.mark.parametrize("staged", [True, False])
+def test_batched_general_graphs_exercise_every_tile_mode_of_the_fused_kernels(staged, monkeypatch):
+    """PGAT (2 heads x 500: the shared-memory ring of the staged backward holds 53 row pairs) on a batch of random multigraphs
+    whose sizes force every staging mode: small tiles (g + ft staged), tiles with a 54..80-row graph (ft then g staged), graphs
+    too large for the tile metadata (global-memory path), single-node graphs, and tiles with more edges than the metadata holds."""
+    monkeypatch.setattr(txf, "STAGED_BWD", staged)
+    rng = np.random.default_rng(7)
+    sizes = [1, 3, 17, 60, 2, 75, 8, 110, 1, 1, 33, 52, 54, 5, 95, 20, 70, 4, 40, 41]
+    n, src, dst, pos, n_e = _random_batched_graph(sizes, rng)
+    # one dense small graph: 30 nodes, 400 edges (> 160 edges in a tile: metadata overflow with few rows)
+    dsrc, ddst = torch.from_numpy(rng.integers(0, 30, 400)) + n, torch.from_numpy(rng.integers(0, 30, 400)) + n
+    src, dst, pos = torch.cat([src, dsrc]), torch.cat([dst, ddst]), torch.cat([pos, torch.from_numpy(rng.integers(0, 3, 30))])
+    sizes, n_e, n = sizes + [30], n_e + [400], n + 30
+    og = orc.OracleGraph(n, src, dst, pos, list(sizes), list(n_e))
+    d = 40
+    cfg = orc.OracleConfig(propagation_method="PGAT", readout_method="WMR", matching_method="BIM", in_dim=d, hidden_dim=500,
+                           out_dim=500, pos_dim=12, num_layers=1, heads=[2, 1])
+    params = orc.init_model_params(cfg, seed=11)
+    x = torch.from_numpy(tx.synth.unit_rows(n, d, seed=5))
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    h = x.clone().requires_grad_(True)
+    captured = capture_hidden_outputs(monkeypatch)
+    model = build_model(cfg, params).train()
+    g = tx.DGLGraph()
+    g.add_nodes(n, {"pos": pos.clone()})
+    g.add_edges(src, dst)
+    g.batch_num_nodes = list(sizes)
+    hc = x.to(dev()).requires_grad_(True)
+    out = model.graph_propagate(g, hc)
+    w = torch.from_numpy(tx.synth.unit_rows(n, out.shape[1], seed=6))
+    (out * w.to(dev())).sum().backward()
+    ref = orc.propagate(cfg, og, h, p, masks=branch_pins(cfg, captured))
+    (ref * w).sum().backward()
+    assert float((out.detach().cpu() - ref.detach()).abs().max()) <= TOL
+    assert float((hc.grad.cpu() - h.grad).abs().max()) <= GTOL * float(h.grad.abs().max())
+    gscale = max(float(v.grad.abs().max()) for k, v in p.items() if k.startswith("graph_propagate") and v.grad is not None)
+    for k, v in model.named_parameters():
+        if k.startswith("graph_propagate"):
+            r = p[k].grad
+            assert float((v.grad.cpu() - r).abs().max()) <= GTOL * max(float(r.abs().max()), 5e-2 * gscale), k
+
+
+def test_degenerate_batches():
+    """An empty batch, a batch of single-node egonets (root anchors without siblings, dataset.py:251) and one maximal egonet."""
+    cfg = orc.OracleConfig(**MAGCS)
+    params = orc.init_model_params(cfg, seed=3)
+    model = build_model(cfg, params).train()
+    # empty batch: no nodes, no graphs
+    g0 = tx.EgonetBatch.from_counts([], [])
+    s0 = model(g0, torch.zeros(0, cfg.in_dim, device=dev()), torch.zeros(0, cfg.in_dim, device=dev()))
+    assert tuple(s0.shape) == (0, 1)
+    for n_gp, n_sib in (([0] * 32, [0] * 32), ([8, 1], [50, 2]), ([0, 8, 0, 1], [50, 0, 0, 50])):
+        model.zero_grad(set_to_none=True)
+        og = orc.batch_star_egonets(n_gp, n_sib)
+        x = torch.from_numpy(tx.synth.unit_rows(og.n, cfg.in_dim, seed=1))
+        qf = torch.from_numpy(tx.synth.unit_rows(og.num_graphs, cfg.in_dim, seed=2))
+        got = run_cuda(model, tx.EgonetBatch.from_counts(n_gp, n_sib), x, qf, 1)
+        ref = run_oracle(cfg, og, x, qf, params, 1)
+        assert_close(got, ref, TOL, GTOL, what=f"{n_gp}/{n_sib}: ")
+
+
 def test_standalone_layers_follow_reference_signatures():
     """GATLayer.forward(g, feature) -> [N, H, D'] and GCNLayer.forward(g, h) -> [N, out] (model_zoo.py:34,80)."""
     og = orc.batch_star_egonets([1, 0, 2], [3, 0, 5])
