@@ -241,7 +241,8 @@ def run_b200(args, rank, world, local_rank):
             ev.record(copy_stream)
         return g, x, qf, ev
 
-    e2e_state = {"next": None, "loss": None}
+    e2e_state = {"next": None, "pending": []}
+    loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(4)]     # pinned landing slots of the per-step loss
 
     host_t = {"prefetch": 0.0, "fwd_bwd": 0.0, "item": 0.0, "n": 0}
 
@@ -255,18 +256,26 @@ def run_b200(args, rank, world, local_rank):
         for t in (x, qf, g._staged):
             t.record_stream(main_stream)
         t1 = time.perf_counter()
-        prev = e2e_state["loss"]
-        e2e_state["loss"] = fwd_bwd(g, x, qf)
+        loss = fwd_bwd(g, x, qf)
+        slot = loss_host[i % 4]
+        slot.copy_(loss.detach(), non_blocking=True)             # D2H of this step's result, every step, asynchronously ...
+        ev_l = torch.cuda.Event()
+        ev_l.record(main_stream)
+        e2e_state["pending"].append((slot, ev_l))
         t2 = time.perf_counter()
-        if prev is not None:
-            prev.item()                                          # D2H read of the previous step's result (keeps the CPU one step ahead)
+        if len(e2e_state["pending"]) > 2:                        # ... and read on the host two steps later (a logging loop that blocks on the
+            s_old, e_old = e2e_state["pending"].pop(0)           # previous step's loss serialises host enqueue and GPU work: measured +0.5 ms/step)
+            e_old.synchronize()
+            float(s_old)
         t3 = time.perf_counter()
         host_t["prefetch"] += t1 - t0; host_t["fwd_bwd"] += t2 - t1; host_t["item"] += t3 - t2; host_t["n"] += 1
 
     def e2e_flush():
-        if e2e_state["loss"] is not None:
-            e2e_state["loss"].item()
-        e2e_state["next"] = e2e_state["loss"] = None
+        for s_old, e_old in e2e_state["pending"]:
+            e_old.synchronize()
+            float(s_old)
+        e2e_state["pending"] = []
+        e2e_state["next"] = None
 
     def barrier():
         if world > 1:
@@ -310,6 +319,20 @@ def run_b200(args, rank, world, local_rank):
     e2e_ms, _, _ = timed(step_e2e, args.steps, flush=e2e_flush)
     e2e_host = {k: round(v / max(host_t["n"], 1) * 1e3, 4) for k, v in host_t.items() if k != "n"}   # host ms per step by phase
     clocks = sampler.stop() if rank == 0 else None
+
+    # isolated host->device bandwidth of the pinned feature buffer (explains e2e: the 45.6 MB/step copy runs on its own stream one
+    # step ahead, so e2e = max(GPU step, H2D time) whenever the host keeps up)
+    torch.cuda.synchronize()
+    hx = batches[0]["x_host"]
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(copy_stream):
+        hx.to(dev, non_blocking=True)
+        c0.record(copy_stream)
+        for _ in range(5):
+            hx.to(dev, non_blocking=True)
+        c1.record(copy_stream)
+    torch.cuda.synchronize()
+    h2d_gbs = 5 * hx.numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
 
     # totals over ranks
     egonets = torch.tensor([sum(batches[i % nb]["shapes"].num_graphs for i in range(args.steps))], device=dev, dtype=torch.float64)
@@ -395,7 +418,8 @@ def run_b200(args, rank, world, local_rank):
                    "dense": {"f16x3": "tcgen05 kind::f16 on fp16 hi/lo operand pairs, 3 MMAs per product (tx_gemm.cu), fp32-faithful",
                              "tf32x3": "tcgen05 3xTF32 (tx_gemm.cu), fp32-faithful"}.get(txf.GEMM_BACKEND, "torch.mm (cuBLAS fp32, TF32 off)")},
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": x_bytes, "d2h_bytes_per_step": 4,
-                "ms_per_step": round(e2e_ms / args.steps, 4), "host_ms_per_step": e2e_host},
+                "ms_per_step": round(e2e_ms / args.steps, 4), "host_ms_per_step": e2e_host,
+                "h2d_gb_per_s_isolated": round(h2d_gbs, 2), "h2d_ms_per_step_at_that_rate": round(x_bytes / h2d_gbs / 1e6, 4)},
         "gpu_launches": launches,
         "host_enqueue_ms_per_step": round(host_enqueue_ms, 4),
         "clocks": clocks,

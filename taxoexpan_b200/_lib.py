@@ -144,6 +144,11 @@ class Stats:
 class timed_region:
     """`with timed_region("mm", tag):` records CUDA events around non-ABI work (cuBLAS GEMMs) when profiling."""
 
+    def __new__(cls, name, tag=None):
+        if not Stats.profiling:
+            return _NULL                      # nothing to record: no object, no event bookkeeping
+        return super().__new__(cls)
+
     def __init__(self, name, tag=None):
         self.name, self.tag = name, tag
 
@@ -213,8 +218,31 @@ def check(rc: int, what: str):
 
 
 def ptr(t):
-    """Device pointer of a torch tensor (or None)."""
-    return None if t is None else c_void_p(t.data_ptr())
+    """Device pointer of a torch tensor (or None) as a plain int (ctypes converts it for the c_void_p parameters)."""
+    return None if t is None else t.data_ptr()
+
+
+class _NullContext:
+    __slots__ = ()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL = _NullContext()
+
+
+def device_guard(device):
+    """`with device_guard(t.device):` - torch.cuda.device(...) only when the tensor does not live on the current device (the context
+    manager costs ~10 us and every autograd Function entered one or two of them per call)."""
+    import torch
+    idx = device.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NULL
+    return torch.cuda.device(device)
 
 
 _raw_stream = None

@@ -17,7 +17,7 @@ import torch
 from torch.autograd import Function
 
 from . import _lib
-from ._lib import GatEpilogue, Stats, check, current_stream, ptr, timed_region
+from ._lib import GatEpilogue, Stats, check, current_stream, device_guard, ptr, timed_region
 from .graph import GraphStructure
 
 _NEG_SLOPE_NONE = 1.0
@@ -363,7 +363,7 @@ def dropout_keep_mask(seed: int, stream_id: int, first_index: int, n: int, p: fl
     """The exact keep-mask (uint8, 1 = keep) the kernels use; lets the CPU oracle replay a dropout run."""
     lib = _lib.load()
     keep = torch.empty(n, dtype=torch.uint8, device=device)
-    with torch.cuda.device(keep.device):
+    with device_guard(keep.device):
         check(lib.tx_dropout_keep_mask(seed, stream_id, first_index, n, p, ptr(keep), current_stream()), "tx_dropout_keep_mask")
     return keep
 
@@ -383,7 +383,7 @@ class ConcatPosDropout(Function):
         ldz = round4(k_in + pd)
         z = torch.empty((n, ldz), dtype=torch.float32, device=x.device)
         tab = None if pos_table is None else pos_table.contiguous()
-        with torch.cuda.device(x.device):
+        with device_guard(x.device):
             check(lib.tx_concat_pos_dropout_fwd(ptr(x), x.stride(0) if n > 1 else k_in, ptr(tab), ptr(pos32), n, k_in, pd,
                                                 ptr(z), ldz, p, seed, stream_id, current_stream()),
                   "tx_concat_pos_dropout_fwd")
@@ -404,7 +404,7 @@ class ConcatPosDropout(Function):
         if not need_x:
             # x carries no gradient (the usual case, trainer.py:48): only d(position table) = sum over rows of the kept,
             # rescaled position columns is needed - one read of [N, pos_dim] instead of a rescale of the whole d(z)
-            with torch.cuda.device(dz.device):
+            with device_guard(dz.device):
                 nb = int(lib.tx_row_blocks(n))
                 partial = torch.empty(nb * vocab * pd, dtype=torch.float32, device=dz.device)
                 check(lib.tx_pos_grad_partials(ptr(dz), dz.stride(0) if n > 1 else ldz, k_in, ptr(pos32), n, pd, vocab, p, seed, stream_id,
@@ -413,7 +413,7 @@ class ConcatPosDropout(Function):
             return None, dtab, None, None, None, None
         if p > 0.0:
             dz = dz.clone()      # the kernel rescales the kept entries in place; never touch the caller's grad
-        with torch.cuda.device(dz.device):
+        with device_guard(dz.device):
             nb = int(lib.tx_row_blocks(n))
             partial = torch.empty(nb * vocab * pd, dtype=torch.float32, device=dz.device) if need_tab else None
             # with p == 0 and no activation the kernel's feature pass is a no-op (dz is only read)
@@ -474,7 +474,7 @@ class GatLayer(Function):
         F_ = H * D
         dev = z.device
         f32 = dict(dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with device_guard(dev):
             stream = current_stream()
             Stats.tag = cfg.tag
             f16 = GEMM_BACKEND == "f16x3"
@@ -575,7 +575,7 @@ class GatLayer(Function):
         dev = ft.device
         f32 = dict(dtype=torch.float32, device=dev)
         dtab = None
-        with torch.cuda.device(dev):
+        with device_guard(dev):
             stream = current_stream()
             Stats.tag = cfg.tag
             dout = _rowmajor(dout)
@@ -700,7 +700,7 @@ class GcnLayer(Function):
         D, K = cfg.dim, cfg.k
         dev = z.device
         f32 = dict(dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with device_guard(dev):
             stream = current_stream()
             Stats.tag = cfg.tag
             with timed_region("gemm_fwd"):
@@ -734,7 +734,7 @@ class GcnLayer(Function):
         dev = norm.device
         f32 = dict(dtype=torch.float32, device=dev)
         dtab = db = None
-        with torch.cuda.device(dev):
+        with device_guard(dev):
             stream = current_stream()
             dout = _rowmajor(dout)
             ldg = dout.stride(0) if n > 1 else dout.shape[1]
@@ -775,7 +775,7 @@ class DenseRight(Function):
     @staticmethod
     def forward(ctx, a, w):
         _check_cuda(a, "a")
-        with torch.cuda.device(a.device):
+        with device_guard(a.device):
             m, l = a.shape
             r = w.shape[1]
             ap = split_f16(a, l)
@@ -790,7 +790,7 @@ class DenseRight(Function):
         a_hi, a_lo, a_sc, w_hi, w_lo, w_sc = ctx.saved_tensors
         m, l, r = ctx.dims
         da = dw = None
-        with torch.cuda.device(dy.device):
+        with device_guard(dy.device):
             dp = split_f16(_rowmajor(dy), r)
             if ctx.needs_input_grad[0]:
                 da = gemm_nt_f16(dp, r, F16Pair(w_hi, w_lo, w_sc, r), l)
@@ -821,7 +821,7 @@ class Readout(Function):
         width = 3 * D if kind == _lib.TX_READOUT_CONCAT else D
         hg = torch.empty((st.g, width), dtype=torch.float32, device=h.device)
         w = None if pos_weight is None else pos_weight.reshape(-1).contiguous()
-        with torch.cuda.device(h.device):
+        with device_guard(h.device):
             check(lib.tx_readout_fwd(kind, ptr(h), h.stride(0) if n > 1 else D, ptr(pos32), ptr(w), ptr(st.node_off), st.g, D,
                                      ptr(hg), width, current_stream()), "tx_readout_fwd")
         ctx.st, ctx.kind = st, kind
@@ -838,7 +838,7 @@ class Readout(Function):
         dhg = _rowmajor(dhg)
         dh = torch.empty((n, D), dtype=torch.float32, device=h.device)
         dw = None
-        with torch.cuda.device(h.device):
+        with device_guard(h.device):
             need_w = kind == _lib.TX_READOUT_WMEAN and ctx.needs_input_grad[1]
             nbr = int(lib.tx_readout_bwd_blocks(st.g))
             partial = torch.empty(nbr * 3, dtype=torch.float32, device=h.device) if need_w else None
