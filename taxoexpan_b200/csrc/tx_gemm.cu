@@ -462,14 +462,16 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
   constexpr int BOX_BYTES = BKE * 128;
   constexpr int SL = BN / 4;                              // columns drained / stored by one epilogue warp (4 warps per TMEM lane quadrant)
   static_assert(BN % 128 == 0, "the pair kernel's 16 epilogue warps take BN / 4 columns each, in chunks of 32");
-  constexpr uint32_t TMEM_COLS = 2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512));
+  constexpr uint32_t TMEM_COLS = 512;
+  constexpr int NBUF = 512 / BN;                          // accumulator buffers in TMEM: 2 (BN = 256) or 4 (BN = 128).  With 4 the MMA
+                                                          // stream can run a whole short-K tile ahead of an epilogue that is stuck in its stores
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * NBUF);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
-  const uint32_t tfull0 = smem_u32(bars + 2 * STAGES), tempty0 = smem_u32(bars + 2 * STAGES + 2);
+  const uint32_t tfull0 = smem_u32(bars + 2 * STAGES), tempty0 = smem_u32(bars + 2 * STAGES + NBUF);
   const uint32_t crank = cluster_ctarank();
   const bool leader = crank == 0;
 
@@ -482,7 +484,7 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < NBUF; ++b) {
       mbar_init(tfull0 + 8 * b, 1);
       mbar_init(tempty0 + 8 * b, 32);          // 16 epilogue warps of each CTA of the pair
     }
@@ -555,8 +557,8 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
       work_coords(w, m0, n0, kb0, nkb, z);
       const int n_chunks = (nkb + kChunk - 1) / kChunk;
       for (int ch = 0; ch < n_chunks; ++ch, ++gch) {
-        const int buf = gch & 1;
-        mbar_wait(tempty0 + 8 * buf, ((gch >> 1) & 1) ^ 1);
+        const int buf = gch % NBUF;
+        mbar_wait(tempty0 + 8 * buf, ((gch / NBUF) & 1) ^ 1);
         tcgen05_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
         const int kb_end = min(nkb, (ch + 1) * kChunk);
@@ -602,8 +604,8 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
 #pragma unroll
     for (int c = 0; c < SL; ++c) acc[c] = 0.f;
     for (int ch = 0; ch < n_chunks; ++ch, ++gch) {
-      const int buf = gch & 1;
-      mbar_wait(tfull0 + 8 * buf, (gch >> 1) & 1);
+      const int buf = gch % NBUF;
+      mbar_wait(tfull0 + 8 * buf, (gch / NBUF) & 1);
       tcgen05_fence_after();
       const uint32_t tacc = tmem_base + (uint32_t)(buf * BN + hsel * SL) + ((uint32_t)(q * 32) << 16);
 #pragma unroll
@@ -1245,8 +1247,15 @@ int tx_gemm_nt_f16x3(const void* a_hi, const void* a_lo, int64_t lda, const void
     epi.on = 1.f / (1.f - e->p_drop); epi.neg = e->act_slope * epi.on;
   }
   if (amax_out && cudaMemsetAsync(amax_out, 0, sizeof(float), st) != cudaSuccess) { set_error("gemm_f16: memset failed"); return TX_ERR_CUDA; }
-  if (use_pair() && m > kBM && n > 128 && pick_bn(n) == 256)
+  if (use_pair() && m > kBM && n > 128 && pick_bn(n) == 256) {
+    // experiment knob: 128-wide tiles leave room for 4 accumulator buffers in TMEM, so the MMA stream can run a whole short-K tile
+    // ahead of the epilogue.  Measured on the two wide-output GEMMs (K = 300 / 500): no gain (0.226 vs 0.229 ms, 0.290 vs 0.262 ms),
+    // so it is off unless TAXO_GEMM_NARROW_K=<K limit> asks for it
+    static int narrow_k = -1;
+    if (narrow_k < 0) { const char* e_n = getenv("TAXO_GEMM_NARROW_K"); narrow_k = e_n ? atoi(e_n) : 0; }
+    if (k <= narrow_k) return launch_gemm_pair<128, 4, false, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
     return launch_gemm_pair<256, 3, false, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
+  }
   if (use_cluster() && m > kBM && n > 128) {
     if (pick_bn(n) == 160) return launch_gemm<160, 3, false, 32, 2, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
     return launch_gemm<256, 2, false, 32, 2, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
