@@ -36,11 +36,36 @@ NEGATIVE_SIZE = 31                                                              
 
 
 def load_peaks():
+    """(HBM GB/s, bf16 TFLOP/s, source).  MEASURED_PEAKS.json is written by the driver; its key names are not part of any contract
+    here, so any numeric entry whose key mentions hbm / bandwidth (resp. bf16 / tflop) is accepted, nested dicts included."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm = tf = None
     if os.path.exists(path):
-        with open(path) as f:
-            d = json.load(f)
-        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1400.0))), "measured (MEASURED_PEAKS.json)"
+        try:
+            with open(path) as f:
+                d = json.load(f)
+        except (OSError, ValueError):
+            d = {}
+
+        def walk(obj, prefix=""):
+            if isinstance(obj, dict):
+                for k, v in obj.items():
+                    yield from walk(v, f"{prefix}.{k}".lower())
+            elif isinstance(obj, (int, float)) and not isinstance(obj, bool):
+                yield prefix, float(obj)
+
+        items = list(walk(d))
+        for key, val in items:
+            if hbm is None and ("hbm" in key or "bandwidth" in key or "copy" in key) and 500.0 < val < 20000.0:
+                hbm = val
+            if ("bf16" in key or "tflop" in key or "tensor" in key) and 100.0 < val < 5000.0:
+                if tf is None or "sustain" in key:
+                    tf = val
+        for key, val in items:          # bandwidth given in TB/s
+            if hbm is None and ("hbm" in key or "bandwidth" in key) and 0.5 < val < 20.0:
+                hbm = val * 1000.0
+    if hbm is not None:
+        return hbm, (tf if tf is not None else 1400.0), "measured (MEASURED_PEAKS.json)"
     return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
 
 

@@ -442,3 +442,27 @@ def random_keep_masks(cfg: OracleConfig, g: OracleGraph, seed=0):
             masks[f"feat.{l}"] = torch.rand((g.n, k), generator=gen) >= p
             k = cfg.hidden_dim + pd
     return masks
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# evaluation: rank of every true position of a query among all candidate positions
+# ---------------------------------------------------------------------------------------------------------------------
+def ranks_from_similarities(all_similarities: np.ndarray, positive_relations) -> List[int]:
+    """reference model/metric.py:7-19: rank of each true position = 1 + number of NON-true positions with a strictly larger
+    similarity (the true positions themselves are masked out)."""
+    all_similarities = np.asarray(all_similarities)
+    pos = np.asarray(list(positive_relations), dtype=np.int64)
+    neg_mask = np.ones(all_similarities.shape[0], dtype=bool)
+    neg_mask[pos] = False
+    neg = all_similarities[neg_mask]
+    return [int((neg > all_similarities[p]).sum()) + 1 for p in pos]
+
+
+def all_pairs_ranks(cfg: "OracleConfig", hg, queries, params, positives) -> List[List[int]]:
+    """reference test_fast.py:187-218: for every query, score it against every position with model.match on the expanded query
+    feature, then rank its true positions (similarity mode, used with the InfoNCE loss)."""
+    out = []
+    for j in range(queries.shape[0]):
+        scores = match(cfg, hg, queries[j:j + 1].expand(hg.shape[0], -1), params).reshape(-1).detach().numpy()
+        out.append(ranks_from_similarities(scores, positives[j]))
+    return out

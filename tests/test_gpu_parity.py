@@ -445,3 +445,42 @@ def test_full_size_properties_magcs_batch256():
     pos = graph.host_pos()
     hg = model.readout(graph, pos)
     assert float((hg.detach() - 3.0).abs().max()) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# all-pairs inference scoring (reference test_fast.py:93-218, metric.py:7-60)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mm", ["LBM", "BIM", "MLP"])
+def test_all_pairs_scoring_and_ranks_match_the_reference_loop(mm):
+    cfg = orc.OracleConfig(**dict(MAGCS, matching_method=mm))
+    params = orc.init_model_params(cfg, seed=21)
+    model = build_model(cfg, params).eval()
+    rng = np.random.default_rng(5)
+    shapes = tx.synth.sample_shapes(20, 31, "mag-cs", seed=17)           # 640 candidate positions, encoded in 3 chunks
+    n_gp, n_sib = np.asarray(shapes.n_gp), np.asarray(shapes.n_sib)
+    og = orc.batch_star_egonets(n_gp, n_sib)
+    x = torch.from_numpy(tx.synth.unit_rows(og.n, cfg.in_dim, seed=1))
+    n_per = n_gp + 1 + n_sib
+    off = np.concatenate([[0], np.cumsum(n_per)])
+    bounds = [0, 250, 500, len(n_gp)]
+    batches = [(tx.EgonetBatch.from_counts(n_gp[a:b], n_sib[a:b]), x[off[a]:off[b]].to(dev())) for a, b in zip(bounds[:-1], bounds[1:])]
+    hg = tx.inference.encode_positions(model, batches)
+    with torch.no_grad():
+        hg_ref = orc.readout(cfg, og, orc.propagate(cfg, og, x, params), params)
+    assert float((hg.cpu() - hg_ref).abs().max()) <= TOL
+    P, Q = hg.shape[0], 37
+    queries = torch.from_numpy(tx.synth.unit_rows(Q, cfg.in_dim, seed=9))
+    positives = [sorted(rng.choice(P, size=int(rng.integers(1, 4)), replace=False).tolist()) for _ in range(Q)]
+    res = tx.inference.score_and_rank(model, hg, queries.to(dev()), positives, topk=5, query_chunk=16)
+    with torch.no_grad():
+        ref = orc.all_pairs_ranks(cfg, hg.cpu(), queries, params, positives)
+    # ranks are integers: identical unless two scores are closer than the fp32 tolerance of the scoring path
+    flat = [(a, b) for ra, rb in zip(res["ranks"], ref) for a, b in zip(ra.tolist(), rb)]
+    assert len(flat) == sum(len(p) for p in positives)
+    assert sum(abs(a - b) for a, b in flat) <= 2 and max(abs(a - b) for a, b in flat) <= 1
+    for j in (0, Q - 1):
+        with torch.no_grad():
+            s = orc.match(cfg, hg.cpu(), queries[j:j + 1].expand(P, -1), params).reshape(-1)
+        top_ref = torch.topk(s, 5)
+        assert top_ref.indices.tolist() == res["topk_idx"][j].tolist()
+        assert float((top_ref.values - res["topk_score"][j]).abs().max()) <= 1e-5 * max(1.0, float(top_ref.values.abs().max()))

@@ -63,3 +63,15 @@ def test_vectorised_batch_equals_per_graph_construction():
     assert np.array_equal(np.diff(noff), np.asarray(og.batch_num_nodes))
     assert np.array_equal(np.diff(eoff), np.asarray(og.batch_num_edges))
     assert shapes.total_nodes == og.n and shapes.total_edges == og.src.numel()
+
+
+def test_rank_restatement_matches_its_definition():
+    """oracle.ranks_from_similarities (metric.py:7-19) against the definition, ties and multiple true positions included."""
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        n = int(rng.integers(2, 40))
+        s = rng.integers(0, 6, n).astype(np.float64)          # many ties
+        pos = rng.choice(n, size=int(rng.integers(1, min(4, n))), replace=False).tolist()
+        got = orc.ranks_from_similarities(s, pos)
+        want = [1 + sum(1 for i in range(n) if i not in pos and s[i] > s[p]) for p in pos]
+        assert got == want
