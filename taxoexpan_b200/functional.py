@@ -75,9 +75,6 @@ def use_fused(lib, heads: int, dim: int, mean_heads: int, st=None) -> bool:
 GEMM_BACKEND = os.environ.get("TAXO_GEMM", "f16x3")
 
 
-def _tc_backend() -> bool:
-    return GEMM_BACKEND in ("tf32x3", "f16x3")
-
 
 def split_tf32(x: torch.Tensor, cols: int = None):
     """x [rows, >=cols] -> (hi, lo) padded [rows, round4(cols)] TF32-representable parts with x = hi + lo (+ 2^-22 rel.)."""
