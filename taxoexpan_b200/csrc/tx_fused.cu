@@ -585,12 +585,23 @@ __global__ void __launch_bounds__(256) pos_grad_partials_kernel(const float* __r
 #pragma unroll
     for (int v = 0; v < kMaxVocab; ++v) acc[v] = 0.f;
     if (c < pd) {
-      for (int i = r0 + rg; i < r1; i += 4) {
-        float g = __ldg(dz + (int64_t)i * ldz + col0 + c);
-        if (thr) g = drop_keep1(seed, stream_id, (uint64_t)((int64_t)i * ldz + col0 + c), thr) ? g * inv_keep : 0.f;
-        const int r = __ldg(pos + i);
+      for (int i0 = r0 + rg; i0 < r1; i0 += 16) {        // 4 rows per step: their loads are issued together
+        float gv[4];
+        int rv[4];
 #pragma unroll
-        for (int v = 0; v < kMaxVocab; ++v) acc[v] += (r == v) ? g : 0.f;
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + 4 * u;
+          gv[u] = i < r1 ? __ldg(dz + (int64_t)i * ldz + col0 + c) : 0.f;
+          rv[u] = i < r1 ? __ldg(pos + i) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + 4 * u;
+          float g = gv[u];
+          if (thr && i < r1) g = drop_keep1(seed, stream_id, (uint64_t)((int64_t)i * ldz + col0 + c), thr) ? g * inv_keep : 0.f;
+#pragma unroll
+          for (int v = 0; v < kMaxVocab; ++v) acc[v] += (rv[u] == v) ? g : 0.f;
+        }
       }
     }
     if (rg > 0) {

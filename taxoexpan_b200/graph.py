@@ -26,12 +26,13 @@ class GraphStructure:
     """Device-resident structure of one batched graph (all int32)."""
 
     __slots__ = ("device", "n", "e", "g", "in_ptr", "in_src", "in_eid", "out_ptr", "out_dst", "out_slot", "node_off",
-                 "pos", "src", "dst", "max_nodes", "max_out_deg", "_norm", "is_star", "_bwd_tiles")
+                 "pos", "src", "dst", "max_nodes", "max_out_deg", "_norm", "is_star", "_bwd_tiles", "_dh_bound")
 
     def __init__(self, device):
         self.device = device
         self._norm = None
         self._bwd_tiles = {}
+        self._dh_bound = None      # (data_ptr of the readout's d(h), device bound of max|d(h)|): hand-over to the output layer's backward
         self.max_out_deg = 0       # host-side upper bound of the largest out-degree (bounds |dft| for the fp16-split GEMM operands)
         self.pos = None
         self.src = self.dst = None
