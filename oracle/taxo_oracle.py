@@ -466,3 +466,25 @@ def all_pairs_ranks(cfg: "OracleConfig", hg, queries, params, positives) -> List
         scores = match(cfg, hg, queries[j:j + 1].expand(hg.shape[0], -1), params).reshape(-1).detach().numpy()
         out.append(ranks_from_similarities(scores, positives[j]))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# egonet construction (the data layer's format spec for the kernels' input)
+# ---------------------------------------------------------------------------------------------------------------------
+def get_subgraph_nodes(parents_of, children_of, query_node, anchor_node, instance_mode, expand_factor=50, rng=None):
+    """reference data_loader/dataset.py:404-426 (`_get_subgraph`) for ONE egonet: (node ids, positions) in the reference's node
+    order.  parents_of / children_of: dict node -> list in edge order (networkx in_edges / out_edges)."""
+    import random
+    rng = rng or random
+    nodes = list(parents_of.get(anchor_node, []))
+    pos = [0] * len(nodes)
+    nodes.append(anchor_node)
+    pos.append(1)
+    kids = list(children_of.get(anchor_node, []))
+    if len(kids) > expand_factor:
+        kids = rng.choices(kids, k=expand_factor)
+    if instance_mode == 1:
+        kids = [k for k in kids if k != query_node]
+    nodes.extend(kids)
+    pos.extend([2] * len(kids))
+    return nodes, pos

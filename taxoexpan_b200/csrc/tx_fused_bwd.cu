@@ -31,7 +31,10 @@
 
 namespace tx {
 
-constexpr int kCW = 12;                  // compute warps
+#ifndef TX_BWD_CW
+#define TX_BWD_CW 12
+#endif
+constexpr int kCW = TX_BWD_CW;           // compute warps
 constexpr int kPW = 4;                   // producer warps (16 warps = 4 per scheduler -> 128 registers each)
 constexpr int kCT = kCW * 32;            // compute threads (D = 500: 3 row groups x 125 float4 columns = 375 of 384 busy in phase B)
 constexpr int kBwdThreads = kCT + kPW * 32;

@@ -484,3 +484,36 @@ def test_all_pairs_scoring_and_ranks_match_the_reference_loop(mm):
         top_ref = torch.topk(s, 5)
         assert top_ref.indices.tolist() == res["topk_idx"][j].tolist()
         assert float((top_ref.values - res["topk_score"][j]).abs().max()) <= 1e-5 * max(1.0, float(top_ref.values.abs().max()))
+
+
+# ------------------------------------------------------------------------------------------------
+# vectorised egonet construction on the GPU feeding the model
+# ------------------------------------------------------------------------------------------------
+def test_gpu_built_egonet_batch_matches_the_per_egonet_reference_construction():
+    from tests.test_sampler_cpu import _random_taxonomy
+    rng = np.random.default_rng(11)
+    n = 500
+    par, chi, parents_of, children_of = _random_taxonomy(n, 1400, rng)
+    tax = tx.sampler.TaxonomyCSR.from_edges(par, chi, n).to(dev())
+    cfg = orc.OracleConfig(**dict(MAGCS, in_dim=24, hidden_dim=16, out_dim=12, pos_dim=4, heads=[2, 1]))
+    params = orc.init_model_params(cfg, seed=4)
+    model = build_model(cfg, params).eval()
+    feats = torch.from_numpy(tx.synth.unit_rows(n, cfg.in_dim, seed=3))
+    G = 64
+    anchors, modes = rng.integers(0, n, G), rng.integers(0, 2, G)
+    queries = np.array([rng.choice(children_of[a]) if (m == 1 and a in children_of) else rng.integers(0, n) for a, m in zip(anchors, modes)])
+    bg, x, ids = tx.sampler.build_egonet_batch(tax, feats.to(dev()), anchors, queries, modes, expand_factor=50)
+    # the reference construction, one egonet at a time (dataset.py:404-437)
+    nodes_all, n_gp, n_sib = [], [], []
+    for a, q, m in zip(anchors.tolist(), queries.tolist(), modes.tolist()):
+        nodes, pos = orc.get_subgraph_nodes(parents_of, children_of, q, a, m, expand_factor=50)
+        nodes_all += nodes
+        n_gp.append(pos.count(0))
+        n_sib.append(pos.count(2))
+    assert ids.cpu().tolist() == nodes_all
+    og = orc.batch_star_egonets(n_gp, n_sib)
+    qf = feats[torch.from_numpy(queries)]
+    with torch.no_grad():
+        scores = model(bg, x, qf.to(dev()))
+        ref, _, _ = orc.taxoexpan_forward(cfg, og, feats[torch.tensor(nodes_all)], qf, params)
+    assert float((scores.cpu() - ref).abs().max()) <= TOL * max(1.0, float(ref.abs().max()))
