@@ -327,6 +327,8 @@ def run_b200(args, rank, world, local_rank):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), Stats.launches, Stats.timings_ms() if profile else {}
 
+    for i in range(nb):          # setup: touch every rotating batch once (its tile table, the allocator's block sizes for its shape);
+        step_resident(i)         # a batch first seen inside the timed region costs a cudaMalloc storm of ~100 ms
     for i in range(max(args.warmup, 3)):
         step_resident(i)
     sampler = ClockSampler(local_rank)
@@ -337,7 +339,7 @@ def run_b200(args, rank, world, local_rank):
 
     # per-kernel CUDA-event timings (separate pass so the headline loop carries no event overhead)
     _, _, prof = timed(step_resident, args.steps, profile=True)
-    for i in range(3):
+    for i in range(max(3, nb)):
         step_e2e(i)
     e2e_flush()
     host_t.update(prefetch=0.0, fwd_bwd=0.0, item=0.0, n=0)
