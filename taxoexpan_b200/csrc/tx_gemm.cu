@@ -443,7 +443,7 @@ __device__ __forceinline__ void mbar_arrive_cta0(uint32_t bar) {   // arrive on 
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
-template <int BN, int STAGES, bool TN, bool F16>
+template <int BN, int STAGES, bool TN, bool F16, bool SLAB>
 __global__ void __launch_bounds__(kPairThreads, 1)
 gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                         const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -469,6 +469,7 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * NBUF);
+  float* stg = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);    // SLAB: 16 epilogue warps x [32][36] floats
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
   const uint32_t tfull0 = smem_u32(bars + 2 * STAGES), tempty0 = smem_u32(bars + 2 * STAGES + NBUF);
@@ -634,7 +635,47 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
         }
       }
     }
-    if (row < M) {
+    if constexpr (SLAB) {
+      // Stores through a per-warp shared-memory slab (32 rows x 32 columns, pitch 36 floats: conflict-free both ways).  A thread owns
+      // one ROW of the accumulator, so storing straight from registers makes every STG touch 32 different lines with 16 bytes each
+      // (half sectors); ncu shows the epilogue warps stalled on exactly those stores (the next write of the store's source register
+      // waits until the LSU has drained it).  After the transpose one STG writes 4 rows x 128 contiguous bytes: full lines.
+      float* slab = stg + (warp - 2) * (32 * 36);
+      const int row_base = m0 + q * 32;
+#pragma unroll
+      for (int g2 = 0; g2 < SL / 32; ++g2) {
+        const int colg = n0 + hsel * SL + g2 * 32;
+        if (colg < n_store) {                                     // warp-uniform
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int j = g2 * 8 + u;
+            const int col = colg + u * 4;
+            float4 v = make_float4(acc[4 * j] * inv_scale, acc[4 * j + 1] * inv_scale, acc[4 * j + 2] * inv_scale, acc[4 * j + 3] * inv_scale);
+            if (row < M && col < n_store) {
+              if (masked && col < epi.feat_cols) {
+                uint32_t code = (mw[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+                if (!epi.has_keep) code |= 0xF0u;
+                v.x *= (code & 16u) ? ((code & 1u) ? epi.on : epi.neg) : 0.f;
+                v.y *= (code & 32u) ? ((code & 2u) ? epi.on : epi.neg) : 0.f;
+                v.z *= (code & 64u) ? ((code & 4u) ? epi.on : epi.neg) : 0.f;
+                v.w *= (code & 128u) ? ((code & 8u) ? epi.on : epi.neg) : 0.f;
+              }
+              vmax = fmaxf(vmax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+            }
+            *reinterpret_cast<float4*>(slab + lane * 36 + u * 4) = v;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int rl = 4 * t + (lane >> 3), c4 = lane & 7;
+            const int grow = row_base + rl, col = colg + c4 * 4;
+            if (grow < M && col < n_store)
+              *reinterpret_cast<float4*>(C + (int64_t)z * split_stride + (int64_t)grow * ldc + col) = *reinterpret_cast<const float4*>(slab + rl * 36 + c4 * 4);
+          }
+          __syncwarp();
+        }
+      }
+    } else if (row < M) {
       float* crow = C + (int64_t)z * split_stride + (int64_t)row * ldc + n0 + hsel * SL;
 #pragma unroll
       for (int j = 0; j < SL / 4; ++j) {
@@ -947,7 +988,7 @@ static int launch_gemm(const void* a_hi, const void* a_lo, int64_t lda, const vo
   return TX_OK;
 }
 
-template <int BN, int STAGES, bool TN, bool F16 = false>
+template <int BN, int STAGES, bool TN, bool F16 = false, bool SLAB = false>
 static int launch_gemm_pair(const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi, const void* b_lo, int64_t ldb,
                             float* c, int64_t ldc, int64_t split_stride, int64_t M, int64_t N, int64_t K, int splits, cudaStream_t st,
                             const GemmEpilogue& epi = GemmEpilogue{nullptr, 0, 1, 0, 0, 0, 1.f, 1.f, nullptr, nullptr, nullptr}) {
@@ -970,10 +1011,11 @@ static int launch_gemm_pair(const void* a_hi, const void* a_lo, int64_t lda, con
     if ((rc = make_map(&mb_lo, b_lo, K, N, ldb, BKE, sw, BOXC, F16)) != TX_OK) return rc;
   }
   constexpr int STAGE_BYTES = 2 * kBM * BK * 4 + 2 * (BN / 2) * BK * 4;
-  constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
+  constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256 + (SLAB ? 16 * 32 * 36 * 4 : 0);
+  static_assert(SMEM <= 227 * 1024, "pair kernel: shared memory budget");
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_pair_kernel<BN, STAGES, TN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_pair_kernel<BN, STAGES, TN, F16, SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
     if (e != cudaSuccess) {
       set_error("gemm(pair): cudaFuncSetAttribute(%zu B smem) failed: %s", SMEM, cudaGetErrorString(e));
       return TX_ERR_CUDA;
@@ -1013,7 +1055,7 @@ static int launch_gemm_pair(const void* a_hi, const void* a_lo, int64_t lda, con
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tf32x3_pair_kernel<BN, STAGES, TN, F16>, ma_hi, ma_lo, mb_hi, mb_lo, c, ldc, split_stride,
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tf32x3_pair_kernel<BN, STAGES, TN, F16, SLAB>, ma_hi, ma_lo, mb_hi, mb_lo, c, ldc, split_stride,
                                      (int)M, (int)n_store, kbt, kbs, mn_bits, epi, n_tiles_n, n_m_pairs, n_work, chunk_kb);
   if (e != cudaSuccess) {
     set_error("gemm(pair): cluster launch failed: %s", cudaGetErrorString(e));
@@ -1254,6 +1296,10 @@ int tx_gemm_nt_f16x3(const void* a_hi, const void* a_lo, int64_t lda, const void
     static int narrow_k = -1;
     if (narrow_k < 0) { const char* e_n = getenv("TAXO_GEMM_NARROW_K"); narrow_k = e_n ? atoi(e_n) : 0; }
     if (k <= narrow_k) return launch_gemm_pair<128, 4, false, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
+    // short reductions with wide outputs (fwd L0: K = 300, dz L1: K = 500) are bound by the stores of C: 2-stage ring + store slabs
+    static int slab_k = -1;
+    if (slab_k < 0) { const char* e_s = getenv("TAXO_GEMM_SLAB_K"); slab_k = e_s ? atoi(e_s) : 640; }
+    if (k <= slab_k) return launch_gemm_pair<256, 2, false, true, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
     return launch_gemm_pair<256, 3, false, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
   }
   if (use_cluster() && m > kBM && n > 128) {
