@@ -604,6 +604,18 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
     float acc[SL];
 #pragma unroll
     for (int c = 0; c < SL; ++c) acc[c] = 0.f;
+    // sign / keep bytes of this thread's row: requested before the accumulator chunks arrive, so the loads are off the store path
+    const int row = m0 + q * 32 + lane;
+    uint32_t mw[SL / 16];
+    const bool masked = !TN && epi.mask != nullptr;
+    if (masked && row < M) {
+#pragma unroll
+      for (int w = 0; w < SL / 16; ++w) {
+        const int col = n0 + hsel * SL + w * 16;
+        mw[w] = (col < epi.feat_cols)
+                    ? __ldg(reinterpret_cast<const uint32_t*>(epi.mask + (int64_t)row * epi.stride + (col >> 2))) : 0xFFFFFFFFu;
+      }
+    }
     for (int ch = 0; ch < n_chunks; ++ch, ++gch) {
       const int buf = gch % NBUF;
       mbar_wait(tfull0 + 8 * buf, (gch / NBUF) & 1);
@@ -620,19 +632,6 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
       __syncwarp();
       if (lane == 0) {
         if (leader) mbar_arrive(tempty0 + 8 * buf); else mbar_arrive_cta0(tempty0 + 8 * buf);
-      }
-    }
-    const int row = m0 + q * 32 + lane;
-    uint32_t mw[SL / 16];
-    const bool masked = !TN && epi.mask != nullptr;
-    if (row < M) {
-      if (masked) {
-#pragma unroll
-        for (int w = 0; w < SL / 16; ++w) {
-          const int col = n0 + hsel * SL + w * 16;
-          mw[w] = (col < epi.feat_cols)
-                      ? __ldg(reinterpret_cast<const uint32_t*>(epi.mask + (int64_t)row * epi.stride + (col >> 2))) : 0xFFFFFFFFu;
-        }
       }
     }
     if constexpr (SLAB) {
