@@ -179,27 +179,31 @@ __global__ void __launch_bounds__(256) reduce_partials_wide_kernel(const float* 
   }
 }
 
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int64_t n_blocks, int64_t m_len,
-                                                              float* __restrict__ out) {
-  __shared__ float sm[8][33];
+// partial[b, m] summed over b in a FIXED order: 32 columns per CTA, the blocks dealt round-robin to WY warps (4 independent loads
+// in flight per thread), then a fixed-order tree over the warps.  WY = 32 for long block lists (few columns, hundreds of
+// blocks: the dependent-load chain per thread was 70+ loads with 8 warps), 8 otherwise.
+template <int WY>
+__global__ void __launch_bounds__(32 * WY) reduce_partials_kernel(const float* __restrict__ partial, int64_t n_blocks, int64_t m_len,
+                                                                  float* __restrict__ out) {
+  __shared__ float sm[WY][33];
   const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
   const int64_t m = (int64_t)blockIdx.x * 32 + x;
   float acc = 0.f;
   if (m < m_len) {
     int64_t b = y;
-    for (; b + 24 < n_blocks; b += 32) {   // 4 independent loads in flight per thread
-      const float v0 = partial[b * m_len + m], v1 = partial[(b + 8) * m_len + m];
-      const float v2 = partial[(b + 16) * m_len + m], v3 = partial[(b + 24) * m_len + m];
+    for (; b + 3 * WY < n_blocks; b += 4 * WY) {   // 4 independent loads in flight per thread
+      const float v0 = partial[b * m_len + m], v1 = partial[(b + WY) * m_len + m];
+      const float v2 = partial[(b + 2 * WY) * m_len + m], v3 = partial[(b + 3 * WY) * m_len + m];
       acc += v0; acc += v1; acc += v2; acc += v3;
     }
-    for (; b < n_blocks; b += 8) acc += partial[b * m_len + m];
+    for (; b < n_blocks; b += WY) acc += partial[b * m_len + m];
   }
   sm[y][x] = acc;
   __syncthreads();
   if (y == 0 && m < m_len) {
     float t = sm[0][x];
 #pragma unroll
-    for (int r = 1; r < 8; ++r) t += sm[r][x];
+    for (int r = 1; r < WY; ++r) t += sm[r][x];
     out[m] = t;
   }
 }
@@ -740,32 +744,35 @@ __device__ __forceinline__ void ro_load(const float* __restrict__ p, int lane, i
   }
 }
 
+constexpr int kBigGraph = 12;   // graphs with more rows are shared by the 8 warps of a CTA (one warp per graph otherwise)
+
+// A CTA owns groups of 8 consecutive graphs.  Egonet sizes are skewed (1..57 rows, one large positive egonet per query): with
+// one warp per graph the CTA waited ~14 us for the warp that drew the 53-row graph while the others were done after 1-2 us
+// (43 us for a 74 MB read).  Small graphs still get one warp each; the large ones of the group are then taken by all 8 warps
+// together (rows dealt round-robin, fixed-order reduction over the warps: deterministic).
 template <int NV>
 __global__ void __launch_bounds__(256) readout_fwd_fast_kernel(int kind, const float* __restrict__ h, int64_t ldh,
                                                                const int32_t* __restrict__ pos, const float* __restrict__ pw,
                                                                const int32_t* __restrict__ node_off, int n_graphs, int D,
                                                                float* __restrict__ hg, int64_t ldhg) {
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  __shared__ float4 s_acc[8][NV * 32];
+  __shared__ float s_S[8];
+  __shared__ int s_size[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   float sw[3] = {1.f, 1.f, 1.f};
   if (kind == TX_READOUT_WMEAN) {
 #pragma unroll
     for (int r = 0; r < 3; ++r) sw[r] = softplus_f(__ldg(pw + r));
   }
-  for (int g = warp; g < n_graphs; g += nwarps) {
-    const int beg = __ldg(node_off + g), end = __ldg(node_off + g + 1);
-    float S = 0.f;
-    float4 acc[NV];
-#pragma unroll
-    for (int t = 0; t < NV; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = beg; i < end; i += 4) {
+  // rows [beg, end) with stride `step` starting at beg + first: weighted sum into acc / S
+  auto accumulate = [&](int beg, int end, int first, int step, float4 (&acc)[NV], float& S) {
+    for (int i = beg + first; i < end; i += 4 * step) {
       float4 r[4][NV];
       float a[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const bool ok = i + u < end;
-        const int row = ok ? i + u : beg;
+        const bool ok = i + u * step < end;
+        const int row = ok ? i + u * step : beg;
         const int pr = kind == TX_READOUT_WMEAN ? __ldg(pos + row) : 0;
         a[u] = ok ? (pr == 0 ? sw[0] : (pr == 1 ? sw[1] : sw[2])) : 0.f;
         ro_load<NV>(h + (int64_t)row * ldh, lane, D, r[u]);
@@ -780,12 +787,61 @@ __global__ void __launch_bounds__(256) readout_fwd_fast_kernel(int kind, const f
         }
       }
     }
-    float* orow = hg + (int64_t)g * ldhg;
+  };
+  for (int g0 = blockIdx.x * 8; g0 < n_graphs; g0 += gridDim.x * 8) {
+    const int g = g0 + wid;
+    int beg = 0, end = 0;
+    if (g < n_graphs) { beg = __ldg(node_off + g); end = __ldg(node_off + g + 1); }
+    if (lane == 0) s_size[wid] = end - beg;
+    if (g < n_graphs && end - beg <= kBigGraph) {
+      float S = 0.f;
+      float4 acc[NV];
 #pragma unroll
-    for (int t = 0; t < NV; ++t) {
-      const int c = (lane + 32 * t) * 4;
-      if (c < D) *reinterpret_cast<float4*>(orow + c) = make_float4(acc[t].x / S, acc[t].y / S, acc[t].z / S, acc[t].w / S);
+      for (int t = 0; t < NV; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      accumulate(beg, end, 0, 1, acc, S);
+      float* orow = hg + (int64_t)g * ldhg;
+#pragma unroll
+      for (int t = 0; t < NV; ++t) {
+        const int c = (lane + 32 * t) * 4;
+        if (c < D) *reinterpret_cast<float4*>(orow + c) = make_float4(acc[t].x / S, acc[t].y / S, acc[t].z / S, acc[t].w / S);
+      }
     }
+    __syncthreads();
+    for (int w = 0; w < 8; ++w) {                       // uniform over the CTA
+      if (s_size[w] <= kBigGraph) continue;
+      const int gb = g0 + w;
+      const int b0 = __ldg(node_off + gb), b1 = __ldg(node_off + gb + 1);
+      float S = 0.f;
+      float4 acc[NV];
+#pragma unroll
+      for (int t = 0; t < NV; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      accumulate(b0, b1, wid, 8, acc, S);
+#pragma unroll
+      for (int t = 0; t < NV; ++t) s_acc[wid][lane + 32 * t] = acc[t];
+      if (lane == 0) s_S[wid] = S;
+      __syncthreads();
+      if (wid == 0) {
+        float St = s_S[0];
+#pragma unroll
+        for (int v = 1; v < 8; ++v) St += s_S[v];
+        float* orow = hg + (int64_t)gb * ldhg;
+#pragma unroll
+        for (int t = 0; t < NV; ++t) {
+          const int c = (lane + 32 * t) * 4;
+          if (c < D) {
+            float4 a = s_acc[0][lane + 32 * t];
+#pragma unroll
+            for (int v = 1; v < 8; ++v) {
+              const float4 x = s_acc[v][lane + 32 * t];
+              a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+            }
+            *reinterpret_cast<float4*>(orow + c) = make_float4(a.x / St, a.y / St, a.z / St, a.w / St);
+          }
+        }
+      }
+      __syncthreads();
+    }
+    __syncthreads();                                    // s_size is rewritten by the next group
   }
 }
 
@@ -797,9 +853,8 @@ __global__ void __launch_bounds__(256) readout_bwd_fast_kernel(int kind, const f
                                                                const int32_t* __restrict__ node_off, int n_graphs, int D,
                                                                float* __restrict__ dh, int64_t lddh, float* __restrict__ dw_partial) {
   __shared__ float sdw[8][3];
+  __shared__ int s_size[8];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const bool wm = kind == TX_READOUT_WMEAN;
   float sw[3] = {1.f, 1.f, 1.f}, sg[3] = {0.f, 0.f, 0.f};
   if (wm) {
@@ -811,8 +866,8 @@ __global__ void __launch_bounds__(256) readout_bwd_fast_kernel(int kind, const f
     }
   }
   float dw[3] = {0.f, 0.f, 0.f};
-  for (int g = warp; g < n_graphs; g += nwarps) {
-    const int beg = __ldg(node_off + g), end = __ldg(node_off + g + 1);
+  // rows beg + first, + step, ... of graph g: dh rows and this warp's share of d(position weights)
+  auto graph_rows = [&](int g, int beg, int end, int first, int step) {
     float4 d[NV], m[NV];
     ro_load<NV>(dhg + (int64_t)g * lddhg, lane, D, d);
     if (wm) ro_load<NV>(hg + (int64_t)g * ldhg, lane, D, m);
@@ -823,22 +878,22 @@ __global__ void __launch_bounds__(256) readout_bwd_fast_kernel(int kind, const f
     }
     S = warp_sum(S);
     const float inv_s = 1.f / S;
-    for (int i = beg; i < end; i += 4) {
+    for (int i = beg + first; i < end; i += 4 * step) {
       float4 r[4][NV];
       int pr[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int row = i + u < end ? i + u : beg;
+        const int row = i + u * step < end ? i + u * step : beg;
         pr[u] = wm ? __ldg(pos + row) : 0;
         if (wm) ro_load<NV>(h + (int64_t)row * ldh, lane, D, r[u]);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        if (i + u < end) {                       // warp-uniform
+        if (i + u * step < end) {                       // warp-uniform
           const float a = pr[u] == 0 ? sw[0] : (pr[u] == 1 ? sw[1] : sw[2]);
           const float sc = a * inv_s;
           float dot = 0.f;
-          float* orow = dh + (int64_t)(i + u) * lddh;
+          float* orow = dh + (int64_t)(i + u * step) * lddh;
 #pragma unroll
           for (int t = 0; t < NV; ++t) {
             const int c = (lane + 32 * t) * 4;
@@ -857,6 +912,28 @@ __global__ void __launch_bounds__(256) readout_bwd_fast_kernel(int kind, const f
         }
       }
     }
+  };
+  for (int g0 = blockIdx.x * 8; g0 < n_graphs; g0 += gridDim.x * 8) {
+    const int g = g0 + wid;
+    int beg = 0, end = 0;
+    if (g < n_graphs) { beg = __ldg(node_off + g); end = __ldg(node_off + g + 1); }
+    if (lane == 0) s_size[wid] = end - beg;
+    // task 0: this warp's own graph if it is small; tasks 1..8: the large graphs of the group, rows dealt round-robin to the 8
+    // warps (ONE call site of graph_rows: two inlined copies doubled the register count)
+    for (int task = 0; task <= 8; ++task) {
+      if (task == 1) __syncthreads();                   // s_size of the whole group is visible
+      int gg = g, b0 = beg, b1 = end, first = 0, step = 1;
+      if (task == 0) {
+        if (!(g < n_graphs && end - beg <= kBigGraph)) continue;
+      } else {
+        if (s_size[task - 1] <= kBigGraph) continue;
+        gg = g0 + task - 1;
+        b0 = __ldg(node_off + gg); b1 = __ldg(node_off + gg + 1);
+        first = wid; step = 8;
+      }
+      graph_rows(gg, b0, b1, first, step);
+    }
+    __syncthreads();                                    // s_size is rewritten by the next group
   }
   if (wm && dw_partial) {
     if (lane == 0) { sdw[wid][0] = dw[0]; sdw[wid][1] = dw[1]; sdw[wid][2] = dw[2]; }
@@ -934,7 +1011,10 @@ int tx_reduce_partials(const float* partial, int64_t n_blocks, int64_t m_len, fl
     TX_LAUNCH_CHECK("tx_reduce_partials");
     return TX_OK;
   }
-  reduce_partials_kernel<<<(int)((m_len + 31) / 32), 256, 0, (cudaStream_t)stream>>>(partial, n_blocks, m_len, out);
+  if (n_blocks >= 128)
+    reduce_partials_kernel<32><<<(int)((m_len + 31) / 32), 1024, 0, (cudaStream_t)stream>>>(partial, n_blocks, m_len, out);
+  else
+    reduce_partials_kernel<8><<<(int)((m_len + 31) / 32), 256, 0, (cudaStream_t)stream>>>(partial, n_blocks, m_len, out);
   TX_LAUNCH_CHECK("tx_reduce_partials");
   return TX_OK;
 }
