@@ -194,7 +194,6 @@ def run_reference(args, rank):
 # ------------------------------------------------------------------------------------------------
 def run_b200(args, rank, world, local_rank):
     import torch.distributed as dist
-    import torch.nn.functional as F
 
     import taxoexpan_b200 as tx
     from taxoexpan_b200 import _lib, synth
@@ -230,13 +229,12 @@ def run_b200(args, rank, world, local_rank):
         g = tx.EgonetBatch.from_counts(shapes.n_gp, shapes.n_sib).pin_memory()
         batches.append(dict(shapes=shapes, x_host=x, qf_host=qf, graph=g, x=x.to(dev), qf=qf.to(dev)))
         g.structure(dev)
-    target = torch.zeros(nq, dtype=torch.long, device=dev)
     torch.cuda.synchronize()
 
     def fwd_bwd(g, x, qf):
         flat.zero_()
         scores = model(g, x, qf)                                              # trainer.py:51
-        loss = F.cross_entropy(scores.reshape(nq, -1), target, reduction="sum")   # trainer.py:52-56, loss.py:57
+        loss = tx.info_nce_loss(scores.reshape(nq, -1), None)                 # trainer.py:52-56, loss.py:52-57 (target = zeros)
         loss.backward()                                                       # trainer.py:60
         bucket.all_reduce()                                                   # the only exchange of the path (no-op at N = 1)
         return loss

@@ -349,6 +349,28 @@ int tx_gemm_tn_f16x3(const void* a_hi, const void* a_lo, int64_t lda, const void
                      const float* scale_a, const float* scale_b, float* c_partial, int64_t ldc, int64_t split_stride, int64_t m,
                      int64_t n, int64_t r, int64_t splits, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Matching + InfoNCE epilogue: the step right after the readout.
+ * tx_match_rowdot: scores[g] = f(<u[g,:], q[g,:]>) with u = hg . W[0] (the projection half of nn.Bilinear(l, r, 1, bias=False),
+ *   a GEMM of this library), f = identity for BIM (model/model_zoo.py:301-313) and exp for LBM (:316-328; apply_exp = 1).
+ *   Backward: dt = dscores[g] * (apply_exp ? scores[g] : 1); du[g,:] = dt q[g,:]; dq[g,:] = dt u[g,:] (du or dq may be NULL).
+ * tx_info_nce: loss = sum_q (logsumexp_j scores[q, j] - scores[q, target[q]]) = F.cross_entropy(scores.reshape(n_queries, group),
+ *   target, reduction="sum") (model/loss.py:52-57 on the reshape of trainer/trainer.py:52-55).  target may be NULL (= all zeros,
+ *   the only layout the reference produces: one positive first, then negative_size negatives, data_loader/dataset.py:308-313);
+ *   a class index outside [0, group) yields a NaN loss.  loss_per_query / lse_per_query: [n_queries] device floats of caller-owned
+ *   workspace (lse is kept for the backward pass); *loss is summed in a fixed order (deterministic).
+ *   Backward: dscores[q, j] = *dloss * (exp(scores[q, j] - lse[q]) - [j == target[q]]).
+ * ------------------------------------------------------------------------------------------------ */
+int tx_match_rowdot_fwd(const float* u, int64_t ldu, const float* q, int64_t ldq, int64_t n_rows, int64_t r, int32_t apply_exp,
+                        float* scores, void* stream);
+int tx_match_rowdot_bwd(const float* u, int64_t ldu, const float* q, int64_t ldq, const float* scores, const float* dscores,
+                        int64_t n_rows, int64_t r, int32_t apply_exp, float* du, int64_t lddu, float* dq, int64_t lddq,
+                        void* stream);
+int tx_info_nce_fwd(const float* scores, int64_t n_queries, int64_t group, const int32_t* target, float* loss_per_query,
+                    float* lse_per_query, float* loss, void* stream);
+int tx_info_nce_bwd(const float* scores, const float* lse_per_query, int64_t n_queries, int64_t group, const int32_t* target,
+                    const float* dloss, float* dscores, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

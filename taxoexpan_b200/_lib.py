@@ -103,6 +103,10 @@ _SIGNATURES = {
     "tx_gemm_nt_f16x3": [P, P, I64, P, P, I64, P, P, P, I64, I64, I64, I64, POINTER(GemmEpilogue), P, P],
     "tx_gemm_tn_f16_splits": [I64, I64, I64],
     "tx_gemm_tn_f16x3": [P, P, I64, P, P, I64, P, P, P, I64, I64, I64, I64, I64, I64, P],
+    "tx_match_rowdot_fwd": [P, I64, P, I64, I64, I64, c_int32, P, P],
+    "tx_match_rowdot_bwd": [P, I64, P, I64, P, P, I64, I64, c_int32, P, I64, P, I64, P],
+    "tx_info_nce_fwd": [P, I64, I64, P, P, P, P, P],
+    "tx_info_nce_bwd": [P, P, I64, I64, P, P, P, P],
 }
 _RESTYPES = {"tx_last_error": c_char_p, "tx_target_arch": c_char_p, "tx_row_blocks": c_int64, "tx_readout_bwd_blocks": c_int64,
              "tx_gat_fused_mask_words": c_int64, "tx_gat_fused_mask_ld": c_int64, "tx_gat_fused_bwd_blocks": c_int64, "tx_gemm_tn_splits": c_int64,

@@ -810,6 +810,81 @@ def dense_right(a: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------------------------
+# Matching row-dot (+ exp) and InfoNCE (tx_match.cu)
+# --------------------------------------------------------------------------------------------------
+class MatchRowDot(Function):
+    """scores[g, 0] = f(<u_g, q_g>), f = exp (LBM) or identity (BIM): the row-dot half of nn.Bilinear(l, r, 1) once u = e1 W[0]
+    is known (reference model_zoo.py:301-328)."""
+
+    @staticmethod
+    def forward(ctx, u, q, apply_exp: bool):
+        lib = _lib.load()
+        _check_cuda(u, "projected graph embeddings")
+        _check_cuda(q, "query features")
+        u, q = _rowmajor(u), _rowmajor(q)
+        G, r = u.shape
+        if q.shape != u.shape:
+            raise ValueError(f"match: {tuple(u.shape)} projected embeddings against {tuple(q.shape)} query features")
+        scores = torch.empty((G, 1), dtype=torch.float32, device=u.device)
+        with device_guard(u.device):
+            check(lib.tx_match_rowdot_fwd(ptr(u), u.stride(0) if G > 1 else r, ptr(q), q.stride(0) if G > 1 else r, G, r,
+                                          int(bool(apply_exp)), ptr(scores), current_stream()), "tx_match_rowdot_fwd")
+        ctx.apply_exp = bool(apply_exp)
+        ctx.save_for_backward(u, q, scores)
+        return scores
+
+    @staticmethod
+    def backward(ctx, dscores):
+        lib = _lib.load()
+        u, q, scores = ctx.saved_tensors
+        G, r = u.shape
+        dscores = dscores.reshape(-1).contiguous()
+        du = torch.empty((G, r), dtype=torch.float32, device=u.device) if ctx.needs_input_grad[0] else None
+        dq = torch.empty((G, r), dtype=torch.float32, device=u.device) if ctx.needs_input_grad[1] else None
+        with device_guard(u.device):
+            check(lib.tx_match_rowdot_bwd(ptr(u), u.stride(0) if G > 1 else r, ptr(q), q.stride(0) if G > 1 else r, ptr(scores),
+                                          ptr(dscores), G, r, int(ctx.apply_exp), ptr(du), r, ptr(dq), r, current_stream()),
+                  "tx_match_rowdot_bwd")
+        return du, dq, None
+
+
+def match_rowdot(u: torch.Tensor, q: torch.Tensor, apply_exp: bool) -> torch.Tensor:
+    return MatchRowDot.apply(u, q, apply_exp)
+
+
+class InfoNCE(Function):
+    """sum_q CE(output[q, :], target[q]) = F.cross_entropy(output, target, reduction="sum") (reference loss.py:52-57)."""
+
+    @staticmethod
+    def forward(ctx, output, target32):
+        lib = _lib.load()
+        _check_cuda(output, "scores")
+        output = _rowmajor(output).contiguous()
+        nq, m = output.shape
+        if nq > 0 and m < 1:
+            raise ValueError("info_nce_loss: no classes")
+        work = torch.empty((2, max(nq, 1)), dtype=torch.float32, device=output.device)
+        loss = torch.empty((), dtype=torch.float32, device=output.device)
+        with device_guard(output.device):
+            check(lib.tx_info_nce_fwd(ptr(output), nq, max(m, 1), ptr(target32), ptr(work[0]), ptr(work[1]), ptr(loss),
+                                      current_stream()), "tx_info_nce_fwd")
+        ctx.save_for_backward(output, work, target32)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        lib = _lib.load()
+        output, work, target32 = ctx.saved_tensors
+        nq, m = output.shape
+        dloss = dloss.reshape(()).contiguous().to(torch.float32)
+        dscores = torch.empty_like(output)
+        with device_guard(output.device):
+            check(lib.tx_info_nce_bwd(ptr(output), ptr(work[1]), nq, max(m, 1), ptr(target32), ptr(dloss), ptr(dscores),
+                                      current_stream()), "tx_info_nce_bwd")
+        return dscores, None
+
+
+# --------------------------------------------------------------------------------------------------
 # Readout
 # --------------------------------------------------------------------------------------------------
 class Readout(Function):

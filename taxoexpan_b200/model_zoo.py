@@ -273,8 +273,9 @@ class ConcatReadout(nn.Module):
 
 
 # =====================================================================================================
-# Graph matching modules (SURVEY.md section 8 row f1 "next"): plain PyTorch, except that the bilinear forms' projection e1 W and its
-# autograd GEMMs run on the library's fp32-faithful tensor-core kernels (they were 180 us of cuBLAS SIMT sgemm per step)
+# Graph matching modules: the bilinear forms' projection e1 W and its autograd GEMMs run on the library's
+# fp32-faithful tensor-core kernels (they were 180 us of cuBLAS SIMT sgemm per step), the row-dot with the query features (+ LBM's exp)
+# on tx_match_rowdot_fwd/bwd; the InfoNCE loss that follows is taxoexpan_b200.loss.info_nce_loss.  MLP stays torch glue.
 # =====================================================================================================
 class MLP(nn.Module):
     """reference model_zoo.py:281-298"""
@@ -294,12 +295,13 @@ class BIM(nn.Module):
         super().__init__()
         self.W = nn.Bilinear(l_dim, r_dim, 1, bias=False)
 
+    apply_exp = False
+
     def forward(self, e1, e2):
-        return (txf.dense_right(e1, self.W.weight[0]) * e2).sum(dim=1, keepdim=True)
+        return txf.match_rowdot(txf.dense_right(e1, self.W.weight[0]), e2, self.apply_exp)     # tx_match_rowdot_fwd/bwd
 
 
 class LBM(BIM):
-    """reference model_zoo.py:316-328"""
+    """reference model_zoo.py:316-328: exp of the bilinear form (fused into the row-dot kernel)"""
 
-    def forward(self, e1, e2):
-        return torch.exp(super().forward(e1, e2))
+    apply_exp = True

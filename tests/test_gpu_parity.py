@@ -35,7 +35,8 @@ def run_cuda(model, graph, x, qf, n_q):
     node_h = graph.ndata["h"]
     pos = torch.as_tensor(np.asarray(graph.host_pos() if hasattr(graph, "host_pos") else graph._pos_backup))
     hg = model.readout(graph, pos)
-    loss = F.cross_entropy(scores.reshape(n_q, -1), torch.zeros(n_q, dtype=torch.long, device=dev()), reduction="sum")
+    # trainer.py:52-56 + loss.py:52-57 on the library's fused InfoNCE kernels (taxoexpan_b200/loss.py)
+    loss = tx.info_nce_loss(scores.reshape(n_q, -1), torch.zeros(n_q, dtype=torch.long, device=dev()))
     loss.backward()
     torch.cuda.synchronize()
     grads = {k: p.grad.detach().cpu().numpy() for k, p in model.named_parameters()}
@@ -207,7 +208,10 @@ WORDNET = dict(propagation_method="PGCN", readout_method="MR", matching_method="
 @pytest.mark.parametrize("cfg_kw,model_name,n_q", [(MAGCS, "mag-cs", 16), (WORDNET, "wordnet", 16),
                                                     (dict(MAGCS, readout_method="CR"), "mag-cs", 4),
                                                     (dict(MAGCS, propagation_method="GAT", readout_method="MR"), "mag-cs", 4),
-                                                    (dict(WORDNET, propagation_method="GCN", num_layers=2), "wordnet", 4)])
+                                                    (dict(WORDNET, propagation_method="GCN", num_layers=2), "wordnet", 4),
+                                                    # BASELINE configs[4] (SURVEY 8d "config 5"): d = 512, three propagation layers
+                                                    (dict(MAGCS, in_dim=512, hidden_dim=512, out_dim=512, pos_dim=64, num_layers=2,
+                                                          heads=[4, 4, 1]), "mag-cs", 4)])
 def test_cuda_path_matches_oracle_on_synthetic_batches(cfg_kw, model_name, n_q, monkeypatch):
     cfg = orc.OracleConfig(**cfg_kw)
     shapes = tx.synth.sample_shapes(n_q, 31, model_name, seed=99)
@@ -422,7 +426,7 @@ def test_full_size_properties_magcs_batch256():
         model.zero_grad()
         g = tx.EgonetBatch.from_counts(shapes.n_gp, shapes.n_sib)
         s = model(g, x, qf)
-        loss = F.cross_entropy(s.reshape(256, -1), torch.zeros(256, dtype=torch.long, device=dev()), reduction="sum")
+        loss = tx.info_nce_loss(s.reshape(256, -1), torch.zeros(256, dtype=torch.long, device=dev()))
         loss.backward()
         return s.detach().clone(), g.ndata["h"].detach().clone(), {k: p.grad.clone() for k, p in model.named_parameters()}, g
 
@@ -517,3 +521,76 @@ def test_gpu_built_egonet_batch_matches_the_per_egonet_reference_construction():
         scores = model(bg, x, qf.to(dev()))
         ref, _, _ = orc.taxoexpan_forward(cfg, og, feats[torch.tensor(nodes_all)], qf, params)
     assert float((scores.cpu() - ref).abs().max()) <= TOL * max(1.0, float(ref.abs().max()))
+
+
+# ------------------------------------------------------------------------------------------------
+# matching row-dot (+ exp) and InfoNCE kernels against the reference formulas (model_zoo.py:301-328,
+# loss.py:52-57) in torch fp64 on the CPU.  Tolerance: 1e-5 relative to the largest entry (fp32 path).
+# ------------------------------------------------------------------------------------------------
+def _rel_err(a, b):
+    b = b.double()
+    return float((a.detach().cpu().double() - b).abs().max() / max(float(b.abs().max()), 1e-30))
+
+
+@pytest.mark.parametrize("apply_exp", [False, True])
+@pytest.mark.parametrize("G,r", [(1, 1), (7, 250), (64, 256), (33, 301), (2048, 250)])
+def test_match_rowdot_matches_bilinear_formula(apply_exp, G, r):
+    gen = torch.Generator().manual_seed(100 * G + r)
+    u = (torch.randn(G, r, generator=gen) / max(r, 1) ** 0.5)
+    q = torch.randn(G, r, generator=gen)
+    up, qp = u.double().requires_grad_(True), q.double().requires_grad_(True)
+    t = (up * qp).sum(1, keepdim=True)
+    ref = torch.exp(t) if apply_exp else t
+    w = torch.randn(G, 1, generator=gen).double()
+    (ref * w).sum().backward()
+    ud, qd = u.to(dev()).requires_grad_(True), q.to(dev()).requires_grad_(True)
+    got = txf.match_rowdot(ud, qd, apply_exp)
+    assert got.shape == (G, 1)
+    (got * w.float().to(dev())).sum().backward()
+    assert _rel_err(got, ref) <= TOL
+    assert _rel_err(ud.grad, up.grad) <= TOL
+    assert _rel_err(qd.grad, qp.grad) <= TOL
+
+
+def test_match_rowdot_handles_padded_rows_and_frozen_queries():
+    gen = torch.Generator().manual_seed(5)
+    base_u = torch.randn(40, 264, generator=gen).to(dev())
+    u = base_u[:, :250].requires_grad_(True)                    # leading dimension 264 != r = 250
+    q = torch.randn(40, 250, generator=gen).to(dev())           # requires no gradient: dq is skipped
+    got = txf.match_rowdot(u, q, True)
+    got.sum().backward()
+    ref = torch.exp((base_u[:, :250].double() * q.double()).sum(1, keepdim=True))
+    assert _rel_err(got, ref.cpu()) <= TOL
+    assert _rel_err(u.grad, (ref * q.double()).cpu()) <= TOL
+
+
+@pytest.mark.parametrize("nq,m", [(1, 1), (3, 32), (256, 32), (5, 77), (4096, 32)])
+def test_info_nce_loss_matches_cross_entropy_sum(nq, m):
+    gen = torch.Generator().manual_seed(nq * 131 + m)
+    x = torch.randn(nq, m, generator=gen) * 3.0
+    for target in (None, torch.zeros(nq, dtype=torch.long), torch.randint(0, m, (nq,), generator=gen)):
+        xr = x.double().requires_grad_(True)
+        ref = F.cross_entropy(xr, torch.zeros(nq, dtype=torch.long) if target is None else target, reduction="sum")
+        (ref * 0.7).backward()
+        xd = x.to(dev()).requires_grad_(True)
+        got = tx.info_nce_loss(xd, None if target is None else target.to(dev()))
+        assert got.shape == ()
+        (got * 0.7).backward()
+        assert abs(float(got) - float(ref)) <= TOL * max(1.0, abs(float(ref)))
+        assert float((xd.grad.cpu().double() - xr.grad).abs().max()) <= TOL
+    # bitwise run-to-run determinism (fixed-order reductions)
+    a = tx.info_nce_loss(x.to(dev()), None)
+    b = tx.info_nce_loss(x.to(dev()), None)
+    assert torch.equal(a, b)
+
+
+def test_info_nce_rejects_bad_shapes_and_flags_bad_targets():
+    x = torch.randn(4, 8).to(dev())
+    with pytest.raises(ValueError):
+        tx.info_nce_loss(x.reshape(-1), None)
+    with pytest.raises(ValueError):
+        tx.info_nce_loss(x, torch.zeros(3, dtype=torch.long, device=dev()))
+    with pytest.raises(tx.TaxoLibraryError):
+        tx.info_nce_loss(x.cpu(), None)                       # no CPU path
+    bad = torch.tensor([0, 8, 0, 0], device=dev())            # class index out of range: a NaN loss, not an out-of-bounds read
+    assert torch.isnan(tx.info_nce_loss(x, bad))
