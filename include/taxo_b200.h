@@ -235,6 +235,23 @@ int tx_gat_fused_fwd_staged(const float* ft, int64_t ldf, const float* attn_l, c
                             float* alpha_d, float* elog, float* out, int64_t ldo, const tx_gat_epilogue* epi, uint32_t* maskbits,
                             float* out_lo, void* out16_hi, void* out16_lo, int64_t ld16, const float* bound, float* scale_out,
                             void* stream);
+/* Star-egonet variant of tx_gat_fused_fwd / tx_gat_fused_fwd_f16 (same arithmetic and outputs; reference model_zoo.py:83-96,106-114)
+ * for batches whose structure is the closed form of tx_star_batch_structure (data_loader/dataset.py:404-437): no CSR is read, every
+ * ft row is loaded once per work item, the anchor row stays in registers while its siblings stream by.
+ *   tasks: int32 [4 * n_tasks] (16-byte aligned), one record per (egonet, chunk c):
+ *          {node_off, edge_off, n_gp | c << 24, n_sib} of that egonet (the quantities of tx_star_batch_structure); chunk c covers
+ *          siblings [c C, (c+1) C) with C = `chunk` (tx_gat_star_chunk() is the recommended value); chunk 0 (present for every
+ *          egonet) also owns the grand-parents and the anchor; an egonet has max(1, ceil(n_sib / C)) <= tx_gat_star_max_chunks()
+ *          chunks and n_gp < 2^24.
+ *   queue: int32 [2 * heads] work-queue counters, ZERO before the first launch; the kernel leaves them zero again (one buffer per
+ *          stream: concurrent launches must not share it).
+ *   Exactly one of {out (fp32), out16_hi/out16_lo (+ bound, scale_out)} is written; alpha / alpha_d / elog per slot as usual. */
+int64_t tx_gat_star_chunk(void);
+int64_t tx_gat_star_max_chunks(void);
+int tx_gat_star_fwd(const float* ft, int64_t ldf, const float* attn_l, const float* attn_r, const int32_t* tasks, int64_t n_tasks, int64_t chunk,
+                    int64_t n_nodes, int64_t heads, int64_t dim, float neg_slope, float p_attn, uint64_t attn_seed, uint32_t attn_stream_id,
+                    float* alpha, float* alpha_d, float* elog, float* out, int64_t ldo, const tx_gat_epilogue* epi, uint32_t* maskbits,
+                    void* out16_hi, void* out16_lo, int64_t ld16, const float* bound, float* scale_out, int32_t* queue, void* stream);
 /* dpos_partial[b, r, :] = sum over rows i of block b (tx_row_blocks) with pos_i = r of dz[i, col0 : col0+pos_dim] * keep/(1-p)
  * (gradient of the appended position-embedding block, reference model_zoo.py:214-215). */
 int tx_pos_grad_partials(const float* dz, int64_t ldz, int64_t col0, const int32_t* pos, int64_t n_nodes,

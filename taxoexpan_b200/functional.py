@@ -58,6 +58,26 @@ STAGED_BWD = os.environ.get("TAXO_STAGED_BWD", "1") not in ("", "0")
 # MAG-CS shapes (L0: 0.35 ms vs 0.23 ms - its one-thread-per-row softmax step and the two extra CTA barriers per tile cost more than
 # the gather they save), so it is opt-in: TAXO_STAGED_FWD=1
 STAGED_FWD = os.environ.get("TAXO_STAGED_FWD", "0") not in ("", "0")
+# star-specialised fused GAT forward (tx_star_fwd.cu) for EgonetBatch structures: closed-form in-edges, every ft row loaded once per
+# work item, anchor row in registers; TAXO_STAR_FWD=0 -> the general warp-per-(row, head) kernel
+STAR_FWD = os.environ.get("TAXO_STAR_FWD", "1") not in ("", "0")
+STAR_FWD_OUTPUT_LAYER = os.environ.get("TAXO_STAR_FWD", "1") != "hidden"     # TAXO_STAR_FWD=hidden: hidden layers only
+
+_star_queues = {}
+
+
+def _star_queue(device) -> torch.Tensor:
+    """Work-queue counters of tx_gat_star_fwd (zero before the first launch, left zero by every launch): one buffer per
+    (device, stream), because launches on different streams may overlap."""
+    key = (device.index, current_stream().value)
+    q = _star_queues.get(key)
+    if q is None:
+        lib = _lib.load()
+        from .graph import STAR_MAX_CHUNKS
+        if int(lib.tx_gat_star_max_chunks()) != STAR_MAX_CHUNKS:
+            raise _lib.TaxoLibraryError("tx_gat_star_fwd: task encoding of the library differs from taxoexpan_b200.graph; rebuild")
+        q = _star_queues[key] = torch.zeros(2 * 64, dtype=torch.int32, device=device)
+    return q
 
 
 def use_fused(lib, heads: int, dim: int, mean_heads: int, st=None) -> bool:
@@ -497,6 +517,7 @@ class GatLayer(Function):
                               pos=ptr(pos32) if pd > 0 else None, pos_dim=pd, p_drop=cfg.p_next if cfg.hidden else 0.0,
                               seed=cfg.next_seed, stream_id=cfg.next_stream)
             fused = use_fused(lib, H, D, 0 if cfg.hidden else 1, st)
+            star = fused and STAR_FWD and st.star is not None and H <= 64 and n > 0
             maskbits = None
             out_lo = None
             out16 = None
@@ -516,7 +537,12 @@ class GatLayer(Function):
                     bound = torch.empty(1, **f32)
                     check(lib.tx_bound_max2(ptr(ft_amax), 1.0 / ((1.0 - cfg.p_attn) * (1.0 - cfg.p_next)), ptr(tab) if pd > 0 else None,
                                             tab.numel() if pd > 0 else 0, 1.0 / (1.0 - cfg.p_next), ptr(bound), stream), "tx_bound_max2")
-                    if STAGED_FWD:
+                    if star:
+                        sg = st.star
+                        check(lib.tx_gat_star_fwd(ptr(ft), F_, ptr(al), ptr(ar), ptr(sg[0]), sg[1], sg[2], n, H, D, cfg.neg_slope, cfg.p_attn, cfg.attn_seed, cfg.attn_stream, ptr(alpha),
+                                                  ptr(alpha_d), ptr(elog), None, ldo, epi, ptr(maskbits), ptr(o_hi), ptr(o_lo), ld16,
+                                                  ptr(bound), ptr(o_scale), ptr(_star_queue(dev)), stream), "tx_gat_star_fwd")
+                    elif STAGED_FWD:
                         check(lib.tx_gat_fused_fwd_staged(ptr(ft), F_, ptr(al), ptr(ar), ptr(st.in_ptr), ptr(st.in_src), ptr(st.in_eid),
                                                           ptr(st.bwd_tiles(D)), n, H, D, cfg.neg_slope, cfg.p_attn, cfg.attn_seed,
                                                           cfg.attn_stream, ptr(alpha), ptr(alpha_d), ptr(elog), None, ldo, epi,
@@ -528,6 +554,11 @@ class GatLayer(Function):
                                                        ptr(elog), ldo, epi, ptr(maskbits), ptr(o_hi), ptr(o_lo), ld16, ptr(bound),
                                                        ptr(o_scale), stream), "tx_gat_fused_fwd")
                     out16 = F16Pair(o_hi, o_lo, o_scale, F_ + pd)
+                elif star and STAR_FWD_OUTPUT_LAYER and out_lo is None and n > 0:
+                    sg = st.star
+                    check(lib.tx_gat_star_fwd(ptr(ft), F_, ptr(al), ptr(ar), ptr(sg[0]), sg[1], sg[2], n, H, D, cfg.neg_slope, cfg.p_attn, cfg.attn_seed, cfg.attn_stream, ptr(alpha), ptr(alpha_d),
+                                              ptr(elog), ptr(out), ldo, epi, ptr(maskbits), None, None, 0, None, None,
+                                              ptr(_star_queue(dev)), stream), "tx_gat_star_fwd")
                 elif STAGED_FWD and n > 0:
                     check(lib.tx_gat_fused_fwd_staged(ptr(ft), F_, ptr(al), ptr(ar), ptr(st.in_ptr), ptr(st.in_src), ptr(st.in_eid),
                                                       ptr(st.bwd_tiles(D)), n, H, D, cfg.neg_slope, cfg.p_attn, cfg.attn_seed,

@@ -16,17 +16,23 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional, Sequence
 
+import os
+
 import numpy as np
 import torch
 
 from . import _lib
 
 
+STAR_CHUNK = int(os.environ.get("TAXO_STAR_CHUNK", "4"))   # siblings per work item of the star-specialised forward kernel
+STAR_MAX_CHUNKS = 128    # = tx_gat_star_max_chunks()
+
+
 class GraphStructure:
     """Device-resident structure of one batched graph (all int32)."""
 
     __slots__ = ("device", "n", "e", "g", "in_ptr", "in_src", "in_eid", "out_ptr", "out_dst", "out_slot", "node_off",
-                 "pos", "src", "dst", "max_nodes", "max_out_deg", "_norm", "is_star", "_bwd_tiles", "_dh_bound")
+                 "pos", "src", "dst", "max_nodes", "max_out_deg", "_norm", "is_star", "_bwd_tiles", "_dh_bound", "star")
 
     def __init__(self, device):
         self.device = device
@@ -37,6 +43,7 @@ class GraphStructure:
         self.pos = None
         self.src = self.dst = None
         self.is_star = False
+        self.star = None           # (task records, n_tasks, chunk) of an EgonetBatch on the device (tx_gat_star_fwd)
 
     def bwd_tiles(self, dim: int) -> torch.Tensor:
         """Tile table of the TMA-staged fused GAT backward (tx_gat_bwd_tiles) for per-head width `dim`; built once per batch."""
@@ -222,9 +229,28 @@ class EgonetBatch(DGLGraph):
         self._bnn = self._bne = None          # (two 8192-element tolist() calls were 0.2 ms of every freshly built batch)
         self._edges_built = False
         self._max_nodes = int(n.max()) if n.size else 0
-        # one pinned staging buffer: [n_gp | n_sib | node_off | edge_off] as int32
         g = n.shape[0]
-        packed = np.concatenate([self.n_gp, self.n_sib, self._node_off.astype(np.int32), self._edge_off.astype(np.int32)])
+        # work items of the star-specialised forward kernel (tx_gat_star_fwd): one 16-byte record {node_off, edge_off, n_gp | chunk << 24,
+        # n_sib} per (egonet, chunk of STAR_CHUNK siblings); none when the batch exceeds the encoding (the general fused kernel takes over)
+        n_chunks = np.maximum(1, (self.n_sib.astype(np.int64) + STAR_CHUNK - 1) // STAR_CHUNK)
+        self._n_tasks = 0
+        tasks = np.zeros(0, dtype=np.int32)
+        if g and int(self.n_gp.max()) < (1 << 24) and int(n_chunks.max()) <= STAR_MAX_CHUNKS:
+            first = np.zeros(g + 1, dtype=np.int64)
+            np.cumsum(n_chunks, out=first[1:])
+            owner = np.repeat(np.arange(g, dtype=np.int64), n_chunks)
+            chunk = np.arange(first[-1], dtype=np.int64) - first[owner]
+            rec = np.empty((owner.shape[0], 4), dtype=np.int32)
+            rec[:, 0] = self._node_off[owner]
+            rec[:, 1] = self._edge_off[owner]
+            rec[:, 2] = self.n_gp[owner] | (chunk << 24)
+            rec[:, 3] = self.n_sib[owner]
+            tasks = rec.reshape(-1)
+            self._n_tasks = int(owner.shape[0])
+        # one pinned staging buffer: [n_gp | n_sib | node_off | edge_off | pad to 16 bytes | task records] as int32
+        head = np.concatenate([self.n_gp, self.n_sib, self._node_off.astype(np.int32), self._edge_off.astype(np.int32)])
+        self._task_off = (head.shape[0] + 3) // 4 * 4
+        packed = np.concatenate([head, np.zeros(self._task_off - head.shape[0], dtype=np.int32), tasks])
         self._packed = torch.from_numpy(packed)
         self._g = g
         if ndata:
@@ -327,6 +353,8 @@ class EgonetBatch(DGLGraph):
             node_off, edge_off = packed[2 * g:3 * g + 1], packed[3 * g + 1:4 * g + 2]
             i32 = dict(dtype=torch.int32, device=device)
             st.node_off = node_off
+            if self._n_tasks:
+                st.star = (packed[self._task_off:self._task_off + 4 * self._n_tasks], self._n_tasks, STAR_CHUNK)
             st.pos = torch.empty(st.n, **i32)
             st.in_ptr, st.in_src, st.in_eid = torch.empty(st.n + 1, **i32), torch.empty(st.e, **i32), torch.empty(st.e, **i32)
             st.out_ptr, st.out_dst, st.out_slot = torch.empty(st.n + 1, **i32), torch.empty(st.e, **i32), torch.empty(st.e, **i32)

@@ -167,9 +167,11 @@ def test_dropout_mask_is_reproducible_and_calibrated():
 # golden vectors from the unmodified reference
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", CASES)
-@pytest.mark.parametrize("graph_kind", ["egonet_batch", "dgl_batch", "general_kernels", "first_gen_fused", "staged_fwd", "tf32x3", "cublas"])
+@pytest.mark.parametrize("graph_kind", ["egonet_batch", "general_fused_fwd", "dgl_batch", "general_kernels", "first_gen_fused", "staged_fwd",
+                                        "tf32x3", "cublas"])
 def test_cuda_path_matches_reference_golden(name, graph_kind, monkeypatch):
-    """egonet_batch: closed-form structure + default kernels (TMA-staged fused backward, fp16-split GEMMs); dgl_batch: per-edge
+    """egonet_batch: closed-form structure + default kernels (star-specialised fused forward, TMA-staged fused backward, fp16-split
+    GEMMs); general_fused_fwd: the warp-per-(row, head) fused forward on the same batch; dgl_batch: per-edge
     construction + GPU CSR build; general_kernels: the general-CSR kernels (fused path disabled); first_gen_fused: the
     warp-per-row fused backward instead of the staged one; staged_fwd: the opt-in TMA-staged forward; tf32x3 / cublas: the other
     dense backends."""
@@ -178,6 +180,8 @@ def test_cuda_path_matches_reference_golden(name, graph_kind, monkeypatch):
     model.train()     # dropout rates 0: exercises the training graph exactly like the golden run
     if graph_kind == "general_kernels":
         monkeypatch.setattr(txf, "FUSED_ENABLED", False)
+    elif graph_kind == "general_fused_fwd":
+        monkeypatch.setattr(txf, "STAR_FWD", False)
     elif graph_kind == "first_gen_fused":
         monkeypatch.setattr(txf, "STAGED_BWD", False)
     elif graph_kind == "staged_fwd":
@@ -594,3 +598,52 @@ def test_info_nce_rejects_bad_shapes_and_flags_bad_targets():
         tx.info_nce_loss(x.cpu(), None)                       # no CPU path
     bad = torch.tensor([0, 8, 0, 0], device=dev())            # class index out of range: a NaN loss, not an out-of-bounds read
     assert torch.isnan(tx.info_nce_loss(x, bad))
+
+
+# ------------------------------------------------------------------------------------------------
+# star-specialised fused forward (tx_gat_star_fwd) against the general fused forward on the same EgonetBatch: every saved tensor
+# of the layer (alpha, alpha~, post-leaky logits in slot order) and the outputs, with dropout on (same counter-based masks), on
+# shapes that exercise > 32 grand-parents (logit spill path), many sibling chunks, roots and leaves.
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shapes", [([1, 2, 0, 3], [2, 0, 0, 50]), ([40, 0, 33], [3, 170, 0]), ([0] * 5, [0, 1, 16, 17, 32])])
+@pytest.mark.parametrize("p_drop", [0.0, 0.3])
+def test_star_forward_matches_general_fused_forward(shapes, p_drop, monkeypatch):
+    n_gp, n_sib = shapes
+    cfg = orc.OracleConfig(**MAGCS)
+    params = orc.init_model_params(cfg, seed=5)
+    og = orc.batch_star_egonets(n_gp, n_sib)
+    x = torch.from_numpy(tx.synth.unit_rows(og.n, cfg.in_dim, seed=1)).to(dev())
+    qf = torch.from_numpy(tx.synth.unit_rows(og.num_graphs, cfg.in_dim, seed=2)).to(dev())
+    outs = {}
+    for star in (True, False):
+        monkeypatch.setattr(txf, "STAR_FWD", star)
+        saved = []
+        orig = txf.GatLayer.apply
+
+        def wrapped(*a, _orig=orig, _saved=saved):
+            out = _orig(*a)
+            fn = out.grad_fn
+            _saved.append([t.detach().clone() for t in fn.saved_tensors[6:9]])      # alpha, alpha_d, elog
+            return out
+        monkeypatch.setattr(txf.GatLayer, "apply", wrapped)
+        model = build_model(cfg, params, p_feat=p_drop, p_attn=p_drop, p_hidden=p_drop, p_out=p_drop).train()
+        g = tx.EgonetBatch.from_counts(n_gp, n_sib)
+        h = x.clone().requires_grad_(True)
+        torch.manual_seed(1234)                      # same dropout seeds (functional.new_seed) in both runs
+        scores = model(g, h, qf)
+        scores.sum().backward()
+        torch.cuda.synchronize()
+        outs[star] = (scores.detach(), g.ndata["h"].detach(), h.grad.clone(), saved,
+                      {k: p.grad.clone() for k, p in model.named_parameters()})
+        monkeypatch.setattr(txf.GatLayer, "apply", orig)
+    a, b = outs[True], outs[False]
+    assert len(a[3]) == len(b[3]) == 2
+    for la, lb in zip(a[3], b[3]):
+        for ta, tb in zip(la, lb):
+            assert float((ta - tb).abs().max()) <= 2e-6
+    assert float((a[1] - b[1]).abs().max()) <= TOL
+    assert float((a[0] - b[0]).abs().max()) <= TOL * max(1.0, float(b[0].abs().max()))
+    assert float((a[2] - b[2]).abs().max()) <= GTOL * float(b[2].abs().max())
+    gscale = max(float(v.abs().max()) for v in b[4].values())
+    for k in b[4]:
+        assert float((a[4][k] - b[4][k]).abs().max()) <= GTOL * max(float(b[4][k].abs().max()), 5e-2 * gscale), k
