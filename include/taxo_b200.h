@@ -243,7 +243,7 @@ int tx_gat_fused_fwd_staged(const float* ft, int64_t ldf, const float* attn_l, c
  *          siblings [c C, (c+1) C) with C = `chunk` (tx_gat_star_chunk() is the recommended value); chunk 0 (present for every
  *          egonet) also owns the grand-parents and the anchor; an egonet has max(1, ceil(n_sib / C)) <= tx_gat_star_max_chunks()
  *          chunks and n_gp < 2^24.
- *   queue: int32 [2 * heads] work-queue counters, ZERO before the first launch; the kernel leaves them zero again (one buffer per
+ *   queue: int32 [32 * heads] work-queue counters (one 128-byte line per head), ZERO before the first launch; the kernel leaves them zero again (one buffer per
  *          stream: concurrent launches must not share it).
  *   Exactly one of {out (fp32), out16_hi/out16_lo (+ bound, scale_out)} is written; alpha / alpha_d / elog per slot as usual. */
 int64_t tx_gat_star_chunk(void);

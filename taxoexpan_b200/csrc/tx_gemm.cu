@@ -16,6 +16,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "tx_common.cuh"
 
 namespace tx {
@@ -812,10 +814,12 @@ __global__ void split_f16_kernel(const float* __restrict__ x, int64_t ldx, int r
   }
 }
 
-// One launch for a WEIGHT matrix w [rows, cols]: max|w| (grid-wide, through a device counter: the grid is at most one CTA per SM,
-// so every CTA is resident and the spin below cannot deadlock), then the fp16 hi/lo split both row-major [rows, ld] (forward
+// One launch for a WEIGHT matrix w [rows, cols]: max|w| (grid-wide, through a device counter: the grid is at most kSplitWCtasPerSm
+// CTAs per SM and the launch bounds guarantee that many fit, so every CTA is resident and the spin below cannot deadlock), then
+// the fp16 hi/lo split both row-major [rows, ld] (forward
 // projection operand) and transposed [cols, ldt] (input-gradient operand) with the same scale.
-__global__ void __launch_bounds__(256) split_f16_weight_kernel(const float* __restrict__ w, int64_t ldw, int rows, int cols,
+constexpr int kSplitWCtasPerSm = 4;
+__global__ void __launch_bounds__(256, kSplitWCtasPerSm) split_f16_weight_kernel(const float* __restrict__ w, int64_t ldw, int rows, int cols,
                                                                __half* __restrict__ hi, __half* __restrict__ lo, int ld,
                                                                __half* __restrict__ hit, __half* __restrict__ lot, int ldt,
                                                                float* __restrict__ amax, unsigned int* __restrict__ counter,
@@ -823,9 +827,17 @@ __global__ void __launch_bounds__(256) split_f16_weight_kernel(const float* __re
   const int64_t total = (int64_t)rows * cols;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
   float m = 0.f;
-  for (int64_t t = tid; t < total; t += nth) {
-    const int i = (int)(t / cols), c = (int)(t - (int64_t)i * cols);
-    m = fmaxf(m, fabsf(__ldg(w + (int64_t)i * ldw + c)));
+  if (ldw == cols && (total & 3) == 0 && aligned16(w)) {       // a contiguous parameter tensor: flat 128-bit loads, no index arithmetic
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+    for (int64_t t = tid; t < (total >> 2); t += nth) {
+      const float4 v = __ldg(w4 + t);
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+  } else {
+    for (int64_t t = tid; t < total; t += nth) {
+      const int i = (int)(t / cols), c = (int)(t - (int64_t)i * cols);
+      m = fmaxf(m, fabsf(__ldg(w + (int64_t)i * ldw + c)));
+    }
   }
   m = warp_max(m);
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned int*>(amax), __float_as_uint(m));
@@ -1223,9 +1235,9 @@ int tx_split_f16_weight(const float* w, int64_t ldw, int64_t rows, int64_t cols,
              "split_f16_weight: outputs need ld %% 8 == 0 and 16-byte alignment");
   cudaStream_t st = (cudaStream_t)stream;
   if (cudaMemsetAsync(scratch2, 0, 2 * sizeof(float), st) != cudaSuccess) { set_error("split_f16_weight: memset failed"); return TX_ERR_CUDA; }
-  const int64_t total = rows * (ld > ld_t ? ld : ld_t);
-  int64_t grid = (total + 2047) / 2048;
-  if (grid > kNumSms) grid = kNumSms;     // <= one CTA per SM: the grid-wide rendezvous needs every CTA resident
+  const int64_t tiles = ((std::max(rows, ld_t) + 31) / 32) * ((std::max(cols, ld) + 31) / 32);      // 32 x 32 tiles of the split phase
+  int64_t grid = tiles;
+  if (grid > (int64_t)kNumSms * kSplitWCtasPerSm) grid = (int64_t)kNumSms * kSplitWCtasPerSm;     // the grid-wide rendezvous needs every CTA resident
   if (grid < 1) grid = 1;
   split_f16_weight_kernel<<<(int)grid, 256, 0, st>>>(w, ldw, (int)rows, (int)cols, (__half*)hi, (__half*)lo, (int)ld, (__half*)hi_t, (__half*)lo_t,
                                                      (int)ld_t, scratch2, reinterpret_cast<unsigned int*>(scratch2 + 1), scale_out);

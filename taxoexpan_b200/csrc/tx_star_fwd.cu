@@ -10,10 +10,11 @@
 //     softmax  out = a~_1 ft_anchor + a~_2 ft_self  (no online-softmax rescaling);
 //   * work items are (egonet, chunk of C siblings, head), one 16-byte host-built record each; chunk 0 also owns the grand-parents and
 //     the anchor.  Warps pull items from a self-resetting atomic queue (egonets have 1..2000 nodes: static dealing leaves a long
-//     tail); each warp bulk-prefetches the rows of its NEXT item into L2 (cp.async.bulk.prefetch) before working on the current one
-//     and keeps the next row of the current item in flight in registers.
+//     tail); each warp keeps the next row of its current item in flight in registers (an optional bulk L2 prefetch of the NEXT item's
+//     rows, TAXO_STAR_PREFETCH, measured no gain).
 // Each output element is produced by exactly one item in a fixed order: results are run-to-run deterministic.
 #include <math.h>
+#include <stdlib.h>
 
 #include "tx_common.cuh"
 
@@ -37,7 +38,9 @@ struct StarFwdParams {
   uint8_t* maskbits; int mask_ld;
   int hidden; float act_slope; const float* next_pos_table; const int32_t* pos; int pos_dim;
   float next_inv_keep; uint32_t next_thr; uint64_t next_seed; uint32_t next_stream;
-  int* queue;                             // [2 * H]: per head {next item, warps retired}; zero before the first launch, self-resetting
+  int* queue;                             // [32 * H]: per head (stride 32) {next item, warps retired}; zero before the first launch, self-resetting
+  int prefetch;                           // L2 prefetch of the next item's rows (TAXO_STAR_PREFETCH): 0 none (default: measured no gain - the
+                                          // kernel is issue-bound, not latency-bound), 1 anchor + first row, 2 all rows
 };
 
 struct StarTask { int o, q, a, s, c; };   // first node, first edge / slot, #grand-parents, #siblings, chunk
@@ -47,7 +50,8 @@ __device__ __forceinline__ void star_load_row(const float* __restrict__ p, int l
 #pragma unroll
   for (int t = 0; t < NV; ++t) {
     const int c = (lane + 32 * t) * 4;
-    v[t] = c < D ? __ldg(reinterpret_cast<const float4*>(p + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    // D > 128 (NV - 1): only the last column block can be partial
+    v[t] = (t < NV - 1 || c < D) ? __ldg(reinterpret_cast<const float4*>(p + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -200,7 +204,7 @@ __global__ void __launch_bounds__(256, TX_STAR_MIN_BLOCKS) gat_star_fwd_kernel(c
   const uint32_t rowB = (uint32_t)D * 4u;
   const float scale16 = p.out16_hi ? f16_split_scale(__ldg(p.bound)) : 1.f;
   if (p.out16_hi && p.scale_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *p.scale_out = scale16;
-  int* qn = p.queue + 2 * h;
+  int* qn = p.queue + 32 * h;              // one 128-byte line per head: the heads' tickets do not serialise on one L2 sector
 
   // work item record (host-built, one 16-byte load): {first node o, first edge / slot q, n_gp | chunk << 24, n_sib}
   auto decode = [&](int item) -> StarTask {
@@ -214,9 +218,10 @@ __global__ void __launch_bounds__(256, TX_STAR_MIN_BLOCKS) gat_star_fwd_kernel(c
   auto prefetch_item = [&](const StarTask& k) {
     const int k0 = k.c * p.chunk, k1 = min(k.s, k0 + p.chunk);
     const int rb = k.c == 0 ? k.o : k.o + k.a + 1 + k0, re = k.o + k.a + 1 + k1;
-    for (int r = rb + lane; r < re; r += 32)
+    if (p.prefetch == 0) return;
+    for (int r = rb + lane; r < (p.prefetch == 1 ? min(re, rb + 1) : re); r += 32)
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + (int64_t)r * p.ldf), "r"(rowB) : "memory");
-    if (k.c != 0 && lane == 31)
+    if ((k.c != 0 || p.prefetch == 1) && lane == 31)
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + (int64_t)(k.o + k.a) * p.ldf), "r"(rowB) : "memory");
   };
   auto keepw = [&](int eid) -> float {
@@ -365,8 +370,8 @@ __global__ void __launch_bounds__(256, TX_STAR_MIN_BLOCKS) gat_star_fwd_kernel(c
   }
   // ---- retire: the last warp of this head's queue resets it for the next launch ----
   if (lane == 0) {
+    // (this warp's last ticket has been read, i.e. performed, before this point: no fence needed to order the two counters)
     const int total = (int)(gridDim.x * (blockDim.x >> 5));
-    __threadfence();
     if (atomicAdd(qn + 1, 1) == total - 1) {
       qn[0] = 0;
       qn[1] = 0;
@@ -413,6 +418,7 @@ int tx_gat_star_fwd(const float* ft, int64_t ldf, const float* attn_l, const flo
   p.hidden = epi->mean_heads ? 0 : 1; p.act_slope = epi->act_slope; p.next_pos_table = epi->next_pos_table; p.pos = epi->pos;
   p.pos_dim = (int)epi->pos_dim; p.next_inv_keep = 1.f / (1.f - epi->p_drop); p.next_thr = drop_threshold(epi->p_drop);
   p.next_seed = epi->seed; p.next_stream = epi->stream_id; p.queue = queue;
+  { static int pf = -1; if (pf < 0) { const char* e = getenv("TAXO_STAR_PREFETCH"); pf = e ? atoi(e) : 0; } p.prefetch = pf; }
   const int nv = (int)((dim + 127) / 128);
   int gx = grid_for_warps(n_tasks * heads, 8, TX_STAR_MIN_BLOCKS);
   gx = (gx + (int)heads - 1) / (int)heads;

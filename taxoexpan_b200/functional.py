@@ -76,7 +76,7 @@ def _star_queue(device) -> torch.Tensor:
         from .graph import STAR_MAX_CHUNKS
         if int(lib.tx_gat_star_max_chunks()) != STAR_MAX_CHUNKS:
             raise _lib.TaxoLibraryError("tx_gat_star_fwd: task encoding of the library differs from taxoexpan_b200.graph; rebuild")
-        q = _star_queues[key] = torch.zeros(2 * 64, dtype=torch.int32, device=device)
+        q = _star_queues[key] = torch.zeros(32 * 64, dtype=torch.int32, device=device)
     return q
 
 
