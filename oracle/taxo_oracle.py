@@ -488,3 +488,122 @@ def get_subgraph_nodes(parents_of, children_of, query_node, anchor_node, instanc
     nodes.extend(kids)
     pos.extend([2] * len(kids))
     return nodes, pos
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# negative-anchor sampling and the egonet cache (the step before egonet construction)
+# ---------------------------------------------------------------------------------------------------------------------
+def node_masks(parents_of, children_of, nodes, roots):
+    """reference data_loader/dataset.py:248-258: node2masks[n] = descendants(n) + parents(n) + [n] + roots, for every n in `nodes`
+    (positions that must not be drawn as negative anchors of query n)."""
+    out = {}
+    for n in nodes:
+        seen, stack = set(), list(children_of.get(n, []))
+        while stack:                                   # nx.descendants: everything reachable through out-edges, n itself excluded
+            v = stack.pop()
+            if v in seen or v == n:
+                continue
+            seen.add(v)
+            stack.extend(children_of.get(v, []))
+        out[n] = set(list(seen) + list(parents_of.get(n, [])) + [n] + list(roots))
+    return out
+
+
+class NegativeQueueOracle:
+    """reference data_loader/dataset.py:285-287,334-381 restated line by line: a queue of candidate positions (train ids x 5)
+    walked by a pointer and reshuffled when exhausted; `rng` is a random.Random (the reference uses the module-level one)."""
+
+    def __init__(self, train_node_ids, node2masks, rng):
+        self.queue = (list(train_node_ids) * 5).copy()
+        self.pointer = 0
+        self.node2masks = node2masks
+        self.rng = rng
+
+    def at_most_k(self, query_node, negative_size):          # dataset.py:340-356
+        if self.pointer == 0:
+            self.rng.shuffle(self.queue)
+        while True:
+            negatives = [e for e in self.queue[self.pointer: self.pointer + negative_size] if e not in self.node2masks[query_node]]
+            if len(negatives) > 0:
+                break
+        self.pointer += negative_size
+        if self.pointer >= len(self.queue):
+            self.pointer = 0
+        return negatives
+
+    def exactly_k(self, query_node, negative_size):          # dataset.py:358-381
+        if self.pointer == 0:
+            self.rng.shuffle(self.queue)
+        masks = self.node2masks[query_node]
+        negatives = []
+        max_try = 0
+        while len(negatives) != negative_size:
+            n_lack = negative_size - len(negatives)
+            negatives.extend([e for e in self.queue[self.pointer: self.pointer + n_lack] if e not in masks])
+            self.pointer += n_lack
+            if self.pointer >= len(self.queue):
+                self.pointer = 0
+                self.rng.shuffle(self.queue)
+            max_try += 1
+            if max_try > 10:
+                if len(negatives) > negative_size:
+                    negatives = negatives[:negative_size]
+                else:
+                    negatives.extend([e for e in self.queue[: (negative_size - len(negatives))]])
+        return negatives
+
+
+_M64 = (1 << 64) - 1
+POSITIVE_GENERATION_BASE = 1 << 40
+
+
+def counter_draw(seed, anchor, generation, slot, degree):
+    """The counter-based replacement of `random.choices(out_edges, k=expand_factor)` (dataset.py:419,424) shared by the oracle and
+    taxoexpan_b200.sampler: draw number `slot` of generation `generation` of `anchor` = floor(u * degree), u a 53-bit uniform from a
+    splitmix64 finaliser of the four integers.  Pure function of its arguments, so a 'cached' egonet is reproducible from its
+    generation number alone."""
+    z = (seed ^ (anchor * 0x9E3779B97F4A7C15) ^ (generation * 0xC2B2AE3D27D4EB4F) ^ (slot * 0x165667B19E3779F9)) & _M64
+    z = (z + 0x9E3779B97F4A7C15) & _M64
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+    z ^= z >> 31
+    return min(int(float(z >> 11) * (degree / 2.0 ** 53)), degree - 1)
+
+
+class EgonetCacheOracle:
+    """reference data_loader/dataset.py:383-402 (`_get_subgraph_and_node_pair`) restated: negative egonets are cached per anchor
+    and reused until they have been read `cache_refresh_time` times; positives are always rebuilt and never cached.  The random
+    sibling draws of dataset.py:419,424 come from `counter_draw` (generation = number of earlier creations for that anchor)."""
+
+    def __init__(self, parents_of, children_of, expand_factor, cache_refresh_time, seed):
+        self.parents_of, self.children_of = parents_of, children_of
+        self.expand_factor, self.cache_refresh_time, self.seed = expand_factor, cache_refresh_time, seed
+        self.cache, self.cache_counter = {}, {}
+        self.created, self.positives = {}, 0
+
+    def _get_subgraph(self, query_node, anchor_node, instance_mode):
+        nodes = list(self.parents_of.get(anchor_node, []))
+        nodes.append(anchor_node)
+        kids = list(self.children_of.get(anchor_node, []))
+        if instance_mode == 0:
+            generation = self.created.get(anchor_node, 0)
+            self.created[anchor_node] = generation + 1
+        else:
+            generation = POSITIVE_GENERATION_BASE + self.positives
+            self.positives += 1
+        if len(kids) > self.expand_factor:
+            kids = [kids[counter_draw(self.seed, anchor_node, generation, t, len(kids))] for t in range(self.expand_factor)]
+        if instance_mode == 1:
+            kids = [k for k in kids if k != query_node]
+        return nodes + kids
+
+    def get(self, query_node, anchor_node, instance_mode):
+        if instance_mode == 0 and (anchor_node in self.cache) and (self.cache_counter[anchor_node] < self.cache_refresh_time):
+            g = self.cache[anchor_node]
+            self.cache_counter[anchor_node] += 1
+        else:
+            g = self._get_subgraph(query_node, anchor_node, instance_mode)
+            if instance_mode == 0:
+                self.cache[anchor_node] = g
+                self.cache_counter[anchor_node] = 0
+        return g

@@ -12,11 +12,15 @@ anchor (pos 2, in out-edge order)]; a positive instance (mode 1) drops the query
 than `expand_factor` children gets `expand_factor` children drawn WITH replacement (`random.choices`, dataset.py:419,424 - so
 duplicates can occur, and for positives the draws that hit the query are dropped afterwards).  The edge list itself is never
 materialised: `EgonetBatch.from_counts` + `tx_star_batch_structure` produce positions and both CSRs in closed form.
-Not covered (still "next"): the negative-anchor sampler and the egonet cache of dataset.py:334-402.
+The negative-anchor sampler (`NegativeSampler`, dataset.py:248-258,285-287,334-381) and the egonet cache (`EgonetCache`,
+dataset.py:383-402) are here too.  The cache does not store subgraphs: sibling draws are counter-based (a pure function of
+(seed, anchor, generation, slot)), so "reuse the cached egonet of this anchor until it has been read cache_refresh_time times" is
+one integer per node - the number of negative uses so far - and generation = uses // (cache_refresh_time + 1).
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+import random
+from typing import Dict, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -53,9 +57,38 @@ class TaxonomyCSR:
         return self.par_ptr.device
 
 
+POSITIVE_GENERATION_BASE = 1 << 40
+
+
+def _i64(c: int) -> int:
+    """a 64-bit constant as the signed value torch.int64 holds for the same bit pattern"""
+    return c - (1 << 64) if c >= (1 << 63) else c
+
+
+def _lsr(z: torch.Tensor, k: int) -> torch.Tensor:
+    """logical right shift of int64 bit patterns"""
+    return (z >> k) & ((1 << (64 - k)) - 1)
+
+
+def counter_draws(seed: int, anchor: torch.Tensor, generation: torch.Tensor, slot: torch.Tensor, degree: torch.Tensor) -> torch.Tensor:
+    """floor(u * degree) with u a 53-bit uniform from a splitmix64 finaliser of (seed, anchor, generation, slot): the counter-based
+    replacement of `random.choices(out_edges, k=expand_factor)` (dataset.py:419,424); bit-for-bit `oracle.counter_draw`.  int64
+    tensors wrap modulo 2^64 like the unsigned arithmetic of the definition."""
+    z = (anchor * _i64(0x9E3779B97F4A7C15)) ^ (generation * _i64(0xC2B2AE3D27D4EB4F)) ^ (slot * _i64(0x165667B19E3779F9)) ^ _i64(seed & ((1 << 64) - 1))
+    z = z + _i64(0x9E3779B97F4A7C15)
+    z = (z ^ _lsr(z, 30)) * _i64(0xBF58476D1CE4E5B9)
+    z = (z ^ _lsr(z, 27)) * _i64(0x94D049BB133111EB)
+    z = z ^ _lsr(z, 31)
+    pick = (_lsr(z, 11).to(torch.float64) * (degree.to(torch.float64) / 2.0 ** 53)).to(torch.int64)
+    return torch.minimum(pick, torch.clamp(degree - 1, min=0))
+
+
 def egonet_node_ids(tax: TaxonomyCSR, anchors, queries, modes, expand_factor: int = 50,
-                    generator: Optional[torch.Generator] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """(ids [N] int64 in batched egonet order, n_gp [G], n_sib [G]) on tax.device - dataset.py:404-426 for G egonets at once."""
+                    generator: Optional[torch.Generator] = None, draw_seed: Optional[int] = None,
+                    generation: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(ids [N] int64 in batched egonet order, n_gp [G], n_sib [G]) on tax.device - dataset.py:404-426 for G egonets at once.
+    Sibling draws of anchors with more than expand_factor children: torch.rand (`generator`) by default; with `draw_seed` and a
+    per-egonet `generation` [G] they are `counter_draws(draw_seed, anchor, generation, slot, degree)` (see EgonetCache)."""
     dev = tax.device
     a = torch.as_tensor(anchors, dtype=torch.int64, device=dev).reshape(-1)
     q = torch.as_tensor(queries, dtype=torch.int64, device=dev).reshape(-1)
@@ -75,8 +108,13 @@ def egonet_node_ids(tax: TaxonomyCSR, anchors, queries, modes, expand_factor: in
     is_sib = local > ngp_g
     t_sib = local - ngp_g - 1
     # children: all of them in out-edge order, or expand_factor uniform draws with replacement
-    draw = torch.rand(total, device=dev, generator=generator)
-    pick = torch.where(deg_g <= expand_factor, t_sib, torch.clamp((draw * deg_g).to(torch.int64), max=torch.clamp(deg_g - 1, min=0)))
+    if draw_seed is not None:
+        gen = torch.as_tensor(generation, dtype=torch.int64, device=dev).reshape(-1)
+        drawn = counter_draws(int(draw_seed), a_g, gen[gid], torch.clamp(t_sib, min=0), deg_g)
+    else:
+        draw = torch.rand(total, device=dev, generator=generator)
+        drawn = torch.clamp((draw * deg_g).to(torch.int64), max=torch.clamp(deg_g - 1, min=0))
+    pick = torch.where(deg_g <= expand_factor, t_sib, drawn)
     gp_src = tax.par_ptr[a_g] + local
     sib_src = tax.chi_ptr[a_g] + pick
     n_par, n_chi = tax.par_idx.numel(), tax.chi_idx.numel()
@@ -89,11 +127,155 @@ def egonet_node_ids(tax: TaxonomyCSR, anchors, queries, modes, expand_factor: in
     return ids[keep], n_gp, n_sib
 
 
+class EgonetCache:
+    """dataset.py:383-402 without stored subgraphs.  The reference keeps, per negative anchor, the last egonet it built and hands
+    it out again until it has been read `cache_refresh_time` times (positives are rebuilt every time and never cached).  With
+    counter-based draws the egonet of an anchor is a pure function of its generation number, so the whole cache is `uses[node]` =
+    how often the node has served as a negative anchor: use number u belongs to generation u // (cache_refresh_time + 1).
+    `generations()` numbers the egonets of one batch exactly as the reference's sequential loop would (duplicates of an anchor
+    inside a batch advance its counter one by one, in batch order)."""
+
+    def __init__(self, num_nodes: int, cache_refresh_time: int, seed: int = 0, device="cpu"):
+        self.uses = torch.zeros(num_nodes, dtype=torch.int64, device=device)
+        self.period = int(cache_refresh_time) + 1
+        self.seed = int(seed)
+        self.positives = 0
+
+    def generations(self, anchors, modes) -> torch.Tensor:
+        dev = self.uses.device
+        a = torch.as_tensor(anchors, dtype=torch.int64, device=dev).reshape(-1)
+        m = torch.as_tensor(modes, dtype=torch.int64, device=dev).reshape(-1)
+        gen = torch.zeros_like(a)
+        pos_idx = torch.nonzero(m == 1).reshape(-1)
+        gen[pos_idx] = POSITIVE_GENERATION_BASE + self.positives + torch.arange(pos_idx.numel(), device=dev)
+        self.positives += int(pos_idx.numel())
+        neg_idx = torch.nonzero(m != 1).reshape(-1)
+        if neg_idx.numel():
+            an = a[neg_idx]
+            order = torch.sort(an, stable=True).indices              # occurrences of one anchor stay in batch order
+            sa = an[order]
+            first = torch.ones_like(sa, dtype=torch.bool)
+            first[1:] = sa[1:] != sa[:-1]
+            start = torch.cummax(torch.where(first, torch.arange(sa.numel(), device=dev), torch.zeros_like(sa)), 0).values
+            rank = torch.arange(sa.numel(), device=dev) - start      # 0, 1, 2, ... within each anchor
+            g_sorted = (self.uses[sa] + rank) // self.period
+            gn = torch.empty_like(g_sorted)
+            gn[order] = g_sorted
+            gen[neg_idx] = gn
+            self.uses.index_add_(0, an, torch.ones_like(an))
+        return gen
+
+
+def taxonomy_masks(tax: TaxonomyCSR, nodes: Sequence[int], roots: Sequence[int]) -> Dict[int, np.ndarray]:
+    """node2masks of dataset.py:248-258 as sorted arrays: descendants(n) + parents(n) + [n] + roots for every n in `nodes`
+    (frontier expansion over the children CSR; the graph is a DAG but cycles are tolerated)."""
+    chi_ptr, chi_idx = tax.chi_ptr.cpu().numpy(), tax.chi_idx.cpu().numpy()
+    par_ptr, par_idx = tax.par_ptr.cpu().numpy(), tax.par_idx.cpu().numpy()
+    roots = np.asarray(list(roots), dtype=np.int64)
+    out = {}
+    for n in nodes:
+        seen = np.zeros(0, dtype=np.int64)
+        frontier = chi_idx[chi_ptr[n]:chi_ptr[n + 1]]
+        while frontier.size:
+            frontier = np.setdiff1d(np.unique(frontier), seen, assume_unique=True)
+            frontier = frontier[frontier != n]
+            if not frontier.size:
+                break
+            seen = np.union1d(seen, frontier)
+            cnt = chi_ptr[frontier + 1] - chi_ptr[frontier]
+            if not cnt.sum():
+                break
+            base = np.repeat(chi_ptr[frontier], cnt)
+            within = np.arange(cnt.sum()) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+            frontier = chi_idx[base + within]
+        out[int(n)] = np.unique(np.concatenate([seen, par_idx[par_ptr[n]:par_ptr[n + 1]], [n], roots]).astype(np.int64))
+    return out
+
+
+class NegativeSampler:
+    """dataset.py:285-287,334-381: negative anchors come from a queue (train ids x 5) walked by a pointer shared by all queries and
+    reshuffled with `random.shuffle` whenever it is exhausted; positions in the query's mask are skipped.  Same sequence as the
+    reference for the same `random.Random` state (the reference uses the module-level generator); the membership test runs on
+    sorted mask arrays instead of Python sets."""
+
+    def __init__(self, train_node_ids: Sequence[int], node2masks: Dict[int, np.ndarray], rng: Optional[random.Random] = None):
+        self.queue = list(train_node_ids) * 5
+        self.pointer = 0
+        self.node2masks = node2masks
+        self.rng = rng if rng is not None else random
+        self._arr = None                      # numpy view of the queue, rebuilt after every shuffle
+
+    def _shuffle(self):
+        self.rng.shuffle(self.queue)
+        self._arr = None
+
+    def _window(self, lo: int, n: int, mask: np.ndarray) -> list:
+        if self._arr is None:
+            self._arr = np.asarray(self.queue, dtype=np.int64)
+        w = self._arr[lo:lo + n]
+        if not mask.size or not w.size:
+            return w.tolist()
+        at = np.searchsorted(mask, w)
+        hit = mask[np.minimum(at, mask.size - 1)] == w
+        return w[~hit].tolist()
+
+    def at_most_k(self, query_node: int, negative_size: int) -> list:
+        """dataset.py:340-356 (sampling_mode 0)"""
+        if self.pointer == 0:
+            self._shuffle()
+        mask = self.node2masks[query_node]
+        while True:
+            negatives = self._window(self.pointer, negative_size, mask)
+            if len(negatives) > 0:
+                break
+        self.pointer += negative_size
+        if self.pointer >= len(self.queue):
+            self.pointer = 0
+        return negatives
+
+    def exactly_k(self, query_node: int, negative_size: int) -> list:
+        """dataset.py:358-381 (sampling_mode 1: the InfoNCE layout of one positive followed by exactly negative_size negatives)"""
+        if self.pointer == 0:
+            self._shuffle()
+        mask = self.node2masks[query_node]
+        negatives = []
+        max_try = 0
+        while len(negatives) != negative_size:
+            n_lack = negative_size - len(negatives)
+            negatives.extend(self._window(self.pointer, n_lack, mask))
+            self.pointer += n_lack
+            if self.pointer >= len(self.queue):
+                self.pointer = 0
+                self._shuffle()
+            max_try += 1
+            if max_try > 10:                  # corner case of the reference: trim / pad from the head of the queue, mask ignored
+                if len(negatives) > negative_size:
+                    negatives = negatives[:negative_size]
+                else:
+                    negatives.extend(self.queue[:negative_size - len(negatives)])
+        return negatives
+
+    def batch(self, query_nodes: Sequence[int], positive_parents: Sequence[int], negative_size: int):
+        """(anchors, queries, modes) of a training batch in the reference's order (dataset.py:308-332 + data_loaders.py:9-28):
+        per query its positive parent first, then exactly `negative_size` negatives."""
+        anchors, queries, modes = [], [], []
+        for q, p in zip(query_nodes, positive_parents):
+            neg = self.exactly_k(int(q), negative_size)
+            anchors += [int(p)] + neg
+            queries += [int(q)] * (1 + len(neg))
+            modes += [1] + [0] * len(neg)
+        return np.asarray(anchors, np.int64), np.asarray(queries, np.int64), np.asarray(modes, np.int64)
+
+
 def build_egonet_batch(tax: TaxonomyCSR, features: torch.Tensor, anchors, queries, modes, expand_factor: int = 50,
-                       generator: Optional[torch.Generator] = None):
+                       generator: Optional[torch.Generator] = None, cache: Optional[EgonetCache] = None):
     """(EgonetBatch, x [N, d], ids [N]): the batched graph of `collate_graph_and_node_small_batch` (data_loaders.py:9-28) with
     ndata 'x' / '_id' / 'pos' semantics - x and ids are returned as device tensors, positions come from the closed-form structure."""
-    ids, n_gp, n_sib = egonet_node_ids(tax, anchors, queries, modes, expand_factor, generator)
+    if cache is not None:           # dataset.py:383-402: negatives reuse their anchor's egonet until it has been read cache_refresh_time times
+        ids, n_gp, n_sib = egonet_node_ids(tax, anchors, queries, modes, expand_factor, draw_seed=cache.seed,
+                                           generation=cache.generations(anchors, modes).to(tax.device))
+    else:
+        ids, n_gp, n_sib = egonet_node_ids(tax, anchors, queries, modes, expand_factor, generator)
     bg = EgonetBatch.from_counts(n_gp.cpu().numpy().astype(np.int32), n_sib.cpu().numpy().astype(np.int32))
     x = features.index_select(0, ids.to(features.device))
     bg.ndata["_id"] = ids

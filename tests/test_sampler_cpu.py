@@ -65,3 +65,87 @@ def test_sampled_children_follow_random_choices_semantics():
     assert abs(hits / (G * ef) - 1.0 / 150) < 3e-3        # each draw hits the query with probability 1 / 150
     neg_ids, _, neg_sib = sampler.egonet_node_ids(tax, np.zeros(8, np.int64), np.full(8, 7), np.zeros(8, np.int64), expand_factor=ef, generator=g)
     assert neg_sib.tolist() == [ef] * 8                   # negatives keep every draw
+
+
+def test_counter_draws_match_the_oracle_definition():
+    rng = np.random.default_rng(11)
+    n = 500
+    anchor = rng.integers(0, 10 ** 6, n)
+    gen = np.where(rng.random(n) < 0.5, rng.integers(0, 50, n), sampler.POSITIVE_GENERATION_BASE + rng.integers(0, 10 ** 6, n))
+    slot = rng.integers(0, 50, n)
+    deg = rng.integers(1, 5000, n)
+    for seed in (0, 12345, (1 << 63) + 7):
+        got = sampler.counter_draws(seed, torch.from_numpy(anchor), torch.from_numpy(gen), torch.from_numpy(slot), torch.from_numpy(deg))
+        want = [orc.counter_draw(seed, int(a), int(g), int(s), int(d)) for a, g, s, d in zip(anchor, gen, slot, deg)]
+        assert got.tolist() == want
+        assert int(got.min()) >= 0 and bool((got < torch.from_numpy(deg)).all())
+
+
+def test_egonet_cache_reproduces_the_reference_cache_semantics():
+    """dataset.py:383-402: a negative anchor's egonet is reused until it has been read cache_refresh_time times, positives are
+    always rebuilt; repeated anchors inside one batch advance the counter in batch order.  Checked over several batches against
+    the sequential dict-cache restatement, node list by node list."""
+    rng = np.random.default_rng(5)
+    n, ef, refresh = 300, 4, 2
+    par, chi, parents_of, children_of = _random_taxonomy(n, 2500, rng)       # ~8 children per node: most anchors exceed ef = 4
+    tax = sampler.TaxonomyCSR.from_edges(par, chi, n)
+    cache = sampler.EgonetCache(n, refresh, seed=99)
+    ref = orc.EgonetCacheOracle(parents_of, children_of, ef, refresh, seed=99)
+    changed = 0
+    last = {}
+    for step in range(6):
+        G = 200
+        anchors = rng.integers(0, 40, G)                 # few distinct anchors: every one is hit many times per batch
+        modes = (rng.random(G) < 0.2).astype(np.int64)
+        queries = np.array([rng.choice(children_of[a]) if (m == 1 and a in children_of) else rng.integers(0, n)
+                            for a, m in zip(anchors, modes)])
+        feats = torch.arange(n, dtype=torch.float32)[:, None]
+        bg, x, ids = sampler.build_egonet_batch(tax, feats, anchors, queries, modes, expand_factor=ef, cache=cache)
+        off = np.concatenate([[0], np.cumsum(bg.batch_num_nodes)])
+        ids = ids.tolist()
+        for k, (a, q, m) in enumerate(zip(anchors.tolist(), queries.tolist(), modes.tolist())):
+            want = ref.get(q, a, m)
+            assert ids[off[k]:off[k + 1]] == want, (step, k)
+            if m == 0:
+                changed += int(a in last and last[a] != want)
+                last[a] = want
+    assert changed > 20                                   # the cache did refresh (the test would be vacuous otherwise)
+    assert cache.positives == ref.positives
+    assert {a: int(c) for a, c in enumerate(cache.uses.tolist()) if c} == \
+        {a: (ref.created[a] - 1) * (refresh + 1) + ref.cache_counter[a] + 1 for a in ref.created}
+
+
+def test_negative_sampler_matches_the_reference_queue_walk():
+    import random
+    rng = np.random.default_rng(8)
+    n = 120
+    par, chi, parents_of, children_of = _random_taxonomy(n, 200, rng)
+    keep = par < chi                                      # a DAG
+    par, chi = par[keep], chi[keep]
+    parents_of, children_of = {}, {}
+    for p, c in zip(par.tolist(), chi.tolist()):
+        parents_of.setdefault(c, []).append(p)
+        children_of.setdefault(p, []).append(c)
+    tax = sampler.TaxonomyCSR.from_edges(par, chi, n)
+    roots = [v for v in range(n) if v not in parents_of]
+    train = [v for v in range(n) if v % 5 != 0]
+    queries = [v for v in train if v not in roots]
+    want_masks = orc.node_masks(parents_of, children_of, queries, roots)
+    masks = sampler.taxonomy_masks(tax, queries, roots)
+    assert {k: sorted(v) for k, v in want_masks.items()} == {k: v.tolist() for k, v in masks.items()}
+    got_s = sampler.NegativeSampler(train, masks, random.Random(42))
+    ref_s = orc.NegativeQueueOracle(train, want_masks, random.Random(42))
+    for rep in range(40):                                 # > one pass over the queue: exercises the reshuffle
+        for q in queries[:20]:
+            assert got_s.exactly_k(q, 31) == ref_s.exactly_k(q, 31)
+        assert got_s.pointer == ref_s.pointer
+    for q in queries[:30]:
+        assert got_s.at_most_k(q, 7) == ref_s.at_most_k(q, 7)
+    # a query whose mask covers every candidate: the reference gives up after 10 tries and pads from the head of the queue
+    full = {queries[0]: np.arange(n)}
+    a = sampler.NegativeSampler(train, full, random.Random(1)).exactly_k(queries[0], 5)
+    b = orc.NegativeQueueOracle(train, {queries[0]: set(range(n))}, random.Random(1)).exactly_k(queries[0], 5)
+    assert a == b and len(a) >= 5
+    anchors, qs, modes = got_s.batch(queries[:4], [parents_of[q][0] for q in queries[:4]], 31)
+    assert anchors.shape == (4 * 32,) and modes.reshape(4, 32)[:, 0].tolist() == [1] * 4 and int(modes.sum()) == 4
+    assert qs.reshape(4, 32)[:, 0].tolist() == queries[:4]
