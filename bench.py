@@ -390,7 +390,8 @@ def run_b200(args, rank, world, local_rank):
     step_prof_ms = sum(v for k, v in kern.items() if not k.startswith(nested) or txf.GEMM_BACKEND == "cublas")
     rl = []
     for tag, H, W in (("L0", H0, W0), ("L1", H1, W1)):
-        for fwd_names, label in ((("tx_gat_fused_fwd_staged",), "tx_gat_fused_fwd_staged"), (("tx_gat_fused_fwd", "tx_gat_fused_fwd_f16"), "tx_gat_fused_fwd"),
+        for fwd_names, label in ((("tx_gat_star_fwd",), "tx_gat_star_fwd"), (("tx_gat_fused_fwd_staged",), "tx_gat_fused_fwd_staged"),
+                                 (("tx_gat_fused_fwd", "tx_gat_fused_fwd_f16"), "tx_gat_fused_fwd"),
                                  (("tx_gat_node_logits", "tx_gat_aggregate_fwd"), "tx_gat_node_logits+aggregate_fwd")):
             t_f = sum(avg(nm, tag) for nm in fwd_names)
             if t_f > 0:

@@ -6,7 +6,7 @@ nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,memory.total,driver_ver
 timeout 300 python bench.py --impl reference --steps 10 --warmup 2 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
 timeout 400 python bench.py --steps 30 --warmup 5 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/b_ncu.log 2>&1
-timeout 700 ncu -k regex:'gat_bwd_staged|gat_fused_fwd|gemm_tf32x3' --launch-skip 26 -c 26 --set full --import-source on --clock-control none -f -o gpurun_out/kernels_full python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+timeout 700 ncu -k regex:'gat_bwd_staged|gat_fused_fwd|gat_star_fwd|gemm_tf32x3' --launch-skip 26 -c 26 --set full --import-source on --clock-control none -f -o gpurun_out/kernels_full python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 tail -n 2 gpurun_out/pytest_gpu.log
 tail -n 2 gpurun_out/ncu_full.log
 head -c 1200 gpurun_out/bench_n1.json

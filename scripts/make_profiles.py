@@ -82,9 +82,10 @@ with open(os.path.join(DST, "r1_ncu_full_summary.csv"), "w", newline="") as f:
         dw = to_bytes(r[hdr.index("dram__bytes_write.sum")], units[hdr.index("dram__bytes_write.sum")])
         per_kernel[name.split("(")[0]].append((float(r[hdr.index("gpu__time_duration.sum")].replace(",", "")), dr + dw))
 traffic = {}
-for key, label in (("gat_bwd_staged_kernel", "tx_gat_fused_bwd_staged"), ("gat_fused_fwd_kernel", "tx_gat_fused_fwd")):
-    ls = [v for k, v in per_kernel.items() if key in k]
-    ls = sorted(ls[0], key=lambda t: -t[1]) if ls else []
+for key, label in (("gat_bwd_staged_kernel", "tx_gat_fused_bwd_staged"), ("gat_fused_fwd_kernel", "tx_gat_fused_fwd"),
+                   ("gat_star_fwd_kernel", "tx_gat_star_fwd")):
+    ls = [t for k, v in per_kernel.items() if key in k for t in v]      # all template instances of the kernel
+    ls = sorted(ls, key=lambda t: -t[1])
     if ls and ls[0][1] > 2.5 * ls[-1][1]:                          # L0 launches move ~4x the bytes of L1 launches
         cut = (ls[0][1] * ls[-1][1]) ** 0.5
         big = [b for _, b in ls if b > cut]
