@@ -111,6 +111,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def wait_ready(self, timeout=5.0):
+        """Blocks until nvidia-smi has delivered its first sample: its start-up (NVML initialisation, 0.1-0.3 s, takes driver locks)
+        must not overlap the first timed loop - measured: a 30-step loop (60 ms) that raced it enqueued at 2.8 ms/step instead of 1.6."""
+        t0 = time.perf_counter()
+        while self.proc and not self.lines and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -325,13 +332,15 @@ def run_b200(args, rank, world, local_rank):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), Stats.launches, Stats.timings_ms() if profile else {}
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()          # sampled across the value, per-kernel and e2e loops (a 30-step loop alone is ~0.1 s)
     for i in range(nb):          # setup: touch every rotating batch once (its tile table, the allocator's block sizes for its shape);
         step_resident(i)         # a batch first seen inside the timed region costs a cudaMalloc storm of ~100 ms
     for i in range(max(args.warmup, 3)):
         step_resident(i)
-    sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()          # sampled across the value, per-kernel and e2e loops (a 30-step loop alone is ~0.1 s)
+        sampler.wait_ready()     # nvidia-smi's start-up stays outside the timed loops; from here on it only polls every 100 ms
     total_ms, launches, _ = timed(step_resident, args.steps)
     host_enqueue_ms = timed.host_enqueue_ms
 

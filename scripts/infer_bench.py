@@ -27,7 +27,23 @@ for _ in range(3):
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 3
 G = sum(sh.num_graphs for sh, _ in chunks); N = sum(sh.total_nodes for sh, _ in chunks)
-print(f"encode ({name}-shaped): {G} egonets / {N} nodes in {ms:.2f} ms  -> {G / ms * 1e3 / 1e6:.2f} M egonets/s forward-only")
+print(f"encode ({name}-shaped): {G} egonets / {N} nodes in {ms:.2f} ms  -> {G / ms * 1e3 / 1e6:.2f} M egonets/s forward-only "
+      f"(EgonetBatch built from host counts inside the timed region; star forward {'on' if tx.functional.STAR_FWD else 'off'})")
+t0 = time.perf_counter()
+for _ in range(3):
+    built = [(tx.EgonetBatch.from_counts(sh.n_gp, sh.n_sib), x) for sh, x in chunks]
+t_build = (time.perf_counter() - t0) / 3 * 1e3
+for g, _ in built:
+    g.structure(dev)
+torch.cuda.synchronize()
+e0.record()
+for _ in range(3):
+    for g, _ in built:
+        g.ndata["pos"] = tx.graph._LazyPos(g)
+    hg = tx.inference.encode_positions(model, iter(built))
+e1.record(); torch.cuda.synchronize()
+ms2 = e0.elapsed_time(e1) / 3
+print(f"  host construction of the 3 batches: {t_build:.2f} ms; encode with resident structures: {ms2:.2f} ms -> {G / ms2 * 1e3 / 1e6:.2f} M egonets/s")
 Q = 2048
 queries = torch.from_numpy(synth.unit_rows(Q, 250, seed=7)).to(dev)
 rng = np.random.default_rng(0)

@@ -109,3 +109,33 @@ def test_synthetic_shapes_statistics():
     assert s.total_edges == 2 * s.total_nodes - s.num_graphs
     assert 3.5 < s.total_nodes / s.num_graphs < 6.0 and int(s.num_nodes.max()) <= 1 + 50 + 8
     assert (s.n_sib <= 50).all() and (s.n_gp >= 1).all()
+
+
+def test_star_task_records_cover_every_sibling_exactly_once():
+    """EgonetBatch ships one 16-byte record {node_off, edge_off, n_gp | chunk << 24, n_sib} per (egonet, chunk of STAR_CHUNK siblings)
+    for tx_gat_star_fwd (include/taxo_b200.h): chunk 0 exists for every egonet, chunks tile [0, n_sib) without gaps or overlaps."""
+    import numpy as np
+    from taxoexpan_b200 import graph as txg
+    rng = np.random.default_rng(0)
+    n_gp = rng.integers(0, 5, 200)
+    n_sib = np.concatenate([rng.integers(0, 60, 190), [0, 1, txg.STAR_CHUNK, txg.STAR_CHUNK + 1, 4 * txg.STAR_CHUNK, 0, 0, 7, 50, 50]])
+    g = tx.EgonetBatch.from_counts(n_gp, n_sib)
+    rec = g._packed.numpy()[g._task_off:g._task_off + 4 * g._n_tasks].reshape(-1, 4)
+    assert g._task_off % 4 == 0 and rec.shape[0] == int(np.maximum(1, -(-n_sib // txg.STAR_CHUNK)).sum())
+    node_off = np.concatenate([[0], np.cumsum(n_gp + 1 + n_sib)])
+    edge_off = np.concatenate([[0], np.cumsum(2 * (n_gp + 1 + n_sib) - 1)])
+    covered = [np.zeros(s, dtype=int) for s in n_sib]
+    owner_of = {int(o): k for k, o in enumerate(node_off[:-1])}
+    seen_chunk0 = set()
+    for o, q, ac, s in rec.tolist():
+        k = owner_of[o]
+        a, c = ac & 0xFFFFFF, ac >> 24
+        assert (q, a, s) == (edge_off[k], n_gp[k], n_sib[k])
+        if c == 0:
+            seen_chunk0.add(k)
+        covered[k][c * txg.STAR_CHUNK:min(s, (c + 1) * txg.STAR_CHUNK)] += 1
+    assert seen_chunk0 == set(range(len(n_gp)))
+    assert all((c == 1).all() for c in covered)
+    # a batch the encoding cannot hold (more chunks than the 7-bit field) falls back to the general kernel: no records
+    big = tx.EgonetBatch.from_counts([1], [txg.STAR_CHUNK * txg.STAR_MAX_CHUNKS + 1])
+    assert big._n_tasks == 0
