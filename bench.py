@@ -212,6 +212,20 @@ def run_b200(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     torch.backends.cuda.matmul.allow_tf32 = False          # parity bar is fp32 1e-5
+    # one process per GPU: give every rank its own slice of the host cores (the enqueue thread of a rank, its autograd thread and
+    # NCCL's proxy threads otherwise migrate over / pile up on the same cores; a step is host-bound at ~1.6 ms of enqueue)
+    host_info = {"cpus_visible": None, "cpus_pinned": None}
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+        host_info["cpus_visible"] = len(cpus)
+        lw = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+        if world > 1 and args.pin_cores and len(cpus) >= 2 * lw:
+            per = len(cpus) // lw
+            mine = cpus[local_rank * per:(local_rank + 1) * per]
+            os.sched_setaffinity(0, mine)
+            host_info["cpus_pinned"] = len(mine)
+    except (AttributeError, OSError):
+        pass
     _lib.load()
     nq = args.queries
     nb = args.batches
@@ -465,6 +479,7 @@ def run_b200(args, rank, world, local_rank):
         "kernel_ms_per_step": kern,
         "kernel_ms_sum": round(step_prof_ms, 4),
         "cpu_baseline": cpu,
+        "host": host_info,
     }
     print(json.dumps(line), flush=True)
 
@@ -478,6 +493,7 @@ def main():
     ap.add_argument("--queries", type=int, default=256, help="queries per GPU per step (x32 egonets)")
     ap.add_argument("--batches", type=int, default=4, help="distinct rotating synthetic batches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pin-cores", dest="pin_cores", action="store_false", help="N > 1: do not partition the host cores among the ranks")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
