@@ -139,3 +139,17 @@ def test_star_task_records_cover_every_sibling_exactly_once():
     # a batch the encoding cannot hold (more chunks than the 7-bit field) falls back to the general kernel: no records
     big = tx.EgonetBatch.from_counts([1], [txg.STAR_CHUNK * txg.STAR_MAX_CHUNKS + 1])
     assert big._n_tasks == 0
+
+
+def test_matching_and_loss_have_no_cpu_path():
+    """SURVEY 8 f1 surface: `info_nce_loss(output, target)` (model/loss.py:52-57) and the BIM / LBM row-dot run on the CUDA library
+    only - CPU tensors raise instead of silently taking a torch fallback."""
+    import torch
+    out = torch.randn(4, 32)
+    with pytest.raises(tx.TaxoLibraryError):
+        tx.info_nce_loss(out, torch.zeros(4, dtype=torch.long))
+    with pytest.raises(ValueError):
+        tx.info_nce_loss(out.reshape(-1), None)
+    from taxoexpan_b200 import functional as txf
+    with pytest.raises(tx.TaxoLibraryError):
+        txf.match_rowdot(torch.randn(4, 8), torch.randn(4, 8), True)
