@@ -10,8 +10,8 @@
 //     softmax  out = a~_1 ft_anchor + a~_2 ft_self  (no online-softmax rescaling);
 //   * work items are (egonet, chunk of C siblings, head), one 16-byte host-built record each; chunk 0 also owns the grand-parents and
 //     the anchor.  Warps pull items from a self-resetting atomic queue (egonets have 1..2000 nodes: static dealing leaves a long
-//     tail); each warp keeps the next row of its current item in flight in registers (an optional bulk L2 prefetch of the NEXT item's
-//     rows, TAXO_STAR_PREFETCH, measured no gain).
+//     tail).  Neither a register double buffer for the next row nor a bulk L2 prefetch of the NEXT item's rows (TAXO_STAR_PREFETCH)
+//     measured any gain: 24 resident warps per SM hide the loads, the kernel is issue-bound.
 // Each output element is produced by exactly one item in a fixed order: results are run-to-run deterministic.
 #include <math.h>
 #include <stdlib.h>
@@ -251,25 +251,23 @@ __global__ void __launch_bounds__(256, TX_STAR_MIN_BLOCKS) gat_star_fwd_kernel(c
     // local rows of this item: chunk 0 -> [0, a + 1 + min(s, C)) = grand-parents, anchor, first siblings; chunk c -> its siblings
     const int k0 = ck.c * p.chunk, k1 = min(s, k0 + p.chunk);
     const int j0 = ck.c == 0 ? 0 : a + 1 + k0, j1 = a + 1 + k1;
-    float4 ra[NV], nx[NV];
+    float4 ra[NV];
     star_load_row<NV>(base + (int64_t)(o + a) * p.ldf, lane, D, ra);
-    if (j0 != a && j0 < j1) star_load_row<NV>(base + (int64_t)(o + j0) * p.ldf, lane, D, nx);     // first non-anchor row in flight
     float a1a, a2a;
     star_dots<NV>(ra, s_l, s_r, lane, a1a, a2a);
     float m = -INFINITY, l = 0.f, s_mine = 0.f, kw_mine = 1.f;     // softmax statistics over the anchor's in-edges (chunk 0 only)
 
     for (int j = j0; j < j1; ++j) {
       const bool is_anchor = j == a, is_sib = j > a;
-      const bool more = j + 1 < j1 && j + 1 != a;      // the next local row needs a load (the anchor row is resident)
       float4 r[NV];
       float a1r = a1a, a2r = a2a;
       if (is_anchor) {
 #pragma unroll
         for (int t = 0; t < NV; ++t) r[t] = ra[t];
       } else {
-#pragma unroll
-        for (int t = 0; t < NV; ++t) r[t] = nx[t];
-        if (more) star_load_row<NV>(base + (int64_t)(o + j + 1) * p.ldf, lane, D, nx);             // next row in flight
+        // (keeping the next row in flight in a second register buffer measured no gain: 24 resident warps hide the load, and the
+        //  copy + 16 registers cost ~4 % of the instructions)
+        star_load_row<NV>(base + (int64_t)(o + j) * p.ldf, lane, D, r);
         star_dots<NV>(r, s_l, s_r, lane, a1r, a2r);
       }
       const float kw_self = keepw(self0 + j);                        // self loop of local row j: edge id self0 + j
@@ -305,6 +303,7 @@ __global__ void __launch_bounds__(256, TX_STAR_MIN_BLOCKS) gat_star_fwd_kernel(c
             for (int t = 0; t < NV; ++t) { r[t].x *= w; r[t].y *= w; r[t].z *= w; r[t].w *= w; }
           }
           for (int k = 0; k < a; ++k) {
+            float4 nx[NV];
             star_load_row<NV>(base + (int64_t)(o + k) * p.ldf, lane, D, nx);
             float sk, kwk;
             if (k < 32 && deg <= 32) {
@@ -321,7 +320,6 @@ __global__ void __launch_bounds__(256, TX_STAR_MIN_BLOCKS) gat_star_fwd_kernel(c
               r[t].z = fmaf(w, nx[t].z, r[t].z); r[t].w = fmaf(w, nx[t].w, r[t].w);
             }
           }
-          if (more) star_load_row<NV>(base + (int64_t)(o + j + 1) * p.ldf, lane, D, nx);           // first sibling in flight
           if (deg <= 32) {
             if (lane < deg) {
               const int64_t so = (int64_t)(q + a + lane) * H + h;
