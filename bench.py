@@ -89,14 +89,48 @@ def gemm_flops_per_node(cfg):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  Default: in-process NVML queries
+    (nvidia_ml_py) issued by the enqueue thread itself, twice inside every timed loop (`sample_once`; the loop is GPU-bound, the
+    ~0.1 ms query hides behind the queued launches).  TAXO_SAMPLER=thread polls from a thread every 20 ms; without NVML a polling
+    `nvidia-smi -lms` child is the fallback.  (Both background variants disturbed the FIRST timed loop on some boxes: the host's
+    enqueue time went from 1.6 to 3-5 ms/step, i.e. the headline dropped by up to 60 % while the later loops were normal.)"""
 
     def __init__(self, index):
         self.index = index
         self.proc = None
         self.lines = []
+        self.samples = []            # (sm_mhz, sm_max_mhz, reasons bitmask) from NVML
+        self.nvml = None
+        self.thread = None
+        self._stop = False
 
-    def start(self):
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            uuid = torch.cuda.get_device_properties(self.index).uuid
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+        except Exception:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                ids = [v for v in vis.split(",") if v.strip() != ""]
+                if self.index < len(ids) and ids[self.index].strip().isdigit():
+                    idx = int(ids[self.index])
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
+
+    def start(self, threaded=True):
+        try:
+            self.nvml, self.handle = self._nvml_handle()
+            self.max_mhz = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+            if threaded:
+                self.thread = threading.Thread(target=self._poll, daemon=True)
+                self.thread.start()
+            else:
+                self.sample_once()
+            return
+        except Exception:
+            self.nvml = None
         q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
@@ -107,18 +141,50 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def sample_once(self):
+        n = self.nvml
+        if not n:
+            return
+        try:
+            sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+            try:
+                why = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            except Exception:
+                why = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            self.samples.append((sm, self.max_mhz, why))
+        except Exception:
+            pass
+
+    def _poll(self):
+        while not self._stop:
+            self.sample_once()
+            time.sleep(0.02)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def wait_ready(self, timeout=5.0):
-        """Blocks until nvidia-smi has delivered its first sample: its start-up (NVML initialisation, 0.1-0.3 s, takes driver locks)
-        must not overlap the first timed loop - measured: a 30-step loop (60 ms) that raced it enqueued at 2.8 ms/step instead of 1.6."""
+        """Blocks until the first sample is in: the sampler's start-up (NVML initialisation takes driver locks) must not overlap the
+        first timed loop."""
         t0 = time.perf_counter()
-        while self.proc and not self.lines and time.perf_counter() - t0 < timeout:
+        while (self.nvml or self.proc) and not (self.samples or self.lines) and time.perf_counter() - t0 < timeout:
             time.sleep(0.01)
 
     def stop(self):
+        if self.nvml:
+            self._stop = True
+            if self.thread:
+                self.thread.join(timeout=1)
+            sm = [s[0] for s in self.samples]
+            bits = 0
+            for s in self.samples:
+                bits |= s[2]
+            n = self.nvml
+            names = (("hw_slowdown", n.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", n.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", n.nvmlClocksThrottleReasonSwPowerCap))
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz if sm else None,
+                    "reasons": sorted(k for k, b in names if bits & b), "samples": len(sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.05)
@@ -140,7 +206,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -335,6 +401,8 @@ def run_b200(args, rank, world, local_rank):
         e0.record()
         for i in range(steps):
             step_fn(i)
+            if sampler_mode == "inline" and rank == 0 and (i + 1) % max(steps // 3, 1) == 0 and i + 1 < steps:
+                sampler.sample_once()      # clocks / throttle reasons from the enqueue thread itself, twice per loop
         if flush is not None:
             flush()
         e1.record()
@@ -346,14 +414,15 @@ def run_b200(args, rank, world, local_rank):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), Stats.launches, Stats.timings_ms() if profile else {}
 
+    sampler_mode = os.environ.get("TAXO_SAMPLER", "inline")     # inline (default) | thread | off
     sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()          # sampled across the value, per-kernel and e2e loops (a 30-step loop alone is ~0.1 s)
+    if rank == 0 and sampler_mode != "off":
+        sampler.start(threaded=sampler_mode == "thread")          # sampled across the value, per-kernel and e2e loops (a 30-step loop alone is ~0.1 s)
     for i in range(nb):          # setup: touch every rotating batch once (its tile table, the allocator's block sizes for its shape);
         step_resident(i)         # a batch first seen inside the timed region costs a cudaMalloc storm of ~100 ms
     for i in range(max(args.warmup, 3)):
         step_resident(i)
-    if rank == 0:
+    if rank == 0 and sampler.thread is not None:
         sampler.wait_ready()     # nvidia-smi's start-up stays outside the timed loops; from here on it only polls every 100 ms
     for i in range(max(args.warmup, 3)):      # second warm-up pass with the sampler polling: on some boxes the first loop after its
         step_resident(i)                      # start enqueued at ~3 ms/step instead of 1.6 (host-bound), whatever came next was normal
