@@ -442,6 +442,32 @@ def run_b200(args, rank, world, local_rank):
     e2e_host = {k: round(v / max(host_t["n"], 1) * 1e3, 4) for k, v in host_t.items() if k != "n"}   # host ms per step by phase
     clocks = sampler.stop() if rank == 0 else None
 
+    # propagate + readout alone (graph_propagate -> readout, fwd + bwd against a fixed upstream gradient; no matching, no
+    # loss, no all-reduce).  A side measurement: it never touches the headline, and a failure is reported instead of raised.
+    prop_ro = None
+    try:
+        gout = {}
+
+        def step_prop_readout(i):
+            b = batches[i % nb]
+            g = b["graph"]
+            g.ndata["pos"] = tx.graph._LazyPos(g)
+            flat.zero_()
+            pos = g.ndata["pos"].to(dev)
+            g.ndata["h"] = model.graph_propagate(g, b["x"])
+            hg = model.readout(g, pos)
+            go = gout.get(tuple(hg.shape))
+            if go is None:
+                go = gout[tuple(hg.shape)] = torch.full_like(hg, 1e-3)
+            hg.backward(go)
+
+        for i in range(max(3, nb)):
+            step_prop_readout(i)
+        pr_ms, _, _ = timed(step_prop_readout, args.steps)
+        prop_ro = {"ms_per_step": round(pr_ms / args.steps, 4)}
+    except Exception as e:      # noqa: BLE001 - diagnostic leg only
+        prop_ro = {"error": f"{type(e).__name__}: {e}"[:200]}
+
     # isolated host->device bandwidth of the pinned feature buffer (explains e2e: the 45.6 MB/step copy runs on its own stream one
     # step ahead, so e2e = max(GPU step, H2D time) whenever the host keeps up)
     torch.cuda.synchronize()
@@ -465,6 +491,8 @@ def run_b200(args, rank, world, local_rank):
         return
 
     value = total_egonets / (total_ms * 1e-3)
+    if prop_ro and "ms_per_step" in prop_ro:
+        prop_ro["egonets_per_s"] = round(total_egonets / (prop_ro["ms_per_step"] * args.steps * 1e-3), 1)
     e2e_value = total_egonets / (e2e_ms * 1e-3)
     b0 = batches[0]
     sh = b0["shapes"]
@@ -554,6 +582,7 @@ def run_b200(args, rank, world, local_rank):
         "kernel_ms_sum": round(step_prof_ms, 4),
         "cpu_baseline": cpu,
         "host": host_info,
+        "propagate_readout": prop_ro,
     }
     print(json.dumps(line), flush=True)
 
