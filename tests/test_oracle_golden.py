@@ -75,3 +75,43 @@ def test_rank_restatement_matches_its_definition():
         got = orc.ranks_from_similarities(s, pos)
         want = [1 + sum(1 for i in range(n) if i not in pos and s[i] > s[p]) for p in pos]
         assert got == want
+
+
+def test_closed_form_star_backward_matches_autograd():
+    """oracle/star_backward.py (the per-egonet closed form a star-specialised backward kernel implements) against torch autograd of
+    the restated GAT layer, fp64, with attention dropout masks and egonets that cover roots, leaves and many grand-parents."""
+    import numpy as np
+    import torch
+    from oracle import star_backward
+    n_gp, n_sib = [1, 0, 3, 2, 0, 5], [2, 0, 0, 7, 3, 1]
+    og = orc.batch_star_egonets(n_gp, n_sib)
+    H, D, K = 3, 8, 6
+    gen = torch.Generator().manual_seed(4)
+    z = torch.randn(og.n, K, generator=gen, dtype=torch.float64)
+    W = (torch.randn(H * D, K, generator=gen, dtype=torch.float64) * 0.5).requires_grad_(True)
+    al = torch.randn(1, H, D, generator=gen, dtype=torch.float64).requires_grad_(True)
+    ar = torch.randn(1, H, D, generator=gen, dtype=torch.float64).requires_grad_(True)
+    p = 0.3
+    keep = (torch.rand(og.src.shape[0], H, 1, generator=gen) > p)
+    ft_holder = {}
+    orig_linear = torch.nn.functional.linear
+
+    def linear(x, w):                         # capture ft with its gradient
+        y = orig_linear(x, w)
+        y.retain_grad()
+        ft_holder["ft"] = y
+        return y
+    torch.nn.functional.linear = linear
+    try:
+        out = orc.gat_layer(og, z, W, al, ar, H, negative_slope=0.2, attn_keep=keep, p_attn=p)
+    finally:
+        torch.nn.functional.linear = orig_linear
+    gout = torch.randn(out.shape, generator=gen, dtype=torch.float64)
+    out.backward(gout)
+    ft = ft_holder["ft"]
+    keepw = (keep.double() / (1.0 - p)).reshape(-1, H).numpy()
+    dft, dal, dar = star_backward.star_gat_backward(n_gp, n_sib, ft.detach().reshape(og.n, H, D).numpy(), gout.numpy(),
+                                                   al.detach()[0].numpy(), ar.detach()[0].numpy(), keepw, 0.2)
+    assert np.abs(dft.reshape(og.n, -1) - ft.grad.numpy()).max() <= 1e-12
+    assert np.abs(dal - al.grad[0].numpy()).max() <= 1e-12
+    assert np.abs(dar - ar.grad[0].numpy()).max() <= 1e-12
