@@ -607,3 +607,23 @@ class EgonetCacheOracle:
                 self.cache[anchor_node] = g
                 self.cache_counter[anchor_node] = 0
         return g
+
+
+class TrainItemOracle:
+    """reference MaskedGraphDataset.__getitem__ for sampling_mode 1 in train mode (dataset.py:290-332) restated on top of the
+    restated queue walk and egonet cache: [(egonet node list, query node, label)], the positive first."""
+
+    def __init__(self, node_list, node2parents, queue: NegativeQueueOracle, cache: EgonetCacheOracle, negative_size):
+        self.node_list, self.node2parents, self.queue, self.cache, self.negative_size = node_list, node2parents, queue, cache, negative_size
+        self.node2positive_pointer = {n: 0 for n in node2parents}
+
+    def __getitem__(self, idx):
+        res = []
+        query_node = self.node_list[idx]
+        positive_pointer = self.node2positive_pointer[query_node]
+        parent_node = self.node2parents[query_node][positive_pointer]
+        res.append((self.cache.get(query_node, parent_node, 1), query_node, 1))
+        self.node2positive_pointer[query_node] = (positive_pointer + 1) % len(self.node2parents[query_node])
+        for negative_parent in self.queue.exactly_k(query_node, self.negative_size):
+            res.append((self.cache.get(query_node, negative_parent, 0), query_node, 0))
+        return res

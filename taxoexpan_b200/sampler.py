@@ -280,3 +280,41 @@ def build_egonet_batch(tax: TaxonomyCSR, features: torch.Tensor, anchors, querie
     x = features.index_select(0, ids.to(features.device))
     bg.ndata["_id"] = ids
     return bg, x, ids
+
+
+class TrainBatcher:
+    """One training batch = `collate_graph_and_node_small_batch` (data_loaders.py:9-28) of `MaskedGraphDataset.__getitem__`
+    (dataset.py:290-332, sampling_mode 1) for a list of dataset indices: per query node its next true parent (the cyclic positive
+    pointer of dataset.py:316-321), then exactly `negative_size` negative anchors from the shared queue, every (anchor, query) pair
+    turned into an egonet - all egonets of the batch built at once on the taxonomy's device instead of one DGLGraph at a time in 20
+    worker processes.  Returns what the trainer consumes (trainer.py:44-51): (batched graph, node features x, query features, labels)."""
+
+    def __init__(self, tax: TaxonomyCSR, features: torch.Tensor, node_list: Sequence[int], negatives: NegativeSampler,
+                 negative_size: int, expand_factor: int = 50, cache: Optional[EgonetCache] = None):
+        self.tax, self.features = tax, features
+        self.node_list = [int(v) for v in node_list]
+        self.negatives, self.negative_size, self.expand_factor, self.cache = negatives, int(negative_size), int(expand_factor), cache
+        self._par_ptr = tax.par_ptr.cpu().numpy()
+        self._par_idx = tax.par_idx.cpu().numpy()
+        self.positive_pointer: Dict[int, int] = {}          # node2positive_pointer (dataset.py:252,316-321)
+
+    def __len__(self):
+        return len(self.node_list)
+
+    def _next_parent(self, q: int) -> int:
+        lo, hi = int(self._par_ptr[q]), int(self._par_ptr[q + 1])
+        if hi == lo:
+            raise ValueError(f"query node {q} has no parent in the training graph (roots are excluded, dataset.py:241-244)")
+        ptr = self.positive_pointer.get(q, 0)
+        self.positive_pointer[q] = (ptr + 1) % (hi - lo)
+        return int(self._par_idx[lo + ptr])
+
+    def batch(self, indices: Sequence[int]):
+        queries = [self.node_list[int(i)] for i in indices]
+        parents = [self._next_parent(q) for q in queries]
+        anchors, qs, modes = self.negatives.batch(queries, parents, self.negative_size)
+        bg, x, _ = build_egonet_batch(self.tax, self.features, anchors, qs, modes, self.expand_factor, cache=self.cache)
+        dev = self.features.device
+        qf = self.features.index_select(0, torch.as_tensor(qs, dtype=torch.int64, device=dev))
+        labels = torch.as_tensor(modes, dtype=torch.int64, device=dev)
+        return bg, x, qf, labels

@@ -149,3 +149,42 @@ def test_negative_sampler_matches_the_reference_queue_walk():
     anchors, qs, modes = got_s.batch(queries[:4], [parents_of[q][0] for q in queries[:4]], 31)
     assert anchors.shape == (4 * 32,) and modes.reshape(4, 32)[:, 0].tolist() == [1] * 4 and int(modes.sum()) == 4
     assert qs.reshape(4, 32)[:, 0].tolist() == queries[:4]
+
+
+def test_train_batcher_reproduces_getitem_plus_collate():
+    """dataset.py:290-332 (`__getitem__`, sampling_mode 1) + data_loaders.py:9-28 (collate) for whole batches: positive pointer
+    cycling over several parents, negatives from the shared queue, cached negative egonets, labels and query features."""
+    import random
+    rng = np.random.default_rng(21)
+    n, ef, neg, refresh = 150, 3, 7, 2
+    par, chi, _, _ = _random_taxonomy(n, 420, rng)
+    keep = par < chi
+    par, chi = par[keep], chi[keep]
+    parents_of, children_of = {}, {}
+    for p, c in zip(par.tolist(), chi.tolist()):
+        parents_of.setdefault(c, []).append(p)
+        children_of.setdefault(p, []).append(c)
+    tax = sampler.TaxonomyCSR.from_edges(par, chi, n)
+    roots = [v for v in range(n) if v not in parents_of]
+    node_list = [v for v in range(n) if v in parents_of]
+    feats = torch.from_numpy(rng.standard_normal((n, 5)).astype(np.float32))
+    masks = sampler.taxonomy_masks(tax, node_list, roots)
+    got = sampler.TrainBatcher(tax, feats, node_list, sampler.NegativeSampler(list(range(n)), masks, random.Random(3)), neg,
+                               expand_factor=ef, cache=sampler.EgonetCache(n, refresh, seed=5))
+    ref = orc.TrainItemOracle(node_list, parents_of, orc.NegativeQueueOracle(list(range(n)), orc.node_masks(parents_of, children_of, node_list, roots),
+                                                                           random.Random(3)),
+                              orc.EgonetCacheOracle(parents_of, children_of, ef, refresh, seed=5), neg)
+    order = list(range(len(node_list)))
+    for epoch in range(3):                                    # pointers cycle through multi-parent nodes
+        random.Random(epoch).shuffle(order)
+        for b0 in range(0, len(order) - 15, 16):
+            idx = order[b0:b0 + 16]
+            bg, x, qf, labels = got.batch(idx)
+            items = [it for i in idx for it in ref[i]]
+            want_ids = [v for nodes, _, _ in items for v in nodes]
+            assert bg.ndata["_id"].tolist() == want_ids
+            assert list(bg.batch_num_nodes) == [len(nodes) for nodes, _, _ in items]
+            assert labels.tolist() == [lab for _, _, lab in items]
+            assert torch.equal(qf, feats[[q for _, q, _ in items]])
+            assert torch.equal(x, feats[want_ids])
+            assert labels.reshape(16, 1 + neg)[:, 0].tolist() == [1] * 16 and int(labels.sum()) == 16
