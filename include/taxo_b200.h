@@ -252,6 +252,19 @@ int tx_gat_star_fwd(const float* ft, int64_t ldf, const float* attn_l, const flo
                     int64_t n_nodes, int64_t heads, int64_t dim, float neg_slope, float p_attn, uint64_t attn_seed, uint32_t attn_stream_id,
                     float* alpha, float* alpha_d, float* elog, float* out, int64_t ldo, const tx_gat_epilogue* epi, uint32_t* maskbits,
                     void* out16_hi, void* out16_lo, int64_t ld16, const float* bound, float* scale_out, int32_t* queue, void* stream);
+/* Opt-in (TAXO_STAR_BWD=1; parity-green on B200, not yet faster than the staged kernel): star-egonet variant of tx_gat_fused_bwd_staged - same
+ * arithmetic and outputs (autograd of model_zoo.py:84-96,106-114; closed form per egonet restated in oracle/star_backward.py), no CSR
+ * and no tile table: a warp owns whole egonets (static ownership by rows, so d(attn) stays fixed-order), the anchor's g / ft rows and
+ * its accumulator stay in registers.  n_gp, n_sib, node_off, edge_off as for tx_star_batch_structure; ds: scratch [E * heads];
+ * dattn_partial: [tx_gat_star_bwd_blocks(N, heads), 2, heads, dim]; exactly one of {dft (fp32, ldd), dft16_hi/dft16_lo (+ bound,
+ * scale_out)} is written. */
+int64_t tx_gat_star_bwd_blocks(int64_t n_nodes, int64_t heads);
+int tx_gat_star_bwd(const float* g, int64_t ldg, int64_t g_head_stride, float g_scale, const float* ft, int64_t ldf,
+                    const float* alpha, const float* alpha_d, const float* elog, const float* attn_l, const float* attn_r,
+                    const int32_t* n_gp, const int32_t* n_sib, const int32_t* node_off, const int32_t* edge_off, int64_t n_graphs,
+                    int64_t n_nodes, int64_t heads, int64_t dim, float neg_slope, float p_attn, uint64_t attn_seed,
+                    uint32_t attn_stream_id, float* ds, float* dft, int64_t ldd, void* dft16_hi, void* dft16_lo, int64_t ld16,
+                    const float* bound, float* scale_out, float* dattn_partial, void* stream);
 /* dpos_partial[b, r, :] = sum over rows i of block b (tx_row_blocks) with pos_i = r of dz[i, col0 : col0+pos_dim] * keep/(1-p)
  * (gradient of the appended position-embedding block, reference model_zoo.py:214-215). */
 int tx_pos_grad_partials(const float* dz, int64_t ldz, int64_t col0, const int32_t* pos, int64_t n_nodes,

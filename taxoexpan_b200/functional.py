@@ -62,6 +62,9 @@ STAGED_FWD = os.environ.get("TAXO_STAGED_FWD", "0") not in ("", "0")
 # work item, anchor row in registers; TAXO_STAR_FWD=0 -> the general warp-per-(row, head) kernel
 STAR_FWD = os.environ.get("TAXO_STAR_FWD", "1") not in ("", "0")
 STAR_FWD_OUTPUT_LAYER = os.environ.get("TAXO_STAR_FWD", "1") != "hidden"     # TAXO_STAR_FWD=hidden: hidden layers only
+# star-specialised fused GAT backward (tx_star_bwd.cu), first version: parity-green on a B200 (test_star_backward_matches_staged_backward,
+# TAXO_STAR_BWD_TEST=1) but only on par with the staged kernel at H = 4 (0.279 vs 0.283 ms) and slower at H = 1 (0.145 vs 0.097 ms): opt-in
+STAR_BWD = os.environ.get("TAXO_STAR_BWD", "0") not in ("", "0")
 
 _star_queues = {}
 
@@ -655,12 +658,22 @@ class GatLayer(Function):
                             d_lo[:, F_:].zero_()
                         d_scale = torch.empty(1, **f32)
                         dft16 = F16Pair(d_hi, d_lo, d_scale, F_)
-                    check(lib.tx_gat_fused_bwd_staged(ptr(dout), ldg, g_head_stride, g_scale, ptr(ft), F_, ptr(alpha), ptr(alpha_d),
-                                                      ptr(elog), ptr(al), ptr(ar), ptr(st.in_ptr), ptr(st.in_src), ptr(st.in_eid),
-                                                      ptr(st.out_ptr), ptr(st.out_dst), ptr(st.out_slot), ptr(tiles), n, H, D,
-                                                      cfg.neg_slope, cfg.p_attn, cfg.attn_seed, cfg.attn_stream, ptr(ds), ptr(da2),
-                                                      ptr(dft), F_, ptr(dft_lo), ptr(d_hi), ptr(d_lo), ld16, ptr(bound), ptr(d_scale),
-                                                      ptr(partial), stream), "tx_gat_fused_bwd_staged")
+                    if STAR_BWD and st.counts is not None and dft_lo is None and n > 0:
+                        cg = st.counts
+                        nbf = int(lib.tx_gat_star_bwd_blocks(n, H))
+                        partial = torch.empty(nbf * 2 * F_, **f32)
+                        check(lib.tx_gat_star_bwd(ptr(dout), ldg, g_head_stride, g_scale, ptr(ft), F_, ptr(alpha), ptr(alpha_d), ptr(elog),
+                                                  ptr(al), ptr(ar), ptr(cg[0]), ptr(cg[1]), ptr(cg[2]), ptr(cg[3]), st.g, n, H, D,
+                                                  cfg.neg_slope, cfg.p_attn, cfg.attn_seed, cfg.attn_stream, ptr(ds), ptr(dft), F_,
+                                                  ptr(d_hi), ptr(d_lo), ld16, ptr(bound), ptr(d_scale), ptr(partial), stream),
+                              "tx_gat_star_bwd")
+                    else:
+                        check(lib.tx_gat_fused_bwd_staged(ptr(dout), ldg, g_head_stride, g_scale, ptr(ft), F_, ptr(alpha), ptr(alpha_d),
+                                                          ptr(elog), ptr(al), ptr(ar), ptr(st.in_ptr), ptr(st.in_src), ptr(st.in_eid),
+                                                          ptr(st.out_ptr), ptr(st.out_dst), ptr(st.out_slot), ptr(tiles), n, H, D,
+                                                          cfg.neg_slope, cfg.p_attn, cfg.attn_seed, cfg.attn_stream, ptr(ds), ptr(da2),
+                                                          ptr(dft), F_, ptr(dft_lo), ptr(d_hi), ptr(d_lo), ld16, ptr(bound), ptr(d_scale),
+                                                          ptr(partial), stream), "tx_gat_fused_bwd_staged")
                 else:
                     nbf = int(lib.tx_gat_fused_bwd_blocks(n, H))
                     partial = torch.empty(nbf * 2 * F_, **f32)

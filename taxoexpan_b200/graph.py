@@ -32,7 +32,7 @@ class GraphStructure:
     """Device-resident structure of one batched graph (all int32)."""
 
     __slots__ = ("device", "n", "e", "g", "in_ptr", "in_src", "in_eid", "out_ptr", "out_dst", "out_slot", "node_off",
-                 "pos", "src", "dst", "max_nodes", "max_out_deg", "_norm", "is_star", "_bwd_tiles", "_dh_bound", "star")
+                 "pos", "src", "dst", "max_nodes", "max_out_deg", "_norm", "is_star", "_bwd_tiles", "_dh_bound", "star", "counts")
 
     def __init__(self, device):
         self.device = device
@@ -44,6 +44,7 @@ class GraphStructure:
         self.src = self.dst = None
         self.is_star = False
         self.star = None           # (task records, n_tasks, chunk) of an EgonetBatch on the device (tx_gat_star_fwd)
+        self.counts = None         # (n_gp, n_sib, node_off, edge_off) device vectors of an EgonetBatch (tx_gat_star_bwd)
 
     def bwd_tiles(self, dim: int) -> torch.Tensor:
         """Tile table of the TMA-staged fused GAT backward (tx_gat_bwd_tiles) for per-head width `dim`; built once per batch."""
@@ -353,6 +354,7 @@ class EgonetBatch(DGLGraph):
             node_off, edge_off = packed[2 * g:3 * g + 1], packed[3 * g + 1:4 * g + 2]
             i32 = dict(dtype=torch.int32, device=device)
             st.node_off = node_off
+            st.counts = (n_gp, n_sib, node_off, edge_off)
             if self._n_tasks:
                 st.star = (packed[self._task_off:self._task_off + 4 * self._n_tasks], self._n_tasks, STAR_CHUNK)
             st.pos = torch.empty(st.n, **i32)
