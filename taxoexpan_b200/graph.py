@@ -231,27 +231,34 @@ class EgonetBatch(DGLGraph):
         self._edges_built = False
         self._max_nodes = int(n.max()) if n.size else 0
         g = n.shape[0]
+        # one staging buffer: [n_gp | n_sib | node_off | edge_off | pad to 16 bytes | task records] as int32, filled in place
+        head_len = 4 * g + 2
+        self._task_off = (head_len + 3) // 4 * 4
         # work items of the star-specialised forward kernel (tx_gat_star_fwd): one 16-byte record {node_off, edge_off, n_gp | chunk << 24,
         # n_sib} per (egonet, chunk of STAR_CHUNK siblings); none when the batch exceeds the encoding (the general fused kernel takes over)
-        n_chunks = np.maximum(1, (self.n_sib.astype(np.int64) + STAR_CHUNK - 1) // STAR_CHUNK)
-        self._n_tasks = 0
-        tasks = np.zeros(0, dtype=np.int32)
-        if g and int(self.n_gp.max()) < (1 << 24) and int(n_chunks.max()) <= STAR_MAX_CHUNKS:
-            first = np.zeros(g + 1, dtype=np.int64)
-            np.cumsum(n_chunks, out=first[1:])
-            owner = np.repeat(np.arange(g, dtype=np.int64), n_chunks)
-            chunk = np.arange(first[-1], dtype=np.int64) - first[owner]
-            rec = np.empty((owner.shape[0], 4), dtype=np.int32)
-            rec[:, 0] = self._node_off[owner]
-            rec[:, 1] = self._edge_off[owner]
-            rec[:, 2] = self.n_gp[owner] | (chunk << 24)
-            rec[:, 3] = self.n_sib[owner]
-            tasks = rec.reshape(-1)
-            self._n_tasks = int(owner.shape[0])
-        # one pinned staging buffer: [n_gp | n_sib | node_off | edge_off | pad to 16 bytes | task records] as int32
-        head = np.concatenate([self.n_gp, self.n_sib, self._node_off.astype(np.int32), self._edge_off.astype(np.int32)])
-        self._task_off = (head.shape[0] + 3) // 4 * 4
-        packed = np.concatenate([head, np.zeros(self._task_off - head.shape[0], dtype=np.int32), tasks])
+        n_chunks = (self.n_sib + (STAR_CHUNK - 1)) // STAR_CHUNK
+        np.maximum(n_chunks, 1, out=n_chunks)
+        n_tasks = int(n_chunks.sum(dtype=np.int64)) if g else 0
+        ok = g > 0 and int(self.n_gp.max()) < (1 << 24) and int(n_chunks.max()) <= STAR_MAX_CHUNKS
+        self._n_tasks = n_tasks if ok else 0
+        packed = np.empty(self._task_off + 4 * self._n_tasks, dtype=np.int32)
+        packed[:g] = self.n_gp
+        packed[g:2 * g] = self.n_sib
+        packed[2 * g:3 * g + 1] = self._node_off
+        packed[3 * g + 1:4 * g + 2] = self._edge_off
+        packed[head_len:self._task_off] = 0
+        if self._n_tasks:
+            # record r of egonet k carries chunk number r - first[k]: in wrapping int32 arithmetic
+            # (n_gp - (first << 24)) + (r << 24) = n_gp | (chunk << 24), so one row-repeat and one strided add build all records
+            first = np.cumsum(n_chunks, dtype=np.int32) - n_chunks
+            base = np.empty((g, 4), dtype=np.int32)
+            base[:, 0] = self._node_off[:-1]
+            base[:, 1] = self._edge_off[:-1]
+            base[:, 2] = self.n_gp - np.left_shift(first, 24)
+            base[:, 3] = self.n_sib
+            rec = packed[self._task_off:].reshape(-1, 4)
+            rec[:] = np.repeat(base, n_chunks, axis=0)
+            rec[:, 2] += np.left_shift(np.arange(self._n_tasks, dtype=np.int32), 24)
         self._packed = torch.from_numpy(packed)
         self._g = g
         if ndata:
