@@ -627,3 +627,17 @@ class TrainItemOracle:
         for negative_parent in self.queue.exactly_k(query_node, self.negative_size):
             res.append((self.cache.get(query_node, negative_parent, 0), query_node, 0))
         return res
+
+
+def large_batch_chunks(nodes_per_graph, limit=100000):
+    """reference data_loaders.py:31-72 (`collate_graph_and_node_large_batch`) restated: [(first, last + 1)] of every emitted batch."""
+    out, start, count, size = [], 0, 0, 0
+    for i, n in enumerate(nodes_per_graph):
+        size += 1
+        count += n
+        if count > limit and size > 1:
+            out.append((start, i + 1))
+            start, count, size = i + 1, 0, 0
+    if size != 0:
+        out.append((start, len(nodes_per_graph)))
+    return out

@@ -318,3 +318,30 @@ class TrainBatcher:
         qf = self.features.index_select(0, torch.as_tensor(qs, dtype=torch.int64, device=dev))
         labels = torch.as_tensor(modes, dtype=torch.int64, device=dev)
         return bg, x, qf, labels
+
+
+BATCH_GRAPH_NODE_LIMIT = 100000      # data_loaders.py:7
+
+
+def chunk_by_node_limit(nodes_per_egonet: Sequence[int], limit: int = BATCH_GRAPH_NODE_LIMIT):
+    """Chunk boundaries of `collate_graph_and_node_large_batch` (data_loaders.py:31-72, the test-stage collate): egonets are appended
+    to the current chunk and the chunk is closed right AFTER the egonet that pushes its node count above `limit` (if it holds more
+    than one egonet).  Returns [(first, last + 1), ...] over the egonet list; found with one searchsorted per chunk instead of a
+    Python loop over all egonets."""
+    n = np.asarray(nodes_per_egonet, dtype=np.int64)
+    csum = np.concatenate([[0], np.cumsum(n)])
+    out, lo, total = [], 0, n.shape[0]
+    while lo < total:
+        # first egonet index hi >= lo with csum[hi + 1] - csum[lo] > limit
+        hi = int(np.searchsorted(csum, csum[lo] + limit, side="right")) - 1
+        if hi >= total:
+            out.append((lo, total))
+            break
+        if hi == lo:                      # a single egonet above the limit never closes a chunk on its own (len(gs) > 1 rule)
+            hi = lo + 1
+            if hi >= total:
+                out.append((lo, total))
+                break
+        out.append((lo, hi + 1))
+        lo = hi + 1
+    return out

@@ -188,3 +188,12 @@ def test_train_batcher_reproduces_getitem_plus_collate():
             assert torch.equal(qf, feats[[q for _, q, _ in items]])
             assert torch.equal(x, feats[want_ids])
             assert labels.reshape(16, 1 + neg)[:, 0].tolist() == [1] * 16 and int(labels.sum()) == 16
+
+
+def test_chunk_by_node_limit_matches_the_test_stage_collate():
+    rng = np.random.default_rng(2)
+    cases = [rng.integers(1, 58, 5000).tolist(), [150000, 3, 4], [5, 150000, 3, 200000, 200000, 1], [100000], [100000, 1], [1] * 10, [],
+             [99999, 1, 1], [50000, 50000, 1, 99999, 2]]
+    for nodes in cases:
+        for limit in (100000, 1000, 57):
+            assert sampler.chunk_by_node_limit(nodes, limit) == orc.large_batch_chunks(nodes, limit), (nodes[:8], limit)
