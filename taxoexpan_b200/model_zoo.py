@@ -244,6 +244,9 @@ class PGCN(nn.Module):
 class MeanReadout(nn.Module):
     """reference model_zoo.py:227-232"""
 
+    def __init__(self):
+        super().__init__()
+
     def forward(self, g, pos=None):
         h = g.ndata['h']
         return txf.Readout.apply(h, None, g.structure(h.device), None, _lib.TX_READOUT_MEAN)
@@ -265,6 +268,9 @@ class WeightedMeanReadout(nn.Module):
 
 class ConcatReadout(nn.Module):
     """reference model_zoo.py:244-258"""
+
+    def __init__(self):
+        super().__init__()
 
     def forward(self, g, pos):
         h = g.ndata['h']
