@@ -68,3 +68,79 @@ def test_module_signatures_and_state_dicts_match_the_reference():
         m = tx.TaxoExpan(pm, rm, mmeth, **kw)
         got = {k: list(v.shape) for k, v in m.state_dict().items()}
         assert got == ref["state"][name], name
+
+
+DATASET_PROBE = r'''
+import json, random, sys
+import networkx as nx, numpy as np, torch
+import dgl
+def to_networkx(self):                       # DGL 0.4.0: nodes 0..n-1, edges in edge-id order
+    G = nx.MultiDiGraph()
+    G.add_nodes_from(range(self.number_of_nodes()))
+    for eid, (u, v) in enumerate(zip(self._src.tolist(), self._dst.tolist())):
+        G.add_edge(u, v, id=eid)
+    return G
+dgl.DGLGraph.to_networkx = to_networkx
+from data_loader.dataset import MaskedGraphDataset   # the reference, unmodified
+spec = json.loads(sys.stdin.read())
+g = dgl.DGLGraph()
+g.add_nodes(spec["n"], {"x": torch.arange(spec["n"], dtype=torch.float32)[:, None].repeat(1, 3)})
+g.add_edges(spec["par"], spec["chi"])
+class GD: pass
+gd = GD(); gd.g_full = g; gd.vocab = [str(i) for i in range(spec["n"])]
+gd.train_node_ids = spec["train"]; gd.validation_node_ids = []; gd.test_node_ids = []
+random.seed(spec["seed"])
+ds = MaskedGraphDataset(gd, mode="train", sampling_mode=1, negative_size=spec["neg"], expand_factor=spec["ef"], cache_refresh_time=spec["refresh"])
+out = {"node_list": [int(v) for v in ds.node_list], "items": []}
+for idx in spec["indices"]:
+    item = ds[idx]
+    out["items"].append([[t[0].ndata["_id"].tolist(), t[0].ndata["pos"].tolist(), t[0]._src.tolist(), t[0]._dst.tolist(), float(t[1][0]), int(t[2])] for t in item])
+print(json.dumps(out))
+'''
+
+
+def test_train_batcher_matches_the_unmodified_reference_dataset():
+    """The reference's own MaskedGraphDataset (data_loader/dataset.py, byte-for-byte, through the DGL / gensim shims and real
+    networkx) against NegativeSampler + taxonomy_masks + TrainBatcher for the same `random` seed: node lists, positions, edge lists,
+    query features and labels of every (query, anchor) egonet over three passes.  expand_factor exceeds every out-degree, so the only
+    random numbers consumed are the queue shuffles (sibling sub-sampling is counter-based here by design and checked separately)."""
+    import random
+
+    import numpy as np
+    import torch
+
+    from taxoexpan_b200 import sampler
+    rng = np.random.default_rng(17)
+    n, neg, seed = 90, 9, 4242
+    par = rng.integers(0, n, 260)
+    chi = rng.integers(0, n, 260)
+    keep = par < chi                                       # a DAG without self loops
+    edges = sorted(set(zip(par[keep].tolist(), chi[keep].tolist())), key=lambda e: (e[0], e[1]))
+    par, chi = [e[0] for e in edges], [e[1] for e in edges]
+    train = list(range(n))
+    indices = list(range(40)) * 3
+    spec = dict(n=n, par=par, chi=chi, train=train, seed=seed, neg=neg, ef=1000, refresh=3, indices=indices)
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "oracle", "dgl_shim"), REF]))
+    r = subprocess.run([sys.executable, "-c", DATASET_PROBE], input=json.dumps(spec), env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    ref = json.loads(r.stdout.strip().splitlines()[-1])
+
+    tax = sampler.TaxonomyCSR.from_edges(par, chi, n)
+    has_parent = set(chi)
+    roots = [v for v in range(n) if v not in has_parent]
+    node_list = ref["node_list"]                            # the reference's list(set(...)) order is an implementation detail: take it
+    assert sorted(node_list) == sorted(set(train) - set(roots))
+    feats = torch.arange(n, dtype=torch.float32)[:, None].repeat(1, 3)
+    masks = sampler.taxonomy_masks(tax, node_list, roots)
+    batcher = sampler.TrainBatcher(tax, feats, node_list, sampler.NegativeSampler(train, masks, random.Random(seed)), neg,
+                                   expand_factor=1000, cache=sampler.EgonetCache(n, 3, seed=1))
+    for idx, item in zip(indices, ref["items"]):
+        bg, x, qf, labels = batcher.batch([idx])
+        assert labels.tolist() == [t[5] for t in item]
+        assert qf[:, 0].tolist() == [t[4] for t in item]
+        assert bg.ndata["_id"].tolist() == [v for t in item for v in t[0]]
+        assert bg.host_pos().tolist() == [v for t in item for v in t[1]]
+        src, dst = bg.edges()
+        off = np.concatenate([[0], np.cumsum([len(t[0]) for t in item])])
+        assert src.tolist() == [int(off[k]) + v for k, t in enumerate(item) for v in t[2]]
+        assert dst.tolist() == [int(off[k]) + v for k, t in enumerate(item) for v in t[3]]
