@@ -144,3 +144,35 @@ def test_train_batcher_matches_the_unmodified_reference_dataset():
         off = np.concatenate([[0], np.cumsum([len(t[0]) for t in item])])
         assert src.tolist() == [int(off[k]) + v for k, t in enumerate(item) for v in t[2]]
         assert dst.tolist() == [int(off[k]) + v for k, t in enumerate(item) for v in t[3]]
+
+
+RAW_PROBE = r'''
+import json, sys
+import dgl
+from data_loader.dataset import MAGDataset            # the reference, unmodified
+d = MAGDataset(name="toy", path=sys.argv[1], raw=True)
+src, dst = d.g_full.edges()
+print(json.dumps({"vocab": d.vocab, "src": src.tolist(), "dst": dst.tolist(), "x": d.g_full.ndata["x"].tolist(),
+                  "train": list(map(int, d.train_node_ids)), "validation": list(map(int, d.validation_node_ids)),
+                  "test": list(map(int, d.test_node_ids))}))
+'''
+
+
+def test_raw_dataset_loader_matches_the_unmodified_reference(tmp_path):
+    """dataset_io.load_raw against the reference's own MAGDataset._load_dataset_raw (data_loader/dataset.py:92-194) on the same
+    .terms / .taxo / .embed files: vocabulary, node numbering, edge order, features and the random 10 % / 10 % leaf split."""
+    import numpy as np
+
+    from taxoexpan_b200 import dataset_io
+    from tests.test_dataset_io_cpu import _write_dataset
+    _write_dataset(tmp_path, np.random.default_rng(2))
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "oracle", "dgl_shim"), REF]))
+    r = subprocess.run([sys.executable, "-c", RAW_PROBE, str(tmp_path)], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    ref = json.loads(r.stdout.strip().splitlines()[-1])
+    ds = dataset_io.load_raw(str(tmp_path), "toy")
+    assert ds.vocab == ref["vocab"]
+    assert ds.parents.tolist() == ref["src"] and ds.children.tolist() == ref["dst"]
+    assert np.array_equal(ds.features, np.asarray(ref["x"], dtype=np.float32))
+    assert ds.train_node_ids.tolist() == ref["train"]
+    assert ds.validation_node_ids.tolist() == ref["validation"] and ds.test_node_ids.tolist() == ref["test"]
