@@ -176,3 +176,45 @@ def test_raw_dataset_loader_matches_the_unmodified_reference(tmp_path):
     assert np.array_equal(ds.features, np.asarray(ref["x"], dtype=np.float32))
     assert ds.train_node_ids.tolist() == ref["train"]
     assert ds.validation_node_ids.tolist() == ref["validation"] and ds.test_node_ids.tolist() == ref["test"]
+
+
+METRIC_PROBE = r'''
+import json, sys
+import numpy as np
+import model.metric as M                                   # the reference, unmodified
+spec = json.loads(sys.stdin.read())
+out = {"ranks": [[int(r) for r in M.calculate_ranks_from_similarities(np.asarray(s, dtype=np.float32), p)] for s, p in zip(spec["sims"], spec["pos"])]}
+R = spec["all_ranks"]
+out.update(macro_mr=float(M.macro_mr(R)), micro_mr=float(M.micro_mr(R)), hit1=float(M.hit_at_1(R)), hit3=float(M.hit_at_3(R)),
+           hit5=float(M.hit_at_5(R)), mrr=float(M.mrr_scaled_10(R)))
+print(json.dumps(out))
+'''
+
+
+def test_rank_and_metric_restatements_match_the_unmodified_reference():
+    """oracle.ranks_from_similarities (the checker of the GPU all-pairs ranking) and inference.macro_mr / micro_mr / hit_at_k /
+    mrr_scaled_10 against model/metric.py:7-19,62-95, ties included."""
+    import numpy as np
+
+    from oracle import taxo_oracle as orc
+    from taxoexpan_b200 import inference
+    rng = np.random.default_rng(9)
+    sims, pos = [], []
+    for _ in range(40):
+        n = int(rng.integers(3, 60))
+        s = np.round(rng.standard_normal(n), 1).astype(np.float32)           # coarse values: many ties
+        sims.append(s.tolist())
+        pos.append(sorted(rng.choice(n, size=int(rng.integers(1, 4)), replace=False).tolist()))
+    all_ranks = [[int(v) for v in rng.integers(1, 200, int(rng.integers(1, 5)))] for _ in range(50)]
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "oracle", "dgl_shim"), REF]))
+    r = subprocess.run([sys.executable, "-c", METRIC_PROBE], input=json.dumps(dict(sims=sims, pos=pos, all_ranks=all_ranks)), env=env,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    ref = json.loads(r.stdout.strip().splitlines()[-1])
+    assert [orc.ranks_from_similarities(np.asarray(s, dtype=np.float32), p) for s, p in zip(sims, pos)] == ref["ranks"]
+    assert abs(inference.macro_mr(all_ranks) - ref["macro_mr"]) < 1e-9
+    assert abs(inference.micro_mr(all_ranks) - ref["micro_mr"]) < 1e-9
+    assert abs(inference.hit_at_k(all_ranks, 1) - ref["hit1"]) < 1e-12
+    assert abs(inference.hit_at_k(all_ranks, 3) - ref["hit3"]) < 1e-12
+    assert abs(inference.hit_at_k(all_ranks, 5) - ref["hit5"]) < 1e-12
+    assert abs(inference.mrr_scaled_10(all_ranks) - ref["mrr"]) < 1e-12
