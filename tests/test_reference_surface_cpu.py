@@ -218,3 +218,46 @@ def test_rank_and_metric_restatements_match_the_unmodified_reference():
     assert abs(inference.hit_at_k(all_ranks, 3) - ref["hit3"]) < 1e-12
     assert abs(inference.hit_at_k(all_ranks, 5) - ref["hit5"]) < 1e-12
     assert abs(inference.mrr_scaled_10(all_ranks) - ref["mrr"]) < 1e-12
+
+
+CKPT_PROBE = r'''
+import sys, json
+import torch
+import model.model as mm                                  # the reference, unmodified
+import parse_config                                       # its ConfigParser is pickled into every checkpoint (base_trainer.py:141)
+kw = json.loads(sys.argv[2])
+torch.manual_seed(7)
+m = mm.TaxoExpan("PGAT", "WMR", "LBM", **kw)
+opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+cfg = object.__new__(parse_config.ConfigParser)           # constructor wants argparse + files; the pickled object is what matters
+cfg.__dict__.update({"_ConfigParser__config": {"name": "toy", "arch": {"type": "TaxoExpan", "args": kw}}, "resume": None})
+state = {"arch": type(m).__name__, "epoch": 3, "state_dict": m.state_dict(), "optimizer": opt.state_dict(), "monitor_best": 12.5,
+         "config": cfg}                                    # base/base_trainer.py:134-142
+torch.save(state, sys.argv[1])
+print(json.dumps({k: [float(v.double().sum()), float(v.double().abs().max())] for k, v in m.state_dict().items()}))
+'''
+
+
+def test_checkpoint_written_by_the_reference_classes_loads_without_the_reference(tmp_path):
+    """A checkpoint saved the way base/base_trainer.py:126-149 does - state_dict of the reference's own TaxoExpan plus its pickled
+    parse_config.ConfigParser - loaded here with no reference code on the path, into the drop-in model, tensor for tensor."""
+    import torch
+
+    from taxoexpan_b200 import dataset_io
+    kw = dict(in_dim=12, hidden_dim=8, out_dim=6, pos_dim=4, num_layers=1, heads=[2, 1], feat_drop=0.1, attn_drop=0.1, hidden_drop=0.1,
+              out_drop=0.1)
+    path = str(tmp_path / "checkpoint-epoch3.pth")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "oracle", "dgl_shim"), REF]))
+    r = subprocess.run([sys.executable, "-c", CKPT_PROBE, path, json.dumps(kw)], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    ref = json.loads(r.stdout.strip().splitlines()[-1])
+    assert "parse_config" not in sys.modules and "model.model" not in sys.modules
+    model = tx.TaxoExpan("PGAT", "WMR", "LBM", **kw)
+    ckpt = dataset_io.load_reference_checkpoint(path, model)
+    assert ckpt["arch"] == "TaxoExpan" and ckpt["epoch"] == 3 and ckpt["monitor_best"] == 12.5
+    got = model.state_dict()
+    assert set(got) == set(ref)
+    for k, (s, mx) in ref.items():
+        assert abs(float(got[k].double().sum()) - s) <= 1e-9 * max(1.0, abs(s)) and float(got[k].double().abs().max()) == mx, k
+    assert type(ckpt["config"]).__name__ == "ConfigParser"          # a stub carrying the pickled attributes
+    assert ckpt["config"].__dict__["_ConfigParser__config"]["name"] == "toy"
