@@ -652,7 +652,7 @@ def test_star_forward_matches_general_fused_forward(shapes, p_drop, monkeypatch)
 # ------------------------------------------------------------------------------------------------
 # Opt-in star-specialised fused backward (tx_gat_star_bwd, functional.STAR_BWD) against the default staged backward.  Passed on a B200
 # (6 cases) when it was written; not part of the default suite because the default product path never launches the kernel.
-# Run with TAXO_STAR_BWD_TEST=1.
+# Run with TAXO_STAR_BWD_TEST=1; add TAXO_STAR_BWD_COOP=24 to check the team variant (the library reads it once per process).
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.skipif(__import__("os").environ.get("TAXO_STAR_BWD_TEST", "") != "1",
                     reason="opt-in kernel: set TAXO_STAR_BWD_TEST=1 to check tx_gat_star_bwd against the staged backward")
