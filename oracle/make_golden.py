@@ -67,6 +67,17 @@ CASES = {
         cfg=dict(propagation_method="PGCN", readout_method="MR", matching_method="BIM", in_dim=300, hidden_dim=600,
                  out_dim=300, pos_dim=50, num_layers=1, heads=[4, 1]),
         synth=dict(n_queries=2, negative_size=31, model="wordnet", seed=11), n_queries=2),
+    # BASELINE configs[1] at FULL size: 256 queries x 32 = 8192 egonets (the batch bench.py times), all gradients; large tensors are
+    # stored sub-sampled (every 997th element of node_h / dh / hg, every 97th of the large parameter gradients)
+    "pgat_wmr_lbm_magcs_full": dict(
+        cfg=dict(propagation_method="PGAT", readout_method="WMR", matching_method="LBM", in_dim=250, hidden_dim=500,
+                 out_dim=500, pos_dim=50, num_layers=1, heads=[4, 1]),
+        synth=dict(n_queries=256, negative_size=31, model="mag-cs", seed=20200420), n_queries=256, big_step=997),
+    # BASELINE configs[0] at FULL size: SemEval-Noun / WordNet dims PGCN+MR(+BIM), 32 queries x 32 = 1024 egonets
+    "pgcn_mr_bim_wordnet_full": dict(
+        cfg=dict(propagation_method="PGCN", readout_method="MR", matching_method="BIM", in_dim=300, hidden_dim=600,
+                 out_dim=300, pos_dim=50, num_layers=1, heads=[4, 1]),
+        synth=dict(n_queries=32, negative_size=31, model="wordnet", seed=20200420), n_queries=32, big_step=97),
 }
 
 
@@ -94,6 +105,11 @@ def checksum(t):
 
 def subsample(a, step=97):
     return np.ascontiguousarray(np.asarray(a).reshape(-1)[::step])
+
+
+def sub_rows(a, step):
+    """every step-th ROW (scores / hg of the full-size cases)"""
+    return np.ascontiguousarray(np.asarray(a)[::step])
 
 
 def run_case(name, spec):
@@ -160,14 +176,19 @@ def run_case(name, spec):
         assert worst < tol, (name, tag, errs)
 
     f32, f64 = res["f32"], res["f64"]
-    for key in ("scores", "hg", "loss"):
+    big_step = int(spec.get("big_step", 97))
+    out["big_step"] = np.array([big_step])
+    hg_rows = 1 if f32["hg"].size <= 200000 else 64          # full-size cases keep every 64th row of hg
+    out["hg_row_step"] = np.array([hg_rows])
+    for key in ("scores", "loss"):
         out[key] = f32[key]
         out[key + "_f64"] = f64[key]
+    out["hg"], out["hg_f64"] = sub_rows(f32["hg"], hg_rows), sub_rows(f64["hg"], hg_rows)
     if big:
-        out["node_h_sub"] = subsample(f32["node_h"])
-        out["node_h_sub_f64"] = subsample(f64["node_h"])
-        out["dh_sub"] = subsample(f32["dh"])
-        out["dh_sub_f64"] = subsample(f64["dh"])
+        out["node_h_sub"] = subsample(f32["node_h"], big_step)
+        out["node_h_sub_f64"] = subsample(f64["node_h"], big_step)
+        out["dh_sub"] = subsample(f32["dh"], big_step)
+        out["dh_sub_f64"] = subsample(f64["dh"], big_step)
     else:
         out["node_h"], out["node_h_f64"] = f32["node_h"], f64["node_h"]
         out["dh"], out["dh_f64"] = f32["dh"], f64["dh"]
@@ -187,7 +208,10 @@ def run_case(name, spec):
 
 if __name__ == "__main__":
     torch.set_num_threads(max(1, os.cpu_count() or 1))
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]
     for name, spec in CASES.items():
+        if only and name not in only:
+            continue
         print(name)
         run_case(name, spec)
     print("golden fixtures written to", GOLD)

@@ -4,11 +4,15 @@ The reference has no working multi-device path (torch.nn.DataParallel cannot spl
 base/base_trainer.py:18-19; every config sets n_gpu = 1).  Here: one process per GPU, each rank holds a full replica and a
 contiguous range of queries (a query's 1 positive + `negative_size` negatives stay together so the per-query InfoNCE
 soft-max of trainer/trainer.py:52-56 is rank-local), the loss reduction is a sum (model/loss.py:57), so the exact
-single-GPU gradient is the SUM over ranks: one all-reduce of the flat gradient buffer per step, no other exchange.
+single-GPU gradient is the SUM over ranks: the flat gradient buffer is all-reduced once per step, no other exchange.
+
+The all-reduce is issued in (by default two) contiguous SEGMENTS of the flat buffer, each as soon as autograd has finished the
+last parameter of the segment (post-accumulate-grad hooks), asynchronously on NCCL's stream: the segment holding the matching,
+readout and output-layer gradients (60 % of the bytes) travels while the first layer's backward kernels still run.
 """
 from __future__ import annotations
 
-from typing import Iterable, List, Tuple
+from typing import Iterable, List, Optional, Tuple
 
 import numpy as np
 import torch
@@ -37,25 +41,126 @@ def shard_queries(nodes_per_query: np.ndarray, world_size: int) -> List[Tuple[in
 
 
 class FlatGradBucket:
-    """All gradients of a module live in ONE flat fp32 buffer (each parameter's .grad is a view into it), so a step needs
-    exactly one all-reduce (1 755 303 floats = 7.0 MB for the MAG-CS PGAT+WMR+LBM model)."""
+    """All gradients of a module live in ONE flat fp32 buffer (each parameter's .grad is a view into it; 1 755 303 floats = 7.0 MB
+    for the MAG-CS PGAT+WMR+LBM model), all-reduced in `segments` contiguous pieces.
 
-    def __init__(self, params: Iterable[torch.nn.Parameter]):
+    Protocol per step:   bucket.zero_()  ->  forward / loss.backward()  ->  bucket.all_reduce()  ->  optimizer.step()
+
+    * `zero_()` (or `optimizer.zero_grad(set_to_none=False)`) clears the buffer in place.  `optimizer.zero_grad()` with torch's
+      default `set_to_none=True` (what the reference trainer calls, trainer/trainer.py:50) drops the views; the bucket notices:
+      the post-accumulate-grad hook of every parameter copies a gradient that autograd allocated elsewhere back into the flat
+      buffer and re-binds `.grad` to its view, and `all_reduce()` re-checks every parameter (a parameter that received no gradient
+      contributes zeros) - so the reduced buffer always equals the sum of the ranks' gradients, whichever way the caller zeroes.
+    * with `overlap=True` (default) a segment's all-reduce starts inside backward, as soon as its last gradient is final;
+      `all_reduce()` launches whatever has not started and makes the CURRENT stream wait for all of it (no host block).
+    """
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], segments: int = 2, overlap: bool = True, group=None):
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
         dev, dt = self.params[0].device, self.params[0].dtype
         self.flat = torch.zeros(sum(p.numel() for p in self.params), device=dev, dtype=dt)
+        self.group = group
+        self.overlap = overlap
+        self._views = []
         off = 0
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            v = self.flat[off:off + p.numel()].view_as(p)
+            self._views.append(v)
+            p.grad = v
             off += p.numel()
+        # contiguous parameter groups of about equal size; backward finishes them from the LAST group to the first
+        n_seg = max(1, min(int(segments), len(self.params)))
+        target = self.flat.numel() / n_seg
+        self._seg_of, self._seg_range, self._seg_size = [], [], []
+        seg, start, acc = 0, 0, 0
+        for i, p in enumerate(self.params):
+            self._seg_of.append(seg)
+            acc += p.numel()
+            left = len(self.params) - 1 - i
+            if (acc - start >= target and seg < n_seg - 1 and left >= 1) or left == 0:
+                self._seg_range.append((start, acc))
+                self._seg_size.append(sum(1 for s in self._seg_of if s == seg))
+                start, seg = acc, seg + 1
+        self._ready = [0] * len(self._seg_range)
+        self._launched = [False] * len(self._seg_range)
+        self._seen = [False] * len(self.params)
+        self._works = []
+        self._hooks = [p.register_post_accumulate_grad_hook(self._make_hook(i)) for i, p in enumerate(self.params)]
 
+    # ---- internals ----
+    def _dist_active(self) -> bool:
+        import torch.distributed as dist
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def _rebind(self, i: int):
+        """Make parameter i's .grad the flat view again: copy a gradient autograd allocated elsewhere (after
+        zero_grad(set_to_none=True)); a parameter without any gradient this step contributes zeros."""
+        p, v = self.params[i], self._views[i]
+        g = p.grad
+        if g is None:
+            v.zero_()
+        elif g.data_ptr() != v.data_ptr() or g.shape != v.shape:
+            v.copy_(g)
+        p.grad = v
+
+    def _make_hook(self, i: int):
+        def hook(param):
+            s = self._seg_of[i]
+            if self._launched[s]:
+                raise RuntimeError("FlatGradBucket: backward ran again after this segment's all-reduce was launched; call "
+                                   "all_reduce() / zero_() between backward passes or construct the bucket with overlap=False")
+            self._rebind(i)
+            if not self._seen[i]:
+                self._seen[i] = True
+                self._ready[s] += 1
+            if self.overlap and self._ready[s] == self._seg_size[s]:
+                self._launch(s)
+        return hook
+
+    def _launch(self, s: int):
+        self._launched[s] = True
+        if self._dist_active():
+            import torch.distributed as dist
+            a, b = self._seg_range[s]
+            self._works.append(dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def _reset_step(self):
+        self._ready = [0] * len(self._seg_range)
+        self._launched = [False] * len(self._seg_range)
+        self._seen = [False] * len(self.params)
+        self._works = []
+
+    # ---- public ----
     def zero_(self):
+        """Clear the flat buffer in place and (re-)bind every .grad view: call before each backward."""
+        for w in self._works:                     # a reduction still in flight must not race the clear
+            w.wait()
         self.flat.zero_()
+        for p, v in zip(self.params, self._views):
+            p.grad = v
+        self._reset_step()
 
     def all_reduce(self, group=None):
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        """Finish the step's gradient exchange: returns the flat buffer holding the SUM over ranks (stream-ordered: the current
+        stream waits for NCCL's stream, the host does not block)."""
+        if group is not None:
+            self.group = group
+        for i, (p, v) in enumerate(zip(self.params, self._views)):
+            if p.grad is None or p.grad.data_ptr() != v.data_ptr():
+                if self._launched[self._seg_of[i]]:
+                    raise RuntimeError("FlatGradBucket: a gradient was replaced after its segment's all-reduce was launched")
+                self._rebind(i)
+        for s in range(len(self._seg_range) - 1, -1, -1):
+            if not self._launched[s]:
+                self._launch(s)
+        for w in self._works:
+            w.wait()
+        self._reset_step()
         return self.flat
+
+    def close(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []

@@ -26,6 +26,13 @@ CASE_CFG = {
                                 hidden_dim=600, out_dim=300, pos_dim=50, num_layers=1, heads=[4, 1]),
 }
 CASES = sorted(CASE_CFG)
+# BASELINE configs[1] / configs[0] at their FULL sizes (8192 / 1024 egonets): outputs and ALL gradients of the unmodified reference
+FULL_CASE_CFG = {
+    "pgat_wmr_lbm_magcs_full": CASE_CFG["pgat_wmr_lbm_magcs"],
+    "pgcn_mr_bim_wordnet_full": CASE_CFG["pgcn_mr_bim_wordnet"],
+}
+FULL_CASES = sorted(FULL_CASE_CFG)
+CASE_CFG.update(FULL_CASE_CFG)
 SUB_STEP = 97  # oracle/make_golden.py subsample()
 
 
@@ -34,8 +41,8 @@ def checksum(t):
     return np.array([t.sum(), np.abs(t).sum()])
 
 
-def sub(a):
-    return np.ascontiguousarray(np.asarray(a).reshape(-1)[::SUB_STEP])
+def sub(a, step=SUB_STEP):
+    return np.ascontiguousarray(np.asarray(a).reshape(-1)[::step])
 
 
 def load_case(name):
@@ -62,15 +69,17 @@ def compare_to_fixture(fx, scores, hg, node_h, loss, grads, dh, tol, gtol):
         err = np.abs(a - b).max() if a.size else 0.0
         assert err <= t, f"{what}: max-abs err {err:.3e} > {t:.3e}"
 
+    big_step = int(fx["big_step"][0]) if "big_step" in fx else SUB_STEP
+    hg_rows = int(fx["hg_row_step"][0]) if "hg_row_step" in fx else 1
     close(scores, fx["scores"], tol * max(1.0, float(np.abs(fx["scores"]).max())), "scores")
-    close(hg, fx["hg"], tol, "hg")
+    close(np.asarray(hg)[::hg_rows], fx["hg"], tol, "hg")
     close(loss, fx["loss"], tol * max(1.0, float(abs(fx["loss"]))), "loss")
     if "node_h" in fx:
         close(node_h, fx["node_h"], tol, "node_h")
         close(dh, fx["dh"], gtol * max(float(np.abs(fx["dh"]).max()), 1e-30), "dh")
     else:
-        close(sub(node_h), fx["node_h_sub"], tol, "node_h")
-        close(sub(dh), fx["dh_sub"], gtol * max(float(np.abs(fx["dh_sub"]).max()), 1e-30), "dh")
+        close(sub(node_h, big_step), fx["node_h_sub"], tol, "node_h")
+        close(sub(dh, big_step), fx["dh_sub"], gtol * max(float(np.abs(fx["dh_sub"]).max()), 1e-30), "dh")
     gscale = max(float(np.abs(fx[k]).max()) for k in fx.files if k.startswith("grad.") or k.startswith("grad_sub."))
     for k, g in grads.items():
         if "grad." + k in fx:

@@ -112,3 +112,35 @@ def test_flat_bucket_views_alias_the_buffer():
     assert torch.equal(b.flat[:6].view(2, 3), lin.weight.grad) and float(b.flat.abs().sum()) > 0
     b.zero_()
     assert float(lin.weight.grad.abs().sum()) == 0.0
+
+
+def test_flat_bucket_survives_zero_grad_set_to_none():
+    """The reference trainer calls optimizer.zero_grad() (trainer.py:50; torch's default set_to_none=True drops the views): the bucket
+    must still end up holding the real gradient (it used to all-reduce zeros)."""
+    lin = torch.nn.Linear(3, 2)
+    b = FlatGradBucket(lin.parameters())
+    opt = torch.optim.SGD(lin.parameters(), lr=0.1)
+    for _ in range(2):
+        opt.zero_grad()                              # set_to_none=True
+        assert lin.weight.grad is None
+        lin(torch.ones(1, 3)).sum().backward()
+        flat = b.all_reduce()
+        assert torch.equal(flat[:6].view(2, 3), torch.ones(2, 3)) and torch.equal(flat[6:], torch.ones(2))
+        assert lin.weight.grad.data_ptr() == flat.data_ptr()       # .grad is the view again
+    # a parameter that received no gradient contributes zeros, not last step's values
+    opt.zero_grad()
+    (lin.weight.sum()).backward()
+    flat = b.all_reduce()
+    assert torch.equal(flat[:6], torch.ones(6)) and float(flat[6:].abs().sum()) == 0.0
+    # in-place zeroing keeps working
+    b.zero_()
+    lin(torch.ones(1, 3)).sum().backward()
+    assert torch.equal(b.all_reduce()[:6], torch.ones(6))
+
+
+def test_flat_bucket_segments_cover_the_buffer():
+    ps = [torch.nn.Parameter(torch.zeros(n)) for n in (600000, 200, 50, 1025000, 500, 150, 3, 125000)]
+    b = FlatGradBucket(ps, segments=2)
+    assert b._seg_range[0][0] == 0 and b._seg_range[-1][1] == b.flat.numel()
+    assert all(x[1] == y[0] for x, y in zip(b._seg_range, b._seg_range[1:])) and sum(b._seg_size) == len(ps)
+    assert len(b._seg_range) == 2

@@ -10,7 +10,7 @@ import taxoexpan_b200 as tx
 from oracle import taxo_oracle as orc
 from taxoexpan_b200 import _lib
 from taxoexpan_b200 import functional as txf
-from tests._golden import CASES, compare_to_fixture, load_case
+from tests._golden import CASES, FULL_CASES, compare_to_fixture, load_case
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5       # BASELINE.json: "within 1e-5 fp32"
@@ -200,6 +200,21 @@ def test_cuda_path_matches_reference_golden(name, graph_kind, monkeypatch):
     compare_to_fixture(fx, *got, tol=TOL, gtol=GTOL)
 
 
+@pytest.mark.parametrize("name", FULL_CASES)
+@pytest.mark.parametrize("graph_kind", ["egonet_batch", "general_kernels"])
+def test_cuda_path_matches_reference_golden_at_full_baseline_size(name, graph_kind, monkeypatch):
+    """BASELINE configs[1] (MAG-CS PGAT+WMR+LBM, 256 queries x 32 = 8192 egonets, N = 37 319) and configs[0] (SemEval-Noun dims
+    PGCN+MR, 32 queries x 32 = 1024 egonets) at their FULL sizes against the unmodified reference: scores of every egonet, the loss,
+    sub-sampled node states / readout rows / d(features) and ALL parameter gradients (oracle/make_golden.py freezes them)."""
+    cfg, og, x, qf, params, fx = load_case(name)
+    model = build_model(cfg, params).train()
+    if graph_kind == "general_kernels":
+        monkeypatch.setattr(txf, "FUSED_ENABLED", False)
+    g = tx.EgonetBatch.from_counts(fx["n_gp"], fx["n_sib"])
+    got = run_cuda(model, g, x, qf, int(fx["n_queries"][0]))
+    compare_to_fixture(fx, *got, tol=TOL, gtol=GTOL)
+
+
 # ------------------------------------------------------------------------------------------------
 # oracle parity on seeded synthetic batches (sizes the oracle finishes in seconds)
 # ------------------------------------------------------------------------------------------------
@@ -321,6 +336,105 @@ def test_general_graph_gat_and_gcn_layers_match_oracle():
             r = p[k].grad
             bound = GTOL * max(float(r.abs().max()), 5e-2 * gscale)
             assert float((v.grad.cpu() - r).abs().max()) <= bound, (pm, k)
+
+
+def _power_law_graph(n, rng, max_in_deg=10_000, n_hubs=3, exponent=1.6):
+    """One graph with power-law in-degrees up to `max_in_deg` (BASELINE configs[4] "general-CSR stress variant"): a few hubs
+    at the cap, a Zipf body, ~20 % of the nodes without any in-edge, duplicate edges and self loops present."""
+    deg = np.minimum(rng.zipf(exponent, n), max_in_deg).astype(np.int64)
+    deg[rng.random(n) < 0.2] = 0
+    deg[rng.choice(n, n_hubs, replace=False)] = max_in_deg
+    dst = np.repeat(np.arange(n), deg)
+    src = rng.integers(0, n, dst.shape[0])
+    perm = rng.permutation(dst.shape[0])                       # edge ids in random order: the CSR build has to sort them
+    return torch.from_numpy(src[perm]), torch.from_numpy(dst[perm]), int(deg.max())
+
+
+@pytest.mark.parametrize("pm", ["GAT", "GCN", "PGAT", "PGCN"])
+def test_general_csr_stress_power_law_in_degrees_up_to_1e4(pm):
+    """A single graph far above FUSED_MAX_GRAPH_NODES (2048) with in-degrees from 0 to 10^4 through the GAT / GCN stacks
+    (model_zoo.py:116-137,169-190 accept any graph): the general-CSR kernels, not the star / tile-staged ones, forward and backward."""
+    rng = np.random.default_rng(11)
+    n, d = 6000, 24
+    src, dst, max_deg = _power_law_graph(n, rng)
+    assert n > txf.FUSED_MAX_GRAPH_NODES and max_deg == 10_000
+    e = int(src.numel())
+    pos = torch.from_numpy(rng.integers(0, 3, n))
+    og = orc.OracleGraph(n, src, dst, pos, [n], [e])
+    x = torch.from_numpy(tx.synth.unit_rows(n, d, seed=5))
+    cfg = orc.OracleConfig(propagation_method=pm, readout_method="MR", matching_method="BIM", in_dim=d, hidden_dim=16,
+                           out_dim=12, pos_dim=4, num_layers=2, heads=[3, 2, 2])
+    params = orc.init_model_params(cfg, seed=8)
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    h = x.clone().requires_grad_(True)
+    ref = orc.propagate(cfg, og, h, p)
+    w = torch.from_numpy(tx.synth.unit_rows(n, ref.shape[1], seed=6))
+    (ref * w).sum().backward()
+    model = build_model(cfg, params).train()
+    g = tx.DGLGraph()
+    g.add_nodes(n, {"pos": pos.clone()})
+    g.add_edges(src, dst)
+    hc = x.to(dev()).requires_grad_(True)
+    out = model.graph_propagate(g, hc)
+    (out * w.to(dev())).sum().backward()
+    scale = max(1.0, float(ref.detach().abs().max()))            # GCN sums 10^4 messages into a hub: outputs are O(sqrt(deg))
+    assert float((out.detach().cpu() - ref.detach()).abs().max()) <= TOL * scale, pm
+    assert float((hc.grad.cpu() - h.grad).abs().max()) <= GTOL * float(h.grad.abs().max()), pm
+    gscale = max(float(v.grad.abs().max()) for k, v in p.items() if k.startswith("graph_propagate") and v.grad is not None)
+    for k, v in model.named_parameters():
+        if not k.startswith("graph_propagate"):
+            continue
+        r = p[k].grad
+        bound = GTOL * max(float(r.abs().max()), 5e-2 * gscale)
+        assert float((v.grad.cpu() - r).abs().max()) <= bound, (pm, k)
+
+
+def test_general_csr_stress_batched_with_a_huge_member():
+    """A batch whose members are small egonet-like graphs plus ONE 3000-node power-law graph (> 2048 nodes: the fused tile kernels
+    step aside for the whole batch) through PGAT + WMR: forward, readout and every gradient against the oracle."""
+    rng = np.random.default_rng(12)
+    sizes = [5, 1, 17, 3000, 8, 2, 40]
+    srcs, dsts, n_e, off = [], [], [], 0
+    for nn in sizes:
+        if nn >= 1000:
+            s_, d_, _ = _power_law_graph(nn, rng, max_in_deg=2500, n_hubs=2)
+        else:
+            e_ = max(1, 2 * nn)
+            s_, d_ = torch.from_numpy(rng.integers(0, nn, e_)), torch.from_numpy(rng.integers(0, nn, e_))
+        srcs.append(s_ + off); dsts.append(d_ + off); n_e.append(int(s_.numel())); off += nn
+    n, src, dst = off, torch.cat(srcs), torch.cat(dsts)
+    pos = torch.from_numpy(rng.integers(0, 3, n))
+    og = orc.OracleGraph(n, src, dst, pos, list(sizes), n_e)
+    d = 20
+    cfg = orc.OracleConfig(propagation_method="PGAT", readout_method="WMR", matching_method="BIM", in_dim=d, hidden_dim=24,
+                           out_dim=16, pos_dim=4, num_layers=1, heads=[2, 1])
+    params = orc.init_model_params(cfg, seed=13)
+    x = torch.from_numpy(tx.synth.unit_rows(n, d, seed=5))
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    h = x.clone().requires_grad_(True)
+    ref = orc.propagate(cfg, og, h, p)
+    hg_ref = orc.readout(cfg, og, ref, p)
+    wv = torch.from_numpy(tx.synth.unit_rows(len(sizes), hg_ref.shape[1], seed=6))
+    (hg_ref * wv).sum().backward()
+    model = build_model(cfg, params).train()
+    g = tx.DGLGraph()
+    g.add_nodes(n, {"pos": pos.clone()})
+    g.add_edges(src, dst)
+    g.batch_num_nodes = list(sizes)
+    hc = x.to(dev()).requires_grad_(True)
+    out = model.graph_propagate(g, hc)
+    g.ndata["h"] = out
+    hg = model.readout(g, pos)
+    (hg * wv.to(dev())).sum().backward()
+    assert float((out.detach().cpu() - ref.detach()).abs().max()) <= TOL
+    assert float((hg.detach().cpu() - hg_ref.detach()).abs().max()) <= TOL
+    assert float((hc.grad.cpu() - h.grad).abs().max()) <= GTOL * float(h.grad.abs().max())
+    gscale = max(float(v.grad.abs().max()) for k, v in p.items() if v.grad is not None)
+    for k, v in model.named_parameters():
+        if p[k].grad is None:
+            continue
+        r = p[k].grad
+        assert float((v.grad.cpu() - r).abs().max()) <= GTOL * max(float(r.abs().max()), 5e-2 * gscale), k
 
 
 def _random_batched_graph(sizes, rng, edge_factor=2.0):
