@@ -252,19 +252,28 @@ int tx_gat_star_fwd(const float* ft, int64_t ldf, const float* attn_l, const flo
                     int64_t n_nodes, int64_t heads, int64_t dim, float neg_slope, float p_attn, uint64_t attn_seed, uint32_t attn_stream_id,
                     float* alpha, float* alpha_d, float* elog, float* out, int64_t ldo, const tx_gat_epilogue* epi, uint32_t* maskbits,
                     void* out16_hi, void* out16_lo, int64_t ld16, const float* bound, float* scale_out, int32_t* queue, void* stream);
-/* Opt-in (TAXO_STAR_BWD=1; parity-green on B200, not yet faster than the staged kernel): star-egonet variant of tx_gat_fused_bwd_staged - same
- * arithmetic and outputs (autograd of model_zoo.py:84-96,106-114; closed form per egonet restated in oracle/star_backward.py), no CSR
- * and no tile table: a warp owns whole egonets (static ownership by rows, so d(attn) stays fixed-order), the anchor's g / ft rows and
- * its accumulator stay in registers.  n_gp, n_sib, node_off, edge_off as for tx_star_batch_structure; ds: scratch [E * heads];
- * dattn_partial: [tx_gat_star_bwd_blocks(N, heads), 2, heads, dim]; exactly one of {dft (fp32, ldd), dft16_hi/dft16_lo (+ bound,
- * scale_out)} is written. */
-int64_t tx_gat_star_bwd_blocks(int64_t n_nodes, int64_t heads);
+/* Star-egonet fused GAT backward (tx_star_bwd.cu; default for EgonetBatch structures, TAXO_STAR_BWD=0 -> tx_gat_fused_bwd_staged):
+ * the autograd of model_zoo.py:84-96,106-114 in closed form per egonet (restated in oracle/star_backward.py).  Work items = the
+ * (egonet, chunk of `chunk` siblings) records of tx_gat_star_fwd's task table pulled from a self-resetting queue; rows reach each warp
+ * through its own TMA ring in shared memory; an egonet with several chunks combines its anchor row through `partial`
+ * ([tx_gat_star_bwd_partial_floats(n_tasks, heads, dim)] floats) and `counters` ([n_tasks * heads] int32, zero before the first
+ * launch, left zero) in chunk order.  Outputs: d(ft) either as fp32 (dft, ldd; then da1 / da2 [N * heads] are required) or as the fp16
+ * hi/lo pair [N, ld16] with ld16 >= heads * dim + 2 * heads: columns heads*dim + h and heads*dim + heads + h carry c * da1[., h] and
+ * c * da2[., h] (the per-node coefficients of attn_l / attn_r), so that the weight-gradient GEMM over heads*dim + 2*heads columns also
+ * returns v = z^T [c da1 | c da2] and d(attn_l)[h] = W_h v[h] / c, d(attn_r)[h] = W_h v[heads + h] / c (tx_attn_grad_from_v; W_h = rows
+ * h*dim.. of the layer's fc weight, because ft_h = z W_h^T).  bounds = the 4 floats written by tx_bound_dft: the kernel first runs with
+ * the optimistic scale (bounds[1]); a value outside the fp16 range sets *flag (= bounds + 3, reset by tx_bound_dft) and the second
+ * launch, which otherwise exits at once, redoes the pass with the rigorous scale (bounds[0]); *reruns (optional) counts those.
+ * ds: scratch [E * heads] (anchors with more than 31 grand-parents). */
+int64_t tx_gat_star_bwd_partial_floats(int64_t n_tasks, int64_t heads, int64_t dim);
 int tx_gat_star_bwd(const float* g, int64_t ldg, int64_t g_head_stride, float g_scale, const float* ft, int64_t ldf,
                     const float* alpha, const float* alpha_d, const float* elog, const float* attn_l, const float* attn_r,
-                    const int32_t* n_gp, const int32_t* n_sib, const int32_t* node_off, const int32_t* edge_off, int64_t n_graphs,
-                    int64_t n_nodes, int64_t heads, int64_t dim, float neg_slope, float p_attn, uint64_t attn_seed,
-                    uint32_t attn_stream_id, float* ds, float* dft, int64_t ldd, void* dft16_hi, void* dft16_lo, int64_t ld16,
-                    const float* bound, float* scale_out, float* dattn_partial, void* stream);
+                    const int32_t* tasks, int64_t n_tasks, int64_t chunk, int64_t n_nodes, int64_t heads, int64_t dim, float neg_slope,
+                    float* ds, float* da1, float* da2, float* dft, int64_t ldd, void* dft16_hi, void* dft16_lo, int64_t ld16,
+                    const float* bounds, int32_t* flag, int32_t* reruns, float* scale_out, float* partial, int32_t* counters,
+                    int32_t* queue, void* stream);
+int tx_attn_grad_from_v(const float* weight, int64_t ldw, const float* v, int64_t ldv, int64_t heads, int64_t dim, int64_t k,
+                        const float* c, float* dattn_l, float* dattn_r, void* stream);
 /* dpos_partial[b, r, :] = sum over rows i of block b (tx_row_blocks) with pos_i = r of dz[i, col0 : col0+pos_dim] * keep/(1-p)
  * (gradient of the appended position-embedding block, reference model_zoo.py:214-215). */
 int tx_pos_grad_partials(const float* dz, int64_t ldz, int64_t col0, const int32_t* pos, int64_t n_nodes,
@@ -356,10 +365,12 @@ int tx_dropout_keep_mask(uint64_t seed, uint32_t stream_id, int64_t first_index,
 int tx_absmax(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* out, void* stream);  /* *out = max |x[i, c]| */
 /* *out = max(*a ca, max|b[0..b_len)| cb); b (a small parameter table, reduced by the same launch) may be NULL */
 int tx_bound_max2(const float* a, float ca, const float* b, int64_t b_len, float cb, float* out, void* stream);
-/* *out = *g_amax (c_direct + c_attn *ft_amax max(max|attn_l|, max|attn_r|)) over attn_l/attn_r[0..attn_len): bound of |dft| written
- * by the fused GAT backward (dft_j = sum_i alpha~_ij g_i + da1_j attn_l + da2_j attn_r with |d alpha~| <= dim max|g| max|ft|). */
+/* out[0] = *g_amax (c_direct + c_attn *ft_amax c), c = max(max|attn_l|, max|attn_r|, 2^-20) over attn_l/attn_r[0..attn_len): rigorous
+ * bound of |dft| written by the fused GAT backward (dft_j = sum_i alpha~_ij g_i + da1_j attn_l + da2_j attn_r with |d alpha~| <= dim
+ * max|g| max|ft|);  out[1] = min(out[0], *g_amax c_optimistic) (c_optimistic <= 0: out[0]): the scale tx_gat_star_bwd tries first;
+ * out[2] = c;  out[3] = 0 as int32: tx_gat_star_bwd's fp16-range flag.  out: 4 floats, 16-byte aligned. */
 int tx_bound_dft(const float* g_amax, const float* ft_amax, const float* attn_l, const float* attn_r, int64_t attn_len, float c_direct,
-                 float c_attn, float* out, void* stream);
+                 float c_attn, float c_optimistic, float* out, void* stream);
 /* hi, lo: fp16 [rows, ldo] (columns >= cols zero); *scale_out (optional) = the scale derived from *bound. */
 int tx_split_f16(const float* x, int64_t ldx, int64_t rows, int64_t cols, const float* bound, void* hi, void* lo, int64_t ldo,
                  float* scale_out, void* stream);

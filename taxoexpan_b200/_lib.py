@@ -97,7 +97,7 @@ _SIGNATURES = {
     "tx_gemm_tn_tf32x3": [P, P, I64, P, P, I64, P, I64, I64, I64, I64, I64, I64, P],
     "tx_absmax": [P, I64, I64, I64, P, P],
     "tx_bound_max2": [P, F32, P, I64, F32, P, P],
-    "tx_bound_dft": [P, P, P, P, I64, F32, F32, P, P],
+    "tx_bound_dft": [P, P, P, P, I64, F32, F32, F32, P, P],
     "tx_split_f16": [P, I64, I64, I64, P, P, P, I64, P, P],
     "tx_split_f16_weight": [P, I64, I64, I64, P, P, I64, P, P, I64, P, P, P],
     "tx_gemm_nt_f16x3": [P, P, I64, P, P, I64, P, P, P, I64, I64, I64, I64, POINTER(GemmEpilogue), P, P],
@@ -107,9 +107,10 @@ _SIGNATURES = {
     "tx_gat_star_max_chunks": [],
     "tx_gat_star_fwd": [P, I64, P, P, P, I64, I64, I64, I64, I64, F32, F32, c_uint64, c_uint32, P, P, P, P, I64,
                         POINTER(GatEpilogue), P, P, P, I64, P, P, P, P],
-    "tx_gat_star_bwd_blocks": [I64, I64],
-    "tx_gat_star_bwd": [P, I64, I64, F32, P, I64, P, P, P, P, P, P, P, P, P, I64, I64, I64, I64, F32, F32, c_uint64, c_uint32, P, P, I64,
-                        P, P, I64, P, P, P, P],
+    "tx_gat_star_bwd_partial_floats": [I64, I64, I64],
+    "tx_gat_star_bwd": [P, I64, I64, F32, P, I64, P, P, P, P, P, P, I64, I64, I64, I64, I64, F32, P, P, P, P, I64, P, P, I64,
+                        P, P, P, P, P, P, P, P],
+    "tx_attn_grad_from_v": [P, I64, P, I64, I64, I64, I64, P, P, P, P],
     "tx_match_rowdot_fwd": [P, I64, P, I64, I64, I64, c_int32, P, P],
     "tx_match_rowdot_bwd": [P, I64, P, I64, P, P, I64, I64, c_int32, P, I64, P, I64, P],
     "tx_info_nce_fwd": [P, I64, I64, P, P, P, P, P],
@@ -119,7 +120,7 @@ _RESTYPES = {"tx_last_error": c_char_p, "tx_target_arch": c_char_p, "tx_row_bloc
              "tx_gat_fused_mask_words": c_int64, "tx_gat_fused_mask_ld": c_int64, "tx_gat_fused_bwd_blocks": c_int64, "tx_gemm_tn_splits": c_int64,
              "tx_gat_bwd_tile_rows": c_int64, "tx_gat_bwd_num_tiles": c_int64, "tx_gat_fused_bwd_staged_blocks": c_int64,
              "tx_gemm_tn_f16_splits": c_int64, "tx_gat_star_chunk": c_int64, "tx_gat_star_max_chunks": c_int64,
-             "tx_gat_star_bwd_blocks": c_int64}
+             "tx_gat_star_bwd_partial_floats": c_int64}
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -129,7 +130,7 @@ _raw = None
 # names of ABI calls that do not enqueue GPU work
 _NO_LAUNCH = {"tx_abi_version", "tx_last_error", "tx_target_arch", "tx_row_blocks", "tx_csr_workspace_bytes",
               "tx_readout_bwd_blocks", "tx_gat_fused_supported", "tx_gat_fused_mask_words", "tx_gat_fused_mask_ld", "tx_gat_fused_bwd_blocks", "tx_gemm_tn_splits",
-              "tx_gat_bwd_tile_rows", "tx_gat_bwd_num_tiles", "tx_gat_fused_bwd_staged_blocks", "tx_gemm_tn_f16_splits", "tx_gat_star_chunk", "tx_gat_star_max_chunks", "tx_gat_star_bwd_blocks"}
+              "tx_gat_bwd_tile_rows", "tx_gat_bwd_num_tiles", "tx_gat_fused_bwd_staged_blocks", "tx_gemm_tn_f16_splits", "tx_gat_star_chunk", "tx_gat_star_max_chunks", "tx_gat_star_bwd_partial_floats"}
 
 
 class Stats:

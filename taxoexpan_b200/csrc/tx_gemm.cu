@@ -780,12 +780,20 @@ __global__ void bound_max2_kernel(const float* a, float ca, const float* b, int6
   const float mb = block_absmax(b, b_len, s_red);
   if (threadIdx.x == 0) *out = fmaxf(*a * ca, mb * cb);
 }
-// bound of |dft| (see tx_bound_dft): g (c_direct + c_attn ft max(max|attn_l|, max|attn_r|))
+// bounds of |dft| (see tx_bound_dft): out[0] = g (c_direct + c_attn ft c) with c = max(max|attn_l|, max|attn_r|, 2^-20) - rigorous;
+// out[1] = min(out[0], g c_optimistic) - the scale the star backward tries first; out[2] = c; out[3] = 0 (its fp16-range flag)
 __global__ void bound_dft_kernel(const float* g, const float* ft, const float* al, const float* ar, int64_t len, float c_direct, float c_attn,
-                                 float* out) {
+                                 float c_optimistic, float* out) {
   __shared__ float s_red[8];
   const float ml = block_absmax(al, len, s_red), mr = block_absmax(ar, len, s_red);
-  if (threadIdx.x == 0) *out = *g * (c_direct + c_attn * *ft * fmaxf(ml, mr));
+  if (threadIdx.x == 0) {
+    const float c = fmaxf(fmaxf(ml, mr), 9.5367431640625e-07f);
+    const float rigorous = *g * (c_direct + c_attn * *ft * c);
+    out[0] = rigorous;
+    out[1] = c_optimistic > 0.f ? fminf(rigorous, *g * c_optimistic) : rigorous;
+    out[2] = c;
+    reinterpret_cast<int*>(out)[3] = 0;
+  }
 }
 
 __global__ void split_f16_kernel(const float* __restrict__ x, int64_t ldx, int rows, int cols, const float* __restrict__ bound,
@@ -1209,9 +1217,9 @@ int tx_bound_max2(const float* a, float ca, const float* b, int64_t b_len, float
 }
 
 int tx_bound_dft(const float* g_amax, const float* ft_amax, const float* attn_l, const float* attn_r, int64_t attn_len, float c_direct,
-                 float c_attn, float* out, void* stream) {
-  TX_REQUIRE(g_amax && ft_amax && attn_l && attn_r && attn_len >= 0 && out, "bound_dft: bad arguments");
-  bound_dft_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(g_amax, ft_amax, attn_l, attn_r, attn_len, c_direct, c_attn, out);
+                 float c_attn, float c_optimistic, float* out, void* stream) {
+  TX_REQUIRE(g_amax && ft_amax && attn_l && attn_r && attn_len >= 0 && out && aligned16(out), "bound_dft: bad arguments (out: 4 floats, 16-byte aligned)");
+  bound_dft_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(g_amax, ft_amax, attn_l, attn_r, attn_len, c_direct, c_attn, c_optimistic, out);
   TX_LAUNCH_CHECK("tx_bound_dft");
   return TX_OK;
 }

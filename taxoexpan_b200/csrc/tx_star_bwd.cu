@@ -1,21 +1,33 @@
-// Star-egonet fused GAT backward (sm_100a) - first version, opt-in (TAXO_STAR_BWD=1).  Parity-green on a B200 against the staged
-// backward (tests/test_gpu_parity.py::test_star_backward_matches_staged_backward, TAXO_STAR_BWD_TEST=1); measured on the MAG-CS
-// benchmark: L0 (H = 4) 0.279 ms vs 0.283 ms staged, L1 (H = 1) 0.145 ms vs 0.097 ms - not yet the default: whole egonets per warp leave
-// a tail at H = 1, and the epilogue / pointer arithmetic have not had the forward's treatment.
+// Star-egonet fused GAT backward (sm_100a), second generation: the default backward of the hot path for EgonetBatch structures.
 //
-// The forward's recipe (tx_star_fwd.cu) applied to the backward pass: for the egonets of data_loader/dataset.py:404-437 the autograd
-// of model_zoo.py:84-96,106-114 has a closed form per egonet (restated and checked against torch autograd in
-// oracle/star_backward.py), so neither CSR is read and no tile has to be staged:
-//   * grand-parent k (one in-edge, its self loop): alpha = 1, the softmax backward vanishes:
+// Arithmetic: the autograd of reference model_zoo.py:84-96,106-114 in the closed form the egonets of data_loader/dataset.py:404-437
+// allow (restated and checked against torch autograd in oracle/star_backward.py):
+//   * grand-parent k (one in-edge, its self loop: alpha = 1, its softmax backward vanishes):
 //       d(ft_k) = alpha~_self g_k + alpha~(k->anchor) g_anchor + ds(k->anchor) attn_l
-//   * sibling s (in-edges {anchor, self}): closed-form 2x2 softmax backward from <g_s, ft_anchor> and <g_s, ft_s>:
-//       d(ft_s) = alpha~_self g_s + ds_self attn_l + (ds_anchor + ds_self) attn_r;   anchor += alpha~(anchor->s) g_s, da1 += ds_anchor
+//   * sibling s (in-edges {anchor, self}): 2x2 softmax backward from <g_s, ft_anchor> and <g_s, ft_s>:
+//       d(ft_s) = alpha~_self g_s + ds_self attn_l + (ds_anchor + ds_self) attn_r;   anchor += alpha~(anchor->s) g_s, da1_anchor += ds_anchor
 //   * anchor (in-edges {gp_0.., self}): dots <g_anchor, ft_gp_k>, <g_anchor, ft_anchor>, softmax backward over a + 1 logits.
-// A warp owns whole egonets; the anchor's g / ft rows and its accumulator stay in registers while the other rows stream by (each
-// row's g and ft are read exactly once, plus one re-read of the grand-parents' ft rows through L1).  Ownership is STATIC - warp W of a
-// head owns the egonets whose first row lies in [W N / nW, (W + 1) N / nW) - so the per-warp d(attn_l) / d(attn_r) sums
-// (shared-memory accumulators, reduced per CTA in a fixed order) are run-to-run deterministic like everything else in the library.
-// Same outputs as tx_gat_fused_bwd_staged: dft (fp32 or fp16 hi/lo pair) and dattn_partial [gridDim.x, 2, H, D].
+//   With alpha~ = alpha * keep / (1 - p) saved by the forward, ds = (alpha~ d - alpha sum_k alpha~_k d_k) * lrelu'(e): no dropout hash here.
+//
+// How it runs (what the first version - whole egonets per warp, rows through LDG, d(attn) in shared memory - lacked):
+//   * WARP-PRIVATE TMA RING: every warp owns 3 shared-memory slots {64-byte header, g row, ft row}.  Lane 0 issues the bulk copies
+//     (cp.async.bulk + mbarrier complete_tx) of the row(s) TWO steps ahead of the one being processed, six lanes add the step's
+//     attention scalars (alpha, alpha~, logits) with 4-byte cp.async on the same mbarrier, so every byte a step needs is in flight long
+//     before it is touched and the rows cost no registers while they fly.  The first version had 16 warps x one row pair in flight
+//     only while the warp was not computing: 38 % of the HBM rate, long-scoreboard 4.8 per issue.
+//   * WORK ITEMS = (egonet, chunk of C siblings) from the forward's task table, pulled from a self-resetting atomic queue (tickets two
+//     items ahead).  An egonet with more than C siblings is shared by several warps: every chunk writes its part of the anchor's
+//     accumulator to a scratch row, bumps the egonet's counter, and the LAST chunk to arrive adds the parts IN CHUNK ORDER and writes
+//     the anchor's row - deterministic whoever finishes last, no second launch, no whole-egonet tail (an egonet of 57 rows was 3.5 x
+//     the average warp load of the output layer).
+//   * d(attn_l), d(attn_r) leave the hot loop: the kernel only emits da1_j, da2_j per (row, head).  With the fp16-pair output they go
+//     into 2 H extra columns of the d(ft) operand, so the weight-gradient GEMM dW = d(ft)^T z that follows returns
+//     v_h = z^T da_h as 2 H extra rows for free, and d(attn_l)[h] = W_h v_h (tx_attn_grad_from_v) because ft_h = z W_h^T.
+//   * fp16-pair scale: the rigorous bound of |d ft| (tx_bound_dft) is ~2^13 above the true maximum, which costs small rows their
+//     `lo` bits.  The kernel therefore runs with an OPTIMISTIC scale (a small multiple of max|g|) and records any value that leaves the
+//     fp16 range in a device flag; a second launch with the rigorous bound exits at once unless the flag is set.  Never saturates
+//     silently, and the common case keeps 22 significant bits for every row within 2^13 of the largest.
+// Every output element is produced by exactly one step in a fixed order: results are run-to-run deterministic.
 #include <math.h>
 #include <stdlib.h>
 
@@ -23,30 +35,65 @@
 
 namespace tx {
 
+constexpr int kSbWarps = 16;           // one CTA per SM
+constexpr int kSbStages = 3;
+constexpr int kSbHdrBytes = 64;
+enum : int { kOpEnd = 0, kOpAnchor0 = 1, kOpAnchorC = 2, kOpGpDot = 3, kOpGpOut = 4, kOpSib = 5 };
+
 struct StarBwdParams {
   const float* g; int64_t ldg; int64_t g_head_stride; float g_scale;
   const float* ft; int64_t ldf;
   const float* alpha; const float* alpha_d; const float* elog;
   const float* attn_l; const float* attn_r;
-  const int32_t* n_gp; const int32_t* n_sib; const int32_t* node_off; const int32_t* edge_off;
-  int n_graphs; int n; int H; int D;
-  float neg_slope; float attn_inv_keep; uint32_t attn_thr; uint64_t attn_seed; uint32_t attn_stream;
+  const int32_t* tasks; int n_tasks; int chunk;
+  int H; int D;
+  float neg_slope;
   float* ds;                     // scratch [E * H]: only anchors with more than 31 grand-parents spill their dots / d(logit) here
+  float* da1; float* da2;        // optional fp32 [N * H]: coefficients of attn_l / attn_r per (row, head)
   float* dft; int64_t ldd;
-  __half* dft16_hi; __half* dft16_lo; int64_t ld16; const float* bound; float* scale_out;
-  float* dattn_partial;          // [gridDim.x, 2, H, D]
+  __half* dft16_hi; __half* dft16_lo; int64_t ld16; int tail16;   // tail16 = ld16 - H * D columns: [da1 x H | da2 x H | zeros]
+  const float* bounds;           // [0] rigorous bound of |dft|, [1] optimistic bound, [2] c (da is stored as da * c), device scalars
+  int* flag;                     // != 0: a value left the fp16 range under the optimistic scale
+  int* reruns;                   // optional statistics: number of second launches that had to do the work
+  float* scale_out;
+  float* partial;                // [n_tasks, H, NV * 128 + 4]: anchor parts of egonets with several chunks
+  int* counters;                 // [n_tasks * H], zero before the first launch, self-resetting
+  int* queue;                    // [32 * H]: per head {next item, warps retired}; zero before the first launch, self-resetting
+  int pass;                      // 0: optimistic scale; 1: rigorous scale, runs only if *flag
 };
 
-constexpr int kStarBwdWarps = 8;
-
-template <int NV>
-__device__ __forceinline__ void sb_load_row(const float* __restrict__ p, int lane, int D, float4 (&v)[NV]) {
-#pragma unroll
-  for (int t = 0; t < NV; ++t) {
-    const int c = (lane + 32 * t) * 4;
-    v[t] = (t < NV - 1 || c < D) ? __ldg(reinterpret_cast<const float4*>(p + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
+__device__ __forceinline__ uint32_t sb_saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sb_bar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void sb_bar_arrive_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sb_bar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void sb_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void sb_cp4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+// the executing thread's earlier cp.async copies arrive on `bar` when they have landed (counted in the barrier's expected arrivals)
+__device__ __forceinline__ void sb_cp_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
 template <int NV>
 __device__ __forceinline__ float sb_dot(const float4 (&a)[NV], const float4 (&b)[NV]) {
   float acc = 0.f;
@@ -64,11 +111,21 @@ __device__ __forceinline__ void sb_warp_sum2(float& a, float& b) {
   }
 }
 
-template <int NV>
-__global__ void __launch_bounds__(kStarBwdWarps * 32, 2) gat_star_bwd_kernel(const StarBwdParams p) {
-  __shared__ float4 s_l[NV * 32];
-  __shared__ float4 s_r[NV * 32];
-  __shared__ float4 s_acc[kStarBwdWarps][2][NV * 32];      // per warp: d(attn_l), d(attn_r) of this head
+struct SbItem { int o, q, a, s, c, ticket; };
+
+template <int NV, bool F16OUT>
+__global__ void __launch_bounds__(kSbWarps * 32, 1) gat_star_bwd_kernel(const StarBwdParams p) {
+  constexpr int kRowB = NV * 512;                          // one staged row (zero-padded columns are never copied)
+  constexpr int kSlotB = kSbHdrBytes + 2 * kRowB;
+  constexpr int kPartLd = NV * 128 + 4;                    // floats per partial row: accumulator | da1 part, da2 (chunk 0)
+  if (p.pass == 1 && *reinterpret_cast<volatile int*>(p.flag) == 0) return;      // the optimistic launch was exact: nothing to redo
+
+  extern __shared__ __align__(128) unsigned char sb_smem[];
+  float4* s_l = reinterpret_cast<float4*>(sb_smem);
+  float4* s_r = s_l + NV * 32;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(sb_smem + 2 * kRowB);
+  unsigned char* s_slots = sb_smem + 2 * kRowB + 512;      // 16 warps x 3 barriers x 8 B = 384 B, padded to 512
+
   const int h = blockIdx.y;
   const int H = p.H, D = p.D;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -77,396 +134,429 @@ __global__ void __launch_bounds__(kStarBwdWarps * 32, 2) gat_star_bwd_kernel(con
     s_l[t] = c < D ? __ldg(reinterpret_cast<const float4*>(p.attn_l + (int64_t)h * D + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
     s_r[t] = c < D ? __ldg(reinterpret_cast<const float4*>(p.attn_r + (int64_t)h * D + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  const uint32_t bar0 = sb_saddr(s_bar + wid * kSbStages);
+  unsigned char* my_slots = s_slots + (size_t)wid * kSbStages * kSlotB;
+  const uint32_t slot0 = sb_saddr(my_slots);
+  if (lane == 0) {
 #pragma unroll
-  for (int t = 0; t < NV; ++t) {
-    s_acc[wid][0][lane + 32 * t] = make_float4(0.f, 0.f, 0.f, 0.f);
-    s_acc[wid][1][lane + 32 * t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int st = 0; st < kSbStages; ++st) sb_bar_init(bar0 + 8 * st, 33);      // lane 0's arrive.expect_tx + 32 cp.async arrivals
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-  const bool attn_drop = p.attn_thr != 0;
+
   const float gs = p.g_scale;
   const float* gbase = p.g + (int64_t)h * p.g_head_stride;
   const float* fbase = p.ft + (int64_t)h * D;
-  const float scale16 = p.dft16_hi ? f16_split_scale(__ldg(p.bound)) : 1.f;
-  if (p.dft16_hi && p.scale_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *p.scale_out = scale16;
+  const uint32_t rowB = (uint32_t)D * 4u;
+  const int C = p.chunk;
+  const float bound = F16OUT ? __ldg(p.bounds + (p.pass == 0 ? 1 : 0)) : 1.f;
+  const float scale16 = F16OUT ? f16_split_scale(bound) : 1.f;
+  const float da_scale = F16OUT ? scale16 * __ldg(p.bounds + 2) : 1.f;
+  const float gsS = p.g_scale * scale16;                   // attention weights of g rows carry the output scale
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    if (F16OUT && p.scale_out) *p.scale_out = scale16;
+    if (p.pass == 1 && p.reruns) atomicAdd(p.reruns, 1);
+  }
+  int* qn = p.queue + 32 * h;
+  float vmax = 0.f;                                        // largest |scaled value| this lane has written (fp16 range check)
 
-  auto keepw = [&](int eid) -> float {
-    if (!attn_drop) return 1.f;
-    return drop_keep1(p.attn_seed, p.attn_stream, (uint64_t)((int64_t)eid * H + h), p.attn_thr) ? p.attn_inv_keep : 0.f;
+  auto decode = [&](int item) -> SbItem {
+    const int4 w = __ldg(reinterpret_cast<const int4*>(p.tasks) + item);
+    SbItem k;
+    k.o = w.x; k.q = w.y; k.a = w.z & 0xFFFFFF; k.c = (w.z >> 24) & 0x7F; k.s = w.w; k.ticket = item;
+    return k;
+  };
+  auto n_ops_of = [&](const SbItem& k) -> int {
+    return k.c == 0 ? 1 + 2 * k.a + min(k.s, C) : 1 + min(C, k.s - k.c * C);
   };
   auto dslope = [&](float e) -> float { return e > 0.f ? 1.f : p.neg_slope; };
-  // first egonet whose first row is >= x (node_off is strictly increasing: every egonet has its anchor)
-  auto first_egonet = [&](int64_t x) -> int {
-    int lo = 0, hi = p.n_graphs;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if ((int64_t)__ldg(p.node_off + mid) < x) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-  };
-  const int64_t nW = (int64_t)gridDim.x * kStarBwdWarps, W = (int64_t)blockIdx.x * kStarBwdWarps + wid;
-  const int eg_beg = first_egonet(W * p.n / nW), eg_end = first_egonet((W + 1) * p.n / nW);
 
-  for (int eg = eg_beg; eg < eg_end; ++eg) {
-    const int a = __ldg(p.n_gp + eg), s = __ldg(p.n_sib + eg), o = __ldg(p.node_off + eg), q = __ldg(p.edge_off + eg);
-    const int n = a + 1 + s, self0 = q + a + s, A = o + a, deg = a + 1;
-    float4 gA[NV], fA[NV], accA[NV];
-    sb_load_row<NV>(gbase + (int64_t)A * p.ldg, lane, D, gA);
-    sb_load_row<NV>(fbase + (int64_t)A * p.ldf, lane, D, fA);
-    // ---- anchor: d(alpha~) of its in-edges {gp_0 .. gp_{a-1}, self} and their weighted sum ----
-    float dd_mine = 0.f, al_mine = 0.f, el_mine = 1.f, tsum = 0.f;
-    for (int k = 0; k <= a; ++k) {
-      float4 rf[NV];
-      if (k < a) {
-        sb_load_row<NV>(fbase + (int64_t)(o + k) * p.ldf, lane, D, rf);
+  // ---- producer side: the item queue (tickets two items ahead) and the step cursor ----
+  int pending = 0;
+  SbItem fk = {0, 0, 0, 0, 0, 0}, nk = {0, 0, 0, 0, 0, 0};
+  {
+    int c0 = 0, c1 = 0;
+    if (lane == 0) { c0 = atomicAdd(qn, 1); c1 = atomicAdd(qn, 1); pending = atomicAdd(qn, 1); }
+    c0 = __shfl_sync(0xffffffffu, c0, 0);
+    c1 = __shfl_sync(0xffffffffu, c1, 0);
+    fk.ticket = c0; nk.ticket = c1;
+    if (c0 < p.n_tasks) fk = decode(c0);
+    if (c1 < p.n_tasks) nk = decode(c1);
+  }
+  int f_t = 0, f_n = fk.ticket < p.n_tasks ? n_ops_of(fk) : 0;
+  bool f_done = false;
+  // The steps of an item are a pure function of its record; every lane works out ONE of them (step t0 + lane) when the item starts and
+  // a staging step just picks its lane's descriptor with two shuffles: {kind | row << 3, first attention slot}.
+  int my_kr = 0, my_so = 0;
+  auto build_steps = [&](int t0) {
+    const int t = t0 + lane;
+    int kind = kOpEnd, row = 0, so = 0;
+    if (fk.ticket < p.n_tasks && t < f_n) {
+      if (t == 0) {
+        kind = fk.c == 0 ? kOpAnchor0 : kOpAnchorC; row = fk.o + fk.a; so = fk.q + 2 * fk.a;
+      } else if (fk.c == 0 && t <= fk.a) {
+        kind = kOpGpDot; row = fk.o + t - 1; so = fk.q + fk.a + t - 1;
+      } else if (fk.c == 0 && t <= 2 * fk.a) {
+        kind = kOpGpOut; row = fk.o + t - fk.a - 1; so = fk.q + t - fk.a - 1;
       } else {
-#pragma unroll
-        for (int t = 0; t < NV; ++t) rf[t] = fA[t];
-      }
-      const int64_t so = (int64_t)(q + a + k) * H + h;
-      const float d = warp_sum(sb_dot<NV>(gA, rf)) * gs * keepw(k < a ? q + k : self0 + a);
-      const float alk = __ldg(p.alpha + so);
-      tsum = fmaf(alk, d, tsum);
-      if (deg <= 32) {
-        if (lane == k) { dd_mine = d; al_mine = alk; el_mine = __ldg(p.elog + so); }
-      } else if (lane == 0) {
-        p.ds[so] = d;
+        const int j = fk.c == 0 ? t - fk.a : fk.a + 1 + fk.c * C + (t - 1);      // local row of the sibling
+        kind = kOpSib; row = fk.o + j; so = fk.q + 2 * j - 1;
       }
     }
-    float ds_mine = 0.f, da2A = 0.f, ds_aa;
-    if (deg <= 32) {
-      if (lane < deg) ds_mine = al_mine * (dd_mine - tsum) * dslope(el_mine);
-      da2A = warp_sum(ds_mine);
-      ds_aa = __shfl_sync(0xffffffffu, ds_mine, a);
-    } else {
-      __syncwarp();
-      for (int k = lane; k < deg; k += 32) {
-        const int64_t so = (int64_t)(q + a + k) * H + h;
-        const float dsv = __ldg(p.alpha + so) * (p.ds[so] - tsum) * dslope(__ldg(p.elog + so));
-        p.ds[so] = dsv;
-        da2A += dsv;
-      }
-      da2A = warp_sum(da2A);
-      __syncwarp();
-      ds_aa = p.ds[(int64_t)(q + 2 * a) * H + h];
+    my_kr = kind | (row << 3);
+    my_so = so;
+  };
+  build_steps(0);
+  // this lane's attention scalar of a step: lanes 0..5 -> {alpha[so], alpha[so + 1], elog[so], elog[so + 1], alpha_d[so], alpha_d[so + 1]}
+  // (slot units, times H, plus h); which lanes take part depends on the kind (one byte per kind, bit = lane)
+  const float* my_arr = (lane < 2 ? p.alpha : (lane < 4 ? p.elog : p.alpha_d)) + h;
+  const uint64_t kLaneMask = (0x15ull << (8 * kOpAnchor0)) | (0x15ull << (8 * kOpGpDot)) | (0x10ull << (8 * kOpGpOut)) | (0x3Full << (8 * kOpSib));
+
+  // stage step number `it` (slot it % 3): header, scalars, row copies.  Warp-uniform control flow; every lane arrives once.
+  auto fetch = [&](int it) {
+    if (f_done) return;
+    const int st = it % kSbStages;
+    const uint32_t bar = bar0 + 8 * st;
+    const uint32_t slot = slot0 + st * kSlotB;
+    if (f_t == f_n) {                                      // next item
+      fk = nk;
+      f_t = 0;
+      const int t2 = __shfl_sync(0xffffffffu, pending, 0);
+      nk.ticket = t2;
+      if (t2 < p.n_tasks) nk = decode(t2);
+      // (no new ticket once the queue is exhausted: every atomic of this warp has been read, i.e. performed, before it retires)
+      if (lane == 0 && fk.ticket < p.n_tasks) pending = atomicAdd(qn, 1);
+      f_n = fk.ticket < p.n_tasks ? n_ops_of(fk) : 0;
+      build_steps(0);
+    } else if ((f_t & 31) == 0) {
+      build_steps(f_t);
     }
-    float da1A = ds_aa;                                   // + sum over siblings of ds(anchor -> sibling), collected below
-    {
-      const float w = __ldg(p.alpha_d + (int64_t)(q + 2 * a) * H + h) * gs;          // alpha~ of the anchor's self loop
-#pragma unroll
-      for (int t = 0; t < NV; ++t) accA[t] = make_float4(w * gA[t].x, w * gA[t].y, w * gA[t].z, w * gA[t].w);
+    const int kr = __shfl_sync(0xffffffffu, my_kr, f_t & 31), so = __shfl_sync(0xffffffffu, my_so, f_t & 31);
+    const int kind = kr & 7, row = kr >> 3;
+    ++f_t;
+    f_done = kind == kOpEnd;
+    if (lane < 8 && ((kLaneMask >> (8 * kind + lane)) & 1ull))
+      sb_cp4(slot + 32 + 4 * lane, my_arr + (int64_t)(so + (kind == kOpSib ? (lane & 1) : 0)) * H);
+    sb_cp_arrive(bar);
+    if (lane == 0) {
+      const bool has_g = (0x32 >> kind) & 1, has_f = (0x2E >> kind) & 1;       // kinds {1, 4, 5} carry g, {1, 2, 3, 5} carry ft
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot), "r"(kind), "r"(row), "r"(fk.ticket), "r"(0) : "memory");
+      if (kind == kOpAnchor0 || kind == kOpAnchorC)
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot + 16), "r"(fk.o), "r"(fk.q), "r"(fk.a | (fk.c << 24)), "r"(fk.s) : "memory");
+      sb_bar_arrive_tx(bar, ((has_g ? 1u : 0u) + (has_f ? 1u : 0u)) * rowB);
+      if (has_g) sb_bulk_g2s(slot + kSbHdrBytes, gbase + (int64_t)row * p.ldg, rowB, bar);
+      if (has_f) sb_bulk_g2s(slot + kSbHdrBytes + kRowB, fbase + (int64_t)row * p.ldf, rowB, bar);
     }
-    // ---- every row once: grand-parents, siblings, the anchor LAST (it needs the siblings' contributions); ONE loop body ----
-    for (int jj = 0; jj < n; ++jj) {
-      const int j = jj < a ? jj : (jj < n - 1 ? jj + 1 : a);       // local row: 0..a-1 gp, a anchor, a+1.. siblings
-      float4 rg[NV], rf[NV];
-      float c1, c2;                                                // da1_j, da2_j: coefficients of attn_l / attn_r and of ft_j in d(attn)
-      if (j == a) {
-#pragma unroll
-        for (int t = 0; t < NV; ++t) { rg[t] = accA[t]; rf[t] = fA[t]; }
-        c1 = da1A; c2 = da2A;
-      } else {
-        sb_load_row<NV>(gbase + (int64_t)(o + j) * p.ldg, lane, D, rg);
-        sb_load_row<NV>(fbase + (int64_t)(o + j) * p.ldf, lane, D, rf);
-        if (j < a) {
-          // grand-parent: alpha~_self g_j + alpha~(j -> anchor) g_anchor; its own softmax backward vanishes (single in-edge)
-          const float dsk = deg <= 32 ? __shfl_sync(0xffffffffu, ds_mine, j) : p.ds[(int64_t)(q + a + j) * H + h];
-          const float w_self = __ldg(p.alpha_d + (int64_t)(q + j) * H + h) * gs;
-          const float w_anch = __ldg(p.alpha_d + (int64_t)(q + a + j) * H + h) * gs;
-#pragma unroll
-          for (int t = 0; t < NV; ++t) {
-            rg[t].x = fmaf(w_self, rg[t].x, w_anch * gA[t].x); rg[t].y = fmaf(w_self, rg[t].y, w_anch * gA[t].y);
-            rg[t].z = fmaf(w_self, rg[t].z, w_anch * gA[t].z); rg[t].w = fmaf(w_self, rg[t].w, w_anch * gA[t].w);
-          }
-          c1 = dsk; c2 = 0.f;
-        } else {
-          // sibling: in-edges {anchor -> j (slot q + 2j - 1, edge id q + j - 1), self (slot q + 2j, edge id self0 + j)}
-          const int64_t s1 = (int64_t)(q + 2 * j - 1) * H + h, s2 = s1 + H;
-          float d1 = sb_dot<NV>(rg, fA), d2 = sb_dot<NV>(rg, rf);
-          sb_warp_sum2(d1, d2);
-          d1 *= gs * keepw(q + j - 1);
-          d2 *= gs * keepw(self0 + j);
-          const float al1 = __ldg(p.alpha + s1), al2 = __ldg(p.alpha + s2);
-          const float ts = fmaf(al1, d1, al2 * d2);
-          const float ds1 = al1 * (d1 - ts) * dslope(__ldg(p.elog + s1));
-          const float ds2 = al2 * (d2 - ts) * dslope(__ldg(p.elog + s2));
-          da1A += ds1;
-          const float w1 = __ldg(p.alpha_d + s1) * gs, w2 = __ldg(p.alpha_d + s2) * gs;
-#pragma unroll
-          for (int t = 0; t < NV; ++t) {
-            accA[t].x = fmaf(w1, rg[t].x, accA[t].x); accA[t].y = fmaf(w1, rg[t].y, accA[t].y);
-            accA[t].z = fmaf(w1, rg[t].z, accA[t].z); accA[t].w = fmaf(w1, rg[t].w, accA[t].w);
-            rg[t].x *= w2; rg[t].y *= w2; rg[t].z *= w2; rg[t].w *= w2;
-          }
-          c1 = ds2; c2 = ds1 + ds2;
-        }
-      }
-      // common tail: d(ft_j) = rg + c1 attn_l + c2 attn_r;  d(attn_l) += c1 ft_j;  d(attn_r) += c2 ft_j
-      const int64_t row = o + j;
+  };
+
+  // d(ft_row) S = rg + (c1 S) attn_l + (c2 S) attn_r with rg ALREADY times S = the fp16-pair scale (1 for fp32 output; the callers fold
+  // it into the attention weights), written as fp16 hi/lo pair or fp32, and the row's (da1, da2) = (c1, c2)
+  auto write_row = [&](int row, const float4 (&rg)[NV], float c1, float c2) {
+    const int64_t r64 = row;
+    const float c1s = c1 * scale16, c2s = c2 * scale16;
+    if constexpr (F16OUT) {
+      __half* hi = p.dft16_hi + r64 * p.ld16 + (int64_t)h * D + lane * 4;
+      __half* lo = p.dft16_lo + r64 * p.ld16 + (int64_t)h * D + lane * 4;
 #pragma unroll
       for (int t = 0; t < NV; ++t) {
         const int c4 = lane + 32 * t;
-        const float4 l = s_l[c4], r = s_r[c4];
-        float4 v;
-        v.x = fmaf(c1, l.x, fmaf(c2, r.x, rg[t].x)); v.y = fmaf(c1, l.y, fmaf(c2, r.y, rg[t].y));
-        v.z = fmaf(c1, l.z, fmaf(c2, r.z, rg[t].z)); v.w = fmaf(c1, l.w, fmaf(c2, r.w, rg[t].w));
-        float4 hl = s_acc[wid][0][c4], hr = s_acc[wid][1][c4];
-        hl.x = fmaf(c1, rf[t].x, hl.x); hl.y = fmaf(c1, rf[t].y, hl.y); hl.z = fmaf(c1, rf[t].z, hl.z); hl.w = fmaf(c1, rf[t].w, hl.w);
-        hr.x = fmaf(c2, rf[t].x, hr.x); hr.y = fmaf(c2, rf[t].y, hr.y); hr.z = fmaf(c2, rf[t].z, hr.z); hr.w = fmaf(c2, rf[t].w, hr.w);
-        s_acc[wid][0][c4] = hl;
-        s_acc[wid][1][c4] = hr;
         if (t < NV - 1 || c4 * 4 < D) {
-          if (p.dft16_hi) {
-            uint2 h16, l16;
-            f16_split4(v, scale16, h16, l16);
-            const int64_t o16 = row * p.ld16 + (int64_t)h * D + c4 * 4;
-            *reinterpret_cast<uint2*>(p.dft16_hi + o16) = h16;
-            *reinterpret_cast<uint2*>(p.dft16_lo + o16) = l16;
-          } else {
-            *reinterpret_cast<float4*>(p.dft + row * p.ldd + (int64_t)h * D + c4 * 4) = v;
-          }
+          const float4 l = s_l[c4], r = s_r[c4];
+          const float x0 = fmaf(c1s, l.x, fmaf(c2s, r.x, rg[t].x)), x1 = fmaf(c1s, l.y, fmaf(c2s, r.y, rg[t].y));
+          const float x2 = fmaf(c1s, l.z, fmaf(c2s, r.z, rg[t].z)), x3 = fmaf(c1s, l.w, fmaf(c2s, r.w, rg[t].w));
+          vmax = fmaxf(fmaxf(vmax, fabsf(x0)), fmaxf(fabsf(x1), fmaxf(fabsf(x2), fabsf(x3))));
+          const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+          const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+          const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y), l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
+          *reinterpret_cast<uint2*>(hi + 128 * t) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+          *reinterpret_cast<uint2*>(lo + 128 * t) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+        }
+      }
+      // tail columns [H D, ld16): da1 of head h at H D + h, da2 at H D + H + h (both times c, scaled like the row), zeros after 2 H
+      if (lane < 2) {
+        const float x = (lane ? c2 : c1) * da_scale;
+        vmax = fmaxf(vmax, fabsf(x));
+        const __half xh = __float2half_rn(x);
+        const int64_t o = r64 * p.ld16 + (int64_t)H * D + lane * H + h;
+        p.dft16_hi[o] = xh;
+        p.dft16_lo[o] = __float2half_rn(x - __half2float(xh));
+      } else if (h == 0 && lane - 2 < p.tail16 - 2 * H) {
+        const int64_t o = r64 * p.ld16 + (int64_t)H * D + 2 * H + (lane - 2);
+        p.dft16_hi[o] = __float2half_rn(0.f);
+        p.dft16_lo[o] = __float2half_rn(0.f);
+      }
+    } else {
+      float* out = p.dft + r64 * p.ldd + (int64_t)h * D + lane * 4;
+#pragma unroll
+      for (int t = 0; t < NV; ++t) {
+        const int c4 = lane + 32 * t;
+        if (t < NV - 1 || c4 * 4 < D) {
+          const float4 l = s_l[c4], r = s_r[c4];
+          float4 v;
+          v.x = fmaf(c1s, l.x, fmaf(c2s, r.x, rg[t].x)); v.y = fmaf(c1s, l.y, fmaf(c2s, r.y, rg[t].y));
+          v.z = fmaf(c1s, l.z, fmaf(c2s, r.z, rg[t].z)); v.w = fmaf(c1s, l.w, fmaf(c2s, r.w, rg[t].w));
+          *reinterpret_cast<float4*>(out + 128 * t) = v;
         }
       }
     }
-  }
-  // ---- d(attn) partials: the warps' accumulators summed in warp order (fixed) ----
-  __syncthreads();
-  const int D4 = D >> 2;
-  for (int t = threadIdx.x; t < 2 * D4; t += blockDim.x) {
-    const int lr = t / D4, c4 = t - lr * D4;
-    float4 sum = s_acc[0][lr][c4];
-#pragma unroll
-    for (int w = 1; w < kStarBwdWarps; ++w) {
-      const float4 x = s_acc[w][lr][c4];
-      sum.x += x.x; sum.y += x.y; sum.z += x.z; sum.w += x.w;
+    if (p.da1 && lane == 0) {
+      p.da1[r64 * H + h] = c1;
+      p.da2[r64 * H + h] = c2;
     }
-    *reinterpret_cast<float4*>(p.dattn_partial + (((int64_t)blockIdx.x * 2 + lr) * H + h) * D + c4 * 4) = sum;
-  }
-}
-
-
-// ---------------------------------------------------------------------------------------------------------------------------------
-// Team variant (TAXO_STAR_BWD_COOP=<rows>, opt-in, NOT yet run on hardware): same arithmetic, different dealing.  A CTA owns the
-// egonets whose first row lies in its slice of the rows; SMALL egonets (fewer than `coop_rows` rows) go to its warps round-robin, a
-// LARGE egonet is processed by all 8 warps together: every warp loads the anchor pair, takes the siblings k = warp (mod 8), and the
-// warps' anchor accumulators are added through one shared-memory row in warp order (fixed -> deterministic) before warp 0 writes the
-// anchor row.  This removes the tail of the whole-egonet-per-warp dealing (a 55-row egonet is 3.5 x the average warp load at H = 1)
-// without per-chunk scratch rows or a fix-up pass.  One loop body serves both team sizes.
-// ---------------------------------------------------------------------------------------------------------------------------------
-template <int NV>
-__global__ void __launch_bounds__(kStarBwdWarps * 32, 2) gat_star_bwd_team_kernel(const StarBwdParams p, const int coop_rows) {
-  __shared__ float4 s_l[NV * 32];
-  __shared__ float4 s_r[NV * 32];
-  __shared__ float4 s_acc[kStarBwdWarps][2][NV * 32];      // per warp: d(attn_l), d(attn_r) of this head
-  __shared__ float4 s_red[NV * 32];                        // anchor accumulator of a team, added warp by warp
-  __shared__ float s_da1;
-  const int h = blockIdx.y;
-  const int H = p.H, D = p.D;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int t = threadIdx.x; t < NV * 32; t += blockDim.x) {
-    const int c = t * 4;
-    s_l[t] = c < D ? __ldg(reinterpret_cast<const float4*>(p.attn_l + (int64_t)h * D + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    s_r[t] = c < D ? __ldg(reinterpret_cast<const float4*>(p.attn_r + (int64_t)h * D + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-#pragma unroll
-  for (int t = 0; t < NV; ++t) {
-    s_acc[wid][0][lane + 32 * t] = make_float4(0.f, 0.f, 0.f, 0.f);
-    s_acc[wid][1][lane + 32 * t] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  __syncthreads();
-  const bool attn_drop = p.attn_thr != 0;
-  const float gs = p.g_scale;
-  const float* gbase = p.g + (int64_t)h * p.g_head_stride;
-  const float* fbase = p.ft + (int64_t)h * D;
-  const float scale16 = p.dft16_hi ? f16_split_scale(__ldg(p.bound)) : 1.f;
-  if (p.dft16_hi && p.scale_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *p.scale_out = scale16;
-
-  auto keepw = [&](int eid) -> float {
-    if (!attn_drop) return 1.f;
-    return drop_keep1(p.attn_seed, p.attn_stream, (uint64_t)((int64_t)eid * H + h), p.attn_thr) ? p.attn_inv_keep : 0.f;
   };
-  auto dslope = [&](float e) -> float { return e > 0.f ? 1.f : p.neg_slope; };
-  auto first_egonet = [&](int64_t x) -> int {
-    int lo = 0, hi = p.n_graphs;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if ((int64_t)__ldg(p.node_off + mid) < x) lo = mid + 1; else hi = mid;
+
+  // ---- consumer state of the current item ----
+  SbItem ck = {0, 0, 0, 0, 0, 0};
+  int ops_left = 0;
+  float4 gA[NV], fA[NV], accA[NV];
+  float dd_mine = 0.f, al_mine = 0.f, el_mine = 1.f, ad_mine = 0.f, ds_mine = 0.f, tsum = 0.f, da1A = 0.f, da2A = 0.f;
+#pragma unroll
+  for (int t = 0; t < NV; ++t) gA[t] = fA[t] = accA[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  // softmax + leaky-relu backward over the anchor's a + 1 in-edges once all their dots are known
+  auto finish_anchor_softmax = [&]() {
+    const int a = ck.a, deg = a + 1;
+    if (deg <= 32) {
+      ds_mine = lane < deg ? (ad_mine * dd_mine - al_mine * tsum) * dslope(el_mine) : 0.f;
+      da2A = warp_sum(ds_mine);
+      da1A = __shfl_sync(0xffffffffu, ds_mine, a);
+    } else {
+      __syncwarp();
+      float acc = 0.f;
+      for (int k = lane; k < deg; k += 32) {
+        const int64_t so = (int64_t)(ck.q + a + k) * H + h;
+        const float dsv = (__ldg(p.alpha_d + so) * p.ds[so] - __ldg(p.alpha + so) * tsum) * dslope(__ldg(p.elog + so));
+        p.ds[so] = dsv;
+        acc += dsv;
+      }
+      da2A = warp_sum(acc);
+      __syncwarp();
+      da1A = p.ds[(int64_t)(ck.q + 2 * a) * H + h];
     }
-    return lo;
   };
-  // the CTA's egonets (identical in every warp: the loop below is CTA-uniform, so the barriers of the large egonets are safe)
-  const int eg_beg = first_egonet((int64_t)blockIdx.x * p.n / gridDim.x), eg_end = first_egonet((int64_t)(blockIdx.x + 1) * p.n / gridDim.x);
-  int n_small = 0;
 
-  for (int eg = eg_beg; eg < eg_end; ++eg) {
-    const int a = __ldg(p.n_gp + eg), s = __ldg(p.n_sib + eg), o = __ldg(p.node_off + eg), q = __ldg(p.edge_off + eg);
-    const int n = a + 1 + s, self0 = q + a + s, A = o + a, deg = a + 1;
-    const bool big = n >= coop_rows;                     // CTA-uniform
-    int team = 1, rank = 0;
-    if (big) { team = kStarBwdWarps; rank = wid; }
-    else if ((n_small++ % kStarBwdWarps) != wid) continue;     // a small egonet belongs to one warp; the others move on (no barrier here)
+  fetch(0);
+  fetch(1);
+  for (int it = 0;; ++it) {
+    __syncwarp();                                          // every lane is done with the slot that is staged next
+    fetch(it + 2);
+    const int st = it % kSbStages;
+    sb_bar_wait(bar0 + 8 * st, (uint32_t)((it / kSbStages) & 1));
+    const unsigned char* slot = my_slots + (size_t)st * kSlotB;
+    const uint4 hd = *reinterpret_cast<const uint4*>(slot);
+    const int kind = (int)hd.x, row = (int)hd.y;
+    if (kind == kOpEnd) break;
+    const float4 sc0 = *reinterpret_cast<const float4*>(slot + 32);       // alpha[so], alpha[so+1], elog[so], elog[so+1]
+    const float2 sc1 = *reinterpret_cast<const float2*>(slot + 48);       // alpha_d[so], alpha_d[so+1]
+    const float4* sg = reinterpret_cast<const float4*>(slot + kSbHdrBytes);
+    const float4* sf = reinterpret_cast<const float4*>(slot + kSbHdrBytes + kRowB);
+    const int D4 = D >> 2;
 
-    float4 gA[NV], fA[NV], accA[NV];
-    sb_load_row<NV>(gbase + (int64_t)A * p.ldg, lane, D, gA);
-    sb_load_row<NV>(fbase + (int64_t)A * p.ldf, lane, D, fA);
-    float ds_mine = 0.f, da2A = 0.f, da1A = 0.f;
+    if (kind == kOpAnchor0 || kind == kOpAnchorC) {
+      const uint4 rec = *reinterpret_cast<const uint4*>(slot + 16);
+      ck.o = (int)rec.x; ck.q = (int)rec.y; ck.a = (int)(rec.z & 0xFFFFFF); ck.c = (int)((rec.z >> 24) & 0x7F); ck.s = (int)rec.w;
+      ck.ticket = (int)hd.z;
+      ops_left = n_ops_of(ck);
+      da1A = 0.f; da2A = 0.f; tsum = 0.f;
 #pragma unroll
-    for (int t = 0; t < NV; ++t) accA[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (rank == 0) {
-      // ---- anchor: d(alpha~) of its in-edges {gp_0 .. gp_{a-1}, self}, softmax backward (as in gat_star_bwd_kernel) ----
-      float dd_mine = 0.f, al_mine = 0.f, el_mine = 1.f, tsum = 0.f;
-      for (int k = 0; k <= a; ++k) {
-        float4 rf[NV];
-        if (k < a) {
-          sb_load_row<NV>(fbase + (int64_t)(o + k) * p.ldf, lane, D, rf);
-        } else {
-#pragma unroll
-          for (int t = 0; t < NV; ++t) rf[t] = fA[t];
-        }
-        const int64_t so = (int64_t)(q + a + k) * H + h;
-        const float d = warp_sum(sb_dot<NV>(gA, rf)) * gs * keepw(k < a ? q + k : self0 + a);
-        const float alk = __ldg(p.alpha + so);
-        tsum = fmaf(alk, d, tsum);
-        if (deg <= 32) {
-          if (lane == k) { dd_mine = d; al_mine = alk; el_mine = __ldg(p.elog + so); }
-        } else if (lane == 0) {
-          p.ds[so] = d;
-        }
+      for (int t = 0; t < NV; ++t) {
+        const int c4 = lane + 32 * t;
+        fA[t] = (t < NV - 1 || c4 < D4) ? sf[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      float ds_aa;
-      if (deg <= 32) {
-        if (lane < deg) ds_mine = al_mine * (dd_mine - tsum) * dslope(el_mine);
-        da2A = warp_sum(ds_mine);
-        ds_aa = __shfl_sync(0xffffffffu, ds_mine, a);
-      } else {
-        __syncwarp();
-        for (int k = lane; k < deg; k += 32) {
-          const int64_t so = (int64_t)(q + a + k) * H + h;
-          const float dsv = __ldg(p.alpha + so) * (p.ds[so] - tsum) * dslope(__ldg(p.elog + so));
-          p.ds[so] = dsv;
-          da2A += dsv;
-        }
-        da2A = warp_sum(da2A);
-        __syncwarp();
-        ds_aa = p.ds[(int64_t)(q + 2 * a) * H + h];
-      }
-      da1A = ds_aa;
-      const float w = __ldg(p.alpha_d + (int64_t)(q + 2 * a) * H + h) * gs;            // alpha~ of the anchor's self loop
-#pragma unroll
-      for (int t = 0; t < NV; ++t) accA[t] = make_float4(w * gA[t].x, w * gA[t].y, w * gA[t].z, w * gA[t].w);
-    }
-    // rows of this warp: rank 0 takes the grand-parents, every rank the siblings k = rank (mod team); the anchor row is a second
-    // pass of the SAME loop body (rank 0 only), after the team's anchor accumulators have been combined
-    const int cnt_gp = rank == 0 ? a : 0;
-    const int cnt_sib = s > rank ? (s - rank + team - 1) / team : 0;
-    for (int pass = 0; pass < 2; ++pass) {
-      const int it_beg = pass == 0 ? 0 : cnt_gp + cnt_sib;
-      const int it_end = pass == 0 ? cnt_gp + cnt_sib : (rank == 0 ? cnt_gp + cnt_sib + 1 : cnt_gp + cnt_sib);
-      for (int it = it_beg; it < it_end; ++it) {
-        const int j = it < cnt_gp ? it : (it < cnt_gp + cnt_sib ? a + 1 + rank + (it - cnt_gp) * team : a);
-        float4 rg[NV], rf[NV];
-        float c1, c2;
-        if (j == a) {
-#pragma unroll
-          for (int t = 0; t < NV; ++t) { rg[t] = accA[t]; rf[t] = fA[t]; }
-          c1 = da1A; c2 = da2A;
-        } else {
-          sb_load_row<NV>(gbase + (int64_t)(o + j) * p.ldg, lane, D, rg);
-          sb_load_row<NV>(fbase + (int64_t)(o + j) * p.ldf, lane, D, rf);
-          if (j < a) {
-            const float dsk = deg <= 32 ? __shfl_sync(0xffffffffu, ds_mine, j) : p.ds[(int64_t)(q + a + j) * H + h];
-            const float w_self = __ldg(p.alpha_d + (int64_t)(q + j) * H + h) * gs;
-            const float w_anch = __ldg(p.alpha_d + (int64_t)(q + a + j) * H + h) * gs;
-#pragma unroll
-            for (int t = 0; t < NV; ++t) {
-              rg[t].x = fmaf(w_self, rg[t].x, w_anch * gA[t].x); rg[t].y = fmaf(w_self, rg[t].y, w_anch * gA[t].y);
-              rg[t].z = fmaf(w_self, rg[t].z, w_anch * gA[t].z); rg[t].w = fmaf(w_self, rg[t].w, w_anch * gA[t].w);
-            }
-            c1 = dsk; c2 = 0.f;
-          } else {
-            const int64_t s1 = (int64_t)(q + 2 * j - 1) * H + h, s2 = s1 + H;
-            float d1 = sb_dot<NV>(rg, fA), d2 = sb_dot<NV>(rg, rf);
-            sb_warp_sum2(d1, d2);
-            d1 *= gs * keepw(q + j - 1);
-            d2 *= gs * keepw(self0 + j);
-            const float al1 = __ldg(p.alpha + s1), al2 = __ldg(p.alpha + s2);
-            const float ts = fmaf(al1, d1, al2 * d2);
-            const float ds1 = al1 * (d1 - ts) * dslope(__ldg(p.elog + s1));
-            const float ds2 = al2 * (d2 - ts) * dslope(__ldg(p.elog + s2));
-            da1A += ds1;
-            const float w1 = __ldg(p.alpha_d + s1) * gs, w2 = __ldg(p.alpha_d + s2) * gs;
-#pragma unroll
-            for (int t = 0; t < NV; ++t) {
-              accA[t].x = fmaf(w1, rg[t].x, accA[t].x); accA[t].y = fmaf(w1, rg[t].y, accA[t].y);
-              accA[t].z = fmaf(w1, rg[t].z, accA[t].z); accA[t].w = fmaf(w1, rg[t].w, accA[t].w);
-              rg[t].x *= w2; rg[t].y *= w2; rg[t].z *= w2; rg[t].w *= w2;
-            }
-            c1 = ds2; c2 = ds1 + ds2;
-          }
-        }
-        const int64_t row = o + j;
+      if (kind == kOpAnchor0) {
 #pragma unroll
         for (int t = 0; t < NV; ++t) {
           const int c4 = lane + 32 * t;
-          const float4 l = s_l[c4], r = s_r[c4];
-          float4 v;
-          v.x = fmaf(c1, l.x, fmaf(c2, r.x, rg[t].x)); v.y = fmaf(c1, l.y, fmaf(c2, r.y, rg[t].y));
-          v.z = fmaf(c1, l.z, fmaf(c2, r.z, rg[t].z)); v.w = fmaf(c1, l.w, fmaf(c2, r.w, rg[t].w));
-          float4 hl = s_acc[wid][0][c4], hr = s_acc[wid][1][c4];
-          hl.x = fmaf(c1, rf[t].x, hl.x); hl.y = fmaf(c1, rf[t].y, hl.y); hl.z = fmaf(c1, rf[t].z, hl.z); hl.w = fmaf(c1, rf[t].w, hl.w);
-          hr.x = fmaf(c2, rf[t].x, hr.x); hr.y = fmaf(c2, rf[t].y, hr.y); hr.z = fmaf(c2, rf[t].z, hr.z); hr.w = fmaf(c2, rf[t].w, hr.w);
-          s_acc[wid][0][c4] = hl;
-          s_acc[wid][1][c4] = hr;
-          if (t < NV - 1 || c4 * 4 < D) {
-            if (p.dft16_hi) {
-              uint2 h16, l16;
-              f16_split4(v, scale16, h16, l16);
-              const int64_t o16 = row * p.ld16 + (int64_t)h * D + c4 * 4;
-              *reinterpret_cast<uint2*>(p.dft16_hi + o16) = h16;
-              *reinterpret_cast<uint2*>(p.dft16_lo + o16) = l16;
-            } else {
-              *reinterpret_cast<float4*>(p.dft + row * p.ldd + (int64_t)h * D + c4 * 4) = v;
-            }
-          }
+          gA[t] = (t < NV - 1 || c4 < D4) ? sg[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        // the anchor's self loop: in-edge number a of its softmax
+        const float d = warp_sum(sb_dot<NV>(gA, fA)) * gs;
+        const float al = sc0.x, el = sc0.z, ad = sc1.x;
+        tsum = ad * d;
+        if (ck.a + 1 <= 32) {
+          if (lane == ck.a) { dd_mine = d; al_mine = al; el_mine = el; ad_mine = ad; }
+        } else if (lane == 0) {
+          p.ds[(int64_t)(ck.q + 2 * ck.a) * H + h] = d;
+        }
+        const float w = ad * gsS;
+#pragma unroll
+        for (int t = 0; t < NV; ++t) accA[t] = make_float4(w * gA[t].x, w * gA[t].y, w * gA[t].z, w * gA[t].w);
+        if (ck.a == 0) finish_anchor_softmax();
+      } else {
+#pragma unroll
+        for (int t = 0; t < NV; ++t) accA[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    } else if (kind == kOpGpDot) {
+      const int k = row - ck.o;
+      float acc = 0.f;
+#pragma unroll
+      for (int t = 0; t < NV; ++t) {
+        const int c4 = lane + 32 * t;
+        if (t < NV - 1 || c4 < D4) {
+          const float4 f = sf[c4];
+          acc = fmaf(gA[t].x, f.x, acc); acc = fmaf(gA[t].y, f.y, acc); acc = fmaf(gA[t].z, f.z, acc); acc = fmaf(gA[t].w, f.w, acc);
         }
       }
-      if (pass == 0 && big) {
-        // combine the team: accA and da1A of the 8 warps, added in warp order through one shared row (CTA-uniform branch)
-        for (int w = 0; w < kStarBwdWarps; ++w) {
-          if (wid == w) {
+      const float d = warp_sum(acc) * gs;
+      const float al = sc0.x, el = sc0.z, ad = sc1.x;
+      tsum = fmaf(ad, d, tsum);
+      if (ck.a + 1 <= 32) {
+        if (lane == k) { dd_mine = d; al_mine = al; el_mine = el; ad_mine = ad; }
+      } else if (lane == 0) {
+        p.ds[(int64_t)(ck.q + ck.a + k) * H + h] = d;
+      }
+      if (k == ck.a - 1) finish_anchor_softmax();
+    } else if (kind == kOpGpOut) {
+      const int j = row - ck.o;
+      float dsk, w_anch;
+      if (ck.a + 1 <= 32) {
+        dsk = __shfl_sync(0xffffffffu, ds_mine, j);
+        w_anch = __shfl_sync(0xffffffffu, ad_mine, j) * gsS;
+      } else {
+        const int64_t so = (int64_t)(ck.q + ck.a + j) * H + h;
+        dsk = p.ds[so];
+        w_anch = __ldg(p.alpha_d + so) * gsS;
+      }
+      const float w_self = sc1.x * gsS;
+      float4 rg[NV];
+#pragma unroll
+      for (int t = 0; t < NV; ++t) {
+        const int c4 = lane + 32 * t;
+        const float4 x = (t < NV - 1 || c4 < D4) ? sg[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+        rg[t].x = fmaf(w_self, x.x, w_anch * gA[t].x); rg[t].y = fmaf(w_self, x.y, w_anch * gA[t].y);
+        rg[t].z = fmaf(w_self, x.z, w_anch * gA[t].z); rg[t].w = fmaf(w_self, x.w, w_anch * gA[t].w);
+      }
+      write_row(row, rg, dsk, 0.f);
+    } else {   // kOpSib
+      float4 rg[NV];
+      float d1 = 0.f, d2 = 0.f;
+#pragma unroll
+      for (int t = 0; t < NV; ++t) {
+        const int c4 = lane + 32 * t;
+        if (t < NV - 1 || c4 < D4) {
+          rg[t] = sg[c4];
+          const float4 f = sf[c4];
+          d1 = fmaf(rg[t].x, fA[t].x, d1); d1 = fmaf(rg[t].y, fA[t].y, d1); d1 = fmaf(rg[t].z, fA[t].z, d1); d1 = fmaf(rg[t].w, fA[t].w, d1);
+          d2 = fmaf(rg[t].x, f.x, d2); d2 = fmaf(rg[t].y, f.y, d2); d2 = fmaf(rg[t].z, f.z, d2); d2 = fmaf(rg[t].w, f.w, d2);
+        } else {
+          rg[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      sb_warp_sum2(d1, d2);
+      d1 *= gs; d2 *= gs;
+      const float al1 = sc0.x, al2 = sc0.y, el1 = sc0.z, el2 = sc0.w, ad1 = sc1.x, ad2 = sc1.y;
+      const float ts = fmaf(ad1, d1, ad2 * d2);
+      const float ds1 = (ad1 * d1 - al1 * ts) * dslope(el1);
+      const float ds2 = (ad2 * d2 - al2 * ts) * dslope(el2);
+      da1A += ds1;
+      const float w1 = ad1 * gsS, w2 = ad2 * gsS;
+#pragma unroll
+      for (int t = 0; t < NV; ++t) {
+        accA[t].x = fmaf(w1, rg[t].x, accA[t].x); accA[t].y = fmaf(w1, rg[t].y, accA[t].y);
+        accA[t].z = fmaf(w1, rg[t].z, accA[t].z); accA[t].w = fmaf(w1, rg[t].w, accA[t].w);
+        rg[t].x *= w2; rg[t].y *= w2; rg[t].z *= w2; rg[t].w *= w2;
+      }
+      write_row(row, rg, ds2, ds1 + ds2);
+    }
+
+    if (--ops_left == 0) {
+      // ---- end of the item: the anchor's row ----
+      const int n_chunks = ck.s > C ? (ck.s + C - 1) / C : 1;
+      if (n_chunks == 1) {
+        write_row(ck.o + ck.a, accA, da1A, da2A);
+      } else {
+        float* part = p.partial + ((int64_t)ck.ticket * H + h) * kPartLd;
+#pragma unroll
+        for (int t = 0; t < NV; ++t) __stcg(reinterpret_cast<float4*>(part) + lane + 32 * t, accA[t]);
+        if (lane == 0) __stcg(reinterpret_cast<float4*>(part) + NV * 32, make_float4(da1A, da2A, 0.f, 0.f));
+        __syncwarp();                                      // the warp's stores happen before lane 0's fence (cumulativity)
+        const int first = ck.ticket - ck.c;
+        int prev = 0;
+        if (lane == 0) {
+          __threadfence();
+          prev = atomicAdd(p.counters + (int64_t)first * H + h, 1);
+        }
+        prev = __shfl_sync(0xffffffffu, prev, 0);
+        if (prev == n_chunks - 1) {
+          // last chunk to arrive: add the parts in chunk order (fixed) and write the anchor's row
+          __threadfence();
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int t = 0; t < NV; ++t) accA[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int cc = 0; cc < n_chunks; ++cc) {
+            const float4* pr = reinterpret_cast<const float4*>(p.partial + ((int64_t)(first + cc) * H + h) * kPartLd);
 #pragma unroll
             for (int t = 0; t < NV; ++t) {
-              const int c4 = lane + 32 * t;
-              float4 x = accA[t];
-              if (w > 0) { const float4 y = s_red[c4]; x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
-              s_red[c4] = x;
+              const float4 x = __ldcg(pr + lane + 32 * t);
+              accA[t].x += x.x; accA[t].y += x.y; accA[t].z += x.z; accA[t].w += x.w;
             }
-            if (lane == 0) s_da1 = w > 0 ? s_da1 + da1A : da1A;
+            const float4 sc = __ldcg(pr + NV * 32);
+            s1 += sc.x;
+            if (cc == 0) s2 = sc.y;
           }
-          __syncthreads();
+          if (lane == 0) p.counters[(int64_t)first * H + h] = 0;
+          write_row(ck.o + ck.a, accA, s1, s2);
         }
-        if (rank == 0) {
-#pragma unroll
-          for (int t = 0; t < NV; ++t) accA[t] = s_red[lane + 32 * t];
-          da1A = s_da1;
-        }
-        __syncthreads();                                  // s_red / s_da1 are free again before the next large egonet
       }
     }
   }
-  // ---- d(attn) partials: the warps' accumulators summed in warp order (fixed) ----
-  __syncthreads();
-  const int D4 = D >> 2;
-  for (int t = threadIdx.x; t < 2 * D4; t += blockDim.x) {
-    const int lr = t / D4, c4 = t - lr * D4;
-    float4 sum = s_acc[0][lr][c4];
-#pragma unroll
-    for (int w = 1; w < kStarBwdWarps; ++w) {
-      const float4 x = s_acc[w][lr][c4];
-      sum.x += x.x; sum.y += x.y; sum.z += x.z; sum.w += x.w;
+  if (F16OUT && vmax > 65504.f) *p.flag = 1;           // (benign race: every writer stores the same value)
+  // ---- retire: the last warp of this head's queue resets it for the next launch ----
+  if (lane == 0) {
+    const int total = (int)(gridDim.x * kSbWarps);
+    if (atomicAdd(qn + 1, 1) == total - 1) {
+      qn[0] = 0;
+      qn[1] = 0;
     }
-    *reinterpret_cast<float4*>(p.dattn_partial + (((int64_t)blockIdx.x * 2 + lr) * H + h) * D + c4 * 4) = sum;
   }
+}
+
+// d(attn_l)[h, :] = W_h v[h, :] / c,  d(attn_r)[h, :] = W_h v[H + h, :] / c   (W_h = rows h D .. h D + D - 1 of the layer's fc weight,
+// v = z^T [da1 c | da2 c] = the 2 H extra rows of the weight-gradient GEMM): one warp per output element pair, fixed-order sums.
+__global__ void attn_grad_from_v_kernel(const float* __restrict__ w, int64_t ldw, const float* __restrict__ v, int64_t ldv, int H, int D, int K,
+                                        const float* __restrict__ c_ptr, float* __restrict__ dal, float* __restrict__ dar) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= H * D) return;
+  const int h = row / D;
+  const float* wr = w + (int64_t)row * ldw;
+  const float* v1 = v + (int64_t)h * ldv;
+  const float* v2 = v + (int64_t)(H + h) * ldv;
+  float a = 0.f, b = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float x = __ldg(wr + k);
+    a = fmaf(x, __ldg(v1 + k), a);
+    b = fmaf(x, __ldg(v2 + k), b);
+  }
+  sb_warp_sum2(a, b);
+  if (lane == 0) {
+    const float inv = 1.f / __ldg(c_ptr);
+    dal[row] = a * inv;
+    dar[row] = b * inv;
+  }
+}
+
+template <int NV>
+static size_t sb_smem_bytes() { return (size_t)2 * NV * 512 + 512 + (size_t)kSbWarps * kSbStages * (kSbHdrBytes + 2 * NV * 512); }
+
+template <int NV, bool F16OUT>
+static int sb_launch2(const StarBwdParams& p, dim3 grid, cudaStream_t st) {
+  static bool attr_done = false;
+  const size_t smem = sb_smem_bytes<NV>();
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(gat_star_bwd_kernel<NV, F16OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      set_error("gat_star_bwd: cannot reserve %zu bytes of shared memory", smem);
+      return TX_ERR_CUDA;
+    }
+    attr_done = true;
+  }
+  gat_star_bwd_kernel<NV, F16OUT><<<grid, kSbWarps * 32, smem, st>>>(p);
+  return TX_OK;
+}
+template <int NV>
+static int sb_launch(const StarBwdParams& p, dim3 grid, cudaStream_t st) {
+  return p.dft16_hi ? sb_launch2<NV, true>(p, grid, st) : sb_launch2<NV, false>(p, grid, st);
 }
 
 }  // namespace tx
@@ -475,61 +565,67 @@ using namespace tx;
 
 extern "C" {
 
-int64_t tx_gat_star_bwd_blocks(int64_t n_nodes, int64_t heads) {
-  if (heads < 1) heads = 1;
-  int64_t gx = (2 * (int64_t)kNumSms + heads - 1) / heads;          // two CTAs per SM over all heads
-  const int64_t need = (n_nodes + kStarBwdWarps - 1) / kStarBwdWarps;
-  if (gx > need) gx = need;
-  return gx < 1 ? 1 : gx;
+int64_t tx_gat_star_bwd_partial_floats(int64_t n_tasks, int64_t heads, int64_t dim) {
+  return n_tasks * heads * (((dim + 127) / 128) * 128 + 4);
 }
 
 int tx_gat_star_bwd(const float* g, int64_t ldg, int64_t g_head_stride, float g_scale, const float* ft, int64_t ldf,
                     const float* alpha, const float* alpha_d, const float* elog, const float* attn_l, const float* attn_r,
-                    const int32_t* n_gp, const int32_t* n_sib, const int32_t* node_off, const int32_t* edge_off, int64_t n_graphs,
-                    int64_t n_nodes, int64_t heads, int64_t dim, float neg_slope, float p_attn, uint64_t attn_seed,
-                    uint32_t attn_stream_id, float* ds, float* dft, int64_t ldd, void* dft16_hi, void* dft16_lo, int64_t ld16,
-                    const float* bound, float* scale_out, float* dattn_partial, void* stream) {
+                    const int32_t* tasks, int64_t n_tasks, int64_t chunk, int64_t n_nodes, int64_t heads, int64_t dim, float neg_slope,
+                    float* ds, float* da1, float* da2, float* dft, int64_t ldd, void* dft16_hi, void* dft16_lo, int64_t ld16,
+                    const float* bounds, int32_t* flag, int32_t* reruns, float* scale_out, float* partial, int32_t* counters,
+                    int32_t* queue, void* stream) {
   TX_REQUIRE(g_head_stride != 0 || heads == 1, "gat_star_bwd: a shared g row (head mean) needs heads == 1");
-  TX_REQUIRE(!dft16_hi || (dft16_lo && bound && aligned16(dft16_hi) && aligned16(dft16_lo) && ld16 % 8 == 0 && ld16 >= heads * dim),
-             "gat_star_bwd: bad fp16 output buffers");
-  TX_REQUIRE(dft16_hi || (dft && aligned16(dft) && ldd % 4 == 0 && ldd >= heads * dim), "gat_star_bwd: an output buffer is required");
+  TX_REQUIRE(!dft16_hi || (dft16_lo && bounds && flag && aligned16(dft16_hi) && aligned16(dft16_lo) && ld16 % 8 == 0 &&
+                           ld16 >= heads * dim + 2 * heads && ld16 - heads * dim <= 2 * heads + 30),
+             "gat_star_bwd: bad fp16 output buffers (ld16 must hold heads * dim + 2 * heads columns)");
+  TX_REQUIRE(dft16_hi || (dft && da1 && da2 && aligned16(dft) && ldd % 4 == 0 && ldd >= heads * dim),
+             "gat_star_bwd: an output buffer is required (fp32 output also needs da1 / da2)");
+  TX_REQUIRE((da1 == nullptr) == (da2 == nullptr), "gat_star_bwd: da1 and da2 go together");
   TX_REQUIRE(dim > 0 && dim % 4 == 0 && dim <= 512, "gat_star_bwd: dim must be a multiple of 4 and <= 512");
   TX_REQUIRE(aligned16(g) && ldg % 4 == 0 && g_head_stride % 4 == 0 && aligned16(ft) && ldf % 4 == 0 && aligned16(attn_l) &&
-             aligned16(attn_r) && aligned16(dattn_partial), "gat_star_bwd: 16-byte aligned rows required");
-  TX_REQUIRE(p_attn >= 0.f && p_attn < 1.f, "gat_star_bwd: dropout rate must be in [0,1)");
-  TX_REQUIRE(n_gp && n_sib && node_off && edge_off && alpha && elog && ds && dattn_partial, "gat_star_bwd: null pointer");
-  TX_REQUIRE(n_graphs >= 0 && n_graphs < (1ll << 31) && n_nodes >= 0 && n_nodes < (1ll << 31), "gat_star_bwd: bad sizes");
-  if (n_nodes == 0 || n_graphs == 0) return TX_OK;
+             aligned16(attn_r) && aligned16(partial), "gat_star_bwd: 16-byte aligned rows required");
+  TX_REQUIRE(tasks && aligned16(tasks) && alpha && alpha_d && elog && ds && partial && counters && queue, "gat_star_bwd: null pointer");
+  TX_REQUIRE(n_tasks >= 0 && n_tasks < (1ll << 31) && n_nodes >= 0 && n_nodes < (1ll << 31) && chunk >= 1 && chunk < (1 << 20) &&
+             heads >= 1 && heads <= 64, "gat_star_bwd: bad sizes");
+  if (n_nodes == 0 || n_tasks == 0) return TX_OK;
   StarBwdParams p;
   p.g = g; p.ldg = ldg; p.g_head_stride = g_head_stride; p.g_scale = g_scale; p.ft = ft; p.ldf = ldf;
-  p.alpha = alpha; p.alpha_d = alpha_d ? alpha_d : alpha; p.elog = elog; p.attn_l = attn_l; p.attn_r = attn_r;
-  p.n_gp = n_gp; p.n_sib = n_sib; p.node_off = node_off; p.edge_off = edge_off; p.n_graphs = (int)n_graphs; p.n = (int)n_nodes;
-  p.H = (int)heads; p.D = (int)dim; p.neg_slope = neg_slope; p.attn_inv_keep = 1.f / (1.f - p_attn);
-  p.attn_thr = drop_threshold(p_attn); p.attn_seed = attn_seed; p.attn_stream = attn_stream_id; p.ds = ds;
-  p.dft = dft; p.ldd = ldd; p.dft16_hi = (__half*)dft16_hi; p.dft16_lo = (__half*)dft16_lo; p.ld16 = ld16; p.bound = bound;
-  p.scale_out = scale_out; p.dattn_partial = dattn_partial;
+  p.alpha = alpha; p.alpha_d = alpha_d; p.elog = elog; p.attn_l = attn_l; p.attn_r = attn_r;
+  p.tasks = tasks; p.n_tasks = (int)n_tasks; p.chunk = (int)chunk; p.H = (int)heads; p.D = (int)dim; p.neg_slope = neg_slope;
+  p.ds = ds; p.da1 = da1; p.da2 = da2; p.dft = dft; p.ldd = ldd;
+  p.dft16_hi = (__half*)dft16_hi; p.dft16_lo = (__half*)dft16_lo; p.ld16 = ld16; p.tail16 = (int)(ld16 - heads * dim);
+  p.bounds = bounds; p.flag = flag; p.reruns = reruns; p.scale_out = scale_out; p.partial = partial; p.counters = counters; p.queue = queue;
   const int nv = (int)((dim + 127) / 128);
-  dim3 grid((unsigned)tx_gat_star_bwd_blocks(n_nodes, heads), (unsigned)heads);
+  int gx = (int)((kNumSms + heads - 1) / heads);
+  const int64_t need = (n_tasks + kSbWarps - 1) / kSbWarps;
+  if (gx > need) gx = (int)need;
+  if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, (unsigned)heads);
   cudaStream_t st = (cudaStream_t)stream;
-  static int coop = -1;                                   // TAXO_STAR_BWD_COOP=<rows>: team variant for egonets with >= rows nodes
-  if (coop < 0) { const char* e = getenv("TAXO_STAR_BWD_COOP"); coop = e ? atoi(e) : 0; if (coop < 0) coop = 0; }
-  if (coop > 0) {
+  const int passes = dft16_hi ? 2 : 1;
+  for (int pass = 0; pass < passes; ++pass) {
+    p.pass = pass;
+    int rc;
     switch (nv) {
-      case 1: gat_star_bwd_team_kernel<1><<<grid, kStarBwdWarps * 32, 0, st>>>(p, coop); break;
-      case 2: gat_star_bwd_team_kernel<2><<<grid, kStarBwdWarps * 32, 0, st>>>(p, coop); break;
-      case 3: gat_star_bwd_team_kernel<3><<<grid, kStarBwdWarps * 32, 0, st>>>(p, coop); break;
-      default: gat_star_bwd_team_kernel<4><<<grid, kStarBwdWarps * 32, 0, st>>>(p, coop); break;
+      case 1: rc = sb_launch<1>(p, grid, st); break;
+      case 2: rc = sb_launch<2>(p, grid, st); break;
+      case 3: rc = sb_launch<3>(p, grid, st); break;
+      default: rc = sb_launch<4>(p, grid, st); break;
     }
-    TX_LAUNCH_CHECK("tx_gat_star_bwd (team)");
-    return TX_OK;
+    if (rc != TX_OK) return rc;
+    TX_LAUNCH_CHECK("tx_gat_star_bwd");
   }
-  switch (nv) {
-    case 1: gat_star_bwd_kernel<1><<<grid, kStarBwdWarps * 32, 0, st>>>(p); break;
-    case 2: gat_star_bwd_kernel<2><<<grid, kStarBwdWarps * 32, 0, st>>>(p); break;
-    case 3: gat_star_bwd_kernel<3><<<grid, kStarBwdWarps * 32, 0, st>>>(p); break;
-    default: gat_star_bwd_kernel<4><<<grid, kStarBwdWarps * 32, 0, st>>>(p); break;
-  }
-  TX_LAUNCH_CHECK("tx_gat_star_bwd");
+  return TX_OK;
+}
+
+int tx_attn_grad_from_v(const float* weight, int64_t ldw, const float* v, int64_t ldv, int64_t heads, int64_t dim, int64_t k,
+                        const float* c, float* dattn_l, float* dattn_r, void* stream) {
+  TX_REQUIRE(weight && v && c && dattn_l && dattn_r && heads >= 1 && dim >= 1 && k >= 1 && ldw >= k && ldv >= k, "attn_grad_from_v: bad arguments");
+  const int64_t rows = heads * dim;
+  attn_grad_from_v_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(weight, ldw, v, ldv, (int)heads, (int)dim, (int)k, c,
+                                                                                        dattn_l, dattn_r);
+  TX_LAUNCH_CHECK("tx_attn_grad_from_v");
   return TX_OK;
 }
 

@@ -62,9 +62,12 @@ STAGED_FWD = os.environ.get("TAXO_STAGED_FWD", "0") not in ("", "0")
 # work item, anchor row in registers; TAXO_STAR_FWD=0 -> the general warp-per-(row, head) kernel
 STAR_FWD = os.environ.get("TAXO_STAR_FWD", "1") not in ("", "0")
 STAR_FWD_OUTPUT_LAYER = os.environ.get("TAXO_STAR_FWD", "1") != "hidden"     # TAXO_STAR_FWD=hidden: hidden layers only
-# star-specialised fused GAT backward (tx_star_bwd.cu), first version: parity-green on a B200 (test_star_backward_matches_staged_backward,
-# TAXO_STAR_BWD_TEST=1) but only on par with the staged kernel at H = 4 (0.279 vs 0.283 ms) and slower at H = 1 (0.145 vs 0.097 ms): opt-in
-STAR_BWD = os.environ.get("TAXO_STAR_BWD", "0") not in ("", "0")
+# star-specialised fused GAT backward (tx_star_bwd.cu, second generation: warp-private TMA rings, (egonet, sibling chunk) work items,
+# d(attn) through 2 H extra rows of the weight-gradient GEMM); TAXO_STAR_BWD=0 -> the tile-staged general backward
+STAR_BWD = os.environ.get("TAXO_STAR_BWD", "1") not in ("", "0")
+# the star backward first writes d(ft) with the fp16-pair scale of  TAXO_DFT_OPTIMISM x max|g| / (1 - p_attn)  and redoes the pass with
+# the rigorous bound of tx_bound_dft only if a value left the fp16 range (device flag, no host sync); 0 = rigorous bound only
+DFT_OPTIMISM = float(os.environ.get("TAXO_DFT_OPTIMISM", "4"))
 
 _star_queues = {}
 
@@ -81,6 +84,30 @@ def _star_queue(device) -> torch.Tensor:
             raise _lib.TaxoLibraryError("tx_gat_star_fwd: task encoding of the library differs from taxoexpan_b200.graph; rebuild")
         q = _star_queues[key] = torch.zeros(32 * 64, dtype=torch.int32, device=device)
     return q
+
+
+_star_counter_bufs = {}
+_star_rerun_bufs = {}
+
+
+def _star_counters(device, n: int) -> torch.Tensor:
+    """Per-egonet arrival counters of tx_gat_star_bwd (zero before the first launch, left zero by every launch), one growing buffer
+    per (device, stream)."""
+    key = (device.index, current_stream().value)
+    c = _star_counter_bufs.get(key)
+    if c is None or c.numel() < n:
+        c = _star_counter_bufs[key] = torch.zeros(max(n, 1 << 16), dtype=torch.int32, device=device)
+    return c
+
+
+def star_bwd_reruns(device) -> torch.Tensor:
+    """Device counter: how many tx_gat_star_bwd calls had to redo their pass with the rigorous fp16 scale (statistics)."""
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    c = _star_rerun_bufs.get(idx)
+    if c is None:
+        c = _star_rerun_bufs[idx] = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", idx))
+    return c
 
 
 def use_fused(lib, heads: int, dim: int, mean_heads: int, st=None) -> bool:
@@ -283,8 +310,10 @@ def _dz_epilogue(in_link, c0a):
     return None
 
 
-def _layer_gemms_bwd_f16(dy, f, saved, w_kf, k, ldz, c0, need_w, need_z, in_link=None, dy16=None):
-    """f16x3 form of _layer_gemms_bwd: dy comes fp16-split from the fused backward kernel (dy16) or is split here."""
+def _layer_gemms_bwd_f16(dy, f, saved, w_kf, k, ldz, c0, need_w, need_z, in_link=None, dy16=None, extra_rows=0):
+    """f16x3 form of _layer_gemms_bwd: dy comes fp16-split from the fused backward kernel (dy16) or is split here.  extra_rows: columns
+    [f, f + extra_rows) of dy16 (the star backward's per-node attention coefficients) join the weight-gradient GEMM: dw has
+    f + extra_rows rows."""
     n = saved[0].shape[0]
     dw = dz = None
     zp = F16Pair(saved[0], saved[1], saved[2], k)
@@ -293,7 +322,7 @@ def _layer_gemms_bwd_f16(dy, f, saved, w_kf, k, ldz, c0, need_w, need_z, in_link
             dy16 = split_f16(dy, f)
     if need_w:
         with timed_region("gemm_dw"):
-            dw = gemm_tn_f16(dy16, f, zp, k)
+            dw = gemm_tn_f16(dy16, f + extra_rows, zp, k)
     if need_z:
         with timed_region("gemm_dz"):
             c0a = (min(c0, k) // 8) * 8                   # fp16 rows: 16-byte aligned slices start at multiples of 8 columns
@@ -314,10 +343,10 @@ def _layer_gemms_bwd_f16(dy, f, saved, w_kf, k, ldz, c0, need_w, need_z, in_link
     return dw, dz
 
 
-def _layer_gemms_bwd(dy, f, saved, w_kf, k, ldz, c0, need_w, need_z, in_link=None, dy_lo=None, dy16=None):
+def _layer_gemms_bwd(dy, f, saved, w_kf, k, ldz, c0, need_w, need_z, in_link=None, dy_lo=None, dy16=None, extra_rows=0):
     """dW_fk = dy[:, :f]^T @ z[:, :k]  and  dz[:, c0a:k] = dy[:, :f] @ w_kf[c0a:k, :f]^T (see _gemm_dz)."""
     if GEMM_BACKEND == "f16x3" and saved[0].shape[0] > 0:
-        return _layer_gemms_bwd_f16(dy, f, saved, w_kf, k, ldz, c0, need_w, need_z, in_link, dy16)
+        return _layer_gemms_bwd_f16(dy, f, saved, w_kf, k, ldz, c0, need_w, need_z, in_link, dy16, extra_rows)
     n = dy.shape[0]
     dw = dz = None
     if GEMM_BACKEND != "tf32x3" or n == 0:
@@ -628,16 +657,18 @@ class GatLayer(Function):
                 g_head_stride, g_scale = (D, 1.0) if cfg.hidden else (0, 1.0 / H)
                 pre = cfg.out_link is not None and cfg.out_link.applied     # d(z_next) already carries the epilogue derivative
                 if STAGED_BWD and (pre or ctx.maskbits is None):
-                    # TMA-staged kernel: rows of a tile of whole graphs are bulk-copied to shared memory one tile ahead
-                    tiles = st.bwd_tiles(D)
-                    nbf = int(lib.tx_gat_fused_bwd_staged_blocks(n, H, D))
-                    partial = torch.empty(nbf * 2 * F_, **f32)
+                    # star backward (EgonetBatch) or the TMA-staged tile kernel (any batched graph)
+                    f16out = FUSE_SPLIT and GEMM_BACKEND == "f16x3" and ft_amax is not None and n > 0
+                    use_star = STAR_BWD and st.star_bwd is not None and dft_lo is None and n > 0 and H <= 64
+                    need_w = ctx.needs_input_grad[1]
                     d_hi = d_lo = d_scale = bound = None
-                    ld16 = round8(F_)
-                    if FUSE_SPLIT and GEMM_BACKEND == "f16x3" and ft_amax is not None and n > 0:
+                    star_extra = 2 * H if (use_star and f16out) else 0
+                    ld16 = round8(F_ + star_extra)
+                    if f16out:
                         # dft goes out fp16-split.  Its scale needs an upper bound of |dft| BEFORE the kernel runs:
                         #   |sum_i alpha~_ij g_i| <= outdeg max|g| / (1 - p_attn),  |d alpha~| = |<g_i, ft_j>| <= D max|g| max|ft|,
                         #   |ds| <= 2 |d alpha~| / (1 - p_attn),  |da1_j| <= outdeg |ds|,  |da2_i| <= |ds|
+                        # (rigorous, ~2^13 above the true maximum; the star backward tries DFT_OPTIMISM x max|g| first, see above)
                         hand = st._dh_bound
                         st._dh_bound = None
                         if cfg.out_link is not None and cfg.out_link.dz_amax is not None and pre:
@@ -648,26 +679,50 @@ class GatLayer(Function):
                             g_amax = absmax(dout, F_ if cfg.hidden else D)
                         deg = max(int(st.max_out_deg), 1)
                         slope = max(1.0, abs(cfg.neg_slope))
-                        bound = torch.empty(1, **f32)
+                        bound = torch.empty(4, **f32)
                         check(lib.tx_bound_dft(ptr(g_amax), ptr(ft_amax), ptr(al), ptr(ar), al.numel(), g_scale * deg / (1.0 - cfg.p_attn),
-                                               g_scale * 2.0 * (deg + 1) * D * slope / (1.0 - cfg.p_attn), ptr(bound), stream), "tx_bound_dft")
+                                               g_scale * 2.0 * (deg + 1) * D * slope / (1.0 - cfg.p_attn),
+                                               g_scale * DFT_OPTIMISM / (1.0 - cfg.p_attn) if use_star else 0.0, ptr(bound), stream),
+                              "tx_bound_dft")
                         d_hi = torch.empty((n, ld16), dtype=torch.float16, device=dev)
                         d_lo = torch.empty((n, ld16), dtype=torch.float16, device=dev)
-                        if ld16 > F_:
+                        if ld16 > F_ and not use_star:
                             d_hi[:, F_:].zero_()
                             d_lo[:, F_:].zero_()
                         d_scale = torch.empty(1, **f32)
                         dft16 = F16Pair(d_hi, d_lo, d_scale, F_)
-                    if STAR_BWD and st.counts is not None and dft_lo is None and n > 0:
-                        cg = st.counts
-                        nbf = int(lib.tx_gat_star_bwd_blocks(n, H))
-                        partial = torch.empty(nbf * 2 * F_, **f32)
+                    if use_star:
+                        sg = st.star_bwd
+                        partial = torch.empty(int(lib.tx_gat_star_bwd_partial_floats(sg[1], H, D)), **f32)
+                        attn_from_gemm = f16out and need_w               # d(attn) from 2 H extra rows of the weight-gradient GEMM
+                        da1 = None if attn_from_gemm else torch.empty(n * H, **f32)
+                        if not attn_from_gemm:
+                            star_extra = 0
+                        flag = None if bound is None else bound[3:4].view(torch.int32)
                         check(lib.tx_gat_star_bwd(ptr(dout), ldg, g_head_stride, g_scale, ptr(ft), F_, ptr(alpha), ptr(alpha_d), ptr(elog),
-                                                  ptr(al), ptr(ar), ptr(cg[0]), ptr(cg[1]), ptr(cg[2]), ptr(cg[3]), st.g, n, H, D,
-                                                  cfg.neg_slope, cfg.p_attn, cfg.attn_seed, cfg.attn_stream, ptr(ds), ptr(dft), F_,
-                                                  ptr(d_hi), ptr(d_lo), ld16, ptr(bound), ptr(d_scale), ptr(partial), stream),
-                              "tx_gat_star_bwd")
+                                                  ptr(al), ptr(ar), ptr(sg[0]), sg[1], sg[2], n, H, D, cfg.neg_slope, ptr(ds),
+                                                  ptr(da1), None if attn_from_gemm else ptr(da2), None if f16out else ptr(dft), F_,
+                                                  ptr(d_hi), ptr(d_lo), ld16, ptr(bound), ptr(flag), ptr(star_bwd_reruns(dev)) if f16out else None,
+                                                  ptr(d_scale), ptr(partial), ptr(_star_counters(dev, sg[1] * H)),
+                                                  ptr(_star_queue(dev)), stream), "tx_gat_star_bwd")
+                        if attn_from_gemm:
+                            dw, dz = _layer_gemms_bwd(dft, F_, (z0, z1, z_scale, wt_hi, wt_lo, wt_scale), weight.t(), K, ldz, cfg.dz_from, True,
+                                                      ctx.needs_input_grad[0], cfg.in_link, None, dft16, extra_rows=star_extra)
+                            v = dw[F_:]
+                            dw = dw[:F_]
+                            both = torch.empty(2 * F_, **f32)
+                            check(lib.tx_attn_grad_from_v(ptr(weight), weight.stride(0), ptr(v), v.stride(0), H, D, K, ptr(bound[2:3]),
+                                                          ptr(both), ptr(both[F_:]), stream), "tx_attn_grad_from_v")
+                            return dz, dw, both[:F_].view(ctx.attn_shape), both[F_:].view(ctx.attn_shape), dtab, None, None, None
+                        nbp = int(lib.tx_row_blocks(n))
+                        partial = torch.empty(nbp * 2 * F_, **f32)
+                        check(lib.tx_gat_attn_grad_partials(ptr(ft), F_, ptr(da1), ptr(da2), n, H, D, ptr(partial), stream),
+                              "tx_gat_attn_grad_partials")
+                        nbf = nbp
                     else:
+                        tiles = st.bwd_tiles(D)
+                        nbf = int(lib.tx_gat_fused_bwd_staged_blocks(n, H, D))
+                        partial = torch.empty(nbf * 2 * F_, **f32)
                         check(lib.tx_gat_fused_bwd_staged(ptr(dout), ldg, g_head_stride, g_scale, ptr(ft), F_, ptr(alpha), ptr(alpha_d),
                                                           ptr(elog), ptr(al), ptr(ar), ptr(st.in_ptr), ptr(st.in_src), ptr(st.in_eid),
                                                           ptr(st.out_ptr), ptr(st.out_dst), ptr(st.out_slot), ptr(tiles), n, H, D,

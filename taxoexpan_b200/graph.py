@@ -25,6 +25,10 @@ from . import _lib
 
 
 STAR_CHUNK = int(os.environ.get("TAXO_STAR_CHUNK", "4"))   # siblings per work item of the star-specialised forward kernel
+# siblings per work item of the star backward: its chunks of one egonet meet in a partial-row combine (a fence + an atomic per chunk), so
+# larger chunks pay there while the forward prefers small ones for its tail (measured L0: backward 0.200 -> 0.192 ms at 8, forward
+# 0.182 -> 0.192 ms at 8)
+STAR_BWD_CHUNK = int(os.environ.get("TAXO_STAR_BWD_CHUNK", "8"))
 STAR_MAX_CHUNKS = 128    # = tx_gat_star_max_chunks()
 
 
@@ -32,7 +36,7 @@ class GraphStructure:
     """Device-resident structure of one batched graph (all int32)."""
 
     __slots__ = ("device", "n", "e", "g", "in_ptr", "in_src", "in_eid", "out_ptr", "out_dst", "out_slot", "node_off",
-                 "pos", "src", "dst", "max_nodes", "max_out_deg", "_norm", "is_star", "_bwd_tiles", "_dh_bound", "star", "counts")
+                 "pos", "src", "dst", "max_nodes", "max_out_deg", "_norm", "is_star", "_bwd_tiles", "_dh_bound", "star", "star_bwd", "counts")
 
     def __init__(self, device):
         self.device = device
@@ -44,6 +48,7 @@ class GraphStructure:
         self.src = self.dst = None
         self.is_star = False
         self.star = None           # (task records, n_tasks, chunk) of an EgonetBatch on the device (tx_gat_star_fwd)
+        self.star_bwd = None       # the same with the backward's chunk size (tx_gat_star_bwd)
         self.counts = None         # (n_gp, n_sib, node_off, edge_off) device vectors of an EgonetBatch (tx_gat_star_bwd)
 
     def bwd_tiles(self, dim: int) -> torch.Tensor:
@@ -231,34 +236,43 @@ class EgonetBatch(DGLGraph):
         self._edges_built = False
         self._max_nodes = int(n.max()) if n.size else 0
         g = n.shape[0]
-        # one staging buffer: [n_gp | n_sib | node_off | edge_off | pad to 16 bytes | task records] as int32, filled in place
+        # one staging buffer: [n_gp | n_sib | node_off | edge_off | pad to 16 bytes | forward task records | backward task records] as
+        # int32, filled in place
         head_len = 4 * g + 2
         self._task_off = (head_len + 3) // 4 * 4
-        # work items of the star-specialised forward kernel (tx_gat_star_fwd): one 16-byte record {node_off, edge_off, n_gp | chunk << 24,
-        # n_sib} per (egonet, chunk of STAR_CHUNK siblings); none when the batch exceeds the encoding (the general fused kernel takes over)
-        n_chunks = (self.n_sib + (STAR_CHUNK - 1)) // STAR_CHUNK
-        np.maximum(n_chunks, 1, out=n_chunks)
-        n_tasks = int(n_chunks.sum(dtype=np.int64)) if g else 0
-        ok = g > 0 and int(self.n_gp.max()) < (1 << 24) and int(n_chunks.max()) <= STAR_MAX_CHUNKS
-        self._n_tasks = n_tasks if ok else 0
-        packed = np.empty(self._task_off + 4 * self._n_tasks, dtype=np.int32)
+        # work items of the star-specialised kernels (tx_gat_star_fwd / tx_gat_star_bwd): one 16-byte record {node_off, edge_off,
+        # n_gp | chunk << 24, n_sib} per (egonet, chunk of C siblings), C = STAR_CHUNK for the forward and STAR_BWD_CHUNK for the backward;
+        # none when the batch exceeds the encoding (the general fused kernels take over)
+        plans = []
+        for chunk in ((STAR_CHUNK,) if STAR_BWD_CHUNK == STAR_CHUNK else (STAR_CHUNK, STAR_BWD_CHUNK)):
+            n_chunks = (self.n_sib + (chunk - 1)) // chunk
+            np.maximum(n_chunks, 1, out=n_chunks)
+            plans.append((chunk, n_chunks, int(n_chunks.sum(dtype=np.int64)) if g else 0))
+        ok = g > 0 and int(self.n_gp.max()) < (1 << 24) and int(plans[0][1].max()) <= STAR_MAX_CHUNKS
+        self._n_tasks = plans[0][2] if ok else 0
+        self._n_tasks_bwd = plans[-1][2] if ok else 0
+        self._task_off_bwd = self._task_off + (4 * self._n_tasks if len(plans) > 1 else 0)
+        packed = np.empty(self._task_off + 4 * sum(pl[2] for pl in plans) * (1 if ok else 0), dtype=np.int32)
         packed[:g] = self.n_gp
         packed[g:2 * g] = self.n_sib
         packed[2 * g:3 * g + 1] = self._node_off
         packed[3 * g + 1:4 * g + 2] = self._edge_off
         packed[head_len:self._task_off] = 0
-        if self._n_tasks:
-            # record r of egonet k carries chunk number r - first[k]: in wrapping int32 arithmetic
-            # (n_gp - (first << 24)) + (r << 24) = n_gp | (chunk << 24), so one row-repeat and one strided add build all records
-            first = np.cumsum(n_chunks, dtype=np.int32) - n_chunks
+        if ok:
             base = np.empty((g, 4), dtype=np.int32)
             base[:, 0] = self._node_off[:-1]
             base[:, 1] = self._edge_off[:-1]
-            base[:, 2] = self.n_gp - np.left_shift(first, 24)
             base[:, 3] = self.n_sib
-            rec = packed[self._task_off:].reshape(-1, 4)
-            rec[:] = np.repeat(base, n_chunks, axis=0)
-            rec[:, 2] += np.left_shift(np.arange(self._n_tasks, dtype=np.int32), 24)
+            off = self._task_off
+            for chunk, n_chunks, n_tasks in plans:
+                # record r of egonet k carries chunk number r - first[k]: in wrapping int32 arithmetic
+                # (n_gp - (first << 24)) + (r << 24) = n_gp | (chunk << 24), so one row-repeat and one strided add build all records
+                first = np.cumsum(n_chunks, dtype=np.int32) - n_chunks
+                base[:, 2] = self.n_gp - np.left_shift(first, 24)
+                rec = packed[off:off + 4 * n_tasks].reshape(-1, 4)
+                rec[:] = np.repeat(base, n_chunks, axis=0)
+                rec[:, 2] += np.left_shift(np.arange(n_tasks, dtype=np.int32), 24)
+                off += 4 * n_tasks
         self._packed = torch.from_numpy(packed)
         self._g = g
         if ndata:
@@ -364,6 +378,7 @@ class EgonetBatch(DGLGraph):
             st.counts = (n_gp, n_sib, node_off, edge_off)
             if self._n_tasks:
                 st.star = (packed[self._task_off:self._task_off + 4 * self._n_tasks], self._n_tasks, STAR_CHUNK)
+                st.star_bwd = (packed[self._task_off_bwd:self._task_off_bwd + 4 * self._n_tasks_bwd], self._n_tasks_bwd, STAR_BWD_CHUNK)
             st.pos = torch.empty(st.n, **i32)
             st.in_ptr, st.in_src, st.in_eid = torch.empty(st.n + 1, **i32), torch.empty(st.e, **i32), torch.empty(st.e, **i32)
             st.out_ptr, st.out_dst, st.out_slot = torch.empty(st.n + 1, **i32), torch.empty(st.e, **i32), torch.empty(st.e, **i32)

@@ -61,8 +61,14 @@ def load_case(name):
     return cfg, og, x, qf, params, fx
 
 
-def compare_to_fixture(fx, scores, hg, node_h, loss, grads, dh, tol, gtol):
-    """tol: max-abs tolerance on O(1) outputs; gtol: tolerance on gradients relative to the largest |grad| of a tensor."""
+def compare_to_fixture(fx, scores, hg, node_h, loss, grads, dh, tol, gtol, ref_noise_factor=0.0):
+    """tol: max-abs tolerance on O(1) outputs; gtol: tolerance on gradients relative to the largest |grad| of a tensor.
+    ref_noise_factor > 0 (full-size cases): a gradient may additionally deviate by that multiple of the REFERENCE's own fp32-vs-fp64
+    difference on the same tensor (both runs are in the fixture).  At 8192 egonets the hidden layer holds 7.5e7 pre-activations, a
+    handful of them within fp32 rounding of the leaky-relu kink: the unmodified reference's fp32 run takes the other branch there than
+    its own fp64 run and its layer-0 gradients move by 1.5e-4 of their maximum (layer-1 gradients, behind no kink: 5e-7).  No
+    implementation can agree with the fp32 reference more closely than the reference agrees with itself; the arithmetic is pinned at
+    2e-5 by test_full_size_gradients_match_oracle_with_pinned_branches, which makes the oracle take the CUDA run's branches."""
     def close(a, b, t, what):
         a = np.asarray(a, dtype=np.float64)
         b = np.asarray(b, dtype=np.float64)
@@ -79,7 +85,8 @@ def compare_to_fixture(fx, scores, hg, node_h, loss, grads, dh, tol, gtol):
         close(dh, fx["dh"], gtol * max(float(np.abs(fx["dh"]).max()), 1e-30), "dh")
     else:
         close(sub(node_h, big_step), fx["node_h_sub"], tol, "node_h")
-        close(sub(dh, big_step), fx["dh_sub"], gtol * max(float(np.abs(fx["dh_sub"]).max()), 1e-30), "dh")
+        noise = ref_noise_factor * float(np.abs(fx["dh_sub"] - fx["dh_sub_f64"]).max()) if ref_noise_factor else 0.0
+        close(sub(dh, big_step), fx["dh_sub"], max(gtol * max(float(np.abs(fx["dh_sub"]).max()), 1e-30), noise), "dh")
     gscale = max(float(np.abs(fx[k]).max()) for k in fx.files if k.startswith("grad.") or k.startswith("grad_sub."))
     for k, g in grads.items():
         if "grad." + k in fx:
@@ -89,4 +96,8 @@ def compare_to_fixture(fx, scores, hg, node_h, loss, grads, dh, tol, gtol):
             ref = fx["grad_sub." + k]
             got = sub(g)
         scale = max(float(np.abs(ref).max()), 5e-2 * gscale)   # near-cancelling grads: noise scales with the largest grad
-        close(got, ref, gtol * scale, "grad " + k)
+        noise = 0.0
+        if ref_noise_factor:
+            k64 = ("grad_f64." if "grad." + k in fx else "grad_sub_f64.") + k
+            noise = ref_noise_factor * float(np.abs(ref.astype(np.float64) - fx[k64]).max())
+        close(got, ref, max(gtol * scale, noise), "grad " + k)

@@ -212,7 +212,22 @@ def test_cuda_path_matches_reference_golden_at_full_baseline_size(name, graph_ki
         monkeypatch.setattr(txf, "FUSED_ENABLED", False)
     g = tx.EgonetBatch.from_counts(fx["n_gp"], fx["n_sib"])
     got = run_cuda(model, g, x, qf, int(fx["n_queries"][0]))
-    compare_to_fixture(fx, *got, tol=TOL, gtol=GTOL)
+    # outputs at 1e-5; gradients at 2e-5 or 4 x the reference's own fp32-vs-fp64 difference (leaky-relu kink flips, see _golden.py)
+    compare_to_fixture(fx, *got, tol=TOL, gtol=GTOL, ref_noise_factor=4.0)
+
+
+@pytest.mark.parametrize("backend", ["f16x3", "cublas"])
+def test_full_size_gradients_match_oracle_with_pinned_branches(backend, monkeypatch):
+    """BASELINE configs[1] at full size (8192 egonets, N = 37 319), EVERY gradient entry (not a sub-sample) against the fp32 oracle
+    made to take the same leaky-relu branches as the CUDA run (the only discontinuity of the path): 2e-5 of each tensor's maximum."""
+    monkeypatch.setattr(txf, "GEMM_BACKEND", backend)
+    cfg, og, x, qf, params, fx = load_case("pgat_wmr_lbm_magcs_full")
+    n_q = int(fx["n_queries"][0])
+    captured = capture_hidden_outputs(monkeypatch)
+    model = build_model(cfg, params).train()
+    got = run_cuda(model, tx.EgonetBatch.from_counts(fx["n_gp"], fx["n_sib"]), x, qf, n_q)
+    ref = run_oracle(cfg, og, x, qf, params, n_q, masks=branch_pins(cfg, captured))
+    assert_close(got, ref, TOL, GTOL, what=f"full size, {backend}: ")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -764,34 +779,45 @@ def test_star_forward_matches_general_fused_forward(shapes, p_drop, monkeypatch)
 
 
 # ------------------------------------------------------------------------------------------------
-# Opt-in star-specialised fused backward (tx_gat_star_bwd, functional.STAR_BWD) against the default staged backward.  Passed on a B200
-# (6 cases) when it was written; not part of the default suite because the default product path never launches the kernel.
-# Run with TAXO_STAR_BWD_TEST=1; add TAXO_STAR_BWD_COOP=24 to check the team variant (the library reads it once per process).
+# Star-specialised fused backward (tx_gat_star_bwd, the default for EgonetBatch) against the tile-staged general backward on shapes that
+# exercise every branch: > 32 grand-parents (dots spilled to scratch), 170 siblings (43 chunks combined through partial rows), roots,
+# leaves, single nodes; attention dropout on and off; the fp16-pair output with d(attn) from the weight-gradient GEMM (f16x3), the fp32
+# output with the general attention-gradient kernel (cublas backend), and the rigorous-scale second pass forced (DFT_OPTIMISM tiny).
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.skipif(__import__("os").environ.get("TAXO_STAR_BWD_TEST", "") != "1",
-                    reason="opt-in kernel: set TAXO_STAR_BWD_TEST=1 to check tx_gat_star_bwd against the staged backward")
 @pytest.mark.parametrize("shapes", [([1, 2, 0, 3], [2, 0, 0, 50]), ([40, 0, 33], [3, 170, 0]), ([0] * 5, [0, 1, 16, 17, 32])])
 @pytest.mark.parametrize("p_drop", [0.0, 0.3])
-def test_star_backward_matches_staged_backward(shapes, p_drop, monkeypatch):
+@pytest.mark.parametrize("variant", ["f16x3", "cublas", "forced_rerun"])
+def test_star_backward_matches_oracle(shapes, p_drop, variant, monkeypatch):
+    """Both fused backward kernels against the fp64 oracle (dropout masks replayed, leaky-relu branches pinned).  The star backward
+    must meet the 2e-5 gradient bar; with its second pass forced (the rigorous fp16 scale, ~2^13 - here, with 170 siblings, 2^15 -
+    above the true maximum) and for the tile-staged kernel, which only has that scale, small gradient entries lose their `lo` bits:
+    up to 3e-4 of a tensor's maximum on the 170-sibling shape (asserted at 5e-4).  That gap is why the optimistic-scale star backward is the default."""
     n_gp, n_sib = shapes
-    cfg = orc.OracleConfig(**MAGCS)
+    if variant == "cublas":
+        monkeypatch.setattr(txf, "GEMM_BACKEND", "cublas")
+    cfg = orc.OracleConfig(**dict(MAGCS, feat_drop=p_drop, attn_drop=p_drop, hidden_drop=p_drop, out_drop=p_drop))
     params = orc.init_model_params(cfg, seed=5)
     og = orc.batch_star_egonets(n_gp, n_sib)
-    x = torch.from_numpy(tx.synth.unit_rows(og.n, cfg.in_dim, seed=1)).to(dev())
-    qf = torch.from_numpy(tx.synth.unit_rows(og.num_graphs, cfg.in_dim, seed=2)).to(dev())
-    outs = {}
+    x = torch.from_numpy(tx.synth.unit_rows(og.n, cfg.in_dim, seed=1))
+    qf = torch.from_numpy(tx.synth.unit_rows(og.num_graphs, cfg.in_dim, seed=2))
+    seed = 0x2468_ACE0_1357
+    monkeypatch.setattr(txf, "new_seed", lambda: seed)
     for star in (True, False):
+        if not star and variant != "f16x3":
+            continue
+        reruns0 = int(txf.star_bwd_reruns(dev()).item())
         monkeypatch.setattr(txf, "STAR_BWD", star)
+        monkeypatch.setattr(txf, "DFT_OPTIMISM", 1e-6 if variant == "forced_rerun" else 4.0)
+        captured = capture_hidden_outputs(monkeypatch)
         model = build_model(cfg, params, p_feat=p_drop, p_attn=p_drop, p_hidden=p_drop, p_out=p_drop).train()
-        g = tx.EgonetBatch.from_counts(n_gp, n_sib)
-        h = x.clone().requires_grad_(True)
-        torch.manual_seed(1234)
-        scores = model(g, h, qf)
-        scores.sum().backward()
-        torch.cuda.synchronize()
-        outs[star] = (h.grad.clone(), {k: p.grad.clone() for k, p in model.named_parameters()})
-    a, b = outs[True], outs[False]
-    assert float((a[0] - b[0]).abs().max()) <= GTOL * float(b[0].abs().max())
-    gscale = max(float(v.abs().max()) for v in b[1].values())
-    for k in b[1]:
-        assert float((a[1][k] - b[1][k]).abs().max()) <= GTOL * max(float(b[1][k].abs().max()), 5e-2 * gscale), k
+        got = run_cuda(model, tx.EgonetBatch.from_counts(n_gp, n_sib), x, qf, 1)
+        monkeypatch.undo()
+        if variant == "cublas":
+            monkeypatch.setattr(txf, "GEMM_BACKEND", "cublas")
+        monkeypatch.setattr(txf, "new_seed", lambda: seed)
+        reruns = int(txf.star_bwd_reruns(dev()).item()) - reruns0
+        assert reruns == (2 if (variant == "forced_rerun" and star) else 0), reruns     # both layers redo their pass only when forced to
+        masks = _replay_masks(cfg, og, seed, [p_drop] * (cfg.num_layers + 1), p_drop) if p_drop > 0 else None
+        ref = run_oracle(cfg, og, x, qf, params, 1, masks=branch_pins(cfg, captured, masks), training=p_drop > 0, dtype=torch.float64)
+        loose = GTOL if (star and variant != "forced_rerun") else 5e-4
+        assert_close(got, ref, TOL, loose, what=f"star={star} {variant}: ")
