@@ -412,7 +412,7 @@ def run_b200(args, rank, world, local_rank):
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), Stats.launches, Stats.timings_ms() if profile else {}
+        return float(ms.item()), Stats.total_launches(), Stats.timings_ms() if profile else {}
 
     sampler_mode = os.environ.get("TAXO_SAMPLER", "inline")     # inline (default) | thread | off
     sampler = ClockSampler(local_rank)

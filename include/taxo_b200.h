@@ -391,6 +391,55 @@ int tx_gemm_tn_f16x3(const void* a_hi, const void* a_lo, int64_t lda, const void
                      int64_t n, int64_t r, int64_t splits, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * One call per GAT layer and direction (tx_layer.cu): the launch sequence of the default hot path - GATLayer.forward and its autograd,
+ * model/model_zoo.py:80-114 inside the stacks of :183-190,210-220, on the fp16-pair GEMMs and the star-egonet kernels above - enqueued
+ * from native code into ONE caller-owned workspace (tx_gat_layer_fwd_bytes / tx_gat_layer_bwd_bytes; 16-byte aligned; the forward
+ * workspace must stay alive until the layer's backward has run, the backward workspace until the layer below has run its backward).
+ * Same kernels, arguments and order as the per-kernel calls; nothing allocates, synchronises or reads device data on the host.
+ *   forward : ft = z W^T (z: fp32 [N, ldz], split here, or the previous layer's published fp16 pair `prev`), star forward; a hidden layer
+ *             publishes the next layer's input pair + sign/keep bytes in `state`, the output layer writes `out` [N, dim].
+ *   backward: d(pos table) of the appended rows (hidden), |dft| bounds, star backward, dW (+ 2 heads extra rows) -> dw_ext
+ *             [(heads*dim + 2*heads), round4(k)], d(attn_l | attn_r) -> dattn [2 * heads*dim], d(z)[:, dz_from8 : k] -> dz [N, round4(k)]
+ *             (dz may be NULL) with the previous layer's activation / dropout derivative applied from `prev` (NULL for the first layer);
+ *             g_amax: device bound of max|dout| or NULL (measured here); *dz_amax_out: device max|dz| for the layer below.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct tx_gat_layer_desc {
+  int64_t n, e, k, heads, dim, pos_dim, vocab, dz_from, max_out_deg;
+  int32_t hidden;                         /* 1: hidden layer (emits the next layer's input), 0: output layer (head mean, heads == 1) */
+  float neg_slope, p_attn, act_slope, p_next, dft_optimism;
+  uint64_t attn_seed, next_seed;
+  uint32_t attn_stream, next_stream;
+  const int32_t* tasks_fwd; int64_t n_tasks_fwd, chunk_fwd;     /* tx_gat_star_fwd's task table */
+  const int32_t* tasks_bwd; int64_t n_tasks_bwd, chunk_bwd;     /* tx_gat_star_bwd's task table */
+  const int32_t* pos;
+  int32_t *queue, *counters, *reruns;
+  const float* weight; int64_t ldw;       /* fc weight [heads*dim, k] */
+  const float *attn_l, *attn_r, *next_pos_table;
+  char tag[16];                           /* label of the per-launch timings (tx_prof_get) */
+} tx_gat_layer_desc;
+typedef struct tx_gat_layer_state {       /* filled by tx_gat_layer_fwd; pointers into its workspace (or the previous layer's) */
+  void *z_hi, *z_lo; float* z_scale; int64_t ldz16;
+  void *wt_hi, *wt_lo; float* w_scale; int64_t ldwt;
+  float *ft, *ft_amax, *alpha, *alpha_d, *elog;
+  void *out_hi, *out_lo; float* out_scale; int64_t ld16_out; uint32_t* maskbits;
+  int64_t heads, dim; float act_slope, p_next;
+} tx_gat_layer_state;
+int64_t tx_gat_layer_fwd_bytes(const tx_gat_layer_desc* d, int32_t split_input);
+int64_t tx_gat_layer_bwd_bytes(const tx_gat_layer_desc* d);
+int tx_gat_layer_fwd(const tx_gat_layer_desc* d, const float* z, int64_t ldz, const tx_gat_layer_state* prev, void* workspace,
+                     tx_gat_layer_state* state, float* out, void* stream);
+int tx_gat_layer_bwd(const tx_gat_layer_desc* d, const tx_gat_layer_state* state, const tx_gat_layer_state* prev, const float* dout,
+                     int64_t ldg, const float* g_amax, void* workspace, float* dz, float* dw_ext, float* dattn, float* dtab,
+                     float** dz_amax_out, void* stream);
+/* measurement aid (bench.py): kernel launches issued by the two calls above since the last reset, and optional CUDA-event timing of
+ * each of them (creates events; read after synchronising the stream) */
+int64_t tx_layer_launches(int32_t reset);
+void tx_prof_enable(int32_t on);
+void tx_prof_clear(void);
+int64_t tx_prof_count(void);
+int tx_prof_get(int64_t i, char* name64, char* tag64, float* ms);
+
+/* ------------------------------------------------------------------------------------------------
  * Matching + InfoNCE epilogue: the step right after the readout.
  * tx_match_rowdot: scores[g] = f(<u[g,:], q[g,:]>) with u = hg . W[0] (the projection half of nn.Bilinear(l, r, 1, bias=False),
  *   a GEMM of this library), f = identity for BIM (model/model_zoo.py:301-313) and exp for LBM (:316-328; apply_exp = 1).

@@ -43,6 +43,26 @@ class GemmEpilogue(Structure):
                 ("act_slope", c_float), ("p_drop", c_float), ("has_keep_plane", c_int32)]
 
 
+class GatLayerDesc(Structure):
+    """struct tx_gat_layer_desc"""
+    _fields_ = [(k, c_int64) for k in ("n", "e", "k", "heads", "dim", "pos_dim", "vocab", "dz_from", "max_out_deg")] + [
+        ("hidden", c_int32), ("neg_slope", c_float), ("p_attn", c_float), ("act_slope", c_float), ("p_next", c_float),
+        ("dft_optimism", c_float), ("attn_seed", c_uint64), ("next_seed", c_uint64), ("attn_stream", c_uint32),
+        ("next_stream", c_uint32), ("tasks_fwd", c_void_p), ("n_tasks_fwd", c_int64), ("chunk_fwd", c_int64),
+        ("tasks_bwd", c_void_p), ("n_tasks_bwd", c_int64), ("chunk_bwd", c_int64), ("pos", c_void_p), ("queue", c_void_p),
+        ("counters", c_void_p), ("reruns", c_void_p), ("weight", c_void_p), ("ldw", c_int64), ("attn_l", c_void_p),
+        ("attn_r", c_void_p), ("next_pos_table", c_void_p), ("tag", ctypes.c_char * 16)]
+
+
+class GatLayerState(Structure):
+    """struct tx_gat_layer_state"""
+    _fields_ = [("z_hi", c_void_p), ("z_lo", c_void_p), ("z_scale", c_void_p), ("ldz16", c_int64),
+                ("wt_hi", c_void_p), ("wt_lo", c_void_p), ("w_scale", c_void_p), ("ldwt", c_int64),
+                ("ft", c_void_p), ("ft_amax", c_void_p), ("alpha", c_void_p), ("alpha_d", c_void_p), ("elog", c_void_p),
+                ("out_hi", c_void_p), ("out_lo", c_void_p), ("out_scale", c_void_p), ("ld16_out", c_int64), ("maskbits", c_void_p),
+                ("heads", c_int64), ("dim", c_int64), ("act_slope", c_float), ("p_next", c_float)]
+
+
 # name -> argtypes (all return int unless listed in _RESTYPES)
 _SIGNATURES = {
     "tx_abi_version": [],
@@ -111,6 +131,16 @@ _SIGNATURES = {
     "tx_gat_star_bwd": [P, I64, I64, F32, P, I64, P, P, P, P, P, P, I64, I64, I64, I64, I64, F32, P, P, P, P, I64, P, P, I64,
                         P, P, P, P, P, P, P, P],
     "tx_attn_grad_from_v": [P, I64, P, I64, I64, I64, I64, P, P, P, P],
+    "tx_gat_layer_fwd_bytes": [POINTER(GatLayerDesc), c_int32],
+    "tx_gat_layer_bwd_bytes": [POINTER(GatLayerDesc)],
+    "tx_gat_layer_fwd": [POINTER(GatLayerDesc), P, I64, POINTER(GatLayerState), P, POINTER(GatLayerState), P, P],
+    "tx_gat_layer_bwd": [POINTER(GatLayerDesc), POINTER(GatLayerState), POINTER(GatLayerState), P, I64, P, P, P, P, P, P,
+                         POINTER(c_void_p), P],
+    "tx_layer_launches": [c_int32],
+    "tx_prof_enable": [c_int32],
+    "tx_prof_clear": [],
+    "tx_prof_count": [],
+    "tx_prof_get": [I64, ctypes.c_char_p, ctypes.c_char_p, POINTER(c_float)],
     "tx_match_rowdot_fwd": [P, I64, P, I64, I64, I64, c_int32, P, P],
     "tx_match_rowdot_bwd": [P, I64, P, I64, P, P, I64, I64, c_int32, P, I64, P, I64, P],
     "tx_info_nce_fwd": [P, I64, I64, P, P, P, P, P],
@@ -120,7 +150,8 @@ _RESTYPES = {"tx_last_error": c_char_p, "tx_target_arch": c_char_p, "tx_row_bloc
              "tx_gat_fused_mask_words": c_int64, "tx_gat_fused_mask_ld": c_int64, "tx_gat_fused_bwd_blocks": c_int64, "tx_gemm_tn_splits": c_int64,
              "tx_gat_bwd_tile_rows": c_int64, "tx_gat_bwd_num_tiles": c_int64, "tx_gat_fused_bwd_staged_blocks": c_int64,
              "tx_gemm_tn_f16_splits": c_int64, "tx_gat_star_chunk": c_int64, "tx_gat_star_max_chunks": c_int64,
-             "tx_gat_star_bwd_partial_floats": c_int64}
+             "tx_gat_star_bwd_partial_floats": c_int64, "tx_gat_layer_fwd_bytes": c_int64, "tx_gat_layer_bwd_bytes": c_int64,
+             "tx_layer_launches": c_int64, "tx_prof_count": c_int64, "tx_prof_enable": None, "tx_prof_clear": None}
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -130,7 +161,10 @@ _raw = None
 # names of ABI calls that do not enqueue GPU work
 _NO_LAUNCH = {"tx_abi_version", "tx_last_error", "tx_target_arch", "tx_row_blocks", "tx_csr_workspace_bytes",
               "tx_readout_bwd_blocks", "tx_gat_fused_supported", "tx_gat_fused_mask_words", "tx_gat_fused_mask_ld", "tx_gat_fused_bwd_blocks", "tx_gemm_tn_splits",
-              "tx_gat_bwd_tile_rows", "tx_gat_bwd_num_tiles", "tx_gat_fused_bwd_staged_blocks", "tx_gemm_tn_f16_splits", "tx_gat_star_chunk", "tx_gat_star_max_chunks", "tx_gat_star_bwd_partial_floats"}
+              "tx_gat_bwd_tile_rows", "tx_gat_bwd_num_tiles", "tx_gat_fused_bwd_staged_blocks", "tx_gemm_tn_f16_splits", "tx_gat_star_chunk", "tx_gat_star_max_chunks", "tx_gat_star_bwd_partial_floats",
+              # the per-layer calls enqueue several kernels each: they are counted through tx_layer_launches, timed through tx_prof_*
+              "tx_gat_layer_fwd_bytes", "tx_gat_layer_bwd_bytes", "tx_gat_layer_fwd", "tx_gat_layer_bwd", "tx_layer_launches",
+              "tx_prof_enable", "tx_prof_clear", "tx_prof_count", "tx_prof_get"}
 
 
 class Stats:
@@ -144,6 +178,23 @@ class Stats:
     def reset(cls):
         cls.launches = 0
         cls.events = []
+        if _lib is not None:
+            _lib.tx_layer_launches(1)
+            _lib.tx_prof_clear()
+
+    @classmethod
+    def total_launches(cls):
+        """ABI calls that enqueued kernels + the kernels enqueued inside the per-layer calls (tx_layer.cu) since the last reset."""
+        return cls.launches + (int(_lib.tx_layer_launches(0)) if _lib is not None else 0)
+
+    @classmethod
+    def sync_native_profiling(cls):
+        """Mirror `profiling` into the library (per-launch CUDA events inside the per-layer calls)."""
+        if _lib is not None and cls._native_prof != cls.profiling:
+            _lib.tx_prof_enable(1 if cls.profiling else 0)
+            cls._native_prof = cls.profiling
+
+    _native_prof = False
 
     @classmethod
     def timings_ms(cls):
@@ -151,6 +202,11 @@ class Stats:
         out = {}
         for name, tag, e0, e1 in cls.events:
             out.setdefault((name, tag), []).append(e0.elapsed_time(e1))
+        if _lib is not None:
+            nb, tb, ms = ctypes.create_string_buffer(64), ctypes.create_string_buffer(64), c_float()
+            for i in range(int(_lib.tx_prof_count())):
+                check(_lib.tx_prof_get(i, nb, tb, ctypes.byref(ms)), "tx_prof_get")
+                out.setdefault((nb.value.decode(), tb.value.decode()), []).append(float(ms.value))
         return out
 
 
@@ -215,7 +271,7 @@ def load():
         except AttributeError as e:
             raise TaxoLibraryError(f"{LIB_PATH} does not export {name}; rebuild with `python -m taxoexpan_b200.build --force`") from e
         fn.argtypes = argtypes
-        fn.restype = _RESTYPES.get(name, ctypes.c_int)
+        fn.restype = _RESTYPES[name] if name in _RESTYPES else ctypes.c_int
         setattr(ns, name, fn if name in _NO_LAUNCH else _wrap(fn, name))
     if lib.tx_abi_version() != 1:
         raise TaxoLibraryError(f"ABI version mismatch: library {lib.tx_abi_version()}, binding 1")

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtaxo_sm100.so")
-SOURCES = ["tx_general.cu", "tx_graph.cu", "tx_fused.cu", "tx_fused_bwd.cu", "tx_fused_fwd.cu", "tx_gemm.cu", "tx_match.cu", "tx_star_fwd.cu", "tx_star_bwd.cu"]
+SOURCES = ["tx_general.cu", "tx_graph.cu", "tx_fused.cu", "tx_fused_bwd.cu", "tx_fused_fwd.cu", "tx_gemm.cu", "tx_match.cu", "tx_star_fwd.cu", "tx_star_bwd.cu", "tx_layer.cu"]
 HEADERS = [os.path.join(CSRC, "tx_common.cuh"), os.path.join(ROOT, "include", "taxo_b200.h")]
 
 

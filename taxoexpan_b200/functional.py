@@ -17,7 +17,9 @@ import torch
 from torch.autograd import Function
 
 from . import _lib
-from ._lib import GatEpilogue, Stats, check, current_stream, device_guard, ptr, timed_region
+import ctypes
+
+from ._lib import GatEpilogue, GatLayerDesc, GatLayerState, Stats, check, current_stream, device_guard, ptr, timed_region
 from .graph import GraphStructure
 
 _NEG_SLOPE_NONE = 1.0
@@ -85,6 +87,10 @@ def _star_queue(device) -> torch.Tensor:
         q = _star_queues[key] = torch.zeros(32 * 64, dtype=torch.int32, device=device)
     return q
 
+
+# one C-ABI call per GAT layer and direction (tx_layer.cu: same kernels, arguments and order, one workspace) whenever the layer runs the
+# default hot path (fp16-pair GEMMs, star forward / backward on an EgonetBatch); TAXO_LAYER_CALL=0 -> one ctypes call per kernel
+LAYER_CALL = os.environ.get("TAXO_LAYER_CALL", "1") not in ("", "0")
 
 _star_counter_bufs = {}
 _star_rerun_bufs = {}
@@ -483,7 +489,7 @@ class MaskLink:
     """Hand-shake between consecutive fused GAT layers: layer l-1's forward publishes the sign/keep bytes of its epilogue,
     layer l's backward applies their derivative inside its d(z) GEMM epilogue and flags it, so layer l-1's backward kernel
     reads d(z) as is (no per-load decode)."""
-    __slots__ = ("mask", "heads", "dim", "act_slope", "p_drop", "applied", "z_lo", "z16", "dz_amax")
+    __slots__ = ("mask", "heads", "dim", "act_slope", "p_drop", "applied", "z_lo", "z16", "dz_amax", "c_state", "c_ws", "c_dims", "c_bwd")
 
     def __init__(self):
         self.mask = None
@@ -491,6 +497,25 @@ class MaskLink:
         self.z_lo = None      # TF32 "lo" part of the published z when the producer wrote z pre-split (z itself is then the "hi" part)
         self.z16 = None       # F16Pair of the published z when the producer wrote it fp16-split (z itself is then never written)
         self.dz_amax = None   # device scalar max|d(z)| published by the consumer layer's backward GEMM epilogue
+        self.c_state = None   # tx_gat_layer_state of a producer that ran through tx_gat_layer_fwd (pointers into c_ws)
+        self.c_ws = None
+        self.c_dims = None    # (n, cols, ld16, mask words) of the published pair / mask
+        self.c_bwd = None     # (device pointer of max|d(z)|, backward workspace keeping it alive) published by a native consumer
+
+    def materialize(self):
+        """Tensor views (z16, mask) of what a native producer published, for a consumer on the per-kernel path."""
+        if self.c_state is None or self.z16 is not None:
+            return
+        n, cols, ld16, words = self.c_dims
+        ws, s_ = self.c_ws, self.c_state
+        base = ws.data_ptr()
+
+        def view(p, nbytes, dtype):
+            return ws[p - base:p - base + nbytes].view(dtype)
+        self.z16 = F16Pair(view(s_.out_hi, n * ld16 * 2, torch.float16).view(n, ld16), view(s_.out_lo, n * ld16 * 2, torch.float16).view(n, ld16),
+                           view(s_.out_scale, 4, torch.float32), cols)
+        if s_.maskbits:
+            self.mask = view(s_.maskbits, words * 4, torch.int32)
 
 
 @dataclass
@@ -513,6 +538,52 @@ class GatLayerCfg:
     out_link: Optional[MaskLink] = None   # published to the next layer
 
 
+def _native_layer_ok(lib, z, weight, attn_l, attn_r, next_pos_table, st, cfg, n) -> bool:
+    """The layer runs the default hot path end to end: one native call per direction (tx_gat_layer_fwd / _bwd)."""
+    if not (LAYER_CALL and GEMM_BACKEND == "f16x3" and FUSE_SPLIT and FUSE_DZ_EPILOGUE and STAR_FWD and STAR_BWD and STAGED_BWD
+            and FUSED_ENABLED and not STAGED_FWD and n > 0):
+        return False
+    if st.star is None or st.star_bwd is None or cfg.heads > 64 or not use_fused(lib, cfg.heads, cfg.dim, 0 if cfg.hidden else 1, st):
+        return False
+    if cfg.hidden and cfg.out_link is None:
+        return False
+    if not cfg.hidden and not STAR_FWD_OUTPUT_LAYER:
+        return False
+    if weight.shape[1] != cfg.k or not weight.is_contiguous() or not attn_l.is_contiguous() or not attn_r.is_contiguous():
+        return False
+    if next_pos_table is not None and not next_pos_table.is_contiguous():
+        return False
+    if cfg.in_link is not None and cfg.in_link.c_state is None:
+        return False                                    # the layer below published tensors, not a native state
+    if cfg.in_link is None and (z.stride(1) != 1 or z.stride(0) % 4 != 0 or z.data_ptr() % 16 != 0):
+        return False
+    return True
+
+
+def _native_desc(lib, st, cfg, n, weight, attn_l, attn_r, next_pos_table, pos32, dev):
+    H, D = cfg.heads, cfg.dim
+    d = GatLayerDesc()
+    d.n, d.e, d.k, d.heads, d.dim = n, st.e, cfg.k, H, D
+    pd = 0 if (next_pos_table is None or not cfg.hidden) else int(next_pos_table.shape[1])
+    d.pos_dim, d.vocab = pd, (0 if pd == 0 else int(next_pos_table.shape[0]))
+    d.dz_from, d.max_out_deg, d.hidden = cfg.dz_from, max(int(st.max_out_deg), 1), 1 if cfg.hidden else 0
+    d.neg_slope, d.p_attn, d.act_slope = cfg.neg_slope, cfg.p_attn, cfg.act_slope
+    d.p_next, d.dft_optimism = (cfg.p_next if cfg.hidden else 0.0), DFT_OPTIMISM
+    d.attn_seed, d.next_seed, d.attn_stream, d.next_stream = cfg.attn_seed, cfg.next_seed, cfg.attn_stream, cfg.next_stream
+    sf, sb = st.star, st.star_bwd
+    d.tasks_fwd, d.n_tasks_fwd, d.chunk_fwd = sf[0].data_ptr(), sf[1], sf[2]
+    d.tasks_bwd, d.n_tasks_bwd, d.chunk_bwd = sb[0].data_ptr(), sb[1], sb[2]
+    d.pos = None if pd == 0 else pos32.data_ptr()
+    d.queue = _star_queue(dev).data_ptr()
+    d.counters = _star_counters(dev, sb[1] * H).data_ptr()
+    d.reruns = star_bwd_reruns(dev).data_ptr()
+    d.weight, d.ldw = weight.data_ptr(), weight.stride(0)
+    d.attn_l, d.attn_r = attn_l.data_ptr(), attn_r.data_ptr()
+    d.next_pos_table = None if pd == 0 else next_pos_table.data_ptr()
+    d.tag = cfg.tag.encode()[:15]
+    return d, pd
+
+
 class GatLayer(Function):
     @staticmethod
     def forward(ctx, z, weight, attn_l, attn_r, next_pos_table, st: GraphStructure, pos32, cfg: GatLayerCfg):
@@ -523,6 +594,36 @@ class GatLayer(Function):
         F_ = H * D
         dev = z.device
         f32 = dict(dtype=torch.float32, device=dev)
+        ctx.native = None
+        if _native_layer_ok(lib, z, weight, attn_l, attn_r, next_pos_table, st, cfg, n):
+            # ---- one native call: split / GEMM / bound / star forward into one workspace (tx_layer.cu) ----
+            with device_guard(dev):
+                Stats.sync_native_profiling()
+                desc, pd = _native_desc(lib, st, cfg, n, weight, attn_l, attn_r, next_pos_table, pos32, dev)
+                prev = None if cfg.in_link is None else cfg.in_link.c_state
+                ws = torch.empty(int(lib.tx_gat_layer_fwd_bytes(ctypes.byref(desc), 1 if prev is None else 0)), dtype=torch.uint8, device=dev)
+                state = GatLayerState()
+                out = torch.empty((n, round4(F_ + pd)) if cfg.hidden else (n, D), **f32)     # hidden: a placeholder, never written
+                check(lib.tx_gat_layer_fwd(ctypes.byref(desc), ptr(z) if prev is None else None, ldz,
+                                           None if prev is None else ctypes.byref(prev), ptr(ws), ctypes.byref(state),
+                                           None if cfg.hidden else ptr(out), current_stream()), "tx_gat_layer_fwd")
+            if cfg.out_link is not None:
+                lk = cfg.out_link
+                lk.c_state, lk.c_ws, lk.applied, lk.z16, lk.z_lo, lk.dz_amax, lk.c_bwd = state, ws, False, None, None, None, None
+                lk.c_dims = (n, F_ + pd, round8(F_ + pd), int(lib.tx_gat_fused_mask_words(n, H, D)))
+                lk.mask = None
+                if state.maskbits:
+                    lk.heads, lk.dim, lk.act_slope, lk.p_drop = H, D, cfg.act_slope, cfg.p_next
+            ctx.native = (desc, state, ws, pd)
+            ctx.fused, ctx.maskbits = True, None
+            ctx.st, ctx.cfg, ctx.pd = st, cfg, pd
+            ctx.vocab = 0 if next_pos_table is None else int(next_pos_table.shape[0])
+            ctx.save_for_backward(weight, attn_l, attn_r, next_pos_table, pos32, z if prev is None else None)
+            ctx.attn_shape = attn_l.shape
+            ctx.zshape = tuple(z.shape)
+            return out
+        if cfg.in_link is not None:
+            cfg.in_link.materialize()
         with device_guard(dev):
             stream = current_stream()
             Stats.tag = cfg.tag
@@ -625,9 +726,93 @@ class GatLayer(Function):
         return out
 
     @staticmethod
+    def _native_saved(ctx):
+        """The per-kernel backward's saved tensors as views of a native forward's workspace (rare fall-back: frozen weights, a
+        consumer that did not apply the activation / dropout derivative)."""
+        desc, state, ws, pd = ctx.native
+        weight, attn_l, attn_r, tab, pos32, _ = ctx.saved_tensors
+        cfg, st = ctx.cfg, ctx.st
+        n = ctx.zshape[0]
+        H, D, K = cfg.heads, cfg.dim, cfg.k
+        F_ = H * D
+
+        def view(src, p, count, dtype):
+            nb = count * torch.empty((), dtype=dtype).element_size()
+            off = p - src.data_ptr()
+            return src[off:off + nb].view(dtype)
+        if cfg.in_link is None:
+            zsrc, ldz16 = ws, round8(K)
+        else:
+            zsrc, ldz16 = cfg.in_link.c_ws, int(state.ldz16)
+        z_hi = view(zsrc, state.z_hi, n * ldz16, torch.float16).view(n, ldz16)
+        z_lo = view(zsrc, state.z_lo, n * ldz16, torch.float16).view(n, ldz16)
+        z_scale = view(zsrc, state.z_scale, 1, torch.float32)
+        ldwt = int(state.ldwt)
+        wt_hi = view(ws, state.wt_hi, K * ldwt, torch.float16).view(K, ldwt)
+        wt_lo = view(ws, state.wt_lo, K * ldwt, torch.float16).view(K, ldwt)
+        w_scale = view(ws, state.w_scale, 1, torch.float32)
+        ft = view(ws, state.ft, n * F_, torch.float32).view(n, F_)
+        ft_amax = view(ws, state.ft_amax, 1, torch.float32)
+        alpha = view(ws, state.alpha, st.e * H, torch.float32)
+        elog = view(ws, state.elog, st.e * H, torch.float32)
+        alpha_d = view(ws, state.alpha_d, st.e * H, torch.float32)
+        if state.maskbits:
+            ctx.maskbits = view(ws, state.maskbits, int(_lib.load().tx_gat_fused_mask_words(n, H, D)), torch.int32)
+        return (z_hi, z_lo, weight, attn_l.reshape(-1), attn_r.reshape(-1), ft, alpha, alpha_d, elog, None, pos32, z_scale, ft_amax,
+                wt_hi, wt_lo, w_scale)
+
+    @staticmethod
     def backward(ctx, dout):
         lib = _lib.load()
-        z0, z1, weight, al, ar, ft, alpha, alpha_d, elog, out, pos32, z_scale, ft_amax, wt_hi, wt_lo, wt_scale = ctx.saved_tensors
+        if ctx.native is not None:
+            desc, state, ws, pd = ctx.native
+            cfg, st = ctx.cfg, ctx.st
+            lk_out = cfg.out_link
+            pre = lk_out is not None and lk_out.applied
+            if ctx.needs_input_grad[1] and (pre or not state.maskbits) and dout.dim() == 2:
+                # ---- one native call: bounds / star backward / dW (+ attention rows) / d(attn) / d(z) (tx_layer.cu) ----
+                weight, attn_l, attn_r, tab, pos32, z_in = ctx.saved_tensors
+                n, ldz = ctx.zshape
+                H, D, K = cfg.heads, cfg.dim, cfg.k
+                F_ = H * D
+                dev = dout.device
+                f32 = dict(dtype=torch.float32, device=dev)
+                with device_guard(dev):
+                    Stats.sync_native_profiling()
+                    dout = _rowmajor(dout)
+                    ldg = dout.stride(0) if n > 1 else dout.shape[1]
+                    need_tab = cfg.hidden and ctx.needs_input_grad[4] and pd > 0
+                    need_z = ctx.needs_input_grad[0]
+                    g_amax = None
+                    hand = st._dh_bound
+                    st._dh_bound = None
+                    if lk_out is not None and lk_out.c_bwd is not None and pre:
+                        g_amax = lk_out.c_bwd[0]                            # max|d(z_next)|, measured by the layer above's d(z) GEMM
+                    elif lk_out is not None and lk_out.dz_amax is not None and pre:
+                        g_amax = lk_out.dz_amax.data_ptr()
+                    elif not cfg.hidden and hand is not None and hand[0] == dout.data_ptr():
+                        g_amax = hand[1].data_ptr()                         # published by the readout's backward
+                    bws = torch.empty(int(lib.tx_gat_layer_bwd_bytes(ctypes.byref(desc))), dtype=torch.uint8, device=dev)
+                    ldc = round4(K)
+                    dw_ext = torch.empty((F_ + 2 * H, ldc), **f32)
+                    both = torch.empty(2 * F_, **f32)
+                    dz = torch.empty((n, ldz), **f32) if need_z else None
+                    dtab = torch.empty((ctx.vocab, pd), **f32) if need_tab else None
+                    dz_amax = ctypes.c_void_p()
+                    prev = None if cfg.in_link is None else cfg.in_link.c_state
+                    check(lib.tx_gat_layer_bwd(ctypes.byref(desc), ctypes.byref(state), None if prev is None else ctypes.byref(prev),
+                                               ptr(dout), ldg, g_amax, ptr(bws), ptr(dz), ptr(dw_ext), ptr(both), ptr(dtab),
+                                               ctypes.byref(dz_amax), current_stream()), "tx_gat_layer_bwd")
+                    if cfg.in_link is not None and need_z:
+                        cfg.in_link.c_bwd = (dz_amax.value, bws)
+                        cfg.in_link.applied = bool(prev is not None and prev.maskbits)
+                        cfg.in_link.dz_amax = None
+                dw = dw_ext[:F_, :K]
+                return dz, dw, both[:F_].view(ctx.attn_shape), both[F_:].view(ctx.attn_shape), dtab, None, None, None
+            saved = GatLayer._native_saved(ctx)
+        else:
+            saved = ctx.saved_tensors
+        z0, z1, weight, al, ar, ft, alpha, alpha_d, elog, out, pos32, z_scale, ft_amax, wt_hi, wt_lo, wt_scale = saved
         st, cfg, pd = ctx.st, ctx.cfg, ctx.pd
         n, ldz = ctx.zshape
         H, D, K = cfg.heads, cfg.dim, cfg.k

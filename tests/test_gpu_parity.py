@@ -63,6 +63,8 @@ def capture_hidden_outputs(monkeypatch):
         def wrapped(*a, _orig=orig):
             out = _orig(*a)
             link = getattr(a[-1], "out_link", None)
+            if link is not None:
+                link.materialize()           # a layer that ran through tx_gat_layer_fwd publishes pointers; make them tensors
             z16 = getattr(link, "z16", None) if link is not None else None
             if z16 is not None:      # f16x3 backend: the hidden layer's output exists only as the next GEMM's fp16 hi/lo operand pair
                 captured.append(((z16.hi.double() + z16.lo.double()) / z16.scale.double()).float()[:, :out.shape[1]])
@@ -541,6 +543,33 @@ def test_standalone_layers_follow_reference_signatures():
     out = gl(g, x.to(dev()))
     ref = orc.gcn_layer(og, x, gl.weight.detach().cpu(), gl.bias.detach().cpu(), orc.gcn_norm(og, torch.float32), F.leaky_relu)
     assert out.shape == (og.n, 8) and float((out.detach().cpu() - ref).abs().max()) <= TOL
+
+
+@pytest.mark.parametrize("cfg_kw,p_drop", [(MAGCS, 0.1), (MAGCS, 0.0), (dict(MAGCS, in_dim=512, hidden_dim=512, out_dim=512, pos_dim=64,
+                                                                             num_layers=2, heads=[4, 4, 1]), 0.1),
+                                           (dict(MAGCS, num_layers=2, heads=[2, 3, 2]), 0.1)])
+def test_native_layer_calls_are_bit_identical_to_the_per_kernel_path(cfg_kw, p_drop, monkeypatch):
+    """tx_gat_layer_fwd / tx_gat_layer_bwd (one call per layer and direction, one workspace) enqueue the same kernels with the same
+    arguments in the same order as the per-kernel ctypes path: every output and gradient must be BIT-identical (dropout on; the last
+    case ends in a two-head output layer that falls back to the per-kernel path behind two native hidden layers)."""
+    cfg = orc.OracleConfig(**dict(cfg_kw, feat_drop=p_drop, attn_drop=p_drop, hidden_drop=p_drop, out_drop=p_drop))
+    n_q = 8
+    shapes = tx.synth.sample_shapes(n_q, 31, "mag-cs", seed=23)
+    og = orc.batch_star_egonets(shapes.n_gp, shapes.n_sib)
+    x = torch.from_numpy(tx.synth.unit_rows(og.n, cfg.in_dim, seed=1))
+    qf = torch.from_numpy(tx.synth.unit_rows(og.num_graphs, cfg.in_dim, seed=2))
+    params = orc.init_model_params(cfg, seed=3)
+    monkeypatch.setattr(txf, "new_seed", lambda: 0x0BAD_5EED_1234)
+    outs = []
+    for native in (True, False):
+        monkeypatch.setattr(txf, "LAYER_CALL", native)
+        model = build_model(cfg, params, p_drop, p_drop, p_drop, p_drop).train()
+        outs.append(run_cuda(model, tx.EgonetBatch.from_counts(shapes.n_gp, shapes.n_sib), x, qf, n_q))
+    a, b = outs
+    for i in (0, 1, 2, 3, 5):
+        assert np.array_equal(a[i], b[i]), i
+    for k in a[4]:
+        assert np.array_equal(a[4][k], b[4][k]), k
 
 
 # ------------------------------------------------------------------------------------------------
