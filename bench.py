@@ -35,6 +35,18 @@ MAGCS = dict(in_dim=250, hidden_dim=500, out_dim=500, pos_dim=50, num_layers=1, 
 NEGATIVE_SIZE = 31                                                              # config.mag.json:30
 
 
+def csrc_sha16():
+    """hash of the CUDA sources the library is built from (ties profiles/traffic.json to the kernels it was measured on)"""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "taxoexpan_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh")):
+            with open(os.path.join(d, name), "rb") as f:
+                h.update(name.encode() + b"\0" + f.read())
+    return h.hexdigest()[:16]
+
+
 def load_peaks():
     """(HBM GB/s, bf16 TFLOP/s, source).  MEASURED_PEAKS.json is written by the driver; its key names are not part of any contract
     here, so any numeric entry whose key mentions hbm / bandwidth (resp. bf16 / tflop) is accepted, nested dicts included."""
@@ -210,29 +222,86 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference path on the host cores
+# CPU arm: the reference path on the host cores.  kind "reference" = the UNMODIFIED reference model code (model/model.py, model_zoo.py,
+# loss.py byte-compiled into oracle/_ref by oracle/build_ref.py) through oracle/dgl_shim (DGL 0.4.0 is not installable offline);
+# kind "port" = the oracle restatement (oracle/taxo_oracle.py), used when oracle/_ref has not been built.
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(n_queries, steps, warmup, seed=20200420):
-    from oracle import taxo_oracle as orc
+WORKLOAD = "configs[1]: MAG-CS PGAT+WMR+LBM, d=250, 2-hop egonets, batch=256 queries x 32 = 8192 egonets per GPU"
+
+
+WORDNET = dict(in_dim=300, hidden_dim=600, out_dim=300, pos_dim=50, num_layers=1, heads=[4, 1],
+               feat_drop=0.1, attn_drop=0.1, hidden_drop=0.1, out_drop=0.1)     # config_files/config.wordnet.json:11-20
+ARCHS = {"mag-cs": ("PGAT", "WMR", "LBM", MAGCS), "wordnet": ("PGCN", "MR", "BIM", WORDNET)}     # BASELINE configs[1] / configs[0]
+
+
+def _cpu_batches(n_queries, n_batches, rank=0, shape_model="mag-cs"):
     from taxoexpan_b200 import synth
+    d = ARCHS[shape_model][3]["in_dim"]
+    out = []
+    for b in range(n_batches):
+        shapes = synth.sample_shapes(n_queries, NEGATIVE_SIZE, shape_model, seed=20200420 + 1000 * rank + b)   # = the B200 arm's batches
+        x = torch.from_numpy(synth.unit_rows(shapes.total_nodes, d, seed=11 + 1000 * rank + b))
+        qf = torch.from_numpy(synth.unit_rows(shapes.num_graphs, d, seed=13 + 1000 * rank + b))
+        out.append((shapes, x, qf))
+    return out
+
+
+def cpu_reference_run(n_queries, steps, warmup, n_batches=1, kind=None, arch="mag-cs"):
+    """fwd + InfoNCE + bwd (dropout 0.1 active, no optimizer, no batch construction in the timed region: BASELINE.md section 4) of the
+    MAG-CS config on all host cores.  Returns egonets/s over `steps` steps rotating over `n_batches` seeded batches."""
+    from oracle import build_ref
+    from oracle import taxo_oracle as orc
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = orc.OracleConfig(propagation_method="PGAT", readout_method="WMR", matching_method="LBM",
-                           **{k: v for k, v in MAGCS.items()})
-    shapes = synth.sample_shapes(n_queries, NEGATIVE_SIZE, "mag-cs", seed=seed)
-    og = orc.batch_star_egonets(shapes.n_gp, shapes.n_sib)
-    x = torch.from_numpy(synth.unit_rows(og.n, cfg.in_dim, seed=1))
-    qf = torch.from_numpy(synth.unit_rows(og.num_graphs, cfg.in_dim, seed=2))
-    params = {k: v.clone().requires_grad_(True) for k, v in orc.init_model_params(cfg, seed=3).items()}
+    if kind is None:
+        kind = "reference" if build_ref.available() else "port"
+    data = _cpu_batches(n_queries, n_batches, shape_model=arch)
+    pm, rm, mm, dims = ARCHS[arch]
+    torch.manual_seed(0)
+    if kind == "reference":
+        TaxoExpan, info_nce_loss, dgl = build_ref.import_reference()
+        model = TaxoExpan(pm, rm, mm, **dims)
+        model.train()
+        graphs = []
+        for shapes, x, qf in data:
+            gs, off = [], 0
+            for a, s_ in zip(shapes.n_gp.tolist(), shapes.n_sib.tolist()):       # data_loader/dataset.py:429-435, one DGLGraph per egonet
+                n = a + 1 + s_
+                gr = dgl.DGLGraph()
+                gr.add_nodes(n, {"x": x[off:off + n], "_id": torch.arange(off, off + n), "pos": torch.tensor([0] * a + [1] + [2] * s_)})
+                gr.add_edges(list(range(a)), a)
+                gr.add_edges(a, list(range(a + 1, n)))
+                gr.add_edges(gr.nodes(), gr.nodes())
+                gs.append(gr)
+                off += n
+            bg = dgl.batch(gs)                                                    # data_loader/data_loaders.py:25
+            graphs.append((bg, bg.ndata.pop("x"), bg.ndata["pos"].clone(), qf))
+        target = torch.zeros(n_queries, dtype=torch.long)
 
-    def step(i):
-        for p in params.values():
-            p.grad = None
-        masks = orc.random_keep_masks(cfg, og, seed=i)           # nn.Dropout's bernoulli is part of the reference step
-        scores, _, _ = orc.taxoexpan_forward(cfg, og, x, qf, params, masks=masks, training=True)
-        loss = orc.info_nce_step_loss(scores, n_queries)
-        loss.backward()
-        return float(loss.detach())
+        def step(i):
+            bg, h, pos, qf = graphs[i % len(graphs)]
+            bg.ndata["pos"] = pos                                                 # PGAT.forward pops it (model_zoo.py:212)
+            model.zero_grad()
+            scores = model(bg, h, qf)                                             # trainer/trainer.py:51
+            loss = info_nce_loss(scores.reshape(n_queries, -1), target)           # trainer.py:52-56, model/loss.py:52-57
+            loss.backward()                                                       # trainer.py:60
+            return float(loss.detach())
+        sizes = [(int(bg.number_of_nodes()), int(bg._src.numel())) for bg, _, _, _ in graphs]
+    else:
+        cfg = orc.OracleConfig(propagation_method=pm, readout_method=rm, matching_method=mm, **{k: v for k, v in dims.items()})
+        ogs = [(orc.batch_star_egonets(sh.n_gp, sh.n_sib), x, qf) for sh, x, qf in data]
+        params = {k: v.clone().requires_grad_(True) for k, v in orc.init_model_params(cfg, seed=3).items()}
+
+        def step(i):
+            og, x, qf = ogs[i % len(ogs)]
+            for p in params.values():
+                p.grad = None
+            masks = orc.random_keep_masks(cfg, og, seed=i)           # nn.Dropout's bernoulli is part of the reference step
+            scores, _, _ = orc.taxoexpan_forward(cfg, og, x, qf, params, masks=masks, training=True)
+            loss = orc.info_nce_step_loss(scores, n_queries)
+            loss.backward()
+            return float(loss.detach())
+        sizes = [(og.n, int(og.src.numel())) for og, _, _ in ogs]
 
     for i in range(warmup):
         step(i)
@@ -240,26 +309,201 @@ def cpu_reference_run(n_queries, steps, warmup, seed=20200420):
     for i in range(steps):
         step(warmup + i)
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    g = og.num_graphs
-    return {"value": g / dt, "ms_per_step": dt * 1e3, "cores": cores, "egonets": g, "nodes": og.n, "edges": int(og.src.numel())}
+    g = data[0][0].num_graphs
+    return {"value": g / dt, "ms_per_step": dt * 1e3, "cores": cores, "egonets": g, "nodes": int(np.mean([s_[0] for s_ in sizes])),
+            "edges": int(np.mean([s_[1] for s_ in sizes])), "kind": kind}
+
+
+def _cpu_sample_text(r, nq, n_batches):
+    what = ("the UNMODIFIED reference model/model.py + model_zoo.py + loss.py (byte-compiled, oracle/_ref) on torch-CPU through oracle/dgl_shim"
+            if r["kind"] == "reference" else "torch-CPU port (oracle/taxo_oracle.py) of reference model_zoo.py PGAT/WMR/LBM + InfoNCE")
+    return (f"{nq} queries x {1 + NEGATIVE_SIZE} = {r['egonets']} egonets ({r['nodes']} nodes) per step, {n_batches} rotating batch(es) of the "
+            f"MAG-CS config, TaxoExpan.forward + info_nce_loss + backward, dropout 0.1 active, {r['cores']} host threads: {what} "
+            "(real DGL 0.4.0 is not installable offline)")
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    nq = 32
-    r = cpu_reference_run(nq, args.steps, args.warmup)
-    sample = (f"{nq} queries x {1 + NEGATIVE_SIZE} = {r['egonets']} egonets ({r['nodes']} nodes) per step of the MAG-CS config, "
-              "fwd+InfoNCE+bwd, dropout 0.1 active, torch-CPU port of model_zoo.py PGAT/WMR/LBM (DGL 0.4.0 not installable offline)")
+    nq, nb = args.queries, args.batches
+    r = cpu_reference_run(nq, args.steps, args.warmup, n_batches=nb)
+    port = cpu_reference_run(32, 4, 1, kind="port") if r["kind"] == "reference" else None
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: MAG-CS PGAT+WMR+LBM d=250 2-hop egonets (bounded CPU sample)", "egonets_per_step": r["egonets"],
-                       "nodes": r["nodes"], "edges": r["edges"]},
-            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
+            "config": {"workload": WORKLOAD, "egonets_per_gpu_step": r["egonets"], "nodes_per_gpu_step": r["nodes"],
+                       "edges_per_gpu_step": r["edges"], "dropout": 0.1, "parallelism": "host cores (one process)"},
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": _cpu_sample_text(r, nq, nb)},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if port is not None:
+        line["cpu_port"] = {"value": port["value"], "unit": UNIT, "cores": port["cores"], "kind": "port",
+                            "sample": _cpu_sample_text(port, 32, 1)}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# Side legs (never the headline): the other BASELINE.json configs on one GPU, each a few seconds.
+# ------------------------------------------------------------------------------------------------
+def _event_ms(fn, steps, warmup=3):
+    for i in range(warmup):
+        fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def leg_pgcn_wordnet(dev, hbm_peak, with_cpu):
+    """configs[0]: SemEval-Noun PGCN+MR(+BIM), d=300, batch=32 queries x 32 = 1024 egonets, fwd + InfoNCE + bwd; CPU arm beside it."""
+    import taxoexpan_b200 as tx
+    from taxoexpan_b200 import synth
+    from taxoexpan_b200._lib import Stats
+    pm, rm, mm, dims = ARCHS["wordnet"]
+    nq = 32
+    torch.manual_seed(0)
+    model = tx.TaxoExpan(pm, rm, mm, **dims).to(dev).train()
+    data = []
+    for b in range(4):
+        sh = synth.sample_shapes(nq, NEGATIVE_SIZE, "wordnet", seed=20200420 + b)
+        data.append((sh, torch.from_numpy(synth.unit_rows(sh.total_nodes, dims["in_dim"], seed=11 + b)).to(dev),
+                     torch.from_numpy(synth.unit_rows(sh.num_graphs, dims["in_dim"], seed=13 + b)).to(dev)))
+
+    def step(i):
+        sh, x, qf = data[i % 4]
+        model.zero_grad(set_to_none=True)
+        g = tx.EgonetBatch.from_counts(sh.n_gp, sh.n_sib)
+        loss = tx.info_nce_loss(model(g, x, qf).reshape(nq, -1), None)
+        loss.backward()
+    ms = _event_ms(step, 30, 5)
+    Stats.reset()
+    Stats.profiling = True
+    for i in range(8):
+        step(i)
+    torch.cuda.synchronize()
+    Stats.profiling = False
+    prof = Stats.timings_ms()
+    n = float(np.mean([d[0].total_nodes for d in data]))
+    e = float(np.mean([d[0].total_edges for d in data]))
+    kern, rl = {}, []
+    for (name, tag), v in sorted(prof.items()):
+        kern[f"{name}[{tag}]"] = round(float(np.sum(v)) / 8, 4)
+    # GCN aggregate (model_zoo.py:39-47): fwd reads y once, writes out once (+ norm, CSR); bwd reads g once, writes dy once
+    for tag, w in (("L0", dims["hidden_dim"]), ("L1", dims["out_dim"])):
+        for nm in ("tx_gcn_aggregate_fwd", "tx_gcn_aggregate_bwd"):
+            t = float(np.mean(prof.get((nm, tag), [0.0])))
+            if t > 0:
+                by = 4 * (2 * n * w + n) + 4 * (n + 1 + e)
+                rl.append({"kernel": f"{nm}[{tag}]", "ms": round(t, 4), "bytes": int(by), "achieved": round(by / t / 1e6, 1),
+                           "frac": round(by / t / 1e6 / hbm_peak, 4)})
+    out = {"workload": "configs[0]: SemEval-Noun PGCN+MR+BIM, d=300, 2-hop egonets, batch=32 queries x 32 = 1024 egonets",
+           "egonets_per_step": nq * 32, "nodes_per_step": int(n), "ms_per_step": round(ms, 4), "egonets_per_s": round(nq * 32 / ms * 1e3, 1),
+           "kernel_ms_per_step": kern, "roofline_gcn_aggregate": rl,
+           "note": "4.5 k nodes per step: every kernel of this config is launch-latency bound (a few us each), not bandwidth bound"}
+    if with_cpu:
+        r = cpu_reference_run(nq, 10, 2, n_batches=1, arch="wordnet")
+        out["cpu_baseline"] = {"value": round(r["value"], 1), "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                               "sample": f"the same config, {r['egonets']} egonets ({r['nodes']} nodes) per step x 10 steps on the host cores"}
+    return out
+
+
+def leg_inference(dev):
+    """configs[3]: MAG-Full-shaped inference (test_fast.py:149-225, --batch_size 30000): forward-only encode of 30 000-egonet chunks,
+    then all-pairs scoring + ranking of 2048 queries against the encoded positions."""
+    import taxoexpan_b200 as tx
+    from taxoexpan_b200 import synth
+    torch.manual_seed(0)
+    model = tx.TaxoExpan("PGAT", "WMR", "LBM", **MAGCS).to(dev).eval()
+    name = "mag-full" if "mag-full" in synth.SHAPE_MODELS else "mag-cs"
+    chunks = []
+    for c in range(3):
+        sh = synth.sample_shapes(30000, 0, name, seed=100 + c, positives=False)
+        chunks.append((sh, torch.from_numpy(synth.unit_rows(sh.total_nodes, 250, seed=200 + c)).to(dev)))
+    G = sum(sh.num_graphs for sh, _ in chunks)
+    N = sum(sh.total_nodes for sh, _ in chunks)
+    hold = {}
+
+    def encode(i):
+        hold["hg"] = tx.inference.encode_positions(model, ((tx.EgonetBatch.from_counts(sh.n_gp, sh.n_sib), x) for sh, x in chunks))
+    ms = _event_ms(encode, 5, 2)
+    hg = hold["hg"]
+    Q = 2048
+    queries = torch.from_numpy(synth.unit_rows(Q, 250, seed=7)).to(dev)
+    rng = np.random.default_rng(0)
+    positives = [rng.choice(hg.shape[0], size=2, replace=False).tolist() for _ in range(Q)]
+    tx.inference.score_and_rank(model, hg, queries[:256], positives[:256])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = tx.inference.score_and_rank(model, hg, queries, positives)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {"workload": f"configs[3]: {name}-shaped inference, PGAT+WMR+LBM forward-only, chunks of 30000 egonets (test_fast.py:160)",
+            "encode": {"egonets": G, "nodes": N, "ms": round(ms, 3), "egonets_per_s": round(G / ms * 1e3, 1),
+                       "includes": "host construction of each EgonetBatch + its structure kernel + propagate + readout"},
+            "score_and_rank": {"queries": Q, "positions": int(hg.shape[0]), "ms": round(dt * 1e3, 2),
+                               "pairs_per_s": round(Q * hg.shape[0] / dt, 1), "macro_mr": round(tx.inference.macro_mr(res["ranks"]), 1),
+                               "includes": "U = hg W, one NT GEMM per 256-query chunk, on-GPU ranks + top-5, D2H of the results (wall clock)"}}
+
+
+def leg_d512_sweep(dev, hbm_peak):
+    """configs[4] on one GPU: d = 512, three propagation layers (num_layers = 2, heads [4, 4, 1], pos_dim 64; SURVEY 8d "config 5"),
+    fwd + bwd over G = 2^13 .. 2^16 egonets per step (TAXO_SWEEP_MAX_LOG2 raises the cap), plus the general-CSR stress variant: one
+    power-law graph (in-degrees up to 10^4) through a 2-layer GAT on the general kernels."""
+    import taxoexpan_b200 as tx
+    from taxoexpan_b200 import synth
+    dims = dict(in_dim=512, hidden_dim=512, out_dim=512, pos_dim=64, num_layers=2, heads=[4, 4, 1], feat_drop=0.1, attn_drop=0.1,
+                hidden_drop=0.1, out_drop=0.1)
+    torch.manual_seed(0)
+    model = tx.TaxoExpan("PGAT", "WMR", "LBM", **dims).to(dev).train()
+    rows = []
+    top = int(os.environ.get("TAXO_SWEEP_MAX_LOG2", "16"))
+    for lg in range(13, top + 1):
+        G = 1 << lg
+        nq = G // 32
+        sh = synth.sample_shapes(nq, NEGATIVE_SIZE, "mag-cs", seed=500 + lg)
+        x = torch.from_numpy(synth.unit_rows(sh.total_nodes, 512, seed=600 + lg)).to(dev)
+        qf = torch.from_numpy(synth.unit_rows(sh.num_graphs, 512, seed=700 + lg)).to(dev)
+
+        def step(i):
+            model.zero_grad(set_to_none=True)
+            g = tx.EgonetBatch.from_counts(sh.n_gp, sh.n_sib)
+            tx.info_nce_loss(model(g, x, qf).reshape(nq, -1), None).backward()
+        ms = _event_ms(step, 6 if lg >= 15 else 12, 3)
+        n, e = sh.total_nodes, sh.total_edges
+        gaa = sum(gaa_fwd_bytes(n, e, h, 512 * h) + gaa_bwd_bytes(n, e, h, 512 * h) for h in (4, 4, 1))
+        rows.append({"egonets": G, "nodes": n, "ms_per_step": round(ms, 3), "egonets_per_s": round(G / ms * 1e3, 1),
+                     "gaa_algorithmic_gb": round(gaa / 1e9, 3), "gaa_only_roofline_ms": round(gaa / hbm_peak / 1e6, 3)})
+        del x, qf
+        torch.cuda.empty_cache()
+    # general-CSR stress: N = 2^17 nodes, Zipf in-degrees capped at 10^4
+    rng = np.random.default_rng(3)
+    n = 1 << 17
+    deg = np.minimum(rng.zipf(1.6, n), 10_000).astype(np.int64)
+    deg[rng.choice(n, 8, replace=False)] = 10_000
+    dst = np.repeat(np.arange(n), deg)
+    src = rng.integers(0, n, dst.shape[0])
+    g = tx.DGLGraph()
+    g.add_nodes(n)
+    g.add_edges(torch.from_numpy(src), torch.from_numpy(dst))
+    gat = tx.GAT(256, 128, 128, 1, [4, 1], torch.nn.functional.leaky_relu, 0.1, 0.1).to(dev).train()
+    xg = torch.from_numpy(synth.unit_rows(n, 256, seed=9)).to(dev)
+    w = torch.full((n, 128), 1e-3, device=dev)
+
+    def gstep(i):
+        gat.zero_grad(set_to_none=True)
+        (gat(g, xg) * w).sum().backward()
+    gms = _event_ms(gstep, 6, 2)
+    e = int(dst.shape[0])
+    by = sum(gaa_fwd_bytes(n, e, h, 128 * h) + gaa_bwd_bytes(n, e, h, 128 * h) for h in (4, 1))
+    return {"workload": "configs[4] (one GPU): PGAT+WMR+LBM d=512, 3 propagation layers, heads [4,4,1], fwd+bwd, sweep over egonets per step",
+            "sweep": rows,
+            "general_csr_stress": {"nodes": n, "edges": e, "max_in_degree": int(deg.max()), "model": "GAT 256 -> 4x128 -> 128, fwd+bwd, general-CSR kernels",
+                                   "ms_per_step": round(gms, 3), "gaa_algorithmic_gb": round(by / 1e9, 3),
+                                   "edges_per_s": round(e / gms * 1e3, 1)}}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -319,7 +563,7 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.synchronize()
 
     def fwd_bwd(g, x, qf):
-        flat.zero_()
+        bucket.zero_()
         scores = model(g, x, qf)                                              # trainer.py:51
         loss = tx.info_nce_loss(scores.reshape(nq, -1), None)                 # trainer.py:52-56, loss.py:52-57 (target = zeros)
         loss.backward()                                                       # trainer.py:60
@@ -452,7 +696,7 @@ def run_b200(args, rank, world, local_rank):
             b = batches[i % nb]
             g = b["graph"]
             g.ndata["pos"] = tx.graph._LazyPos(g)
-            flat.zero_()
+            bucket.zero_()
             pos = g.ndata["pos"].to(dev)
             g.ndata["h"] = model.graph_propagate(g, b["x"])
             hg = model.readout(g, pos)
@@ -461,9 +705,11 @@ def run_b200(args, rank, world, local_rank):
                 go = gout[tuple(hg.shape)] = torch.full_like(hg, 1e-3)
             hg.backward(go)
 
+        bucket.active = False                # this leg exchanges nothing
         for i in range(max(3, nb)):
             step_prop_readout(i)
         pr_ms, _, _ = timed(step_prop_readout, args.steps)
+        bucket.active = True
         prop_ro = {"ms_per_step": round(pr_ms / args.steps, 4)}
     except Exception as e:      # noqa: BLE001 - diagnostic leg only
         prop_ro = {"error": f"{type(e).__name__}: {e}"[:200]}
@@ -522,7 +768,8 @@ def run_b200(args, rank, world, local_rank):
             if t_f > 0:
                 by = gaa_fwd_bytes(n_avg, e_avg, H, W)
                 rl.append({"kernel": f"{label}[{tag}]", "ms": t_f, "bytes": by, "achieved": by / t_f / 1e6})
-        for bwd_names, label in ((("tx_gat_fused_bwd_staged",), "tx_gat_fused_bwd_staged"), (("tx_gat_fused_bwd",), "tx_gat_fused_bwd"),
+        for bwd_names, label in ((("tx_gat_star_bwd",), "tx_gat_star_bwd"), (("tx_gat_fused_bwd_staged",), "tx_gat_fused_bwd_staged"),
+                                 (("tx_gat_fused_bwd",), "tx_gat_fused_bwd"),
                                  (("tx_epilogue_bwd", "tx_gat_aggregate_bwd_dst", "tx_gat_aggregate_bwd_src", "tx_gat_attn_grad_partials"),
                                   "tx_epilogue_bwd+aggregate_bwd_dst+src+attn_grad")):
             if not avg(bwd_names[-1] if len(bwd_names) == 1 else "tx_gat_aggregate_bwd_dst", tag):
@@ -536,7 +783,11 @@ def run_b200(args, rank, world, local_rank):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")      # dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu --set full)
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get("per_launch_bytes", {})
+            tj = json.load(f)
+        # the capture is only quoted for the kernel sources it was taken on (scripts/make_profiles.py records their hash): a kernel
+        # that changed since reports traffic = null instead of a stale number
+        if tj.get("csrc_sha16") == csrc_sha16():
+            traffic = tj.get("per_launch_bytes", {})
     for r in rl:
         r["traffic"] = traffic.get(r["kernel"])
     dom = max(rl, key=lambda r: r["ms"]) if rl else None
@@ -551,17 +802,27 @@ def run_b200(args, rank, world, local_rank):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(32, 8, 1)
-        cpu = {"value": round(r["value"], 1), "unit": UNIT, "cores": r["cores"], "kind": "port",
-               "sample": f"32 queries x 32 = {r['egonets']} egonets ({r['nodes']} nodes) x 8 steps of the same MAG-CS config on the host "
-                         "cores: torch-CPU port of reference model_zoo.py PGAT/WMR/LBM + InfoNCE fwd+bwd, dropout 0.1 "
-                         "(real DGL 0.4.0 not installable offline)"}
+        r = cpu_reference_run(64, 6, 1)        # bounded sample: 2048 egonets per step, ~10-20 s of host work
+        cpu = {"value": round(r["value"], 1), "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": _cpu_sample_text(r, 64, 1)}
+
+    other = None
+    if world == 1 and not args.no_side_legs:
+        other = {}
+        del batches
+        torch.cuda.empty_cache()
+        for key, fn in (("configs[0]", lambda: leg_pgcn_wordnet(dev, hbm_peak, not args.no_cpu_baseline)),
+                        ("configs[3]", lambda: leg_inference(dev)), ("configs[4]", lambda: leg_d512_sweep(dev, hbm_peak))):
+            try:
+                other[key] = fn()
+            except Exception as e_:      # noqa: BLE001 - side measurements never break the headline
+                other[key] = {"error": f"{type(e_).__name__}: {e_}"[:300]}
+            torch.cuda.empty_cache()
 
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: MAG-CS PGAT+WMR+LBM, d=250, 2-hop egonets, batch=256 queries x 32 = 8192 egonets per GPU"
+        "config": {"workload": WORKLOAD
                                + (f" (configs[2] sharding: {world} x 256 queries, one NCCL all-reduce of {flat.numel()} fp32 grads)" if world > 1 else ""),
                    "egonets_per_gpu_step": sh.num_graphs, "nodes_per_gpu_step": int(n_avg), "edges_per_gpu_step": int(e_avg),
                    "dropout": 0.1, "parallelism": f"dp{world} (egonet shards by query group)",
@@ -583,6 +844,8 @@ def run_b200(args, rank, world, local_rank):
         "cpu_baseline": cpu,
         "host": host_info,
         "propagate_readout": prop_ro,
+        "star_bwd_reruns": int(txf.star_bwd_reruns(dev).item()),
+        "other_configs": other,
     }
     print(json.dumps(line), flush=True)
 
@@ -596,6 +859,7 @@ def main():
     ap.add_argument("--queries", type=int, default=256, help="queries per GPU per step (x32 egonets)")
     ap.add_argument("--batches", type=int, default=4, help="distinct rotating synthetic batches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side-legs", action="store_true", help="skip the configs[0] / [3] / [4] side measurements (N = 1 only)")
     ap.add_argument("--no-pin-cores", dest="pin_cores", action="store_false", help="N > 1: do not partition the host cores among the ranks")
     args = ap.parse_args()
 

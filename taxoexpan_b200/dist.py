@@ -59,35 +59,51 @@ class FlatGradBucket:
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
-        dev, dt = self.params[0].device, self.params[0].dtype
-        self.flat = torch.zeros(sum(p.numel() for p in self.params), device=dev, dtype=dt)
         self.group = group
         self.overlap = overlap
-        self._views = []
-        off = 0
-        for p in self.params:
-            v = self.flat[off:off + p.numel()].view_as(p)
-            self._views.append(v)
-            p.grad = v
-            off += p.numel()
-        # contiguous parameter groups of about equal size; backward finishes them from the LAST group to the first
-        n_seg = max(1, min(int(segments), len(self.params)))
-        target = self.flat.numel() / n_seg
-        self._seg_of, self._seg_range, self._seg_size = [], [], []
-        seg, start, acc = 0, 0, 0
-        for i, p in enumerate(self.params):
-            self._seg_of.append(seg)
-            acc += p.numel()
-            left = len(self.params) - 1 - i
-            if (acc - start >= target and seg < n_seg - 1 and left >= 1) or left == 0:
-                self._seg_range.append((start, acc))
-                self._seg_size.append(sum(1 for s in self._seg_of if s == seg))
-                start, seg = acc, seg + 1
+        self.segments = segments
+        self.active = True                        # False: hooks only keep the views bound (no exchange is launched)
+        self._rebuilt = False
+        self._fire_order = []
+        self._layout(list(range(len(self.params))), None)
         self._ready = [0] * len(self._seg_range)
         self._launched = [False] * len(self._seg_range)
         self._seen = [False] * len(self.params)
         self._works = []
         self._hooks = [p.register_post_accumulate_grad_hook(self._make_hook(i)) for i, p in enumerate(self.params)]
+
+    def _layout(self, order, old_views):
+        """(Re)build the flat buffer with the parameters laid out in `order` (indices into self.params) and cut it into segments of
+        about equal size, each boundary at the parameter edge closest to its target."""
+        dev, dt = self.params[0].device, self.params[0].dtype
+        self.flat = torch.zeros(sum(p.numel() for p in self.params), device=dev, dtype=dt)
+        self._views = [None] * len(self.params)
+        edges = [0]
+        for i in order:
+            p = self.params[i]
+            v = self.flat[edges[-1]:edges[-1] + p.numel()].view_as(p)
+            if old_views is not None:
+                v.copy_(old_views[i])
+            self._views[i] = v
+            p.grad = v
+            edges.append(edges[-1] + p.numel())
+        n_seg = max(1, min(int(self.segments), len(order)))
+        total = self.flat.numel()
+        cuts = [0]
+        for k in range(1, n_seg):
+            target = total * k / n_seg
+            j = min(range(cuts[-1] + 1, len(order) - (n_seg - 1 - k)), key=lambda i: abs(edges[i] - target), default=None)
+            if j is None:
+                break
+            cuts.append(j)
+        cuts.append(len(order))
+        self._seg_of = [0] * len(self.params)
+        self._seg_range, self._seg_size = [], []
+        for s_, (a, b) in enumerate(zip(cuts, cuts[1:])):
+            for i in order[a:b]:
+                self._seg_of[i] = s_
+            self._seg_range.append((edges[a], edges[b]))
+            self._seg_size.append(b - a)
 
     # ---- internals ----
     def _dist_active(self) -> bool:
@@ -108,6 +124,9 @@ class FlatGradBucket:
     def _make_hook(self, i: int):
         def hook(param):
             s = self._seg_of[i]
+            if not self.active:
+                self._rebind(i)
+                return
             if self._launched[s]:
                 raise RuntimeError("FlatGradBucket: backward ran again after this segment's all-reduce was launched; call "
                                    "all_reduce() / zero_() between backward passes or construct the bucket with overlap=False")
@@ -115,6 +134,8 @@ class FlatGradBucket:
             if not self._seen[i]:
                 self._seen[i] = True
                 self._ready[s] += 1
+                if not self._rebuilt:
+                    self._fire_order.append(i)
             if self.overlap and self._ready[s] == self._seg_size[s]:
                 self._launch(s)
         return hook
@@ -157,6 +178,11 @@ class FlatGradBucket:
                 self._launch(s)
         for w in self._works:
             w.wait()
+        if not self._rebuilt and len(self._fire_order) == len(self.params):
+            # like DDP after its first iteration: lay the buffer out in the order autograd finishes the gradients (last finished first), so
+            # that every segment but the first is complete - and on the wire - while the layers below still run their backward
+            self._layout(self._fire_order[::-1], self._views)
+            self._rebuilt = True
         self._reset_step()
         return self.flat
 

@@ -28,6 +28,11 @@ def build(dev, drop=0.0):
     return m.to(dev).train()
 
 
+def grads_of(model):
+    """all gradients in registration order (the bucket re-lays its buffer out in backward order after the first step)"""
+    return torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+
+
 def step(model, bucket, shapes, x, qf, q0, q1, dev):
     per = 1 + NEG
     g0, g1 = q0 * per, q1 * per
@@ -56,7 +61,8 @@ def main():
         model = build(dev)
         bucket = FlatGradBucket(model.parameters(), overlap=overlap)
         loss = step(model, bucket, shapes, x, qf, q0, q1, dev)
-        flat = bucket.all_reduce().clone()
+        bucket.all_reduce()
+        flat = grads_of(model)
         loss_sum = loss.detach().clone()
         dist.all_reduce(loss_sum)
         # the reference trainer's zeroing (optimizer.zero_grad(), set_to_none=True) must give the same reduced buffer
@@ -70,14 +76,15 @@ def main():
         bucket._reset_step()
         s = model(g, x[n0:n1].to(dev), qf[g0:g1].to(dev))
         tx.info_nce_loss(s.reshape(q1 - q0, -1), torch.zeros(q1 - q0, dtype=torch.long, device=dev)).backward()
-        flat_none = bucket.all_reduce().clone()
+        bucket.all_reduce()
+        flat_none = grads_of(model)
         torch.cuda.synchronize()
         if rank == 0:
             ref_model = build(dev)
             ref_bucket = FlatGradBucket(ref_model.parameters(), overlap=False, group=None)
             ref_bucket._dist_active = lambda: False                       # single-GPU run: no exchange
             ref_loss = step(ref_model, ref_bucket, shapes, x, qf, 0, N_Q, dev)
-            ref = ref_bucket.flat
+            ref = grads_of(ref_model)
             torch.cuda.synchronize()
             scale = max(1.0, float(ref.abs().max()))
             res[f"overlap={overlap}"] = {

@@ -6,17 +6,23 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 
 def test_reference_arm_prints_the_contract_line():
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600, cwd=ROOT)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--queries", "8",
+                          "--batches", "1"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [ln for ln in out.stdout.strip().splitlines() if ln.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "egonets/s" and d["higher_is_better"] is True and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    from oracle import build_ref
+    # the unmodified reference (byte-compiled into oracle/_ref by oracle/build_ref.py) when it has been built, else the oracle port
+    assert d["cpu_baseline"]["kind"] == ("reference" if build_ref.available() else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert ("cpu_port" in d) == build_ref.available()
     assert d["e2e"] == {"value": d["value"], "unit": "egonets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["metric"].startswith("egonets/s (fwd+bwd) PGAT d=250") and "workload" in d["config"]
 

@@ -70,7 +70,7 @@ def _worker(rank, world, port, out):
     model.loss(og, xs, qs, nq).backward()
     bucket.all_reduce()                       # the single exchange of the path
     if rank == 0:
-        torch.save(bucket.flat.clone(), out)
+        torch.save(torch.cat([p.grad.reshape(-1) for p in model.parameters()]), out)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -85,7 +85,7 @@ def test_sharded_gradients_sum_to_unsharded(tmp_path):
     shapes, nodes, x, qf = _data()
     og, xs, qs, nq = _shard(shapes, nodes, x, qf, 0, N_Q)
     model.loss(og, xs, qs, nq).backward()
-    ref = bucket.flat
+    ref = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
     assert got.shape == ref.shape
     assert float((got - ref).abs().max()) <= 2e-6 * max(1.0, float(ref.abs().max()))
 
@@ -125,17 +125,40 @@ def test_flat_bucket_survives_zero_grad_set_to_none():
         assert lin.weight.grad is None
         lin(torch.ones(1, 3)).sum().backward()
         flat = b.all_reduce()
-        assert torch.equal(flat[:6].view(2, 3), torch.ones(2, 3)) and torch.equal(flat[6:], torch.ones(2))
-        assert lin.weight.grad.data_ptr() == flat.data_ptr()       # .grad is the view again
+        assert torch.equal(flat, torch.ones(8))
+        lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * 4
+        assert all(lo <= p.grad.data_ptr() < hi for p in lin.parameters())       # .grad is a view of the buffer again
+        assert torch.equal(lin.weight.grad, torch.ones(2, 3)) and torch.equal(lin.bias.grad, torch.ones(2))
     # a parameter that received no gradient contributes zeros, not last step's values
     opt.zero_grad()
     (lin.weight.sum()).backward()
     flat = b.all_reduce()
-    assert torch.equal(flat[:6], torch.ones(6)) and float(flat[6:].abs().sum()) == 0.0
+    assert float(flat.sum()) == 6.0 and torch.equal(lin.weight.grad, torch.ones(2, 3)) and float(lin.bias.grad.abs().sum()) == 0.0
     # in-place zeroing keeps working
     b.zero_()
     lin(torch.ones(1, 3)).sum().backward()
-    assert torch.equal(b.all_reduce()[:6], torch.ones(6))
+    assert torch.equal(b.all_reduce(), torch.ones(8))
+
+
+def test_flat_bucket_relayouts_in_backward_order_after_the_first_step():
+    """Like DDP: after the first backward the buffer is laid out in the order the gradients become final (last finished first), so the
+    segment holding the LATE layers completes - and is all-reduced - while the early layers still run their backward."""
+    net = torch.nn.Sequential(torch.nn.Linear(4, 300), torch.nn.Linear(300, 200), torch.nn.Linear(200, 1))
+    b = FlatGradBucket(net.parameters(), segments=2)
+    x = torch.ones(2, 4)
+    net(x).sum().backward()
+    ref = [p.grad.clone() for p in net.parameters()]
+    b.all_reduce()
+    assert b._rebuilt
+    # the first segment now holds the first layer (its gradients are final last), the last segment the last layers
+    first_layer = {id(p) for p in net[0].parameters()}
+    seg0 = {id(p) for i, p in enumerate(b.params) if b._seg_of[i] == 0}
+    assert first_layer <= seg0 and id(net[2].weight) not in seg0
+    assert all(torch.equal(p.grad, r) for p, r in zip(net.parameters(), ref))    # values survive the re-layout
+    b.zero_()
+    net(x).sum().backward()
+    b.all_reduce()
+    assert all(torch.equal(p.grad, r) for p, r in zip(net.parameters(), ref))
 
 
 def test_flat_bucket_segments_cover_the_buffer():
