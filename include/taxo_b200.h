@@ -74,6 +74,12 @@ int tx_star_batch_structure(const int32_t* n_gp, const int32_t* n_sib, const int
                             const int32_t* edge_off, int64_t n_graphs, int32_t* pos, int32_t* src, int32_t* dst,
                             int32_t* in_ptr, int32_t* in_src, int32_t* in_eid, int32_t* out_ptr, int32_t* out_dst,
                             int32_t* out_slot, void* stream);
+/* The plan of a star-egonet batch from the counts alone (one launch): node_off / edge_off [G + 1] (exclusive scans of n = n_gp + 1 + n_sib
+ * and 2 n - 1, the layout of dataset.py:404-437 batched as data_loaders.py:25 does) and the work-item tables of tx_gat_star_fwd /
+ * tx_gat_star_bwd: one 16-byte record {first node, first edge, n_gp | chunk << 24, n_sib} per (egonet, chunk of chunk_fwd resp.
+ * chunk_bwd siblings), sum_k max(1, ceil(n_sib_k / chunk)) records each (the caller sizes them; either table may be NULL). */
+int tx_star_batch_plan(const int32_t* n_gp, const int32_t* n_sib, int64_t n_graphs, int64_t chunk_fwd, int64_t chunk_bwd, int32_t* node_off,
+                       int32_t* edge_off, int32_t* tasks_fwd, int32_t* tasks_bwd, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Position-embedding concat + feature dropout: z = drop([x || P[pos]])

@@ -14,11 +14,14 @@ x = torch.from_numpy(synth.unit_rows(sh.total_nodes, 250, seed=11)).to(dev)
 qf = torch.from_numpy(synth.unit_rows(sh.num_graphs, 250, seed=13)).to(dev)
 g = tx.EgonetBatch.from_counts(sh.n_gp, sh.n_sib)
 target = torch.zeros(nq, dtype=torch.long, device=dev)
+from taxoexpan_b200.dist import FlatGradBucket
+bucket = FlatGradBucket(model.parameters())
 def step():
     g.ndata["pos"] = tx.graph._LazyPos(g)
-    model.zero_grad()
-    loss = F.cross_entropy(model(g, x, qf).reshape(nq, -1), target, reduction="sum")
+    bucket.zero_()
+    loss = tx.info_nce_loss(model(g, x, qf).reshape(nq, -1), None)
     loss.backward()
+    bucket.all_reduce()
 for _ in range(5): step()
 torch.cuda.synchronize()
 pr = cProfile.Profile()
@@ -27,5 +30,13 @@ for _ in range(30): step()
 pr.disable()
 torch.cuda.synchronize()
 s = io.StringIO()
-pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(28)
-print(s.getvalue()[:6000])
+pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(40)
+print(s.getvalue()[:9000])
+import time
+t0 = time.perf_counter()
+for _ in range(50): step()
+t1 = time.perf_counter(); torch.cuda.synchronize()
+print("host enqueue per step (no profiler): %.3f ms" % ((t1 - t0) / 50 * 1e3))
+t0 = time.perf_counter()
+for _ in range(50): tx.EgonetBatch.from_counts(sh.n_gp, sh.n_sib)
+print("EgonetBatch.from_counts: %.3f ms" % ((time.perf_counter() - t0) / 50 * 1e3))

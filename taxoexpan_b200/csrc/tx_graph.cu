@@ -143,6 +143,74 @@ __global__ void __launch_bounds__(256) star_batch_structure_kernel(
   }
 }
 
+
+// Plan of a star-egonet batch from the per-egonet counts alone (one CTA, tiles of 1024 egonets): node / edge offsets (exclusive scans of
+// n = a + 1 + s and e = 2 n - 1) and the work-item tables of the star kernels - one 16-byte record {first node, first edge,
+// n_gp | chunk << 24, n_sib} per (egonet, chunk of C siblings), C = chunk_fwd for tx_gat_star_fwd and chunk_bwd for tx_gat_star_bwd; an
+// egonet's records are consecutive.  Moves ~0.4 ms of numpy (two cumsums, two row-repeats per table) per batch off the host.
+__global__ void __launch_bounds__(1024, 1) star_batch_plan_kernel(const int32_t* __restrict__ n_gp, const int32_t* __restrict__ n_sib, int G,
+                                                                   int chunk_fwd, int chunk_bwd, int32_t* __restrict__ node_off,
+                                                                   int32_t* __restrict__ edge_off, int4* __restrict__ tasks_fwd,
+                                                                   int4* __restrict__ tasks_bwd) {
+  __shared__ int s_warp[3][32];
+  __shared__ int s_carry[3];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x < 3) s_carry[threadIdx.x] = 0;
+  __syncthreads();
+  for (int base = 0; base < G; base += 1024) {
+    const int k = base + threadIdx.x;
+    int a = 0, s = 0, v[3] = {0, 0, 0};
+    if (k < G) {
+      a = n_gp[k]; s = n_sib[k];
+      v[0] = a + 1 + s;
+      v[1] = tasks_fwd ? max(1, (s + chunk_fwd - 1) / chunk_fwd) : 0;
+      v[2] = tasks_bwd ? max(1, (s + chunk_bwd - 1) / chunk_bwd) : 0;
+    }
+    int incl[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      int x = v[q];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      incl[q] = x;
+      if (lane == 31) s_warp[q][wid] = x;
+    }
+    __syncthreads();
+    if (wid < 3) {
+      int x = s_warp[wid][lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      s_warp[wid][lane] = x;                                // inclusive scan of the warp totals
+    }
+    __syncthreads();
+    int excl[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) excl[q] = s_carry[q] + (wid ? s_warp[q][wid - 1] : 0) + incl[q] - v[q];
+    if (k < G) {
+      const int o = excl[0], e = 2 * o - k;                // sum of (2 n - 1) over the earlier egonets
+      node_off[k] = o;
+      edge_off[k] = e;
+      if (tasks_fwd)
+        for (int c = 0; c < v[1]; ++c) tasks_fwd[excl[1] + c] = make_int4(o, e, a | (c << 24), s);
+      if (tasks_bwd)
+        for (int c = 0; c < v[2]; ++c) tasks_bwd[excl[2] + c] = make_int4(o, e, a | (c << 24), s);
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) s_carry[threadIdx.x] += s_warp[threadIdx.x][31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    node_off[G] = s_carry[0];
+    edge_off[G] = 2 * s_carry[0] - G;
+  }
+}
+
 }  // namespace tx
 
 using namespace tx;
@@ -220,6 +288,17 @@ int tx_star_batch_structure(const int32_t* n_gp, const int32_t* n_sib, const int
   star_batch_structure_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n_gp, n_sib, node_off, edge_off, (int)n_graphs, pos, src,
                                                                      dst, in_ptr, in_src, in_eid, out_ptr, out_dst, out_slot);
   TX_LAUNCH_CHECK("tx_star_batch_structure");
+  return TX_OK;
+}
+
+int tx_star_batch_plan(const int32_t* n_gp, const int32_t* n_sib, int64_t n_graphs, int64_t chunk_fwd, int64_t chunk_bwd, int32_t* node_off,
+                       int32_t* edge_off, int32_t* tasks_fwd, int32_t* tasks_bwd, void* stream) {
+  TX_REQUIRE(n_graphs >= 0 && n_graphs < INT32_MAX && n_gp && n_sib && node_off && edge_off, "star_batch_plan: bad arguments");
+  TX_REQUIRE((!tasks_fwd || (chunk_fwd >= 1 && aligned16(tasks_fwd))) && (!tasks_bwd || (chunk_bwd >= 1 && aligned16(tasks_bwd))),
+             "star_batch_plan: task tables need a chunk size >= 1 and 16-byte alignment");
+  star_batch_plan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(n_gp, n_sib, (int)n_graphs, (int)chunk_fwd, (int)chunk_bwd, node_off, edge_off,
+                                                               reinterpret_cast<int4*>(tasks_fwd), reinterpret_cast<int4*>(tasks_bwd));
+  TX_LAUNCH_CHECK("tx_star_batch_plan");
   return TX_OK;
 }
 

@@ -222,63 +222,57 @@ class EgonetBatch(DGLGraph):
             raise ValueError("n_gp and n_sib must be 1-D arrays of the same length")
         if (self.n_gp < 0).any() or (self.n_sib < 0).any():
             raise ValueError("negative egonet counts")
-        n = self.n_gp.astype(np.int64) + 1 + self.n_sib.astype(np.int64)
-        self._node_off = np.zeros(n.shape[0] + 1, dtype=np.int64)
-        np.cumsum(n, out=self._node_off[1:])
-        self._edge_off = np.zeros(n.shape[0] + 1, dtype=np.int64)
-        np.cumsum(2 * n - 1, out=self._edge_off[1:])
-        if self._edge_off[-1] >= 2 ** 31 - 1:
+        # Host work per batch is a handful of reductions over the counts: totals for the allocations and the launch sizes.  Offsets and
+        # the work-item tables of the star kernels are built on the GPU by tx_star_batch_plan from the two count vectors (they were
+        # two cumsums and two row-repeats per table in numpy: 0.5 ms per 8192-egonet batch on the path of every step).
+        g = self.n_gp.shape[0]
+        n = self.n_gp.astype(np.int64) + 1 + self.n_sib
+        self._n = int(n.sum()) if g else 0
+        self._e = 2 * self._n - g
+        if self._e >= 2 ** 31 - 1:
             raise ValueError("batch too large for int32 indices")
-        self._n = int(self._node_off[-1])
-        self._e = int(self._edge_off[-1])
         self._n_per_graph = n                 # batch_num_nodes / batch_num_edges lists are materialised on first use only
         self._bnn = self._bne = None          # (two 8192-element tolist() calls were 0.2 ms of every freshly built batch)
+        self._offs = None                     # host (node_off, edge_off), materialised on first use only
         self._edges_built = False
-        self._max_nodes = int(n.max()) if n.size else 0
-        g = n.shape[0]
-        # one staging buffer: [n_gp | n_sib | node_off | edge_off | pad to 16 bytes | forward task records | backward task records] as
-        # int32, filled in place
-        head_len = 4 * g + 2
-        self._task_off = (head_len + 3) // 4 * 4
+        self._max_nodes = int(n.max()) if g else 0
         # work items of the star-specialised kernels (tx_gat_star_fwd / tx_gat_star_bwd): one 16-byte record {node_off, edge_off,
         # n_gp | chunk << 24, n_sib} per (egonet, chunk of C siblings), C = STAR_CHUNK for the forward and STAR_BWD_CHUNK for the backward;
         # none when the batch exceeds the encoding (the general fused kernels take over)
-        plans = []
-        for chunk in ((STAR_CHUNK,) if STAR_BWD_CHUNK == STAR_CHUNK else (STAR_CHUNK, STAR_BWD_CHUNK)):
-            n_chunks = (self.n_sib + (chunk - 1)) // chunk
-            np.maximum(n_chunks, 1, out=n_chunks)
-            plans.append((chunk, n_chunks, int(n_chunks.sum(dtype=np.int64)) if g else 0))
-        ok = g > 0 and int(self.n_gp.max()) < (1 << 24) and int(plans[0][1].max()) <= STAR_MAX_CHUNKS
-        self._n_tasks = plans[0][2] if ok else 0
-        self._n_tasks_bwd = plans[-1][2] if ok else 0
-        self._task_off_bwd = self._task_off + (4 * self._n_tasks if len(plans) > 1 else 0)
-        packed = np.empty(self._task_off + 4 * sum(pl[2] for pl in plans) * (1 if ok else 0), dtype=np.int32)
+        s_max = int(self.n_sib.max()) if g else 0
+        ok = g > 0 and int(self.n_gp.max()) < (1 << 24) and (s_max + STAR_CHUNK - 1) // STAR_CHUNK <= STAR_MAX_CHUNKS
+
+        def count(chunk):
+            return int(np.maximum((self.n_sib + (chunk - 1)) // chunk, 1).sum(dtype=np.int64))
+        self._n_tasks = count(STAR_CHUNK) if ok else 0
+        self._n_tasks_bwd = (self._n_tasks if STAR_BWD_CHUNK == STAR_CHUNK else count(STAR_BWD_CHUNK)) if ok else 0
+        packed = np.empty(2 * g, dtype=np.int32)          # the staging buffer of a step: [n_gp | n_sib]
         packed[:g] = self.n_gp
-        packed[g:2 * g] = self.n_sib
-        packed[2 * g:3 * g + 1] = self._node_off
-        packed[3 * g + 1:4 * g + 2] = self._edge_off
-        packed[head_len:self._task_off] = 0
-        if ok:
-            base = np.empty((g, 4), dtype=np.int32)
-            base[:, 0] = self._node_off[:-1]
-            base[:, 1] = self._edge_off[:-1]
-            base[:, 3] = self.n_sib
-            off = self._task_off
-            for chunk, n_chunks, n_tasks in plans:
-                # record r of egonet k carries chunk number r - first[k]: in wrapping int32 arithmetic
-                # (n_gp - (first << 24)) + (r << 24) = n_gp | (chunk << 24), so one row-repeat and one strided add build all records
-                first = np.cumsum(n_chunks, dtype=np.int32) - n_chunks
-                base[:, 2] = self.n_gp - np.left_shift(first, 24)
-                rec = packed[off:off + 4 * n_tasks].reshape(-1, 4)
-                rec[:] = np.repeat(base, n_chunks, axis=0)
-                rec[:, 2] += np.left_shift(np.arange(n_tasks, dtype=np.int32), 24)
-                off += 4 * n_tasks
+        packed[g:] = self.n_sib
         self._packed = torch.from_numpy(packed)
         self._g = g
         if ndata:
             self.ndata.update(ndata)
         if "pos" not in self.ndata:
             self.ndata["pos"] = _LazyPos(self)
+
+    def _host_offsets(self):
+        if self._offs is None:
+            n = self._n_per_graph
+            node_off = np.zeros(n.shape[0] + 1, dtype=np.int64)
+            np.cumsum(n, out=node_off[1:])
+            edge_off = np.zeros(n.shape[0] + 1, dtype=np.int64)
+            np.cumsum(2 * n - 1, out=edge_off[1:])
+            self._offs = (node_off, edge_off)
+        return self._offs
+
+    @property
+    def _node_off(self):
+        return self._host_offsets()[0]
+
+    @property
+    def _edge_off(self):
+        return self._host_offsets()[1]
 
     @property
     def batch_num_nodes(self):
@@ -372,13 +366,27 @@ class EgonetBatch(DGLGraph):
             if packed is None or packed.device != device:
                 packed = self._packed.to(device, non_blocking=True)
             n_gp, n_sib = packed[:g], packed[g:2 * g]
-            node_off, edge_off = packed[2 * g:3 * g + 1], packed[3 * g + 1:4 * g + 2]
             i32 = dict(dtype=torch.int32, device=device)
+            # one allocation for everything tx_star_batch_plan writes: node_off | edge_off | forward records | backward records
+            o1 = (g + 1 + 3) // 4 * 4
+            o2 = 2 * o1
+            two = STAR_BWD_CHUNK != STAR_CHUNK
+            o3 = o2 + 4 * self._n_tasks
+            plan = torch.empty(o3 + (4 * self._n_tasks_bwd if two else 0), **i32)
+            node_off, edge_off = plan[:g + 1], plan[o1:o1 + g + 1]
+            t_f = plan[o2:o3] if self._n_tasks else None
+            t_b = (plan[o3:o3 + 4 * self._n_tasks_bwd] if two else t_f) if self._n_tasks else None
+            if g:
+                _lib.check(lib.tx_star_batch_plan(_lib.ptr(n_gp), _lib.ptr(n_sib), g, STAR_CHUNK, STAR_BWD_CHUNK, _lib.ptr(node_off),
+                                                  _lib.ptr(edge_off), _lib.ptr(t_f), _lib.ptr(t_b) if two else None,
+                                                  _lib.current_stream()), "tx_star_batch_plan")
+            else:
+                plan.zero_()
             st.node_off = node_off
             st.counts = (n_gp, n_sib, node_off, edge_off)
             if self._n_tasks:
-                st.star = (packed[self._task_off:self._task_off + 4 * self._n_tasks], self._n_tasks, STAR_CHUNK)
-                st.star_bwd = (packed[self._task_off_bwd:self._task_off_bwd + 4 * self._n_tasks_bwd], self._n_tasks_bwd, STAR_BWD_CHUNK)
+                st.star = (t_f, self._n_tasks, STAR_CHUNK)
+                st.star_bwd = (t_b, self._n_tasks_bwd, STAR_BWD_CHUNK)
             st.pos = torch.empty(st.n, **i32)
             st.in_ptr, st.in_src, st.in_eid = torch.empty(st.n + 1, **i32), torch.empty(st.e, **i32), torch.empty(st.e, **i32)
             st.out_ptr, st.out_dst, st.out_slot = torch.empty(st.n + 1, **i32), torch.empty(st.e, **i32), torch.empty(st.e, **i32)

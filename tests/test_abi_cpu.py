@@ -111,34 +111,24 @@ def test_synthetic_shapes_statistics():
     assert (s.n_sib <= 50).all() and (s.n_gp >= 1).all()
 
 
-def test_star_task_records_cover_every_sibling_exactly_once():
-    """EgonetBatch ships one 16-byte record {node_off, edge_off, n_gp | chunk << 24, n_sib} per (egonet, chunk of STAR_CHUNK siblings)
-    for tx_gat_star_fwd (include/taxo_b200.h): chunk 0 exists for every egonet, chunks tile [0, n_sib) without gaps or overlaps."""
+def test_star_task_counts_and_the_encoding_limit():
+    """EgonetBatch sizes the work-item tables of the star kernels on the host - one record per (egonet, chunk of STAR_CHUNK resp.
+    STAR_BWD_CHUNK siblings), chunk 0 for every egonet - and ships only the two count vectors; the records themselves are written on
+    the GPU by tx_star_batch_plan (checked bit for bit in tests/test_gpu_parity.py::test_star_batch_plan_tables_are_bit_exact)."""
     import numpy as np
     from taxoexpan_b200 import graph as txg
     rng = np.random.default_rng(0)
     n_gp = rng.integers(0, 5, 200)
     n_sib = np.concatenate([rng.integers(0, 60, 190), [0, 1, txg.STAR_CHUNK, txg.STAR_CHUNK + 1, 4 * txg.STAR_CHUNK, 0, 0, 7, 50, 50]])
     g = tx.EgonetBatch.from_counts(n_gp, n_sib)
-    rec = g._packed.numpy()[g._task_off:g._task_off + 4 * g._n_tasks].reshape(-1, 4)
-    assert g._task_off % 4 == 0 and rec.shape[0] == int(np.maximum(1, -(-n_sib // txg.STAR_CHUNK)).sum())
-    node_off = np.concatenate([[0], np.cumsum(n_gp + 1 + n_sib)])
-    edge_off = np.concatenate([[0], np.cumsum(2 * (n_gp + 1 + n_sib) - 1)])
-    covered = [np.zeros(s, dtype=int) for s in n_sib]
-    owner_of = {int(o): k for k, o in enumerate(node_off[:-1])}
-    seen_chunk0 = set()
-    for o, q, ac, s in rec.tolist():
-        k = owner_of[o]
-        a, c = ac & 0xFFFFFF, ac >> 24
-        assert (q, a, s) == (edge_off[k], n_gp[k], n_sib[k])
-        if c == 0:
-            seen_chunk0.add(k)
-        covered[k][c * txg.STAR_CHUNK:min(s, (c + 1) * txg.STAR_CHUNK)] += 1
-    assert seen_chunk0 == set(range(len(n_gp)))
-    assert all((c == 1).all() for c in covered)
+    assert g._n_tasks == int(np.maximum(1, -(-n_sib // txg.STAR_CHUNK)).sum())
+    assert g._n_tasks_bwd == int(np.maximum(1, -(-n_sib // txg.STAR_BWD_CHUNK)).sum())
+    assert g._packed.numel() == 2 * 200 and np.array_equal(g._packed.numpy()[:200], n_gp) and np.array_equal(g._packed.numpy()[200:], n_sib)
+    assert g.number_of_nodes() == int((n_gp + 1 + n_sib).sum()) and g.number_of_edges() == 2 * g.number_of_nodes() - 200
+    assert np.array_equal(g.node_offsets().numpy(), np.concatenate([[0], np.cumsum(n_gp + 1 + n_sib)]))
     # a batch the encoding cannot hold (more chunks than the 7-bit field) falls back to the general kernel: no records
     big = tx.EgonetBatch.from_counts([1], [txg.STAR_CHUNK * txg.STAR_MAX_CHUNKS + 1])
-    assert big._n_tasks == 0
+    assert big._n_tasks == 0 and big._n_tasks_bwd == 0
 
 
 def test_matching_and_loss_have_no_cpu_path():

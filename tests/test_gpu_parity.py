@@ -134,6 +134,27 @@ def test_star_structure_closed_form_is_bit_exact():
     assert np.array_equal(st.pos.cpu().numpy(), og.pos.numpy())
 
 
+def test_star_batch_plan_tables_are_bit_exact():
+    """tx_star_batch_plan (offsets + the work-item tables of the star kernels, built on the GPU from the counts) against numpy, on a
+    batch larger than one scan tile with roots, leaves, 50-sibling egonets and > 32 grand-parents."""
+    shapes = tx.synth.sample_shapes(96, 31, "mag-cs", seed=8)                     # 3072 egonets: three tiles of 1024
+    n_gp = np.concatenate([shapes.n_gp, [0, 0, 40, 1]]).astype(np.int64)
+    n_sib = np.concatenate([shapes.n_sib, [0, 50, 0, 33]]).astype(np.int64)
+    st = tx.EgonetBatch.from_counts(n_gp, n_sib).structure(dev())
+    n = n_gp + 1 + n_sib
+    node_off = np.concatenate([[0], np.cumsum(n)])
+    edge_off = np.concatenate([[0], np.cumsum(2 * n - 1)])
+    assert np.array_equal(st.node_off.cpu().numpy(), node_off) and np.array_equal(st.counts[3].cpu().numpy(), edge_off)
+    for (tab, n_tasks, chunk) in (st.star, st.star_bwd):
+        n_chunks = np.maximum((n_sib + chunk - 1) // chunk, 1)
+        assert n_tasks == int(n_chunks.sum())
+        eg = np.repeat(np.arange(len(n)), n_chunks)
+        c = np.arange(n_tasks) - np.repeat(np.cumsum(n_chunks) - n_chunks, n_chunks)
+        want = np.stack([node_off[eg], edge_off[eg], n_gp[eg] | (c << 24), n_sib[eg]], 1).astype(np.int32)
+        assert np.array_equal(tab.cpu().numpy().reshape(-1, 4), want)
+    assert st.star[2] == tx.graph.STAR_CHUNK and st.star_bwd[2] == tx.graph.STAR_BWD_CHUNK
+
+
 def test_general_csr_build_is_bit_exact():
     rng = np.random.default_rng(0)
     n, e = 1000, 7000
