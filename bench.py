@@ -550,7 +550,9 @@ def run_b200(args, rank, world, local_rank):
     bucket = FlatGradBucket(model.parameters())     # gradients live in one flat fp32 bucket -> ONE all-reduce per step
     flat = bucket.flat
 
-    # rotating seeded batches (different shapes/features per rank and per slot), host copies pinned
+    # rotating seeded batches (different shapes/features per rank and per slot), host copies pinned.  The same rows are available two
+    # ways: as per-batch feature matrices (x_host / qf_host: what a DataLoader collating rows on the host would hand over) and as node
+    # ids into a node-embedding table resident in HBM (ids_host / qids_host; table = the batch's rows, every row referenced once)
     batches = []
     for b in range(nb):
         shapes = synth.sample_shapes(nq, NEGATIVE_SIZE, "mag-cs", seed=20200420 + 1000 * rank + b)
@@ -558,7 +560,13 @@ def run_b200(args, rank, world, local_rank):
         x = torch.from_numpy(synth.unit_rows(n, MAGCS["in_dim"], seed=11 + 1000 * rank + b)).pin_memory()
         qf = torch.from_numpy(synth.unit_rows(shapes.num_graphs, MAGCS["in_dim"], seed=13 + 1000 * rank + b)).pin_memory()
         g = tx.EgonetBatch.from_counts(shapes.n_gp, shapes.n_sib).pin_memory()
-        batches.append(dict(shapes=shapes, x_host=x, qf_host=qf, graph=g, x=x.to(dev), qf=qf.to(dev)))
+        rng_b = np.random.default_rng(77 + 1000 * rank + b)
+        perm = rng_b.permutation(n + shapes.num_graphs).astype(np.int32)        # rows of the table in shuffled order: a real gather
+        table = torch.empty((n + shapes.num_graphs, MAGCS["in_dim"]), dtype=torch.float32)
+        table[torch.from_numpy(perm[:n].astype(np.int64))] = x
+        table[torch.from_numpy(perm[n:].astype(np.int64))] = qf
+        batches.append(dict(shapes=shapes, x_host=x, qf_host=qf, graph=g, x=x.to(dev), qf=qf.to(dev), table=table.to(dev),
+                            ids_host=torch.from_numpy(perm[:n].copy()).pin_memory(), qids_host=torch.from_numpy(perm[n:].copy()).pin_memory()))
         g.structure(dev)
     torch.cuda.synchronize()
 
@@ -582,6 +590,8 @@ def run_b200(args, rank, world, local_rank):
     copy_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream(dev)
 
+    e2e_mode = {"ids": True}       # True: ship node ids, gather rows from the resident table on the GPU; False: ship the feature rows
+
     def prefetch(i):
         b = batches[i % nb]
         sh = b["shapes"]
@@ -589,11 +599,15 @@ def run_b200(args, rank, world, local_rank):
             g = tx.EgonetBatch.from_counts(sh.n_gp, sh.n_sib)    # fresh batch object: structure is rebuilt from host counts
             g._packed = b["graph"]._packed                       # reuse the pinned staging buffer
             g.stage(dev)
-            x = b["x_host"].to(dev, non_blocking=True)
-            qf = b["qf_host"].to(dev, non_blocking=True)
+            if e2e_mode["ids"]:
+                x = b["ids_host"].to(dev, non_blocking=True)
+                qf = b["qids_host"].to(dev, non_blocking=True)
+            else:
+                x = b["x_host"].to(dev, non_blocking=True)
+                qf = b["qf_host"].to(dev, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        return g, x, qf, ev
+        return g, x, qf, ev, b["table"]
 
     e2e_state = {"next": None, "pending": []}
     loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(4)]     # pinned landing slots of the per-step loss
@@ -604,12 +618,14 @@ def run_b200(args, rank, world, local_rank):
         t0 = time.perf_counter()
         if e2e_state["next"] is None:
             e2e_state["next"] = prefetch(i)
-        g, x, qf, ev = e2e_state["next"]
+        g, x, qf, ev, table = e2e_state["next"]
         e2e_state["next"] = prefetch(i + 1)                      # overlaps with this step's compute
         main_stream.wait_event(ev)
         for t in (x, qf, g._staged):
             t.record_stream(main_stream)
         t1 = time.perf_counter()
+        if e2e_mode["ids"]:                                      # rows from the table resident in HBM (tx_gather_rows)
+            x, qf = txf.gather_rows(table, x), txf.gather_rows(table, qf)
         loss = fwd_bwd(g, x, qf)
         slot = loss_host[i % 4]
         slot.copy_(loss.detach(), non_blocking=True)             # D2H of this step's result, every step, asynchronously ...
@@ -684,6 +700,13 @@ def run_b200(args, rank, world, local_rank):
     host_t.update(prefetch=0.0, fwd_bwd=0.0, item=0.0, n=0)
     e2e_ms, _, _ = timed(step_e2e, args.steps, flush=e2e_flush)
     e2e_host = {k: round(v / max(host_t["n"], 1) * 1e3, 4) for k, v in host_t.items() if k != "n"}   # host ms per step by phase
+    # the same loop shipping the feature ROWS (45.6 MB per step) instead of node ids: what round 1 reported as e2e
+    e2e_mode["ids"] = False
+    for i in range(max(3, nb)):
+        step_e2e(i)
+    e2e_flush()
+    e2e_rows_ms, _, _ = timed(step_e2e, args.steps, flush=e2e_flush)
+    e2e_mode["ids"] = True
     clocks = sampler.stop() if rank == 0 else None
 
     # propagate + readout alone (graph_propagate -> readout, fwd + bwd against a fixed upstream gradient; no matching, no
@@ -798,7 +821,8 @@ def run_b200(args, rank, world, local_rank):
                     "algorithmic_bytes_per_launch": int(dom["bytes"]), "ms_per_launch": round(dom["ms"], 4)}
     gemm_ms = sum(v for k, v in kern.items() if k.startswith("gemm") or k.startswith("split_dy"))
     gemm_flops = 3 * gemm_flops_per_node(MAGCS) * n_avg - 2 * n_avg * MAGCS["in_dim"] * W0   # dz0 only for the 50 pos columns
-    x_bytes = int(b0["x_host"].numel() * 4 + b0["qf_host"].numel() * 4 + b0["graph"]._packed.numel() * 4)
+    rows_bytes = int(b0["x_host"].numel() * 4 + b0["qf_host"].numel() * 4 + b0["graph"]._packed.numel() * 4)
+    x_bytes = int(b0["ids_host"].numel() * 4 + b0["qids_host"].numel() * 4 + b0["graph"]._packed.numel() * 4)
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -831,7 +855,11 @@ def run_b200(args, rank, world, local_rank):
                              "tf32x3": "tcgen05 3xTF32 (tx_gemm.cu), fp32-faithful"}.get(txf.GEMM_BACKEND, "torch.mm (cuBLAS fp32, TF32 off)")},
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": x_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": round(e2e_ms / args.steps, 4), "host_ms_per_step": e2e_host,
-                "h2d_gb_per_s_isolated": round(h2d_gbs, 2), "h2d_ms_per_step_at_that_rate": round(x_bytes / h2d_gbs / 1e6, 4)},
+                "inputs": "per step from pinned host memory: egonet counts + int32 node ids + int32 query ids; the node-embedding table is "
+                          "resident in HBM (like the model's parameters) and the rows are gathered by tx_gather_rows inside the timed region",
+                "feature_rows_variant": {"value": round(total_egonets / (e2e_rows_ms * 1e-3), 1), "ms_per_step": round(e2e_rows_ms / args.steps, 4),
+                                         "h2d_bytes_per_step": rows_bytes, "h2d_gb_per_s_isolated": round(h2d_gbs, 2),
+                                         "note": "the same loop shipping the fp32 feature ROWS of every batch instead of ids"}},
         "gpu_launches": launches,
         "host_enqueue_ms_per_step": round(host_enqueue_ms, 4),
         "clocks": clocks,

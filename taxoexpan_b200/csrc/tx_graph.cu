@@ -211,6 +211,27 @@ __global__ void __launch_bounds__(1024, 1) star_batch_plan_kernel(const int32_t*
   }
 }
 
+
+// out[i, :] = table[ids[i], :]: the per-step feature rows of a batch taken from the RESIDENT node-embedding table (the reference keeps
+// g_full.ndata['x'] in host memory and collates rows per egonet, dataset.py:157,429-431; here a step ships node ids, not rows).
+template <int VEC>
+__global__ void gather_rows_kernel(const float* __restrict__ table, int64_t ldt, const int32_t* __restrict__ ids, int64_t n, int d, int64_t n_table,
+                                   float* __restrict__ out, int64_t ldo) {
+  const int per_row = d / VEC;
+  const int64_t total = n * per_row;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / per_row;
+    const int c = (int)(t - i * per_row) * VEC;
+    int64_t r = ids[i];
+    r = r < 0 ? 0 : (r >= n_table ? n_table - 1 : r);      // ids are validated by the caller; never read out of bounds
+    if (VEC == 4) {
+      *reinterpret_cast<float4*>(out + i * ldo + c) = __ldg(reinterpret_cast<const float4*>(table + r * ldt + c));
+    } else {
+      out[i * ldo + c] = __ldg(table + r * ldt + c);
+    }
+  }
+}
+
 }  // namespace tx
 
 using namespace tx;
@@ -288,6 +309,20 @@ int tx_star_batch_structure(const int32_t* n_gp, const int32_t* n_sib, const int
   star_batch_structure_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n_gp, n_sib, node_off, edge_off, (int)n_graphs, pos, src,
                                                                      dst, in_ptr, in_src, in_eid, out_ptr, out_dst, out_slot);
   TX_LAUNCH_CHECK("tx_star_batch_structure");
+  return TX_OK;
+}
+
+int tx_gather_rows(const float* table, int64_t ldt, int64_t n_table, const int32_t* ids, int64_t n, int64_t d, float* out, int64_t ldo,
+                   void* stream) {
+  TX_REQUIRE(table && ids && out && n >= 0 && d > 0 && n_table > 0 && ldt >= d && ldo >= d && d < INT32_MAX, "gather_rows: bad arguments");
+  if (n == 0) return TX_OK;
+  const bool vec = d % 4 == 0 && ldt % 4 == 0 && ldo % 4 == 0 && aligned16(table) && aligned16(out);
+  const int64_t total = n * (vec ? d / 4 : d);
+  int64_t grid = (total + 255) / 256;
+  if (grid > (int64_t)kNumSms * 16) grid = (int64_t)kNumSms * 16;
+  if (vec) gather_rows_kernel<4><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(table, ldt, ids, n, (int)d, n_table, out, ldo);
+  else gather_rows_kernel<1><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(table, ldt, ids, n, (int)d, n_table, out, ldo);
+  TX_LAUNCH_CHECK("tx_gather_rows");
   return TX_OK;
 }
 

@@ -414,6 +414,28 @@ def _reduce_partials(lib, partial: torch.Tensor, n_blocks: int, m_len: int) -> t
     return out
 
 
+def gather_rows(table: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+    """x[i] = table[ids[i]]: the feature rows of a batch from the node-embedding table kept RESIDENT on the device (tx_gather_rows), so
+    a training step ships node ids instead of rows (the reference collates rows of g_full.ndata['x'] on the host per egonet,
+    data_loader/dataset.py:157,429-431).  ids: int32 / int64 device tensor; the table carries no gradient (trainer.py:48 never asks
+    for one)."""
+    lib = _lib.load()
+    _check_cuda(table, "feature table")
+    if table.dim() != 2 or table.stride(1) != 1:
+        raise ValueError("gather_rows: the table must be a row-major 2-D tensor")
+    if ids.device != table.device:
+        raise ValueError("gather_rows: ids must live on the table's device")
+    ids32 = ids if ids.dtype == torch.int32 else ids.to(torch.int32)
+    ids32 = ids32.contiguous()
+    n, d = int(ids32.numel()), int(table.shape[1])
+    out = torch.empty((n, d), dtype=torch.float32, device=table.device)
+    if n == 0:
+        return out
+    with device_guard(table.device):
+        check(lib.tx_gather_rows(ptr(table), table.stride(0), table.shape[0], ptr(ids32), n, d, ptr(out), d, current_stream()), "tx_gather_rows")
+    return out
+
+
 def dropout_keep_mask(seed: int, stream_id: int, first_index: int, n: int, p: float, device) -> torch.Tensor:
     """The exact keep-mask (uint8, 1 = keep) the kernels use; lets the CPU oracle replay a dropout run."""
     lib = _lib.load()

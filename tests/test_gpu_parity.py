@@ -155,6 +155,19 @@ def test_star_batch_plan_tables_are_bit_exact():
     assert st.star[2] == tx.graph.STAR_CHUNK and st.star_bwd[2] == tx.graph.STAR_BWD_CHUNK
 
 
+@pytest.mark.parametrize("d", [250, 13])
+def test_gather_rows_is_bit_exact(d):
+    g = torch.Generator().manual_seed(d)
+    table = torch.randn(1000, d, generator=g).to(dev())
+    ids = torch.randint(0, 1000, (4097,), generator=g)
+    out = txf.gather_rows(table, ids.to(dev()))
+    assert torch.equal(out, table[ids.to(dev())])
+    wide = torch.randn(1000, 256, generator=g).to(dev())
+    out = txf.gather_rows(wide[:, :252], ids.to(dev()).to(torch.int32))          # a strided view of a wider table
+    assert torch.equal(out, wide[:, :252][ids.to(dev())])
+    assert txf.gather_rows(table, torch.zeros(0, dtype=torch.int32, device=dev())).shape == (0, d)
+
+
 def test_general_csr_build_is_bit_exact():
     rng = np.random.default_rng(0)
     n, e = 1000, 7000
