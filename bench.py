@@ -813,7 +813,9 @@ def run_b200(args, rank, world, local_rank):
             traffic = tj.get("per_launch_bytes", {})
     for r in rl:
         r["traffic"] = traffic.get(r["kernel"])
-    dom = max(rl, key=lambda r: r["ms"]) if rl else None
+    # the dominant HBM kernel = the fused gather-attend-aggregate launch that moves the most algorithmic bytes (the layer-0 backward: it
+    # is also the longest of the four; roofline_all lists every launch)
+    dom = max(rl, key=lambda r: r["bytes"]) if rl else None
     roofline = None
     if dom:
         roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": round(dom["achieved"], 1), "peak": hbm_peak,

@@ -256,6 +256,24 @@ __global__ void __launch_bounds__(256, TX_STAR_MIN_BLOCKS) gat_star_fwd_kernel(c
     float a1a, a2a;
     star_dots<NV>(ra, s_l, s_r, lane, a1a, a2a);
     float m = -INFINITY, l = 0.f, s_mine = 0.f, kw_mine = 1.f;     // softmax statistics over the anchor's in-edges (chunk 0 only)
+    // attention-dropout weight of ONE in-edge of the item per lane (one hash per lane instead of one per row, head and WARP: the
+    // row-by-row hashes were 9 % of the kernel's instructions).  chunk 0: [gp self loops (a) | gp -> anchor (a) | anchor self |
+    // (anchor -> sibling, sibling self) x siblings of the chunk]; chunk c: the sibling pairs only
+    const int e_sib0 = ck.c == 0 ? 2 * a + 1 : 0;
+    const bool lanes_kw = e_sib0 + 2 * (k1 - k0) <= 32;
+    float kw_lane = 1.f;
+    if (attn_drop && lanes_kw) {
+      int eid = -1;
+      if (ck.c == 0 && lane < a) eid = self0 + lane;
+      else if (ck.c == 0 && lane < 2 * a) eid = q + lane - a;
+      else if (ck.c == 0 && lane == 2 * a) eid = self0 + a;
+      else if (lane >= e_sib0 && lane < e_sib0 + 2 * (k1 - k0)) {
+        const int mm = k0 + ((lane - e_sib0) >> 1);
+        eid = ((lane - e_sib0) & 1) ? self0 + a + 1 + mm : q + a + mm;
+      }
+      if (eid >= 0) kw_lane = keepw(eid);
+    }
+    auto kw_of = [&](int idx, int eid) -> float { return lanes_kw ? __shfl_sync(0xffffffffu, kw_lane, idx) : keepw(eid); };
 
     for (int j = j0; j < j1; ++j) {
       const bool is_anchor = j == a, is_sib = j > a;
@@ -270,12 +288,13 @@ __global__ void __launch_bounds__(256, TX_STAR_MIN_BLOCKS) gat_star_fwd_kernel(c
         star_load_row<NV>(base + (int64_t)(o + j) * p.ldf, lane, D, r);
         star_dots<NV>(r, s_l, s_r, lane, a1r, a2r);
       }
-      const float kw_self = keepw(self0 + j);                        // self loop of local row j: edge id self0 + j
+      // self loop of local row j (edge id self0 + j): lane j (gp), 2a (anchor) or the sibling's second slot
+      const float kw_self = kw_of(is_sib ? e_sib0 + 2 * (j - a - 1 - k0) + 1 : (is_anchor ? 2 * a : j), self0 + j);
       const float s_self = lrelu(a1r + a2r);
       if (!is_sib) {
         // in-edge number min(j, a) of the anchor: gp_j -> anchor (edge id q + j) or the anchor's self loop
         const float sv = is_anchor ? s_self : lrelu(a1r + a2a);
-        const float kw = is_anchor ? kw_self : keepw(q + j);
+        const float kw = is_anchor ? kw_self : kw_of(a + j, q + j);
         if (lane == (j & 31)) { s_mine = sv; kw_mine = kw; }
         if (deg > 32 && lane == 0) p.elog[(int64_t)(q + a + j) * H + h] = sv;
         const float m_new = fmaxf(m, sv);
@@ -340,7 +359,7 @@ __global__ void __launch_bounds__(256, TX_STAR_MIN_BLOCKS) gat_star_fwd_kernel(c
       } else {
         // sibling k = j - a - 1: in-edges {anchor -> sib (edge id q + a + k = q + j - 1), self loop}; slots q + 2a + 1 + 2k, + 1
         const float s1 = lrelu(a1a + a2r);
-        const float kw1 = keepw(q + j - 1);
+        const float kw1 = kw_of(e_sib0 + 2 * (j - a - 1 - k0), q + j - 1);
         const float mx = fmaxf(s1, s_self);
         const float e1 = expf(s1 - mx), e2 = expf(s_self - mx);
         const float inv = 1.f / (e1 + e2);
