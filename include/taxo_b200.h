@@ -78,7 +78,7 @@ int tx_star_batch_structure(const int32_t* n_gp, const int32_t* n_sib, const int
  * (the reference collates them per egonet from g_full.ndata['x'] on the host, data_loader/dataset.py:157,429-431). */
 int tx_gather_rows(const float* table, int64_t ldt, int64_t n_table, const int32_t* ids, int64_t n, int64_t d, float* out, int64_t ldo,
                    void* stream);
-/* The plan of a star-egonet batch from the counts alone (one launch): node_off / edge_off [G + 1] (exclusive scans of n = n_gp + 1 + n_sib
+/* The plan of a star-egonet batch from the counts alone (one launch; egonets in size-class order, longest work items first): node_off / edge_off [G + 1] (exclusive scans of n = n_gp + 1 + n_sib
  * and 2 n - 1, the layout of dataset.py:404-437 batched as data_loaders.py:25 does) and the work-item tables of tx_gat_star_fwd /
  * tx_gat_star_bwd: one 16-byte record {first node, first edge, n_gp | chunk << 24, n_sib} per (egonet, chunk of chunk_fwd resp.
  * chunk_bwd siblings), sum_k max(1, ceil(n_sib_k / chunk)) records each (the caller sizes them; either table may be NULL). */

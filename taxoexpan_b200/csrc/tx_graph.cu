@@ -146,29 +146,63 @@ __global__ void __launch_bounds__(256) star_batch_structure_kernel(
 
 // Plan of a star-egonet batch from the per-egonet counts alone (one CTA, tiles of 1024 egonets): node / edge offsets (exclusive scans of
 // n = a + 1 + s and e = 2 n - 1) and the work-item tables of the star kernels - one 16-byte record {first node, first edge,
-// n_gp | chunk << 24, n_sib} per (egonet, chunk of C siblings), C = chunk_fwd for tx_gat_star_fwd and chunk_bwd for tx_gat_star_bwd; an
-// egonet's records are consecutive.  Moves ~0.4 ms of numpy (two cumsums, two row-repeats per table) per batch off the host.
+// n_gp | chunk << 24, n_sib} per (egonet, chunk of C siblings), C = chunk_fwd for tx_gat_star_fwd and chunk_bwd for tx_gat_star_bwd.  An
+// egonet's records are consecutive; the EGONETS are ordered by size class - more than C siblings first, then 1..C siblings, then none
+// (stable inside a class) - so that the work queues of the star kernels hand out their longest items first and the last warps to
+// finish hold items of a few rows, not of 17 (the tail was 27 % of the output layer's backward).  Moves ~0.4 ms of numpy (two cumsums,
+// two row-repeats per table) per batch off the host.
 __global__ void __launch_bounds__(1024, 1) star_batch_plan_kernel(const int32_t* __restrict__ n_gp, const int32_t* __restrict__ n_sib, int G,
                                                                    int chunk_fwd, int chunk_bwd, int32_t* __restrict__ node_off,
                                                                    int32_t* __restrict__ edge_off, int4* __restrict__ tasks_fwd,
                                                                    int4* __restrict__ tasks_bwd) {
-  __shared__ int s_warp[3][32];
-  __shared__ int s_carry[3];
+  constexpr int NQ = 7;                                   // scanned quantities: nodes, records of the 3 classes x {fwd, bwd}
+  __shared__ int s_warp[NQ][32];
+  __shared__ int s_carry[NQ];
+  __shared__ int s_tot[NQ];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (threadIdx.x < 3) s_carry[threadIdx.x] = 0;
-  __syncthreads();
-  for (int base = 0; base < G; base += 1024) {
-    const int k = base + threadIdx.x;
-    int a = 0, s = 0, v[3] = {0, 0, 0};
+  auto cls = [](int s, int chunk) -> int { return s > chunk ? 0 : (s > 0 ? 1 : 2); };
+  auto values = [&](int k, int& a, int& s, int (&v)[NQ]) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) v[q] = 0;
+    a = 0; s = 0;
     if (k < G) {
       a = n_gp[k]; s = n_sib[k];
       v[0] = a + 1 + s;
-      v[1] = tasks_fwd ? max(1, (s + chunk_fwd - 1) / chunk_fwd) : 0;
-      v[2] = tasks_bwd ? max(1, (s + chunk_bwd - 1) / chunk_bwd) : 0;
+      if (tasks_fwd) v[1 + cls(s, chunk_fwd)] = max(1, (s + chunk_fwd - 1) / chunk_fwd);
+      if (tasks_bwd) v[4 + cls(s, chunk_bwd)] = max(1, (s + chunk_bwd - 1) / chunk_bwd);
     }
-    int incl[3];
+  };
+  // ---- pass 1: records per class (the classes' base offsets in the tables) ----
+  if (threadIdx.x < NQ) { s_carry[threadIdx.x] = 0; s_tot[threadIdx.x] = 0; }
+  __syncthreads();
+  {
+    int acc[NQ];
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
+    for (int q = 0; q < NQ; ++q) acc[q] = 0;
+    for (int k = threadIdx.x; k < G; k += 1024) {
+      int a, s, v[NQ];
+      values(k, a, s, v);
+#pragma unroll
+      for (int q = 1; q < NQ; ++q) acc[q] += v[q];
+    }
+#pragma unroll
+    for (int q = 1; q < NQ; ++q) {
+      int x = acc[q];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      if (lane == 0) atomicAdd(&s_tot[q], x);            // integer sums: order does not matter
+    }
+  }
+  __syncthreads();
+  const int base_f[3] = {0, s_tot[1], s_tot[1] + s_tot[2]};
+  const int base_b[3] = {0, s_tot[4], s_tot[4] + s_tot[5]};
+  // ---- pass 2: exclusive scans, tile by tile ----
+  for (int base = 0; base < G; base += 1024) {
+    const int k = base + threadIdx.x;
+    int a, s, v[NQ], incl[NQ];
+    values(k, a, s, v);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
       int x = v[q];
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -179,7 +213,7 @@ __global__ void __launch_bounds__(1024, 1) star_batch_plan_kernel(const int32_t*
       if (lane == 31) s_warp[q][wid] = x;
     }
     __syncthreads();
-    if (wid < 3) {
+    if (wid < NQ) {
       int x = s_warp[wid][lane];
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -189,20 +223,22 @@ __global__ void __launch_bounds__(1024, 1) star_batch_plan_kernel(const int32_t*
       s_warp[wid][lane] = x;                                // inclusive scan of the warp totals
     }
     __syncthreads();
-    int excl[3];
-#pragma unroll
-    for (int q = 0; q < 3; ++q) excl[q] = s_carry[q] + (wid ? s_warp[q][wid - 1] : 0) + incl[q] - v[q];
     if (k < G) {
-      const int o = excl[0], e = 2 * o - k;                // sum of (2 n - 1) over the earlier egonets
+      auto excl = [&](int q) -> int { return s_carry[q] + (wid ? s_warp[q][wid - 1] : 0) + incl[q] - v[q]; };
+      const int o = excl(0), e = 2 * o - k;                // sum of (2 n - 1) over the earlier egonets
       node_off[k] = o;
       edge_off[k] = e;
-      if (tasks_fwd)
-        for (int c = 0; c < v[1]; ++c) tasks_fwd[excl[1] + c] = make_int4(o, e, a | (c << 24), s);
-      if (tasks_bwd)
-        for (int c = 0; c < v[2]; ++c) tasks_bwd[excl[2] + c] = make_int4(o, e, a | (c << 24), s);
+      if (tasks_fwd) {
+        const int c3 = cls(s, chunk_fwd), first = base_f[c3] + excl(1 + c3), cnt = v[1 + c3];
+        for (int c = 0; c < cnt; ++c) tasks_fwd[first + c] = make_int4(o, e, a | (c << 24), s);
+      }
+      if (tasks_bwd) {
+        const int c3 = cls(s, chunk_bwd), first = base_b[c3] + excl(4 + c3), cnt = v[4 + c3];
+        for (int c = 0; c < cnt; ++c) tasks_bwd[first + c] = make_int4(o, e, a | (c << 24), s);
+      }
     }
     __syncthreads();
-    if (threadIdx.x < 3) s_carry[threadIdx.x] += s_warp[threadIdx.x][31];
+    if (threadIdx.x < NQ) s_carry[threadIdx.x] += s_warp[threadIdx.x][31];
     __syncthreads();
   }
   if (threadIdx.x == 0) {
@@ -210,7 +246,6 @@ __global__ void __launch_bounds__(1024, 1) star_batch_plan_kernel(const int32_t*
     edge_off[G] = 2 * s_carry[0] - G;
   }
 }
-
 
 // out[i, :] = table[ids[i], :]: the per-step feature rows of a batch taken from the RESIDENT node-embedding table (the reference keeps
 // g_full.ndata['x'] in host memory and collates rows per egonet, dataset.py:157,429-431; here a step ships node ids, not rows).

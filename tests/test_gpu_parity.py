@@ -146,9 +146,12 @@ def test_star_batch_plan_tables_are_bit_exact():
     edge_off = np.concatenate([[0], np.cumsum(2 * n - 1)])
     assert np.array_equal(st.node_off.cpu().numpy(), node_off) and np.array_equal(st.counts[3].cpu().numpy(), edge_off)
     for (tab, n_tasks, chunk) in (st.star, st.star_bwd):
-        n_chunks = np.maximum((n_sib + chunk - 1) // chunk, 1)
-        assert n_tasks == int(n_chunks.sum())
-        eg = np.repeat(np.arange(len(n)), n_chunks)
+        n_chunks_all = np.maximum((n_sib + chunk - 1) // chunk, 1)
+        assert n_tasks == int(n_chunks_all.sum())
+        # egonets in size-class order (more than `chunk` siblings, 1..chunk siblings, none; stable), their chunk records consecutive
+        order = np.argsort(np.where(n_sib > chunk, 0, np.where(n_sib > 0, 1, 2)), kind="stable")
+        n_chunks = n_chunks_all[order]
+        eg = np.repeat(order, n_chunks)
         c = np.arange(n_tasks) - np.repeat(np.cumsum(n_chunks) - n_chunks, n_chunks)
         want = np.stack([node_off[eg], edge_off[eg], n_gp[eg] | (c << 24), n_sib[eg]], 1).astype(np.int32)
         assert np.array_equal(tab.cpu().numpy().reshape(-1, 4), want)
