@@ -175,7 +175,7 @@ int tx_gat_layer_fwd(const tx_gat_layer_desc* d, const float* z, int64_t ldz, co
   { ProfScope ps("tx_split_f16_weight", d->tag, st);
     TX_SUB(tx_split_f16_weight(d->weight, d->ldw, F, K, L.w_hi, L.w_lo, r8(K), L.wt_hi, L.wt_lo, r8(F), L.w_scal, L.w_scal + 2, stream)); }
   S.wt_hi = L.wt_hi; S.wt_lo = L.wt_lo; S.w_scale = L.w_scal + 2; S.ldwt = r8(F);
-  if (cudaMemsetAsync(L.ft_amax, 0, sizeof(float), st) != cudaSuccess) { set_error("gat_layer_fwd: memset failed"); return TX_ERR_CUDA; }
+  // (tx_gemm_nt_f16x3 clears its amax_out itself)
   { ProfScope ps("gemm_fwd", d->tag, st);                                       // ft = fc(h), model_zoo.py:83
     TX_SUB(tx_gemm_nt_f16x3(S.z_hi, S.z_lo, S.ldz16, L.w_hi, L.w_lo, r8(K), S.z_scale, S.w_scale, L.ft, F, n, F, K, nullptr, L.ft_amax, stream)); }
   S.ft = L.ft; S.ft_amax = L.ft_amax; S.alpha = L.alpha; S.alpha_d = L.alpha_d; S.elog = L.elog;
@@ -259,7 +259,6 @@ int tx_gat_layer_bwd(const tx_gat_layer_desc* d, const tx_gat_layer_state* state
     const int64_t c0a = (c0 / 8) * 8;
     const int64_t ldz = r4(K);
     if (K > c0a) {
-      if (cudaMemsetAsync(L.dz_amax, 0, sizeof(float), st) != cudaSuccess) { set_error("gat_layer_bwd: memset failed"); return TX_ERR_CUDA; }
       tx_gemm_epilogue epi;
       const tx_gemm_epilogue* pe = nullptr;
       if (prev && prev->maskbits && c0a == 0) {

@@ -88,12 +88,14 @@ def load_raw(dir_path: str, name: str, embed_suffix: str = "", existing_partitio
     terms = _read_pairs(os.path.join(dir_path, f"{name}.terms"))
     tx_id2node = {}
     names = []
-    for tx_id, surface in terms:                       # nx.DiGraph.add_node keeps first insertion: node id = first occurrence order
-        if tx_id not in tx_id2node:
-            tx_id2node[tx_id] = len(names)
-            names.append(surface)
-        else:                                          # a repeated id overwrites the Taxon but keeps the node (dataset.py:114-116)
-            names[tx_id2node[tx_id]] = surface
+    for tx_id, surface in terms:
+        if tx_id in tx_id2node:
+            # The reference would add a SECOND graph node here (its Taxon class defines neither __eq__ nor __hash__, so
+            # nx.DiGraph.add_node(taxon) at dataset.py:114-116 never merges two lines with the same id) and node ids / edge order
+            # would depend on that accident.  No released data set repeats an id; refuse instead of guessing.
+            raise ValueError(f"{name}.terms: taxon id {tx_id!r} appears twice")
+        tx_id2node[tx_id] = len(names)
+        names.append(surface)
     tx_ids = [None] * len(names)
     for k, v in tx_id2node.items():
         tx_ids[v] = k
@@ -148,12 +150,25 @@ class _Stub:
         self.__dict__.update(state if isinstance(state, dict) else {"state": state})
 
 
+# globals a reference checkpoint legitimately needs: tensor / storage rebuilders, OrderedDict, numpy scalars.  Everything else in the
+# pickle (the reference's ConfigParser, loggers, pathlib objects ...) is replaced by an inert stub: loading a downloaded checkpoint must
+# not import - i.e. execute - arbitrary modules, and only state_dict / epoch / monitor_best are used anyway.
+_SAFE_GLOBALS = {
+    ("collections", "OrderedDict"), ("torch._utils", "_rebuild_tensor_v2"), ("torch._utils", "_rebuild_parameter"),
+    ("torch._utils", "_rebuild_tensor"), ("torch", "Size"), ("torch", "device"), ("torch", "dtype"),
+    ("torch.serialization", "_get_layout"), ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"),
+    ("numpy", "dtype"), ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"), ("numpy", "ndarray"),
+    ("builtins", "set"), ("builtins", "frozenset"), ("builtins", "dict"), ("builtins", "list"), ("builtins", "tuple"),
+    ("builtins", "int"), ("builtins", "float"), ("builtins", "str"), ("builtins", "bool"), ("builtins", "bytes"),
+}
+
+
 class _TolerantUnpickler(pickle.Unpickler):
     def find_class(self, module, name):
-        try:
+        if (module, name) in _SAFE_GLOBALS or (module == "torch" and name.endswith("Storage")) or \
+                (module == "torch" and name in ("float32", "float64", "float16", "bfloat16", "int64", "int32", "int16", "int8", "uint8", "bool")):
             return super().find_class(module, name)
-        except (ImportError, AttributeError):
-            return type(name, (_Stub,), {})
+        return type(name, (_Stub,), {})
 
 
 class _TolerantPickle:

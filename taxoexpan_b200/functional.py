@@ -478,6 +478,8 @@ class ConcatPosDropout(Function):
         if not (need_x or need_tab):
             return None, None, None, None, None, None
         dz = _rowmajor(dz)
+        if n > 1 and dz.stride(0) != ldz:
+            dz = dz.contiguous()              # the keep-mask counters are indexed with the forward's row pitch ldz
         if not need_x:
             # x carries no gradient (the usual case, trainer.py:48): only d(position table) = sum over rows of the kept,
             # rescaled position columns is needed - one read of [N, pos_dim] instead of a rescale of the whole d(z)
@@ -802,6 +804,8 @@ class GatLayer(Function):
                 with device_guard(dev):
                     Stats.sync_native_profiling()
                     dout = _rowmajor(dout)
+                    if cfg.hidden and n > 1 and dout.stride(0) != round4(F_ + pd):
+                        dout = dout.contiguous()  # the dropout counters of the forward epilogue are indexed with ITS row pitch
                     ldg = dout.stride(0) if n > 1 else dout.shape[1]
                     need_tab = cfg.hidden and ctx.needs_input_grad[4] and pd > 0
                     need_z = ctx.needs_input_grad[0]
@@ -846,6 +850,8 @@ class GatLayer(Function):
             stream = current_stream()
             Stats.tag = cfg.tag
             dout = _rowmajor(dout)
+            if cfg.hidden and n > 1 and dout.stride(0) != round4(F_ + pd):
+                dout = dout.contiguous()      # the dropout counters of the forward epilogue are indexed with ITS row pitch
             ldg = dout.stride(0) if n > 1 else dout.shape[1]
             need_tab = cfg.hidden and ctx.needs_input_grad[4] and pd > 0
             nb = int(lib.tx_row_blocks(n))
@@ -853,6 +859,8 @@ class GatLayer(Function):
             dft16 = None
             ds = torch.empty(st.e * H, **f32)
             da2 = torch.empty(n * H, **f32)
+            hand = st._dh_bound               # the readout's hand-over is consumed (or dropped) by the FIRST layer backward after it
+            st._dh_bound = None
             if ctx.fused:
                 # g is read straight from d(z_next); dropout / leaky-relu derivative rebuilt from the forward's bit-planes
                 if need_tab:
@@ -876,8 +884,6 @@ class GatLayer(Function):
                         #   |sum_i alpha~_ij g_i| <= outdeg max|g| / (1 - p_attn),  |d alpha~| = |<g_i, ft_j>| <= D max|g| max|ft|,
                         #   |ds| <= 2 |d alpha~| / (1 - p_attn),  |da1_j| <= outdeg |ds|,  |da2_i| <= |ds|
                         # (rigorous, ~2^13 above the true maximum; the star backward tries DFT_OPTIMISM x max|g| first, see above)
-                        hand = st._dh_bound
-                        st._dh_bound = None
                         if cfg.out_link is not None and cfg.out_link.dz_amax is not None and pre:
                             g_amax = cfg.out_link.dz_amax                 # published by the d(z) GEMM epilogue of the layer above
                         elif not cfg.hidden and hand is not None and hand[0] == dout.data_ptr():
@@ -1209,6 +1215,7 @@ class Readout(Function):
             check(lib.tx_readout_fwd(kind, ptr(h), h.stride(0) if n > 1 else D, ptr(pos32), ptr(w), ptr(st.node_off), st.g, D,
                                      ptr(hg), width, current_stream()), "tx_readout_fwd")
         ctx.st, ctx.kind = st, kind
+        st._dh_bound = None            # a bound left behind by an earlier backward on this structure must never be picked up
         ctx.wshape = None if pos_weight is None else pos_weight.shape
         ctx.save_for_backward(h, hg, w, pos32)
         return hg

@@ -194,9 +194,13 @@ def taxonomy_masks(tax: TaxonomyCSR, nodes: Sequence[int], roots: Sequence[int])
 
 class NegativeSampler:
     """dataset.py:285-287,334-381: negative anchors come from a queue (train ids x 5) walked by a pointer shared by all queries and
-    reshuffled with `random.shuffle` whenever it is exhausted; positions in the query's mask are skipped.  Same sequence as the
-    reference for the same `random.Random` state (the reference uses the module-level generator); the membership test runs on
-    sorted mask arrays instead of Python sets."""
+    reshuffled with `random.shuffle` whenever it is exhausted; positions in the query's mask are skipped.  The queue walk gives the same
+    sequence as the reference for the same `random.Random` state AS LONG AS no anchor of the run has more than `expand_factor`
+    children: the reference draws the sub-sampled siblings of such an anchor with `random.choices` from the SAME module-level generator
+    (`_get_subgraph`, dataset.py:416-424), interleaved with these shuffles, while the sibling draws here are counter-based
+    (`counter_draws`) and leave the generator alone - after the first large anchor the reference's queue order moves on, this one's does
+    not (tests/test_sampler_cpu.py::test_negative_queue_diverges_from_the_reference_after_a_large_anchor documents it).  The
+    membership test runs on sorted mask arrays instead of Python sets."""
 
     def __init__(self, train_node_ids: Sequence[int], node2masks: Dict[int, np.ndarray], rng: Optional[random.Random] = None):
         self.queue = list(train_node_ids) * 5

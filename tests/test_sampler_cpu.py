@@ -197,3 +197,23 @@ def test_chunk_by_node_limit_matches_the_test_stage_collate():
     for nodes in cases:
         for limit in (100000, 1000, 57):
             assert sampler.chunk_by_node_limit(nodes, limit) == orc.large_batch_chunks(nodes, limit), (nodes[:8], limit)
+
+
+def test_negative_queue_diverges_from_the_reference_after_a_large_anchor():
+    """Documents a deliberate difference: the reference draws the sub-sampled siblings of an anchor with more than
+    `expand_factor` children with random.choices from the SAME module-level generator that shuffles the negative queue
+    (dataset.py:416-424 interleaved with :340-381), so every such draw moves its queue order on; the sampler's sibling draws are
+    counter-based and leave the generator alone.  Identical queue walks are therefore guaranteed only while no anchor is sub-sampled."""
+    import random
+    train = list(range(40))
+    masks = {0: np.array([0])}
+    sets = {0: {0}}
+    a = sampler.NegativeSampler(train, masks, random.Random(7))
+    b = orc.NegativeQueueOracle(train, sets, random.Random(7))
+    for _ in range(3):
+        assert a.exactly_k(0, 31) == b.exactly_k(0, 31)              # no sub-sampled anchor so far: same walk
+    b.rng.choices(range(100), k=50)                                   # the reference samples a large anchor's siblings here
+    diverged = False
+    for _ in range(12):                                               # crosses the next reshuffle of the 200-entry queue
+        diverged |= a.exactly_k(0, 31) != b.exactly_k(0, 31)
+    assert diverged
