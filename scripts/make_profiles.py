@@ -81,11 +81,13 @@ with open(os.path.join(DST, "r2_ncu_full_summary.csv"), "w", newline="") as f:
         name = r[hdr.index("Kernel Name")]
         dr = to_bytes(r[hdr.index("dram__bytes_read.sum")], units[hdr.index("dram__bytes_read.sum")])
         dw = to_bytes(r[hdr.index("dram__bytes_write.sum")], units[hdr.index("dram__bytes_write.sum")])
-        per_kernel[name.split("(")[0]].append((float(r[hdr.index("gpu__time_duration.sum")].replace(",", "")), dr + dw))
+        t_unit = units[hdr.index("gpu__time_duration.sum")]
+        t_us = float(r[hdr.index("gpu__time_duration.sum")].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(t_unit, 1.0)
+        per_kernel[name.split("(")[0]].append((t_us, dr + dw))
 traffic = {}
 for key, label in (("gat_star_bwd_kernel", "tx_gat_star_bwd"), ("gat_bwd_staged_kernel", "tx_gat_fused_bwd_staged"),
                    ("gat_fused_fwd_kernel", "tx_gat_fused_fwd"), ("gat_star_fwd_kernel", "tx_gat_star_fwd")):
-    ls = [t for k, v in per_kernel.items() if key in k for t in v if t[0] > 20000.0]      # all template instances (ns; the star backward's
+    ls = [t for k, v in per_kernel.items() if key in k for t in v if t[0] > 20.0]      # all template instances (us; the star backward's
     # second launch, which exits at once unless the fp16-range flag is set, is not a traffic sample)
     ls = sorted(ls, key=lambda t: -t[1])
     if ls and ls[0][1] > 2.5 * ls[-1][1]:                          # L0 launches move ~4x the bytes of L1 launches

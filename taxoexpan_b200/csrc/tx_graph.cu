@@ -156,34 +156,24 @@ __global__ void __launch_bounds__(1024, 1) star_batch_plan_kernel(const int32_t*
                                                                    int32_t* __restrict__ edge_off, int4* __restrict__ tasks_fwd,
                                                                    int4* __restrict__ tasks_bwd) {
   constexpr int NQ = 7;                                   // scanned quantities: nodes, records of the 3 classes x {fwd, bwd}
+  constexpr int PER = 8;                                  // consecutive egonets per thread and round (8192 per round)
   __shared__ int s_warp[NQ][32];
   __shared__ int s_carry[NQ];
   __shared__ int s_tot[NQ];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   auto cls = [](int s, int chunk) -> int { return s > chunk ? 0 : (s > 0 ? 1 : 2); };
-  auto values = [&](int k, int& a, int& s, int (&v)[NQ]) {
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) v[q] = 0;
-    a = 0; s = 0;
-    if (k < G) {
-      a = n_gp[k]; s = n_sib[k];
-      v[0] = a + 1 + s;
-      if (tasks_fwd) v[1 + cls(s, chunk_fwd)] = max(1, (s + chunk_fwd - 1) / chunk_fwd);
-      if (tasks_bwd) v[4 + cls(s, chunk_bwd)] = max(1, (s + chunk_bwd - 1) / chunk_bwd);
-    }
-  };
-  // ---- pass 1: records per class (the classes' base offsets in the tables) ----
   if (threadIdx.x < NQ) { s_carry[threadIdx.x] = 0; s_tot[threadIdx.x] = 0; }
   __syncthreads();
-  {
+  // ---- pass 1 (only when the batch does not fit one round): records per class = the classes' base offsets in the tables ----
+  const bool one_round = G <= 1024 * PER;
+  if (!one_round) {
     int acc[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) acc[q] = 0;
     for (int k = threadIdx.x; k < G; k += 1024) {
-      int a, s, v[NQ];
-      values(k, a, s, v);
-#pragma unroll
-      for (int q = 1; q < NQ; ++q) acc[q] += v[q];
+      const int s = n_sib[k];
+      if (tasks_fwd) acc[1 + cls(s, chunk_fwd)] += max(1, (s + chunk_fwd - 1) / chunk_fwd);
+      if (tasks_bwd) acc[4 + cls(s, chunk_bwd)] += max(1, (s + chunk_bwd - 1) / chunk_bwd);
     }
 #pragma unroll
     for (int q = 1; q < NQ; ++q) {
@@ -192,18 +182,29 @@ __global__ void __launch_bounds__(1024, 1) star_batch_plan_kernel(const int32_t*
       for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
       if (lane == 0) atomicAdd(&s_tot[q], x);            // integer sums: order does not matter
     }
+    __syncthreads();
   }
-  __syncthreads();
-  const int base_f[3] = {0, s_tot[1], s_tot[1] + s_tot[2]};
-  const int base_b[3] = {0, s_tot[4], s_tot[4] + s_tot[5]};
-  // ---- pass 2: exclusive scans, tile by tile ----
-  for (int base = 0; base < G; base += 1024) {
-    const int k = base + threadIdx.x;
-    int a, s, v[NQ], incl[NQ];
-    values(k, a, s, v);
+  // ---- pass 2: every thread owns PER consecutive egonets of a round: local sums, ONE block-wide scan, local prefix walk ----
+  for (int base = 0; base < G; base += 1024 * PER) {
+    const int k0 = base + threadIdx.x * PER;
+    int a[PER], s[PER], tot[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) tot[q] = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int k = k0 + i;
+      a[i] = k < G ? n_gp[k] : 0;
+      s[i] = k < G ? n_sib[k] : 0;
+      if (k < G) {
+        tot[0] += a[i] + 1 + s[i];
+        if (tasks_fwd) tot[1 + cls(s[i], chunk_fwd)] += max(1, (s[i] + chunk_fwd - 1) / chunk_fwd);
+        if (tasks_bwd) tot[4 + cls(s[i], chunk_bwd)] += max(1, (s[i] + chunk_bwd - 1) / chunk_bwd);
+      }
+    }
+    int incl[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
-      int x = v[q];
+      int x = tot[q];
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int y = __shfl_up_sync(0xffffffffu, x, o);
@@ -221,20 +222,32 @@ __global__ void __launch_bounds__(1024, 1) star_batch_plan_kernel(const int32_t*
         if (lane >= o) x += y;
       }
       s_warp[wid][lane] = x;                                // inclusive scan of the warp totals
+      if (one_round && lane == 31) s_tot[wid] = x;          // a single round: its totals ARE the class sizes
     }
     __syncthreads();
-    if (k < G) {
-      auto excl = [&](int q) -> int { return s_carry[q] + (wid ? s_warp[q][wid - 1] : 0) + incl[q] - v[q]; };
-      const int o = excl(0), e = 2 * o - k;                // sum of (2 n - 1) over the earlier egonets
-      node_off[k] = o;
-      edge_off[k] = e;
-      if (tasks_fwd) {
-        const int c3 = cls(s, chunk_fwd), first = base_f[c3] + excl(1 + c3), cnt = v[1 + c3];
-        for (int c = 0; c < cnt; ++c) tasks_fwd[first + c] = make_int4(o, e, a | (c << 24), s);
-      }
-      if (tasks_bwd) {
-        const int c3 = cls(s, chunk_bwd), first = base_b[c3] + excl(4 + c3), cnt = v[4 + c3];
-        for (int c = 0; c < cnt; ++c) tasks_bwd[first + c] = make_int4(o, e, a | (c << 24), s);
+    int run[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) run[q] = s_carry[q] + (wid ? s_warp[q][wid - 1] : 0) + incl[q] - tot[q];
+    const int base_f[3] = {0, s_tot[1], s_tot[1] + s_tot[2]};
+    const int base_b[3] = {0, s_tot[4], s_tot[4] + s_tot[5]};
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int k = k0 + i;
+      if (k < G) {
+        const int o = run[0], e = 2 * o - k;               // sum of (2 n - 1) over the earlier egonets
+        node_off[k] = o;
+        edge_off[k] = e;
+        run[0] += a[i] + 1 + s[i];
+        if (tasks_fwd) {
+          const int c3 = cls(s[i], chunk_fwd), cnt = max(1, (s[i] + chunk_fwd - 1) / chunk_fwd), first = base_f[c3] + run[1 + c3];
+          for (int c = 0; c < cnt; ++c) tasks_fwd[first + c] = make_int4(o, e, a[i] | (c << 24), s[i]);
+          run[1 + c3] += cnt;
+        }
+        if (tasks_bwd) {
+          const int c3 = cls(s[i], chunk_bwd), cnt = max(1, (s[i] + chunk_bwd - 1) / chunk_bwd), first = base_b[c3] + run[4 + c3];
+          for (int c = 0; c < cnt; ++c) tasks_bwd[first + c] = make_int4(o, e, a[i] | (c << 24), s[i]);
+          run[4 + c3] += cnt;
+        }
       }
     }
     __syncthreads();

@@ -134,10 +134,11 @@ def test_star_structure_closed_form_is_bit_exact():
     assert np.array_equal(st.pos.cpu().numpy(), og.pos.numpy())
 
 
-def test_star_batch_plan_tables_are_bit_exact():
-    """tx_star_batch_plan (offsets + the work-item tables of the star kernels, built on the GPU from the counts) against numpy, on a
-    batch larger than one scan tile with roots, leaves, 50-sibling egonets and > 32 grand-parents."""
-    shapes = tx.synth.sample_shapes(96, 31, "mag-cs", seed=8)                     # 3072 egonets: three tiles of 1024
+@pytest.mark.parametrize("n_queries", [3, 96, 300, 1100])
+def test_star_batch_plan_tables_are_bit_exact(n_queries):
+    """tx_star_batch_plan (offsets + the work-item tables of the star kernels, built on the GPU from the counts) against numpy, with
+    roots, leaves, 50-sibling egonets and > 32 grand-parents; 300 / 1100 queries = 9 604 / 35 204 egonets: more than one round of 8192."""
+    shapes = tx.synth.sample_shapes(n_queries, 31, "mag-cs", seed=8)
     n_gp = np.concatenate([shapes.n_gp, [0, 0, 40, 1]]).astype(np.int64)
     n_sib = np.concatenate([shapes.n_sib, [0, 50, 0, 33]]).astype(np.int64)
     st = tx.EgonetBatch.from_counts(n_gp, n_sib).structure(dev())
