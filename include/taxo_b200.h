@@ -300,6 +300,19 @@ int tx_gcn_norm(const int32_t* in_ptr, int64_t n_nodes, float* norm, void* strea
 int tx_gcn_aggregate_fwd(const float* y, int64_t ldy, const float* norm, const float* bias, const int32_t* in_ptr,
                          const int32_t* in_src, int64_t n_nodes, int64_t dim, float* out, int64_t ldo,
                          const tx_gat_epilogue* epi, void* stream);
+/* The same aggregate with the fused next-layer epilogue of the GAT path: the hidden layer's output goes out as the NEXT GEMM's fp16 hi/lo
+ * operand pair [N, ld16] (x * scale = hi + lo, scale from *bound, see tx_bound_gcn; the fp32 tensor is never written) plus the sign /
+ * keep bytes (tx_gat_fused_mask_words(N, 1, dim) words; may be NULL) consumed by the next layer's d(z) GEMM epilogue
+ * (tx_gemm_epilogue), and d(y) of the backward aggregate as an fp16 pair as well (columns [dim, ld16) zero).  ldo = the LOGICAL fp32
+ * pitch round4(dim + pos_dim): it indexes the dropout counters exactly like tx_gcn_aggregate_fwd. */
+int tx_gcn_aggregate_fwd_f16(const float* y, int64_t ldy, const float* norm, const float* bias, const int32_t* in_ptr,
+                             const int32_t* in_src, int64_t n_nodes, int64_t dim, int64_t ldo, const tx_gat_epilogue* epi, void* out_hi,
+                             void* out_lo, int64_t ld16, const float* bound, float* scale_out, uint32_t* maskbits, void* stream);
+int tx_gcn_aggregate_bwd_f16(const float* g, int64_t ldg, const float* norm, const int32_t* out_ptr, const int32_t* out_dst, int64_t n_nodes,
+                             int64_t dim, void* dy_hi, void* dy_lo, int64_t ld16, const float* bound, float* scale_out, void* stream);
+/* *out = max(2 ca *a, 2 cb max|b[0..b_len)|, ct max|t[0..t_len)|): bound of a GCN epilogue's output (a = max|y|, b = bias, t = the next
+ * position table) or, with b = t = NULL, of d(y) (a = max|g|). */
+int tx_bound_gcn(const float* a, float ca, const float* b, int64_t b_len, float cb, const float* t, int64_t t_len, float ct, float* out, void* stream);
 /* dy[j,:] = norm_j * sum_out norm_dst * g[dst,:] */
 int tx_gcn_aggregate_bwd(const float* g, int64_t ldg, const float* norm, const int32_t* out_ptr,
                          const int32_t* out_dst, int64_t n_nodes, int64_t dim, float* dy, int64_t ldd, void* stream);
@@ -440,6 +453,28 @@ int tx_gat_layer_fwd(const tx_gat_layer_desc* d, const float* z, int64_t ldz, co
                      tx_gat_layer_state* state, float* out, void* stream);
 int tx_gat_layer_bwd(const tx_gat_layer_desc* d, const tx_gat_layer_state* state, const tx_gat_layer_state* prev, const float* dout,
                      int64_t ldg, const float* g_amax, void* workspace, float* dz, float* dw_ext, float* dattn, float* dtab,
+                     float** dz_amax_out, void* stream);
+/* The same for a GCN layer (GCNLayer.forward and its autograd, model/model_zoo.py:34-50 inside the stacks of :128-137,155-167): split /
+ * weight split / y = z W GEMM / bound / tx_gcn_aggregate_fwd(_f16), and d(position table), d(bias), bound, tx_gcn_aggregate_bwd_f16,
+ * dW^T (-> dwt [dim, round4(k)]) , d(z).  Layers hand each other the tx_gat_layer_state (ft = y; alpha / elog unused; heads = 1). */
+typedef struct tx_gcn_layer_desc {
+  int64_t n, k, dim, pos_dim, vocab, dz_from, max_in_deg, max_out_deg;
+  int32_t hidden;                         /* 1: hidden layer (emits the next layer's input), 0: output layer (fp32 [N, dim]) */
+  float act_slope, p_next;
+  uint64_t next_seed;
+  uint32_t next_stream;
+  const int32_t *in_ptr, *in_src, *out_ptr, *out_dst, *pos;
+  const float* norm;
+  const float* weight; int64_t ldw;       /* weight [k, dim] (torch.mm(h, W), model_zoo.py:37) */
+  const float *bias, *next_pos_table;
+  char tag[16];
+} tx_gcn_layer_desc;
+int64_t tx_gcn_layer_fwd_bytes(const tx_gcn_layer_desc* d, int32_t split_input);
+int64_t tx_gcn_layer_bwd_bytes(const tx_gcn_layer_desc* d);
+int tx_gcn_layer_fwd(const tx_gcn_layer_desc* d, const float* z, int64_t ldz, const tx_gat_layer_state* prev, void* workspace,
+                     tx_gat_layer_state* state, float* out, void* stream);
+int tx_gcn_layer_bwd(const tx_gcn_layer_desc* d, const tx_gat_layer_state* state, const tx_gat_layer_state* prev, const float* dout,
+                     int64_t ldg, const float* g_amax, void* workspace, float* dz, float* dwt, float* dbias, float* dtab,
                      float** dz_amax_out, void* stream);
 /* measurement aid (bench.py): kernel launches issued by the two calls above since the last reset, and optional CUDA-event timing of
  * each of them (creates events; read after synchronising the stream) */

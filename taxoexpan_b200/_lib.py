@@ -54,6 +54,14 @@ class GatLayerDesc(Structure):
         ("attn_r", c_void_p), ("next_pos_table", c_void_p), ("tag", ctypes.c_char * 16)]
 
 
+class GcnLayerDesc(Structure):
+    """struct tx_gcn_layer_desc"""
+    _fields_ = [(k, c_int64) for k in ("n", "k", "dim", "pos_dim", "vocab", "dz_from", "max_in_deg", "max_out_deg")] + [
+        ("hidden", c_int32), ("act_slope", c_float), ("p_next", c_float), ("next_seed", c_uint64), ("next_stream", c_uint32),
+        ("in_ptr", c_void_p), ("in_src", c_void_p), ("out_ptr", c_void_p), ("out_dst", c_void_p), ("pos", c_void_p), ("norm", c_void_p),
+        ("weight", c_void_p), ("ldw", c_int64), ("bias", c_void_p), ("next_pos_table", c_void_p), ("tag", ctypes.c_char * 16)]
+
+
 class GatLayerState(Structure):
     """struct tx_gat_layer_state"""
     _fields_ = [("z_hi", c_void_p), ("z_lo", c_void_p), ("z_scale", c_void_p), ("ldz16", c_int64),
@@ -133,10 +141,18 @@ _SIGNATURES = {
     "tx_gat_star_bwd": [P, I64, I64, F32, P, I64, P, P, P, P, P, P, I64, I64, I64, I64, I64, F32, P, P, P, P, I64, P, P, I64,
                         P, P, P, P, P, P, P, P],
     "tx_attn_grad_from_v": [P, I64, P, I64, I64, I64, I64, P, P, P, P],
+    "tx_gcn_aggregate_fwd_f16": [P, I64, P, P, P, P, I64, I64, I64, POINTER(GatEpilogue), P, P, I64, P, P, P, P],
+    "tx_gcn_aggregate_bwd_f16": [P, I64, P, P, P, I64, I64, P, P, I64, P, P, P],
+    "tx_bound_gcn": [P, F32, P, I64, F32, P, I64, F32, P, P],
     "tx_gat_layer_fwd_bytes": [POINTER(GatLayerDesc), c_int32],
     "tx_gat_layer_bwd_bytes": [POINTER(GatLayerDesc)],
     "tx_gat_layer_fwd": [POINTER(GatLayerDesc), P, I64, POINTER(GatLayerState), P, POINTER(GatLayerState), P, P],
     "tx_gat_layer_bwd": [POINTER(GatLayerDesc), POINTER(GatLayerState), POINTER(GatLayerState), P, I64, P, P, P, P, P, P,
+                         POINTER(c_void_p), P],
+    "tx_gcn_layer_fwd_bytes": [POINTER(GcnLayerDesc), c_int32],
+    "tx_gcn_layer_bwd_bytes": [POINTER(GcnLayerDesc)],
+    "tx_gcn_layer_fwd": [POINTER(GcnLayerDesc), P, I64, POINTER(GatLayerState), P, POINTER(GatLayerState), P, P],
+    "tx_gcn_layer_bwd": [POINTER(GcnLayerDesc), POINTER(GatLayerState), POINTER(GatLayerState), P, I64, P, P, P, P, P, P,
                          POINTER(c_void_p), P],
     "tx_layer_launches": [c_int32],
     "tx_prof_enable": [c_int32],
@@ -152,7 +168,7 @@ _RESTYPES = {"tx_last_error": c_char_p, "tx_target_arch": c_char_p, "tx_row_bloc
              "tx_gat_fused_mask_words": c_int64, "tx_gat_fused_mask_ld": c_int64, "tx_gat_fused_bwd_blocks": c_int64, "tx_gemm_tn_splits": c_int64,
              "tx_gat_bwd_tile_rows": c_int64, "tx_gat_bwd_num_tiles": c_int64, "tx_gat_fused_bwd_staged_blocks": c_int64,
              "tx_gemm_tn_f16_splits": c_int64, "tx_gat_star_chunk": c_int64, "tx_gat_star_max_chunks": c_int64,
-             "tx_gat_star_bwd_partial_floats": c_int64, "tx_gat_layer_fwd_bytes": c_int64, "tx_gat_layer_bwd_bytes": c_int64,
+             "tx_gat_star_bwd_partial_floats": c_int64, "tx_gat_layer_fwd_bytes": c_int64, "tx_gat_layer_bwd_bytes": c_int64, "tx_gcn_layer_fwd_bytes": c_int64, "tx_gcn_layer_bwd_bytes": c_int64,
              "tx_layer_launches": c_int64, "tx_prof_count": c_int64, "tx_prof_enable": None, "tx_prof_clear": None}
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -166,6 +182,7 @@ _NO_LAUNCH = {"tx_abi_version", "tx_last_error", "tx_target_arch", "tx_row_block
               "tx_gat_bwd_tile_rows", "tx_gat_bwd_num_tiles", "tx_gat_fused_bwd_staged_blocks", "tx_gemm_tn_f16_splits", "tx_gat_star_chunk", "tx_gat_star_max_chunks", "tx_gat_star_bwd_partial_floats",
               # the per-layer calls enqueue several kernels each: they are counted through tx_layer_launches, timed through tx_prof_*
               "tx_gat_layer_fwd_bytes", "tx_gat_layer_bwd_bytes", "tx_gat_layer_fwd", "tx_gat_layer_bwd", "tx_layer_launches",
+              "tx_gcn_layer_fwd_bytes", "tx_gcn_layer_bwd_bytes", "tx_gcn_layer_fwd", "tx_gcn_layer_bwd",
               "tx_prof_enable", "tx_prof_clear", "tx_prof_count", "tx_prof_get"}
 
 

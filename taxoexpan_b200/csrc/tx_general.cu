@@ -569,6 +569,134 @@ __global__ void __launch_bounds__(256) gcn_aggregate_bwd_kernel(const float* __r
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// GCN aggregate with the fused next-layer epilogue PGAT has (round 2): the hidden layer's output goes out as the NEXT GEMM's fp16 hi/lo
+// operand pair (the fp32 tensor is never written) together with the sign / keep bytes (1 byte per 4 columns: 4 sign bits | 4 keep
+// bits << 4, the layout of tx_gat_fused_mask_ld(1, D)) that let the next layer's d(z) GEMM epilogue apply the derivative of
+// "leaky-relu -> dropout" where the gradient is produced - no tx_epilogue_bwd pass, no clone of the gradient - and the backward
+// aggregate writes d(y) as an fp16 pair too.  Same arithmetic, dropout counters (row * ldo + col with the LOGICAL fp32 pitch ldo) and
+// reference call sites as the fp32 kernels above (model_zoo.py:39-49 followed by :164-165,37 of the next layer).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gcn_aggregate_fwd_f16_kernel(const float* __restrict__ y, int64_t ldy, const float* __restrict__ norm,
+                                                                    const float* __restrict__ bias, const int32_t* __restrict__ in_ptr,
+                                                                    const int32_t* __restrict__ in_src, int n, int D, int64_t ldo,
+                                                                    const Epilogue ep, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                                                                    int64_t ld16, const float* __restrict__ bound, float* __restrict__ scale_out,
+                                                                    uint8_t* __restrict__ mask, int mask_ld) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int nvec = D >> 2;
+  const float scale16 = f16_split_scale(__ldg(bound));
+  if (scale_out && blockIdx.x == 0 && threadIdx.x == 0) *scale_out = scale16;
+  const bool activate = ep.act_slope != 1.f;
+  for (int i = warp; i < n; i += nwarps) {
+    const int beg = __ldg(in_ptr + i), end = __ldg(in_ptr + i + 1);
+    const float ni = __ldg(norm + i);
+    const int64_t idx_base = (int64_t)i * ldo;
+    for (int c = lane; c < nvec; c += 32) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = beg; k < end; ++k) {
+        const int j = __ldg(in_src + k);
+        const float nj = __ldg(norm + j);
+        const float4 f = __ldg(reinterpret_cast<const float4*>(y + (int64_t)j * ldy + c * 4));
+        acc.x += f.x * nj; acc.y += f.y * nj; acc.z += f.z * nj; acc.w += f.w * nj;     // (y_j * norm_j) summed, model_zoo.py:39-41
+      }
+      float v[4] = {acc.x * ni, acc.y * ni, acc.z * ni, acc.w * ni};
+      if (bias) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c * 4));
+        v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+      }
+      uint32_t code = 0xF0u;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool pos = v[u] > 0.f;
+        code |= pos ? (1u << u) : 0u;
+        if (activate) v[u] = pos ? v[u] : v[u] * ep.act_slope;
+      }
+      if (ep.thr) {
+        bool keep[4];
+        drop_keep4(ep.seed, ep.stream_id, (uint64_t)((idx_base + c * 4) >> 2), ep.thr, keep);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          v[u] = keep[u] ? v[u] * ep.inv_keep : 0.f;
+          code &= keep[u] ? 0xFFu : ~(16u << u);
+        }
+      }
+      uint2 h16, l16;
+      f16_split4(make_float4(v[0], v[1], v[2], v[3]), scale16, h16, l16);
+      *reinterpret_cast<uint2*>(out_hi + (int64_t)i * ld16 + c * 4) = h16;
+      *reinterpret_cast<uint2*>(out_lo + (int64_t)i * ld16 + c * 4) = l16;
+      if (mask) mask[(int64_t)i * mask_ld + c] = (uint8_t)code;
+    }
+    // appended drop(P_next[pos_i]) and the zero padding up to ld16
+    const int pd = ep.pos_dim;
+    const float* prow = pd > 0 ? ep.next_pos_table + (int64_t)ep.pos[i] * pd : nullptr;
+    for (int c = D + lane; c < (int)ld16; c += 32) {
+      float v = 0.f;
+      if (c < D + pd) {
+        v = __ldg(prow + (c - D));
+        if (ep.thr) v = drop_keep1(ep.seed, ep.stream_id, (uint64_t)(idx_base + c), ep.thr) ? v * ep.inv_keep : 0.f;
+      }
+      const float x = fminf(fmaxf(v * scale16, -65504.f), 65504.f);
+      const __half hh = __float2half_rn(x);
+      out_hi[(int64_t)i * ld16 + c] = hh;
+      out_lo[(int64_t)i * ld16 + c] = __float2half_rn(x - __half2float(hh));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) gcn_aggregate_bwd_f16_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ norm,
+                                                                    const int32_t* __restrict__ out_ptr, const int32_t* __restrict__ out_dst,
+                                                                    int n, int D, __half* __restrict__ dy_hi, __half* __restrict__ dy_lo,
+                                                                    int64_t ld16, const float* __restrict__ bound, float* __restrict__ scale_out) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int nvec16 = (int)(ld16 >> 2);
+  const float scale16 = f16_split_scale(__ldg(bound));
+  if (scale_out && blockIdx.x == 0 && threadIdx.x == 0) *scale_out = scale16;
+  for (int j = warp; j < n; j += nwarps) {
+    const int beg = __ldg(out_ptr + j), end = __ldg(out_ptr + j + 1);
+    const float nj = __ldg(norm + j);
+    for (int c = lane; c < nvec16; c += 32) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c * 4 < D) {
+        for (int k = beg; k < end; ++k) {
+          const int i = __ldg(out_dst + k);
+          const float ni = __ldg(norm + i);
+          const float4 gv = __ldg(reinterpret_cast<const float4*>(g + (int64_t)i * ldg + c * 4));
+          acc.x = fmaf(ni, gv.x, acc.x); acc.y = fmaf(ni, gv.y, acc.y); acc.z = fmaf(ni, gv.z, acc.z); acc.w = fmaf(ni, gv.w, acc.w);
+        }
+        acc.x *= nj; acc.y *= nj; acc.z *= nj; acc.w *= nj;
+      }
+      uint2 h16, l16;
+      f16_split4(acc, scale16, h16, l16);
+      *reinterpret_cast<uint2*>(dy_hi + (int64_t)j * ld16 + c * 4) = h16;       // columns [D, ld16) are written as zeros
+      *reinterpret_cast<uint2*>(dy_lo + (int64_t)j * ld16 + c * 4) = l16;
+    }
+  }
+}
+
+// *out = max(2 ca *a, 2 cb max|b|, ct max|t|): bound of a GCN layer's epilogue output, |norm_i sum_j norm_j y_j + bias| <= sqrt(max
+// in-degree) max|y| + max|bias| <= 2 max(.., ..), and of the appended position rows
+__global__ void bound_gcn_kernel(const float* a, float ca, const float* b, int64_t nb, float cb, const float* t, int64_t nt, float ct, float* out) {
+  __shared__ float s_red[8];
+  auto block_max = [&](const float* v, int64_t len) -> float {
+    float m = 0.f;
+    for (int64_t k = threadIdx.x; k < len; k += blockDim.x) m = fmaxf(m, fabsf(v[k]));
+    m = warp_max(m);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    float r = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) r = fmaxf(r, s_red[w]);
+    return r;
+  };
+  const float mb = b ? block_max(b, nb) : 0.f, mt = t ? block_max(t, nt) : 0.f;
+  if (threadIdx.x == 0) *out = fmaxf(fmaxf(2.f * ca * *a, 2.f * cb * mb), ct * mt);
+}
+
 // =============================================================================================
 // Readout: one CTA per graph
 // =============================================================================================
@@ -1144,6 +1272,43 @@ int tx_gcn_aggregate_fwd(const float* y, int64_t ldy, const float* norm, const f
   else
     gcn_aggregate_fwd_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(y, ldy, norm, bias, in_ptr, in_src, (int)n_nodes, (int)dim, out, ldo, ep);
   TX_LAUNCH_CHECK("tx_gcn_aggregate_fwd");
+  return TX_OK;
+}
+
+int tx_gcn_aggregate_fwd_f16(const float* y, int64_t ldy, const float* norm, const float* bias, const int32_t* in_ptr,
+                             const int32_t* in_src, int64_t n_nodes, int64_t dim, int64_t ldo, const tx_gat_epilogue* epi, void* out_hi,
+                             void* out_lo, int64_t ld16, const float* bound, float* scale_out, uint32_t* maskbits, void* stream) {
+  TX_REQUIRE(dim > 0 && dim % 4 == 0 && ldy >= dim && vec4_ok(y, ldy, dim) && (!bias || aligned16(bias)), "gcn_aggregate_fwd_f16: dim % 4 == 0 and 16-byte aligned rows required");
+  TX_REQUIRE(epi && !epi->mean_heads, "gcn_aggregate_fwd_f16: hidden layers only");
+  Epilogue ep;
+  if (make_epilogue(epi, &ep) != TX_OK) return TX_ERR_INVALID_ARGUMENT;
+  TX_REQUIRE(out_hi && out_lo && bound && aligned16(out_hi) && aligned16(out_lo) && ld16 % 8 == 0 && ld16 >= dim + ep.pos_dim && ldo % 4 == 0 &&
+             ldo >= dim + ep.pos_dim, "gcn_aggregate_fwd_f16: bad output buffers");
+  if (n_nodes == 0) return TX_OK;
+  const int grid = grid_for_warps(n_nodes, 8, 8);
+  gcn_aggregate_fwd_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, ldy, norm, bias, in_ptr, in_src, (int)n_nodes, (int)dim, ldo, ep,
+                                                                      (__half*)out_hi, (__half*)out_lo, ld16, bound, scale_out,
+                                                                      reinterpret_cast<uint8_t*>(maskbits), (int)tx_gat_fused_mask_ld(1, dim));
+  TX_LAUNCH_CHECK("tx_gcn_aggregate_fwd_f16");
+  return TX_OK;
+}
+
+int tx_gcn_aggregate_bwd_f16(const float* g, int64_t ldg, const float* norm, const int32_t* out_ptr, const int32_t* out_dst, int64_t n_nodes,
+                             int64_t dim, void* dy_hi, void* dy_lo, int64_t ld16, const float* bound, float* scale_out, void* stream) {
+  TX_REQUIRE(dim > 0 && dim % 4 == 0 && ldg >= dim && vec4_ok(g, ldg, dim), "gcn_aggregate_bwd_f16: dim % 4 == 0 and 16-byte aligned rows required");
+  TX_REQUIRE(dy_hi && dy_lo && bound && aligned16(dy_hi) && aligned16(dy_lo) && ld16 % 8 == 0 && ld16 >= dim, "gcn_aggregate_bwd_f16: bad output buffers");
+  if (n_nodes == 0) return TX_OK;
+  const int grid = grid_for_warps(n_nodes, 8, 8);
+  gcn_aggregate_bwd_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, ldg, norm, out_ptr, out_dst, (int)n_nodes, (int)dim, (__half*)dy_hi,
+                                                                      (__half*)dy_lo, ld16, bound, scale_out);
+  TX_LAUNCH_CHECK("tx_gcn_aggregate_bwd_f16");
+  return TX_OK;
+}
+
+int tx_bound_gcn(const float* a, float ca, const float* b, int64_t b_len, float cb, const float* t, int64_t t_len, float ct, float* out, void* stream) {
+  TX_REQUIRE(a && out && b_len >= 0 && t_len >= 0, "bound_gcn: bad arguments");
+  bound_gcn_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(a, ca, b_len > 0 ? b : nullptr, b_len, cb, t_len > 0 ? t : nullptr, t_len, ct, out);
+  TX_LAUNCH_CHECK("tx_bound_gcn");
   return TX_OK;
 }
 

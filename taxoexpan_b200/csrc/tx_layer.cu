@@ -278,6 +278,192 @@ int tx_gat_layer_bwd(const tx_gat_layer_desc* d, const tx_gat_layer_state* state
   return TX_OK;
 }
 
+// =================================================================================================================================
+// GCN layer (model_zoo.py:34-50)
+// =================================================================================================================================
+}  // extern "C"
+
+namespace tx {
+
+struct GcnFwdLayout {
+  __half *z_hi, *z_lo; float *z_scale, *z_amax;
+  __half *w_hi, *w_lo, *wt_hi, *wt_lo; float* w_scal;
+  float *y, *y_amax; uint32_t* maskbits; __half *out_hi, *out_lo; float *out_scale, *bound;
+  size_t bytes;
+};
+static GcnFwdLayout carve_gcn_fwd(const tx_gcn_layer_desc& d, int split_input, void* ws) {
+  Carver c(ws);
+  GcnFwdLayout L;
+  const int64_t D = d.dim, K = d.k;
+  L.z_hi = c.take<__half>(split_input ? d.n * r8(K) : 0);
+  L.z_lo = c.take<__half>(split_input ? d.n * r8(K) : 0);
+  L.z_scale = c.take<float>(1);
+  L.z_amax = c.take<float>(1);
+  L.w_hi = c.take<__half>(K * r8(D));        // [K, D]: the d(z) operand
+  L.w_lo = c.take<__half>(K * r8(D));
+  L.wt_hi = c.take<__half>(D * r8(K));       // [D, K]: the forward operand
+  L.wt_lo = c.take<__half>(D * r8(K));
+  L.w_scal = c.take<float>(4);
+  L.y = c.take<float>(d.n * r4(D));
+  L.y_amax = c.take<float>(1);
+  const bool mask = d.hidden && (d.act_slope != 1.f || d.p_next > 0.f);
+  L.maskbits = c.take<uint32_t>(mask ? tx_gat_fused_mask_words(d.n, 1, D) : 0);
+  if (!mask) L.maskbits = nullptr;
+  const int64_t ld16 = r8(D + d.pos_dim);
+  L.out_hi = c.take<__half>(d.hidden ? d.n * ld16 : 0);
+  L.out_lo = c.take<__half>(d.hidden ? d.n * ld16 : 0);
+  L.out_scale = c.take<float>(1);
+  L.bound = c.take<float>(1);
+  L.bytes = c.off;
+  return L;
+}
+struct GcnBwdLayout {
+  float *pos_partial, *col_partial, *bound, *g_amax; __half *d_hi, *d_lo; float *d_scale, *tn_partial, *dz_amax;
+  int64_t splits;
+  size_t bytes;
+};
+static GcnBwdLayout carve_gcn_bwd(const tx_gcn_layer_desc& d, void* ws) {
+  Carver c(ws);
+  GcnBwdLayout L;
+  const int64_t D = d.dim, K = d.k;
+  L.pos_partial = c.take<float>(d.hidden && d.pos_dim > 0 ? tx_row_blocks(d.n) * d.vocab * d.pos_dim : 0);
+  L.col_partial = c.take<float>(d.bias ? tx_row_blocks(d.n) * D : 0);
+  L.bound = c.take<float>(1);
+  L.g_amax = c.take<float>(1);
+  L.d_hi = c.take<__half>(d.n * r8(D));
+  L.d_lo = c.take<__half>(d.n * r8(D));
+  L.d_scale = c.take<float>(1);
+  L.splits = tx_gemm_tn_f16_splits(D, K, d.n);
+  L.tn_partial = c.take<float>(L.splits > 1 ? L.splits * D * r4(K) : 0);
+  L.dz_amax = c.take<float>(1);
+  L.bytes = c.off;
+  return L;
+}
+static int check_gcn_desc(const tx_gcn_layer_desc* d, const char* who) {
+  TX_REQUIRE(d, "%s: null descriptor", who);
+  TX_REQUIRE(d->n > 0 && d->k > 0 && d->dim > 0 && d->dim % 4 == 0 && d->pos_dim >= 0, "%s: bad sizes", who);
+  TX_REQUIRE(d->weight && d->ldw >= d->dim && d->norm && d->in_ptr && d->in_src && d->out_ptr && d->out_dst, "%s: parameters / structure missing", who);
+  TX_REQUIRE(!(d->hidden && d->pos_dim > 0) || (d->next_pos_table && d->pos && d->vocab > 0), "%s: next position table / positions missing", who);
+  return TX_OK;
+}
+
+}  // namespace tx
+
+extern "C" {
+
+int64_t tx_gcn_layer_fwd_bytes(const tx_gcn_layer_desc* d, int32_t split_input) { return d ? (int64_t)carve_gcn_fwd(*d, split_input, nullptr).bytes : -1; }
+int64_t tx_gcn_layer_bwd_bytes(const tx_gcn_layer_desc* d) { return d ? (int64_t)carve_gcn_bwd(*d, nullptr).bytes : -1; }
+
+int tx_gcn_layer_fwd(const tx_gcn_layer_desc* d, const float* z, int64_t ldz, const tx_gat_layer_state* prev, void* workspace,
+                     tx_gat_layer_state* state, float* out, void* stream) {
+  TX_SUB(check_gcn_desc(d, "gcn_layer_fwd"));
+  TX_REQUIRE(workspace && state && aligned16(workspace), "gcn_layer_fwd: workspace / state missing");
+  TX_REQUIRE((z != nullptr) != (prev != nullptr), "gcn_layer_fwd: exactly one of z (fp32 input) / prev (the previous layer's fp16-pair output)");
+  TX_REQUIRE(d->hidden || out, "gcn_layer_fwd: the output layer needs `out`");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = d->n, K = d->k, D = d->dim, pd = d->hidden ? d->pos_dim : 0;
+  const GcnFwdLayout L = carve_gcn_fwd(*d, z != nullptr, workspace);
+  tx_gat_layer_state& S = *state;
+  memset(&S, 0, sizeof(S));
+  if (z) {
+    { ProfScope ps("tx_absmax", d->tag, st); TX_SUB(tx_absmax(z, ldz, n, K, L.z_amax, stream)); }
+    { ProfScope ps("tx_split_f16", d->tag, st); TX_SUB(tx_split_f16(z, ldz, n, K, L.z_amax, L.z_hi, L.z_lo, r8(K), L.z_scale, stream)); }
+    S.z_hi = L.z_hi; S.z_lo = L.z_lo; S.z_scale = L.z_scale; S.ldz16 = r8(K);
+  } else {
+    TX_REQUIRE(prev->out_hi && prev->out_lo && prev->out_scale && prev->ld16_out >= r8(K), "gcn_layer_fwd: the previous layer published no fp16 pair");
+    S.z_hi = prev->out_hi; S.z_lo = prev->out_lo; S.z_scale = prev->out_scale; S.ldz16 = prev->ld16_out;
+  }
+  { ProfScope ps("tx_split_f16_weight", d->tag, st);
+    TX_SUB(tx_split_f16_weight(d->weight, d->ldw, K, D, L.w_hi, L.w_lo, r8(D), L.wt_hi, L.wt_lo, r8(K), L.w_scal, L.w_scal + 2, stream)); }
+  S.wt_hi = L.w_hi; S.wt_lo = L.w_lo; S.w_scale = L.w_scal + 2; S.ldwt = r8(D);       // [K, D]: rows c0a.. are the d(z) operand
+  { ProfScope ps("gemm_fwd", d->tag, st);                                       // y = torch.mm(h, W), model_zoo.py:37
+    TX_SUB(tx_gemm_nt_f16x3(S.z_hi, S.z_lo, S.ldz16, L.wt_hi, L.wt_lo, r8(K), S.z_scale, S.w_scale, L.y, r4(D), n, D, K, nullptr, L.y_amax, stream)); }
+  S.ft = L.y; S.ft_amax = L.y_amax;
+  tx_gat_epilogue epi;
+  memset(&epi, 0, sizeof(epi));
+  epi.mean_heads = d->hidden ? 0 : 1;
+  epi.act_slope = d->act_slope;
+  epi.next_pos_table = pd > 0 ? d->next_pos_table : nullptr;
+  epi.pos = pd > 0 ? d->pos : nullptr;
+  epi.pos_dim = pd;
+  epi.p_drop = d->hidden ? d->p_next : 0.f;
+  epi.seed = d->next_seed;
+  epi.stream_id = d->next_stream;
+  if (d->hidden) {
+    const float keep = 1.f - d->p_next;
+    const int64_t ld16 = r8(D + pd);
+    { ProfScope ps("tx_bound_gcn", d->tag, st);
+      TX_SUB(tx_bound_gcn(L.y_amax, sqrtf((float)(d->max_in_deg > 1 ? d->max_in_deg : 1)) / keep, d->bias, d->bias ? D : 0, 1.f / keep,
+                          pd > 0 ? d->next_pos_table : nullptr, pd > 0 ? d->vocab * pd : 0, 1.f / keep, L.bound, stream)); }
+    { ProfScope ps("tx_gcn_aggregate_fwd", d->tag, st);
+      TX_SUB(tx_gcn_aggregate_fwd_f16(L.y, r4(D), d->norm, d->bias, d->in_ptr, d->in_src, n, D, r4(D + pd), &epi, L.out_hi, L.out_lo, ld16,
+                                      L.bound, L.out_scale, L.maskbits, stream)); }
+    S.out_hi = L.out_hi; S.out_lo = L.out_lo; S.out_scale = L.out_scale; S.ld16_out = ld16; S.maskbits = L.maskbits;
+  } else {
+    ProfScope ps("tx_gcn_aggregate_fwd", d->tag, st);
+    TX_SUB(tx_gcn_aggregate_fwd(L.y, r4(D), d->norm, d->bias, d->in_ptr, d->in_src, n, D, out, D, &epi, stream));
+  }
+  S.heads = 1; S.dim = D; S.act_slope = d->act_slope; S.p_next = d->hidden ? d->p_next : 0.f;
+  return TX_OK;
+}
+
+int tx_gcn_layer_bwd(const tx_gcn_layer_desc* d, const tx_gat_layer_state* state, const tx_gat_layer_state* prev, const float* dout,
+                     int64_t ldg, const float* g_amax, void* workspace, float* dz, float* dwt, float* dbias, float* dtab,
+                     float** dz_amax_out, void* stream) {
+  TX_SUB(check_gcn_desc(d, "gcn_layer_bwd"));
+  TX_REQUIRE(state && workspace && aligned16(workspace) && dout && dwt, "gcn_layer_bwd: missing buffers");
+  cudaStream_t st = (cudaStream_t)stream;
+  const tx_gat_layer_state& S = *state;
+  const int64_t n = d->n, K = d->k, D = d->dim, pd = d->hidden ? d->pos_dim : 0;
+  const GcnBwdLayout L = carve_gcn_bwd(*d, workspace);
+  if (d->hidden && pd > 0 && dtab) {
+    { ProfScope ps("tx_pos_grad_partials", d->tag, st);
+      TX_SUB(tx_pos_grad_partials(dout, ldg, D, d->pos, n, pd, d->vocab, d->p_next, d->next_seed, d->next_stream, L.pos_partial, stream)); }
+    { ProfScope ps("tx_reduce_partials", d->tag, st); TX_SUB(tx_reduce_partials(L.pos_partial, tx_row_blocks(n), d->vocab * pd, dtab, stream)); }
+  }
+  if (d->bias && dbias) {                                                      // d(bias) = column sums of the gradient (model_zoo.py:47)
+    { ProfScope ps("tx_colsum_partials", d->tag, st); TX_SUB(tx_colsum_partials(dout, ldg, n, D, L.col_partial, stream)); }
+    { ProfScope ps("tx_reduce_partials", d->tag, st); TX_SUB(tx_reduce_partials(L.col_partial, tx_row_blocks(n), D, dbias, stream)); }
+  }
+  if (!g_amax) {
+    ProfScope ps("tx_absmax", d->tag, st);
+    TX_SUB(tx_absmax(dout, ldg, n, D, L.g_amax, stream));
+    g_amax = L.g_amax;
+  }
+  { ProfScope ps("tx_bound_gcn", d->tag, st);                                  // |dy_j| <= out-degree max|g|
+    TX_SUB(tx_bound_gcn(g_amax, 0.5f * (float)(d->max_out_deg > 1 ? d->max_out_deg : 1), nullptr, 0, 0.f, nullptr, 0, 0.f, L.bound, stream)); }
+  const int64_t ld16 = r8(D);
+  { ProfScope ps("tx_gcn_aggregate_bwd", d->tag, st);
+    TX_SUB(tx_gcn_aggregate_bwd_f16(dout, ldg, d->norm, d->out_ptr, d->out_dst, n, D, L.d_hi, L.d_lo, ld16, L.bound, L.d_scale, stream)); }
+  const int64_t ldc = r4(K);
+  { ProfScope ps("gemm_dw", d->tag, st);                                       // dW^T [D, K] = d(y)^T z
+    TX_SUB(tx_gemm_tn_f16x3(L.d_hi, L.d_lo, ld16, S.z_hi, S.z_lo, S.ldz16, L.d_scale, S.z_scale, L.splits > 1 ? L.tn_partial : dwt, ldc, D * ldc,
+                            D, K, n, L.splits, stream));
+    if (L.splits > 1) TX_SUB(tx_reduce_partials(L.tn_partial, L.splits, D * ldc, dwt, stream)); }
+  if (dz) {
+    const int64_t c0 = d->dz_from < K ? d->dz_from : K;
+    const int64_t c0a = (c0 / 8) * 8;
+    const int64_t ldz = r4(K);
+    if (K > c0a) {
+      tx_gemm_epilogue epi;
+      const tx_gemm_epilogue* pe = nullptr;
+      if (prev && prev->maskbits && c0a == 0) {
+        memset(&epi, 0, sizeof(epi));
+        epi.act_mask = reinterpret_cast<const uint8_t*>(prev->maskbits);
+        epi.heads = prev->heads; epi.dim = prev->dim; epi.mask_stride = tx_gat_fused_mask_ld(prev->heads, prev->dim); epi.col0 = 0;
+        epi.act_slope = prev->act_slope; epi.p_drop = prev->p_next; epi.has_keep_plane = prev->p_next > 0.f ? 1 : 0;
+        pe = &epi;
+      }
+      ProfScope ps("gemm_dz", d->tag, st);
+      TX_SUB(tx_gemm_nt_f16x3(L.d_hi, L.d_lo, ld16, reinterpret_cast<const __half*>(S.wt_hi) + c0a * S.ldwt,
+                              reinterpret_cast<const __half*>(S.wt_lo) + c0a * S.ldwt, S.ldwt, L.d_scale, S.w_scale, dz + c0a, ldz, n, K - c0a,
+                              D, pe, L.dz_amax, stream));
+    }
+    if (dz_amax_out) *dz_amax_out = L.dz_amax;
+  }
+  return TX_OK;
+}
+
 // ---- launch accounting and per-launch timing of the calls above ----
 int64_t tx_layer_launches(int32_t reset) {
   const int64_t v = g_sub_launches;

@@ -19,7 +19,7 @@ from torch.autograd import Function
 from . import _lib
 import ctypes
 
-from ._lib import GatEpilogue, GatLayerDesc, GatLayerState, Stats, check, current_stream, device_guard, ptr, timed_region
+from ._lib import GatEpilogue, GatLayerDesc, GatLayerState, GcnLayerDesc, Stats, check, current_stream, device_guard, ptr, timed_region
 from .graph import GraphStructure
 
 _NEG_SLOPE_NONE = 1.0
@@ -1004,6 +1004,14 @@ class GcnLayerCfg:
     next_stream: int = 0
     dz_from: int = 0
     tag: str = ""
+    in_link: Optional[MaskLink] = None     # published by the previous layer (its epilogue produced this layer's z)
+    out_link: Optional[MaskLink] = None    # published to the next layer
+
+
+# GCN hidden layers on the fused epilogue the GAT path has (tx_gcn_aggregate_fwd_f16 / _bwd_f16): the output goes out as the next GEMM's
+# fp16 pair + sign / keep bytes, the next layer's d(z) GEMM applies the activation / dropout derivative, d(y) goes out as a pair.
+# TAXO_GCN_FUSED=0 -> fp32 round trips with a separate tx_epilogue_bwd pass (round 1)
+GCN_FUSED = os.environ.get("TAXO_GCN_FUSED", "1") not in ("", "0")
 
 
 class GcnLayer(Function):
@@ -1015,12 +1023,59 @@ class GcnLayer(Function):
         D, K = cfg.dim, cfg.k
         dev = z.device
         f32 = dict(dtype=torch.float32, device=dev)
+        f16 = GEMM_BACKEND == "f16x3"
+        ctx.native = None
+        if (LAYER_CALL and GCN_FUSED and FUSE_SPLIT and FUSE_DZ_EPILOGUE and f16 and n > 0 and D % 4 == 0 and weight.shape[0] == K
+                and weight.is_contiguous() and (bias is None or bias.is_contiguous()) and (not cfg.hidden or cfg.out_link is not None)
+                and (next_pos_table is None or next_pos_table.is_contiguous())
+                and (cfg.in_link.c_state is not None if cfg.in_link is not None
+                     else (z.stride(1) == 1 and z.stride(0) % 4 == 0 and z.data_ptr() % 16 == 0))):
+            # ---- one native call: split / weight split / GEMM / bound / aggregate + epilogue into one workspace (tx_layer.cu) ----
+            with device_guard(dev):
+                Stats.sync_native_profiling()
+                norm = st.gcn_norm()
+                pd = 0 if (next_pos_table is None or not cfg.hidden) else int(next_pos_table.shape[1])
+                d = GcnLayerDesc()
+                d.n, d.k, d.dim, d.pos_dim = n, K, D, pd
+                d.vocab = 0 if pd == 0 else int(next_pos_table.shape[0])
+                d.dz_from, d.max_in_deg, d.max_out_deg = cfg.dz_from, max(int(st.max_in_deg), 1), max(int(st.max_out_deg), 1)
+                d.hidden, d.act_slope, d.p_next = (1 if cfg.hidden else 0), cfg.act_slope, (cfg.p_next if cfg.hidden else 0.0)
+                d.next_seed, d.next_stream = cfg.next_seed, cfg.next_stream
+                d.in_ptr, d.in_src, d.out_ptr, d.out_dst = st.in_ptr.data_ptr(), st.in_src.data_ptr(), st.out_ptr.data_ptr(), st.out_dst.data_ptr()
+                d.pos = None if pd == 0 else pos32.data_ptr()
+                d.norm, d.weight, d.ldw = norm.data_ptr(), weight.data_ptr(), weight.stride(0)
+                d.bias = None if bias is None else bias.data_ptr()
+                d.next_pos_table = None if pd == 0 else next_pos_table.data_ptr()
+                d.tag = cfg.tag.encode()[:15]
+                prev = None if cfg.in_link is None else cfg.in_link.c_state
+                ws = torch.empty(int(lib.tx_gcn_layer_fwd_bytes(ctypes.byref(d), 1 if prev is None else 0)), dtype=torch.uint8, device=dev)
+                state = GatLayerState()
+                out = torch.empty((n, round4(D + pd)) if cfg.hidden else (n, D), **f32)     # hidden: a placeholder, never written
+                check(lib.tx_gcn_layer_fwd(ctypes.byref(d), ptr(z) if prev is None else None, ldz, None if prev is None else ctypes.byref(prev),
+                                           ptr(ws), ctypes.byref(state), None if cfg.hidden else ptr(out), current_stream()), "tx_gcn_layer_fwd")
+            if cfg.out_link is not None:
+                lk = cfg.out_link
+                lk.c_state, lk.c_ws, lk.applied, lk.z16, lk.z_lo, lk.dz_amax, lk.c_bwd = state, ws, False, None, None, None, None
+                lk.c_dims = (n, D + pd, round8(D + pd), int(lib.tx_gat_fused_mask_words(n, 1, D)))
+                lk.mask = None
+                if state.maskbits:
+                    lk.heads, lk.dim, lk.act_slope, lk.p_drop = 1, D, cfg.act_slope, cfg.p_next
+            ctx.native = (d, state, ws, pd)
+            ctx.st, ctx.cfg, ctx.pd = st, cfg, pd
+            ctx.vocab = 0 if next_pos_table is None else int(next_pos_table.shape[0])
+            ctx.has_bias = bias is not None
+            ctx.save_for_backward(weight, bias, next_pos_table, pos32, norm)
+            ctx.zshape = tuple(z.shape)
+            return out
+        if cfg.in_link is not None:
+            cfg.in_link.materialize()
         with device_guard(dev):
             stream = current_stream()
             Stats.tag = cfg.tag
             with timed_region("gemm_fwd"):
-                y, zsaved, _ = _layer_gemms_fwd(z, K, weight.t(),         # torch.mm(h, W), model_zoo.py:37
-                                                w_rowmajor=weight if (GEMM_BACKEND == "f16x3" and weight.shape[0] == K) else None, w_is_nk=False)
+                y, zsaved, y_amax = _layer_gemms_fwd(z, K, weight.t(),         # torch.mm(h, W), model_zoo.py:37
+                                                     z16=cfg.in_link.z16 if (cfg.in_link is not None and f16) else None,
+                                                     w_rowmajor=weight if (f16 and weight.shape[0] == K) else None, w_is_nk=False)
             norm = st.gcn_norm()
             pd = 0 if next_pos_table is None else int(next_pos_table.shape[1])
             tab = None if next_pos_table is None else next_pos_table.contiguous()
@@ -1030,18 +1085,88 @@ class GcnLayer(Function):
                               pos=ptr(pos32) if pd > 0 else None, pos_dim=pd, p_drop=cfg.p_next if cfg.hidden else 0.0,
                               seed=cfg.next_seed, stream_id=cfg.next_stream)
             b = None if bias is None else bias.contiguous()
-            check(lib.tx_gcn_aggregate_fwd(ptr(y), D, ptr(norm), ptr(b), ptr(st.in_ptr), ptr(st.in_src), n, D, ptr(out), ldo,
-                                           epi, stream), "tx_gcn_aggregate_fwd")
+            fused = (GCN_FUSED and FUSE_SPLIT and FUSE_DZ_EPILOGUE and f16 and cfg.hidden and cfg.out_link is not None and y_amax is not None
+                     and n > 0 and D % 4 == 0 and y.stride(0) % 4 == 0)
+            maskbits = None
+            if fused:
+                # the epilogue writes the next layer's input fp16-split; `out` itself is never written.  |norm_i sum_j norm_j y_j + b| <=
+                # sqrt(max in-degree) max|y| + max|b|, appended rows <= max|P|, both / (1 - p_next)
+                keep = 1.0 - cfg.p_next
+                bound = torch.empty(1, **f32)
+                check(lib.tx_bound_gcn(ptr(y_amax), (max(int(st.max_in_deg), 1) ** 0.5) / keep, ptr(b), 0 if b is None else b.numel(), 1.0 / keep,
+                                       ptr(tab) if pd > 0 else None, tab.numel() if pd > 0 else 0, 1.0 / keep, ptr(bound), stream), "tx_bound_gcn")
+                ld16 = round8(D + pd)
+                o_hi = torch.empty((n, ld16), dtype=torch.float16, device=dev)
+                o_lo = torch.empty((n, ld16), dtype=torch.float16, device=dev)
+                o_scale = torch.empty(1, **f32)
+                if cfg.act_slope != 1.0 or cfg.p_next > 0.0:
+                    maskbits = torch.empty(int(lib.tx_gat_fused_mask_words(n, 1, D)), dtype=torch.int32, device=dev)
+                check(lib.tx_gcn_aggregate_fwd_f16(ptr(y), y.stride(0), ptr(norm), ptr(b), ptr(st.in_ptr), ptr(st.in_src), n, D, ldo, epi,
+                                                   ptr(o_hi), ptr(o_lo), ld16, ptr(bound), ptr(o_scale), ptr(maskbits), stream),
+                      "tx_gcn_aggregate_fwd_f16")
+                lk = cfg.out_link
+                lk.z16, lk.z_lo, lk.c_state, lk.dz_amax, lk.applied = F16Pair(o_hi, o_lo, o_scale, D + pd), None, None, None, False
+                lk.mask = maskbits
+                if maskbits is not None:
+                    lk.heads, lk.dim, lk.act_slope, lk.p_drop = 1, D, cfg.act_slope, cfg.p_next
+            else:
+                check(lib.tx_gcn_aggregate_fwd(ptr(y), y.stride(0), ptr(norm), ptr(b), ptr(st.in_ptr), ptr(st.in_src), n, D, ptr(out), ldo,
+                                               epi, stream), "tx_gcn_aggregate_fwd")
         ctx.st, ctx.cfg, ctx.pd = st, cfg, pd
         ctx.vocab = 0 if next_pos_table is None else int(next_pos_table.shape[0])
         ctx.has_bias = bias is not None
-        ctx.save_for_backward(zsaved[0], zsaved[1], weight, out if cfg.hidden else None, pos32, norm, zsaved[2], zsaved[3], zsaved[4], zsaved[5])
+        ctx.fused, ctx.has_mask = fused, maskbits is not None
+        ctx.save_for_backward(zsaved[0], zsaved[1], weight, out if (cfg.hidden and not fused) else None, pos32, norm, zsaved[2], zsaved[3],
+                              zsaved[4], zsaved[5])
         ctx.zshape = tuple(z.shape)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         lib = _lib.load()
+        if ctx.native is not None:
+            # ---- one native call: d(pos table) / d(bias) / bound / aggregate backward / dW / d(z) (tx_layer.cu) ----
+            d, state, ws, pd = ctx.native
+            weight, bias, tab, pos32, norm = ctx.saved_tensors
+            st, cfg = ctx.st, ctx.cfg
+            n, ldz = ctx.zshape
+            D, K = cfg.dim, cfg.k
+            dev = dout.device
+            f32 = dict(dtype=torch.float32, device=dev)
+            lk_out = cfg.out_link
+            pre = lk_out is not None and lk_out.applied
+            if state.maskbits and not pre:
+                raise _lib.TaxoLibraryError("GcnLayer: the consumer of a fused GCN layer did not apply the activation / dropout derivative "
+                                            "(set TAXO_LAYER_CALL=0 TAXO_GCN_FUSED=0 for this configuration)")
+            with device_guard(dev):
+                Stats.sync_native_profiling()
+                dout = _rowmajor(dout)
+                if cfg.hidden and n > 1 and dout.stride(0) != round4(D + pd):
+                    dout = dout.contiguous()
+                ldg = dout.stride(0) if n > 1 else dout.shape[1]
+                need_tab = cfg.hidden and ctx.needs_input_grad[3] and pd > 0
+                need_z = ctx.needs_input_grad[0]
+                g_amax = None
+                if lk_out is not None and lk_out.c_bwd is not None and pre:
+                    g_amax = lk_out.c_bwd[0]
+                elif lk_out is not None and lk_out.dz_amax is not None and pre:
+                    g_amax = lk_out.dz_amax.data_ptr()
+                bws = torch.empty(int(lib.tx_gcn_layer_bwd_bytes(ctypes.byref(d))), dtype=torch.uint8, device=dev)
+                dwt = torch.empty((D, round4(K)), **f32)
+                db = torch.empty(D, **f32) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+                dz = torch.empty((n, ldz), **f32) if need_z else None
+                dtab = torch.empty((ctx.vocab, pd), **f32) if need_tab else None
+                dz_amax = ctypes.c_void_p()
+                prev = None if cfg.in_link is None else cfg.in_link.c_state
+                check(lib.tx_gcn_layer_bwd(ctypes.byref(d), ctypes.byref(state), None if prev is None else ctypes.byref(prev), ptr(dout), ldg,
+                                           g_amax, ptr(bws), ptr(dz), ptr(dwt), ptr(db), ptr(dtab), ctypes.byref(dz_amax), current_stream()),
+                      "tx_gcn_layer_bwd")
+                if cfg.in_link is not None and need_z:
+                    cfg.in_link.c_bwd = (dz_amax.value, bws)
+                    cfg.in_link.applied = bool(prev is not None and prev.maskbits)
+                    cfg.in_link.dz_amax = None
+            dw = dwt[:, :K].t() if ctx.needs_input_grad[1] else None            # weight is [K, D]
+            return dz, dw, db, dtab, None, None, None
         z0, z1, weight, out, pos32, norm, z_scale, wt_hi, wt_lo, wt_scale = ctx.saved_tensors
         st, cfg, pd = ctx.st, ctx.cfg, ctx.pd
         n, ldz = ctx.zshape
@@ -1049,17 +1174,33 @@ class GcnLayer(Function):
         dev = norm.device
         f32 = dict(dtype=torch.float32, device=dev)
         dtab = db = None
+        dy16 = None
         with device_guard(dev):
             stream = current_stream()
+            Stats.tag = cfg.tag
             dout = _rowmajor(dout)
+            if cfg.hidden and n > 1 and dout.stride(0) != round4(D + pd):
+                dout = dout.contiguous()          # the dropout counters of the forward epilogue are indexed with ITS row pitch
             ldg = dout.stride(0) if n > 1 else dout.shape[1]
+            pre = ctx.fused and (not ctx.has_mask or (cfg.out_link is not None and cfg.out_link.applied))
+            if ctx.fused and not pre:
+                raise _lib.TaxoLibraryError("GcnLayer: the consumer of a fused GCN layer did not apply the activation / dropout derivative "
+                                            "(set TAXO_GCN_FUSED=0 for this configuration)")
             if cfg.hidden:
                 need_tab = ctx.needs_input_grad[3] and pd > 0
-                if cfg.p_next > 0.0 or cfg.act_slope != 1.0 or need_tab:
+                nb = int(lib.tx_row_blocks(n))
+                if pre:
+                    # d(z_next) already carries the epilogue derivative on the feature columns (the next layer's d(z) GEMM epilogue); the
+                    # appended position rows get theirs here
+                    if need_tab:
+                        partial = torch.empty(nb * ctx.vocab * pd, **f32)
+                        check(lib.tx_pos_grad_partials(ptr(dout), ldg, D, ptr(pos32), n, pd, ctx.vocab, cfg.p_next, cfg.next_seed,
+                                                       cfg.next_stream, ptr(partial), stream), "tx_pos_grad_partials")
+                        dtab = _reduce_partials(lib, partial, nb, ctx.vocab * pd).view(ctx.vocab, pd)
+                elif cfg.p_next > 0.0 or cfg.act_slope != 1.0 or need_tab:
                     if cfg.p_next > 0.0 or cfg.act_slope != 1.0:
                         dout = dout.clone()
                         ldg = dout.stride(0) if n > 1 else dout.shape[1]
-                    nb = int(lib.tx_row_blocks(n))
                     partial = torch.empty(nb * ctx.vocab * pd, **f32) if need_tab else None
                     check(lib.tx_epilogue_bwd(ptr(dout), ldg, ptr(out), ptr(pos32) if pd > 0 else None, n, D,
                                               pd if need_tab else 0, ctx.vocab, cfg.act_slope, cfg.p_next, cfg.next_seed,
@@ -1071,11 +1212,29 @@ class GcnLayer(Function):
                 partial = torch.empty(nb * D, **f32)
                 check(lib.tx_colsum_partials(ptr(dout), ldg, n, D, ptr(partial), stream), "tx_colsum_partials")
                 db = _reduce_partials(lib, partial, nb, D)
-            dy = torch.empty((n, D), **f32)
-            check(lib.tx_gcn_aggregate_bwd(ptr(dout), ldg, ptr(norm), ptr(st.out_ptr), ptr(st.out_dst), n, D, ptr(dy), D, stream),
-                  "tx_gcn_aggregate_bwd")
+            f16 = GEMM_BACKEND == "f16x3" and z0.shape[0] > 0
+            dy = None
+            if GCN_FUSED and FUSE_SPLIT and f16 and D % 4 == 0 and ldg % 4 == 0 and dout.data_ptr() % 16 == 0:
+                # d(y) straight as the GEMMs' fp16 pair: |dy_j| = |norm_j sum_i norm_i g_i| <= out-degree max|g|
+                if cfg.out_link is not None and cfg.out_link.dz_amax is not None and pre and cfg.hidden:
+                    g_amax = cfg.out_link.dz_amax
+                else:
+                    g_amax = absmax(dout, D)
+                bound = torch.empty(1, **f32)
+                check(lib.tx_bound_gcn(ptr(g_amax), 0.5 * max(int(st.max_out_deg), 1), None, 0, 0.0, None, 0, 0.0, ptr(bound), stream), "tx_bound_gcn")
+                ld16 = round8(D)
+                d_hi = torch.empty((n, ld16), dtype=torch.float16, device=dev)
+                d_lo = torch.empty((n, ld16), dtype=torch.float16, device=dev)
+                d_scale = torch.empty(1, **f32)
+                check(lib.tx_gcn_aggregate_bwd_f16(ptr(dout), ldg, ptr(norm), ptr(st.out_ptr), ptr(st.out_dst), n, D, ptr(d_hi), ptr(d_lo), ld16,
+                                                   ptr(bound), ptr(d_scale), stream), "tx_gcn_aggregate_bwd_f16")
+                dy16 = F16Pair(d_hi, d_lo, d_scale, D)
+            else:
+                dy = torch.empty((n, D), **f32)
+                check(lib.tx_gcn_aggregate_bwd(ptr(dout), ldg, ptr(norm), ptr(st.out_ptr), ptr(st.out_dst), n, D, ptr(dy), D, stream),
+                      "tx_gcn_aggregate_bwd")
             dwt, dz = _layer_gemms_bwd(dy, D, (z0, z1, z_scale, wt_hi, wt_lo, wt_scale), weight, K, ldz, cfg.dz_from, ctx.needs_input_grad[1],
-                                       ctx.needs_input_grad[0])
+                                       ctx.needs_input_grad[0], cfg.in_link, None, dy16)
             dw = None if dwt is None else dwt.t()                         # weight is [K, D]
         return dz, dw, db, dtab, None, None, None
 

@@ -36,7 +36,7 @@ class GraphStructure:
     """Device-resident structure of one batched graph (all int32)."""
 
     __slots__ = ("device", "n", "e", "g", "in_ptr", "in_src", "in_eid", "out_ptr", "out_dst", "out_slot", "node_off",
-                 "pos", "src", "dst", "max_nodes", "max_out_deg", "_norm", "is_star", "_bwd_tiles", "_dh_bound", "star", "star_bwd", "counts")
+                 "pos", "src", "dst", "max_nodes", "max_out_deg", "max_in_deg", "_norm", "is_star", "_bwd_tiles", "_dh_bound", "star", "star_bwd", "counts")
 
     def __init__(self, device):
         self.device = device
@@ -44,6 +44,7 @@ class GraphStructure:
         self._bwd_tiles = {}
         self._dh_bound = None      # (data_ptr of the readout's d(h), device bound of max|d(h)|): hand-over to the output layer's backward
         self.max_out_deg = 0       # host-side upper bound of the largest out-degree (bounds |dft| for the fp16-split GEMM operands)
+        self.max_in_deg = 0        # ... and of the largest in-degree (bounds a GCN layer's output)
         self.pos = None
         self.src = self.dst = None
         self.is_star = False
@@ -186,6 +187,7 @@ class DGLGraph:
             st = _build_structure_from_edges(self._src, self._dst, self._n, self.node_offsets(), device)
             st.max_nodes = max(self.batch_num_nodes) if self.batch_num_nodes else 0
             st.max_out_deg = int(torch.bincount(self._src.reshape(-1).to(torch.int64)).max()) if self._src.numel() else 0
+            st.max_in_deg = int(torch.bincount(self._dst.reshape(-1).to(torch.int64)).max()) if self._dst.numel() else 0
             self._structure[device] = st
         return st
 
@@ -359,6 +361,7 @@ class EgonetBatch(DGLGraph):
         st.n, st.e, st.g = self._n, self._e, self._g
         st.max_nodes = self._max_nodes
         st.max_out_deg = self._max_nodes          # the anchor: every sibling + its self-loop (<= graph size)
+        st.max_in_deg = self._max_nodes           # the anchor: every grand-parent + its self-loop
         st.is_star = True
         g = self._g
         with torch.cuda.device(device):

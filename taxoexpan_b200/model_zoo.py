@@ -189,9 +189,11 @@ def _gcn_stack_forward(mod, g, features, positions, pos_tables):
     p0 = layers[0].dropout if tr else 0.0
     z = txf.ConcatPosDropout.apply(features, tab(0), pos32, p0, seed, 0)
     k = features.shape[1] + pd
+    links = [txf.MaskLink() for _ in range(n_total - 1)]     # layer l's epilogue mask -> layer l+1's d(z) GEMM epilogue
     for l, layer in enumerate(layers):
         hidden = l < n_total - 1
         cfg = txf.GcnLayerCfg(
+            in_link=links[l - 1] if l > 0 else None, out_link=links[l] if hidden else None,
             k=k, dim=layer.weight.shape[1], hidden=hidden, act_slope=_act_slope(layer.activation) if hidden else 1.0,
             p_next=(layers[l + 1].dropout if tr else 0.0) if hidden else 0.0, next_seed=seed, next_stream=2 * (l + 1),
             dz_from=features.shape[1] if (l == 0 and not features.requires_grad) else 0, tag=f"L{l}")

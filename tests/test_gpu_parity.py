@@ -585,9 +585,11 @@ def test_standalone_layers_follow_reference_signatures():
 
 @pytest.mark.parametrize("cfg_kw,p_drop", [(MAGCS, 0.1), (MAGCS, 0.0), (dict(MAGCS, in_dim=512, hidden_dim=512, out_dim=512, pos_dim=64,
                                                                              num_layers=2, heads=[4, 4, 1]), 0.1),
-                                           (dict(MAGCS, num_layers=2, heads=[2, 3, 2]), 0.1)])
+                                           (dict(MAGCS, num_layers=2, heads=[2, 3, 2]), 0.1),
+                                           (WORDNET, 0.1), (dict(WORDNET, propagation_method="GCN", num_layers=2, readout_method="CR"), 0.1),
+                                           (WORDNET, 0.0)])
 def test_native_layer_calls_are_bit_identical_to_the_per_kernel_path(cfg_kw, p_drop, monkeypatch):
-    """tx_gat_layer_fwd / tx_gat_layer_bwd (one call per layer and direction, one workspace) enqueue the same kernels with the same
+    """tx_gat_layer_fwd / _bwd and tx_gcn_layer_fwd / _bwd (one call per layer and direction, one workspace) enqueue the same kernels with the same
     arguments in the same order as the per-kernel ctypes path: every output and gradient must be BIT-identical (dropout on; the last
     case ends in a two-head output layer that falls back to the per-kernel path behind two native hidden layers)."""
     cfg = orc.OracleConfig(**dict(cfg_kw, feat_drop=p_drop, attn_drop=p_drop, hidden_drop=p_drop, out_drop=p_drop))
@@ -608,6 +610,27 @@ def test_native_layer_calls_are_bit_identical_to_the_per_kernel_path(cfg_kw, p_d
         assert np.array_equal(a[i], b[i]), i
     for k in a[4]:
         assert np.array_equal(a[4][k], b[4][k]), k
+
+
+def test_fused_gcn_epilogue_matches_the_unfused_path(monkeypatch):
+    """PGCN with the fused next-layer epilogue (fp16-pair output + sign / keep bytes, derivative applied by the next d(z) GEMM, d(y)
+    as a pair: tx_gcn_aggregate_fwd_f16 / _bwd_f16) against the round-1 path (fp32 round trips + tx_epilogue_bwd), same dropout masks:
+    same result up to the rounding of the fp16-pair operands."""
+    cfg = orc.OracleConfig(**dict(WORDNET, num_layers=2, feat_drop=0.1, attn_drop=0.1, hidden_drop=0.1, out_drop=0.1))
+    n_q = 8
+    shapes = tx.synth.sample_shapes(n_q, 31, "wordnet", seed=31)
+    og = orc.batch_star_egonets(shapes.n_gp, shapes.n_sib)
+    x = torch.from_numpy(tx.synth.unit_rows(og.n, cfg.in_dim, seed=1))
+    qf = torch.from_numpy(tx.synth.unit_rows(og.num_graphs, cfg.in_dim, seed=2))
+    params = orc.init_model_params(cfg, seed=3)
+    monkeypatch.setattr(txf, "new_seed", lambda: 0x51DE_CA5E)
+    monkeypatch.setattr(txf, "LAYER_CALL", False)
+    outs = []
+    for fused in (True, False):
+        monkeypatch.setattr(txf, "GCN_FUSED", fused)
+        model = build_model(cfg, params, 0.1, 0.1, 0.1, 0.1).train()
+        outs.append(run_cuda(model, tx.EgonetBatch.from_counts(shapes.n_gp, shapes.n_sib), x, qf, n_q))
+    assert_close(outs[0], outs[1], TOL, GTOL, what="fused vs unfused GCN: ")
 
 
 # ------------------------------------------------------------------------------------------------
