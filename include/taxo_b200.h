@@ -476,6 +476,30 @@ int tx_gcn_layer_fwd(const tx_gcn_layer_desc* d, const float* z, int64_t ldz, co
 int tx_gcn_layer_bwd(const tx_gcn_layer_desc* d, const tx_gat_layer_state* state, const tx_gat_layer_state* prev, const float* dout,
                      int64_t ldg, const float* g_amax, void* workspace, float* dz, float* dwt, float* dbias, float* dtab,
                      float** dz_amax_out, void* stream);
+/* Readout + bilinear matching as one call per direction (TaxoExpan.forward lines model/model.py:85-86 and their autograd):
+ * hg = readout(h) (MeanReadout / WeightedMeanReadout, model_zoo.py:227-242), u = hg W (the projection half of nn.Bilinear(l, r, 1),
+ * model_zoo.py:301-328, on the fp16-pair GEMMs), scores = <u, q> (exp'd for LBM); backward: d(u), d(hg) = d(u) W^T, dW = hg^T d(u),
+ * readout backward -> d(h) [N, dim], d(position weights) [3] (WMEAN), and max|d(hg)| (>= max|d(h)|: the bound the output layer's
+ * backward needs) at *dh_amax_out.  The forward workspace must stay alive until the backward has run. */
+typedef struct tx_head_desc {
+  int64_t n, g, dim, r;                   /* nodes, graphs, readout width l = dim, query width r */
+  int32_t kind, apply_exp;                /* TX_READOUT_MEAN / TX_READOUT_WMEAN; 1 = LBM */
+  const int32_t *pos, *node_off;
+  const float* pos_weight;                /* [3] (WMEAN) or NULL */
+  const float* w; int64_t ldw;            /* match.W.weight[0]: [dim, r] */
+  char tag[16];
+} tx_head_desc;
+typedef struct tx_head_state {
+  float* hg; void *hg_hi, *hg_lo; float* hg_scale;
+  void *w_hi, *w_lo; float* w_scale;
+  float* u; float* scores;
+} tx_head_state;
+int64_t tx_head_fwd_bytes(const tx_head_desc* d);
+int64_t tx_head_bwd_bytes(const tx_head_desc* d);
+int tx_head_fwd(const tx_head_desc* d, const float* h, int64_t ldh, const float* q, int64_t ldq, void* workspace, tx_head_state* state,
+                float* scores, void* stream);
+int tx_head_bwd(const tx_head_desc* d, const tx_head_state* state, const float* h, int64_t ldh, const float* q, int64_t ldq,
+                const float* dscores, void* workspace, float* dh, float* dw, float* dpos_weight, float** dh_amax_out, void* stream);
 /* measurement aid (bench.py): kernel launches issued by the two calls above since the last reset, and optional CUDA-event timing of
  * each of them (creates events; read after synchronising the stream) */
 int64_t tx_layer_launches(int32_t reset);

@@ -62,6 +62,18 @@ class GcnLayerDesc(Structure):
         ("weight", c_void_p), ("ldw", c_int64), ("bias", c_void_p), ("next_pos_table", c_void_p), ("tag", ctypes.c_char * 16)]
 
 
+class HeadDesc(Structure):
+    """struct tx_head_desc"""
+    _fields_ = [("n", c_int64), ("g", c_int64), ("dim", c_int64), ("r", c_int64), ("kind", c_int32), ("apply_exp", c_int32),
+                ("pos", c_void_p), ("node_off", c_void_p), ("pos_weight", c_void_p), ("w", c_void_p), ("ldw", c_int64),
+                ("tag", ctypes.c_char * 16)]
+
+
+class HeadState(Structure):
+    """struct tx_head_state"""
+    _fields_ = [(k, c_void_p) for k in ("hg", "hg_hi", "hg_lo", "hg_scale", "w_hi", "w_lo", "w_scale", "u", "scores")]
+
+
 class GatLayerState(Structure):
     """struct tx_gat_layer_state"""
     _fields_ = [("z_hi", c_void_p), ("z_lo", c_void_p), ("z_scale", c_void_p), ("ldz16", c_int64),
@@ -154,6 +166,10 @@ _SIGNATURES = {
     "tx_gcn_layer_fwd": [POINTER(GcnLayerDesc), P, I64, POINTER(GatLayerState), P, POINTER(GatLayerState), P, P],
     "tx_gcn_layer_bwd": [POINTER(GcnLayerDesc), POINTER(GatLayerState), POINTER(GatLayerState), P, I64, P, P, P, P, P, P,
                          POINTER(c_void_p), P],
+    "tx_head_fwd_bytes": [POINTER(HeadDesc)],
+    "tx_head_bwd_bytes": [POINTER(HeadDesc)],
+    "tx_head_fwd": [POINTER(HeadDesc), P, I64, P, I64, P, POINTER(HeadState), P, P],
+    "tx_head_bwd": [POINTER(HeadDesc), POINTER(HeadState), P, I64, P, I64, P, P, P, P, P, POINTER(c_void_p), P],
     "tx_layer_launches": [c_int32],
     "tx_prof_enable": [c_int32],
     "tx_prof_clear": [],
@@ -168,7 +184,7 @@ _RESTYPES = {"tx_last_error": c_char_p, "tx_target_arch": c_char_p, "tx_row_bloc
              "tx_gat_fused_mask_words": c_int64, "tx_gat_fused_mask_ld": c_int64, "tx_gat_fused_bwd_blocks": c_int64, "tx_gemm_tn_splits": c_int64,
              "tx_gat_bwd_tile_rows": c_int64, "tx_gat_bwd_num_tiles": c_int64, "tx_gat_fused_bwd_staged_blocks": c_int64,
              "tx_gemm_tn_f16_splits": c_int64, "tx_gat_star_chunk": c_int64, "tx_gat_star_max_chunks": c_int64,
-             "tx_gat_star_bwd_partial_floats": c_int64, "tx_gat_layer_fwd_bytes": c_int64, "tx_gat_layer_bwd_bytes": c_int64, "tx_gcn_layer_fwd_bytes": c_int64, "tx_gcn_layer_bwd_bytes": c_int64,
+             "tx_gat_star_bwd_partial_floats": c_int64, "tx_gat_layer_fwd_bytes": c_int64, "tx_gat_layer_bwd_bytes": c_int64, "tx_gcn_layer_fwd_bytes": c_int64, "tx_gcn_layer_bwd_bytes": c_int64, "tx_head_fwd_bytes": c_int64, "tx_head_bwd_bytes": c_int64,
              "tx_layer_launches": c_int64, "tx_prof_count": c_int64, "tx_prof_enable": None, "tx_prof_clear": None}
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -183,6 +199,7 @@ _NO_LAUNCH = {"tx_abi_version", "tx_last_error", "tx_target_arch", "tx_row_block
               # the per-layer calls enqueue several kernels each: they are counted through tx_layer_launches, timed through tx_prof_*
               "tx_gat_layer_fwd_bytes", "tx_gat_layer_bwd_bytes", "tx_gat_layer_fwd", "tx_gat_layer_bwd", "tx_layer_launches",
               "tx_gcn_layer_fwd_bytes", "tx_gcn_layer_bwd_bytes", "tx_gcn_layer_fwd", "tx_gcn_layer_bwd",
+              "tx_head_fwd_bytes", "tx_head_bwd_bytes", "tx_head_fwd", "tx_head_bwd",
               "tx_prof_enable", "tx_prof_clear", "tx_prof_count", "tx_prof_get"}
 
 

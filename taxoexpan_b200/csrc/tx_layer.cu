@@ -464,6 +464,119 @@ int tx_gcn_layer_bwd(const tx_gcn_layer_desc* d, const tx_gat_layer_state* state
   return TX_OK;
 }
 
+// =================================================================================================================================
+// Readout + bilinear matching (model.py:85-86)
+// =================================================================================================================================
+}  // extern "C"
+
+namespace tx {
+
+struct HeadFwdLayout { float *hg, *hg_amax; __half *hg_hi, *hg_lo; float* hg_scale; __half *w_hi, *w_lo, *wt_hi, *wt_lo; float *w_scal, *u; size_t bytes; };
+static HeadFwdLayout carve_head_fwd(const tx_head_desc& d, void* ws) {
+  Carver c(ws);
+  HeadFwdLayout L;
+  const int64_t l = d.dim, r = d.r;
+  L.hg = c.take<float>(d.g * l);
+  L.hg_amax = c.take<float>(1);
+  L.hg_hi = c.take<__half>(d.g * r8(l));
+  L.hg_lo = c.take<__half>(d.g * r8(l));
+  L.hg_scale = c.take<float>(1);
+  L.w_hi = c.take<__half>(l * r8(r));          // [l, r]: the d(hg) operand
+  L.w_lo = c.take<__half>(l * r8(r));
+  L.wt_hi = c.take<__half>(r * r8(l));         // [r, l]: the forward operand
+  L.wt_lo = c.take<__half>(r * r8(l));
+  L.w_scal = c.take<float>(4);
+  L.u = c.take<float>(d.g * r4(r));
+  L.bytes = c.off;
+  return L;
+}
+struct HeadBwdLayout { float *du, *du_amax; __half *du_hi, *du_lo; float *du_scale, *dhg, *tn_partial, *pw_partial, *dhg_amax; int64_t splits; size_t bytes; };
+static HeadBwdLayout carve_head_bwd(const tx_head_desc& d, void* ws) {
+  Carver c(ws);
+  HeadBwdLayout L;
+  const int64_t l = d.dim, r = d.r;
+  L.du = c.take<float>(d.g * r);
+  L.du_amax = c.take<float>(1);
+  L.du_hi = c.take<__half>(d.g * r8(r));
+  L.du_lo = c.take<__half>(d.g * r8(r));
+  L.du_scale = c.take<float>(1);
+  L.dhg = c.take<float>(d.g * r4(l));
+  L.splits = tx_gemm_tn_f16_splits(l, r, d.g);
+  L.tn_partial = c.take<float>(L.splits > 1 ? L.splits * l * r4(r) : 0);
+  L.pw_partial = c.take<float>(d.kind == TX_READOUT_WMEAN ? tx_readout_bwd_blocks(d.g) * 3 : 0);
+  L.dhg_amax = c.take<float>(1);
+  L.bytes = c.off;
+  return L;
+}
+static int check_head_desc(const tx_head_desc* d, const char* who) {
+  TX_REQUIRE(d, "%s: null descriptor", who);
+  TX_REQUIRE(d->n > 0 && d->g > 0 && d->dim > 0 && d->r > 0, "%s: bad sizes", who);
+  TX_REQUIRE(d->kind == TX_READOUT_MEAN || d->kind == TX_READOUT_WMEAN, "%s: mean / weighted-mean readout only", who);
+  TX_REQUIRE(d->w && d->ldw >= d->r && d->node_off && (d->kind == TX_READOUT_MEAN || (d->pos && d->pos_weight)), "%s: parameters / structure missing", who);
+  return TX_OK;
+}
+
+}  // namespace tx
+
+extern "C" {
+
+int64_t tx_head_fwd_bytes(const tx_head_desc* d) { return d ? (int64_t)carve_head_fwd(*d, nullptr).bytes : -1; }
+int64_t tx_head_bwd_bytes(const tx_head_desc* d) { return d ? (int64_t)carve_head_bwd(*d, nullptr).bytes : -1; }
+
+int tx_head_fwd(const tx_head_desc* d, const float* h, int64_t ldh, const float* q, int64_t ldq, void* workspace, tx_head_state* state,
+                float* scores, void* stream) {
+  TX_SUB(check_head_desc(d, "head_fwd"));
+  TX_REQUIRE(h && q && workspace && state && scores && aligned16(workspace), "head_fwd: missing buffers");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t G = d->g, l = d->dim, r = d->r;
+  const HeadFwdLayout L = carve_head_fwd(*d, workspace);
+  { ProfScope ps("tx_readout_fwd", d->tag, st);
+    TX_SUB(tx_readout_fwd(d->kind, h, ldh, d->pos, d->pos_weight, d->node_off, G, l, L.hg, l, stream)); }
+  { ProfScope ps("tx_absmax", d->tag, st); TX_SUB(tx_absmax(L.hg, l, G, l, L.hg_amax, stream)); }
+  { ProfScope ps("tx_split_f16", d->tag, st); TX_SUB(tx_split_f16(L.hg, l, G, l, L.hg_amax, L.hg_hi, L.hg_lo, r8(l), L.hg_scale, stream)); }
+  { ProfScope ps("tx_split_f16_weight", d->tag, st);
+    TX_SUB(tx_split_f16_weight(d->w, d->ldw, l, r, L.w_hi, L.w_lo, r8(r), L.wt_hi, L.wt_lo, r8(l), L.w_scal, L.w_scal + 2, stream)); }
+  { ProfScope ps("tx_gemm_nt_f16x3", d->tag, st);                               // u = hg W
+    TX_SUB(tx_gemm_nt_f16x3(L.hg_hi, L.hg_lo, r8(l), L.wt_hi, L.wt_lo, r8(l), L.hg_scale, L.w_scal + 2, L.u, r4(r), G, r, l, nullptr, nullptr, stream)); }
+  { ProfScope ps("tx_match_rowdot_fwd", d->tag, st); TX_SUB(tx_match_rowdot_fwd(L.u, r4(r), q, ldq, G, r, d->apply_exp, scores, stream)); }
+  tx_head_state& S = *state;
+  S.hg = L.hg; S.hg_hi = L.hg_hi; S.hg_lo = L.hg_lo; S.hg_scale = L.hg_scale; S.w_hi = L.w_hi; S.w_lo = L.w_lo; S.w_scale = L.w_scal + 2;
+  S.u = L.u; S.scores = scores;
+  return TX_OK;
+}
+
+int tx_head_bwd(const tx_head_desc* d, const tx_head_state* state, const float* h, int64_t ldh, const float* q, int64_t ldq,
+                const float* dscores, void* workspace, float* dh, float* dw, float* dpos_weight, float** dh_amax_out, void* stream) {
+  TX_SUB(check_head_desc(d, "head_bwd"));
+  TX_REQUIRE(state && h && q && dscores && workspace && dh && dw && aligned16(workspace), "head_bwd: missing buffers");
+  cudaStream_t st = (cudaStream_t)stream;
+  const tx_head_state& S = *state;
+  const int64_t G = d->g, l = d->dim, r = d->r;
+  const HeadBwdLayout L = carve_head_bwd(*d, workspace);
+  { ProfScope ps("tx_match_rowdot_bwd", d->tag, st);
+    TX_SUB(tx_match_rowdot_bwd(S.u, r4(r), q, ldq, S.scores, dscores, G, r, d->apply_exp, L.du, r, nullptr, 0, stream)); }
+  { ProfScope ps("tx_absmax", d->tag, st); TX_SUB(tx_absmax(L.du, r, G, r, L.du_amax, stream)); }
+  { ProfScope ps("tx_split_f16", d->tag, st); TX_SUB(tx_split_f16(L.du, r, G, r, L.du_amax, L.du_hi, L.du_lo, r8(r), L.du_scale, stream)); }
+  { ProfScope ps("tx_gemm_nt_f16x3", d->tag, st);                               // d(hg) = d(u) W^T
+    TX_SUB(tx_gemm_nt_f16x3(L.du_hi, L.du_lo, r8(r), S.w_hi, S.w_lo, r8(r), L.du_scale, S.w_scale, L.dhg, r4(l), G, l, r, nullptr, nullptr, stream)); }
+  const int64_t ldc = r4(r);
+  { ProfScope ps("tx_gemm_tn_f16x3", d->tag, st);                               // dW = hg^T d(u)
+    TX_SUB(tx_gemm_tn_f16x3(S.hg_hi, S.hg_lo, r8(l), L.du_hi, L.du_lo, r8(r), S.hg_scale, L.du_scale, L.splits > 1 ? L.tn_partial : dw, ldc, l * ldc,
+                            l, r, G, L.splits, stream));
+    if (L.splits > 1) TX_SUB(tx_reduce_partials(L.tn_partial, L.splits, l * ldc, dw, stream)); }
+  { ProfScope ps("tx_readout_bwd", d->tag, st);
+    TX_SUB(tx_readout_bwd(d->kind, L.dhg, r4(l), h, ldh, S.hg, l, d->pos, d->pos_weight, d->node_off, G, l, dh, l,
+                          d->kind == TX_READOUT_WMEAN && dpos_weight ? L.pw_partial : nullptr, stream)); }
+  if (d->kind == TX_READOUT_WMEAN && dpos_weight) {
+    ProfScope ps("tx_reduce_partials", d->tag, st);
+    TX_SUB(tx_reduce_partials(L.pw_partial, tx_readout_bwd_blocks(G), 3, dpos_weight, stream));
+  }
+  // every readout weight a_i / S, 1 / n_g is <= 1, so max|d(h)| <= max|d(hg)|: a 16 MB reduction instead of one over the 74 MB d(h)
+  { ProfScope ps("tx_absmax", d->tag, st); TX_SUB(tx_absmax(L.dhg, r4(l), G, l, L.dhg_amax, stream)); }
+  if (dh_amax_out) *dh_amax_out = L.dhg_amax;
+  return TX_OK;
+}
+
 // ---- launch accounting and per-launch timing of the calls above ----
 int64_t tx_layer_launches(int32_t reset) {
   const int64_t v = g_sub_launches;

@@ -19,7 +19,7 @@ from torch.autograd import Function
 from . import _lib
 import ctypes
 
-from ._lib import GatEpilogue, GatLayerDesc, GatLayerState, GcnLayerDesc, Stats, check, current_stream, device_guard, ptr, timed_region
+from ._lib import GatEpilogue, GatLayerDesc, GatLayerState, GcnLayerDesc, HeadDesc, HeadState, Stats, check, current_stream, device_guard, ptr, timed_region
 from .graph import GraphStructure
 
 _NEG_SLOPE_NONE = 1.0
@@ -1402,3 +1402,77 @@ class Readout(Function):
                 # 74 MB d(h); the output layer's backward picks it up if it receives exactly this tensor
                 st._dh_bound = (dh.data_ptr(), absmax(dhg))
         return dh, dw, None, None, None
+
+
+# --------------------------------------------------------------------------------------------------
+# Readout + bilinear matching as one native call per direction (tx_head_fwd / tx_head_bwd, tx_layer.cu)
+# --------------------------------------------------------------------------------------------------
+def head_native_ok(h: torch.Tensor, qf: torch.Tensor, kind: int, w: torch.Tensor) -> bool:
+    """TaxoExpan.forward's readout + match (model.py:85-86) run as one call when the default dense back-end is on, the readout is a
+    (weighted) mean and the matcher bilinear; everything else takes the two modules one after the other."""
+    return (LAYER_CALL and GEMM_BACKEND == "f16x3" and kind in (_lib.TX_READOUT_MEAN, _lib.TX_READOUT_WMEAN) and h.is_cuda and qf.is_cuda
+            and h.dtype == torch.float32 and qf.dtype == torch.float32 and h.dim() == 2 and qf.dim() == 2 and h.shape[0] > 0
+            and qf.shape[0] > 0 and h.stride(1) == 1 and qf.stride(1) == 1 and w.dim() == 2 and w.is_contiguous()
+            and w.shape[0] == h.shape[1] and w.shape[1] == qf.shape[1])
+
+
+class ReadoutMatch(Function):
+    """scores[g] = f(<readout(h)_g W, q_g>) (f = exp for LBM) with its whole autograd, one native call per direction; publishes
+    hg through `holder['hg']` for callers that want the graph embeddings."""
+
+    @staticmethod
+    def forward(ctx, h, pos_weight, w, qf, st: GraphStructure, pos32, kind, apply_exp):
+        lib = _lib.load()
+        n, D = h.shape
+        G, r = qf.shape
+        if G != st.g or n != st.n:
+            raise ValueError(f"readout + match: {n} node rows / {G} queries for a batch of {st.n} nodes / {st.g} graphs")
+        dev = h.device
+        with device_guard(dev):
+            Stats.sync_native_profiling()
+            d = HeadDesc()
+            d.n, d.g, d.dim, d.r, d.kind, d.apply_exp = n, G, D, r, kind, 1 if apply_exp else 0
+            pw = None if pos_weight is None else pos_weight.reshape(-1)
+            d.pos = None if pos32 is None else pos32.data_ptr()
+            d.node_off = st.node_off.data_ptr()
+            d.pos_weight = None if pw is None else pw.data_ptr()
+            d.w, d.ldw = w.data_ptr(), w.stride(0)
+            d.tag = b"head"
+            ws = torch.empty(int(lib.tx_head_fwd_bytes(ctypes.byref(d))), dtype=torch.uint8, device=dev)
+            state = HeadState()
+            scores = torch.empty((G, 1), dtype=torch.float32, device=dev)
+            check(lib.tx_head_fwd(ctypes.byref(d), ptr(h), h.stride(0), ptr(qf), qf.stride(0), ptr(ws), ctypes.byref(state), ptr(scores),
+                                  current_stream()), "tx_head_fwd")
+        st._dh_bound = None
+        ctx.native = (d, state, ws)
+        ctx.st = st
+        ctx.wshape = None if pos_weight is None else pos_weight.shape
+        ctx.save_for_backward(h, qf, w, pos_weight, pos32)
+        return scores
+
+    @staticmethod
+    def backward(ctx, dscores):
+        lib = _lib.load()
+        d, state, ws = ctx.native
+        h, qf, w, pos_weight, pos32 = ctx.saved_tensors
+        st = ctx.st
+        n, D = h.shape
+        r = qf.shape[1]
+        dev = h.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        with device_guard(dev):
+            Stats.sync_native_profiling()
+            dscores = dscores.reshape(-1).contiguous()
+            bws = torch.empty(int(lib.tx_head_bwd_bytes(ctypes.byref(d))), dtype=torch.uint8, device=dev)
+            dh = torch.empty((n, D), **f32)
+            dw_buf = torch.empty((D, round4(r)), **f32)
+            need_pw = pos_weight is not None and ctx.needs_input_grad[1]
+            dpw = torch.empty(3, **f32) if need_pw else None
+            amax = ctypes.c_void_p()
+            check(lib.tx_head_bwd(ctypes.byref(d), ctypes.byref(state), ptr(h), h.stride(0), ptr(qf), qf.stride(0), ptr(dscores), ptr(bws),
+                                  ptr(dh), ptr(dw_buf), ptr(dpw), ctypes.byref(amax), current_stream()), "tx_head_bwd")
+            # max|d(hg)| >= max|d(h)|: handed to the output layer's backward (it receives exactly this d(h))
+            off = amax.value - bws.data_ptr()
+            st._dh_bound = (dh.data_ptr(), bws[off:off + 4].view(torch.float32))
+        dw = dw_buf[:, :r] if ctx.needs_input_grad[2] else None
+        return dh, (dpw.view(ctx.wshape) if need_pw else None), dw, None, None, None, None, None

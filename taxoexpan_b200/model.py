@@ -5,6 +5,9 @@ import numpy as np
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import _lib
+from . import functional as txf
+from .graph import as_int32_pos
 from .model_zoo import GCN, GAT, PGCN, PGAT, MeanReadout, WeightedMeanReadout, ConcatReadout, MLP, BIM, LBM
 
 
@@ -70,6 +73,14 @@ class TaxoExpan(BaseModel):
             return h.new_zeros((0, 1))
         pos = g.ndata['pos'].to(h.device)
         g.ndata['h'] = self.graph_propagate(g, h)
+        kind = getattr(self.readout, "kind", None)
+        if type(self.match) in (BIM, LBM) and kind is not None and txf.head_native_ok(g.ndata['h'], qf, kind, self.match.W.weight[0]):
+            # model.py:85-86 as ONE native call per direction (readout, projection GEMM, row-dot; tx_head_fwd / tx_head_bwd): the same
+            # kernels as self.readout(g, pos) followed by self.match(hg, qf)
+            pw = getattr(self.readout, "position_weights", None)
+            pos32 = as_int32_pos(pos, h.device) if kind == _lib.TX_READOUT_WMEAN else None
+            return txf.ReadoutMatch.apply(g.ndata['h'], None if pw is None else pw.weight, self.match.W.weight[0], qf,
+                                          g.structure(h.device), pos32, kind, self.match.apply_exp)
         hg = self.readout(g, pos)
         scores = self.match(hg, qf)
         return scores

@@ -245,6 +245,7 @@ class PGCN(nn.Module):
 # =====================================================================================================
 class MeanReadout(nn.Module):
     """reference model_zoo.py:227-232"""
+    kind = _lib.TX_READOUT_MEAN
 
     def __init__(self):
         super().__init__()
@@ -256,6 +257,7 @@ class MeanReadout(nn.Module):
 
 class WeightedMeanReadout(nn.Module):
     """reference model_zoo.py:234-242"""
+    kind = _lib.TX_READOUT_WMEAN
 
     def __init__(self):
         super().__init__()
