@@ -199,8 +199,9 @@ class NegativeSampler:
     children: the reference draws the sub-sampled siblings of such an anchor with `random.choices` from the SAME module-level generator
     (`_get_subgraph`, dataset.py:416-424), interleaved with these shuffles, while the sibling draws here are counter-based
     (`counter_draws`) and leave the generator alone - after the first large anchor the reference's queue order moves on, this one's does
-    not (tests/test_sampler_cpu.py::test_negative_queue_diverges_from_the_reference_after_a_large_anchor documents it).  The
-    membership test runs on sorted mask arrays instead of Python sets."""
+    not (tests/test_sampler_cpu.py::test_negative_queue_diverges_from_the_reference_after_a_large_anchor documents it;
+    `ReplayTrainBatcher` below is the mode that follows the reference through such anchors too).  The membership test runs on sorted
+    mask arrays instead of Python sets."""
 
     def __init__(self, train_node_ids: Sequence[int], node2masks: Dict[int, np.ndarray], rng: Optional[random.Random] = None):
         self.queue = list(train_node_ids) * 5
@@ -322,6 +323,68 @@ class TrainBatcher:
         qf = self.features.index_select(0, torch.as_tensor(qs, dtype=torch.int64, device=dev))
         labels = torch.as_tensor(modes, dtype=torch.int64, device=dev)
         return bg, x, qf, labels
+
+
+class ReplayTrainBatcher(TrainBatcher):
+    """TrainBatcher that replays the reference's single-process loader (num_workers=0) DRAW FOR DRAW, sub-sampled anchors included.
+    The reference takes the siblings of an anchor with more than `expand_factor` children with `random.choices` from the same
+    generator that shuffles the negative queue (dataset.py:416-424), inside the per-item loop of `__getitem__` (dataset.py:290-332):
+    positive egonet first, then the queue walk, then the negatives' egonets, each negative read from the per-anchor cache until it has
+    been served `cache_refresh_time` times (dataset.py:383-402).  This batcher keeps exactly that order on the host - one
+    `rng.choices` per large anchor at the position the reference makes it, the same dict cache and counters - and hands the
+    resulting node-id lists to the device as one batch.  It trades the vectorised device construction of `TrainBatcher` for the
+    ability to continue a reference run bit for bit; `rng` must be the generator the NegativeSampler uses."""
+
+    def __init__(self, tax: TaxonomyCSR, features: torch.Tensor, node_list: Sequence[int], negatives: NegativeSampler,
+                 negative_size: int, expand_factor: int = 50, cache_refresh_time: int = 64):
+        super().__init__(tax, features, node_list, negatives, negative_size, expand_factor, cache=None)
+        self._chi_ptr = tax.chi_ptr.cpu().numpy()
+        self._chi_idx = tax.chi_idx.cpu().numpy()
+        self.rng = negatives.rng
+        self.cache_refresh_time = int(cache_refresh_time)
+        self._cached: Dict[int, tuple] = {}                 # anchor -> (grand-parents, siblings) of its last negative egonet
+        self._served: Dict[int, int] = {}
+
+    def _egonet(self, query: int, anchor: int, positive: bool):
+        """dataset.py:404-427 without the DGL object: (grand-parent ids, sibling ids)"""
+        gps = self._par_idx[self._par_ptr[anchor]:self._par_ptr[anchor + 1]].tolist()
+        children = self._chi_idx[self._chi_ptr[anchor]:self._chi_ptr[anchor + 1]].tolist()
+        if len(children) > self.expand_factor:
+            children = self.rng.choices(children, k=self.expand_factor)
+        if positive:
+            children = [c for c in children if c != query]
+        return gps, children
+
+    def _negative_egonet(self, query: int, anchor: int):
+        if anchor in self._cached and self._served[anchor] < self.cache_refresh_time:
+            self._served[anchor] += 1
+            return self._cached[anchor]
+        ego = self._egonet(query, anchor, False)
+        self._cached[anchor] = ego
+        self._served[anchor] = 0
+        return ego
+
+    def batch(self, indices: Sequence[int]):
+        ids, n_gp, n_sib, qs, modes = [], [], [], [], []
+
+        def push(q, a, ego, mode):
+            gps, sibs = ego
+            ids.extend(gps); ids.append(a); ids.extend(sibs)
+            n_gp.append(len(gps)); n_sib.append(len(sibs)); qs.append(q); modes.append(mode)
+
+        for i in indices:
+            q = self.node_list[int(i)]
+            p = self._next_parent(q)
+            push(q, p, self._egonet(q, p, True), 1)
+            for a in self.negatives.exactly_k(q, self.negative_size):
+                push(q, int(a), self._negative_egonet(q, int(a)), 0)
+        dev = self.features.device
+        bg = EgonetBatch.from_counts(np.asarray(n_gp, np.int32), np.asarray(n_sib, np.int32))
+        idt = torch.as_tensor(ids, dtype=torch.int64, device=dev)
+        bg.ndata["_id"] = idt
+        x = self.features.index_select(0, idt)
+        qf = self.features.index_select(0, torch.as_tensor(qs, dtype=torch.int64, device=dev))
+        return bg, x, qf, torch.as_tensor(modes, dtype=torch.int64, device=dev)
 
 
 BATCH_GRAPH_NODE_LIMIT = 100000      # data_loaders.py:7

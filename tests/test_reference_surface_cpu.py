@@ -146,6 +146,53 @@ def test_train_batcher_matches_the_unmodified_reference_dataset():
         assert dst.tolist() == [int(off[k]) + v for k, t in enumerate(item) for v in t[3]]
 
 
+def test_replay_batcher_follows_the_reference_through_sub_sampled_anchors():
+    """ReplayTrainBatcher against the unmodified MaskedGraphDataset with expand_factor BELOW most out-degrees: every large anchor
+    costs the reference one random.choices from the generator that also shuffles the negative queue (dataset.py:416-424), and the
+    per-anchor cache (dataset.py:383-402) decides when a negative is redrawn - node ids, order, labels and the queue walk must still
+    agree item for item over three passes (the case TrainBatcher's counter-based draws cannot replay)."""
+    import random
+
+    import numpy as np
+    import torch
+
+    from taxoexpan_b200 import sampler
+    rng = np.random.default_rng(23)
+    n, neg, seed, ef, refresh = 70, 7, 99, 2, 2
+    par = rng.integers(0, 12, 400)                         # few parents: out-degrees far above expand_factor
+    chi = rng.integers(0, n, 400)
+    keep = par < chi
+    edges = sorted(set(zip(par[keep].tolist(), chi[keep].tolist())), key=lambda e: (e[0], e[1]))
+    par, chi = [e[0] for e in edges], [e[1] for e in edges]
+    assert np.bincount(par).max() > 4 * ef
+    train = list(range(n))
+    indices = list(range(30)) * 3
+    spec = dict(n=n, par=par, chi=chi, train=train, seed=seed, neg=neg, ef=ef, refresh=refresh, indices=indices)
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "oracle", "dgl_shim"), REF]))
+    r = subprocess.run([sys.executable, "-c", DATASET_PROBE], input=json.dumps(spec), env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    ref = json.loads(r.stdout.strip().splitlines()[-1])
+
+    tax = sampler.TaxonomyCSR.from_edges(par, chi, n)
+    has_parent = set(chi)
+    roots = [v for v in range(n) if v not in has_parent]
+    node_list = ref["node_list"]
+    feats = torch.arange(n, dtype=torch.float32)[:, None].repeat(1, 3)
+    masks = sampler.taxonomy_masks(tax, node_list, roots)
+    batcher = sampler.ReplayTrainBatcher(tax, feats, node_list, sampler.NegativeSampler(train, masks, random.Random(seed)), neg,
+                                         expand_factor=ef, cache_refresh_time=refresh)
+    sampled = 0
+    for idx, item in zip(indices, ref["items"]):
+        bg, x, qf, labels = batcher.batch([idx])
+        assert labels.tolist() == [t[5] for t in item]
+        assert qf[:, 0].tolist() == [t[4] for t in item]
+        assert bg.ndata["_id"].tolist() == [v for t in item for v in t[0]]
+        assert bg.host_pos().tolist() == [v for t in item for v in t[1]]
+        assert x[:, 0].tolist() == [float(v) for t in item for v in t[0]]
+        sampled += sum(1 for t in item if t[1].count(2) == ef)
+    assert sampled > 100                                    # the sub-sampled branch was the common case
+
+
 RAW_PROBE = r'''
 import json, sys
 import dgl
