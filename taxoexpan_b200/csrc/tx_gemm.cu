@@ -240,10 +240,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   tcgen05_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * BN;
-  // LAST tile of a row of tiles: the MMA is issued only as wide as the columns that exist (rounded up to the instruction's N
-  // granularity - 16 - or, for MN-major B, to whole TMA boxes), e.g. N = 300 with BN = 192 costs 192 + 128 columns instead of 2 x 192.
-  // The operand loads are unchanged (rows / boxes past N are zero-filled by TMA and simply not read by the narrower MMA).
-  // gran = that granularity (0: always BN).  TN, no multicast: boxes past nd are not even fetched.
+  // LAST tile of a row of tiles: the MMA is issued only as wide as the columns that exist, rounded up to `gran` (the instruction's N
+  // granularity - 16 - or, for MN-major B, whole TMA boxes; 0 = always BN): N = 300 with BN = 192 costs 192 + 128 columns instead of
+  // 2 x 192, and (TN, no multicast) the boxes past nd are not even fetched.  Rows / boxes past N that are fetched are zero-filled by TMA.
+  // (The same narrowing in the cta_group::2 pair kernel bought nothing - its wide GEMMs are not limited by MMA issue slots, see
+  // profiles/r2_gemm_bound_analysis.txt - and the extra live values cost it 3-5 % at its 96-register cap, so it stays fixed-width.)
   const int nd = gran > 0 ? min(BN, ((n_store - n0 + gran - 1) / gran) * gran) : BN;
   const int kb0 = blockIdx.z * k_blocks_per_split;
   const int nkb = max(0, min(k_blocks_per_split, k_blocks_total - kb0));
@@ -453,13 +454,13 @@ __device__ __forceinline__ void mbar_arrive_cta0(uint32_t bar) {   // arrive on 
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
-template <int BN, int STAGES, bool TN, bool F16, int SLAB>
+template <int BN, int STAGES, bool TN, bool F16, bool SLAB>
 __global__ void __launch_bounds__(kPairThreads, 1)
 gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                         const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                         float* __restrict__ C, int64_t ldc, int64_t split_stride, int M, int n_store, int k_blocks_total,
                         int k_blocks_per_split, uint64_t mn_desc_bits, const GemmEpilogue epi, int n_tiles_n, int n_m_pairs,
-                        int n_work, int kChunk, int gran, int dbg) {
+                        int n_work, int kChunk) {
   constexpr int BK = 32;
   constexpr int BKE = F16 ? 2 * BK : BK;                  // reduction elements per k-block
   constexpr int BOXC = F16 ? 64 : 32;                     // TN: MN elements per box row
@@ -479,7 +480,7 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * NBUF);
-  float* stg = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);    // SLAB > 0: 16 epilogue warps x [SLAB][36] floats
+  float* stg = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);    // SLAB: 16 epilogue warps x [32][36] floats
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
   const uint32_t tfull0 = smem_u32(bars + 2 * STAGES), tempty0 = smem_u32(bars + 2 * STAGES + NBUF);
@@ -514,19 +515,12 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
   // linear list (n tile fastest, then M-tile pair, then k split), so that the epilogue of one tile (accumulator drain + global
   // stores) overlaps the TMA / MMA stream of the next: the smem ring and the two TMEM buffers simply keep rotating across tiles.
   const int n_clusters = (int)(gridDim.x >> 1), cluster_id = (int)(blockIdx.x >> 1);
-  // nd = width the MMAs of this tile are issued with: BN, or for the last tile of a row of tiles only the columns that exist, rounded
-  // up to the instruction's granularity (K-major B: N % 16 == 0, i.e. 8-row groups in each CTA's half; MN-major B: whole 64- /
-  // 32-column boxes in each CTA's half).  N = 2050 with BN = 256 then costs 8 tiles + 16 (NT) or 128 (TN) columns instead of 9 tiles.
-  // CTA r of the pair supplies B rows / columns [n0 + r nd/2, n0 + (r + 1) nd/2): its loads start there; their size is unchanged
-  // (what lies past N is zero-filled by TMA, what lies past nd/2 is not read by the narrower MMA).
-  // gran = that granularity (0: always BN)
-  auto work_coords = [&](int w, int& m0, int& n0, int& kb0, int& nkb, int& z, int& nd) {
+  auto work_coords = [&](int w, int& m0, int& n0, int& kb0, int& nkb, int& z) {
     const int n_idx = w % n_tiles_n, rest = w / n_tiles_n;
     const int mp = rest % n_m_pairs;
     z = rest / n_m_pairs;
     m0 = (mp * 2 + (int)crank) * kBM;
     n0 = n_idx * BN;
-    nd = gran > 0 ? min(BN, ((n_store - n0 + gran - 1) / gran) * gran) : BN;
     kb0 = z * k_blocks_per_split;
     nkb = max(0, min(k_blocks_per_split, k_blocks_total - kb0));
   };
@@ -535,8 +529,8 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
     if (lane == 0) {   // ===== TMA producer (both CTAs) =====
       int gkb = 0;       // k-blocks issued so far by this CTA (ring position)
       for (int w = cluster_id; w < n_work; w += n_clusters) {
-      int m0, n0, kb0, nkb, z, nd;
-      work_coords(w, m0, n0, kb0, nkb, z, nd);
+      int m0, n0, kb0, nkb, z;
+      work_coords(w, m0, n0, kb0, nkb, z);
       for (int kb = 0; kb < nkb; ++kb, ++gkb) {
         const int s = gkb % STAGES;
         const uint32_t ph = (gkb / STAGES) & 1;
@@ -548,8 +542,8 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
         if constexpr (!TN) {
           tma_load_2d_pair(base, &map_a_hi, full, kk, m0);
           tma_load_2d_pair(base + kABytes, &map_a_lo, full, kk, m0);
-          tma_load_2d_pair(base + 2 * kABytes, &map_b_hi, full, kk, n0 + (int)crank * (nd >> 1));
-          tma_load_2d_pair(base + 2 * kABytes + BH_BYTES, &map_b_lo, full, kk, n0 + (int)crank * (nd >> 1));
+          tma_load_2d_pair(base + 2 * kABytes, &map_b_hi, full, kk, n0 + (int)crank * BH);
+          tma_load_2d_pair(base + 2 * kABytes + BH_BYTES, &map_b_lo, full, kk, n0 + (int)crank * BH);
         } else {
 #pragma unroll
           for (int b = 0; b < kBM / BOXC; ++b) {
@@ -558,8 +552,8 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
           }
 #pragma unroll
           for (int b = 0; b < BH / BOXC; ++b) {
-            tma_load_2d_pair(base + 2 * kABytes + b * BOX_BYTES, &map_b_hi, full, n0 + (int)crank * (nd >> 1) + BOXC * b, kk);
-            tma_load_2d_pair(base + 2 * kABytes + BH_BYTES + b * BOX_BYTES, &map_b_lo, full, n0 + (int)crank * (nd >> 1) + BOXC * b, kk);
+            tma_load_2d_pair(base + 2 * kABytes + b * BOX_BYTES, &map_b_hi, full, n0 + (int)crank * BH + BOXC * b, kk);
+            tma_load_2d_pair(base + 2 * kABytes + BH_BYTES + b * BOX_BYTES, &map_b_lo, full, n0 + (int)crank * BH + BOXC * b, kk);
           }
         }
       }
@@ -567,13 +561,12 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
     }
   } else if (warp == 1) {
     if (leader && lane == 0) {   // ===== MMA issuer (leader CTA only) =====
-      const uint32_t idesc0 = (1u << 4) | (F16 ? 0u : ((2u << 7) | (2u << 10))) | (TN ? ((1u << 15) | (1u << 16)) : 0u) |
-                              ((uint32_t)((2 * kBM) >> 4) << 24);       // M = 256 across the pair
+      const uint32_t idesc = (1u << 4) | (F16 ? 0u : ((2u << 7) | (2u << 10))) | (TN ? ((1u << 15) | (1u << 16)) : 0u) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * kBM) >> 4) << 24);       // M = 256 across the pair
       int gkb = 0, gch = 0;     // k-blocks / chunks consumed so far (ring and TMEM buffer positions)
       for (int w = cluster_id; w < n_work; w += n_clusters) {
-      int m0, n0, kb0, nkb, z, nd;
-      work_coords(w, m0, n0, kb0, nkb, z, nd);
-      const uint32_t idesc = idesc0 | ((uint32_t)(nd >> 3) << 17);
+      int m0, n0, kb0, nkb, z;
+      work_coords(w, m0, n0, kb0, nkb, z);
       const int n_chunks = (nkb + kChunk - 1) / kChunk;
       for (int ch = 0; ch < n_chunks; ++ch, ++gch) {
         const int buf = gch % NBUF;
@@ -599,7 +592,6 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
           for (int k = 0; k < BK / 8; ++k) {
             const uint64_t adv = TN ? (uint64_t)((k * (F16 ? 2048 : 1024)) >> 4) : (uint64_t)(2 * k);
             const uint32_t first = (kb == ch * kChunk && k == 0) ? 0u : 1u;
-            if (dbg & 8) { umma_tf32_pair<F16>(tacc, a_hi + adv, b_hi + adv, idesc, first); continue; }
             umma_tf32_pair<F16>(tacc, a_lo + adv, b_hi + adv, idesc, first);
             umma_tf32_pair<F16>(tacc, a_hi + adv, b_lo + adv, idesc, 1u);
             umma_tf32_pair<F16>(tacc, a_hi + adv, b_hi + adv, idesc, 1u);
@@ -617,8 +609,8 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
     float vmax = 0.f;
     int gch = 0;
     for (int w = cluster_id; w < n_work; w += n_clusters) {
-    int m0, n0, kb0, nkb, z, nd;
-    work_coords(w, m0, n0, kb0, nkb, z, nd);
+    int m0, n0, kb0, nkb, z;
+    work_coords(w, m0, n0, kb0, nkb, z);
     const int n_chunks = (nkb + kChunk - 1) / kChunk;
     float acc[SL];
 #pragma unroll
@@ -642,12 +634,10 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
       const uint32_t tacc = tmem_base + (uint32_t)(buf * BN + hsel * SL) + ((uint32_t)(q * 32) << 16);
 #pragma unroll
       for (int c = 0; c < SL / 16; ++c) {
-        if (hsel * SL + c * 16 < nd && !(dbg & 4)) {              // warp-uniform: columns >= nd were not computed for this tile
-          uint32_t r[16];
-          tmem_ld16(tacc + (uint32_t)(c * 16), r);
+        uint32_t r[16];
+        tmem_ld16(tacc + (uint32_t)(c * 16), r);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) acc[c * 16 + j] += __uint_as_float(r[j]);
-        }
+        for (int j = 0; j < 16; ++j) acc[c * 16 + j] += __uint_as_float(r[j]);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -655,22 +645,19 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
         if (leader) mbar_arrive(tempty0 + 8 * buf); else mbar_arrive_cta0(tempty0 + 8 * buf);
       }
     }
-    if (dbg & 2) continue;
-    if constexpr (SLAB > 0) {
-      // Stores through a per-warp shared-memory slab (SLAB rows x 32 columns, pitch 36 floats: conflict-free both ways).  A thread owns
+    if constexpr (SLAB) {
+      // Stores through a per-warp shared-memory slab (32 rows x 32 columns, pitch 36 floats: conflict-free both ways).  A thread owns
       // one ROW of the accumulator, so storing straight from registers makes every STG touch 32 different lines with 16 bytes each
       // (half sectors); ncu shows the epilogue warps stalled on exactly those stores (the next write of the store's source register
       // waits until the LSU has drained it).  After the transpose one STG writes 4 rows x 128 contiguous bytes: full lines.
-      // SLAB = 32: the warp's 32 rows at once (73 KB for the 16 warps - leaves room for a 2-stage operand ring only); SLAB = 8: four
-      // passes of 8 rows (18 KB, 3-stage ring).
-      float* slab = stg + (warp - 2) * (SLAB * 36);
+      float* slab = stg + (warp - 2) * (32 * 36);
       const int row_base = m0 + q * 32;
 #pragma unroll
       for (int g2 = 0; g2 < SL / 32; ++g2) {
         const int colg = n0 + hsel * SL + g2 * 32;
         if (colg < n_store) {                                     // warp-uniform
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {                           // scale / mask in place
+          for (int u = 0; u < 8; ++u) {
             const int j = g2 * 8 + u;
             const int col = colg + u * 4;
             float4 v = make_float4(acc[4 * j] * inv_scale, acc[4 * j + 1] * inv_scale, acc[4 * j + 2] * inv_scale, acc[4 * j + 3] * inv_scale);
@@ -685,30 +672,17 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
               }
               vmax = fmaxf(vmax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
             }
-            acc[4 * j] = v.x; acc[4 * j + 1] = v.y; acc[4 * j + 2] = v.z; acc[4 * j + 3] = v.w;
+            *reinterpret_cast<float4*>(slab + lane * 36 + u * 4) = v;
           }
+          __syncwarp();
 #pragma unroll
-          for (int pass = 0; pass < 32 / SLAB; ++pass) {
-            if (SLAB == 32 || (lane / SLAB) == pass) {
-#pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                const int j = g2 * 8 + u;
-                *reinterpret_cast<float4*>(slab + (lane % SLAB) * 36 + u * 4) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-              }
-            }
-            __syncwarp();
-#pragma unroll
-            for (int t = 0; t < SLAB / 4; ++t) {
-              const int rl = 4 * t + (lane >> 3), c4 = lane & 7;
-              const int grow = row_base + pass * SLAB + rl, col = colg + c4 * 4;
-              if (grow < M && col < n_store && !(dbg & 1)) {
-                float4* dst = reinterpret_cast<float4*>(C + (int64_t)z * split_stride + (int64_t)grow * ldc + col);
-                const float4 val = *reinterpret_cast<const float4*>(slab + rl * 36 + c4 * 4);
-                *dst = val;      // (st.global.cs / .wt hints: measured, no effect)
-              }
-            }
-            __syncwarp();
+          for (int t = 0; t < 8; ++t) {
+            const int rl = 4 * t + (lane >> 3), c4 = lane & 7;
+            const int grow = row_base + rl, col = colg + c4 * 4;
+            if (grow < M && col < n_store)
+              *reinterpret_cast<float4*>(C + (int64_t)z * split_stride + (int64_t)grow * ldc + col) = *reinterpret_cast<const float4*>(slab + rl * 36 + c4 * 4);
           }
+          __syncwarp();
         }
       }
     } else if (row < M) {
@@ -793,8 +767,16 @@ __global__ void absmax_kernel(const float* __restrict__ x, int64_t ldx, int rows
       m = fmaxf(m, fabsf(__ldg(x + (int64_t)i * ldx + c)));
     }
   }
+  // one atomic per CTA: ~9.5 k same-address atomics (one per warp) serialised in L2 and cost 10 us on a 16 MB input
+  __shared__ float s_m[8];
   m = warp_max(m);
-  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(m));
+  if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? s_m[threadIdx.x] : 0.f;
+    m = warp_max(m);
+    if (threadIdx.x == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(m));
+  }
 }
 
 // max |v[0 .. len)| over one 256-thread block (small parameter vectors / tables), returned to every thread
@@ -882,13 +864,17 @@ __global__ void __launch_bounds__(256, kSplitWCtasPerSm) split_f16_weight_kernel
       m = fmaxf(m, fabsf(__ldg(w + (int64_t)i * ldw + c)));
     }
   }
+  __shared__ float s_m[8];
   m = warp_max(m);
-  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned int*>(amax), __float_as_uint(m));
-  __threadfence();
+  if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0) {                   // one atomicMax per CTA (same-address atomics serialise in L2), then the arrival
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, s_m[w]);
+    if (m > 0.f) atomicMax(reinterpret_cast<unsigned int*>(amax), __float_as_uint(m));
+    __threadfence();
     atomicAdd(counter, 1u);
-    while (atomicAdd(counter, 0u) < gridDim.x) __nanosleep(64);
+    while (*reinterpret_cast<volatile unsigned int*>(counter) < gridDim.x) __nanosleep(32);
   }
   __syncthreads();
   const float scale = f16_split_scale(__ldcg(amax));
@@ -964,23 +950,14 @@ static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t co
   return TX_OK;
 }
 
-// Granularity of the last tile's MMA width (see the kernels): `natural` = the finest the operand layout allows (16 columns for K-major
-// B; whole boxes per CTA for MN-major B).  TAXO_GEMM_DYN_N=0 switches the narrowing off, =<g> forces a coarser multiple of `natural`.
+// Granularity of the last tile's MMA width in the single-CTA kernel: `natural` = the finest the operand layout allows (16 columns for
+// K-major B; whole boxes for MN-major B).  TAXO_GEMM_DYN_N=0 switches the narrowing off, =<g> forces a coarser multiple of `natural`.
 static int dyn_n_gran(int natural) {
   static int v = -2;
   if (v == -2) { const char* e = getenv("TAXO_GEMM_DYN_N"); v = e ? atoi(e) : -1; }
   if (v < 0) return natural;
   if (v == 0) return 0;
   return ((v + natural - 1) / natural) * natural;
-}
-
-// PROFILING ONLY (results are wrong with any bit set): TAXO_GEMM_DBG bit 0 = no global stores of C, bit 1 = no tile-end phase at all,
-// bit 2 = no accumulator drains, bit 3 = one MMA per k-step instead of three.  Used to separate the operand-load, MMA and epilogue
-// floors of the pair kernel (profiles/r2_gemm_bound_analysis.txt).
-static int gemm_dbg() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("TAXO_GEMM_DBG"); v = e ? atoi(e) : 0; }
-  return v;
 }
 
 template <int BN, int STAGES, bool TN, int BK = 32, int CL = 1, bool F16 = false>
@@ -1062,7 +1039,7 @@ static int launch_gemm(const void* a_hi, const void* a_lo, int64_t lda, const vo
   return TX_OK;
 }
 
-template <int BN, int STAGES, bool TN, bool F16 = false, int SLAB = 0>
+template <int BN, int STAGES, bool TN, bool F16 = false, bool SLAB = false>
 static int launch_gemm_pair(const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi, const void* b_lo, int64_t ldb,
                             float* c, int64_t ldc, int64_t split_stride, int64_t M, int64_t N, int64_t K, int splits, cudaStream_t st,
                             const GemmEpilogue& epi = GemmEpilogue{nullptr, 0, 1, 0, 0, 0, 1.f, 1.f, nullptr, nullptr, nullptr}) {
@@ -1085,7 +1062,7 @@ static int launch_gemm_pair(const void* a_hi, const void* a_lo, int64_t lda, con
     if ((rc = make_map(&mb_lo, b_lo, K, N, ldb, BKE, sw, BOXC, F16)) != TX_OK) return rc;
   }
   constexpr int STAGE_BYTES = 2 * kBM * BK * 4 + 2 * (BN / 2) * BK * 4;
-  constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256 + (size_t)(16 * SLAB * 36 * 4);
+  constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256 + (SLAB ? 16 * 32 * 36 * 4 : 0);
   static_assert(SMEM <= 227 * 1024, "pair kernel: shared memory budget");
   static bool attr_done = false;
   if (!attr_done) {
@@ -1130,8 +1107,7 @@ static int launch_gemm_pair(const void* a_hi, const void* a_lo, int64_t lda, con
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tf32x3_pair_kernel<BN, STAGES, TN, F16, SLAB>, ma_hi, ma_lo, mb_hi, mb_lo, c, ldc, split_stride,
-                                     (int)M, (int)n_store, kbt, kbs, mn_bits, epi, n_tiles_n, n_m_pairs, n_work, chunk_kb,
-                                     dyn_n_gran(TN ? (F16 ? 128 : 64) : 16), gemm_dbg());
+                                     (int)M, (int)n_store, kbt, kbs, mn_bits, epi, n_tiles_n, n_m_pairs, n_work, chunk_kb);
   if (e != cudaSuccess) {
     set_error("gemm(pair): cluster launch failed: %s", cudaGetErrorString(e));
     return TX_ERR_CUDA;
@@ -1374,12 +1350,7 @@ int tx_gemm_nt_f16x3(const void* a_hi, const void* a_lo, int64_t lda, const void
     // short reductions with wide outputs (fwd L0: K = 300, dz L1: K = 500) are bound by the stores of C: 2-stage ring + store slabs
     static int slab_k = -1;
     if (slab_k < 0) { const char* e_s = getenv("TAXO_GEMM_SLAB_K"); slab_k = e_s ? atoi(e_s) : 640; }
-    // 32: 2-stage ring + 32-row slabs (default); TAXO_GEMM_SLAB_ROWS=8: 3-stage ring + 8-row slabs in four passes - measured equal on
-    // dz L1 (0.234 ms both) and slower on fwd L0 (0.158 vs 0.146 ms): the ring depth is not what limits these two GEMMs
-    static int slab_rows = -1;
-    if (slab_rows < 0) { const char* e_r = getenv("TAXO_GEMM_SLAB_ROWS"); slab_rows = e_r ? atoi(e_r) : 32; }
-    if (k <= slab_k && slab_rows == 8) return launch_gemm_pair<256, 3, false, true, 8>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
-    if (k <= slab_k) return launch_gemm_pair<256, 2, false, true, 32>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
+    if (k <= slab_k) return launch_gemm_pair<256, 2, false, true, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
     return launch_gemm_pair<256, 3, false, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, 0, m, n, k, 1, st, epi);
   }
   if (use_cluster() && m > kBM && n > 128) {

@@ -524,7 +524,15 @@ __global__ void attn_grad_from_v_kernel(const float* __restrict__ w, int64_t ldw
   const float* v1 = v + (int64_t)h * ldv;
   const float* v2 = v + (int64_t)(H + h) * ldv;
   float a = 0.f, b = 0.f;
-  for (int k = lane; k < K; k += 32) {
+  int k = lane;
+  for (; k + 7 * 32 < K; k += 8 * 32) {          // 24 independent loads in flight (K = 2050: the plain loop was 64 dependent round trips)
+    float x[8], y1[8], y2[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { x[u] = __ldg(wr + k + 32 * u); y1[u] = __ldg(v1 + k + 32 * u); y2[u] = __ldg(v2 + k + 32 * u); }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { a = fmaf(x[u], y1[u], a); b = fmaf(x[u], y2[u], b); }
+  }
+  for (; k < K; k += 32) {
     const float x = __ldg(wr + k);
     a = fmaf(x, __ldg(v1 + k), a);
     b = fmaf(x, __ldg(v2 + k), b);
