@@ -94,6 +94,13 @@ int tx_star_batch_plan(const int32_t* n_gp, const int32_t* n_sib, int64_t n_grap
 int tx_concat_pos_dropout_fwd(const float* x, int64_t ldx, const float* pos_table, const int32_t* pos,
                               int64_t n_nodes, int64_t k_in, int64_t pos_dim, float* z, int64_t ldz, float p_drop,
                               uint64_t seed, uint32_t stream_id, void* stream);
+/* The same, emitted directly as the fp16 hi / lo operand pair (x * scale = hi + lo, scale = a power of two from the bound
+ * max(*x_amax, max|pos_table|) / (1 - p_drop); *x_amax = max|x| on the device, e.g. from tx_absmax) that the first layer's projection
+ * GEMM reads - z itself is never stored.  Keep decisions are those of tx_concat_pos_dropout_fwd with ldz = round4(k_in + pos_dim).
+ * hi / lo: [n_nodes, ld16] halves, ld16 % 8 == 0, columns >= k_in + pos_dim zero-filled; *scale_out receives the scale. */
+int tx_concat_pos_dropout_f16(const float* x, int64_t ldx, const float* pos_table, const int32_t* pos, int64_t n_nodes, int64_t k_in,
+                              int64_t pos_dim, int64_t vocab, float p_drop, uint64_t seed, uint32_t stream_id, const float* x_amax,
+                              void* hi, void* lo, int64_t ld16, float* scale_out, void* stream);
 
 /* Backward of an "activation -> [.|| P[pos]] -> dropout" epilogue, in place:
  *   dz[i,c] *= keep(i,c)/(1-p) * (c < k_in ? act'(z[i,c]) : 1)          (act' = 1 where z > 0 else slope)

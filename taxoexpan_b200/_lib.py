@@ -96,6 +96,7 @@ _SIGNATURES = {
     "tx_star_batch_plan": [P, P, I64, I64, I64, P, P, P, P, P],
     "tx_gather_rows": [P, I64, I64, P, I64, I64, P, I64, P],
     "tx_concat_pos_dropout_fwd": [P, I64, P, P, I64, I64, I64, P, I64, F32, c_uint64, c_uint32, P],
+    "tx_concat_pos_dropout_f16": [P, I64, P, P, I64, I64, I64, I64, F32, c_uint64, c_uint32, P, P, P, I64, P, P],
     "tx_epilogue_bwd": [P, I64, P, P, I64, I64, I64, I64, F32, F32, c_uint64, c_uint32, P, P],
     "tx_reduce_partials": [P, I64, I64, P, P],
     "tx_colsum_partials": [P, I64, I64, I64, P, P],

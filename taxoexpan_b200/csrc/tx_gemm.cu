@@ -750,7 +750,15 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, int64_t ldx, int 
 // ---- fp16 split path: per-tensor bounds and scales live in DEVICE scalars, so nothing here synchronises with the host ----
 __global__ void absmax_kernel(const float* __restrict__ x, int64_t ldx, int rows, int cols, float* __restrict__ out) {
   float m = 0.f;
-  if ((ldx & 3) == 0 && (cols & 3) == 0 && aligned16(x)) {      // 128-bit loads, one division per 4 elements
+  if (ldx == cols && aligned16(x)) {                            // a contiguous block (e.g. [N, 250] features): flat 128-bit loads + tail
+    const int64_t total = (int64_t)rows * cols, n4 = total >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (int64_t)gridDim.x * blockDim.x) {
+      const float4 v = __ldg(x4 + t);
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (int)(total - (n4 << 2))) m = fmaxf(m, fabsf(__ldg(x + (n4 << 2) + threadIdx.x)));
+  } else if ((ldx & 3) == 0 && (cols & 3) == 0 && aligned16(x)) {      // 128-bit loads, one division per 4 elements
     const int vpr = cols >> 2;
     const int64_t total = (int64_t)rows * vpr;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {

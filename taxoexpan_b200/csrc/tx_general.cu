@@ -111,6 +111,62 @@ __global__ void concat_pos_dropout_fwd_kernel(const float* __restrict__ x, int64
   }
 }
 
+// The same, written straight as the fp16 hi / lo operand pair of the first layer's projection GEMM (z itself is never stored): the
+// scale comes from the bound max(max|x|, max|P|) / (1 - p) - every CTA derives it from the device scalar x_amax and the (tiny) table -
+// and the keep decisions use the SAME counters as the fp32 kernel (row pitch ldz = round4(k_in + pd)), so tx_pos_grad_partials /
+// tx_epilogue_bwd rebuild the identical mask in the backward pass.
+__global__ void __launch_bounds__(256) concat_pos_dropout_f16_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ ptab,
+                                                                     const int32_t* __restrict__ pos, int n, int k_in, int pd, int vocab,
+                                                                     const float* __restrict__ x_amax, __half* __restrict__ hi,
+                                                                     __half* __restrict__ lo, int ld16, int ldz, float inv_keep,
+                                                                     uint32_t thr, uint64_t seed, uint32_t stream_id,
+                                                                     float* __restrict__ scale_out) {
+  __shared__ float s_m[8];
+  float m = 0.f;
+  for (int t = threadIdx.x; t < vocab * pd; t += blockDim.x) m = fmaxf(m, fabsf(__ldg(ptab + t)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = __ldg(x_amax);
+#pragma unroll
+  for (int w = 0; w < 8; ++w) m = fmaxf(m, s_m[w]);
+  const float scale = f16_split_scale(m * inv_keep);
+  if (scale_out && blockIdx.x == 0 && threadIdx.x == 0) *scale_out = scale;
+  const int vec_per_row = ld16 >> 2;
+  const int64_t total = (int64_t)n * vec_per_row;
+  const bool x_vec2 = (ldx & 1) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t / vec_per_row);
+    const int c0 = (int)(t - (int64_t)i * vec_per_row) << 2;
+    float v[4];
+    if (x_vec2 && c0 + 3 < k_in) {                     // even row pitch: two 64-bit loads (a [N, 250] feature block is 8-byte aligned per row)
+      const float2 a = __ldg(reinterpret_cast<const float2*>(x + (int64_t)i * ldx + c0));
+      const float2 b = __ldg(reinterpret_cast<const float2*>(x + (int64_t)i * ldx + c0 + 2));
+      v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + u;
+        float val = 0.f;
+        if (c < k_in) val = __ldg(x + (int64_t)i * ldx + c);
+        else if (c < k_in + pd) val = __ldg(ptab + (int64_t)__ldg(pos + i) * pd + (c - k_in));
+        v[u] = val;
+      }
+    }
+    if (thr && c0 < ldz) {
+      bool keep[4];
+      drop_keep4(seed, stream_id, (uint64_t)(((int64_t)i * ldz + c0) >> 2), thr, keep);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = keep[u] ? v[u] * inv_keep : 0.f;
+    }
+    uint2 h, l;
+    f16_split4(make_float4(v[0], v[1], v[2], v[3]), scale, h, l);
+    *reinterpret_cast<uint2*>(hi + (int64_t)i * ld16 + c0) = h;
+    *reinterpret_cast<uint2*>(lo + (int64_t)i * ld16 + c0) = l;
+  }
+}
+
 // =============================================================================================
 // epilogue backward (in place) + position-table gradient partials
 // =============================================================================================
@@ -1111,6 +1167,27 @@ int tx_concat_pos_dropout_fwd(const float* x, int64_t ldx, const float* pos_tabl
                                                                         (int)pos_dim, z, (int)ldz, 1.f / (1.f - p_drop),
                                                                         drop_threshold(p_drop), seed, stream_id);
   TX_LAUNCH_CHECK("tx_concat_pos_dropout_fwd");
+  return TX_OK;
+}
+
+int tx_concat_pos_dropout_f16(const float* x, int64_t ldx, const float* pos_table, const int32_t* pos, int64_t n_nodes, int64_t k_in,
+                              int64_t pos_dim, int64_t vocab, float p_drop, uint64_t seed, uint32_t stream_id, const float* x_amax,
+                              void* hi, void* lo, int64_t ld16, float* scale_out, void* stream) {
+  TX_REQUIRE(n_nodes >= 0 && k_in >= 0 && pos_dim >= 0 && vocab >= 0, "concat_f16: negative size");
+  TX_REQUIRE(ld16 >= k_in + pos_dim && ld16 % 8 == 0 && aligned16(hi) && aligned16(lo), "concat_f16: outputs need ld %% 8 == 0, ld >= k_in+pos_dim, 16B alignment");
+  TX_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "concat_f16: p_drop must be in [0,1)");
+  TX_REQUIRE(pos_dim == 0 || (pos_table && pos && vocab > 0), "concat_f16: pos_dim > 0 needs pos_table, pos and vocab");
+  TX_REQUIRE(x_amax && scale_out, "concat_f16: x_amax (device max|x|, tx_absmax) and scale_out are required");
+  TX_REQUIRE(n_nodes * ld16 < (int64_t)1 << 40 && n_nodes < INT32_MAX, "concat_f16: too large");
+  if (n_nodes == 0) return TX_OK;
+  const int64_t total = n_nodes * (ld16 / 4);
+  const int grid = (int)((total + 255) / 256 < (int64_t)kNumSms * 16 ? (total + 255) / 256 : (int64_t)kNumSms * 16);
+  const int64_t ldz = ((k_in + pos_dim + 3) / 4) * 4;
+  concat_pos_dropout_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, pos_table, pos, (int)n_nodes, (int)k_in, (int)pos_dim,
+                                                                        (int)(pos_dim > 0 ? vocab : 0), x_amax, (__half*)hi, (__half*)lo,
+                                                                        (int)ld16, (int)ldz, 1.f / (1.f - p_drop), drop_threshold(p_drop),
+                                                                        seed, stream_id, scale_out);
+  TX_LAUNCH_CHECK("tx_concat_pos_dropout_f16");
   return TX_OK;
 }
 

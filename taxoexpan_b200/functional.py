@@ -91,6 +91,10 @@ def _star_queue(device) -> torch.Tensor:
 # one C-ABI call per GAT layer and direction (tx_layer.cu: same kernels, arguments and order, one workspace) whenever the layer runs the
 # default hot path (fp16-pair GEMMs, star forward / backward on an EgonetBatch); TAXO_LAYER_CALL=0 -> one ctypes call per kernel
 LAYER_CALL = os.environ.get("TAXO_LAYER_CALL", "1") not in ("", "0")
+# layer-0 input drop([x || P[pos]]) written directly as the fp16 operand pair of the first projection GEMM (tx_concat_pos_dropout_f16:
+# one pass over x for max|x|, one pass that reads x and writes the pair) instead of fp32 z -> max|z| -> split (three passes over z);
+# TAXO_CONCAT_F16=0 -> the fp32 z
+CONCAT_F16 = os.environ.get("TAXO_CONCAT_F16", "1") not in ("", "0")
 
 _star_counter_bufs = {}
 _star_rerun_bufs = {}
@@ -448,9 +452,15 @@ def dropout_keep_mask(seed: int, stream_id: int, first_index: int, n: int, p: fl
 # --------------------------------------------------------------------------------------------------
 # z = drop([x || P[pos]])
 # --------------------------------------------------------------------------------------------------
+def concat_publishes_f16() -> bool:
+    """The layer-0 input is written straight as the fp16 operand pair of the first projection GEMM (tx_concat_pos_dropout_f16) when the
+    default dense back-end consumes such pairs; any other configuration gets the fp32 z of tx_concat_pos_dropout_fwd."""
+    return CONCAT_F16 and GEMM_BACKEND == "f16x3" and FUSE_SPLIT
+
+
 class ConcatPosDropout(Function):
     @staticmethod
-    def forward(ctx, x, pos_table, pos32, p, seed, stream_id):
+    def forward(ctx, x, pos_table, pos32, p, seed, stream_id, link=None):
         lib = _lib.load()
         _check_cuda(x, "features")
         x = _rowmajor(x)
@@ -460,6 +470,26 @@ class ConcatPosDropout(Function):
         ldz = round4(k_in + pd)
         z = torch.empty((n, ldz), dtype=torch.float32, device=x.device)
         tab = None if pos_table is None else pos_table.contiguous()
+        if link is not None and n > 0 and concat_publishes_f16():
+            # z is published to the first layer as an fp16 hi / lo pair in one workspace [hi | lo | scale]; `z` stays a placeholder
+            # (never written), exactly like the output of a hidden layer that hands its successor a pair
+            ld16 = round8(k_in + pd)
+            half_bytes = n * ld16 * 2
+            with device_guard(x.device):
+                Stats.tag = "L0"
+                ws = torch.empty(2 * half_bytes + 16, dtype=torch.uint8, device=x.device)
+                x_amax = absmax(x, k_in)
+                base = ws.data_ptr()
+                check(lib.tx_concat_pos_dropout_f16(ptr(x), x.stride(0) if n > 1 else k_in, ptr(tab), ptr(pos32), n, k_in, pd, vocab, p, seed,
+                                                    stream_id, ptr(x_amax), base, base + half_bytes, ld16, base + 2 * half_bytes,
+                                                    current_stream()), "tx_concat_pos_dropout_f16")
+            state = _lib.GatLayerState()
+            state.out_hi, state.out_lo, state.out_scale, state.ld16_out = base, base + half_bytes, base + 2 * half_bytes, ld16
+            link.c_state, link.c_ws, link.c_dims = state, ws, (n, k_in + pd, ld16, 0)
+            link.applied, link.z16, link.z_lo, link.dz_amax, link.c_bwd, link.mask = False, None, None, None, None, None
+            ctx.save_for_backward(pos32 if pos32 is not None else torch.empty(0))
+            ctx.meta = (n, k_in, pd, vocab, ldz, float(p), int(seed), int(stream_id))
+            return z
         with device_guard(x.device):
             check(lib.tx_concat_pos_dropout_fwd(ptr(x), x.stride(0) if n > 1 else k_in, ptr(tab), ptr(pos32), n, k_in, pd,
                                                 ptr(z), ldz, p, seed, stream_id, current_stream()),
@@ -476,7 +506,7 @@ class ConcatPosDropout(Function):
         need_x, need_tab = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and pd > 0
         dx = dtab = None
         if not (need_x or need_tab):
-            return None, None, None, None, None, None
+            return None, None, None, None, None, None, None
         dz = _rowmajor(dz)
         if n > 1 and dz.stride(0) != ldz:
             dz = dz.contiguous()              # the keep-mask counters are indexed with the forward's row pitch ldz
@@ -489,7 +519,7 @@ class ConcatPosDropout(Function):
                 check(lib.tx_pos_grad_partials(ptr(dz), dz.stride(0) if n > 1 else ldz, k_in, ptr(pos32), n, pd, vocab, p, seed, stream_id,
                                                ptr(partial), current_stream()), "tx_pos_grad_partials")
                 dtab = _reduce_partials(lib, partial, nb, vocab * pd).view(vocab, pd)
-            return None, dtab, None, None, None, None
+            return None, dtab, None, None, None, None, None
         if p > 0.0:
             dz = dz.clone()      # the kernel rescales the kept entries in place; never touch the caller's grad
         with device_guard(dz.device):
@@ -503,7 +533,7 @@ class ConcatPosDropout(Function):
                 dtab = _reduce_partials(lib, partial, nb, vocab * pd).view(vocab, pd)
         if need_x:
             dx = dz[:, :k_in].contiguous()
-        return dx, dtab, None, None, None, None
+        return dx, dtab, None, None, None, None, None
 
 
 # --------------------------------------------------------------------------------------------------

@@ -116,13 +116,16 @@ def _gat_stack_forward(mod, g, features, positions, pos_tables):
     tab = (lambda l: pos_tables[l].weight) if pos_tables is not None else (lambda l: None)
     pd = pos_tables[0].weight.shape[1] if pos_tables is not None else 0
     p0 = layers[0].feat_drop if tr else 0.0
-    z = txf.ConcatPosDropout.apply(features, tab(0), pos32, p0, seed, 0)
+    link0 = txf.MaskLink() if txf.concat_publishes_f16() else None      # layer-0 input handed over as an fp16 operand pair
+    z = txf.ConcatPosDropout.apply(features, tab(0), pos32, p0, seed, 0, link0)
+    if link0 is not None and link0.c_state is None:
+        link0 = None
     k = features.shape[1] + pd
     links = [txf.MaskLink() for _ in range(n_total - 1)]     # layer l's epilogue mask -> layer l+1's d(z) GEMM epilogue
     for l, layer in enumerate(layers):
         hidden = l < n_total - 1
         cfg = txf.GatLayerCfg(
-            in_link=links[l - 1] if l > 0 else None, out_link=links[l] if hidden else None,
+            in_link=links[l - 1] if l > 0 else link0, out_link=links[l] if hidden else None,
             k=k, heads=layer.num_heads, dim=layer.out_dim, neg_slope=layer.negative_slope,
             p_attn=layer.attn_drop if tr else 0.0, attn_seed=seed, attn_stream=2 * l + 1, hidden=hidden,
             act_slope=slope if hidden else 1.0,
@@ -187,13 +190,16 @@ def _gcn_stack_forward(mod, g, features, positions, pos_tables):
     pd = pos_tables[0].weight.shape[1] if pos_tables is not None else 0
     g.ndata['norm'] = st.gcn_norm().unsqueeze(1)      # reference side effect (model_zoo.py:134,161)
     p0 = layers[0].dropout if tr else 0.0
-    z = txf.ConcatPosDropout.apply(features, tab(0), pos32, p0, seed, 0)
+    link0 = txf.MaskLink() if (txf.concat_publishes_f16() and txf.GCN_FUSED) else None
+    z = txf.ConcatPosDropout.apply(features, tab(0), pos32, p0, seed, 0, link0)
+    if link0 is not None and link0.c_state is None:
+        link0 = None
     k = features.shape[1] + pd
     links = [txf.MaskLink() for _ in range(n_total - 1)]     # layer l's epilogue mask -> layer l+1's d(z) GEMM epilogue
     for l, layer in enumerate(layers):
         hidden = l < n_total - 1
         cfg = txf.GcnLayerCfg(
-            in_link=links[l - 1] if l > 0 else None, out_link=links[l] if hidden else None,
+            in_link=links[l - 1] if l > 0 else link0, out_link=links[l] if hidden else None,
             k=k, dim=layer.weight.shape[1], hidden=hidden, act_slope=_act_slope(layer.activation) if hidden else 1.0,
             p_next=(layers[l + 1].dropout if tr else 0.0) if hidden else 0.0, next_seed=seed, next_stream=2 * (l + 1),
             dz_from=features.shape[1] if (l == 0 and not features.requires_grad) else 0, tag=f"L{l}")

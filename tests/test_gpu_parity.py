@@ -172,6 +172,37 @@ def test_gather_rows_is_bit_exact(d):
     assert txf.gather_rows(table, torch.zeros(0, dtype=torch.int32, device=dev())).shape == (0, d)
 
 
+@pytest.mark.parametrize("k_in,pd,p", [(250, 50, 0.1), (13, 0, 0.0), (300, 50, 0.5), (6, 3, 0.25)])
+def test_concat_published_as_an_fp16_pair_matches_the_fp32_concat(k_in, pd, p, monkeypatch):
+    """tx_concat_pos_dropout_f16 (the default layer-0 input: z is handed to the first projection GEMM as an fp16 hi / lo pair and never
+    stored) against tx_concat_pos_dropout_fwd: the same keep decisions entry for entry, values equal to 2^-21 of the tensor's bound,
+    padding columns zero, and the scale a power of two that keeps the bound inside fp16's range."""
+    monkeypatch.setattr(txf, "GEMM_BACKEND", "f16x3")
+    g = torch.Generator().manual_seed(k_in + pd)
+    n = 1237
+    x = (torch.randn(n, k_in, generator=g) * 37.0).to(dev())
+    tab = (torch.randn(3, pd, generator=g) * 0.3).to(dev()) if pd else None
+    pos32 = torch.randint(0, 3, (n,), generator=g).to(torch.int32).to(dev()) if pd else None
+    seed = 0x1234567
+    z = txf.ConcatPosDropout.apply(x, tab, pos32, p, seed, 0)
+    link = txf.MaskLink()
+    ph = txf.ConcatPosDropout.apply(x, tab, pos32, p, seed, 0, link)
+    assert link.c_state is not None and ph.shape == z.shape
+    link.materialize()
+    pair = link.z16
+    ld16 = txf.round8(k_in + pd)
+    assert pair.hi.shape == (n, ld16) and pair.cols == k_in + pd
+    scale = float(pair.scale.cpu())
+    bound = max(float(x.abs().max()), float(tab.abs().max()) if pd else 0.0) / (1.0 - p)
+    assert scale == 2.0 ** round(np.log2(scale)) and bound * scale <= 65504.0 and bound * scale > 2048.0
+    rec = (pair.hi.double() + pair.lo.double()) / scale
+    zz = z[:, :k_in + pd].double()
+    assert float((rec[:, :k_in + pd] - zz).abs().max()) <= bound * 2.0 ** -21
+    assert torch.equal(rec[:, :k_in + pd] == 0, zz == 0)                 # the same entries dropped
+    if ld16 > k_in + pd:
+        assert float(rec[:, k_in + pd:].abs().max()) == 0.0
+
+
 def test_general_csr_build_is_bit_exact():
     rng = np.random.default_rng(0)
     n, e = 1000, 7000
