@@ -50,6 +50,10 @@ int tx_abi_version(void);
 const char* tx_last_error(void);
 /* Name of the device kernels are compiled for ("sm_100a"). */
 const char* tx_target_arch(void);
+/* Programmatic dependent launch of the hot-path kernels (launch + prologue of kernel k+1 overlap the tail of kernel k; every kernel
+ * waits for its predecessor before it touches global memory, so results do not change): on by default, TAXO_PDL=0 in the environment or
+ * tx_pdl_set(0) switches it off.  Returns the previous setting. */
+int tx_pdl_set(int enabled);
 
 /* ------------------------------------------------------------------------------------------------
  * Graph structure (replaces DGL's graph index built by dgl.batch, data_loader/data_loaders.py:25, and the

@@ -88,6 +88,7 @@ _SIGNATURES = {
     "tx_abi_version": [],
     "tx_last_error": [],
     "tx_target_arch": [],
+    "tx_pdl_set": [ctypes.c_int],
     "tx_row_blocks": [I64],
     "tx_csr_workspace_bytes": [I64, I64, POINTER(c_int64)],
     "tx_build_csr_by_dst": [P, P, I64, I64, P, P, P, P, P, P],
@@ -194,7 +195,7 @@ _lib = None
 _raw = None
 
 # names of ABI calls that do not enqueue GPU work
-_NO_LAUNCH = {"tx_abi_version", "tx_last_error", "tx_target_arch", "tx_row_blocks", "tx_csr_workspace_bytes",
+_NO_LAUNCH = {"tx_abi_version", "tx_last_error", "tx_target_arch", "tx_pdl_set", "tx_row_blocks", "tx_csr_workspace_bytes",
               "tx_readout_bwd_blocks", "tx_gat_fused_supported", "tx_gat_fused_mask_words", "tx_gat_fused_mask_ld", "tx_gat_fused_bwd_blocks", "tx_gemm_tn_splits",
               "tx_gat_bwd_tile_rows", "tx_gat_bwd_num_tiles", "tx_gat_fused_bwd_staged_blocks", "tx_gemm_tn_f16_splits", "tx_gat_star_chunk", "tx_gat_star_max_chunks", "tx_gat_star_bwd_partial_floats",
               # the per-layer calls enqueue several kernels each: they are counted through tx_layer_launches, timed through tx_prof_*

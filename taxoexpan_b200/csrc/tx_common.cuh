@@ -174,6 +174,55 @@ __device__ __forceinline__ void f16_split4(float4 v, float scale, uint2& hi, uin
 
 __host__ __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (sm_90+): the hot-path kernels are launched with the programmatic-stream-serialization attribute and
+// start with TX_PDL_ENTER() (trigger, then wait) - the trigger lets the NEXT kernel of the stream be scheduled as soon as every CTA of this
+// one has started (its launch and prologue then overlap this kernel's tail), the wait blocks until the PREVIOUS kernel has completed and
+// its writes are visible.  Every kernel waits before it touches global memory, so the stream's semantics are unchanged; what goes away
+// is the 2-3 us of launch latency between ~55 short kernels of a step.  TAXO_PDL=0 launches without the attribute (both instructions
+// are then no-ops).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// ld.global.nc (__ldg(), and whatever nvcc derives from `const T* __restrict__`) promises data that is read-only for the kernel's
+// lifetime, so NVVM and ptxas may schedule such a load in front of griddepcontrol.wait - inline-asm memory clobbers do not order it: a
+// kernel that read a device scalar written by its predecessor as its first statement got `LDG.E.CONSTANT` placed before `ACQBULK` and
+// used the stale value.  Everything after the wait is therefore made control-dependent on a value neither compiler stage can fold
+// (%nsmid, read inside the same asm statement): loads through unknown pointers are never speculated across a branch.
+// scripts/check_pdl_sass.py (run by tests/test_abi_cpu.py) disassembles the library and checks that no kernel has a global-memory
+// instruction in front of its ACQBULK.
+__device__ __forceinline__ bool pdl_wait_guard() {
+  unsigned n_sm;
+  asm volatile("griddepcontrol.wait;\n\tmov.u32 %0, %%nsmid;" : "=r"(n_sm)::"memory");
+  return n_sm != 0;
+}
+#define TX_PDL_ENTER()          \
+  do {                          \
+    tx::pdl_trigger();          \
+    if (!tx::pdl_wait_guard()) return; \
+  } while (0)
+bool pdl_enabled(int group = 0, const char* name = nullptr);
+int pdl_set(int enabled);
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(int group, const char* name, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled(group, name) ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// kernel names with template commas go in parentheses: TX_PDL_LAUNCH((k<1, 2>), grid, block, smem, stream, args...)
+#ifndef TX_PDL_GROUP
+#define TX_PDL_GROUP 0
+#endif
+#define TX_PDL_LAUNCH(kernel, grid, block, smem, st, ...) (void)tx::launch_pdl(TX_PDL_GROUP, #kernel, kernel, dim3(grid), dim3(block), (size_t)(smem), st, __VA_ARGS__)
+
 inline int64_t row_blocks(int64_t n) { return (n + kRowsPerBlock - 1) / kRowsPerBlock; }
 inline int grid_for_warps(int64_t n_warp_items, int warps_per_block, int blocks_per_sm) {
   int64_t need = (n_warp_items + warps_per_block - 1) / warps_per_block;

@@ -19,6 +19,7 @@
 #include <math.h>
 #include <stdlib.h>
 
+#define TX_PDL_GROUP 5
 #include "tx_common.cuh"
 
 namespace tx {
@@ -575,6 +576,7 @@ __global__ void __launch_bounds__(256) pos_grad_partials_kernel(const float* __r
                                                                 const int32_t* __restrict__ pos, int n, int pd, int vocab,
                                                                 float inv_keep, uint32_t thr, uint64_t seed, uint32_t stream_id,
                                                                 float* __restrict__ partial) {
+  TX_PDL_ENTER();
   __shared__ float s_acc[3][kMaxVocab][64];
   const int r0 = blockIdx.x * kRowsPerBlock;
   const int r1 = min(n, r0 + kRowsPerBlock);
@@ -797,7 +799,7 @@ int tx_pos_grad_partials(const float* dz, int64_t ldz, int64_t col0, const int32
   TX_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "pos_grad_partials: p_drop must be in [0,1)");
   TX_REQUIRE(pos && partial && ldz >= col0 + pos_dim, "pos_grad_partials: bad arguments");
   if (n_nodes == 0 || pos_dim == 0) return TX_OK;
-  pos_grad_partials_kernel<<<(int)row_blocks(n_nodes), 256, 0, (cudaStream_t)stream>>>(dz, ldz, (int)col0, pos, (int)n_nodes, (int)pos_dim,
+  TX_PDL_LAUNCH((pos_grad_partials_kernel), (int)row_blocks(n_nodes), 256, 0, (cudaStream_t)stream, dz, ldz, (int)col0, pos, (int)n_nodes, (int)pos_dim,
                                                                                       (int)vocab, 1.f / (1.f - p_drop), drop_threshold(p_drop),
                                                                                       seed, stream_id, partial);
   TX_LAUNCH_CHECK("tx_pos_grad_partials");

@@ -18,6 +18,7 @@
 
 #include <algorithm>
 
+#define TX_PDL_GROUP 2
 #include "tx_common.cuh"
 
 namespace tx {
@@ -229,6 +230,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  pdl_trigger();
   const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
   if (warp == 1) {   // one warp allocates both accumulator buffers (power of two >= 32 columns)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
@@ -239,6 +241,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   if (CL > 1) cluster_sync_all();              // the peer's barriers are initialised before anything is multicast into it
   tcgen05_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  if (!pdl_wait_guard()) __trap();             // (never taken, see tx_common.cuh) barriers / TMEM were set up while the previous kernel drained
   const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * BN;
   // LAST tile of a row of tiles: the MMA is issued only as wide as the columns that exist, rounded up to `gran` (the instruction's N
   // granularity - 16 - or, for MN-major B, whole TMA boxes; 0 = always BN): N = 300 with BN = 192 costs 192 + 128 columns instead of
@@ -502,6 +505,7 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  pdl_trigger();
   if (warp == 1) {   // both CTAs, same warp id: paired TMEM allocation
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -511,6 +515,7 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
   cluster_sync_all();
   tcgen05_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  if (!pdl_wait_guard()) __trap();             // (never taken, see tx_common.cuh) barriers / TMEM were set up while the previous kernel drained
   // PERSISTENT: a 1-D grid of 2 x n_clusters CTAs (cluster {2,1,1}); cluster c walks the work items c, c + n_clusters, ... of the
   // linear list (n tile fastest, then M-tile pair, then k split), so that the epilogue of one tile (accumulator drain + global
   // stores) overlaps the TMA / MMA stream of the next: the smem ring and the two TMEM buffers simply keep rotating across tiles.
@@ -749,6 +754,7 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, int64_t ldx, int 
 
 // ---- fp16 split path: per-tensor bounds and scales live in DEVICE scalars, so nothing here synchronises with the host ----
 __global__ void absmax_kernel(const float* __restrict__ x, int64_t ldx, int rows, int cols, float* __restrict__ out) {
+  TX_PDL_ENTER();
   float m = 0.f;
   if (ldx == cols && aligned16(x)) {                            // a contiguous block (e.g. [N, 250] features): flat 128-bit loads + tail
     const int64_t total = (int64_t)rows * cols, n4 = total >> 2;
@@ -801,6 +807,7 @@ __device__ __forceinline__ float block_absmax(const float* __restrict__ v, int64
 }
 // out = max(a ca, max|b[0..b_len)| cb)  (b may be null)
 __global__ void bound_max2_kernel(const float* a, float ca, const float* b, int64_t b_len, float cb, float* out) {
+  TX_PDL_ENTER();
   __shared__ float s_red[8];
   const float mb = block_absmax(b, b_len, s_red);
   if (threadIdx.x == 0) *out = fmaxf(*a * ca, mb * cb);
@@ -809,6 +816,7 @@ __global__ void bound_max2_kernel(const float* a, float ca, const float* b, int6
 // out[1] = min(out[0], g c_optimistic) - the scale the star backward tries first; out[2] = c; out[3] = 0 (its fp16-range flag)
 __global__ void bound_dft_kernel(const float* g, const float* ft, const float* al, const float* ar, int64_t len, float c_direct, float c_attn,
                                  float c_optimistic, float* out) {
+  TX_PDL_ENTER();
   __shared__ float s_red[8];
   const float ml = block_absmax(al, len, s_red), mr = block_absmax(ar, len, s_red);
   if (threadIdx.x == 0) {
@@ -823,6 +831,7 @@ __global__ void bound_dft_kernel(const float* g, const float* ft, const float* a
 
 __global__ void split_f16_kernel(const float* __restrict__ x, int64_t ldx, int rows, int cols, const float* __restrict__ bound,
                                  __half* __restrict__ hi, __half* __restrict__ lo, int ldo, float* __restrict__ scale_out) {
+  TX_PDL_ENTER();
   const float scale = f16_split_scale(__ldg(bound));
   if (scale_out && blockIdx.x == 0 && threadIdx.x == 0) *scale_out = scale;
   const int vec_per_row = ldo >> 2;
@@ -857,6 +866,7 @@ __global__ void __launch_bounds__(256, kSplitWCtasPerSm) split_f16_weight_kernel
                                                                __half* __restrict__ hit, __half* __restrict__ lot, int ldt,
                                                                float* __restrict__ amax, unsigned int* __restrict__ counter,
                                                                float* __restrict__ scale_out) {
+  TX_PDL_ENTER();
   const int64_t total = (int64_t)rows * cols;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
   float m = 0.f;
@@ -1021,21 +1031,23 @@ static int launch_gemm(const void* a_hi, const void* a_lo, int64_t lda, const vo
                                                    e_l ? (uint32_t)atoi(e_l) : 1u);
   const int gran = dyn_n_gran(TN ? (F16 ? 64 : 32) : 16);
   if (CL == 1) {
-    gemm_tf32x3_kernel<BN, STAGES, TN, BK, CL, F16><<<grid, kGemmThreads, SMEM, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, c, ldc, split_stride, (int)M,
-                                                                                  (int)n_store, kbt, kbs, mn_bits, epi, gran);
+    TX_PDL_LAUNCH((gemm_tf32x3_kernel<BN, STAGES, TN, BK, CL, F16>), grid, kGemmThreads, SMEM, st, ma_hi, ma_lo, mb_hi, mb_lo, c, ldc, split_stride, (int)M,
+                  (int)n_store, kbt, kbs, mn_bits, epi, gran);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = SMEM;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 1;
     attr[0].val.clusterDim.y = CL;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled(TX_PDL_GROUP) ? 1 : 0;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<BN, STAGES, TN, BK, CL, F16>, ma_hi, ma_lo, mb_hi, mb_lo, c, ldc, split_stride,
                                        (int)M, (int)n_store, kbt, kbs, mn_bits, epi, gran);
     if (e != cudaSuccess) {
@@ -1107,13 +1119,15 @@ static int launch_gemm_pair(const void* a_hi, const void* a_lo, int64_t lda, con
   cfg.blockDim = dim3(kPairThreads);
   cfg.dynamicSmemBytes = SMEM;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled(TX_PDL_GROUP) ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tf32x3_pair_kernel<BN, STAGES, TN, F16, SLAB>, ma_hi, ma_lo, mb_hi, mb_lo, c, ldc, split_stride,
                                      (int)M, (int)n_store, kbt, kbs, mn_bits, epi, n_tiles_n, n_m_pairs, n_work, chunk_kb);
   if (e != cudaSuccess) {
@@ -1244,14 +1258,14 @@ int tx_absmax(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* ou
   if (rows == 0 || cols == 0) return TX_OK;
   const int64_t total = rows * cols;
   const int grid = (int)((total + 1023) / 1024 < (int64_t)kNumSms * 8 ? (total + 1023) / 1024 : (int64_t)kNumSms * 8);
-  absmax_kernel<<<grid, 256, 0, st>>>(x, ldx, (int)rows, (int)cols, out);
+  TX_PDL_LAUNCH((absmax_kernel), grid, 256, 0, st, x, ldx, (int)rows, (int)cols, out);
   TX_LAUNCH_CHECK("tx_absmax");
   return TX_OK;
 }
 
 int tx_bound_max2(const float* a, float ca, const float* b, int64_t b_len, float cb, float* out, void* stream) {
   TX_REQUIRE(a && out && b_len >= 0, "bound_max2: bad arguments");
-  bound_max2_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(a, ca, b, b_len, cb, out);
+  TX_PDL_LAUNCH((bound_max2_kernel), 1, 256, 0, (cudaStream_t)stream, a, ca, b, b_len, cb, out);
   TX_LAUNCH_CHECK("tx_bound_max2");
   return TX_OK;
 }
@@ -1259,7 +1273,7 @@ int tx_bound_max2(const float* a, float ca, const float* b, int64_t b_len, float
 int tx_bound_dft(const float* g_amax, const float* ft_amax, const float* attn_l, const float* attn_r, int64_t attn_len, float c_direct,
                  float c_attn, float c_optimistic, float* out, void* stream) {
   TX_REQUIRE(g_amax && ft_amax && attn_l && attn_r && attn_len >= 0 && out && aligned16(out), "bound_dft: bad arguments (out: 4 floats, 16-byte aligned)");
-  bound_dft_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(g_amax, ft_amax, attn_l, attn_r, attn_len, c_direct, c_attn, c_optimistic, out);
+  TX_PDL_LAUNCH((bound_dft_kernel), 1, 256, 0, (cudaStream_t)stream, g_amax, ft_amax, attn_l, attn_r, attn_len, c_direct, c_attn, c_optimistic, out);
   TX_LAUNCH_CHECK("tx_bound_dft");
   return TX_OK;
 }
@@ -1271,7 +1285,7 @@ int tx_split_f16(const float* x, int64_t ldx, int64_t rows, int64_t cols, const 
   if (rows == 0 || cols == 0) return TX_OK;
   const int64_t total = rows * (ldo / 4);
   const int grid = (int)((total + 255) / 256 < (int64_t)kNumSms * 16 ? (total + 255) / 256 : (int64_t)kNumSms * 16);
-  split_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, (int)rows, (int)cols, bound, (__half*)hi, (__half*)lo, (int)ldo, scale_out);
+  TX_PDL_LAUNCH((split_f16_kernel), grid, 256, 0, (cudaStream_t)stream, x, ldx, (int)rows, (int)cols, bound, (__half*)hi, (__half*)lo, (int)ldo, scale_out);
   TX_LAUNCH_CHECK("tx_split_f16");
   return TX_OK;
 }
@@ -1287,7 +1301,7 @@ int tx_split_f16_weight(const float* w, int64_t ldw, int64_t rows, int64_t cols,
   int64_t grid = tiles;
   if (grid > (int64_t)kNumSms * kSplitWCtasPerSm) grid = (int64_t)kNumSms * kSplitWCtasPerSm;     // the grid-wide rendezvous needs every CTA resident
   if (grid < 1) grid = 1;
-  split_f16_weight_kernel<<<(int)grid, 256, 0, st>>>(w, ldw, (int)rows, (int)cols, (__half*)hi, (__half*)lo, (int)ld, (__half*)hi_t, (__half*)lo_t,
+  TX_PDL_LAUNCH((split_f16_weight_kernel), (int)grid, 256, 0, st, w, ldw, (int)rows, (int)cols, (__half*)hi, (__half*)lo, (int)ld, (__half*)hi_t, (__half*)lo_t,
                                                      (int)ld_t, scratch2, reinterpret_cast<unsigned int*>(scratch2 + 1), scale_out);
   TX_LAUNCH_CHECK("tx_split_f16_weight");
   return TX_OK;

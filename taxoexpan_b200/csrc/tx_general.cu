@@ -7,7 +7,10 @@
 // reference model/model_zoo.py:116-137,169-190); the egonet-resident fast path lives in tx_egonet.cu.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
 
+#define TX_PDL_GROUP 0
 #include "tx_common.cuh"
 
 namespace tx {
@@ -18,6 +21,30 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+static int g_pdl = -1, g_pdl_mask = 0xFFFF;
+static const char *g_pdl_only = nullptr, *g_pdl_skip = nullptr;
+static void pdl_init() {
+  if (g_pdl >= 0) return;
+  const char* e = getenv("TAXO_PDL"); g_pdl = (e && atoi(e) == 0) ? 0 : 1;
+  const char* m = getenv("TAXO_PDL_MASK"); g_pdl_mask = m ? atoi(m) : 0xFFFF;
+  g_pdl_only = getenv("TAXO_PDL_ONLY"); g_pdl_skip = getenv("TAXO_PDL_SKIP");
+}
+bool pdl_enabled(int group, const char* name) {
+  // TAXO_PDL=0 / tx_pdl_set(0): off; debugging: TAXO_PDL_MASK=<bits> only the source files whose bit is set, TAXO_PDL_ONLY=<substring> only
+  // kernels whose name contains it, TAXO_PDL_SKIP=<substring> all but those
+  pdl_init();
+  if (g_pdl == 0 || !((g_pdl_mask >> group) & 1)) return false;
+  if (name && g_pdl_only && !strstr(name, g_pdl_only)) return false;
+  if (name && g_pdl_skip && strstr(name, g_pdl_skip)) return false;
+  return true;
+}
+int pdl_set(int enabled) {
+  pdl_init();
+  const int prev = g_pdl;
+  g_pdl = enabled ? 1 : 0;
+  return prev;
 }
 
 struct Epilogue {  // device copy of tx_gat_epilogue
@@ -87,6 +114,7 @@ __device__ __forceinline__ void epilogue_tail(const Epilogue& ep, float* out_row
 __global__ void concat_pos_dropout_fwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ ptab,
                                               const int32_t* __restrict__ pos, int n, int k_in, int pd, float* __restrict__ z,
                                               int ldz, float inv_keep, uint32_t thr, uint64_t seed, uint32_t stream_id) {
+  TX_PDL_ENTER();
   const int vec_per_row = ldz >> 2;
   const int64_t total = (int64_t)n * vec_per_row;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -121,6 +149,7 @@ __global__ void __launch_bounds__(256) concat_pos_dropout_f16_kernel(const float
                                                                      __half* __restrict__ lo, int ld16, int ldz, float inv_keep,
                                                                      uint32_t thr, uint64_t seed, uint32_t stream_id,
                                                                      float* __restrict__ scale_out) {
+  TX_PDL_ENTER();
   __shared__ float s_m[8];
   float m = 0.f;
   for (int t = threadIdx.x; t < vocab * pd; t += blockDim.x) m = fmaxf(m, fabsf(__ldg(ptab + t)));
@@ -225,6 +254,7 @@ __global__ void __launch_bounds__(256) epilogue_bwd_kernel(float* __restrict__ d
 // few partial blocks of many elements (split-K GEMM partials): one float4 column per thread, blocks summed in index order
 __global__ void __launch_bounds__(256) reduce_partials_wide_kernel(const float* __restrict__ partial, int n_blocks, int64_t m4,
                                                                    float* __restrict__ out) {
+  TX_PDL_ENTER();
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < m4; t += (int64_t)gridDim.x * blockDim.x) {
     float4 s = __ldg(reinterpret_cast<const float4*>(partial) + t);
     for (int b = 1; b < n_blocks; ++b) {
@@ -241,6 +271,7 @@ __global__ void __launch_bounds__(256) reduce_partials_wide_kernel(const float* 
 template <int WY>
 __global__ void __launch_bounds__(32 * WY) reduce_partials_kernel(const float* __restrict__ partial, int64_t n_blocks, int64_t m_len,
                                                                   float* __restrict__ out) {
+  TX_PDL_ENTER();
   __shared__ float sm[WY][33];
   const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
   const int64_t m = (int64_t)blockIdx.x * 32 + x;
@@ -266,6 +297,7 @@ __global__ void __launch_bounds__(32 * WY) reduce_partials_kernel(const float* _
 
 __global__ void colsum_partials_kernel(const float* __restrict__ x, int64_t ldx, int n_rows, int n_cols,
                                        float* __restrict__ partial) {
+  TX_PDL_ENTER();
   const int r0 = blockIdx.x * kRowsPerBlock;
   const int r1 = min(n_rows, r0 + kRowsPerBlock);
   for (int c = threadIdx.x; c < n_cols; c += blockDim.x) {
@@ -547,6 +579,7 @@ __global__ void __launch_bounds__(256) gat_attn_grad_partials_kernel(const float
 // GCN
 // =============================================================================================
 __global__ void gcn_norm_kernel(const int32_t* __restrict__ in_ptr, int n, float* __restrict__ norm) {
+  TX_PDL_ENTER();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int deg = in_ptr[i + 1] - in_ptr[i];
@@ -639,6 +672,7 @@ __global__ void __launch_bounds__(256) gcn_aggregate_fwd_f16_kernel(const float*
                                                                     const Epilogue ep, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
                                                                     int64_t ld16, const float* __restrict__ bound, float* __restrict__ scale_out,
                                                                     uint8_t* __restrict__ mask, int mask_ld) {
+  TX_PDL_ENTER();
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -706,6 +740,7 @@ __global__ void __launch_bounds__(256) gcn_aggregate_bwd_f16_kernel(const float*
                                                                     const int32_t* __restrict__ out_ptr, const int32_t* __restrict__ out_dst,
                                                                     int n, int D, __half* __restrict__ dy_hi, __half* __restrict__ dy_lo,
                                                                     int64_t ld16, const float* __restrict__ bound, float* __restrict__ scale_out) {
+  TX_PDL_ENTER();
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -737,6 +772,7 @@ __global__ void __launch_bounds__(256) gcn_aggregate_bwd_f16_kernel(const float*
 // *out = max(2 ca *a, 2 cb max|b|, ct max|t|): bound of a GCN layer's epilogue output, |norm_i sum_j norm_j y_j + bias| <= sqrt(max
 // in-degree) max|y| + max|bias| <= 2 max(.., ..), and of the appended position rows
 __global__ void bound_gcn_kernel(const float* a, float ca, const float* b, int64_t nb, float cb, const float* t, int64_t nt, float ct, float* out) {
+  TX_PDL_ENTER();
   __shared__ float s_red[8];
   auto block_max = [&](const float* v, int64_t len) -> float {
     float m = 0.f;
@@ -939,6 +975,7 @@ __global__ void __launch_bounds__(256) readout_fwd_fast_kernel(int kind, const f
                                                                const int32_t* __restrict__ pos, const float* __restrict__ pw,
                                                                const int32_t* __restrict__ node_off, int n_graphs, int D,
                                                                float* __restrict__ hg, int64_t ldhg) {
+  TX_PDL_ENTER();
   __shared__ float4 s_acc[8][NV * 32];
   __shared__ float s_S[8];
   __shared__ int s_size[8];
@@ -1036,6 +1073,7 @@ __global__ void __launch_bounds__(256) readout_bwd_fast_kernel(int kind, const f
                                                                const int32_t* __restrict__ pos, const float* __restrict__ pw,
                                                                const int32_t* __restrict__ node_off, int n_graphs, int D,
                                                                float* __restrict__ dh, int64_t lddh, float* __restrict__ dw_partial) {
+  TX_PDL_ENTER();
   __shared__ float sdw[8][3];
   __shared__ int s_size[8];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -1148,6 +1186,7 @@ using namespace tx;
 extern "C" {
 
 int tx_abi_version(void) { return TX_ABI_VERSION; }
+int tx_pdl_set(int enabled) { return tx::pdl_set(enabled); }
 const char* tx_last_error(void) { return tx::g_err; }
 const char* tx_target_arch(void) { return "sm_100a"; }
 int64_t tx_row_blocks(int64_t n_rows) { return row_blocks(n_rows); }
@@ -1163,7 +1202,7 @@ int tx_concat_pos_dropout_fwd(const float* x, int64_t ldx, const float* pos_tabl
   if (n_nodes == 0) return TX_OK;
   const int64_t total = n_nodes * (ldz / 4);
   const int grid = (int)((total + 255) / 256 < (int64_t)kNumSms * 16 ? (total + 255) / 256 : (int64_t)kNumSms * 16);
-  concat_pos_dropout_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, pos_table, pos, (int)n_nodes, (int)k_in,
+  TX_PDL_LAUNCH((concat_pos_dropout_fwd_kernel), grid, 256, 0, (cudaStream_t)stream, x, ldx, pos_table, pos, (int)n_nodes, (int)k_in,
                                                                         (int)pos_dim, z, (int)ldz, 1.f / (1.f - p_drop),
                                                                         drop_threshold(p_drop), seed, stream_id);
   TX_LAUNCH_CHECK("tx_concat_pos_dropout_fwd");
@@ -1183,7 +1222,7 @@ int tx_concat_pos_dropout_f16(const float* x, int64_t ldx, const float* pos_tabl
   const int64_t total = n_nodes * (ld16 / 4);
   const int grid = (int)((total + 255) / 256 < (int64_t)kNumSms * 16 ? (total + 255) / 256 : (int64_t)kNumSms * 16);
   const int64_t ldz = ((k_in + pos_dim + 3) / 4) * 4;
-  concat_pos_dropout_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, pos_table, pos, (int)n_nodes, (int)k_in, (int)pos_dim,
+  TX_PDL_LAUNCH((concat_pos_dropout_f16_kernel), grid, 256, 0, (cudaStream_t)stream, x, ldx, pos_table, pos, (int)n_nodes, (int)k_in, (int)pos_dim,
                                                                         (int)(pos_dim > 0 ? vocab : 0), x_amax, (__half*)hi, (__half*)lo,
                                                                         (int)ld16, (int)ldz, 1.f / (1.f - p_drop), drop_threshold(p_drop),
                                                                         seed, stream_id, scale_out);
@@ -1212,21 +1251,21 @@ int tx_reduce_partials(const float* partial, int64_t n_blocks, int64_t m_len, fl
   if (n_blocks <= 64 && m_len >= 4096 && m_len % 4 == 0 && aligned16(partial) && aligned16(out)) {   // split-K partials: few, long
     const int64_t m4 = m_len / 4;
     const int grid = (int)((m4 + 255) / 256 < (int64_t)kNumSms * 16 ? (m4 + 255) / 256 : (int64_t)kNumSms * 16);
-    reduce_partials_wide_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(partial, (int)n_blocks, m4, out);
+    TX_PDL_LAUNCH((reduce_partials_wide_kernel), grid, 256, 0, (cudaStream_t)stream, partial, (int)n_blocks, m4, out);
     TX_LAUNCH_CHECK("tx_reduce_partials");
     return TX_OK;
   }
   if (n_blocks >= 128)
-    reduce_partials_kernel<32><<<(int)((m_len + 31) / 32), 1024, 0, (cudaStream_t)stream>>>(partial, n_blocks, m_len, out);
+    TX_PDL_LAUNCH((reduce_partials_kernel<32>), (int)((m_len + 31) / 32), 1024, 0, (cudaStream_t)stream, partial, n_blocks, m_len, out);
   else
-    reduce_partials_kernel<8><<<(int)((m_len + 31) / 32), 256, 0, (cudaStream_t)stream>>>(partial, n_blocks, m_len, out);
+    TX_PDL_LAUNCH((reduce_partials_kernel<8>), (int)((m_len + 31) / 32), 256, 0, (cudaStream_t)stream, partial, n_blocks, m_len, out);
   TX_LAUNCH_CHECK("tx_reduce_partials");
   return TX_OK;
 }
 
 int tx_colsum_partials(const float* x, int64_t ldx, int64_t n_rows, int64_t n_cols, float* partial, void* stream) {
   if (n_rows == 0 || n_cols == 0) return TX_OK;
-  colsum_partials_kernel<<<(int)row_blocks(n_rows), 256, 0, (cudaStream_t)stream>>>(x, ldx, (int)n_rows, (int)n_cols, partial);
+  TX_PDL_LAUNCH((colsum_partials_kernel), (int)row_blocks(n_rows), 256, 0, (cudaStream_t)stream, x, ldx, (int)n_rows, (int)n_cols, partial);
   TX_LAUNCH_CHECK("tx_colsum_partials");
   return TX_OK;
 }
@@ -1329,7 +1368,7 @@ int tx_gat_attn_grad_partials(const float* ft, int64_t ldf, const float* da1, co
 
 int tx_gcn_norm(const int32_t* in_ptr, int64_t n_nodes, float* norm, void* stream) {
   if (n_nodes == 0) return TX_OK;
-  gcn_norm_kernel<<<(int)((n_nodes + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in_ptr, (int)n_nodes, norm);
+  TX_PDL_LAUNCH((gcn_norm_kernel), (int)((n_nodes + 255) / 256), 256, 0, (cudaStream_t)stream, in_ptr, (int)n_nodes, norm);
   TX_LAUNCH_CHECK("tx_gcn_norm");
   return TX_OK;
 }
@@ -1363,7 +1402,7 @@ int tx_gcn_aggregate_fwd_f16(const float* y, int64_t ldy, const float* norm, con
              ldo >= dim + ep.pos_dim, "gcn_aggregate_fwd_f16: bad output buffers");
   if (n_nodes == 0) return TX_OK;
   const int grid = grid_for_warps(n_nodes, 8, 8);
-  gcn_aggregate_fwd_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, ldy, norm, bias, in_ptr, in_src, (int)n_nodes, (int)dim, ldo, ep,
+  TX_PDL_LAUNCH((gcn_aggregate_fwd_f16_kernel), grid, 256, 0, (cudaStream_t)stream, y, ldy, norm, bias, in_ptr, in_src, (int)n_nodes, (int)dim, ldo, ep,
                                                                       (__half*)out_hi, (__half*)out_lo, ld16, bound, scale_out,
                                                                       reinterpret_cast<uint8_t*>(maskbits), (int)tx_gat_fused_mask_ld(1, dim));
   TX_LAUNCH_CHECK("tx_gcn_aggregate_fwd_f16");
@@ -1376,7 +1415,7 @@ int tx_gcn_aggregate_bwd_f16(const float* g, int64_t ldg, const float* norm, con
   TX_REQUIRE(dy_hi && dy_lo && bound && aligned16(dy_hi) && aligned16(dy_lo) && ld16 % 8 == 0 && ld16 >= dim, "gcn_aggregate_bwd_f16: bad output buffers");
   if (n_nodes == 0) return TX_OK;
   const int grid = grid_for_warps(n_nodes, 8, 8);
-  gcn_aggregate_bwd_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, ldg, norm, out_ptr, out_dst, (int)n_nodes, (int)dim, (__half*)dy_hi,
+  TX_PDL_LAUNCH((gcn_aggregate_bwd_f16_kernel), grid, 256, 0, (cudaStream_t)stream, g, ldg, norm, out_ptr, out_dst, (int)n_nodes, (int)dim, (__half*)dy_hi,
                                                                       (__half*)dy_lo, ld16, bound, scale_out);
   TX_LAUNCH_CHECK("tx_gcn_aggregate_bwd_f16");
   return TX_OK;
@@ -1384,7 +1423,7 @@ int tx_gcn_aggregate_bwd_f16(const float* g, int64_t ldg, const float* norm, con
 
 int tx_bound_gcn(const float* a, float ca, const float* b, int64_t b_len, float cb, const float* t, int64_t t_len, float ct, float* out, void* stream) {
   TX_REQUIRE(a && out && b_len >= 0 && t_len >= 0, "bound_gcn: bad arguments");
-  bound_gcn_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(a, ca, b_len > 0 ? b : nullptr, b_len, cb, t_len > 0 ? t : nullptr, t_len, ct, out);
+  TX_PDL_LAUNCH((bound_gcn_kernel), 1, 256, 0, (cudaStream_t)stream, a, ca, b_len > 0 ? b : nullptr, b_len, cb, t_len > 0 ? t : nullptr, t_len, ct, out);
   TX_LAUNCH_CHECK("tx_bound_gcn");
   return TX_OK;
 }
@@ -1415,10 +1454,10 @@ int tx_readout_fwd(int32_t kind, const float* h, int64_t ldh, const int32_t* pos
   const int grid = readout_grid(n_graphs);
   if (kind != TX_READOUT_CONCAT && dim <= 512 && vec4_ok(h, ldh, dim) && vec4_ok(hg, ldhg, dim)) {
     switch ((int)((dim + 127) / 128)) {
-      case 1: readout_fwd_fast_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(kind, h, ldh, pos, pos_weight, node_off, (int)n_graphs, (int)dim, hg, ldhg); break;
-      case 2: readout_fwd_fast_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(kind, h, ldh, pos, pos_weight, node_off, (int)n_graphs, (int)dim, hg, ldhg); break;
-      case 3: readout_fwd_fast_kernel<3><<<grid, 256, 0, (cudaStream_t)stream>>>(kind, h, ldh, pos, pos_weight, node_off, (int)n_graphs, (int)dim, hg, ldhg); break;
-      default: readout_fwd_fast_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(kind, h, ldh, pos, pos_weight, node_off, (int)n_graphs, (int)dim, hg, ldhg); break;
+      case 1: TX_PDL_LAUNCH((readout_fwd_fast_kernel<1>), grid, 256, 0, (cudaStream_t)stream, kind, h, ldh, pos, pos_weight, node_off, (int)n_graphs, (int)dim, hg, ldhg); break;
+      case 2: TX_PDL_LAUNCH((readout_fwd_fast_kernel<2>), grid, 256, 0, (cudaStream_t)stream, kind, h, ldh, pos, pos_weight, node_off, (int)n_graphs, (int)dim, hg, ldhg); break;
+      case 3: TX_PDL_LAUNCH((readout_fwd_fast_kernel<3>), grid, 256, 0, (cudaStream_t)stream, kind, h, ldh, pos, pos_weight, node_off, (int)n_graphs, (int)dim, hg, ldhg); break;
+      default: TX_PDL_LAUNCH((readout_fwd_fast_kernel<4>), grid, 256, 0, (cudaStream_t)stream, kind, h, ldh, pos, pos_weight, node_off, (int)n_graphs, (int)dim, hg, ldhg); break;
     }
     TX_LAUNCH_CHECK("tx_readout_fwd");
     return TX_OK;
@@ -1443,10 +1482,10 @@ int tx_readout_bwd(int32_t kind, const float* dhg, int64_t lddhg, const float* h
   if (v4 && kind != TX_READOUT_CONCAT && dim <= 512) {
     cudaStream_t st = (cudaStream_t)stream;
     switch ((int)((dim + 127) / 128)) {
-      case 1: readout_bwd_fast_kernel<1><<<grid, 256, 0, st>>>(kind, dhg, lddhg, h, ldh, hg, ldhg, pos, pos_weight, node_off, (int)n_graphs, (int)dim, dh, lddh, dw_partial); break;
-      case 2: readout_bwd_fast_kernel<2><<<grid, 256, 0, st>>>(kind, dhg, lddhg, h, ldh, hg, ldhg, pos, pos_weight, node_off, (int)n_graphs, (int)dim, dh, lddh, dw_partial); break;
-      case 3: readout_bwd_fast_kernel<3><<<grid, 256, 0, st>>>(kind, dhg, lddhg, h, ldh, hg, ldhg, pos, pos_weight, node_off, (int)n_graphs, (int)dim, dh, lddh, dw_partial); break;
-      default: readout_bwd_fast_kernel<4><<<grid, 256, 0, st>>>(kind, dhg, lddhg, h, ldh, hg, ldhg, pos, pos_weight, node_off, (int)n_graphs, (int)dim, dh, lddh, dw_partial); break;
+      case 1: TX_PDL_LAUNCH((readout_bwd_fast_kernel<1>), grid, 256, 0, st, kind, dhg, lddhg, h, ldh, hg, ldhg, pos, pos_weight, node_off, (int)n_graphs, (int)dim, dh, lddh, dw_partial); break;
+      case 2: TX_PDL_LAUNCH((readout_bwd_fast_kernel<2>), grid, 256, 0, st, kind, dhg, lddhg, h, ldh, hg, ldhg, pos, pos_weight, node_off, (int)n_graphs, (int)dim, dh, lddh, dw_partial); break;
+      case 3: TX_PDL_LAUNCH((readout_bwd_fast_kernel<3>), grid, 256, 0, st, kind, dhg, lddhg, h, ldh, hg, ldhg, pos, pos_weight, node_off, (int)n_graphs, (int)dim, dh, lddh, dw_partial); break;
+      default: TX_PDL_LAUNCH((readout_bwd_fast_kernel<4>), grid, 256, 0, st, kind, dhg, lddhg, h, ldh, hg, ldhg, pos, pos_weight, node_off, (int)n_graphs, (int)dim, dh, lddh, dw_partial); break;
     }
     TX_LAUNCH_CHECK("tx_readout_bwd");
     return TX_OK;

@@ -1,6 +1,7 @@
 // Graph-structure kernels: CSR construction for arbitrary edge lists and the closed-form structure of a
 // batch of star egonets (reference data_loader/dataset.py:404-437 + dgl.batch, data_loaders.py:25).
 // Integer work only; results are bit-exact against oracle/taxo_oracle.py::csr_by_dst.
+#define TX_PDL_GROUP 6
 #include "tx_common.cuh"
 
 namespace tx {
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(256) star_batch_structure_kernel(
     const int32_t* __restrict__ edge_off, int n_graphs, int32_t* __restrict__ pos, int32_t* __restrict__ src,
     int32_t* __restrict__ dst, int32_t* __restrict__ in_ptr, int32_t* __restrict__ in_src, int32_t* __restrict__ in_eid,
     int32_t* __restrict__ out_ptr, int32_t* __restrict__ out_dst, int32_t* __restrict__ out_slot) {
+  TX_PDL_ENTER();
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -155,6 +157,7 @@ __global__ void __launch_bounds__(1024, 1) star_batch_plan_kernel(const int32_t*
                                                                    int chunk_fwd, int chunk_bwd, int32_t* __restrict__ node_off,
                                                                    int32_t* __restrict__ edge_off, int4* __restrict__ tasks_fwd,
                                                                    int4* __restrict__ tasks_bwd) {
+  TX_PDL_ENTER();
   constexpr int NQ = 7;                                   // scanned quantities: nodes, records of the 3 classes x {fwd, bwd}
   constexpr int PER = 8;                                  // consecutive egonets per thread and round (8192 per round)
   __shared__ int s_warp[NQ][32];
@@ -265,6 +268,7 @@ __global__ void __launch_bounds__(1024, 1) star_batch_plan_kernel(const int32_t*
 template <int VEC>
 __global__ void gather_rows_kernel(const float* __restrict__ table, int64_t ldt, const int32_t* __restrict__ ids, int64_t n, int d, int64_t n_table,
                                    float* __restrict__ out, int64_t ldo) {
+  TX_PDL_ENTER();
   const int per_row = d / VEC;
   const int64_t total = n * per_row;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -354,7 +358,7 @@ int tx_star_batch_structure(const int32_t* n_gp, const int32_t* n_sib, const int
   TX_REQUIRE(!out_ptr || (out_dst && out_slot), "star_batch_structure: out_ptr needs out_dst and out_slot");
   if (n_graphs == 0) return TX_OK;
   const int grid = grid_for_warps(n_graphs, 8, 8);
-  star_batch_structure_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n_gp, n_sib, node_off, edge_off, (int)n_graphs, pos, src,
+  TX_PDL_LAUNCH((star_batch_structure_kernel), grid, 256, 0, (cudaStream_t)stream, n_gp, n_sib, node_off, edge_off, (int)n_graphs, pos, src,
                                                                      dst, in_ptr, in_src, in_eid, out_ptr, out_dst, out_slot);
   TX_LAUNCH_CHECK("tx_star_batch_structure");
   return TX_OK;
@@ -368,8 +372,8 @@ int tx_gather_rows(const float* table, int64_t ldt, int64_t n_table, const int32
   const int64_t total = n * (vec ? d / 4 : d);
   int64_t grid = (total + 255) / 256;
   if (grid > (int64_t)kNumSms * 16) grid = (int64_t)kNumSms * 16;
-  if (vec) gather_rows_kernel<4><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(table, ldt, ids, n, (int)d, n_table, out, ldo);
-  else gather_rows_kernel<1><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(table, ldt, ids, n, (int)d, n_table, out, ldo);
+  if (vec) TX_PDL_LAUNCH((gather_rows_kernel<4>), (unsigned)grid, 256, 0, (cudaStream_t)stream, table, ldt, ids, n, (int)d, n_table, out, ldo);
+  else TX_PDL_LAUNCH((gather_rows_kernel<1>), (unsigned)grid, 256, 0, (cudaStream_t)stream, table, ldt, ids, n, (int)d, n_table, out, ldo);
   TX_LAUNCH_CHECK("tx_gather_rows");
   return TX_OK;
 }
@@ -379,7 +383,7 @@ int tx_star_batch_plan(const int32_t* n_gp, const int32_t* n_sib, int64_t n_grap
   TX_REQUIRE(n_graphs >= 0 && n_graphs < INT32_MAX && n_gp && n_sib && node_off && edge_off, "star_batch_plan: bad arguments");
   TX_REQUIRE((!tasks_fwd || (chunk_fwd >= 1 && aligned16(tasks_fwd))) && (!tasks_bwd || (chunk_bwd >= 1 && aligned16(tasks_bwd))),
              "star_batch_plan: task tables need a chunk size >= 1 and 16-byte alignment");
-  star_batch_plan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(n_gp, n_sib, (int)n_graphs, (int)chunk_fwd, (int)chunk_bwd, node_off, edge_off,
+  TX_PDL_LAUNCH((star_batch_plan_kernel), 1, 1024, 0, (cudaStream_t)stream, n_gp, n_sib, (int)n_graphs, (int)chunk_fwd, (int)chunk_bwd, node_off, edge_off,
                                                                reinterpret_cast<int4*>(tasks_fwd), reinterpret_cast<int4*>(tasks_bwd));
   TX_LAUNCH_CHECK("tx_star_batch_plan");
   return TX_OK;

@@ -12,6 +12,7 @@
 
 #include <initializer_list>
 
+#define TX_PDL_GROUP 1
 #include "tx_common.cuh"
 
 namespace tx {
@@ -42,6 +43,7 @@ template <int VEC>
 __global__ void __launch_bounds__(256) match_rowdot_fwd_kernel(const float* __restrict__ u, int64_t ldu, const float* __restrict__ q,
                                                                int64_t ldq, int n_rows, int r, int apply_exp,
                                                                float* __restrict__ scores) {
+  TX_PDL_ENTER();
   using V = typename VecN<VEC>::type;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -64,6 +66,7 @@ __global__ void __launch_bounds__(256) match_rowdot_bwd_kernel(const float* __re
                                                                const float* __restrict__ dscores, int n_rows, int r, int apply_exp,
                                                                float* __restrict__ du, int64_t lddu, float* __restrict__ dq,
                                                                int64_t lddq) {
+  TX_PDL_ENTER();
   using V = typename VecN<VEC>::type;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -89,6 +92,7 @@ __global__ void __launch_bounds__(256) match_rowdot_bwd_kernel(const float* __re
 __global__ void __launch_bounds__(256) info_nce_fwd_kernel(const float* __restrict__ scores, int n_queries, int group,
                                                            const int32_t* __restrict__ target, float* __restrict__ loss_q,
                                                            float* __restrict__ lse_q) {
+  TX_PDL_ENTER();
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -113,6 +117,7 @@ __global__ void __launch_bounds__(256) info_nce_fwd_kernel(const float* __restri
 __global__ void __launch_bounds__(256) info_nce_bwd_kernel(const float* __restrict__ scores, const float* __restrict__ lse_q,
                                                            int64_t total, int group, const int32_t* __restrict__ target,
                                                            const float* __restrict__ dloss, float* __restrict__ dscores) {
+  TX_PDL_ENTER();
   const float gl = __ldg(dloss);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int qi = (int)(i / group), j = (int)(i - (int64_t)qi * group);
@@ -151,9 +156,9 @@ int tx_match_rowdot_fwd(const float* u, int64_t ldu, const float* q, int64_t ldq
   const int grid = grid_for_warps(n_rows, 8, 8);
   const int vec = pick_vec(r, {ldu, ldq}, {u, q});
   cudaStream_t s = (cudaStream_t)stream;
-  if (vec == 4) match_rowdot_fwd_kernel<4><<<grid, 256, 0, s>>>(u, ldu, q, ldq, (int)n_rows, (int)r, apply_exp, scores);
-  else if (vec == 2) match_rowdot_fwd_kernel<2><<<grid, 256, 0, s>>>(u, ldu, q, ldq, (int)n_rows, (int)r, apply_exp, scores);
-  else match_rowdot_fwd_kernel<1><<<grid, 256, 0, s>>>(u, ldu, q, ldq, (int)n_rows, (int)r, apply_exp, scores);
+  if (vec == 4) TX_PDL_LAUNCH((match_rowdot_fwd_kernel<4>), grid, 256, 0, s, u, ldu, q, ldq, (int)n_rows, (int)r, apply_exp, scores);
+  else if (vec == 2) TX_PDL_LAUNCH((match_rowdot_fwd_kernel<2>), grid, 256, 0, s, u, ldu, q, ldq, (int)n_rows, (int)r, apply_exp, scores);
+  else TX_PDL_LAUNCH((match_rowdot_fwd_kernel<1>), grid, 256, 0, s, u, ldu, q, ldq, (int)n_rows, (int)r, apply_exp, scores);
   TX_LAUNCH_CHECK("tx_match_rowdot_fwd");
   return TX_OK;
 }
@@ -170,11 +175,11 @@ int tx_match_rowdot_bwd(const float* u, int64_t ldu, const float* q, int64_t ldq
   const int vec = pick_vec(r, {ldu, ldq, du ? lddu : 4, dq ? lddq : 4}, {u, q, du, dq});
   cudaStream_t s = (cudaStream_t)stream;
   if (vec == 4)
-    match_rowdot_bwd_kernel<4><<<grid, 256, 0, s>>>(u, ldu, q, ldq, scores, dscores, (int)n_rows, (int)r, apply_exp, du, lddu, dq, lddq);
+    TX_PDL_LAUNCH((match_rowdot_bwd_kernel<4>), grid, 256, 0, s, u, ldu, q, ldq, scores, dscores, (int)n_rows, (int)r, apply_exp, du, lddu, dq, lddq);
   else if (vec == 2)
-    match_rowdot_bwd_kernel<2><<<grid, 256, 0, s>>>(u, ldu, q, ldq, scores, dscores, (int)n_rows, (int)r, apply_exp, du, lddu, dq, lddq);
+    TX_PDL_LAUNCH((match_rowdot_bwd_kernel<2>), grid, 256, 0, s, u, ldu, q, ldq, scores, dscores, (int)n_rows, (int)r, apply_exp, du, lddu, dq, lddq);
   else
-    match_rowdot_bwd_kernel<1><<<grid, 256, 0, s>>>(u, ldu, q, ldq, scores, dscores, (int)n_rows, (int)r, apply_exp, du, lddu, dq, lddq);
+    TX_PDL_LAUNCH((match_rowdot_bwd_kernel<1>), grid, 256, 0, s, u, ldu, q, ldq, scores, dscores, (int)n_rows, (int)r, apply_exp, du, lddu, dq, lddq);
   TX_LAUNCH_CHECK("tx_match_rowdot_bwd");
   return TX_OK;
 }
@@ -190,7 +195,7 @@ int tx_info_nce_fwd(const float* scores, int64_t n_queries, int64_t group, const
     return TX_OK;
   }
   TX_REQUIRE(scores && loss_per_query, "tx_info_nce_fwd: null pointer");
-  info_nce_fwd_kernel<<<grid_for_warps(n_queries, 8, 8), 256, 0, (cudaStream_t)stream>>>(scores, (int)n_queries, (int)group, target,
+  TX_PDL_LAUNCH((info_nce_fwd_kernel), grid_for_warps(n_queries, 8, 8), 256, 0, (cudaStream_t)stream, scores, (int)n_queries, (int)group, target,
                                                                                         loss_per_query, lse_per_query);
   TX_LAUNCH_CHECK("tx_info_nce_fwd");
   return tx_reduce_partials(loss_per_query, n_queries, 1, loss, stream);
@@ -204,7 +209,7 @@ int tx_info_nce_bwd(const float* scores, const float* lse_per_query, int64_t n_q
   TX_REQUIRE(scores && lse_per_query && dloss && dscores, "tx_info_nce_bwd: null pointer");
   const int64_t total = n_queries * group;
   const int64_t need = (total + 255) / 256, cap = (int64_t)kNumSms * 8;
-  info_nce_bwd_kernel<<<(int)(need < cap ? need : cap), 256, 0, (cudaStream_t)stream>>>(scores, lse_per_query, total, (int)group,
+  TX_PDL_LAUNCH((info_nce_bwd_kernel), (int)(need < cap ? need : cap), 256, 0, (cudaStream_t)stream, scores, lse_per_query, total, (int)group,
                                                                                        target, dloss, dscores);
   TX_LAUNCH_CHECK("tx_info_nce_bwd");
   return TX_OK;

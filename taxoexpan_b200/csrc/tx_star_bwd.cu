@@ -31,6 +31,7 @@
 #include <math.h>
 #include <stdlib.h>
 
+#define TX_PDL_GROUP 3
 #include "tx_common.cuh"
 
 namespace tx {
@@ -115,6 +116,7 @@ struct SbItem { int o, q, a, s, c, ticket; };
 
 template <int NV, bool F16OUT>
 __global__ void __launch_bounds__(kSbWarps * 32, 1) gat_star_bwd_kernel(const StarBwdParams p) {
+  TX_PDL_ENTER();
   constexpr int kRowB = NV * 512;                          // one staged row (zero-padded columns are never copied)
   constexpr int kSlotB = kSbHdrBytes + 2 * kRowB;
   constexpr int kPartLd = NV * 128 + 4;                    // floats per partial row: accumulator | da1 part, da2 (chunk 0)
@@ -516,6 +518,7 @@ __global__ void __launch_bounds__(kSbWarps * 32, 1) gat_star_bwd_kernel(const St
 // v = z^T [da1 c | da2 c] = the 2 H extra rows of the weight-gradient GEMM): one warp per output element pair, fixed-order sums.
 __global__ void attn_grad_from_v_kernel(const float* __restrict__ w, int64_t ldw, const float* __restrict__ v, int64_t ldv, int H, int D, int K,
                                         const float* __restrict__ c_ptr, float* __restrict__ dal, float* __restrict__ dar) {
+  TX_PDL_ENTER();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= H * D) return;
@@ -559,7 +562,7 @@ static int sb_launch2(const StarBwdParams& p, dim3 grid, cudaStream_t st) {
     }
     attr_done = true;
   }
-  gat_star_bwd_kernel<NV, F16OUT><<<grid, kSbWarps * 32, smem, st>>>(p);
+  TX_PDL_LAUNCH((gat_star_bwd_kernel<NV, F16OUT>), grid, kSbWarps * 32, smem, st, p);
   return TX_OK;
 }
 template <int NV>
@@ -631,7 +634,7 @@ int tx_attn_grad_from_v(const float* weight, int64_t ldw, const float* v, int64_
                         const float* c, float* dattn_l, float* dattn_r, void* stream) {
   TX_REQUIRE(weight && v && c && dattn_l && dattn_r && heads >= 1 && dim >= 1 && k >= 1 && ldw >= k && ldv >= k, "attn_grad_from_v: bad arguments");
   const int64_t rows = heads * dim;
-  attn_grad_from_v_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(weight, ldw, v, ldv, (int)heads, (int)dim, (int)k, c,
+  TX_PDL_LAUNCH((attn_grad_from_v_kernel), (unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream, weight, ldw, v, ldv, (int)heads, (int)dim, (int)k, c,
                                                                                         dattn_l, dattn_r);
   TX_LAUNCH_CHECK("tx_attn_grad_from_v");
   return TX_OK;

@@ -16,6 +16,7 @@
 #include <math.h>
 #include <stdlib.h>
 
+#define TX_PDL_GROUP 4
 #include "tx_common.cuh"
 
 namespace tx {
@@ -188,6 +189,7 @@ __device__ __forceinline__ void star_epilogue(const StarFwdParams& p, int i, int
 
 template <int NV, int MODE>
 __global__ void __launch_bounds__(256, TX_STAR_MIN_BLOCKS) gat_star_fwd_kernel(const StarFwdParams p) {
+  TX_PDL_ENTER();
   __shared__ float4 s_l[NV * 32];
   __shared__ float4 s_r[NV * 32];
   const int h = blockIdx.y;
@@ -445,17 +447,17 @@ int tx_gat_star_fwd(const float* ft, int64_t ldf, const float* attn_l, const flo
   const bool hot = p.hidden && p.out16_hi && p.maskbits && p.act_slope != 1.f && p.next_thr != 0;
   if (hot) {
     switch (nv) {
-      case 1: gat_star_fwd_kernel<1, 1><<<grid, 256, 0, st>>>(p); break;
-      case 2: gat_star_fwd_kernel<2, 1><<<grid, 256, 0, st>>>(p); break;
-      case 3: gat_star_fwd_kernel<3, 1><<<grid, 256, 0, st>>>(p); break;
-      default: gat_star_fwd_kernel<4, 1><<<grid, 256, 0, st>>>(p); break;
+      case 1: TX_PDL_LAUNCH((gat_star_fwd_kernel<1, 1>), grid, 256, 0, st, p); break;
+      case 2: TX_PDL_LAUNCH((gat_star_fwd_kernel<2, 1>), grid, 256, 0, st, p); break;
+      case 3: TX_PDL_LAUNCH((gat_star_fwd_kernel<3, 1>), grid, 256, 0, st, p); break;
+      default: TX_PDL_LAUNCH((gat_star_fwd_kernel<4, 1>), grid, 256, 0, st, p); break;
     }
   } else {
     switch (nv) {
-      case 1: gat_star_fwd_kernel<1, 0><<<grid, 256, 0, st>>>(p); break;
-      case 2: gat_star_fwd_kernel<2, 0><<<grid, 256, 0, st>>>(p); break;
-      case 3: gat_star_fwd_kernel<3, 0><<<grid, 256, 0, st>>>(p); break;
-      default: gat_star_fwd_kernel<4, 0><<<grid, 256, 0, st>>>(p); break;
+      case 1: TX_PDL_LAUNCH((gat_star_fwd_kernel<1, 0>), grid, 256, 0, st, p); break;
+      case 2: TX_PDL_LAUNCH((gat_star_fwd_kernel<2, 0>), grid, 256, 0, st, p); break;
+      case 3: TX_PDL_LAUNCH((gat_star_fwd_kernel<3, 0>), grid, 256, 0, st, p); break;
+      default: TX_PDL_LAUNCH((gat_star_fwd_kernel<4, 0>), grid, 256, 0, st, p); break;
     }
   }
   TX_LAUNCH_CHECK("tx_gat_star_fwd");

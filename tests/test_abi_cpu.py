@@ -34,6 +34,28 @@ def test_library_exports_every_declared_symbol():
     assert l.tx_row_blocks(65) == 2
 
 
+def test_no_kernel_touches_global_memory_before_it_waits_for_its_predecessor():
+    """Programmatic dependent launch: a kernel may be scheduled while its predecessor still runs, so nothing that reads or writes global
+    memory may sit in front of its griddepcontrol.wait (SASS: ACQBULK).  ld.global.nc loads are NOT ordered by inline-asm memory clobbers -
+    the build once placed `LDG.E.CONSTANT` of a predecessor-written scalar before the wait - hence the check on the disassembly of the
+    library that ships (scripts/check_pdl_sass.py)."""
+    import shutil
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    from taxoexpan_b200 import build
+    build.build()
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import check_pdl_sass
+    res = check_pdl_sass.check(_lib.LIB_PATH)
+    assert len(res) >= 40, "the hot-path kernels are expected to wait on their predecessors"
+    bad = {k: v for k, v in res.items() if v}
+    assert not bad, bad
+    names = " ".join(res)
+    for must in ("gat_star_fwd_kernel", "gat_star_bwd_kernel", "gemm_tf32x3_pair_kernel", "readout_fwd_fast_kernel", "absmax_kernel"):
+        assert must in names, must
+
+
 def test_argument_validation_without_gpu():
     l = _lib.load()
     # invalid dropout rate is rejected before any CUDA call

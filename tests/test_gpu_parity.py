@@ -203,6 +203,42 @@ def test_concat_published_as_an_fp16_pair_matches_the_fp32_concat(k_in, pd, p, m
         assert float(rec[:, k_in + pd:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("arch", ["PGAT-WMR-LBM", "PGCN-MR-BIM"])
+def test_programmatic_dependent_launch_does_not_change_a_single_bit(arch):
+    """The hot-path kernels are launched with programmatic stream serialization (kernel k+1 is scheduled while kernel k drains).  Every
+    kernel waits for its predecessor before touching global memory, so scores, loss and every gradient must be bit-identical to the
+    fully serialised launches (tx_pdl_set(0)) - over several batches of different shapes, dropout active, repeated to give a race a
+    chance to show."""
+    lib = _lib.load()
+    pm, rm, mm = arch.split("-")
+    dims = dict(in_dim=250, hidden_dim=500, out_dim=500, pos_dim=50, num_layers=1, heads=[4, 1], feat_drop=0.1, attn_drop=0.1,
+                hidden_drop=0.1, out_drop=0.1)
+    torch.manual_seed(3)
+    model = tx.TaxoExpan(pm, rm, mm, **dims).to(dev()).train()
+    prev = lib.tx_pdl_set(1)
+    try:
+        for rep, nq in enumerate([64, 7, 64, 33]):
+            sh = tx.synth.sample_shapes(nq, 31, "mag-cs", seed=100 + rep)
+            x = torch.from_numpy(tx.synth.unit_rows(sh.total_nodes, 250, seed=rep)).to(dev())
+            qf = torch.from_numpy(tx.synth.unit_rows(sh.num_graphs, 250, seed=50 + rep)).to(dev())
+            outs = []
+            for pdl in (1, 0, 1):
+                lib.tx_pdl_set(pdl)
+                g = tx.EgonetBatch.from_counts(sh.n_gp, sh.n_sib)
+                model.zero_grad(set_to_none=True)
+                torch.manual_seed(1234 + rep)
+                scores = model(g, x, qf)
+                loss = tx.info_nce_loss(scores.reshape(nq, -1), None)
+                loss.backward()
+                torch.cuda.synchronize()
+                outs.append([scores.detach().clone(), loss.detach().clone()] + [p.grad.detach().clone() for p in model.parameters()])
+            for other in outs[1:]:
+                for a, b in zip(outs[0], other):
+                    assert torch.equal(a, b)
+    finally:
+        lib.tx_pdl_set(prev)
+
+
 def test_general_csr_build_is_bit_exact():
     rng = np.random.default_rng(0)
     n, e = 1000, 7000
