@@ -201,6 +201,17 @@ __device__ __forceinline__ bool pdl_wait_guard() {
     tx::pdl_trigger();          \
     if (!tx::pdl_wait_guard()) return; \
   } while (0)
+// The per-layer calls (tx_layer.cu) clear every device scalar their kernels accumulate into (max|.| outputs, the weight split's
+// rendezvous counter) with ONE memset at the start of the call and set this flag, so that tx_absmax / tx_split_f16_weight /
+// tx_gemm_nt_f16x3 skip their own cudaMemsetAsync: a memset between two kernels is a full stream dependency that the programmatic
+// launch cannot overlap.
+extern thread_local int g_preclear;
+bool preclear_enabled();                 // TAXO_PRECLEAR=0: the kernels' own memsets stay (A/B knob)
+struct PreclearScope {
+  int prev;
+  PreclearScope() : prev(g_preclear) { if (preclear_enabled()) g_preclear = 1; }
+  ~PreclearScope() { g_preclear = prev; }
+};
 bool pdl_enabled(int group = 0, const char* name = nullptr);
 int pdl_set(int enabled);
 template <typename... KArgs, typename... Args>

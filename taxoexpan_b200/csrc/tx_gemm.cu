@@ -1254,7 +1254,7 @@ int tx_gemm_nt_tf32x3_ex(const float* a_hi, const float* a_lo, int64_t lda, cons
 int tx_absmax(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* out, void* stream) {
   TX_REQUIRE(out && rows >= 0 && cols >= 0 && rows < INT32_MAX && cols < INT32_MAX && (rows == 0 || cols == 0 || x), "absmax: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  if (cudaMemsetAsync(out, 0, sizeof(float), st) != cudaSuccess) { set_error("absmax: memset failed"); return TX_ERR_CUDA; }
+  if (!g_preclear && cudaMemsetAsync(out, 0, sizeof(float), st) != cudaSuccess) { set_error("absmax: memset failed"); return TX_ERR_CUDA; }
   if (rows == 0 || cols == 0) return TX_OK;
   const int64_t total = rows * cols;
   const int grid = (int)((total + 1023) / 1024 < (int64_t)kNumSms * 8 ? (total + 1023) / 1024 : (int64_t)kNumSms * 8);
@@ -1296,7 +1296,7 @@ int tx_split_f16_weight(const float* w, int64_t ldw, int64_t rows, int64_t cols,
   TX_REQUIRE(ld % 8 == 0 && ld >= cols && ld_t % 8 == 0 && ld_t >= rows && aligned16(hi) && aligned16(lo) && aligned16(hi_t) && aligned16(lo_t),
              "split_f16_weight: outputs need ld %% 8 == 0 and 16-byte alignment");
   cudaStream_t st = (cudaStream_t)stream;
-  if (cudaMemsetAsync(scratch2, 0, 2 * sizeof(float), st) != cudaSuccess) { set_error("split_f16_weight: memset failed"); return TX_ERR_CUDA; }
+  if (!g_preclear && cudaMemsetAsync(scratch2, 0, 2 * sizeof(float), st) != cudaSuccess) { set_error("split_f16_weight: memset failed"); return TX_ERR_CUDA; }
   const int64_t tiles = ((std::max(rows, ld_t) + 31) / 32) * ((std::max(cols, ld) + 31) / 32);      // 32 x 32 tiles of the split phase
   int64_t grid = tiles;
   if (grid > (int64_t)kNumSms * kSplitWCtasPerSm) grid = (int64_t)kNumSms * kSplitWCtasPerSm;     // the grid-wide rendezvous needs every CTA resident
@@ -1361,7 +1361,7 @@ int tx_gemm_nt_f16x3(const void* a_hi, const void* a_lo, int64_t lda, const void
     epi.feat_cols = (int)(e->heads * e->dim); epi.has_keep = e->has_keep_plane;
     epi.on = 1.f / (1.f - e->p_drop); epi.neg = e->act_slope * epi.on;
   }
-  if (amax_out && cudaMemsetAsync(amax_out, 0, sizeof(float), st) != cudaSuccess) { set_error("gemm_f16: memset failed"); return TX_ERR_CUDA; }
+  if (amax_out && !g_preclear && cudaMemsetAsync(amax_out, 0, sizeof(float), st) != cudaSuccess) { set_error("gemm_f16: memset failed"); return TX_ERR_CUDA; }
   if (use_pair() && m > kBM && n > 128 && pick_bn(n) == 256) {
     // experiment knob: 128-wide tiles leave room for 4 accumulator buffers in TMEM, so the MMA stream can run a whole short-K tile
     // ahead of the epilogue.  Measured on the two wide-output GEMMs (K = 300 / 500): no gain (0.226 vs 0.229 ms, 0.290 vs 0.262 ms),

@@ -23,6 +23,12 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+thread_local int g_preclear = 0;
+bool preclear_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TAXO_PRECLEAR"); v = (e && atoi(e) == 0) ? 0 : 1; }
+  return v != 0;
+}
 static int g_pdl = -1, g_pdl_mask = 0xFFFF;
 static const char *g_pdl_only = nullptr, *g_pdl_skip = nullptr;
 static void pdl_init() {

@@ -67,9 +67,10 @@ struct FwdLayout {
   __half *z_hi, *z_lo; float *z_scale, *z_amax;
   __half *w_hi, *w_lo, *wt_hi, *wt_lo; float* w_scal;
   float *ft, *ft_amax, *alpha, *alpha_d, *elog;
-  uint32_t* maskbits; __half *out_hi, *out_lo; float *out_scale, *bound;
+  uint32_t* maskbits; __half *out_hi, *out_lo; float *out_scale, *bound, *scal;
   size_t bytes;
 };
+constexpr int kScalars = 16;     // floats in a layout's scalar block (64 bytes)
 
 static FwdLayout carve_fwd(const tx_gat_layer_desc& d, int split_input, void* ws) {
   Carver c(ws);
@@ -77,15 +78,13 @@ static FwdLayout carve_fwd(const tx_gat_layer_desc& d, int split_input, void* ws
   const int64_t F = d.heads * d.dim, K = d.k;
   L.z_hi = c.take<__half>(split_input ? d.n * r8(K) : 0);
   L.z_lo = c.take<__half>(split_input ? d.n * r8(K) : 0);
-  L.z_scale = c.take<float>(1);
-  L.z_amax = c.take<float>(1);
+  L.scal = c.take<float>(kScalars);          // every device scalar of the call in one block, cleared by one memset
+  L.w_scal = L.scal; L.z_scale = L.scal + 4; L.z_amax = L.scal + 5; L.ft_amax = L.scal + 6; L.out_scale = L.scal + 7; L.bound = L.scal + 8;
   L.w_hi = c.take<__half>(F * r8(K));
   L.w_lo = c.take<__half>(F * r8(K));
   L.wt_hi = c.take<__half>(K * r8(F));
   L.wt_lo = c.take<__half>(K * r8(F));
-  L.w_scal = c.take<float>(4);
   L.ft = c.take<float>(d.n * F);
-  L.ft_amax = c.take<float>(1);
   L.alpha = c.take<float>(d.e * d.heads);
   L.elog = c.take<float>(d.e * d.heads);
   L.alpha_d = d.p_attn > 0.f ? c.take<float>(d.e * d.heads) : L.alpha;
@@ -95,14 +94,12 @@ static FwdLayout carve_fwd(const tx_gat_layer_desc& d, int split_input, void* ws
   const int64_t ld16 = r8(F + d.pos_dim);
   L.out_hi = c.take<__half>(d.hidden ? d.n * ld16 : 0);
   L.out_lo = c.take<__half>(d.hidden ? d.n * ld16 : 0);
-  L.out_scale = c.take<float>(1);
-  L.bound = c.take<float>(1);
   L.bytes = c.off;
   return L;
 }
 
 struct BwdLayout {
-  float* pos_partial; float* bounds; __half *d_hi, *d_lo; float *d_scale, *g_amax, *star_partial, *ds, *tn_partial, *dz_amax;
+  float* pos_partial; float* bounds; __half *d_hi, *d_lo; float *d_scale, *g_amax, *star_partial, *ds, *tn_partial, *dz_amax, *scal;
   int64_t splits;
   size_t bytes;
 };
@@ -112,17 +109,15 @@ static BwdLayout carve_bwd(const tx_gat_layer_desc& d, void* ws) {
   BwdLayout L;
   const int64_t F = d.heads * d.dim, K = d.k, M = F + 2 * d.heads;
   L.pos_partial = c.take<float>(d.hidden && d.pos_dim > 0 ? tx_row_blocks(d.n) * d.vocab * d.pos_dim : 0);
-  L.bounds = c.take<float>(4);
+  L.scal = c.take<float>(kScalars);
+  L.bounds = L.scal; L.d_scale = L.scal + 4; L.g_amax = L.scal + 5; L.dz_amax = L.scal + 6;
   const int64_t ld16 = r8(M);
   L.d_hi = c.take<__half>(d.n * ld16);
   L.d_lo = c.take<__half>(d.n * ld16);
-  L.d_scale = c.take<float>(1);
-  L.g_amax = c.take<float>(1);
   L.star_partial = c.take<float>(tx_gat_star_bwd_partial_floats(d.n_tasks_bwd, d.heads, d.dim));
   L.ds = c.take<float>(d.e * d.heads);
   L.splits = tx_gemm_tn_f16_splits(M, K, d.n);
   L.tn_partial = c.take<float>(L.splits > 1 ? L.splits * M * r4(K) : 0);
-  L.dz_amax = c.take<float>(1);
   L.bytes = c.off;
   return L;
 }
@@ -161,6 +156,8 @@ int tx_gat_layer_fwd(const tx_gat_layer_desc* d, const float* z, int64_t ldz, co
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n = d->n, K = d->k, H = d->heads, D = d->dim, F = H * D, pd = d->hidden ? d->pos_dim : 0;
   const FwdLayout L = carve_fwd(*d, z != nullptr, workspace);
+  if (cudaMemsetAsync(L.scal, 0, kScalars * sizeof(float), st) != cudaSuccess) { set_error("gat_layer_fwd: memset failed"); return TX_ERR_CUDA; }
+  PreclearScope preclear;
   tx_gat_layer_state& S = *state;
   memset(&S, 0, sizeof(S));
   if (z) {
@@ -219,6 +216,8 @@ int tx_gat_layer_bwd(const tx_gat_layer_desc* d, const tx_gat_layer_state* state
   const tx_gat_layer_state& S = *state;
   const int64_t n = d->n, K = d->k, H = d->heads, D = d->dim, F = H * D, M = F + 2 * H, pd = d->hidden ? d->pos_dim : 0;
   const BwdLayout L = carve_bwd(*d, workspace);
+  if (cudaMemsetAsync(L.scal, 0, kScalars * sizeof(float), st) != cudaSuccess) { set_error("gat_layer_bwd: memset failed"); return TX_ERR_CUDA; }
+  PreclearScope preclear;
   if (d->hidden && pd > 0 && dtab) {
     // gradient of the position rows appended by this layer's epilogue (model_zoo.py:214-215)
     { ProfScope ps("tx_pos_grad_partials", d->tag, st);
@@ -288,7 +287,7 @@ namespace tx {
 struct GcnFwdLayout {
   __half *z_hi, *z_lo; float *z_scale, *z_amax;
   __half *w_hi, *w_lo, *wt_hi, *wt_lo; float* w_scal;
-  float *y, *y_amax; uint32_t* maskbits; __half *out_hi, *out_lo; float *out_scale, *bound;
+  float *y, *y_amax; uint32_t* maskbits; __half *out_hi, *out_lo; float *out_scale, *bound, *scal;
   size_t bytes;
 };
 static GcnFwdLayout carve_gcn_fwd(const tx_gcn_layer_desc& d, int split_input, void* ws) {
@@ -297,28 +296,24 @@ static GcnFwdLayout carve_gcn_fwd(const tx_gcn_layer_desc& d, int split_input, v
   const int64_t D = d.dim, K = d.k;
   L.z_hi = c.take<__half>(split_input ? d.n * r8(K) : 0);
   L.z_lo = c.take<__half>(split_input ? d.n * r8(K) : 0);
-  L.z_scale = c.take<float>(1);
-  L.z_amax = c.take<float>(1);
+  L.scal = c.take<float>(kScalars);
+  L.w_scal = L.scal; L.z_scale = L.scal + 4; L.z_amax = L.scal + 5; L.y_amax = L.scal + 6; L.out_scale = L.scal + 7; L.bound = L.scal + 8;
   L.w_hi = c.take<__half>(K * r8(D));        // [K, D]: the d(z) operand
   L.w_lo = c.take<__half>(K * r8(D));
   L.wt_hi = c.take<__half>(D * r8(K));       // [D, K]: the forward operand
   L.wt_lo = c.take<__half>(D * r8(K));
-  L.w_scal = c.take<float>(4);
   L.y = c.take<float>(d.n * r4(D));
-  L.y_amax = c.take<float>(1);
   const bool mask = d.hidden && (d.act_slope != 1.f || d.p_next > 0.f);
   L.maskbits = c.take<uint32_t>(mask ? tx_gat_fused_mask_words(d.n, 1, D) : 0);
   if (!mask) L.maskbits = nullptr;
   const int64_t ld16 = r8(D + d.pos_dim);
   L.out_hi = c.take<__half>(d.hidden ? d.n * ld16 : 0);
   L.out_lo = c.take<__half>(d.hidden ? d.n * ld16 : 0);
-  L.out_scale = c.take<float>(1);
-  L.bound = c.take<float>(1);
   L.bytes = c.off;
   return L;
 }
 struct GcnBwdLayout {
-  float *pos_partial, *col_partial, *bound, *g_amax; __half *d_hi, *d_lo; float *d_scale, *tn_partial, *dz_amax;
+  float *pos_partial, *col_partial, *bound, *g_amax; __half *d_hi, *d_lo; float *d_scale, *tn_partial, *dz_amax, *scal;
   int64_t splits;
   size_t bytes;
 };
@@ -328,14 +323,12 @@ static GcnBwdLayout carve_gcn_bwd(const tx_gcn_layer_desc& d, void* ws) {
   const int64_t D = d.dim, K = d.k;
   L.pos_partial = c.take<float>(d.hidden && d.pos_dim > 0 ? tx_row_blocks(d.n) * d.vocab * d.pos_dim : 0);
   L.col_partial = c.take<float>(d.bias ? tx_row_blocks(d.n) * D : 0);
-  L.bound = c.take<float>(1);
-  L.g_amax = c.take<float>(1);
+  L.scal = c.take<float>(kScalars);
+  L.bound = L.scal; L.g_amax = L.scal + 1; L.d_scale = L.scal + 2; L.dz_amax = L.scal + 3;
   L.d_hi = c.take<__half>(d.n * r8(D));
   L.d_lo = c.take<__half>(d.n * r8(D));
-  L.d_scale = c.take<float>(1);
   L.splits = tx_gemm_tn_f16_splits(D, K, d.n);
   L.tn_partial = c.take<float>(L.splits > 1 ? L.splits * D * r4(K) : 0);
-  L.dz_amax = c.take<float>(1);
   L.bytes = c.off;
   return L;
 }
@@ -363,6 +356,8 @@ int tx_gcn_layer_fwd(const tx_gcn_layer_desc* d, const float* z, int64_t ldz, co
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n = d->n, K = d->k, D = d->dim, pd = d->hidden ? d->pos_dim : 0;
   const GcnFwdLayout L = carve_gcn_fwd(*d, z != nullptr, workspace);
+  if (cudaMemsetAsync(L.scal, 0, kScalars * sizeof(float), st) != cudaSuccess) { set_error("gcn_layer_fwd: memset failed"); return TX_ERR_CUDA; }
+  PreclearScope preclear;
   tx_gat_layer_state& S = *state;
   memset(&S, 0, sizeof(S));
   if (z) {
@@ -416,6 +411,8 @@ int tx_gcn_layer_bwd(const tx_gcn_layer_desc* d, const tx_gat_layer_state* state
   const tx_gat_layer_state& S = *state;
   const int64_t n = d->n, K = d->k, D = d->dim, pd = d->hidden ? d->pos_dim : 0;
   const GcnBwdLayout L = carve_gcn_bwd(*d, workspace);
+  if (cudaMemsetAsync(L.scal, 0, kScalars * sizeof(float), st) != cudaSuccess) { set_error("gcn_layer_bwd: memset failed"); return TX_ERR_CUDA; }
+  PreclearScope preclear;
   if (d->hidden && pd > 0 && dtab) {
     { ProfScope ps("tx_pos_grad_partials", d->tag, st);
       TX_SUB(tx_pos_grad_partials(dout, ldg, D, d->pos, n, pd, d->vocab, d->p_next, d->next_seed, d->next_stream, L.pos_partial, stream)); }
@@ -471,40 +468,38 @@ int tx_gcn_layer_bwd(const tx_gcn_layer_desc* d, const tx_gat_layer_state* state
 
 namespace tx {
 
-struct HeadFwdLayout { float *hg, *hg_amax; __half *hg_hi, *hg_lo; float* hg_scale; __half *w_hi, *w_lo, *wt_hi, *wt_lo; float *w_scal, *u; size_t bytes; };
+struct HeadFwdLayout { float *hg, *hg_amax; __half *hg_hi, *hg_lo; float* hg_scale; __half *w_hi, *w_lo, *wt_hi, *wt_lo; float *w_scal, *u, *scal; size_t bytes; };
 static HeadFwdLayout carve_head_fwd(const tx_head_desc& d, void* ws) {
   Carver c(ws);
   HeadFwdLayout L;
   const int64_t l = d.dim, r = d.r;
   L.hg = c.take<float>(d.g * l);
-  L.hg_amax = c.take<float>(1);
+  L.scal = c.take<float>(kScalars);
+  L.w_scal = L.scal; L.hg_amax = L.scal + 4; L.hg_scale = L.scal + 5;
   L.hg_hi = c.take<__half>(d.g * r8(l));
   L.hg_lo = c.take<__half>(d.g * r8(l));
-  L.hg_scale = c.take<float>(1);
   L.w_hi = c.take<__half>(l * r8(r));          // [l, r]: the d(hg) operand
   L.w_lo = c.take<__half>(l * r8(r));
   L.wt_hi = c.take<__half>(r * r8(l));         // [r, l]: the forward operand
   L.wt_lo = c.take<__half>(r * r8(l));
-  L.w_scal = c.take<float>(4);
   L.u = c.take<float>(d.g * r4(r));
   L.bytes = c.off;
   return L;
 }
-struct HeadBwdLayout { float *du, *du_amax; __half *du_hi, *du_lo; float *du_scale, *dhg, *tn_partial, *pw_partial, *dhg_amax; int64_t splits; size_t bytes; };
+struct HeadBwdLayout { float *du, *du_amax; __half *du_hi, *du_lo; float *du_scale, *dhg, *tn_partial, *pw_partial, *dhg_amax, *scal; int64_t splits; size_t bytes; };
 static HeadBwdLayout carve_head_bwd(const tx_head_desc& d, void* ws) {
   Carver c(ws);
   HeadBwdLayout L;
   const int64_t l = d.dim, r = d.r;
   L.du = c.take<float>(d.g * r);
-  L.du_amax = c.take<float>(1);
+  L.scal = c.take<float>(kScalars);
+  L.du_amax = L.scal; L.du_scale = L.scal + 1; L.dhg_amax = L.scal + 2;
   L.du_hi = c.take<__half>(d.g * r8(r));
   L.du_lo = c.take<__half>(d.g * r8(r));
-  L.du_scale = c.take<float>(1);
   L.dhg = c.take<float>(d.g * r4(l));
   L.splits = tx_gemm_tn_f16_splits(l, r, d.g);
   L.tn_partial = c.take<float>(L.splits > 1 ? L.splits * l * r4(r) : 0);
   L.pw_partial = c.take<float>(d.kind == TX_READOUT_WMEAN ? tx_readout_bwd_blocks(d.g) * 3 : 0);
-  L.dhg_amax = c.take<float>(1);
   L.bytes = c.off;
   return L;
 }
@@ -530,6 +525,8 @@ int tx_head_fwd(const tx_head_desc* d, const float* h, int64_t ldh, const float*
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t G = d->g, l = d->dim, r = d->r;
   const HeadFwdLayout L = carve_head_fwd(*d, workspace);
+  if (cudaMemsetAsync(L.scal, 0, kScalars * sizeof(float), st) != cudaSuccess) { set_error("head_fwd: memset failed"); return TX_ERR_CUDA; }
+  PreclearScope preclear;
   { ProfScope ps("tx_readout_fwd", d->tag, st);
     TX_SUB(tx_readout_fwd(d->kind, h, ldh, d->pos, d->pos_weight, d->node_off, G, l, L.hg, l, stream)); }
   { ProfScope ps("tx_absmax", d->tag, st); TX_SUB(tx_absmax(L.hg, l, G, l, L.hg_amax, stream)); }
@@ -553,6 +550,8 @@ int tx_head_bwd(const tx_head_desc* d, const tx_head_state* state, const float* 
   const tx_head_state& S = *state;
   const int64_t G = d->g, l = d->dim, r = d->r;
   const HeadBwdLayout L = carve_head_bwd(*d, workspace);
+  if (cudaMemsetAsync(L.scal, 0, kScalars * sizeof(float), st) != cudaSuccess) { set_error("head_bwd: memset failed"); return TX_ERR_CUDA; }
+  PreclearScope preclear;
   { ProfScope ps("tx_match_rowdot_bwd", d->tag, st);
     TX_SUB(tx_match_rowdot_bwd(S.u, r4(r), q, ldq, S.scores, dscores, G, r, d->apply_exp, L.du, r, nullptr, 0, stream)); }
   { ProfScope ps("tx_absmax", d->tag, st); TX_SUB(tx_absmax(L.du, r, G, r, L.du_amax, stream)); }
