@@ -118,6 +118,11 @@ int tx_epilogue_bwd(float* dz, int64_t ldz, const float* z, const int32_t* pos, 
                     float* dpos_partial, void* stream);
 /* out[m] = sum_b partial[b*m_len + m]  (fixed order: deterministic). */
 int tx_reduce_partials(const float* partial, int64_t n_blocks, int64_t m_len, float* out, void* stream);
+/* The same for pitched [rows, cols] partials (partial[b] starts at b * block_stride, row pitch ld_in) into an output of row pitch ld_out:
+ * out[r, c] = sum_b partial[b, r, c], summed in index order (bit-identical to tx_reduce_partials).  Used to land a split-K weight gradient
+ * directly in its contiguous home (a parameter's .grad inside a flat gradient bucket) without a strided copy afterwards. */
+int tx_reduce_partials_rows(const float* partial, int64_t n_blocks, int64_t block_stride, int64_t rows, int64_t cols, int64_t ld_in,
+                            float* out, int64_t ld_out, void* stream);
 /* colsum_partial[b, c] = sum over rows of block b of x[i, c]  (GCN bias gradient, model_zoo.py:47). */
 int tx_colsum_partials(const float* x, int64_t ldx, int64_t n_rows, int64_t n_cols, float* partial, void* stream);
 
@@ -462,9 +467,12 @@ int64_t tx_gat_layer_fwd_bytes(const tx_gat_layer_desc* d, int32_t split_input);
 int64_t tx_gat_layer_bwd_bytes(const tx_gat_layer_desc* d);
 int tx_gat_layer_fwd(const tx_gat_layer_desc* d, const float* z, int64_t ldz, const tx_gat_layer_state* prev, void* workspace,
                      tx_gat_layer_state* state, float* out, void* stream);
+/* dw_ext: [heads*dim + 2*heads, round4(k)] (weight rows, then the attention-coefficient rows); dw_main (optional): contiguous
+ * [heads*dim, k] - when given the weight rows are written there as well / instead (directly by the split-K reduction), e.g. a
+ * parameter's .grad inside a flat gradient bucket; dattn_l / dattn_r: [heads*dim] each; dtab (optional): [vocab, pos_dim]. */
 int tx_gat_layer_bwd(const tx_gat_layer_desc* d, const tx_gat_layer_state* state, const tx_gat_layer_state* prev, const float* dout,
-                     int64_t ldg, const float* g_amax, void* workspace, float* dz, float* dw_ext, float* dattn, float* dtab,
-                     float** dz_amax_out, void* stream);
+                     int64_t ldg, const float* g_amax, void* workspace, float* dz, float* dw_ext, float* dw_main, float* dattn_l,
+                     float* dattn_r, float* dtab, float** dz_amax_out, void* stream);
 /* The same for a GCN layer (GCNLayer.forward and its autograd, model/model_zoo.py:34-50 inside the stacks of :128-137,155-167): split /
  * weight split / y = z W GEMM / bound / tx_gcn_aggregate_fwd(_f16), and d(position table), d(bias), bound, tx_gcn_aggregate_bwd_f16,
  * dW^T (-> dwt [dim, round4(k)]) , d(z).  Layers hand each other the tx_gat_layer_state (ft = y; alpha / elog unused; heads = 1). */
@@ -510,7 +518,8 @@ int64_t tx_head_bwd_bytes(const tx_head_desc* d);
 int tx_head_fwd(const tx_head_desc* d, const float* h, int64_t ldh, const float* q, int64_t ldq, void* workspace, tx_head_state* state,
                 float* scores, void* stream);
 int tx_head_bwd(const tx_head_desc* d, const tx_head_state* state, const float* h, int64_t ldh, const float* q, int64_t ldq,
-                const float* dscores, void* workspace, float* dh, float* dw, float* dpos_weight, float** dh_amax_out, void* stream);
+                const float* dscores, void* workspace, float* dh, float* dw, float* dw_main, float* dpos_weight, float** dh_amax_out,
+                void* stream);      /* dw: [dim, round4(r)] pitched; dw_main (optional): contiguous [dim, r] */
 /* measurement aid (bench.py): kernel launches issued by the two calls above since the last reset, and optional CUDA-event timing of
  * each of them (creates events; read after synchronising the stream) */
 int64_t tx_layer_launches(int32_t reset);

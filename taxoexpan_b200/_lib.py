@@ -100,6 +100,7 @@ _SIGNATURES = {
     "tx_concat_pos_dropout_f16": [P, I64, P, P, I64, I64, I64, I64, F32, c_uint64, c_uint32, P, P, P, I64, P, P],
     "tx_epilogue_bwd": [P, I64, P, P, I64, I64, I64, I64, F32, F32, c_uint64, c_uint32, P, P],
     "tx_reduce_partials": [P, I64, I64, P, P],
+    "tx_reduce_partials_rows": [P, I64, I64, I64, I64, I64, P, I64, P],
     "tx_colsum_partials": [P, I64, I64, I64, P, P],
     "tx_gat_node_logits": [P, I64, P, P, I64, I64, I64, P, P, P],
     "tx_gat_aggregate_fwd": [P, I64, P, P, P, P, P, P, P, I64, I64, I64, I64, F32, F32, c_uint64, c_uint32, P, P, P, P,
@@ -161,7 +162,7 @@ _SIGNATURES = {
     "tx_gat_layer_fwd_bytes": [POINTER(GatLayerDesc), c_int32],
     "tx_gat_layer_bwd_bytes": [POINTER(GatLayerDesc)],
     "tx_gat_layer_fwd": [POINTER(GatLayerDesc), P, I64, POINTER(GatLayerState), P, POINTER(GatLayerState), P, P],
-    "tx_gat_layer_bwd": [POINTER(GatLayerDesc), POINTER(GatLayerState), POINTER(GatLayerState), P, I64, P, P, P, P, P, P,
+    "tx_gat_layer_bwd": [POINTER(GatLayerDesc), POINTER(GatLayerState), POINTER(GatLayerState), P, I64, P, P, P, P, P, P, P, P,
                          POINTER(c_void_p), P],
     "tx_gcn_layer_fwd_bytes": [POINTER(GcnLayerDesc), c_int32],
     "tx_gcn_layer_bwd_bytes": [POINTER(GcnLayerDesc)],
@@ -171,7 +172,7 @@ _SIGNATURES = {
     "tx_head_fwd_bytes": [POINTER(HeadDesc)],
     "tx_head_bwd_bytes": [POINTER(HeadDesc)],
     "tx_head_fwd": [POINTER(HeadDesc), P, I64, P, I64, P, POINTER(HeadState), P, P],
-    "tx_head_bwd": [POINTER(HeadDesc), POINTER(HeadState), P, I64, P, I64, P, P, P, P, P, POINTER(c_void_p), P],
+    "tx_head_bwd": [POINTER(HeadDesc), POINTER(HeadState), P, I64, P, I64, P, P, P, P, P, P, POINTER(c_void_p), P],
     "tx_layer_launches": [c_int32],
     "tx_prof_enable": [c_int32],
     "tx_prof_clear": [],

@@ -271,6 +271,22 @@ __global__ void __launch_bounds__(256) reduce_partials_wide_kernel(const float* 
   }
 }
 
+// the same for a [rows, cols] block of pitched partials written to a (differently) pitched output: out[r, c] = sum_b partial[b, r, c] in
+// index order (bit-identical to reduce_partials_wide_kernel).  Lets a weight gradient land directly in its contiguous [rows, cols] home
+// (a parameter's .grad / a flat gradient bucket) although the split-K partials have a 16-byte-aligned row pitch.
+__global__ void __launch_bounds__(256) reduce_partials_rows_kernel(const float* __restrict__ partial, int n_blocks, int64_t block_stride,
+                                                                   int rows, int cols, int64_t ld_in, float* __restrict__ out, int64_t ld_out) {
+  TX_PDL_ENTER();
+  const int64_t total = (int64_t)rows * cols;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(t / cols), c = (int)(t - (int64_t)r * cols);
+    const float* src = partial + (int64_t)r * ld_in + c;
+    float s = __ldg(src);
+    for (int b = 1; b < n_blocks; ++b) s += __ldg(src + (int64_t)b * block_stride);
+    out[(int64_t)r * ld_out + c] = s;
+  }
+}
+
 // partial[b, m] summed over b in a FIXED order: 32 columns per CTA, the blocks dealt round-robin to WY warps (4 independent loads
 // in flight per thread), then a fixed-order tree over the warps.  WY = 32 for long block lists (few columns, hundreds of
 // blocks: the dependent-load chain per thread was 70+ loads with 8 warps), 8 otherwise.
@@ -1266,6 +1282,19 @@ int tx_reduce_partials(const float* partial, int64_t n_blocks, int64_t m_len, fl
   else
     TX_PDL_LAUNCH((reduce_partials_kernel<8>), (int)((m_len + 31) / 32), 256, 0, (cudaStream_t)stream, partial, n_blocks, m_len, out);
   TX_LAUNCH_CHECK("tx_reduce_partials");
+  return TX_OK;
+}
+
+int tx_reduce_partials_rows(const float* partial, int64_t n_blocks, int64_t block_stride, int64_t rows, int64_t cols, int64_t ld_in,
+                            float* out, int64_t ld_out, void* stream) {
+  TX_REQUIRE(partial && out && n_blocks >= 1 && rows >= 0 && cols >= 0 && ld_in >= cols && ld_out >= cols && block_stride >= rows * ld_in &&
+             rows < INT32_MAX && cols < INT32_MAX && n_blocks < INT32_MAX, "reduce_partials_rows: bad arguments");
+  if (rows == 0 || cols == 0) return TX_OK;
+  const int64_t total = rows * cols;
+  const int grid = (int)((total + 255) / 256 < (int64_t)kNumSms * 16 ? (total + 255) / 256 : (int64_t)kNumSms * 16);
+  TX_PDL_LAUNCH((reduce_partials_rows_kernel), grid, 256, 0, (cudaStream_t)stream, partial, (int)n_blocks, block_stride, (int)rows, (int)cols, ld_in,
+                out, ld_out);
+  TX_LAUNCH_CHECK("tx_reduce_partials_rows");
   return TX_OK;
 }
 

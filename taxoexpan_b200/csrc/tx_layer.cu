@@ -208,10 +208,10 @@ int tx_gat_layer_fwd(const tx_gat_layer_desc* d, const float* z, int64_t ldz, co
 }
 
 int tx_gat_layer_bwd(const tx_gat_layer_desc* d, const tx_gat_layer_state* state, const tx_gat_layer_state* prev, const float* dout,
-                     int64_t ldg, const float* g_amax, void* workspace, float* dz, float* dw_ext, float* dattn, float* dtab,
-                     float** dz_amax_out, void* stream) {
+                     int64_t ldg, const float* g_amax, void* workspace, float* dz, float* dw_ext, float* dw_main, float* dattn_l,
+                     float* dattn_r, float* dtab, float** dz_amax_out, void* stream) {
   TX_SUB(check_desc(d, "gat_layer_bwd"));
-  TX_REQUIRE(state && workspace && aligned16(workspace) && dout && dw_ext && dattn, "gat_layer_bwd: missing buffers");
+  TX_REQUIRE(state && workspace && aligned16(workspace) && dout && dw_ext && dattn_l && dattn_r, "gat_layer_bwd: missing buffers");
   cudaStream_t st = (cudaStream_t)stream;
   const tx_gat_layer_state& S = *state;
   const int64_t n = d->n, K = d->k, H = d->heads, D = d->dim, F = H * D, M = F + 2 * H, pd = d->hidden ? d->pos_dim : 0;
@@ -249,9 +249,19 @@ int tx_gat_layer_bwd(const tx_gat_layer_desc* d, const tx_gat_layer_state* state
   { ProfScope ps("gemm_dw", d->tag, st);
     TX_SUB(tx_gemm_tn_f16x3(L.d_hi, L.d_lo, ld16, S.z_hi, S.z_lo, S.ldz16, L.d_scale, S.z_scale, L.splits > 1 ? L.tn_partial : dw_ext, ldc,
                             M * ldc, M, K, n, L.splits, stream));
-    if (L.splits > 1) TX_SUB(tx_reduce_partials(L.tn_partial, L.splits, M * ldc, dw_ext, stream)); }
+    if (L.splits > 1 && dw_main) {
+      // the F weight rows go straight to their contiguous [F, K] home (a parameter's .grad), the 2 H attention rows to dw_ext
+      TX_SUB(tx_reduce_partials_rows(L.tn_partial, L.splits, M * ldc, F, K, ldc, dw_main, K, stream));
+      TX_SUB(tx_reduce_partials_rows(L.tn_partial + F * ldc, L.splits, M * ldc, 2 * H, K, ldc, dw_ext + F * ldc, ldc, stream));
+    } else {
+      if (L.splits > 1) TX_SUB(tx_reduce_partials(L.tn_partial, L.splits, M * ldc, dw_ext, stream));
+      if (dw_main && cudaMemcpy2DAsync(dw_main, K * sizeof(float), dw_ext, ldc * sizeof(float), K * sizeof(float), F, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+        set_error("gat_layer_bwd: copy of the weight gradient failed");
+        return TX_ERR_CUDA;
+      }
+    } }
   { ProfScope ps("tx_attn_grad_from_v", d->tag, st);
-    TX_SUB(tx_attn_grad_from_v(d->weight, d->ldw, dw_ext + F * ldc, ldc, H, D, K, L.bounds + 2, dattn, dattn + F, stream)); }
+    TX_SUB(tx_attn_grad_from_v(d->weight, d->ldw, dw_ext + F * ldc, ldc, H, D, K, L.bounds + 2, dattn_l, dattn_r, stream)); }
   if (dz) {
     // d(z)[:, c0a:K] = d(ft) W[:, c0a:K]; the epilogue applies the derivative of the previous layer's leaky-relu / dropout
     const int64_t c0 = d->dz_from < K ? d->dz_from : K;
@@ -543,9 +553,10 @@ int tx_head_fwd(const tx_head_desc* d, const float* h, int64_t ldh, const float*
 }
 
 int tx_head_bwd(const tx_head_desc* d, const tx_head_state* state, const float* h, int64_t ldh, const float* q, int64_t ldq,
-                const float* dscores, void* workspace, float* dh, float* dw, float* dpos_weight, float** dh_amax_out, void* stream) {
+                const float* dscores, void* workspace, float* dh, float* dw, float* dw_main, float* dpos_weight, float** dh_amax_out,
+                void* stream) {
   TX_SUB(check_head_desc(d, "head_bwd"));
-  TX_REQUIRE(state && h && q && dscores && workspace && dh && dw && aligned16(workspace), "head_bwd: missing buffers");
+  TX_REQUIRE(state && h && q && dscores && workspace && dh && (dw || dw_main) && aligned16(workspace), "head_bwd: missing buffers");
   cudaStream_t st = (cudaStream_t)stream;
   const tx_head_state& S = *state;
   const int64_t G = d->g, l = d->dim, r = d->r;
@@ -560,9 +571,19 @@ int tx_head_bwd(const tx_head_desc* d, const tx_head_state* state, const float* 
     TX_SUB(tx_gemm_nt_f16x3(L.du_hi, L.du_lo, r8(r), S.w_hi, S.w_lo, r8(r), L.du_scale, S.w_scale, L.dhg, r4(l), G, l, r, nullptr, nullptr, stream)); }
   const int64_t ldc = r4(r);
   { ProfScope ps("tx_gemm_tn_f16x3", d->tag, st);                               // dW = hg^T d(u)
+    // dw: [l, round4(r)] pitched; dw_main (optional): the contiguous [l, r] home of the gradient (a parameter's .grad)
+    TX_REQUIRE(dw || L.splits > 1, "head_bwd: dw (pitched) is required when the weight-gradient GEMM does not run split-K");
     TX_SUB(tx_gemm_tn_f16x3(S.hg_hi, S.hg_lo, r8(l), L.du_hi, L.du_lo, r8(r), S.hg_scale, L.du_scale, L.splits > 1 ? L.tn_partial : dw, ldc, l * ldc,
                             l, r, G, L.splits, stream));
-    if (L.splits > 1) TX_SUB(tx_reduce_partials(L.tn_partial, L.splits, l * ldc, dw, stream)); }
+    if (L.splits > 1 && dw_main) {
+      TX_SUB(tx_reduce_partials_rows(L.tn_partial, L.splits, l * ldc, l, r, ldc, dw_main, r, stream));
+    } else {
+      if (L.splits > 1) TX_SUB(tx_reduce_partials(L.tn_partial, L.splits, l * ldc, dw, stream));
+      if (dw_main && cudaMemcpy2DAsync(dw_main, r * sizeof(float), dw, ldc * sizeof(float), r * sizeof(float), l, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+        set_error("head_bwd: copy of the weight gradient failed");
+        return TX_ERR_CUDA;
+      }
+    } }
   { ProfScope ps("tx_readout_bwd", d->tag, st);
     TX_SUB(tx_readout_bwd(d->kind, L.dhg, r4(l), h, ldh, S.hg, l, d->pos, d->pos_weight, d->node_off, G, l, dh, l,
                           d->kind == TX_READOUT_WMEAN && dpos_weight ? L.pw_partial : nullptr, stream)); }

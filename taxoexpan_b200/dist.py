@@ -53,15 +53,22 @@ class FlatGradBucket:
       contributes zeros) - so the reduced buffer always equals the sum of the ranks' gradients, whichever way the caller zeroes.
     * with `overlap=True` (default) a segment's all-reduce starts inside backward, as soon as its last gradient is final;
       `all_reduce()` launches whatever has not started and makes the CURRENT stream wait for all of it (no host block).
+    * with `write_through=True` (default) every slice is registered as the home of its parameter's gradient
+      (`functional.register_grad_sink`): the native backward calls write the gradient straight into the slice and autograd adopts the
+      alias as `.grad` - no add / copy kernel per parameter - PROVIDED `.grad` is None when backward runs, so `zero_()` then drops
+      the gradients instead of zero-filling the buffer (a parameter that receives no gradient is zero-filled by `all_reduce()`).
+      Gradients produced elsewhere (torch ops, the per-kernel paths) are copied in by the hooks as before.
     """
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], segments: int = 2, overlap: bool = True, group=None):
+    def __init__(self, params: Iterable[torch.nn.Parameter], segments: int = 2, overlap: bool = True, group=None,
+                 write_through: bool = True):
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
         self.group = group
         self.overlap = overlap
         self.segments = segments
+        self.write_through = bool(write_through)
         self.active = True                        # False: hooks only keep the views bound (no exchange is launched)
         self._rebuilt = False
         self._fire_order = []
@@ -86,6 +93,9 @@ class FlatGradBucket:
                 v.copy_(old_views[i])
             self._views[i] = v
             p.grad = v
+            if self.write_through:
+                from . import functional as txf
+                txf.register_grad_sink(p, v)
             edges.append(edges[-1] + p.numel())
         n_seg = max(1, min(int(self.segments), len(order)))
         total = self.flat.numel()
@@ -156,11 +166,15 @@ class FlatGradBucket:
     # ---- public ----
     def zero_(self):
         """Clear the flat buffer in place and (re-)bind every .grad view: call before each backward."""
-        for w in self._works:                     # a reduction still in flight must not race the clear
+        for w in self._works:                     # a reduction still in flight must not race the clear / the next backward's writes
             w.wait()
-        self.flat.zero_()
-        for p, v in zip(self.params, self._views):
-            p.grad = v
+        if self.write_through:
+            for p in self.params:                 # .grad None: the gradient sinks are armed, autograd adopts what backward returns
+                p.grad = None
+        else:
+            self.flat.zero_()
+            for p, v in zip(self.params, self._views):
+                p.grad = v
         self._reset_step()
 
     def all_reduce(self, group=None):
@@ -190,3 +204,7 @@ class FlatGradBucket:
         for h in self._hooks:
             h.remove()
         self._hooks = []
+        if self.write_through:
+            from . import functional as txf
+            for p in self.params:
+                txf.unregister_grad_sink(p)

@@ -10,6 +10,7 @@ for 128-bit accesses / TMA); the logical width K <= ld is tracked by the caller,
 from __future__ import annotations
 
 import os
+import weakref
 from dataclasses import dataclass
 from typing import Optional
 
@@ -95,6 +96,9 @@ LAYER_CALL = os.environ.get("TAXO_LAYER_CALL", "1") not in ("", "0")
 # one pass over x for max|x|, one pass that reads x and writes the pair) instead of fp32 z -> max|z| -> split (three passes over z);
 # TAXO_CONCAT_F16=0 -> the fp32 z
 CONCAT_F16 = os.environ.get("TAXO_CONCAT_F16", "1") not in ("", "0")
+# parameter gradients written by the native backward calls directly into a registered flat gradient bucket (see grad_sink below);
+# TAXO_GRAD_WRITE_THROUGH=0 -> freshly allocated gradients that autograd adds / copies into the bucket
+GRAD_WRITE_THROUGH = os.environ.get("TAXO_GRAD_WRITE_THROUGH", "1") not in ("", "0")
 
 _star_counter_bufs = {}
 _star_rerun_bufs = {}
@@ -412,8 +416,9 @@ def new_seed() -> int:
     return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
 
 
-def _reduce_partials(lib, partial: torch.Tensor, n_blocks: int, m_len: int) -> torch.Tensor:
-    out = torch.empty(m_len, dtype=torch.float32, device=partial.device)
+def _reduce_partials(lib, partial: torch.Tensor, n_blocks: int, m_len: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty(m_len, dtype=torch.float32, device=partial.device)
     check(lib.tx_reduce_partials(ptr(partial), n_blocks, m_len, ptr(out), current_stream()), "tx_reduce_partials")
     return out
 
@@ -452,6 +457,42 @@ def dropout_keep_mask(seed: int, stream_id: int, first_index: int, n: int, p: fl
 # --------------------------------------------------------------------------------------------------
 # z = drop([x || P[pos]])
 # --------------------------------------------------------------------------------------------------
+# --------------------------------------------------------------------------------------------------
+# Gradient sinks: a flat gradient bucket (taxoexpan_b200/dist.py) registers, per parameter, the slice of its buffer that is the
+# parameter's .grad.  The native backward calls then write a gradient straight into that slice and return an alias of it, so
+# autograd's AccumulateGrad adopts the tensor as .grad without an add / copy kernel (it "steals" a contiguous gradient nobody else
+# references when .grad is None).  Only when the parameter's .grad is None - with an existing .grad autograd must accumulate, and the
+# usual freshly allocated gradient is returned.
+# --------------------------------------------------------------------------------------------------
+_grad_sinks = {}
+
+
+def register_grad_sink(param: torch.Tensor, flat_view: torch.Tensor):
+    _grad_sinks[param.data_ptr()] = (weakref.ref(param), flat_view)
+
+
+def unregister_grad_sink(param: torch.Tensor):
+    _grad_sinks.pop(param.data_ptr(), None)
+
+
+def grad_sink(param_like: Optional[torch.Tensor], numel: int) -> Optional[torch.Tensor]:
+    """A fresh 1-D alias of the registered home of this parameter's gradient (matched by data pointer, so views like W.weight.view(l, r)
+    find their parameter), or None when there is none / the parameter already holds a gradient that autograd has to add to."""
+    if param_like is None or not _grad_sinks or not GRAD_WRITE_THROUGH:
+        return None
+    ent = _grad_sinks.get(param_like.data_ptr())
+    if ent is None:
+        return None
+    p = ent[0]()
+    if p is None:
+        _grad_sinks.pop(param_like.data_ptr(), None)
+        return None
+    v = ent[1]
+    if p.grad is not None or v.numel() != numel or v.device != param_like.device or not v.is_contiguous():
+        return None
+    return v.view(-1)
+
+
 def concat_publishes_f16() -> bool:
     """The layer-0 input is written straight as the fp16 operand pair of the first projection GEMM (tx_concat_pos_dropout_f16) when the
     default dense back-end consumes such pairs; any other configuration gets the fp32 z of tx_concat_pos_dropout_fwd."""
@@ -489,6 +530,7 @@ class ConcatPosDropout(Function):
             link.applied, link.z16, link.z_lo, link.dz_amax, link.c_bwd, link.mask = False, None, None, None, None, None
             ctx.save_for_backward(pos32 if pos32 is not None else torch.empty(0))
             ctx.meta = (n, k_in, pd, vocab, ldz, float(p), int(seed), int(stream_id))
+            ctx.tab_ref = pos_table
             return z
         with device_guard(x.device):
             check(lib.tx_concat_pos_dropout_fwd(ptr(x), x.stride(0) if n > 1 else k_in, ptr(tab), ptr(pos32), n, k_in, pd,
@@ -496,6 +538,7 @@ class ConcatPosDropout(Function):
                   "tx_concat_pos_dropout_fwd")
         ctx.save_for_backward(pos32 if pos32 is not None else torch.empty(0))
         ctx.meta = (n, k_in, pd, vocab, ldz, float(p), int(seed), int(stream_id))
+        ctx.tab_ref = pos_table
         return z
 
     @staticmethod
@@ -518,7 +561,7 @@ class ConcatPosDropout(Function):
                 partial = torch.empty(nb * vocab * pd, dtype=torch.float32, device=dz.device)
                 check(lib.tx_pos_grad_partials(ptr(dz), dz.stride(0) if n > 1 else ldz, k_in, ptr(pos32), n, pd, vocab, p, seed, stream_id,
                                                ptr(partial), current_stream()), "tx_pos_grad_partials")
-                dtab = _reduce_partials(lib, partial, nb, vocab * pd).view(vocab, pd)
+                dtab = _reduce_partials(lib, partial, nb, vocab * pd, out=grad_sink(ctx.tab_ref, vocab * pd)).view(vocab, pd)
             return None, dtab, None, None, None, None, None
         if p > 0.0:
             dz = dz.clone()      # the kernel rescales the kept entries in place; never touch the caller's grad
@@ -851,20 +894,29 @@ class GatLayer(Function):
                     bws = torch.empty(int(lib.tx_gat_layer_bwd_bytes(ctypes.byref(desc))), dtype=torch.uint8, device=dev)
                     ldc = round4(K)
                     dw_ext = torch.empty((F_ + 2 * H, ldc), **f32)
-                    both = torch.empty(2 * F_, **f32)
+                    # gradients go straight to their registered homes (a flat bucket's slices) when there are any, else to fresh
+                    # CONTIGUOUS tensors - either way autograd adopts them as .grad without a copy
+                    dw = grad_sink(weight, F_ * K)
+                    dw = torch.empty((F_, K), **f32) if dw is None else dw.view(F_, K)
+                    dal, dar = grad_sink(attn_l, F_), grad_sink(attn_r, F_)
+                    if dal is None or dar is None:
+                        both = torch.empty(2 * F_, **f32)
+                        dal, dar = both[:F_], both[F_:]
                     dz = torch.empty((n, ldz), **f32) if need_z else None
-                    dtab = torch.empty((ctx.vocab, pd), **f32) if need_tab else None
+                    dtab = None
+                    if need_tab:
+                        dtab = grad_sink(tab, ctx.vocab * pd)
+                        dtab = torch.empty((ctx.vocab, pd), **f32) if dtab is None else dtab.view(ctx.vocab, pd)
                     dz_amax = ctypes.c_void_p()
                     prev = None if cfg.in_link is None else cfg.in_link.c_state
                     check(lib.tx_gat_layer_bwd(ctypes.byref(desc), ctypes.byref(state), None if prev is None else ctypes.byref(prev),
-                                               ptr(dout), ldg, g_amax, ptr(bws), ptr(dz), ptr(dw_ext), ptr(both), ptr(dtab),
+                                               ptr(dout), ldg, g_amax, ptr(bws), ptr(dz), ptr(dw_ext), ptr(dw), ptr(dal), ptr(dar), ptr(dtab),
                                                ctypes.byref(dz_amax), current_stream()), "tx_gat_layer_bwd")
                     if cfg.in_link is not None and need_z:
                         cfg.in_link.c_bwd = (dz_amax.value, bws)
                         cfg.in_link.applied = bool(prev is not None and prev.maskbits)
                         cfg.in_link.dz_amax = None
-                dw = dw_ext[:F_, :K]
-                return dz, dw, both[:F_].view(ctx.attn_shape), both[F_:].view(ctx.attn_shape), dtab, None, None, None
+                return dz, dw, dal.view(ctx.attn_shape), dar.view(ctx.attn_shape), dtab, None, None, None
             saved = GatLayer._native_saved(ctx)
         else:
             saved = ctx.saved_tensors
@@ -1496,13 +1548,17 @@ class ReadoutMatch(Function):
             bws = torch.empty(int(lib.tx_head_bwd_bytes(ctypes.byref(d))), dtype=torch.uint8, device=dev)
             dh = torch.empty((n, D), **f32)
             dw_buf = torch.empty((D, round4(r)), **f32)
+            dw = grad_sink(w, D * r)
+            dw = torch.empty((D, r), **f32) if dw is None else dw.view(D, r)
             need_pw = pos_weight is not None and ctx.needs_input_grad[1]
-            dpw = torch.empty(3, **f32) if need_pw else None
+            dpw = None
+            if need_pw:
+                dpw = grad_sink(pos_weight, 3)
+                dpw = torch.empty(3, **f32) if dpw is None else dpw
             amax = ctypes.c_void_p()
             check(lib.tx_head_bwd(ctypes.byref(d), ctypes.byref(state), ptr(h), h.stride(0), ptr(qf), qf.stride(0), ptr(dscores), ptr(bws),
-                                  ptr(dh), ptr(dw_buf), ptr(dpw), ctypes.byref(amax), current_stream()), "tx_head_bwd")
+                                  ptr(dh), ptr(dw_buf), ptr(dw), ptr(dpw), ctypes.byref(amax), current_stream()), "tx_head_bwd")
             # max|d(hg)| >= max|d(h)|: handed to the output layer's backward (it receives exactly this d(h))
             off = amax.value - bws.data_ptr()
             st._dh_bound = (dh.data_ptr(), bws[off:off + 4].view(torch.float32))
-        dw = dw_buf[:, :r] if ctx.needs_input_grad[2] else None
-        return dh, (dpw.view(ctx.wshape) if need_pw else None), dw, None, None, None, None, None
+        return dh, (dpw.view(ctx.wshape) if need_pw else None), (dw if ctx.needs_input_grad[2] else None), None, None, None, None, None

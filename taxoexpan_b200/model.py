@@ -74,12 +74,16 @@ class TaxoExpan(BaseModel):
         pos = g.ndata['pos'].to(h.device)
         g.ndata['h'] = self.graph_propagate(g, h)
         kind = getattr(self.readout, "kind", None)
-        if type(self.match) in (BIM, LBM) and kind is not None and txf.head_native_ok(g.ndata['h'], qf, kind, self.match.W.weight[0]):
+        w_match = None
+        if type(self.match) in (BIM, LBM):     # nn.Bilinear weight [1, l, r] seen as [l, r] - a VIEW (weight[0] would cost a zero-fill + copy in
+            w_match = self.match.W.weight      # its select-backward, and hide the parameter from the gradient sinks)
+            w_match = w_match.view(w_match.shape[1], w_match.shape[2])
+        if w_match is not None and kind is not None and txf.head_native_ok(g.ndata['h'], qf, kind, w_match):
             # model.py:85-86 as ONE native call per direction (readout, projection GEMM, row-dot; tx_head_fwd / tx_head_bwd): the same
             # kernels as self.readout(g, pos) followed by self.match(hg, qf)
             pw = getattr(self.readout, "position_weights", None)
             pos32 = as_int32_pos(pos, h.device) if kind == _lib.TX_READOUT_WMEAN else None
-            return txf.ReadoutMatch.apply(g.ndata['h'], None if pw is None else pw.weight, self.match.W.weight[0], qf,
+            return txf.ReadoutMatch.apply(g.ndata['h'], None if pw is None else pw.weight, w_match, qf,
                                           g.structure(h.device), pos32, kind, self.match.apply_exp)
         hg = self.readout(g, pos)
         scores = self.match(hg, qf)

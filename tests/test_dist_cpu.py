@@ -110,8 +110,20 @@ def test_flat_bucket_views_alias_the_buffer():
     assert b.flat.numel() == 8
     lin(torch.ones(1, 3)).sum().backward()
     assert torch.equal(b.flat[:6].view(2, 3), lin.weight.grad) and float(b.flat.abs().sum()) > 0
+    b.zero_()        # write-through buckets drop the gradients (the sinks are armed; all_reduce() zero-fills what receives none) ...
+    assert lin.weight.grad is None and lin.bias.grad is None
+    lin(torch.ones(1, 3)).sum().backward()
+    assert torch.equal(b.flat[:6].view(2, 3), lin.weight.grad) and torch.equal(lin.weight.grad, torch.ones(2, 3))
+    assert lin.weight.grad.data_ptr() == b.flat.data_ptr()
     b.zero_()
-    assert float(lin.weight.grad.abs().sum()) == 0.0
+    lin.weight.sum().backward()                      # the bias receives no gradient this step
+    assert torch.equal(b.all_reduce(), torch.tensor([1.0] * 6 + [0.0] * 2))
+    b.close()
+    b2 = FlatGradBucket(lin.parameters(), write_through=False)     # ... the classic protocol zero-fills in place
+    lin(torch.ones(1, 3)).sum().backward()
+    b2.zero_()
+    assert float(lin.weight.grad.abs().sum()) == 0.0 and lin.weight.grad.data_ptr() == b2.flat.data_ptr()
+    b2.close()
 
 
 def test_flat_bucket_survives_zero_grad_set_to_none():

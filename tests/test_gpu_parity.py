@@ -239,6 +239,58 @@ def test_programmatic_dependent_launch_does_not_change_a_single_bit(arch):
         lib.tx_pdl_set(prev)
 
 
+def test_gradients_written_through_to_a_flat_bucket_are_bit_identical():
+    """FlatGradBucket registers its slices as gradient sinks: the native backward calls write d(W), d(attn), d(position tables),
+    d(readout weights), d(match W) straight into them and autograd adopts the aliases (no add / copy kernel per parameter).  The
+    values must be those of the plain autograd path bit for bit, every .grad must live inside the flat buffer, and a second
+    backward without zero_() must still ACCUMULATE (the sinks are only used while .grad is None)."""
+    from taxoexpan_b200.dist import FlatGradBucket
+    dims = dict(in_dim=250, hidden_dim=500, out_dim=500, pos_dim=50, num_layers=1, heads=[4, 1], feat_drop=0.1, attn_drop=0.1,
+                hidden_drop=0.1, out_drop=0.1)
+    torch.manual_seed(5)
+    model = tx.TaxoExpan("PGAT", "WMR", "LBM", **dims).to(dev()).train()
+    nq = 48
+    sh = tx.synth.sample_shapes(nq, 31, "mag-cs", seed=9)
+    x = torch.from_numpy(tx.synth.unit_rows(sh.total_nodes, 250, seed=1)).to(dev())
+    qf = torch.from_numpy(tx.synth.unit_rows(sh.num_graphs, 250, seed=2)).to(dev())
+
+    def step():
+        torch.manual_seed(77)
+        g = tx.EgonetBatch.from_counts(sh.n_gp, sh.n_sib)
+        loss = tx.info_nce_loss(model(g, x, qf).reshape(nq, -1), None)
+        loss.backward()
+        return loss.detach().clone()
+
+    model.zero_grad(set_to_none=True)
+    step()
+    ref = [p.grad.detach().clone() for p in model.parameters()]
+    model.zero_grad(set_to_none=True)
+    bucket = FlatGradBucket(model.parameters())
+    try:
+        for _ in range(2):
+            bucket.zero_()
+            assert all(p.grad is None for p in model.parameters())
+            step()
+            flat = bucket.all_reduce()
+            lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * 4
+            for p, r in zip(model.parameters(), ref):
+                assert lo <= p.grad.data_ptr() < hi and p.grad.shape == r.shape
+                assert torch.equal(p.grad, r)
+        step()                                          # no zero_(): autograd accumulates on top of the bucket's views
+        for p, r in zip(model.parameters(), ref):
+            assert torch.equal(p.grad, r + r)
+        # the classic protocol (zero-filled views, autograd adds) gives the same numbers
+        bucket.close()
+        bucket = FlatGradBucket(model.parameters(), write_through=False)
+        bucket.zero_()
+        step()
+        bucket.all_reduce()
+        for p, r in zip(model.parameters(), ref):
+            assert torch.equal(p.grad, r)
+    finally:
+        bucket.close()
+
+
 def test_general_csr_build_is_bit_exact():
     rng = np.random.default_rng(0)
     n, e = 1000, 7000
