@@ -547,7 +547,12 @@ def run_b200(args, rank, world, local_rank):
             dist.broadcast(p.data, 0)
     model.train()
     from taxoexpan_b200.dist import FlatGradBucket
-    bucket = FlatGradBucket(model.parameters())     # gradients live in one flat fp32 bucket -> ONE all-reduce per step
+    # gradients live in one flat fp32 bucket -> ONE all-reduce per step, issued as soon as the last gradient is final.  Two segments with
+    # the first one travelling during layer 0's backward (TAXO_BUCKET_SEGMENTS=2) measured no better on 4 and 8 ranks (1.901 vs 1.872 ms,
+    # 1.929 vs 1.922 ms): NCCL's CTAs take SMs the persistent one-CTA-per-SM kernels count on - the layer-0 star backward then ends
+    # 0.04-0.07 ms later, which is what the overlap had saved.
+    bucket = FlatGradBucket(model.parameters(), segments=int(os.environ.get("TAXO_BUCKET_SEGMENTS", "1")),
+                            overlap=os.environ.get("TAXO_BUCKET_OVERLAP", "1") not in ("", "0"))
     flat = bucket.flat
 
     # rotating seeded batches (different shapes/features per rank and per slot), host copies pinned.  The same rows are available two
