@@ -548,11 +548,13 @@ def run_b200(args, rank, world, local_rank):
     model.train()
     from taxoexpan_b200.dist import FlatGradBucket
     # gradients live in one flat fp32 bucket -> ONE all-reduce per step, issued as soon as the last gradient is final.  Two segments with
-    # the first one travelling during layer 0's backward (TAXO_BUCKET_SEGMENTS=2) measured no better on 4 and 8 ranks (1.901 vs 1.872 ms,
-    # 1.929 vs 1.922 ms): NCCL's CTAs take SMs the persistent one-CTA-per-SM kernels count on - the layer-0 star backward then ends
-    # 0.04-0.07 ms later, which is what the overlap had saved.
+    # the first one travelling during layer 0's backward (TAXO_BUCKET_SEGMENTS=2) measured no better on 4 and 8 ranks when reduced on the
+    # spot (1.901 vs 1.872 ms, 1.929 vs 1.922 ms: NCCL's CTAs take SMs the persistent one-CTA-per-SM kernels count on - the layer-0
+    # star backward ends 0.04-0.07 ms later, which is what the overlap saved) and within the noise when gated behind that kernel
+    # (FlatGradBucket(gate=True): 1.870 vs 1.889 ms resident, 2.002 vs 1.984 ms end to end on 4 ranks); profiles/r2_nccl_overlap.log.
     bucket = FlatGradBucket(model.parameters(), segments=int(os.environ.get("TAXO_BUCKET_SEGMENTS", "1")),
-                            overlap=os.environ.get("TAXO_BUCKET_OVERLAP", "1") not in ("", "0"))
+                            overlap=os.environ.get("TAXO_BUCKET_OVERLAP", "1") not in ("", "0"),
+                            gate=os.environ.get("TAXO_BUCKET_GATE", "1") not in ("", "0"))
     flat = bucket.flat
 
     # rotating seeded batches (different shapes/features per rank and per slot), host copies pinned.  The same rows are available two

@@ -520,6 +520,12 @@ int tx_head_fwd(const tx_head_desc* d, const float* h, int64_t ldh, const float*
 int tx_head_bwd(const tx_head_desc* d, const tx_head_state* state, const float* h, int64_t ldh, const float* q, int64_t ldq,
                 const float* dscores, void* workspace, float* dh, float* dw, float* dw_main, float* dpos_weight, float** dh_amax_out,
                 void* stream);      /* dw: [dim, round4(r)] pitched; dw_main (optional): contiguous [dim, r] */
+/* Multi-GPU hook: tx_gat_layer_bwd records `cuda_event` (a cudaEvent_t, or NULL to stop) on its stream right after it has launched the
+ * star backward, and counts the records.  A gradient bucket lets the all-reduce of the segments that were complete before that point
+ * wait on this event from a side stream: the collective then runs beside the weight- / input-gradient GEMMs of the layer (which leave
+ * SMs idle) instead of beside the persistent one-CTA-per-SM star backward (which it delayed by 0.04-0.07 ms on 4 / 8 GPUs). */
+int tx_set_after_star_bwd_event(void* cuda_event);
+int64_t tx_after_star_bwd_event_count(void);
 /* measurement aid (bench.py): kernel launches issued by the two calls above since the last reset, and optional CUDA-event timing of
  * each of them (creates events; read after synchronising the stream) */
 int64_t tx_layer_launches(int32_t reset);

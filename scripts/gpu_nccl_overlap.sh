@@ -7,5 +7,5 @@ d=json.loads(sys.stdin.read().strip().splitlines()[-1]); k=d['kernel_ms_per_step
 print('$*', 'ms', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'], 'prop_ro', d['propagate_readout']['ms_per_step'], 'star_bwd_L0', k.get('tx_gat_star_bwd[L0]'), 'dz_L0', k.get('gemm_dz[L0]'), 'dw_L0', k.get('gemm_dw[L0]'))"
 }
 for r in 1; do
-for v in ${VARIANTS:-A=0 NCCL_MAX_CTAS=4 TAXO_BUCKET_OVERLAP=0 TAXO_BUCKET_SEGMENTS=1}; do run $v; done
+IFS=";" read -ra VS <<< "${VARIANTS:-TAXO_BUCKET_SEGMENTS=1;TAXO_BUCKET_SEGMENTS=2;TAXO_BUCKET_SEGMENTS=2 TAXO_BUCKET_GATE=0;TAXO_BUCKET_SEGMENTS=3}"; for v in "${VS[@]}"; do run $v; done
 done 2>&1 | tee gpurun_out/n2_nccl.log

@@ -173,6 +173,8 @@ _SIGNATURES = {
     "tx_head_bwd_bytes": [POINTER(HeadDesc)],
     "tx_head_fwd": [POINTER(HeadDesc), P, I64, P, I64, P, POINTER(HeadState), P, P],
     "tx_head_bwd": [POINTER(HeadDesc), POINTER(HeadState), P, I64, P, I64, P, P, P, P, P, P, POINTER(c_void_p), P],
+    "tx_set_after_star_bwd_event": [P],
+    "tx_after_star_bwd_event_count": [],
     "tx_layer_launches": [c_int32],
     "tx_prof_enable": [c_int32],
     "tx_prof_clear": [],
@@ -183,7 +185,7 @@ _SIGNATURES = {
     "tx_info_nce_fwd": [P, I64, I64, P, P, P, P, P],
     "tx_info_nce_bwd": [P, P, I64, I64, P, P, P, P],
 }
-_RESTYPES = {"tx_last_error": c_char_p, "tx_target_arch": c_char_p, "tx_row_blocks": c_int64, "tx_readout_bwd_blocks": c_int64,
+_RESTYPES = {"tx_after_star_bwd_event_count": c_int64, "tx_last_error": c_char_p, "tx_target_arch": c_char_p, "tx_row_blocks": c_int64, "tx_readout_bwd_blocks": c_int64,
              "tx_gat_fused_mask_words": c_int64, "tx_gat_fused_mask_ld": c_int64, "tx_gat_fused_bwd_blocks": c_int64, "tx_gemm_tn_splits": c_int64,
              "tx_gat_bwd_tile_rows": c_int64, "tx_gat_bwd_num_tiles": c_int64, "tx_gat_fused_bwd_staged_blocks": c_int64,
              "tx_gemm_tn_f16_splits": c_int64, "tx_gat_star_chunk": c_int64, "tx_gat_star_max_chunks": c_int64,
@@ -202,7 +204,7 @@ _NO_LAUNCH = {"tx_abi_version", "tx_last_error", "tx_target_arch", "tx_pdl_set",
               # the per-layer calls enqueue several kernels each: they are counted through tx_layer_launches, timed through tx_prof_*
               "tx_gat_layer_fwd_bytes", "tx_gat_layer_bwd_bytes", "tx_gat_layer_fwd", "tx_gat_layer_bwd", "tx_layer_launches",
               "tx_gcn_layer_fwd_bytes", "tx_gcn_layer_bwd_bytes", "tx_gcn_layer_fwd", "tx_gcn_layer_bwd",
-              "tx_head_fwd_bytes", "tx_head_bwd_bytes", "tx_head_fwd", "tx_head_bwd",
+              "tx_head_fwd_bytes", "tx_head_bwd_bytes", "tx_head_fwd", "tx_head_bwd", "tx_set_after_star_bwd_event", "tx_after_star_bwd_event_count",
               "tx_prof_enable", "tx_prof_clear", "tx_prof_count", "tx_prof_get"}
 
 

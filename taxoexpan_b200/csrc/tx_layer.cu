@@ -122,6 +122,10 @@ static BwdLayout carve_bwd(const tx_gat_layer_desc& d, void* ws) {
   return L;
 }
 
+// process-wide (backward runs on autograd's thread, not the caller's)
+static cudaEvent_t g_after_star_event = nullptr;
+static int64_t g_after_star_count = 0;
+
 static int check_desc(const tx_gat_layer_desc* d, const char* who) {
   TX_REQUIRE(d, "%s: null descriptor", who);
   TX_REQUIRE(d->n > 0 && d->e > 0 && d->k > 0 && d->heads >= 1 && d->dim > 0 && d->dim % 4 == 0 && d->pos_dim >= 0, "%s: bad sizes", who);
@@ -244,6 +248,10 @@ int tx_gat_layer_bwd(const tx_gat_layer_desc* d, const tx_gat_layer_state* state
                            d->n_tasks_bwd, d->chunk_bwd, n, H, D, d->neg_slope, L.ds, nullptr, nullptr, nullptr, F, L.d_hi, L.d_lo, ld16,
                            L.bounds, reinterpret_cast<int32_t*>(L.bounds + 3), d->reruns, L.d_scale, L.star_partial, d->counters, d->queue,
                            stream)); }
+  if (g_after_star_event) {     // see tx_set_after_star_bwd_event: a collective may start here, beside the GEMMs that leave SMs idle
+    cudaEventRecord(g_after_star_event, st);
+    ++g_after_star_count;
+  }
   // dW_fk = d(ft)^T z with the 2 H attention-coefficient columns riding along, then d(attn) = W_h v_h / c
   const int64_t ldc = r4(K);
   { ProfScope ps("gemm_dw", d->tag, st);
@@ -596,6 +604,12 @@ int tx_head_bwd(const tx_head_desc* d, const tx_head_state* state, const float* 
   if (dh_amax_out) *dh_amax_out = L.dhg_amax;
   return TX_OK;
 }
+
+int tx_set_after_star_bwd_event(void* cuda_event) {
+  g_after_star_event = reinterpret_cast<cudaEvent_t>(cuda_event);
+  return TX_OK;
+}
+int64_t tx_after_star_bwd_event_count(void) { return g_after_star_count; }
 
 // ---- launch accounting and per-launch timing of the calls above ----
 int64_t tx_layer_launches(int32_t reset) {

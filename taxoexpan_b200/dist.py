@@ -58,10 +58,18 @@ class FlatGradBucket:
       alias as `.grad` - no add / copy kernel per parameter - PROVIDED `.grad` is None when backward runs, so `zero_()` then drops
       the gradients instead of zero-filling the buffer (a parameter that receives no gradient is zero-filled by `all_reduce()`).
       Gradients produced elsewhere (torch ops, the per-kernel paths) are copied in by the hooks as before.
+    * with `gate=True` (default; CUDA, more than one segment) a segment that completes inside backward is not reduced on the spot
+      - NCCL's CTAs would take SMs the persistent one-CTA-per-SM kernels of the next layer's backward count on (its star backward
+      ended 0.04-0.07 ms later on 4 / 8 GPUs, as much as the overlap saved) - but from a side stream that waits for the event
+      `tx_gat_layer_bwd` records right after it has launched its star backward (tx_set_after_star_bwd_event): the collective then runs
+      beside the weight- and input-gradient GEMMs that follow, which leave SMs idle.  Only segments that were complete BEFORE the
+      last such record use the gate (the library counts the records); everything else is reduced from the current stream.
     """
 
+    _gate_owner = None          # the bucket whose event the library records after a layer's star backward (one per process)
+
     def __init__(self, params: Iterable[torch.nn.Parameter], segments: int = 2, overlap: bool = True, group=None,
-                 write_through: bool = True):
+                 write_through: bool = True, gate: bool = True):
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
@@ -69,6 +77,21 @@ class FlatGradBucket:
         self.overlap = overlap
         self.segments = segments
         self.write_through = bool(write_through)
+        self._gate_event = self._side = self._txlib = None
+        if gate and segments > 1 and self.params[0].is_cuda:
+            try:
+                from . import _lib
+                self._txlib = _lib.load()
+                with torch.cuda.device(self.params[0].device):
+                    self._gate_event = torch.cuda.Event()
+                    self._gate_event.record()                       # creates the underlying cudaEvent_t
+                    self._side = torch.cuda.Stream()
+                self._txlib.tx_set_after_star_bwd_event(self._gate_event.cuda_event)
+                FlatGradBucket._gate_owner = self                   # the library records ONE event: the newest bucket owns it
+            except Exception:                                       # no library: reduce on the spot
+                self._gate_event = self._side = self._txlib = None
+        self._deferred = []                                         # (segment, record count when it became ready)
+        self.gated_launches = 0                                     # collectives started from the side stream so far (tests)
         self.active = True                        # False: hooks only keep the views bound (no exchange is launched)
         self._rebuilt = False
         self._fire_order = []
@@ -147,7 +170,11 @@ class FlatGradBucket:
                 if not self._rebuilt:
                     self._fire_order.append(i)
             if self.overlap and self._ready[s] == self._seg_size[s]:
-                self._launch(s)
+                if self._gate_event is not None and FlatGradBucket._gate_owner is self and self._dist_active():
+                    self._launched[s] = True                         # claimed: a late gradient for it is an error, as before
+                    self._deferred.append((s, int(self._txlib.tx_after_star_bwd_event_count())))
+                else:
+                    self._launch(s)
         return hook
 
     def _launch(self, s: int):
@@ -157,7 +184,28 @@ class FlatGradBucket:
             a, b = self._seg_range[s]
             self._works.append(dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
+    def _launch_deferred(self):
+        """Reduce the segments that completed inside backward: gated on the after-star-backward event when one was recorded after they
+        were complete (the collective may then start at that point of the compute stream), else ordered after the current stream."""
+        if not self._deferred:
+            return
+        import torch.distributed as dist
+        now = int(self._txlib.tx_after_star_bwd_event_count())
+        cur = torch.cuda.current_stream(self.flat.device)
+        for s, count in self._deferred:
+            a, b = self._seg_range[s]
+            if now > count and FlatGradBucket._gate_owner is self:
+                with torch.cuda.stream(self._side):
+                    self._side.wait_event(self._gate_event)
+                    self.gated_launches += 1
+                    self._works.append(dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            else:
+                self._works.append(dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        self._deferred = []
+        del cur
+
     def _reset_step(self):
+        self._deferred = []
         self._ready = [0] * len(self._seg_range)
         self._launched = [False] * len(self._seg_range)
         self._seen = [False] * len(self.params)
@@ -187,6 +235,7 @@ class FlatGradBucket:
                 if self._launched[self._seg_of[i]]:
                     raise RuntimeError("FlatGradBucket: a gradient was replaced after its segment's all-reduce was launched")
                 self._rebind(i)
+        self._launch_deferred()
         for s in range(len(self._seg_range) - 1, -1, -1):
             if not self._launched[s]:
                 self._launch(s)
@@ -204,6 +253,11 @@ class FlatGradBucket:
         for h in self._hooks:
             h.remove()
         self._hooks = []
+        if self._gate_event is not None:
+            if FlatGradBucket._gate_owner is self:
+                self._txlib.tx_set_after_star_bwd_event(None)
+                FlatGradBucket._gate_owner = None
+            self._gate_event = None
         if self.write_through:
             from . import functional as txf
             for p in self.params:

@@ -81,7 +81,7 @@ def main():
         torch.cuda.synchronize()
         if rank == 0:
             ref_model = build(dev)
-            ref_bucket = FlatGradBucket(ref_model.parameters(), overlap=False, group=None)
+            ref_bucket = FlatGradBucket(ref_model.parameters(), overlap=False, group=None, gate=False)
             ref_bucket._dist_active = lambda: False                       # single-GPU run: no exchange
             ref_loss = step(ref_model, ref_bucket, shapes, x, qf, 0, N_Q, dev)
             ref = grads_of(ref_model)
@@ -90,7 +90,8 @@ def main():
             res[f"overlap={overlap}"] = {
                 "max_abs_diff": float((flat - ref).abs().max()), "max_abs_diff_set_to_none": float((flat_none - ref).abs().max()),
                 "scale": scale, "grad_max": float(ref.abs().max()), "loss_sharded": float(loss_sum), "loss_single": float(ref_loss),
-                "numel": int(ref.numel()), "world": world, "segments": [list(r) for r in bucket._seg_range]}
+                "numel": int(ref.numel()), "world": world, "segments": [list(r) for r in bucket._seg_range],
+                "gated_launches": int(bucket.gated_launches)}
         bucket.close()
     if rank == 0:
         with open(out_path, "w") as f:

@@ -39,3 +39,6 @@ def test_two_rank_nccl_gradients_equal_the_single_gpu_gradient(tmp_path):
         assert v["max_abs_diff"] <= 2e-6 * v["scale"], (k, v)
         assert v["max_abs_diff_set_to_none"] <= 2e-6 * v["scale"], (k, v)
         assert abs(v["loss_sharded"] - v["loss_single"]) <= 1e-5 * max(1.0, abs(v["loss_single"])), (k, v)
+    # with overlap, the segment that completes inside backward is reduced from the side stream, gated on the event the layer-0
+    # backward records after its star kernel (both steps of the run), and the reduced gradients are still those of the single GPU
+    assert res["overlap=True"]["gated_launches"] >= 1 and res["overlap=False"]["gated_launches"] == 0
