@@ -35,6 +35,8 @@ from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -231,6 +233,10 @@ def _activate(h, activation, branch, l, tol=2e-6):
         return activation(h)
     assert activation is F.leaky_relu, "branch replay is implemented for leaky_relu(0.01)"
     pos = branch[key]
+    if os.environ.get("TAXO_DEBUG_PINS") == "2":      # cross-process repeatability probe of the oracle itself
+        hv = h.detach().contiguous()
+        bits = hv.view(torch.int32 if hv.dtype == torch.float32 else torch.int64)
+        print(f"DEBUG_PINS oracle pre-activation l={l} dtype={hv.dtype} checksum={int(bits.to(torch.int64).sum())} threads={torch.get_num_threads()}")
     disagree = (h.detach() > 0) != pos
     keep = branch.get(f"keep.{l}")
     if keep is not None:

@@ -987,13 +987,21 @@ __device__ __forceinline__ void ro_load(const float* __restrict__ p, int lane, i
 }
 
 constexpr int kBigGraph = 12;   // graphs with more rows are shared by the 8 warps of a CTA (one warp per graph otherwise)
+// rows a warp keeps in flight, and the CTAs per SM the register budget is held to.  4 rows (r[4][NV] = 64 registers, 2 CTAs per SM)
+// vs 2 rows (4 / 3 CTAs per SM), same-box A/B: forward 0.0368 vs 0.0362 ms, backward 0.058 vs 0.067 ms - occupancy is not what bounds
+// these kernels, rows in flight per warp help the backward
+#ifndef TX_RO_ROWS
+#define TX_RO_ROWS 4
+#endif
+constexpr int kRoRows = TX_RO_ROWS;
+constexpr int kRoFwdCtas = TX_RO_ROWS == 2 ? 4 : 2, kRoBwdCtas = TX_RO_ROWS == 2 ? 3 : 2;
 
 // A CTA owns groups of 8 consecutive graphs.  Egonet sizes are skewed (1..57 rows, one large positive egonet per query): with
 // one warp per graph the CTA waited ~14 us for the warp that drew the 53-row graph while the others were done after 1-2 us
 // (43 us for a 74 MB read).  Small graphs still get one warp each; the large ones of the group are then taken by all 8 warps
 // together (rows dealt round-robin, fixed-order reduction over the warps: deterministic).
 template <int NV>
-__global__ void __launch_bounds__(256) readout_fwd_fast_kernel(int kind, const float* __restrict__ h, int64_t ldh,
+__global__ void __launch_bounds__(256, kRoFwdCtas) readout_fwd_fast_kernel(int kind, const float* __restrict__ h, int64_t ldh,
                                                                const int32_t* __restrict__ pos, const float* __restrict__ pw,
                                                                const int32_t* __restrict__ node_off, int n_graphs, int D,
                                                                float* __restrict__ hg, int64_t ldhg) {
@@ -1009,19 +1017,21 @@ __global__ void __launch_bounds__(256) readout_fwd_fast_kernel(int kind, const f
   }
   // rows [beg, end) with stride `step` starting at beg + first: weighted sum into acc / S
   auto accumulate = [&](int beg, int end, int first, int step, float4 (&acc)[NV], float& S) {
-    for (int i = beg + first; i < end; i += 4 * step) {
-      float4 r[4][NV];
-      float a[4];
+    for (int i = beg + first; i < end; i += kRoRows * step) {
+      float4 r[kRoRows][NV];
+      float a[kRoRows];
+      int pr[kRoRows];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const bool ok = i + u * step < end;
+      for (int u = 0; u < kRoRows; ++u) {               // every load of the batch is issued before anything is consumed (the weight of a
+        const bool ok = i + u * step < end;             // row used to be selected right after its position load: the row loads waited for it)
         const int row = ok ? i + u * step : beg;
-        const int pr = kind == TX_READOUT_WMEAN ? __ldg(pos + row) : 0;
-        a[u] = ok ? (pr == 0 ? sw[0] : (pr == 1 ? sw[1] : sw[2])) : 0.f;
+        pr[u] = kind == TX_READOUT_WMEAN ? __ldg(pos + row) : 0;
         ro_load<NV>(h + (int64_t)row * ldh, lane, D, r[u]);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kRoRows; ++u) a[u] = i + u * step < end ? (pr[u] == 0 ? sw[0] : (pr[u] == 1 ? sw[1] : sw[2])) : 0.f;
+#pragma unroll
+      for (int u = 0; u < kRoRows; ++u) {
         S += a[u];
 #pragma unroll
         for (int t = 0; t < NV; ++t) {
@@ -1089,7 +1099,7 @@ __global__ void __launch_bounds__(256) readout_fwd_fast_kernel(int kind, const f
 }
 
 template <int NV>
-__global__ void __launch_bounds__(256) readout_bwd_fast_kernel(int kind, const float* __restrict__ dhg, int64_t lddhg,
+__global__ void __launch_bounds__(256, kRoBwdCtas) readout_bwd_fast_kernel(int kind, const float* __restrict__ dhg, int64_t lddhg,
                                                                const float* __restrict__ h, int64_t ldh,
                                                                const float* __restrict__ hg, int64_t ldhg,
                                                                const int32_t* __restrict__ pos, const float* __restrict__ pw,
@@ -1115,24 +1125,28 @@ __global__ void __launch_bounds__(256) readout_bwd_fast_kernel(int kind, const f
     float4 d[NV], m[NV];
     ro_load<NV>(dhg + (int64_t)g * lddhg, lane, D, d);
     if (wm) ro_load<NV>(hg + (int64_t)g * ldhg, lane, D, m);
-    float S = 0.f;
-    for (int i = beg + lane; i < end; i += 32) {
-      const int pr = wm ? __ldg(pos + i) : 0;
-      S += pr == 0 ? sw[0] : (pr == 1 ? sw[1] : sw[2]);
-    }
-    S = warp_sum(S);
-    const float inv_s = 1.f / S;
-    for (int i = beg + first; i < end; i += 4 * step) {
-      float4 r[4][NV];
-      int pr[4];
+    float4 r[kRoRows][NV];
+    int pr[kRoRows];
+    auto load_batch = [&](int i) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kRoRows; ++u) {
         const int row = i + u * step < end ? i + u * step : beg;
         pr[u] = wm ? __ldg(pos + row) : 0;
         if (wm) ro_load<NV>(h + (int64_t)row * ldh, lane, D, r[u]);
       }
+    };
+    if (beg + first < end) load_batch(beg + first);     // the first rows are on their way while the graph's weight sum is formed
+    float S = 0.f;
+    for (int i = beg + lane; i < end; i += 32) {
+      const int p_ = wm ? __ldg(pos + i) : 0;
+      S += p_ == 0 ? sw[0] : (p_ == 1 ? sw[1] : sw[2]);
+    }
+    S = warp_sum(S);
+    const float inv_s = 1.f / S;
+    for (int i = beg + first; i < end; i += kRoRows * step) {
+      if (i != beg + first) load_batch(i);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kRoRows; ++u) {
         if (i + u * step < end) {                       // warp-uniform
           const float a = pr[u] == 0 ? sw[0] : (pr[u] == 1 ? sw[1] : sw[2]);
           const float sc = a * inv_s;

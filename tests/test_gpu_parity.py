@@ -1,6 +1,8 @@
 """GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden vectors frozen from
 the unmodified reference.  Tolerance: 1e-5 max-abs on O(1) fp32 outputs (BASELINE.json north_star); gradients
 2e-5 relative to the largest entry of each gradient tensor; integer/index work bit-exact."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -377,15 +379,36 @@ def test_cuda_path_matches_reference_golden_at_full_baseline_size(name, graph_ki
 
 @pytest.mark.parametrize("backend", ["f16x3", "cublas"])
 def test_full_size_gradients_match_oracle_with_pinned_branches(backend, monkeypatch):
-    """BASELINE configs[1] at full size (8192 egonets, N = 37 319), EVERY gradient entry (not a sub-sample) against the fp32 oracle
-    made to take the same leaky-relu branches as the CUDA run (the only discontinuity of the path): 2e-5 of each tensor's maximum."""
+    """BASELINE configs[1] at full size (8192 egonets, N = 37 319), EVERY gradient entry (not a sub-sample) against the oracle made to
+    take the same leaky-relu branches as the CUDA run (the only discontinuity of the path): 2e-5 of each tensor's maximum.  The oracle
+    runs in fp64 here: its branch check (a pinned branch may differ from the oracle's own only within 2e-6 of the kink) then measures
+    the CUDA run's error alone.  With the fp32 oracle the check failed in about 1 of 50 fresh processes at |pre-activation| 1.0-1.4e-5
+    while the CUDA hidden output was bit-identical in 41 fresh processes, 300 consecutive steps and on a repeat inside a failing
+    process (scripts/dbg_determinism.py; TAXO_DEBUG_PINS): two fp32 evaluations of a 300-term dot product of O(1) values can
+    legitimately disagree about the sign of a result that small."""
     monkeypatch.setattr(txf, "GEMM_BACKEND", backend)
     cfg, og, x, qf, params, fx = load_case("pgat_wmr_lbm_magcs_full")
     n_q = int(fx["n_queries"][0])
     captured = capture_hidden_outputs(monkeypatch)
     model = build_model(cfg, params).train()
     got = run_cuda(model, tx.EgonetBatch.from_counts(fx["n_gp"], fx["n_sib"]), x, qf, n_q)
-    ref = run_oracle(cfg, og, x, qf, params, n_q, masks=branch_pins(cfg, captured))
+    if os.environ.get("TAXO_DEBUG_PINS") == "2":
+        c0 = captured[0].contiguous()
+        print(f"DEBUG_PINS cuda hidden output checksum={int(c0.view(torch.int32).to(torch.int64).sum())}")
+    try:
+        ref = run_oracle(cfg, og, x, qf, params, n_q, masks=branch_pins(cfg, captured), dtype=torch.float64)
+    except AssertionError:
+        if os.environ.get("TAXO_DEBUG_PINS"):          # diagnostics for a rare branch disagreement: is the CUDA run repeatable?
+            first = captured[0].clone()
+            del captured[:]
+            run_cuda(model, tx.EgonetBatch.from_counts(fx["n_gp"], fx["n_sib"]), x, qf, n_q)
+            again = captured[0]
+            diff = (first != again)
+            print(f"DEBUG_PINS: hidden output of the failing run vs a repeat in the same process: {int(diff.sum())} entries differ, "
+                  f"max |diff| {float((first - again).abs().max()):.3e}; sign flips {int(((first > 0) != (again > 0)).sum())}")
+            idx = diff.nonzero()[:8].tolist()
+            print("DEBUG_PINS first differing entries", [(i, j, float(first[i, j]), float(again[i, j])) for i, j in idx])
+        raise
     assert_close(got, ref, TOL, GTOL, what=f"full size, {backend}: ")
 
 
