@@ -13,7 +13,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "taxoexpan_b200", "libtaxo_sm100.so")
 OUT = os.path.join(ROOT, "profiles", "r2_sass_opcodes.csv")
-WATCH = ["UTCHMMA", "UTCQMMA", "UTMALDG", "UTMASTG", "UTMAPF", "LDTM", "STTM", "UTCBAR", "UBLKCP", "UBLKPF", "SYNCS", "LDGSTS", "HMMA", "FFMA", "LDG", "STG",
+WATCH = ["UTCHMMA", "UTCQMMA", "UTMALDG", "UTMASTG", "UTMAPF", "LDTM", "STTM", "UTCBAR", "UBLKCP", "UBLKPF", "SYNCS", "ACQBULK", "PREEXIT", "LDGSTS", "HMMA", "FFMA", "LDG", "STG",
          "LDS", "STS", "SHFL", "ATOMG", "ATOMS", "RED", "MEMBAR", "BAR", "F2FP", "HADD2", "FMNMX", "IMAD"]
 
 txt = subprocess.run(["cuobjdump", "-sass", LIB], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
@@ -46,5 +46,5 @@ with open(OUT, "w", newline="") as f:
         w.writerow([k[:140], total[k]] + [counts[k][x] for x in WATCH])
     w.writerow(["TOTAL", sum(total.values())] + [sum(counts[k][x] for k in total) for x in WATCH])
 tot = {x: sum(counts[k][x] for k in total) for x in WATCH}
-print("kernels:", len(total), "| tcgen05/TMA/TMEM opcodes:", {x: tot[x] for x in ("UTCHMMA", "UTMALDG", "LDTM", "UTCBAR", "UBLKCP", "SYNCS") if tot[x]})
+print("kernels:", len(total), "| tcgen05/TMA/TMEM opcodes:", {x: tot[x] for x in ("UTCHMMA", "UTMALDG", "LDTM", "UTCBAR", "UBLKCP", "SYNCS", "ACQBULK", "PREEXIT") if tot[x]})
 print("written", OUT)
