@@ -12,7 +12,11 @@ MEM = re.compile(r"^(@!?U?P\d+\s+)?(LDG|LD\.E(?!\.STRONG\.SYS)|STG|ST\.E|ATOMG|A
 
 
 def check(lib):
-    out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
+    return check_text(subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout)
+
+
+def check_text(out):
+    """{kernel: [global-memory instructions in front of its ACQBULK]} for every kernel of a `cuobjdump -sass` listing that has one"""
     fn, seen_mem, results, waited = None, [], {}, False
     for line in out.splitlines():
         m = re.search(r"Function : (\S+)", line)

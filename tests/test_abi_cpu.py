@@ -56,6 +56,41 @@ def test_no_kernel_touches_global_memory_before_it_waits_for_its_predecessor():
         assert must in names, must
 
 
+def test_the_sass_checker_flags_a_load_hoisted_over_the_wait():
+    """The checker itself: the hoisted non-coherent load that broke the GCN forward is reported, the GEMM prologue's shared-memory
+    traffic and loads behind the wait are not."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import check_pdl_sass
+    listing = '''
+	Function : bad_kernel
+        /*0000*/                   LDC R1, c[0x0][0x37c] ;
+        /*0060*/                   LDG.E.CONSTANT R2, desc[UR8][R2.64] ;
+        /*0080*/                   PREEXIT ;
+        /*0090*/                   ACQBULK ;
+        /*00a0*/                   LDG.E R4, desc[UR8][R4.64] ;
+	Function : good_kernel
+        /*0000*/                   LDC R1, c[0x0][0x37c] ;
+        /*0010*/                   SYNCS.ARRIVE.TRANS64.RED RZ, [R7+URZ], R8 ;
+        /*0020*/                   CCTL.IVALL ;
+        /*0030*/                   LD.E.STRONG.SYS R3, desc[UR20][R2.64+0x30040] ;
+        /*0080*/                   PREEXIT ;
+        /*0090*/                   ACQBULK ;
+        /*00a0*/              @!P0 EXIT ;
+        /*00b0*/                   LDG.E.CONSTANT R2, desc[UR8][R2.64] ;
+        /*00c0*/              @P1  STG.E desc[UR8][R4.64], R2 ;
+	Function : predicated_store_before
+        /*0010*/              @P0  STG.E desc[UR8][R4.64], R2 ;
+        /*0090*/                   ACQBULK ;
+	Function : no_wait_kernel
+        /*0010*/                   LDG.E R4, desc[UR8][R4.64] ;
+'''
+    res = check_pdl_sass.check_text(listing)
+    assert set(res) == {"bad_kernel", "good_kernel", "predicated_store_before"}
+    assert res["bad_kernel"] == ["LDG.E.CONSTANT R2, desc[UR8][R2.64]"] and res["good_kernel"] == []
+    assert len(res["predicated_store_before"]) == 1
+
+
 def test_argument_validation_without_gpu():
     l = _lib.load()
     # invalid dropout rate is rejected before any CUDA call
