@@ -12,6 +12,7 @@ readout and output-layer gradients (60 % of the bytes) travels while the first l
 """
 from __future__ import annotations
 
+import weakref
 from typing import Iterable, List, Optional, Tuple
 
 import numpy as np
@@ -87,7 +88,7 @@ class FlatGradBucket:
                     self._gate_event.record()                       # creates the underlying cudaEvent_t
                     self._side = torch.cuda.Stream()
                 self._txlib.tx_set_after_star_bwd_event(self._gate_event.cuda_event)
-                FlatGradBucket._gate_owner = self                   # the library records ONE event: the newest bucket owns it
+                FlatGradBucket._gate_owner = weakref.ref(self)      # the library records ONE event: the newest bucket owns it
             except Exception:                                       # no library: reduce on the spot
                 self._gate_event = self._side = self._txlib = None
         self._deferred = []                                         # (segment, record count when it became ready)
@@ -139,6 +140,10 @@ class FlatGradBucket:
             self._seg_size.append(b - a)
 
     # ---- internals ----
+    def _owns_gate(self) -> bool:
+        ref = FlatGradBucket._gate_owner
+        return ref is not None and ref() is self
+
     def _dist_active(self) -> bool:
         import torch.distributed as dist
         return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
@@ -170,7 +175,7 @@ class FlatGradBucket:
                 if not self._rebuilt:
                     self._fire_order.append(i)
             if self.overlap and self._ready[s] == self._seg_size[s]:
-                if self._gate_event is not None and FlatGradBucket._gate_owner is self and self._dist_active():
+                if self._gate_event is not None and self._owns_gate() and self._dist_active():
                     self._launched[s] = True                         # claimed: a late gradient for it is an error, as before
                     self._deferred.append((s, int(self._txlib.tx_after_star_bwd_event_count())))
                 else:
@@ -194,7 +199,7 @@ class FlatGradBucket:
         cur = torch.cuda.current_stream(self.flat.device)
         for s, count in self._deferred:
             a, b = self._seg_range[s]
-            if now > count and FlatGradBucket._gate_owner is self:
+            if now > count and self._owns_gate():
                 with torch.cuda.stream(self._side):
                     self._side.wait_event(self._gate_event)
                     self.gated_launches += 1
@@ -249,12 +254,21 @@ class FlatGradBucket:
         self._reset_step()
         return self.flat
 
+    def __del__(self):
+        # the library records into this bucket's event by raw handle: never let it outlive the torch.cuda.Event that owns the handle
+        try:
+            if getattr(self, "_gate_event", None) is not None and self._owns_gate():
+                self._txlib.tx_set_after_star_bwd_event(None)
+                FlatGradBucket._gate_owner = None
+        except Exception:
+            pass
+
     def close(self):
         for h in self._hooks:
             h.remove()
         self._hooks = []
         if self._gate_event is not None:
-            if FlatGradBucket._gate_owner is self:
+            if self._owns_gate():
                 self._txlib.tx_set_after_star_bwd_event(None)
                 FlatGradBucket._gate_owner = None
             self._gate_event = None
