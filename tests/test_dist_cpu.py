@@ -179,3 +179,38 @@ def test_flat_bucket_segments_cover_the_buffer():
     assert b._seg_range[0][0] == 0 and b._seg_range[-1][1] == b.flat.numel()
     assert all(x[1] == y[0] for x, y in zip(b._seg_range, b._seg_range[1:])) and sum(b._seg_size) == len(ps)
     assert len(b._seg_range) == 2
+
+
+def test_gradient_sink_registry_rules():
+    """functional.grad_sink (what the native backward calls consult before they write a parameter gradient): a fresh 1-D alias of the
+    registered slice, found through ANY tensor that starts at the parameter's data pointer (e.g. nn.Bilinear's weight viewed as
+    [l, r]); none when the parameter already holds a gradient (autograd has to accumulate), when the size does not match, after
+    unregistering, or once the parameter is gone."""
+    import gc
+    from taxoexpan_b200 import functional as txf
+    lin = torch.nn.Bilinear(3, 2, 1, bias=False)              # weight [1, 3, 2]
+    w = lin.weight
+    flat = torch.zeros(10)
+    txf.register_grad_sink(w, flat[2:8].view_as(w))
+    try:
+        a = txf.grad_sink(w.view(3, 2), 6)
+        assert a is not None and a.shape == (6,) and a.data_ptr() == flat[2:].data_ptr()
+        b = txf.grad_sink(w, 6)
+        assert b is not a and b.data_ptr() == a.data_ptr()    # a fresh alias every time: autograd only adopts unshared tensors
+        assert txf.grad_sink(w, 5) is None                     # wrong size (a row view like weight[0][0] shares the data pointer)
+        assert txf.grad_sink(torch.zeros(6), 6) is None        # unrelated tensor
+        assert txf.grad_sink(None, 6) is None
+        w.grad = torch.ones_like(w)
+        assert txf.grad_sink(w, 6) is None                     # an existing gradient must be accumulated into, not overwritten
+        w.grad = None
+        txf.unregister_grad_sink(w)
+        assert txf.grad_sink(w, 6) is None
+        txf.register_grad_sink(w, flat[2:8].view_as(w))
+        ptr_key = w.data_ptr()
+        probe = torch.zeros(1)
+        del lin, w, a, b
+        gc.collect()
+        assert ptr_key not in txf._grad_sinks or txf._grad_sinks[ptr_key][0]() is None
+    finally:
+        txf._grad_sinks.clear()
+
